@@ -1,0 +1,498 @@
+// C ABI of libaudiomps.so (see include/audiomps.h).  Host-side launch logic only; the kernels
+// are in amps_psi.cuh / amps_rho.cuh / amps_prep.cuh.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <type_traits>
+
+#include "../../include/audiomps.h"
+#include "amps_prep.cuh"
+#include "amps_psi.cuh"
+#include "amps_rho.cuh"
+
+using namespace amps;
+
+struct amps_ctx {
+  int device = 0;
+  char err[512] = {0};
+  int64_t launches = 0;
+  // cached float32 time table
+  float* ttab = nullptr;
+  int ttab_n = 0;
+  uint32_t ttab_dtbits = 0;
+  // context-owned scratch for entry points without a caller workspace
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  // host-entry buffers
+  void* hbuf = nullptr;
+  size_t hbuf_bytes = 0;
+  cudaStream_t hstream = nullptr;
+};
+
+namespace {
+
+int fail(amps_ctx* ctx, int code, const char* fmt, ...) {
+  if (ctx) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                              \
+  do {                                                                                   \
+    cudaError_t e_ = (expr);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(ctx, AMPS_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                   \
+  } while (0)
+
+#define LAUNCH_CHECK(ctx, name)                                                          \
+  do {                                                                                   \
+    cudaError_t e_ = cudaGetLastError();                                                 \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(ctx, AMPS_E_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); \
+    ctx->launches++;                                                                     \
+  } while (0)
+
+inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+int padded_dim(int D) {
+  if (D <= 0) return -1;
+  if (D <= 8) return 8;
+  if (D <= 16) return 16;
+  if (D <= 32) return 32;
+  if (D <= 64) return 64;
+  return -1;
+}
+
+template <int V>
+using IC = std::integral_constant<int, V>;
+
+// f(IC<DP>, IC<NQ>)
+template <class F>
+int dispatch_dp(int DP, F&& f) {
+  switch (DP) {
+    case 8: return f(IC<8>{}, IC<4>{});
+    case 16: return f(IC<16>{}, IC<4>{});
+    case 32: return f(IC<32>{}, IC<4>{});
+    case 64: return f(IC<64>{}, IC<8>{});
+    default: return AMPS_E_UNSUPPORTED;
+  }
+}
+
+struct PsiWs {
+  size_t matN, matR, matRH, matS, psi0p, qtab, lossd;
+  size_t traj, scales, G, gf, lam0, gAdir, Gtot, gftot, lam0tot;
+  size_t total;
+};
+
+PsiWs psi_ws_layout(int DP, int B, int nsteps_tab, int T, bool save) {
+  PsiWs w{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += align_up(bytes);
+    return o;
+  };
+  const size_t mat = (size_t)DP * DP * sizeof(float2);
+  w.matN = take(mat);
+  w.matR = take(mat);
+  w.matRH = take(mat);
+  w.matS = take(mat);
+  w.psi0p = take((size_t)DP * sizeof(float2));
+  w.qtab = take((size_t)(nsteps_tab > 0 ? nsteps_tab : 1) * DP * sizeof(float2));
+  w.lossd = take((size_t)(B > 0 ? B : 1) * sizeof(double));
+  if (save) {
+    const int nsteps = T - 1;
+    const int nchunks = nsteps > 0 ? (nsteps + CH - 1) / CH : 0;
+    w.traj = take((size_t)B * T * DP * sizeof(float2));
+    w.scales = take((size_t)B * (nchunks > 0 ? nchunks : 1) * sizeof(float));
+    w.G = take((size_t)B * 3 * mat);
+    w.gf = take((size_t)B * DP * sizeof(float));
+    w.lam0 = take((size_t)B * DP * sizeof(float2));
+    w.gAdir = take((size_t)B * sizeof(double));
+    w.Gtot = take(3 * mat);
+    w.gftot = take((size_t)DP * sizeof(float));
+    w.lam0tot = take((size_t)DP * sizeof(float2));
+  }
+  w.total = off;
+  return w;
+}
+
+int ensure_ttab(amps_ctx* ctx, int n, float dt32, cudaStream_t st) {
+  uint32_t bits;
+  memcpy(&bits, &dt32, 4);
+  if (ctx->ttab && ctx->ttab_n >= n && ctx->ttab_dtbits == bits) return AMPS_OK;
+  if (ctx->ttab) {
+    CUDA_TRY(ctx, cudaFree(ctx->ttab));
+    ctx->ttab = nullptr;
+  }
+  int cap = n < 70000 ? 70000 : n + n / 4;
+  CUDA_TRY(ctx, cudaMalloc(&ctx->ttab, (size_t)cap * sizeof(float)));
+  prep_ttab_kernel<<<1, 32, 0, st>>>(dt32, cap, ctx->ttab);
+  LAUNCH_CHECK(ctx, "prep_ttab_kernel");
+  ctx->ttab_n = cap;
+  ctx->ttab_dtbits = bits;
+  return AMPS_OK;
+}
+
+int ensure_scratch(amps_ctx* ctx, size_t bytes) {
+  if (ctx->scratch_bytes >= bytes) return AMPS_OK;
+  if (ctx->scratch) {
+    CUDA_TRY(ctx, cudaFree(ctx->scratch));
+    ctx->scratch = nullptr;
+    ctx->scratch_bytes = 0;
+  }
+  CUDA_TRY(ctx, cudaMalloc(&ctx->scratch, bytes));
+  ctx->scratch_bytes = bytes;
+  return AMPS_OK;
+}
+
+int check_common(amps_ctx* ctx, const amps_params* p) {
+  if (!ctx) return AMPS_E_INVALID;
+  if (!p) return fail(ctx, AMPS_E_INVALID, "params is NULL");
+  if (p->D <= 0) return fail(ctx, AMPS_E_INVALID, "bond dimension D=%d must be positive", p->D);
+  if (!p->R_dev || !p->freqs_dev) return fail(ctx, AMPS_E_INVALID, "R_dev/freqs_dev is NULL");
+  if (!(p->A == p->A) || p->A == 0.0f) return fail(ctx, AMPS_E_INVALID, "A must be non-zero");
+  return AMPS_OK;
+}
+
+// mats + psi0 + q table into the workspace
+int psi_prepare(amps_ctx* ctx, const amps_params* p, int DP, char* ws, const PsiWs& L,
+                int nsteps_tab, cudaStream_t st) {
+  const double cprime = -p->delta_t * (double)p->sigma * (double)p->sigma / 2.0;  // model.py:312
+  int rc = ensure_ttab(ctx, nsteps_tab + 1, (float)p->delta_t, st);
+  if (rc) return rc;
+  prep_mats_kernel<<<(DP * DP + 255) / 256, 256, 0, st>>>(
+      (const float2*)p->R_dev, p->D, DP, cprime, (float2*)(ws + L.matN), (float2*)(ws + L.matR),
+      (float2*)(ws + L.matRH), (float2*)(ws + L.matS));
+  LAUNCH_CHECK(ctx, "prep_mats_kernel");
+  prep_pad_vec_kernel<<<1, DP, 0, st>>>((const float2*)p->psi0_dev, p->D, DP,
+                                        (float2*)(ws + L.psi0p));
+  LAUNCH_CHECK(ctx, "prep_pad_vec_kernel");
+  if (nsteps_tab > 0) {
+    const size_t total = (size_t)nsteps_tab * DP;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    prep_qtab_kernel<<<blocks, 256, 0, st>>>(p->freqs_dev, p->D, DP, ctx->ttab, nsteps_tab,
+                                             (float2*)(ws + L.qtab));
+    LAUNCH_CHECK(ctx, "prep_qtab_kernel");
+  }
+  return AMPS_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int amps_version(void) { return AMPS_VERSION; }
+
+int amps_create(int device, amps_ctx** out) {
+  if (!out) return AMPS_E_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return AMPS_E_CUDA;
+  amps_ctx* ctx = new (std::nothrow) amps_ctx();
+  if (!ctx) return AMPS_E_INVALID;
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) {
+    delete ctx;
+    return AMPS_E_CUDA;
+  }
+  *out = ctx;
+  return AMPS_OK;
+}
+
+int amps_destroy(amps_ctx* ctx) {
+  if (!ctx) return AMPS_E_INVALID;
+  cudaSetDevice(ctx->device);
+  if (ctx->ttab) cudaFree(ctx->ttab);
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->hbuf) cudaFree(ctx->hbuf);
+  if (ctx->hstream) cudaStreamDestroy(ctx->hstream);
+  delete ctx;
+  return AMPS_OK;
+}
+
+const char* amps_last_error(const amps_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+int64_t amps_launch_count(const amps_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+size_t amps_psi_grad_count(int D) { return D > 0 ? (size_t)2 * D * D + 3 * (size_t)D + 2 : 0; }
+
+size_t amps_psi_workspace_bytes(int D, int B, int T, int save_for_bwd) {
+  const int DP = padded_dim(D);
+  if (DP < 0 || B < 0 || T < 0) return 0;
+  return psi_ws_layout(DP, B, T > 0 ? T - 1 : 0, T, save_for_bwd != 0).total;
+}
+
+int amps_psi_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T,
+                      float* loss_dev, void* ws_dev, size_t ws_bytes, int save_for_bwd,
+                      void* stream) {
+  int rc = check_common(ctx, p);
+  if (rc) return rc;
+  if (!p->psi0_dev) return fail(ctx, AMPS_E_INVALID, "psi0_dev is NULL");
+  if (B < 0 || T < 1) return fail(ctx, AMPS_E_INVALID, "bad shape B=%d T=%d (need B>=0, T>=1)", B, T);
+  if (B == 0) return AMPS_OK;
+  if (!x_dev || !loss_dev || !ws_dev) return fail(ctx, AMPS_E_INVALID, "NULL buffer");
+  const int DP = padded_dim(p->D);
+  if (DP < 0) return fail(ctx, AMPS_E_UNSUPPORTED, "bond dimension %d > 64 not supported by the sequential kernel", p->D);
+  const bool save = save_for_bwd != 0;
+  const PsiWs L = psi_ws_layout(DP, B, T - 1, T, save);
+  if (ws_bytes < L.total)
+    return fail(ctx, AMPS_E_WORKSPACE, "workspace %zu < required %zu bytes", ws_bytes, L.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)ws_dev;
+  const int nsteps = T - 1;
+  const int nchunks = (nsteps + CH - 1) / CH;
+  rc = psi_prepare(ctx, p, DP, ws, L, nsteps, st);
+  if (rc) return rc;
+  return dispatch_dp(DP, [&](auto dp, auto nq) -> int {
+    constexpr int DPc = decltype(dp)::value, NQc = decltype(nq)::value;
+    auto kern = psi_fwd_kernel<DPc, NQc>;
+    const size_t smem = sizeof(FwdSmem<DPc>);
+    CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<B, DPc * NQc, smem, st>>>(
+        (const float2*)(ws + L.matN), (const float2*)(ws + L.matR), (const float2*)(ws + L.matS),
+        (const float2*)(ws + L.qtab), (const float2*)(ws + L.psi0p), x_dev, T, p->A, loss_dev,
+        (double*)(ws + L.lossd), save ? (float2*)(ws + L.traj) : nullptr,
+        save ? (float*)(ws + L.scales) : nullptr, nchunks);
+    LAUNCH_CHECK(ctx, "psi_fwd_kernel");
+    return AMPS_OK;
+  });
+}
+
+int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T,
+                      const float* w_dev, void* ws_dev, size_t ws_bytes, float* grad_dev,
+                      void* stream) {
+  int rc = check_common(ctx, p);
+  if (rc) return rc;
+  if (B < 0 || T < 1) return fail(ctx, AMPS_E_INVALID, "bad shape B=%d T=%d", B, T);
+  if (!grad_dev) return fail(ctx, AMPS_E_INVALID, "grad_dev is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t ng = amps_psi_grad_count(p->D);
+  if (B == 0) {
+    CUDA_TRY(ctx, cudaMemsetAsync(grad_dev, 0, ng * sizeof(float), st));
+    return AMPS_OK;
+  }
+  if (!x_dev || !w_dev || !ws_dev) return fail(ctx, AMPS_E_INVALID, "NULL buffer");
+  const int DP = padded_dim(p->D);
+  if (DP < 0) return fail(ctx, AMPS_E_UNSUPPORTED, "bond dimension %d > 64 not supported by the sequential kernel", p->D);
+  const PsiWs L = psi_ws_layout(DP, B, T - 1, T, true);
+  if (ws_bytes < L.total)
+    return fail(ctx, AMPS_E_WORKSPACE, "workspace %zu < required %zu bytes", ws_bytes, L.total);
+  char* ws = (char*)ws_dev;
+  const int nsteps = T - 1;
+  const int nchunks = (nsteps + CH - 1) / CH;
+  const double cprime = -p->delta_t * (double)p->sigma * (double)p->sigma / 2.0;
+  if (!ctx->ttab || ctx->ttab_n < T) return fail(ctx, AMPS_E_STATE, "backward without a saving forward");
+  rc = dispatch_dp(DP, [&](auto dp, auto nq) -> int {
+    constexpr int DPc = decltype(dp)::value, NQc = decltype(nq)::value;
+    auto kern = psi_bwd_kernel<DPc, NQc>;
+    const size_t smem = sizeof(BwdSmem<DPc>);
+    CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<B, DPc * NQc, smem, st>>>(
+        (const float2*)(ws + L.matN), (const float2*)(ws + L.matRH), (const float2*)(ws + L.matS),
+        (const float2*)(ws + L.qtab), ctx->ttab, x_dev, T, p->A, w_dev,
+        (const float2*)(ws + L.traj), (const float*)(ws + L.scales), nchunks,
+        (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0), (double*)(ws + L.gAdir));
+    LAUNCH_CHECK(ctx, "psi_bwd_kernel");
+    return AMPS_OK;
+  });
+  if (rc) return rc;
+  {
+    const int total = 3 * DP * DP + 2 * DP;
+    psi_reduce_clips_kernel<<<(total + 127) / 128, 128, 0, st>>>(
+        (const float2*)(ws + L.G), (const float*)(ws + L.gf), (const float2*)(ws + L.lam0), B, DP,
+        (float2*)(ws + L.Gtot), (float*)(ws + L.gftot), (float2*)(ws + L.lam0tot));
+    LAUNCH_CHECK(ctx, "psi_reduce_clips_kernel");
+    psi_grad_finalize_kernel<<<1, 256, 0, st>>>(
+        (const float2*)(ws + L.Gtot), (const float*)(ws + L.gftot), (const float2*)(ws + L.lam0tot),
+        (const double*)(ws + L.gAdir), (const double*)(ws + L.lossd), w_dev, B,
+        (const float2*)(ws + L.matR), p->D, DP, cprime, p->A, grad_dev);
+    LAUNCH_CHECK(ctx, "psi_grad_finalize_kernel");
+  }
+  return AMPS_OK;
+}
+
+int amps_psi_sample(amps_ctx* ctx, const amps_params* p, const float* noise_dev, int L_, int n,
+                    float* out_dev, void* stream) {
+  int rc = check_common(ctx, p);
+  if (rc) return rc;
+  if (!p->psi0_dev) return fail(ctx, AMPS_E_INVALID, "psi0_dev is NULL");
+  if (L_ < 0 || n < 0) return fail(ctx, AMPS_E_INVALID, "bad shape L=%d n=%d", L_, n);
+  if (L_ == 0 || n == 0) return AMPS_OK;
+  if (!noise_dev || !out_dev) return fail(ctx, AMPS_E_INVALID, "NULL buffer");
+  const int DP = padded_dim(p->D);
+  if (DP < 0) return fail(ctx, AMPS_E_UNSUPPORTED, "bond dimension %d > 64 not supported by the sequential kernel", p->D);
+  const PsiWs L = psi_ws_layout(DP, 0, L_, 0, false);
+  rc = ensure_scratch(ctx, L.total);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)ctx->scratch;
+  rc = psi_prepare(ctx, p, DP, ws, L, L_, st);
+  if (rc) return rc;
+  return dispatch_dp(DP, [&](auto dp, auto nq) -> int {
+    constexpr int DPc = decltype(dp)::value, NQc = decltype(nq)::value;
+    auto kern = psi_sample_kernel<DPc, NQc>;
+    const size_t smem = sizeof(SampleSmem<DPc>);
+    CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<n, DPc * NQc, smem, st>>>((const float2*)(ws + L.matN), (const float2*)(ws + L.matR),
+                                     (const float2*)(ws + L.qtab), (const float2*)(ws + L.psi0p),
+                                     noise_dev, L_, n, p->A, (float)p->delta_t, out_dev);
+    LAUNCH_CHECK(ctx, "psi_sample_kernel");
+    return AMPS_OK;
+  });
+}
+
+int amps_psi_evolve(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T,
+                    float* traj_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+  if (!ctx) return AMPS_E_INVALID;
+  if (!traj_dev && B > 0 && T > 1) return fail(ctx, AMPS_E_INVALID, "traj_dev is NULL");
+  if (B <= 0 || T <= 1) return (B < 0 || T < 1) ? fail(ctx, AMPS_E_INVALID, "bad shape") : AMPS_OK;
+  const int DP = padded_dim(p ? p->D : 0);
+  if (DP < 0) return fail(ctx, AMPS_E_UNSUPPORTED, "bond dimension not supported");
+  const PsiWs L = psi_ws_layout(DP, B, T - 1, T, true);
+  if (ws_bytes < L.total)
+    return fail(ctx, AMPS_E_WORKSPACE, "workspace %zu < required %zu bytes", ws_bytes, L.total);
+  // per-clip loss lands in the (unused) gf slot of the workspace
+  char* ws = (char*)ws_dev;
+  int rc = amps_psi_loss_fwd(ctx, p, x_dev, B, T, (float*)(ws + L.gf), ws_dev, ws_bytes, 1, stream);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t items = (size_t)B * (T - 1);
+  int blocks = (int)((items * 32 + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  psi_lab_traj_kernel<<<blocks, 256, 0, st>>>((const float2*)(ws + L.traj), p->freqs_dev, ctx->ttab,
+                                              B, T, p->D, DP, (float2*)traj_dev);
+  LAUNCH_CHECK(ctx, "psi_lab_traj_kernel");
+  return AMPS_OK;
+}
+
+int amps_psi_loss_grad_host(amps_ctx* ctx, const amps_host_params* hp, const float* x_host, int B,
+                            int T, float w, float* loss_host, float* grad_host) {
+  if (!ctx) return AMPS_E_INVALID;
+  if (!hp || !x_host || !loss_host || !grad_host) return fail(ctx, AMPS_E_INVALID, "NULL argument");
+  if (B <= 0 || T < 1) return fail(ctx, AMPS_E_INVALID, "bad shape B=%d T=%d", B, T);
+  const int D = hp->D;
+  if (padded_dim(D) < 0) return fail(ctx, AMPS_E_UNSUPPORTED, "bond dimension %d not supported", D);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->hstream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->hstream, cudaStreamNonBlocking));
+  cudaStream_t st = ctx->hstream;
+  const size_t ng = amps_psi_grad_count(D);
+  const size_t wsb = amps_psi_workspace_bytes(D, B, T, 1);
+  // layout of the host-entry device buffer
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += align_up(bytes);
+    return o;
+  };
+  const size_t oR = take((size_t)D * D * 8), oF = take((size_t)D * 4), oP = take((size_t)D * 8);
+  const size_t oX = take((size_t)B * T * 4), oL = take((size_t)B * 4), oW = take((size_t)B * 4);
+  const size_t oG = take(ng * 4), oWs = take(wsb);
+  if (ctx->hbuf_bytes < off) {
+    if (ctx->hbuf) CUDA_TRY(ctx, cudaFree(ctx->hbuf));
+    ctx->hbuf = nullptr;
+    ctx->hbuf_bytes = 0;
+    CUDA_TRY(ctx, cudaMalloc(&ctx->hbuf, off));
+    ctx->hbuf_bytes = off;
+  }
+  char* d = (char*)ctx->hbuf;
+  CUDA_TRY(ctx, cudaMemcpyAsync(d + oR, hp->R, (size_t)D * D * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d + oF, hp->freqs, (size_t)D * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d + oP, hp->psi0, (size_t)D * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d + oX, x_host, (size_t)B * T * 4, cudaMemcpyHostToDevice, st));
+  fill_kernel<<<(B + 255) / 256, 256, 0, st>>>((float*)(d + oW), B, w);
+  LAUNCH_CHECK(ctx, "fill_kernel");
+  amps_params p{};
+  p.D = D;
+  p.R_dev = (const float*)(d + oR);
+  p.freqs_dev = (const float*)(d + oF);
+  p.psi0_dev = (const float*)(d + oP);
+  p.A = hp->A;
+  p.sigma = hp->sigma;
+  p.delta_t = hp->delta_t;
+  int rc = amps_psi_loss_fwd(ctx, &p, (const float*)(d + oX), B, T, (float*)(d + oL), d + oWs, wsb, 1, st);
+  if (rc) return rc;
+  rc = amps_psi_loss_bwd(ctx, &p, (const float*)(d + oX), B, T, (const float*)(d + oW), d + oWs, wsb,
+                         (float*)(d + oG), st);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaMemcpyAsync(loss_host, d + oL, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(grad_host, d + oG, ng * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  return AMPS_OK;
+}
+
+// ---- RhoCMPS -----------------------------------------------------------------------------
+size_t amps_rho_workspace_bytes(int D, int B, int T) { return rho_workspace_bytes(D, B, T); }
+
+int amps_rho_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T,
+                      float* loss_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+  int rc = check_common(ctx, p);
+  if (rc) return rc;
+  if (!p->rho0_dev) return fail(ctx, AMPS_E_INVALID, "rho0_dev is NULL");
+  if (B < 0 || T < 1) return fail(ctx, AMPS_E_INVALID, "bad shape B=%d T=%d", B, T);
+  if (B == 0) return AMPS_OK;
+  if (!x_dev || !loss_dev) return fail(ctx, AMPS_E_INVALID, "NULL buffer");
+  if (p->D > RHO_MAX_D) return fail(ctx, AMPS_E_UNSUPPORTED, "rho kernels support D <= %d", RHO_MAX_D);
+  if (ws_bytes < rho_workspace_bytes(p->D, B, T))
+    return fail(ctx, AMPS_E_WORKSPACE, "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = ensure_ttab(ctx, T + 1, (float)p->delta_t, st);
+  if (rc) return rc;
+  rc = rho_launch_data(p, ctx->ttab, x_dev, B, T, loss_dev, nullptr, ws_dev, st);
+  if (rc) return fail(ctx, rc, "rho kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  ctx->launches++;
+  return AMPS_OK;
+}
+
+int amps_rho_evolve(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T,
+                    float* traj_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+  int rc = check_common(ctx, p);
+  if (rc) return rc;
+  if (!p->rho0_dev) return fail(ctx, AMPS_E_INVALID, "rho0_dev is NULL");
+  if (B < 0 || T < 1) return fail(ctx, AMPS_E_INVALID, "bad shape B=%d T=%d", B, T);
+  if (B == 0 || T == 1) return AMPS_OK;
+  if (!x_dev || !traj_dev) return fail(ctx, AMPS_E_INVALID, "NULL buffer");
+  if (p->D > RHO_MAX_D) return fail(ctx, AMPS_E_UNSUPPORTED, "rho kernels support D <= %d", RHO_MAX_D);
+  if (ws_bytes < rho_workspace_bytes(p->D, B, T))
+    return fail(ctx, AMPS_E_WORKSPACE, "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = ensure_ttab(ctx, T + 1, (float)p->delta_t, st);
+  if (rc) return rc;
+  rc = rho_launch_data(p, ctx->ttab, x_dev, B, T, nullptr, (float2*)traj_dev, ws_dev, st);
+  if (rc) return fail(ctx, rc, "rho kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  ctx->launches++;
+  return AMPS_OK;
+}
+
+int amps_rho_sample(amps_ctx* ctx, const amps_params* p, const float* noise_dev, int L, int n,
+                    float* out_dev, float* traj_dev, float* purity_dev, void* ws_dev,
+                    size_t ws_bytes, void* stream) {
+  int rc = check_common(ctx, p);
+  if (rc) return rc;
+  if (!p->rho0_dev) return fail(ctx, AMPS_E_INVALID, "rho0_dev is NULL");
+  if (L < 0 || n < 0) return fail(ctx, AMPS_E_INVALID, "bad shape L=%d n=%d", L, n);
+  if (L == 0 || n == 0) return AMPS_OK;
+  if (!noise_dev) return fail(ctx, AMPS_E_INVALID, "noise_dev is NULL");
+  if (p->D > RHO_MAX_D) return fail(ctx, AMPS_E_UNSUPPORTED, "rho kernels support D <= %d", RHO_MAX_D);
+  if (ws_bytes < rho_workspace_bytes(p->D, n, L + 1))
+    return fail(ctx, AMPS_E_WORKSPACE, "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = ensure_ttab(ctx, L + 1, (float)p->delta_t, st);
+  if (rc) return rc;
+  rc = rho_launch_sample(p, ctx->ttab, noise_dev, L, n, out_dev, (float2*)traj_dev, purity_dev,
+                         ws_dev, st);
+  if (rc) return fail(ctx, rc, "rho kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  ctx->launches++;
+  return AMPS_OK;
+}
+
+}  // extern "C"

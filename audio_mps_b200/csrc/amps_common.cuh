@@ -1,0 +1,133 @@
+// Shared device helpers for the AudioMPS scan kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace amps {
+
+// Steps per chunk.  The sequential chain runs CH steps between the batched (lane-parallel)
+// reductions that produce E_k, nu_k^2, log terms and the rescale of the un-normalised state.
+constexpr int CH = 32;
+
+// ---- complex helpers on float2 (re, im) ---------------------------------------------------
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// conj(a) * b
+__device__ __forceinline__ float2 cmul_ca(float2 a, float2 b) {
+  return make_float2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
+}
+// acc += a * x
+__device__ __forceinline__ void cmac(float2& acc, float2 a, float2 x) {
+  acc.x = fmaf(a.x, x.x, acc.x);
+  acc.y = fmaf(a.x, x.y, acc.y);
+  acc.x = fmaf(-a.y, x.y, acc.x);
+  acc.y = fmaf(a.y, x.x, acc.y);
+}
+// acc += a * conj(x)
+__device__ __forceinline__ void cmac_cx(float2& acc, float2 a, float2 x) {
+  acc.x = fmaf(a.x, x.x, acc.x);
+  acc.y = fmaf(a.y, x.x, acc.y);
+  acc.x = fmaf(a.y, x.y, acc.x);
+  acc.y = fmaf(-a.x, x.y, acc.y);
+}
+__device__ __forceinline__ float cabs2(float2 a) { return fmaf(a.x, a.x, a.y * a.y); }
+
+// ---- cp.async (LDGSTS) --------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// ---- thread map ---------------------------------------------------------------------------
+// A CTA of DP*NQ threads owns one clip.  Thread t = i*NQ + jq holds, for matrix row i, the
+// CPT = DP/NQ columns  col(c) = 2*NQ*(c/2) + 2*jq + (c&1)  in registers, so that for a fixed
+// pair index the NQ lanes of a row group read 16*NQ contiguous bytes of the state vector
+// (one conflict-free LDS.128 each).  Row sums are finished with xor-shuffles over the NQ lanes.
+template <int DP, int NQ>
+struct Map {
+  static constexpr int NT = DP * NQ;
+  static constexpr int CPT = DP / NQ;
+  static constexpr int NP = CPT / 2;
+  static_assert(DP % (2 * NQ) == 0, "DP must be a multiple of 2*NQ");
+  static_assert(NT % 32 == 0, "CTA must be whole warps");
+  static_assert(NQ == 4 || NQ == 8, "NQ in {4,8}");
+  __device__ static __forceinline__ int col(int c, int jq) {
+    return 2 * NQ * (c >> 1) + 2 * jq + (c & 1);
+  }
+};
+
+template <int NQ>
+__device__ __forceinline__ float2 group_sum(float2 v) {
+#pragma unroll
+  for (int m = 1; m < NQ; m <<= 1) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, m);
+    v.y += __shfl_xor_sync(0xffffffffu, v.y, m);
+  }
+  return v;
+}
+
+// Load this thread's register slice of row i of a [DP][DP] complex matrix.
+template <int DP, int NQ>
+__device__ __forceinline__ void load_slice(float2 (&dst)[DP / NQ], const float2* __restrict__ mat,
+                                           int i, int jq) {
+#pragma unroll
+  for (int c = 0; c < DP / NQ; ++c) dst[c] = mat[i * DP + Map<DP, NQ>::col(c, jq)];
+}
+
+// Partial complex mat-vec of two register slices against one smem vector:
+//   a += sum_c A[c] * v[col(c)],  b += sum_c Bm[c] * v[col(c)]
+template <int DP, int NQ>
+__device__ __forceinline__ void matvec2(const float2 (&A)[DP / NQ], const float2 (&Bm)[DP / NQ],
+                                        const float2* __restrict__ v, int jq, float2& a,
+                                        float2& b) {
+  float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+#pragma unroll
+  for (int m = 0; m < DP / NQ / 2; ++m) {
+    const float4 xv = *reinterpret_cast<const float4*>(&v[2 * NQ * m + 2 * jq]);
+    const float2 x0 = make_float2(xv.x, xv.y), x1 = make_float2(xv.z, xv.w);
+    cmac(a0, A[2 * m], x0);
+    cmac(a1, A[2 * m + 1], x1);
+    cmac(b0, Bm[2 * m], x0);
+    cmac(b1, Bm[2 * m + 1], x1);
+  }
+  a = make_float2(a0.x + a1.x, a0.y + a1.y);
+  b = make_float2(b0.x + b1.x, b0.y + b1.y);
+}
+
+template <int DP, int NQ>
+__device__ __forceinline__ float2 matvec1(const float2 (&A)[DP / NQ], const float2* __restrict__ v,
+                                          int jq) {
+  float2 a0 = make_float2(0.f, 0.f), a1 = a0;
+#pragma unroll
+  for (int m = 0; m < DP / NQ / 2; ++m) {
+    const float4 xv = *reinterpret_cast<const float4*>(&v[2 * NQ * m + 2 * jq]);
+    cmac(a0, A[2 * m], make_float2(xv.x, xv.y));
+    cmac(a1, A[2 * m + 1], make_float2(xv.z, xv.w));
+  }
+  return make_float2(a0.x + a1.x, a0.y + a1.y);
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  return v;
+}
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  return v;
+}
+
+}  // namespace amps

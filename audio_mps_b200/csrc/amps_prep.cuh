@@ -1,0 +1,198 @@
+// Small parameter-only kernels: step-operator matrices, float32 time table, phase-rotation
+// table, gradient finalisation, lab-frame trajectory.  All O(D^3) or O(T*D): off the hot path.
+#pragma once
+#include "amps_common.cuh"
+
+namespace amps {
+
+// t_0 = 0, t_{k+1} = fl32(t_k + dt32): the float32 running sum of model.py:16,157,281.
+// Strictly sequential by definition; run once per (n, dt32) and cached by the context.
+__global__ void prep_ttab_kernel(float dt32, int n, float* __restrict__ ttab) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < n; ++k) {
+      ttab[k] = t;
+      t = __fadd_rn(t, dt32);
+    }
+  }
+}
+
+// Padded [DP][DP] complex matrices from the effective R [D][D]:
+//   matR = R, matRH = R^dag, matS = R + R^dag, matN = I + cprime * R^dag R  (exactly Hermitian)
+__global__ void prep_mats_kernel(const float2* __restrict__ R, int D, int DP, double cprime,
+                                 float2* __restrict__ matN, float2* __restrict__ matR,
+                                 float2* __restrict__ matRH, float2* __restrict__ matS) {
+  for (int idx = threadIdx.x + blockIdx.x * blockDim.x; idx < DP * DP;
+       idx += blockDim.x * gridDim.x) {
+    const int i = idx / DP, j = idx % DP;
+    const bool in = (i < D && j < D);
+    const float2 rij = in ? R[i * D + j] : make_float2(0.f, 0.f);
+    const float2 rji = in ? R[j * D + i] : make_float2(0.f, 0.f);
+    matR[idx] = rij;
+    matRH[idx] = make_float2(rji.x, -rji.y);
+    matS[idx] = make_float2(rij.x + rji.x, rij.y - rji.y);
+    if (i <= j) {
+      double mr = 0.0, mi = 0.0;  // M_ij = sum_m conj(R_mi) R_mj
+      if (in) {
+        for (int m = 0; m < D; ++m) {
+          const float2 a = R[m * D + i], bb = R[m * D + j];
+          mr += (double)a.x * bb.x + (double)a.y * bb.y;
+          mi += (double)a.x * bb.y - (double)a.y * bb.x;
+        }
+      }
+      const double nr = (i == j ? 1.0 : 0.0) + cprime * mr;
+      const double ni = (i == j ? 0.0 : cprime * mi);
+      matN[i * DP + j] = make_float2((float)nr, (float)ni);
+      if (i != j) matN[j * DP + i] = make_float2((float)nr, (float)(-ni));
+    }
+  }
+}
+
+__global__ void prep_pad_vec_kernel(const float2* __restrict__ v, int D, int DP,
+                                    float2* __restrict__ vp) {
+  const int i = threadIdx.x + blockIdx.x * blockDim.x;
+  if (i < DP) vp[i] = (i < D) ? v[i] : make_float2(0.f, 0.f);
+}
+
+// q_k[c] = p_k[c] conj(p_{k+1}[c]),  p_k[c] = exp(i * fl32(f_c * t_k))  (model.py:304-305).
+// The two float32 angles are exact in double; their difference and the sincos are done in
+// double and rounded once.
+__global__ void prep_qtab_kernel(const float* __restrict__ freqs, int D, int DP,
+                                 const float* __restrict__ ttab, int nsteps,
+                                 float2* __restrict__ qtab) {
+  const size_t total = (size_t)nsteps * DP;
+  for (size_t idx = threadIdx.x + (size_t)blockIdx.x * blockDim.x; idx < total;
+       idx += (size_t)blockDim.x * gridDim.x) {
+    const int k = (int)(idx / DP), c = (int)(idx % DP);
+    float2 q = make_float2(1.f, 0.f);
+    if (c < D) {
+      const float f = freqs[c];
+      const double th0 = (double)__fmul_rn(f, ttab[k]);
+      const double th1 = (double)__fmul_rn(f, ttab[k + 1]);
+      double sn, cs;
+      sincos(th0 - th1, &sn, &cs);
+      q = make_float2((float)cs, (float)sn);
+    }
+    qtab[idx] = q;
+  }
+}
+
+// Sum the per-clip partials over clips in a fixed order (deterministic).
+//   Gtot[e] = sum_b G[b][e]  for e in [0, 3*DP*DP) ; gftot, lam0tot likewise.
+__global__ void psi_reduce_clips_kernel(const float2* __restrict__ G, const float* __restrict__ gf,
+                                        const float2* __restrict__ lam0, int B, int DP,
+                                        float2* __restrict__ Gtot, float* __restrict__ gftot,
+                                        float2* __restrict__ lam0tot) {
+  const int nG = 3 * DP * DP;
+  const int total = nG + 2 * DP;
+  for (int e = threadIdx.x + blockIdx.x * blockDim.x; e < total; e += blockDim.x * gridDim.x) {
+    if (e < nG) {
+      double sx = 0.0, sy = 0.0;
+      for (int b = 0; b < B; ++b) {
+        const float2 v = G[(size_t)b * nG + e];
+        sx += v.x;
+        sy += v.y;
+      }
+      Gtot[e] = make_float2((float)sx, (float)sy);
+    } else if (e < nG + DP) {
+      const int c = e - nG;
+      double s = 0.0;
+      for (int b = 0; b < B; ++b) s += gf[(size_t)b * DP + c];
+      gftot[c] = (float)s;
+    } else {
+      const int c = e - nG - DP;
+      double sx = 0.0, sy = 0.0;
+      for (int b = 0; b < B; ++b) {
+        const float2 v = lam0[(size_t)b * DP + c];
+        sx += v.x;
+        sy += v.y;
+      }
+      lam0tot[c] = make_float2((float)sx, (float)sy);
+    }
+  }
+}
+
+// Packed gradient wrt the effective parameters (single CTA):
+//   gR = G_R + G_E + cprime * R (G_N + G_N^dag)
+//   gA = -(1/A) Re sum conj(G_R) R + sum_b gAdir[b]
+//   out = [ gR (2 D^2) | gf (D) | gpsi0 (2 D) | gA | sum_b w_b loss_b ]
+__global__ void psi_grad_finalize_kernel(const float2* __restrict__ Gtot,
+                                         const float* __restrict__ gftot,
+                                         const float2* __restrict__ lam0tot,
+                                         const double* __restrict__ gAdir,
+                                         const double* __restrict__ lossd,
+                                         const float* __restrict__ w, int B,
+                                         const float2* __restrict__ matR, int D, int DP,
+                                         double cprime, float A, float* __restrict__ out) {
+  __shared__ double red[32];
+  const float2* GR = Gtot;
+  const float2* GN = Gtot + DP * DP;
+  const float2* GE = Gtot + 2 * DP * DP;
+  double part = 0.0;  // Re sum conj(GR) R
+  for (int idx = threadIdx.x; idx < D * D; idx += blockDim.x) {
+    const int i = idx / D, j = idx % D;
+    double cr = 0.0, ci = 0.0;  // (R H)_ij, H = GN + GN^dag
+    for (int m = 0; m < D; ++m) {
+      const float2 r = matR[i * DP + m];
+      const float2 g1 = GN[m * DP + j], g2 = GN[j * DP + m];
+      const double hx = (double)g1.x + g2.x, hy = (double)g1.y - g2.y;
+      cr += r.x * hx - r.y * hy;
+      ci += r.x * hy + r.y * hx;
+    }
+    const float2 gr = GR[i * DP + j], ge = GE[i * DP + j];
+    out[2 * idx] = (float)((double)gr.x + ge.x + cprime * cr);
+    out[2 * idx + 1] = (float)((double)gr.y + ge.y + cprime * ci);
+    const float2 r = matR[i * DP + j];
+    part += (double)gr.x * r.x + (double)gr.y * r.y;
+  }
+  float* o = out + 2 * D * D;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    o[c] = gftot[c];
+    o[D + 2 * c] = lam0tot[c].x;
+    o[D + 2 * c + 1] = lam0tot[c].y;
+  }
+  // block reduce `part`
+  part = warp_sum_d(part);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) tot += red[wv];
+    double ga = -tot / (double)A;
+    double ls = 0.0;
+    for (int b = 0; b < B; ++b) {
+      ga += gAdir[b];
+      ls += (double)w[b] * lossd[b];
+    }
+    o[3 * D] = (float)ga;
+    o[3 * D + 1] = (float)ls;
+  }
+}
+
+// Lab-frame normalised trajectory (model.py:231-240): psi_{k+1} = p_{k+1} x_{k+1} / |x_{k+1}|.
+// One warp per (clip, step).
+__global__ void psi_lab_traj_kernel(const float2* __restrict__ traj, const float* __restrict__ freqs,
+                                    const float* __restrict__ ttab, int B, int T, int D, int DP,
+                                    float2* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const size_t wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nw = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const size_t total = (size_t)B * (T - 1);
+  for (size_t item = wid; item < total; item += nw) {
+    const int b = (int)(item / (T - 1)), k = (int)(item % (T - 1));
+    const float2* xv = traj + ((size_t)b * T + k + 1) * DP;
+    float n2 = 0.f;
+    for (int c = lane; c < D; c += 32) n2 += cabs2(xv[c]);
+    n2 = warp_sum_f(n2);
+    const float rn = rsqrtf(fmaxf(n2, 1e-12f));          // model.py:331-332
+    const float tk = ttab[k + 1];
+    for (int c = lane; c < D; c += 32) {
+      double sn, cs;
+      sincos((double)__fmul_rn(freqs[c], tk), &sn, &cs);
+      const float2 v = cmul(make_float2((float)cs, (float)sn), xv[c]);
+      out[((size_t)b * (T - 1) + k) * D + c] = make_float2(v.x * rn, v.y * rn);
+    }
+  }
+}
+
+}  // namespace amps

@@ -1,0 +1,153 @@
+/*
+ * audiomps.h -- C ABI of libaudiomps.so, the B200-native (sm_100a) implementation of the
+ * continuous-MPS ("AudioMPS") time-step scan of AustenLamacraft/audio-mps.
+ *
+ * The reference has no FFI: the boundary it exposes for this path is the Python model API of
+ * /root/reference/model.py (PsiCMPS / RhoCMPS).  Each entry point below names the reference
+ * interface it replaces (file:line into the reference tree).  The Python host package
+ * (audio_mps_b200/) binds these with ctypes; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative AMPS_E_* code otherwise; no C++ exception
+ *     crosses the ABI; amps_last_error() returns a per-context message.
+ *   - all `*_dev` pointers are CUDA device pointers on the context's device; the caller owns them
+ *     (including the workspace).  `stream` is a cudaStream_t passed as void* (NULL = default
+ *     stream).  Device entry points never synchronise; host entry points (`*_host`) synchronise
+ *     the context's private stream before returning.
+ *   - complex64 arrays are interleaved (re, im) float pairs, row-major.
+ *   - parameters handed to the library are the EFFECTIVE ones (after model.py:31-52 and
+ *     model.py:221-222 / 127-130): R_eff[i,j] = R[i,j] - R[j,j], freqs, normalised psi_0 / rho_0.
+ *     The raw->effective chain (O(D^2), off the hot path) stays in host code.
+ *   - time is the float32 running sum t_{k+1} = fl32(t_k + fl32(delta_t)) (model.py:16,157,281);
+ *     the library reproduces it bit-exactly and forms phases from fl32(f_c * t_k).
+ */
+#ifndef AUDIOMPS_H_
+#define AUDIOMPS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMPS_VERSION 100 /* 0.1.0 */
+
+enum {
+  AMPS_OK = 0,
+  AMPS_E_INVALID = -1,     /* bad argument (null pointer, negative size, ...)          */
+  AMPS_E_UNSUPPORTED = -2, /* bond dimension / shape outside what the kernels cover    */
+  AMPS_E_WORKSPACE = -3,   /* workspace too small (see amps_*_workspace_bytes)          */
+  AMPS_E_CUDA = -4,        /* a CUDA runtime call failed; see amps_last_error           */
+  AMPS_E_STATE = -5        /* call order violated (e.g. bwd without a saving fwd)       */
+};
+
+typedef struct amps_ctx amps_ctx;
+
+/* Effective parameters of one model (device pointers + host scalars).
+ * Replaces the tensors CMPS.__init__ / PsiCMPS.__init__ / RhoCMPS.__init__ build:
+ * model.py:9-52 (R, freqs, A, sigma, delta_t), :221-222 (psi_0), :127-130 (rho_0). */
+typedef struct amps_params {
+  int32_t D;            /* bond dimension (hparams.bond_dim, model.py:11)                   */
+  int32_t reserved;
+  const float* R_dev;     /* complex64 [D,D]  effective R (model.py:41-42)                  */
+  const float* freqs_dev; /* float32   [D]    effective freqs (model.py:44-50)              */
+  const float* psi0_dev;  /* complex64 [D]    normalised psi_0 (model.py:221-222); Psi only */
+  const float* rho0_dev;  /* complex64 [D,D]  rho_0 (model.py:127-130); Rho only            */
+  float A;                /* model.py:19 (trainable scalar, value at this step)             */
+  float sigma;            /* model.py:21                                                    */
+  double delta_t;         /* model.py:15 (python double; dt32 = (float)delta_t, model.py:16)*/
+} amps_params;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+int amps_version(void);
+int amps_create(int device, amps_ctx** out);
+int amps_destroy(amps_ctx* ctx);
+const char* amps_last_error(const amps_ctx* ctx);
+/* number of kernels the context has launched so far (bench.py's gpu_launches evidence) */
+int64_t amps_launch_count(const amps_ctx* ctx);
+
+/* ---- PsiCMPS --------------------------------------------------------------------------- */
+
+/* bytes of caller-owned workspace for the Psi loss forward/backward at (D, B clips, T samples).
+ * save_for_bwd != 0 adds the state trajectory the adjoint sweep consumes. */
+size_t amps_psi_workspace_bytes(int D, int B, int T, int save_for_bwd);
+
+/* Per-clip negative log-likelihood loss_b, the fold of PsiCMPS._build_loss_psi /
+ * _psi_and_loss_update (model.py:257-267, 276-282, 293-334) BEFORE the reduce_mean (:267).
+ *   x_dev    float32 [B,T] row-major waveform (data_iterator)
+ *   loss_dev float32 [B]
+ * With save_for_bwd the workspace keeps what amps_psi_loss_bwd needs. */
+int amps_psi_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T,
+                      float* loss_dev, void* ws_dev, size_t ws_bytes, int save_for_bwd,
+                      void* stream);
+
+/* Gradient of L = sum_b w_b * loss_b with respect to the effective parameters; replaces the
+ * reverse while_loop tf.gradients builds for train.py:89.  Must follow a saving forward on the
+ * same (params, x, workspace).
+ *   w_dev    float32 [B]   per-clip weights (reference: 1/B, model.py:267)
+ *   grad_dev float32 [2*D*D + 3*D + 2] packed:
+ *            gR (complex64 [D,D], dL/dRe + i dL/dIm) | gfreqs [D] | gpsi0 (complex64 [D]) |
+ *            gA [1] | sum_b w_b*loss_b [1]
+ * (the packed buffer is what one NCCL all-reduce sums across data-parallel ranks). */
+int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T,
+                      const float* w_dev, void* ws_dev, size_t ws_bytes, float* grad_dev,
+                      void* stream);
+size_t amps_psi_grad_count(int D); /* = 2*D*D + 3*D + 2 */
+
+/* PsiCMPS.sample / _psi_and_sample_update (model.py:242-251, 284-291) with the noise tensor
+ * supplied by the caller (the reference draws it once, model.py:246).
+ *   noise_dev float32 [L,n] (time-major, as tf.random_normal([length, num_samples]))
+ *   out_dev   float32 [n,L] = A * cumulative X_t (model.py:251) */
+int amps_psi_sample(amps_ctx* ctx, const amps_params* p, const float* noise_dev, int L, int n,
+                    float* out_dev, void* stream);
+
+/* PsiCMPS.psi_evolve_with_data / _psi_update (model.py:231-240, 269-274):
+ *   traj_dev complex64 [B, T-1, D] normalised lab-frame psi after every step.
+ * Uses the same workspace size as a saving forward. */
+int amps_psi_evolve(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T,
+                    float* traj_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
+/* Host-buffer training step (bench.py "e2e"): copies x (pinned or pageable host memory) to the
+ * device, runs forward + backward with w_b = 1/B_global, copies loss[B] and the packed gradient
+ * back.  Parameters are HOST arrays here.  Device scratch is owned by the context and grown on
+ * demand.  Synchronises before returning. */
+typedef struct amps_host_params {
+  int32_t D;
+  int32_t reserved;
+  const float* R;     /* complex64 [D,D] host */
+  const float* freqs; /* float32 [D] host     */
+  const float* psi0;  /* complex64 [D] host   */
+  float A;
+  float sigma;
+  double delta_t;
+} amps_host_params;
+int amps_psi_loss_grad_host(amps_ctx* ctx, const amps_host_params* p, const float* x_host, int B,
+                            int T, float w, float* loss_host, float* grad_host);
+
+/* ---- RhoCMPS --------------------------------------------------------------------------- */
+
+size_t amps_rho_workspace_bytes(int D, int B, int T);
+
+/* RhoCMPS._build_loss_rho / _rho_and_loss_update (model.py:132-142, 152-158, 169-203):
+ * per-clip loss before the reduce_mean. */
+int amps_rho_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T,
+                      float* loss_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
+/* RhoCMPS.rho_evolve_with_data (model.py:76-85): traj_dev complex64 [B, T-1, D, D]. */
+int amps_rho_evolve(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T,
+                    float* traj_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
+/* RhoCMPS.sample / rho_evolve_with_sampling / purity (model.py:87-112, 160-167) from a supplied
+ * noise tensor [L,n].  Any of the three outputs may be NULL.
+ *   out_dev     float32   [n,L]      A * cumulative X_t
+ *   traj_dev    complex64 [n,L,D,D]  rho after every step
+ *   purity_dev  float32   [n,L]      Re tr(rho_k^2) */
+int amps_rho_sample(amps_ctx* ctx, const amps_params* p, const float* noise_dev, int L, int n,
+                    float* out_dev, float* traj_dev, float* purity_dev, void* ws_dev,
+                    size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUDIOMPS_H_ */

@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA GPU (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def lib():
+    """The built C-ABI library (compiled here with nvcc if it is stale or missing)."""
+    from audio_mps_b200 import _lib
+    _lib.build()
+    return _lib.load()
+
+
+@pytest.fixture(scope="session")
+def cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda", 0)

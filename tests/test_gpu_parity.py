@@ -1,0 +1,148 @@
+"""-m gpu parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Tolerances follow BASELINE.json north_star: per-clip loss 1e-4 relative, parameter
+gradients 1e-3 relative, samples 1e-3 -- measured against the oracle's f64 mode (the exact value of
+the reference's function) and, looser by the reference's own float32 noise, its f32 mode."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.cmps_oracle import (PsiCMPSOracle, RhoCMPSOracle, damped_sine, grads_of,
+                                random_raw_params, total_loss)
+from audio_mps_b200 import PsiCMPS, RhoCMPS
+from audio_mps_b200.train import regulariser
+from tests.util import hp_pair, rel, relc, set_raw
+
+pytestmark = pytest.mark.gpu
+
+LOSS_TOL = 1e-4
+GRAD_TOL = 1e-3
+SAMPLE_TOL = 1e-3
+
+CASES = [
+    # D, B, T, hp overrides
+    (7, 8, 256, dict(h_reg=2 / (np.pi * 16000) ** 2, r_reg=2 / (np.pi * 16000))),  # reference test hparams
+    (8, 8, 1500, dict()),                                                           # train.py hparams
+    (2, 3, 100, dict(sigma=1.0, A=1.0)),
+    (16, 5, 333, dict(sigma=0.05)),
+    (32, 4, 700, dict()),
+    (64, 3, 200, dict()),
+    (5, 2, 33, dict()),       # one chunk + one step
+    (8, 1, 2, dict()),        # single step
+]
+
+
+def build(D, B, T, over, cuda, seed=0):
+    ohp, php = hp_pair(bond_dim=D, minibatch_size=B, **over)
+    raw = random_raw_params(ohp, np.random.default_rng(seed))
+    data = damped_sine(B, T, ohp.delta_t, np.random.default_rng(seed + 1))
+    model = PsiCMPS(php, device=cuda)
+    set_raw(model, raw)
+    return ohp, raw, data, model
+
+
+@pytest.mark.parametrize("D,B,T,over", CASES)
+def test_psi_loss_per_clip(cuda, lib, D, B, T, over):
+    ohp, raw, data, model = build(D, B, T, over, cuda)
+    got = model.loss_per_clip(data).detach().cpu().numpy()
+    ref64 = PsiCMPSOracle(ohp, raw, mode="f64").loss_per_clip(data).detach().numpy()
+    assert np.all(np.isfinite(got))
+    assert rel(got, ref64) <= LOSS_TOL, (got, ref64)
+
+
+@pytest.mark.parametrize("D,B,T,over", CASES)
+def test_psi_grads_raw(cuda, lib, D, B, T, over):
+    ohp, raw, data, model = build(D, B, T, over, cuda)
+    o = PsiCMPSOracle(ohp, raw, mode="f64")
+    gref = grads_of(o, total_loss(o, data))
+    obj = model.loss_fn(data) + regulariser(model)
+    names = ["A", "Rx", "Ry", "freqs_raw", "psi_x", "psi_y"]
+    gs = torch.autograd.grad(obj, [getattr(model, n) for n in names])
+    for n, g in zip(names, gs):
+        r = gref["freqs" if n == "freqs_raw" else n]
+        assert rel(g.cpu().numpy(), r) <= GRAD_TOL, (n, rel(g.cpu().numpy(), r))
+
+
+def test_psi_weighted_grads_effective(cuda, lib):
+    """Packed effective-parameter gradient with non-uniform clip weights."""
+    D, B, T = 8, 4, 300
+    ohp, raw, data, model = build(D, B, T, dict(sigma=0.2, A=5.0), cuda)
+    w = np.array([0.1, 0.4, 0.2, 0.3])
+    o = PsiCMPSOracle(ohp, raw, mode="f64")
+    tot = (o.loss_per_clip(data * 0.3) * torch.tensor(w)).sum()
+    gR, gf, gp, gA = torch.autograd.grad(tot, [o.R, o.freqs, o.psi_0, o.A])
+    lpc = model.loss_per_clip(data * np.float32(0.3))
+    (lpc * torch.tensor(w, dtype=torch.float32, device=cuda)).sum().backward()
+    packed = model._last_packed.cpu().numpy()
+    n = 2 * D * D
+    assert relc(packed[:n].reshape(D, D, 2) @ np.array([1, 1j]), gR.numpy()) <= GRAD_TOL
+    assert rel(packed[n:n + D], gf.numpy()) <= GRAD_TOL
+    assert relc(packed[n + D:n + 3 * D].reshape(D, 2) @ np.array([1, 1j]), gp.numpy()) <= GRAD_TOL
+    assert rel(packed[n + 3 * D], float(gA)) <= GRAD_TOL
+    assert rel(packed[n + 3 * D + 1], float(tot)) <= LOSS_TOL
+
+
+@pytest.mark.parametrize("D,n,L,over", [(2, 2, 512, dict(sigma=1.0, A=1.0)), (7, 5, 256, dict()),
+                                        (32, 3, 400, dict(sigma=0.01)), (64, 2, 100, dict())])
+def test_psi_sample_from_noise(cuda, lib, D, n, L, over):
+    ohp, php = hp_pair(bond_dim=D, **over)
+    if D == 2:  # the reference's two-level system (tests/test_model.py:145-152)
+        R = np.array([[0, 1], [0, 0]], dtype=np.complex64)
+        fr = np.array([10, -10], dtype=np.float32)
+        o = PsiCMPSOracle(ohp, {"psi_x": [0.6, 0.3], "psi_y": [0.1, -0.7]}, R_in=R, freqs_in=fr, mode="f64")
+        model = PsiCMPS(php, R_in=R, freqs_in=fr, device=cuda)
+        set_raw(model, {"psi_x": [0.6, 0.3], "psi_y": [0.1, -0.7]})
+    else:
+        raw = random_raw_params(ohp, np.random.default_rng(3))
+        o = PsiCMPSOracle(ohp, raw, mode="f64")
+        model = PsiCMPS(php, device=cuda)
+        set_raw(model, raw)
+    noise = (np.random.default_rng(2).standard_normal((L, n)) * ohp.sigma * np.sqrt(ohp.delta_t)).astype(np.float32)
+    ref = o.sample_from_noise(noise).detach().numpy()
+    got = model.sample_from_noise(noise).cpu().numpy()
+    assert got.shape == (n, L)
+    assert rel(got, ref) <= SAMPLE_TOL
+
+
+@pytest.mark.parametrize("D,B,T", [(7, 8, 256), (32, 2, 100)])
+def test_psi_evolve(cuda, lib, D, B, T):
+    ohp, raw, data, model = build(D, B, T, dict(), cuda)
+    ref = PsiCMPSOracle(ohp, raw, mode="f64").psi_evolve_with_data(data).detach().numpy()
+    got = model.psi_evolve_with_data(data).cpu().numpy()
+    assert got.shape == (B, T - 1, D)
+    # tests/test_model.py:115-122
+    np.testing.assert_allclose(np.linalg.norm(got, axis=-1), 1.0, rtol=1e-5)
+    assert relc(got, ref) <= 1e-4
+
+
+@pytest.mark.parametrize("D,B,T,over", [(7, 8, 256, dict(h_reg=2 / (np.pi * 16000) ** 2, r_reg=2 / (np.pi * 16000))),
+                                        (8, 3, 500, dict()), (2, 2, 64, dict(sigma=1.0, A=1.0))])
+def test_rho_loss_and_traj(cuda, lib, D, B, T, over):
+    ohp, php = hp_pair(bond_dim=D, minibatch_size=B, **over)
+    raw = random_raw_params(ohp, np.random.default_rng(5), rho=True)
+    data = damped_sine(B, T, ohp.delta_t, np.random.default_rng(6))
+    o = RhoCMPSOracle(ohp, raw, mode="f64")
+    model = RhoCMPS(php, device=cuda)
+    set_raw(model, raw)
+    got = model.loss_per_clip(data).cpu().numpy()
+    ref = o.loss_per_clip(data).detach().numpy()
+    assert rel(got, ref) <= LOSS_TOL
+    tr = model.rho_evolve_with_data(data).cpu().numpy()
+    rt = o.rho_evolve_with_data(data).detach().numpy()
+    assert tr.shape == (B, T - 1, D, D)
+    np.testing.assert_allclose(np.trace(tr, axis1=-2, axis2=-1).real, 1.0, rtol=1e-5)  # tests/test_model.py:50-57
+    assert relc(tr, rt) <= 1e-4
+
+
+def test_rho_sampling(cuda, lib):
+    ohp, php = hp_pair(bond_dim=7)
+    raw = random_raw_params(ohp, np.random.default_rng(7), rho=True)
+    o = RhoCMPSOracle(ohp, raw, mode="f64")
+    model = RhoCMPS(php, device=cuda)
+    set_raw(model, raw)
+    noise = o.make_noise(5, 256, rng=np.random.default_rng(8))
+    s = model.sample_from_noise(noise).cpu().numpy()
+    assert rel(s, o.sample_from_noise(noise).detach().numpy()) <= SAMPLE_TOL
+    tr = model.rho_evolve_with_sampling(5, 256, noise=noise).cpu().numpy()
+    np.testing.assert_allclose(np.trace(tr, axis1=-2, axis2=-1).real, 1.0, rtol=1e-4)  # tests/test_model.py:59-67
+    pu = model.purity(5, 256, noise=noise).cpu().numpy()
+    assert rel(pu, o.purity_from_noise(noise).detach().numpy()) <= 1e-4
