@@ -97,10 +97,11 @@ class _PsiLossFn(torch.autograd.Function):
             # data parallel: ONE all-reduce of the packed effective-parameter gradient
             torch.distributed.all_reduce(packed, op=torch.distributed.ReduceOp.SUM, group=dp)
         model._last_packed = packed
-        gR = packed[: 2 * D * D].view(D, D, 2)
-        gf = packed[2 * D * D: 2 * D * D + D]
-        gp = packed[2 * D * D + D: 2 * D * D + 3 * D].view(D, 2)
-        gA = packed[2 * D * D + 3 * D]
+        # clones: view_as_real's backward needs an even storage offset (odd D breaks a view)
+        gR = packed[: 2 * D * D].view(D, D, 2).clone()
+        gf = packed[2 * D * D: 2 * D * D + D].clone()
+        gp = packed[2 * D * D + D: 2 * D * D + 3 * D].clone().view(D, 2)
+        gA = packed[2 * D * D + 3 * D].clone()
         return gR, gf, gp, gA, None, None
 
 
