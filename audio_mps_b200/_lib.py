@@ -51,6 +51,10 @@ SYMBOLS = {
     "amps_destroy": (C.c_int, [C.c_void_p]),
     "amps_last_error": (C.c_char_p, [C.c_void_p]),
     "amps_launch_count": (C.c_int64, [C.c_void_p]),
+    "amps_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "amps_get_kernel_ms": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
+    "amps_fma_peak_tflops": (C.c_double, [C.c_void_p]),
+    "amps_fma_peak_tflops2": (C.c_double, [C.c_void_p, C.c_int]),
     "amps_psi_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "amps_psi_grad_count": (C.c_size_t, [C.c_int]),
     "amps_psi_loss_fwd": (C.c_int, [C.c_void_p, C.POINTER(AmpsParams), C.c_void_p, C.c_int, C.c_int,
@@ -141,3 +145,14 @@ def check(ctx, rc: int):
 
 def launch_count(device_index: int = 0) -> int:
     return int(load().amps_launch_count(context(device_index)))
+
+
+def set_profiling(device_index: int, enable: bool):
+    check(context(device_index), load().amps_set_profiling(context(device_index), 1 if enable else 0))
+
+
+def kernel_ms(device_index: int, which: int) -> float:
+    ms = C.c_float()
+    h = context(device_index)
+    check(h, load().amps_get_kernel_ms(h, which, C.byref(ms)))
+    return float(ms.value)

@@ -30,6 +30,10 @@ struct amps_ctx {
   void* hbuf = nullptr;
   size_t hbuf_bytes = 0;
   cudaStream_t hstream = nullptr;
+  // optional per-kernel timing (CUDA events on the launch stream)
+  bool prof = false;
+  cudaEvent_t ev[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  bool ev_valid[3] = {false, false, false};
 };
 
 namespace {
@@ -59,6 +63,49 @@ int fail(amps_ctx* ctx, int code, const char* fmt, ...) {
       return fail(ctx, AMPS_E_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); \
     ctx->launches++;                                                                     \
   } while (0)
+
+#define PROF_BEGIN(ctx, which, st)                                        \
+  do {                                                                     \
+    if ((ctx)->prof) cudaEventRecord((ctx)->ev[which][0], st);            \
+  } while (0)
+#define PROF_END(ctx, which, st)                                          \
+  do {                                                                     \
+    if ((ctx)->prof) {                                                     \
+      cudaEventRecord((ctx)->ev[which][1], st);                           \
+      (ctx)->ev_valid[which] = true;                                       \
+    }                                                                      \
+  } while (0)
+
+// FP32 FMA issue-rate microbenchmark: 16 independent chains per thread
+__global__ void fma_peak_kernel(float* out, int iters, float a, float b) {
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = (float)(threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = fmaf(acc[i], a, b);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i];
+  if (s == 123.456f) out[0] = s;  // never true; keeps the chains alive
+}
+
+// same with packed FFMA2 (fma.rn.f32x2): 8 independent packed chains per thread
+__global__ void fma2_peak_kernel(float* out, int iters, float a, float b) {
+  float2 acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = make_float2((float)(threadIdx.x + i), (float)i);
+  const float2 a2 = make_float2(a, a), b2 = make_float2(b, b);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = __ffma2_rn(acc[i], a2, b2);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += acc[i].x + acc[i].y;
+  if (s == 123.456f) out[0] = s;
+}
 
 inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
@@ -217,8 +264,59 @@ int amps_destroy(amps_ctx* ctx) {
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->hbuf) cudaFree(ctx->hbuf);
   if (ctx->hstream) cudaStreamDestroy(ctx->hstream);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 2; ++j)
+      if (ctx->ev[i][j]) cudaEventDestroy(ctx->ev[i][j]);
   delete ctx;
   return AMPS_OK;
+}
+
+int amps_set_profiling(amps_ctx* ctx, int enable) {
+  if (!ctx) return AMPS_E_INVALID;
+  if (enable && !ctx->ev[0][0]) {
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 2; ++j) CUDA_TRY(ctx, cudaEventCreate(&ctx->ev[i][j]));
+  }
+  ctx->prof = enable != 0;
+  return AMPS_OK;
+}
+
+int amps_get_kernel_ms(amps_ctx* ctx, int which, float* ms) {
+  if (!ctx || !ms || which < 0 || which > 2) return AMPS_E_INVALID;
+  if (!ctx->ev_valid[which]) return fail(ctx, AMPS_E_STATE, "no timed launch of kernel %d yet", which);
+  CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev[which][1]));
+  CUDA_TRY(ctx, cudaEventElapsedTime(ms, ctx->ev[which][0], ctx->ev[which][1]));
+  return AMPS_OK;
+}
+
+double amps_fma_peak_tflops(amps_ctx* ctx) { return amps_fma_peak_tflops2(ctx, 0); }
+
+double amps_fma_peak_tflops2(amps_ctx* ctx, int packed) {
+  if (!ctx) return -1.0;
+  cudaEvent_t e0, e1;
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -1.0;
+  float* out = nullptr;
+  if (cudaMalloc(&out, 4) != cudaSuccess) return -1.0;
+  const int iters = 1 << 15, blocks = 148 * 8, threads = 256;
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(e0, 0);
+    if (packed)
+      fma2_peak_kernel<<<blocks, threads>>>(out, iters, 0.999f, 0.001f);
+    else
+      fma_peak_kernel<<<blocks, threads>>>(out, iters, 0.999f, 0.001f);
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ctx->launches++;
+    const double flops = 2.0 * 16.0 * iters * (double)blocks * threads;
+    if (ms > 0.f && rep > 0) best = flops / (ms * 1e-3) / 1e12 > best ? flops / (ms * 1e-3) / 1e12 : best;
+  }
+  cudaFree(out);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return best;
 }
 
 const char* amps_last_error(const amps_ctx* ctx) { return ctx ? ctx->err : "null context"; }
@@ -258,11 +356,13 @@ int amps_psi_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
     auto kern = psi_fwd_kernel<DPc, NQc>;
     const size_t smem = sizeof(FwdSmem<DPc>);
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PROF_BEGIN(ctx, 0, st);
     kern<<<B, DPc * NQc, smem, st>>>(
         (const float2*)(ws + L.matN), (const float2*)(ws + L.matR), (const float2*)(ws + L.matS),
         (const float2*)(ws + L.qtab), (const float2*)(ws + L.psi0p), x_dev, T, p->A, loss_dev,
         (double*)(ws + L.lossd), save ? (float2*)(ws + L.traj) : nullptr,
         save ? (float*)(ws + L.scales) : nullptr, nchunks);
+    PROF_END(ctx, 0, st);
     LAUNCH_CHECK(ctx, "psi_fwd_kernel");
     return AMPS_OK;
   });
@@ -297,11 +397,13 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
     auto kern = psi_bwd_kernel<DPc, NQc>;
     const size_t smem = sizeof(BwdSmem<DPc>);
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PROF_BEGIN(ctx, 1, st);
     kern<<<B, DPc * NQc, smem, st>>>(
         (const float2*)(ws + L.matN), (const float2*)(ws + L.matRH), (const float2*)(ws + L.matS),
         (const float2*)(ws + L.qtab), ctx->ttab, x_dev, T, p->A, w_dev,
         (const float2*)(ws + L.traj), (const float*)(ws + L.scales), nchunks,
         (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0), (double*)(ws + L.gAdir));
+    PROF_END(ctx, 1, st);
     LAUNCH_CHECK(ctx, "psi_bwd_kernel");
     return AMPS_OK;
   });
@@ -343,9 +445,11 @@ int amps_psi_sample(amps_ctx* ctx, const amps_params* p, const float* noise_dev,
     auto kern = psi_sample_kernel<DPc, NQc>;
     const size_t smem = sizeof(SampleSmem<DPc>);
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PROF_BEGIN(ctx, 2, st);
     kern<<<n, DPc * NQc, smem, st>>>((const float2*)(ws + L.matN), (const float2*)(ws + L.matR),
                                      (const float2*)(ws + L.qtab), (const float2*)(ws + L.psi0p),
                                      noise_dev, L_, n, p->A, (float)p->delta_t, out_dev);
+    PROF_END(ctx, 2, st);
     LAUNCH_CHECK(ctx, "psi_sample_kernel");
     return AMPS_OK;
   });

@@ -1,7 +1,7 @@
 // PsiCMPS scan kernels (sm_100a): sequential persistent forward-loss kernel, adjoint backward,
 // sampler.  One CTA owns one clip for the whole clip; the step operators live in registers,
-// the state in shared memory, the waveform / phase table stream in through double-buffered
-// cp.async.
+// the state in shared memory, the waveform / phase table / trajectory stream in through
+// multi-buffered cp.async.
 //
 // Formulation (validated against the op-for-op oracle, see DESIGN.md "Chain form"):
 // in the interaction frame x_k = psi_k * conj(p_k) the reference step (model.py:276-334) is
@@ -11,41 +11,50 @@
 //     x_{k+1} = q_k * x'_k (* c),             q_k = p_k conj(p_{k+1})
 // with p_k = exp(i fl32(f t_k)) and t_k the float32 running sum.  The state is carried
 // UN-normalised (the loss is scale invariant) and rescaled by c once per chunk, so the only
-// thing on the per-step critical path is one stacked [N;R] mat-vec; E_k, |x_k|^2, the log and
-// the rescale are done lane-parallel over the CH steps of a chunk.
+// thing on the per-step critical path is one stacked [N;R] mat-vec.  Everything that does not
+// feed the next state (E_k, |x_k|^2, the log, the parameter-gradient tiles) is software-pipelined
+// into the same loop one step (or one chunk) behind, where it fills the issue slots the
+// latency-bound chain leaves empty, or is done lane-parallel over the CH steps of a chunk.
 #pragma once
+#include <type_traits>
+
 #include "amps_common.cuh"
 
 namespace amps {
+
+using TrueT = std::true_type;
+using FalseT = std::false_type;
 
 // -------------------------------------------------------------------------------------------
 // shared-memory layouts
 // -------------------------------------------------------------------------------------------
 template <int DP>
 struct alignas(16) FwdSmem {
-  float2 xs[CH + 1][DP];   // x_{k0+kk}
-  float2 xps[CH][DP];      // x'_{k0+kk}
-  float2 qs[2][CH][DP];    // q_k, double buffered
-  float es[CH][DP + 1];    // Re(conj(x'_i) (S x')_i)
-  float ns[CH][DP + 1];    // |x_{k,i}|^2
-  float wav[2][CH + 4];    // waveform samples k0..k0+len, double buffered
-  float sv[CH];            // s_k
-  float incv[CH];          // inc_k
-  float scal[4];
+  float2 xs[CH + 1][DP];     // x_{k0+kk}
+  float2 xps[CH][DP];        // x'_{k0+kk}
+  float2 qs[2][CH][DP];      // q_k, double buffered
+  float es[CH][DP + 1];      // Re(conj(x'_i) (S x')_i)
+  float ns[2][CH + 1][DP + 1];  // |x_{k,i}|^2, chunk parity (row 0 of the next chunk is written early)
+  float wav[2][CH + 4];      // waveform samples k0..k0+len, double buffered
+  float sv[2][CH];           // s_k
+  float incv[2][CH];         // inc_k
+  double lred[32];
 };
 
 template <int DP>
 struct alignas(16) BwdSmem {
-  float2 xs[2][CH + 1][DP];  // trajectory chunk, double buffered
-  float2 qs[2][CH][DP];
-  float2 xps[CH][DP];        // reconstructed x'_k
-  float2 sps[CH][DP];        // S x'_k
+  float2 xs[3][CH + 1][DP];  // trajectory chunk, triple buffered (chunk c, c-1 in use, c-2 landing)
+  float2 qs[3][CH][DP];
+  float2 xps[2][CH][DP];     // reconstructed x'_k      (chunk c and, being prepared, c-1)
+  float2 sps[2][CH][DP];     // S x'_k
   float2 mus[CH][DP];        // adjoint of x'_k
   float es[CH][DP + 1];
   float ns[CH][DP + 1];
-  float wav[2][CH + 4];
-  float tt[2][CH + 4];
-  float sv[CH], incv[CH], dtk[CH], alphas[CH], betas[CH];
+  float wav[3][CH + 4];
+  float tt[3][CH + 4];
+  float scs[3][4];
+  float sv[2][CH], incv[2][CH], dtk[2][CH], alphas[2][CH], betas[2][CH];
+  double lred[32];
 };
 
 template <int DP>
@@ -57,21 +66,30 @@ struct alignas(16) SampleSmem {
   float wred[2][32][2];
 };
 
-// -------------------------------------------------------------------------------------------
-// P2: for every step of the chunk, (S x')_i and e_i = Re(conj(x'_i) (S x')_i)
-// -------------------------------------------------------------------------------------------
-template <int DP, int NQ, bool STORE_SP>
-__device__ __forceinline__ void chunk_expectation(const float2 (&Sr)[DP / NQ],
-                                                  const float2 (*xps)[DP], float2 (*sps)[DP],
-                                                  float (*es)[DP + 1], int len, int i, int jq) {
-  for (int kk = 0; kk < len; ++kk) {
-    float2 part = matvec1<DP, NQ>(Sr, xps[kk], jq);
-    part = group_sum<NQ>(part);
-    if (STORE_SP && jq == 0) sps[kk][i] = part;
-    if (jq == 1) {
-      const float2 xpi = xps[kk][i];
-      es[kk][i] = fmaf(xpi.x, part.x, xpi.y * part.y);
+// Per-step scalars, lane-parallel over the chunk: G = NT/32 threads share one step, each sums
+// DP/G entries of es / ns, finished with xor-shuffles.  Returns (sum es, sum ns) on every thread
+// of the group; kk is the step this thread works on.
+template <int DP, int NT>
+__device__ __forceinline__ void chunk_scalars(const float (*es)[DP + 1], const float (*ns)[DP + 1],
+                                              int len, int t, int& kk, bool& leader, float& en,
+                                              float& nu2) {
+  constexpr int G = NT / 32, PER = DP / G;
+  kk = t / G;
+  const int g = t % G;
+  leader = (g == 0) && (kk < len);
+  en = 0.f;
+  nu2 = 0.f;
+  if (kk < len) {
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+      en += es[kk][g * PER + r];
+      nu2 += ns[kk][g * PER + r];
     }
+  }
+#pragma unroll
+  for (int m = 1; m < G; m <<= 1) {
+    en += __shfl_xor_sync(0xffffffffu, en, m);
+    nu2 += __shfl_xor_sync(0xffffffffu, nu2, m);
   }
 }
 
@@ -88,6 +106,7 @@ __global__ void __launch_bounds__(DP* NQ)
   using M = Map<DP, NQ>;
   constexpr int NT = M::NT;
   constexpr int CPT = M::CPT;
+  constexpr int NP = M::NP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FwdSmem<DP>& sm = *reinterpret_cast<FwdSmem<DP>*>(smem_raw);
 
@@ -104,6 +123,7 @@ __global__ void __launch_bounds__(DP* NQ)
   if (t < DP) {
     const float2 p = psi0p[t];
     sm.xs[0][t] = p;
+    sm.ns[0][0][t] = cabs2(p);
     if (traj) traj[(size_t)b * T * DP + t] = p;
   }
 
@@ -115,10 +135,22 @@ __global__ void __launch_bounds__(DP* NQ)
     for (int idx = t; idx < len * DP / 2; idx += NT) cp_async16(qdst + 2 * idx, qsrc + 2 * idx);
     for (int idx = t; idx <= len; idx += NT) cp_async4(&sm.wav[buf][idx], xb + k0 + idx);
   };
+  auto compute_s = [&](int buf, int len) {
+    if (t < len) {
+      const float inc = sm.wav[buf][t + 1] - sm.wav[buf][t];   // model.py:263
+      sm.incv[buf][t] = inc;
+      sm.sv[buf][t] = inc / A;                                  // model.py:303
+    }
+  };
 
   double lossacc = 0.0;
-  if (nchunks > 0) issue_loads(0, 0);
-  cp_async_commit();
+  if (nchunks > 0) {
+    issue_loads(0, 0);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    compute_s(0, min(CH, nsteps));
+  }
 
   for (int c = 0; c < nchunks; ++c) {
     const int buf = c & 1;
@@ -126,81 +158,108 @@ __global__ void __launch_bounds__(DP* NQ)
     const int len = min(CH, nsteps - k0);
     if (c + 1 < nchunks) issue_loads(c + 1, buf ^ 1);
     cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
+    __syncthreads();  // (D) sv/incv, xs[0], ns[0] of this chunk visible; last chunk's flush done
 
-    if (t < len) {
-      const float inc = sm.wav[buf][t + 1] - sm.wav[buf][t];   // model.py:263
-      sm.incv[t] = inc;
-      sm.sv[t] = inc / A;                                       // model.py:303
-    }
-    if (t < DP) sm.ns[0][t] = cabs2(sm.xs[0][t]);
-    __syncthreads();
-
-    // ---- sequential chain: one stacked [N;R] mat-vec per step on the critical path --------
-    for (int kk = 0; kk < len; ++kk) {
-      float2 a, y;
-      matvec2<DP, NQ>(Nr, Rr, sm.xs[kk], jq, a, y);
-      a = group_sum<NQ>(a);
-      y = group_sum<NQ>(y);
-      const float s = sm.sv[kk];
-      const float2 xp = make_float2(fmaf(s, y.x, a.x), fmaf(s, y.y, a.y));
-      const float2 xn = cmul(sm.qs[buf][kk][i], xp);
+    float2 xp_prev = make_float2(0.f, 0.f);
+    // One step of the chain (critical path) with the expectation mat-vec of the PREVIOUS step
+    // software-pipelined into it.
+    auto step = [&](auto first_tag, int kk) {
+      constexpr bool FIRST = decltype(first_tag)::value;
+      const float s = sm.sv[buf][kk];
+      const float2 q = sm.qs[buf][kk][i];
+      float2 a0 = make_float2(0.f, 0.f), a1 = a0, y0 = a0, y1 = a0, p0 = a0, p1 = a0;
+#pragma unroll
+      for (int m = 0; m < NP; ++m) {
+        const float4 xv = *reinterpret_cast<const float4*>(&sm.xs[kk][2 * NQ * m + 2 * jq]);
+        const float2 x0 = make_float2(xv.x, xv.y), x1 = make_float2(xv.z, xv.w);
+        cmac(a0, Nr[2 * m], x0);
+        cmac(a1, Nr[2 * m + 1], x1);
+        cmac(y0, Rr[2 * m], x0);
+        cmac(y1, Rr[2 * m + 1], x1);
+        if (!FIRST) {
+          const float4 pv = *reinterpret_cast<const float4*>(&sm.xps[kk - 1][2 * NQ * m + 2 * jq]);
+          cmac(p0, Sr[2 * m], make_float2(pv.x, pv.y));
+          cmac(p1, Sr[2 * m + 1], make_float2(pv.z, pv.w));
+        }
+      }
+      float2 xp = make_float2(fmaf(s, y0.x + y1.x, a0.x + a1.x), fmaf(s, y0.y + y1.y, a0.y + a1.y));
+      float e = 0.f;
+      if (!FIRST) e = fmaf(xp_prev.x, p0.x + p1.x, xp_prev.y * (p0.y + p1.y));
+#pragma unroll
+      for (int m = 1; m < NQ; m <<= 1) {
+        xp.x += __shfl_xor_sync(0xffffffffu, xp.x, m);
+        xp.y += __shfl_xor_sync(0xffffffffu, xp.y, m);
+        if (!FIRST) e += __shfl_xor_sync(0xffffffffu, e, m);
+      }
+      const float2 xn = cmul(q, xp);
       if (jq == 0) sm.xs[kk + 1][i] = xn;
       if (jq == 1) sm.xps[kk][i] = xp;
-      if (jq == 2 && kk + 1 < CH) sm.ns[kk + 1][i] = cabs2(xn);
+      if (jq == 2) sm.ns[buf][kk + 1][i] = cabs2(xn);
+      if (!FIRST && jq == 3) sm.es[kk - 1][i] = e;
+      xp_prev = xp;
       __syncthreads();
-    }
+    };
 
-    // ---- lane-parallel part: E_k for every step of the chunk ------------------------------
-    chunk_expectation<DP, NQ, false>(Sr, sm.xps, nullptr, sm.es, len, i, jq);
-    __syncthreads();
-    if (warp == 0) {
-      const int kk = lane;
-      if (kk < len) {
-        float en = 0.f, nu2 = 0.f;
-#pragma unroll 8
-        for (int r = 0; r < DP; ++r) {
-          en += sm.es[kk][r];
-          nu2 += sm.ns[kk][r];
-        }
-        const float E = en / nu2;                                // model.py:324-325 on x'
-        const float z = (E * sm.incv[kk]) / A;                   // model.py:294
-        lossacc -= log1p((double)z);
-      }
-      // rescale factor from |x_{k0+len}|^2
-      float n2 = 0.f;
-      for (int r = lane; r < DP; r += 32) n2 += cabs2(sm.xs[len][r]);
-      n2 = warp_sum_f(n2);
-      if (lane == 0) sm.scal[0] = rsqrtf(n2);
+    step(TrueT{}, 0);
+    if (len == CH) {
+#pragma unroll 2
+      for (int kk = 1; kk < CH; ++kk) step(FalseT{}, kk);
+    } else {
+      for (int kk = 1; kk < len; ++kk) step(FalseT{}, kk);
     }
-    __syncthreads();
-    const float sc = sm.scal[0];
+    {  // expectation of the chunk's last step
+      const float2 part = matvec1<DP, NQ>(Sr, sm.xps[len - 1], jq);
+      float e = fmaf(xp_prev.x, part.x, xp_prev.y * part.y);
+#pragma unroll
+      for (int m = 1; m < NQ; m <<= 1) e += __shfl_xor_sync(0xffffffffu, e, m);
+      if (jq == 3) sm.es[len - 1][i] = e;
+    }
+    cp_async_wait<0>();
+    __syncthreads();  // (A)
+
+    {  // per-step scalars, lane-parallel over the chunk
+      int kk;
+      bool leader;
+      float en, nu2;
+      chunk_scalars<DP, NT>(sm.es, sm.ns[buf], len, t, kk, leader, en, nu2);
+      if (leader) {
+        const float E = en / nu2;                                  // model.py:324-325 on x'
+        const float z = (E * sm.incv[buf][kk]) / A;                // model.py:294
+        lossacc -= (double)log1pf(z);
+      }
+    }
+    if (c + 1 < nchunks) compute_s(buf ^ 1, min(CH, nsteps - (k0 + CH)));
+    // rescale by 1/|x_{k0+len}| (every warp computes the norm redundantly: no extra barrier)
+    float n2 = 0.f;
+    for (int r = lane; r < DP; r += 32) n2 += sm.ns[buf][len][r];
+    n2 = warp_sum_f(n2);
+    const float sc = rsqrtf(n2);
     if (t < DP) {
       float2 v = sm.xs[len][t];
       v.x *= sc;
       v.y *= sc;
       sm.xs[len][t] = v;
+      sm.xs[0][t] = v;
+      sm.ns[buf ^ 1][0][t] = cabs2(v);
     }
     if (t == 0 && scales) scales[(size_t)b * nchunks + c] = sc;
-    __syncthreads();
     if (traj) {
+      __syncthreads();  // (B) scaled x_{k0+len} visible
       const float4* src = reinterpret_cast<const float4*>(&sm.xs[1][0]);
       float4* dst = reinterpret_cast<float4*>(traj + ((size_t)b * T + k0 + 1) * DP);
       for (int idx = t; idx < len * DP / 2; idx += NT) dst[idx] = src[idx];
-      __syncthreads();
     }
-    if (t < DP) sm.xs[0][t] = sm.xs[len][t];
-    // the __syncthreads after the next cp.async wait orders this write before its readers
   }
-  cp_async_wait<0>();
 
-  if (warp == 0) {
-    lossacc = warp_sum_d(lossacc);
-    if (lane == 0) {
-      loss[b] = (float)lossacc;
-      if (lossd) lossd[b] = lossacc;
-    }
+  // block reduction of the per-thread loss partials
+  lossacc = warp_sum_d(lossacc);
+  if (lane == 0) sm.lred[warp] = lossacc;
+  __syncthreads();
+  if (t == 0) {
+    double tot = 0.0;
+    for (int wv = 0; wv < NT / 32; ++wv) tot += sm.lred[wv];
+    loss[b] = (float)tot;
+    if (lossd) lossd[b] = tot;
   }
 }
 
@@ -208,6 +267,11 @@ __global__ void __launch_bounds__(DP* NQ)
 // K2: adjoint backward over the stored trajectory (replaces tf.gradients for train.py:89)
 //   per-clip outputs: G[b][0]=sum_k s_k mu_k x_k^dag, G[b][1]=sum_k mu_k x_k^dag,
 //                     G[b][2]=sum_k alpha_k x'_k x'_k^dag,  gf[b], lam0[b], gAdir[b]
+// Adjoint recursion (DESIGN.md "Adjoint"), k descending, lam = adjoint of x_{k+1}:
+//     mu_k  = c_k conj(q_k) lam + alpha_k S x'_k          alpha_k = 2 gE_k / |x_k|^2
+//     lam   = N mu_k + s_k R^dag mu_k + beta_k x_k        beta_k  = -alpha_k E_k
+// Pipeline per loop iteration kk of chunk c: chain step kk (critical path), the rank-1 tile
+// updates of step kk+1, and the S x' mat-vec of step kk of chunk c-1.
 // -------------------------------------------------------------------------------------------
 template <int DP, int NQ>
 __global__ void __launch_bounds__(DP* NQ)
@@ -221,6 +285,7 @@ __global__ void __launch_bounds__(DP* NQ)
   using M = Map<DP, NQ>;
   constexpr int NT = M::NT;
   constexpr int CPT = M::CPT;
+  constexpr int NP = M::NP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdSmem<DP>& sm = *reinterpret_cast<BwdSmem<DP>*>(smem_raw);
 
@@ -240,122 +305,119 @@ __global__ void __launch_bounds__(DP* NQ)
 #pragma unroll
   for (int c = 0; c < CPT; ++c) GR[c] = GN[c] = GE[c] = make_float2(0.f, 0.f);
 
-  auto issue_loads = [&](int c, int buf) {
+  auto chunk_len = [&](int c) { return min(CH, nsteps - c * CH); };
+
+  auto issue_loads = [&](int c) {
+    const int lb = c % 3;
     const int k0 = c * CH;
-    const int len = min(CH, nsteps - k0);
+    const int len = chunk_len(c);
     const float2* xsrc = trb + (size_t)k0 * DP;
-    float2* xdst = &sm.xs[buf][0][0];
+    float2* xdst = &sm.xs[lb][0][0];
     for (int idx = t; idx < (len + 1) * DP / 2; idx += NT) cp_async16(xdst + 2 * idx, xsrc + 2 * idx);
     const float2* qsrc = qtab + (size_t)k0 * DP;
-    float2* qdst = &sm.qs[buf][0][0];
+    float2* qdst = &sm.qs[lb][0][0];
     for (int idx = t; idx < len * DP / 2; idx += NT) cp_async16(qdst + 2 * idx, qsrc + 2 * idx);
     for (int idx = t; idx <= len; idx += NT) {
-      cp_async4(&sm.wav[buf][idx], xb + k0 + idx);
-      cp_async4(&sm.tt[buf][idx], ttab + k0 + idx);
+      cp_async4(&sm.wav[lb][idx], xb + k0 + idx);
+      cp_async4(&sm.tt[lb][idx], ttab + k0 + idx);
+    }
+    if (t == 0) cp_async4(&sm.scs[lb][0], scales + (size_t)b * nchunks + c);
+  };
+
+  // P0 + P1 of chunk c: s, inc, dt; x'_k = conj(q_k) x_{k+1} / c_k ; |x_k|^2
+  auto prep_elementwise = [&](int c) {
+    const int lb = c % 3, ds = c & 1, len = chunk_len(c);
+    if (t < len) {
+      const float inc = sm.wav[lb][t + 1] - sm.wav[lb][t];
+      sm.incv[ds][t] = inc;
+      sm.sv[ds][t] = inc / A;
+      sm.dtk[ds][t] = sm.tt[lb][t + 1] - sm.tt[lb][t];
+    }
+    const float inv_sc = 1.0f / sm.scs[lb][0];
+    for (int idx = t; idx < len * DP; idx += NT) {
+      const int kk = idx / DP, r = idx % DP;
+      float2 xp = cmul_ca(sm.qs[lb][kk][r], sm.xs[lb][kk + 1][r]);
+      if (kk == len - 1) {
+        xp.x *= inv_sc;
+        xp.y *= inv_sc;
+      }
+      sm.xps[ds][kk][r] = xp;
+      sm.ns[kk][r] = cabs2(sm.xs[lb][kk][r]);
+    }
+  };
+  // P2 of one step: S x' (stored) and e_i
+  auto expectation_step = [&](int ds, int kk) {
+    float2 part = matvec1<DP, NQ>(Sr, sm.xps[ds][kk], jq);
+    part = group_sum<NQ>(part);
+    if (jq == 0) sm.sps[ds][kk][i] = part;
+    if (jq == 1) {
+      const float2 xpi = sm.xps[ds][kk][i];
+      sm.es[kk][i] = fmaf(xpi.x, part.x, xpi.y * part.y);
+    }
+  };
+  double gAacc = 0.0;
+  // P3 of chunk c: alpha_k, beta_k and the direct dL/dA term
+  auto prep_scalars = [&](int c) {
+    const int ds = c & 1, len = chunk_len(c);
+    int kk;
+    bool leader;
+    float en, nu2;
+    chunk_scalars<DP, NT>(sm.es, sm.ns, len, t, kk, leader, en, nu2);
+    if (leader) {
+      const float E = en / nu2;
+      const float inc = sm.incv[ds][kk];
+      const float arg = 1.0f + (E * inc) / A;
+      const float gE = wb * (-sm.sv[ds][kk] / arg);
+      const float alpha = 2.0f * gE / nu2;
+      sm.alphas[ds][kk] = alpha;
+      sm.betas[ds][kk] = -alpha * E;
+      gAacc += (double)wb * (double)E * (double)inc / ((double)A * (double)A * (double)arg);
     }
   };
 
   float2 lam = make_float2(0.f, 0.f);  // adjoint of x_{k+1}, replicated over the NQ lanes
   float gf = 0.f;
-  double gAacc = 0.0;
 
-  if (nchunks > 0) issue_loads(nchunks - 1, (nchunks - 1) & 1);
-  cp_async_commit();
-
-  for (int c = nchunks - 1; c >= 0; --c) {
-    const int buf = c & 1;
-    const int k0 = c * CH;
-    const int len = min(CH, nsteps - k0);
-    if (c > 0) issue_loads(c - 1, buf ^ 1);
+  if (nchunks > 0) {
+    const int cl = nchunks - 1;
+    issue_loads(cl);
+    cp_async_commit();
+    if (cl >= 1) issue_loads(cl - 1);
     cp_async_commit();
     cp_async_wait<1>();
     __syncthreads();
-
-    const float sc = scales[(size_t)b * nchunks + c];
-    const float inv_sc = 1.0f / sc;
-
-    if (t < len) {
-      const float inc = sm.wav[buf][t + 1] - sm.wav[buf][t];
-      sm.incv[t] = inc;
-      sm.sv[t] = inc / A;
-      sm.dtk[t] = sm.tt[buf][t + 1] - sm.tt[buf][t];
-    }
-    // P1: x'_k = conj(q_k) x_{k+1} / c_k ; |x_k|^2
-    for (int idx = t; idx < len * DP; idx += NT) {
-      const int kk = idx / DP, r = idx % DP;
-      float2 xp = cmul_ca(sm.qs[buf][kk][r], sm.xs[buf][kk + 1][r]);
-      if (kk == len - 1) {
-        xp.x *= inv_sc;
-        xp.y *= inv_sc;
-      }
-      sm.xps[kk][r] = xp;
-      sm.ns[kk][r] = cabs2(sm.xs[buf][kk][r]);
-    }
+    prep_elementwise(cl);
     __syncthreads();
-    // P2: S x' and e_i
-    chunk_expectation<DP, NQ, true>(Sr, sm.xps, sm.sps, sm.es, len, i, jq);
+    for (int kk = 0; kk < chunk_len(cl); ++kk) expectation_step(cl & 1, kk);
     __syncthreads();
-    // P3: per-step scalars
-    if (warp == 0) {
-      const int kk = lane;
-      if (kk < len) {
-        float en = 0.f, nu2 = 0.f;
-#pragma unroll 8
-        for (int r = 0; r < DP; ++r) {
-          en += sm.es[kk][r];
-          nu2 += sm.ns[kk][r];
-        }
-        const float E = en / nu2;
-        const float inc = sm.incv[kk];
-        const float arg = 1.0f + (E * inc) / A;
-        const float gE = wb * (-sm.sv[kk] / arg);
-        const float alpha = 2.0f * gE / nu2;
-        sm.alphas[kk] = alpha;
-        sm.betas[kk] = -alpha * E;
-        gAacc += (double)wb * (double)E * (double)inc / ((double)A * (double)A * (double)arg);
-      }
-    }
-    __syncthreads();
+    prep_scalars(cl);
+  }
 
-    // ---- sequential adjoint chain ---------------------------------------------------------
-    for (int kk = len - 1; kk >= 0; --kk) {
-      const float2 q = sm.qs[buf][kk][i];
-      const float2 xn = sm.xs[buf][kk + 1][i];
-      gf = fmaf(sm.dtk[kk], lam.x * xn.y - lam.y * xn.x, gf);   // Im(conj(lam) x_{k+1})
-      float2 mu = cmul_ca(q, lam);
-      if (kk == len - 1) {
-        mu.x *= sc;
-        mu.y *= sc;
-      }
-      const float al = sm.alphas[kk];
-      const float2 sp = sm.sps[kk][i];
-      mu.x = fmaf(al, sp.x, mu.x);
-      mu.y = fmaf(al, sp.y, mu.y);
-      if (jq == 0) sm.mus[kk][i] = mu;
-      __syncthreads();
-      float2 a, h;
-      matvec2<DP, NQ>(Nr, Hr, sm.mus[kk], jq, a, h);
-      a = group_sum<NQ>(a);
-      h = group_sum<NQ>(h);
-      const float s = sm.sv[kk];
-      const float be = sm.betas[kk];
-      const float2 xk = sm.xs[buf][kk][i];
-      lam.x = fmaf(be, xk.x, fmaf(s, h.x, a.x));
-      lam.y = fmaf(be, xk.y, fmaf(s, h.y, a.y));
-    }
+  for (int c = nchunks - 1; c >= 0; --c) {
+    const int lb = c % 3, ds = c & 1;
+    const int len = chunk_len(c);
+    const bool has_prev = c >= 1;
+    const int pds = ds ^ 1;
+    if (c >= 2) issue_loads(c - 2);
+    cp_async_commit();
+    cp_async_wait<1>();   // chunk c-1 has landed
+    __syncthreads();      // (T1)
+    if (has_prev) prep_elementwise(c - 1);
+    __syncthreads();      // (T2)
+    const float sc = sm.scs[lb][0];
 
-    // ---- parameter-gradient tiles (rank-1 updates, lane-parallel over the chunk) ----------
-    for (int kk = 0; kk < len; ++kk) {
-      const float2 mui = sm.mus[kk][i];
-      const float2 xpi = sm.xps[kk][i];
-      const float s = sm.sv[kk];
-      const float al = sm.alphas[kk];
+    float2 mu_prev = make_float2(0.f, 0.f);
+    // tile update of step kk (its mu is mu_i, row values replicated in the group)
+    auto tiles = [&](int kk, float2 mui) {
+      const float2 xpi = sm.xps[ds][kk][i];
+      const float s = sm.sv[ds][kk];
+      const float al = sm.alphas[ds][kk];
       const float2 u1 = make_float2(s * mui.x, s * mui.y);
       const float2 u3 = make_float2(al * xpi.x, al * xpi.y);
 #pragma unroll
-      for (int m = 0; m < CPT / 2; ++m) {
-        const float4 xv = *reinterpret_cast<const float4*>(&sm.xs[buf][kk][2 * NQ * m + 2 * jq]);
-        const float4 pv = *reinterpret_cast<const float4*>(&sm.xps[kk][2 * NQ * m + 2 * jq]);
+      for (int m = 0; m < NP; ++m) {
+        const float4 xv = *reinterpret_cast<const float4*>(&sm.xs[lb][kk][2 * NQ * m + 2 * jq]);
+        const float4 pv = *reinterpret_cast<const float4*>(&sm.xps[ds][kk][2 * NQ * m + 2 * jq]);
         const float2 x0 = make_float2(xv.x, xv.y), x1 = make_float2(xv.z, xv.w);
         const float2 p0 = make_float2(pv.x, pv.y), p1 = make_float2(pv.z, pv.w);
         cmac_cx(GR[2 * m], u1, x0);
@@ -365,8 +427,51 @@ __global__ void __launch_bounds__(DP* NQ)
         cmac_cx(GE[2 * m], u3, p0);
         cmac_cx(GE[2 * m + 1], u3, p1);
       }
+    };
+
+    auto step = [&](auto first_tag, auto prev_tag, int kk) {
+      constexpr bool FIRST = decltype(first_tag)::value;   // first iteration of the chunk
+      constexpr bool PREV = decltype(prev_tag)::value;     // chunk c-1 exists and has step kk
+      const float2 q = sm.qs[lb][kk][i];
+      const float2 xn = sm.xs[lb][kk + 1][i];
+      gf = fmaf(sm.dtk[ds][kk], lam.x * xn.y - lam.y * xn.x, gf);   // Im(conj(lam) x_{k+1})
+      float2 mu = cmul_ca(q, lam);
+      if (FIRST) {
+        mu.x *= sc;
+        mu.y *= sc;
+      }
+      const float al = sm.alphas[ds][kk];
+      const float2 sp = sm.sps[ds][kk][i];
+      mu.x = fmaf(al, sp.x, mu.x);
+      mu.y = fmaf(al, sp.y, mu.y);
+      if (jq == 0) sm.mus[kk][i] = mu;
+      __syncthreads();
+      float2 a, h;
+      matvec2<DP, NQ>(Nr, Hr, sm.mus[kk], jq, a, h);
+      const float s = sm.sv[ds][kk];
+      float2 lp = make_float2(fmaf(s, h.x, a.x), fmaf(s, h.y, a.y));
+      if (!FIRST) tiles(kk + 1, mu_prev);
+      if (PREV) expectation_step(pds, kk);
+      lp = group_sum<NQ>(lp);
+      const float be = sm.betas[ds][kk];
+      const float2 xk = sm.xs[lb][kk][i];
+      lam.x = fmaf(be, xk.x, lp.x);
+      lam.y = fmaf(be, xk.y, lp.y);
+      mu_prev = mu;
+    };
+
+    if (has_prev) {
+      step(TrueT{}, TrueT{}, len - 1);
+      for (int kk = len - 2; kk >= 0; --kk) step(FalseT{}, TrueT{}, kk);
+      // chunk c-1 is always full; finish its expectation steps if this chunk was short
+      for (int kk = len; kk < CH; ++kk) expectation_step(pds, kk);
+    } else {
+      step(TrueT{}, FalseT{}, len - 1);
+      for (int kk = len - 2; kk >= 0; --kk) step(FalseT{}, FalseT{}, kk);
     }
-    __syncthreads();
+    tiles(0, mu_prev);
+    __syncthreads();      // (E1) es / sps of chunk c-1 complete; mus free
+    if (has_prev) prep_scalars(c - 1);
   }
   cp_async_wait<0>();
 
@@ -383,9 +488,13 @@ __global__ void __launch_bounds__(DP* NQ)
     gfout[(size_t)b * DP + i] = gf;
     lam0out[(size_t)b * DP + i] = lam;
   }
-  if (warp == 0) {
-    gAacc = warp_sum_d(gAacc);
-    if (lane == 0) gAdir[b] = gAacc;
+  gAacc = warp_sum_d(gAacc);
+  if (lane == 0) sm.lred[warp] = gAacc;
+  __syncthreads();
+  if (t == 0) {
+    double tot = 0.0;
+    for (int wv = 0; wv < NT / 32; ++wv) tot += sm.lred[wv];
+    gAdir[b] = tot;
   }
 }
 

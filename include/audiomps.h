@@ -67,6 +67,17 @@ const char* amps_last_error(const amps_ctx* ctx);
 /* number of kernels the context has launched so far (bench.py's gpu_launches evidence) */
 int64_t amps_launch_count(const amps_ctx* ctx);
 
+/* ---- measurement helpers (bench.py) ------------------------------------------------------ */
+/* When enabled, the context brackets the dominant kernel of each entry point with CUDA events on
+ * the launch stream; amps_get_kernel_ms(which: 0 = psi forward, 1 = psi backward, 2 = psi sampler)
+ * synchronises on the stop event and returns the last launch's duration. */
+int amps_set_profiling(amps_ctx* ctx, int enable);
+int amps_get_kernel_ms(amps_ctx* ctx, int which, float* ms);
+/* FP32 FMA issue-rate microbenchmark on the context's device (dense FFMA chains, best of 5). */
+double amps_fma_peak_tflops(amps_ctx* ctx);
+/* packed != 0: the same chains issued as FFMA2 (fma.rn.f32x2). */
+double amps_fma_peak_tflops2(amps_ctx* ctx, int packed);
+
 /* ---- PsiCMPS --------------------------------------------------------------------------- */
 
 /* bytes of caller-owned workspace for the Psi loss forward/backward at (D, B clips, T samples).
