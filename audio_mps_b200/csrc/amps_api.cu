@@ -353,11 +353,12 @@ int amps_psi_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
   if (rc) return rc;
   return dispatch_dp(DP, [&](auto dp, auto nq) -> int {
     constexpr int DPc = decltype(dp)::value, NQc = decltype(nq)::value;
-    auto kern = psi_fwd_kernel<DPc, NQc>;
-    const size_t smem = sizeof(FwdSmem<DPc>);
+    constexpr bool WS = DPc <= 32;   // warp-specialised chain/filler kernel
+    auto kern = WS ? psi_fwd_kernel<DPc, NQc> : psi_fwd_uni_kernel<DPc, NQc>;
+    const size_t smem = WS ? sizeof(FwdSmem<DPc, NQc>) : sizeof(FwdSmemUni<DPc, NQc>);
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PROF_BEGIN(ctx, 0, st);
-    kern<<<B, DPc * NQc, smem, st>>>(
+    kern<<<B, (WS ? 2 : 1) * DPc * NQc, smem, st>>>(
         (const float2*)(ws + L.matN), (const float2*)(ws + L.matR), (const float2*)(ws + L.matS),
         (const float2*)(ws + L.qtab), (const float2*)(ws + L.psi0p), x_dev, T, p->A, loss_dev,
         (double*)(ws + L.lossd), save ? (float2*)(ws + L.traj) : nullptr,
@@ -394,11 +395,12 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
   if (!ctx->ttab || ctx->ttab_n < T) return fail(ctx, AMPS_E_STATE, "backward without a saving forward");
   rc = dispatch_dp(DP, [&](auto dp, auto nq) -> int {
     constexpr int DPc = decltype(dp)::value, NQc = decltype(nq)::value;
-    auto kern = psi_bwd_kernel<DPc, NQc>;
-    const size_t smem = sizeof(BwdSmem<DPc>);
+    constexpr bool WS = DPc <= 32;
+    auto kern = WS ? psi_bwd_kernel<DPc, NQc> : psi_bwd_uni_kernel<DPc, NQc>;
+    const size_t smem = WS ? sizeof(BwdSmem<DPc, NQc>) : sizeof(BwdSmemUni<DPc>);
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PROF_BEGIN(ctx, 1, st);
-    kern<<<B, DPc * NQc, smem, st>>>(
+    kern<<<B, (WS ? 2 : 1) * DPc * NQc, smem, st>>>(
         (const float2*)(ws + L.matN), (const float2*)(ws + L.matRH), (const float2*)(ws + L.matS),
         (const float2*)(ws + L.qtab), ctx->ttab, x_dev, T, p->A, w_dev,
         (const float2*)(ws + L.traj), (const float*)(ws + L.scales), nchunks,

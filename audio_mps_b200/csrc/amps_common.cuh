@@ -50,6 +50,31 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+// ---- predicated shared-memory stores (keeps the per-step stores branch-free) ----------------
+__device__ __forceinline__ void sts_if(bool on, float2* p, float2 v) {
+  const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(p));
+  asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.b32 pp, %0, 0;\n\t@pp st.shared.v2.f32 [%1], {%2, %3};\n\t}\n" ::"r"((int)on),
+               "r"(a), "f"(v.x), "f"(v.y)
+               : "memory");
+}
+__device__ __forceinline__ void sts_if(bool on, float* p, float v) {
+  const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(p));
+  asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.b32 pp, %0, 0;\n\t@pp st.shared.f32 [%1], %2;\n\t}\n" ::"r"((int)on), "r"(a),
+               "f"(v)
+               : "memory");
+}
+
+// 64-bit shared load that the compiler may not fuse into LDS.128: on sm_100a an LDS.128 is always
+// issued as 4 quarter-warp wavefronts, while an LDS.64 whose lanes read <= 128 distinct bytes is a
+// single wavefront (ncu, profiles/r1_smem_wavefronts.md) -- the chain's state-vector loads are
+// 8-lane broadcasts, so two LDS.64 cost half the shared-memory pipe time of one LDS.128.
+__device__ __forceinline__ float2 lds64(const float2* p) {
+  const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(p));
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+
 // ---- thread map ---------------------------------------------------------------------------
 // A CTA of DP*NQ threads owns one clip.  Thread t = i*NQ + jq holds, for matrix row i, the
 // CPT = DP/NQ columns  col(c) = 2*NQ*(c/2) + 2*jq + (c&1)  in registers, so that for a fixed

@@ -1,20 +1,27 @@
 // PsiCMPS scan kernels (sm_100a): sequential persistent forward-loss kernel, adjoint backward,
-// sampler.  One CTA owns one clip for the whole clip; the step operators live in registers,
-// the state in shared memory, the waveform / phase table / trajectory stream in through
-// multi-buffered cp.async.
+// sampler.  One CTA owns one clip for the whole clip.
 //
 // Formulation (validated against the op-for-op oracle, see DESIGN.md "Chain form"):
 // in the interaction frame x_k = psi_k * conj(p_k) the reference step (model.py:276-334) is
-//     x'_k    = N x_k + s_k R x_k,           N = I - (delta_t sigma^2 / 2) R^dag R,  s_k = inc_k / A
+//     x'_k    = L_k x_k,   L_k = N + s_k R,  N = I - (delta_t sigma^2 / 2) R^dag R,  s_k = inc_k / A
 //     E_k     = x'_k^dag (R + R^dag) x'_k / |x_k|^2
 //     loss   += -log(1 + (E_k inc_k) / A)
 //     x_{k+1} = q_k * x'_k (* c),             q_k = p_k conj(p_{k+1})
 // with p_k = exp(i fl32(f t_k)) and t_k the float32 running sum.  The state is carried
-// UN-normalised (the loss is scale invariant) and rescaled by c once per chunk, so the only
-// thing on the per-step critical path is one stacked [N;R] mat-vec.  Everything that does not
-// feed the next state (E_k, |x_k|^2, the log, the parameter-gradient tiles) is software-pipelined
-// into the same loop one step (or one chunk) behind, where it fills the issue slots the
-// latency-bound chain leaves empty, or is done lane-parallel over the CH steps of a chunk.
+// UN-normalised (the loss is scale invariant) and rescaled by c once per chunk of CHK steps.
+//
+// Warp specialisation.  The recursion is a dependent chain
+//     LDS state -> FFMA (mat-vec with L_k) -> 2..3 shuffle levels -> STS -> bar.sync
+// whose measured B200 latencies (profiles/micro: shfl+add 29 cycles, STS+bar+LDS 50 cycles, a
+// dependent FFMA stream 1.4-1.6 cycles/instruction with one warp per SM sub-partition) leave most
+// issue slots empty.  Each CTA therefore runs two sets of warps on the same sub-partitions:
+//   * CHAIN warps (high warp ids): nothing but the recursion; one named barrier per step.
+//   * FILLER warps: everything that does not feed the next state -- cp.async prefetch of the
+//     waveform / phase table / trajectory, s_k, the expectation mat-vec S x', the per-step
+//     scalars (E_k, |x_k|^2, log1p, alpha_k, beta_k), the rank-1 gradient tiles, the trajectory
+//     flush -- one chunk behind (forward) or one chunk ahead/behind (backward), with no per-step
+//     synchronisation.  The hardware scheduler interleaves the two instruction streams.
+// The two sets meet at one __syncthreads per chunk.
 #pragma once
 #include <type_traits>
 
@@ -22,27 +29,547 @@
 
 namespace amps {
 
-using TrueT = std::true_type;
-using FalseT = std::false_type;
+// steps per chunk for a padded bond dimension (shared-memory budget of the backward kernel)
+__host__ __device__ constexpr int chunk_steps(int) { return CH; }
+
+__device__ __forceinline__ void bar_named(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 // -------------------------------------------------------------------------------------------
 // shared-memory layouts
 // -------------------------------------------------------------------------------------------
-template <int DP>
+template <int DP, int NQ>
 struct alignas(16) FwdSmem {
-  float2 xs[CH + 1][DP];     // x_{k0+kk}
-  float2 xps[CH][DP];        // x'_{k0+kk}
-  float2 qs[2][CH][DP];      // q_k, double buffered
-  float es[CH][DP + 1];      // Re(conj(x'_i) (S x')_i)
-  float ns[2][CH + 1][DP + 1];  // |x_{k,i}|^2, chunk parity (row 0 of the next chunk is written early)
-  float wav[2][CH + 4];      // waveform samples k0..k0+len, double buffered
-  float sv[2][CH];           // s_k
-  float incv[2][CH];         // inc_k
+  static constexpr int CHK = chunk_steps(DP);
+  static constexpr int NTC = DP * NQ, G = NTC / CHK, ES = NTC + (G < 32 ? G : 0);
+  float2 xs[2][CHK + 1][DP];   // x_{k0+kk}, ring by chunk parity
+  float2 xps[2][CHK][DP];      // x'_{k0+kk}
+  float2 qs[2][CHK][DP];       // q_k
+  float es[CHK][ES];           // per-thread partial of Re(x'^dag S x')
+  float wav[2][CHK + 4];       // waveform samples k0..k0+len
+  float sv[2][CHK + 4];        // s_k
+  float incv[2][CHK];          // inc_k
+  double lred[32];
+};
+
+template <int DP, int NQ>
+struct alignas(16) BwdSmem {
+  static constexpr int CHK = chunk_steps(DP);
+  float2 xs[4][CHK + 1][DP];   // trajectory chunk (chunk % 4): landing / prep / chain / tiles
+  float2 qs[2][CHK][DP];       // q_k (chunk & 1): landing / prep
+  float2 xps[3][CHK][DP];      // reconstructed x'_k (chunk % 3): prep / - / tiles
+  float4 cina[2][CHK][DP];     // chain inputs (chunk & 1): { c_k q_k , alpha_k (S x'_k)_i }
+  float4 cinb[2][CHK][DP];     //                           { beta_k x_k,i , dtm_k x_k,i }
+  float2 mus[2][CHK][DP];      // adjoint of x'_k (chunk & 1): chain writes, tiles read
+  float2 sps[CHK][DP];         // S x'_k (prep scratch)
+  float es[CHK][DP + 1];       // prep scratch
+  float ns[CHK][DP + 1];       // prep scratch
+  float wav[2][CHK + 4];
+  float tt[2][CHK + 4];        // tt[.][0] = t_{k0-1}, tt[.][1+kk] = t_{k0+kk}
+  float scs[2][4];
+  float sv[3][CHK], alphas[3][CHK];
+  float incv[CHK], betas[CHK], dtm[CHK];
   double lred[32];
 };
 
 template <int DP>
-struct alignas(16) BwdSmem {
+struct alignas(16) SampleSmem {
+  float2 xs[2][DP];
+  float2 qs[2][CH][DP];
+  float nz[2][CH];
+  float outs[CH];
+  float wred[2][32][2];
+};
+
+// -------------------------------------------------------------------------------------------
+// K1: forward per-clip loss (model.py:257-267, 276-282, 293-334)
+// -------------------------------------------------------------------------------------------
+template <int DP, int NQ>
+__global__ void __launch_bounds__(2 * DP * NQ)
+    psi_fwd_kernel(const float2* __restrict__ matN, const float2* __restrict__ matR,
+                   const float2* __restrict__ matS, const float2* __restrict__ qtab,
+                   const float2* __restrict__ psi0p, const float* __restrict__ x, int T, float A,
+                   float* __restrict__ loss, double* __restrict__ lossd,
+                   float2* __restrict__ traj, float* __restrict__ scales, int nchunks) {
+  using M = Map<DP, NQ>;
+  using Sm = FwdSmem<DP, NQ>;
+  constexpr int NTC = M::NT;       // threads per role
+  constexpr int CPT = M::CPT;
+  constexpr int CHK = Sm::CHK;
+  constexpr int G = Sm::G;         // filler threads per step in the scalar phase
+  constexpr int LV = (NQ == 4) ? 2 : 3;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Sm& sm = *reinterpret_cast<Sm*>(smem_raw);
+
+  const int t = threadIdx.x;
+  const bool is_chain = t >= NTC;          // high warp ids: the scheduler favours them
+  const int tr = is_chain ? t - NTC : t;   // thread index within the role
+  const int i = tr / NQ, jq = tr % NQ, lane = t & 31;
+  const int b = blockIdx.x;
+  const int nsteps = T - 1;
+  const float* xb = x + (size_t)b * T;
+  auto chunk_len = [&](int c) { return min(CHK, nsteps - c * CHK); };
+
+  // ---- prologue (all threads): inputs of chunk 0, start state ------------------------------
+  if (t < DP) {
+    const float2 p = psi0p[t];
+    sm.xs[0][0][t] = p;
+    if (traj) traj[(size_t)b * T * DP + t] = p;
+  }
+  auto issue_loads = [&](int c, int nthr, int tid) {
+    const int buf = c & 1, k0 = c * CHK, len = chunk_len(c);
+    const float2* qsrc = qtab + (size_t)k0 * DP;
+    float2* qdst = &sm.qs[buf][0][0];
+    for (int idx = tid; idx < len * DP / 2; idx += nthr) cp_async16(qdst + 2 * idx, qsrc + 2 * idx);
+    for (int idx = tid; idx <= len; idx += nthr) cp_async4(&sm.wav[buf][idx], xb + k0 + idx);
+  };
+  auto compute_s = [&](int c, int tid) {
+    const int buf = c & 1, len = chunk_len(c);
+    if (tid < len) {
+      const float inc = sm.wav[buf][tid + 1] - sm.wav[buf][tid];   // model.py:263
+      sm.incv[buf][tid] = inc;
+      sm.sv[buf][tid] = inc / A;                                    // model.py:303
+    }
+  };
+  if (nchunks > 0) {
+    issue_loads(0, 2 * NTC, t);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    compute_s(0, t);
+  }
+  __syncthreads();
+
+  if (is_chain) {
+    // =================================== CHAIN WARPS ==========================================
+    float2 Nr[CPT], Rr[CPT];
+    load_slice<DP, NQ>(Nr, matN, i, jq);
+    load_slice<DP, NQ>(Rr, matR, i, jq);
+    float2 vstart = make_float2(0.f, 0.f);
+    for (int c = 0; c <= nchunks; ++c) {
+      if (c < nchunks) {
+        const int p = c & 1, len = chunk_len(c);
+        if (c > 0) {
+          if (tr < DP) sm.xs[p][0][tr] = vstart;   // fillers are done with ring p (chunk c-2)
+          bar_named(1, NTC);
+        }
+        // branch-free stores: lane jq==0 writes x_{k+1,i}, jq==1 writes x'_{k,i}
+        float2* const st2 = (jq == 0) ? &sm.xs[p][1][i] : &sm.xps[p][0][i];
+        const bool st2_on = jq < 2;
+        float s_cur = sm.sv[p][0];
+        auto step = [&](int kk) {
+          float2 xv[CPT];
+#pragma unroll
+          for (int m = 0; m < CPT / 2; ++m) {
+            const float4 v = *reinterpret_cast<const float4*>(&sm.xs[p][kk][2 * NQ * m + 2 * jq]);
+            xv[2 * m] = make_float2(v.x, v.y);
+            xv[2 * m + 1] = make_float2(v.z, v.w);
+          }
+          const float2 q = sm.qs[p][kk][i];
+          const float s_next = sm.sv[p][kk + 1];
+          float2 a0 = make_float2(0.f, 0.f), a1 = a0;
+#pragma unroll
+          for (int cc = 0; cc < CPT; cc += 2) {   // L_k slice formed in the shadow of the loads
+            const float2 l0 = make_float2(fmaf(s_cur, Rr[cc].x, Nr[cc].x), fmaf(s_cur, Rr[cc].y, Nr[cc].y));
+            const float2 l1 = make_float2(fmaf(s_cur, Rr[cc + 1].x, Nr[cc + 1].x),
+                                          fmaf(s_cur, Rr[cc + 1].y, Nr[cc + 1].y));
+            cmac(a0, l0, xv[cc]);
+            cmac(a1, l1, xv[cc + 1]);
+          }
+          float2 xp = make_float2(a0.x + a1.x, a0.y + a1.y);
+#pragma unroll
+          for (int lv = 0; lv < LV; ++lv) {
+            xp.x += __shfl_xor_sync(0xffffffffu, xp.x, 1 << lv);
+            xp.y += __shfl_xor_sync(0xffffffffu, xp.y, 1 << lv);
+          }
+          const float2 xn = cmul(q, xp);
+          sts_if(st2_on, st2 + kk * DP, (jq == 0) ? xn : xp);
+          s_cur = s_next;
+          bar_named(1, NTC);
+        };
+        if (len == CHK) {
+#pragma unroll 2
+          for (int kk = 0; kk < CHK; ++kk) step(kk);
+        } else {
+          for (int kk = 0; kk < len; ++kk) step(kk);
+        }
+        // rescale by 1/|x_{k0+len}| (each chain warp computes the norm redundantly)
+        float n2 = 0.f;
+        for (int r = lane; r < DP; r += 32) n2 += cabs2(sm.xs[p][len][r]);
+        n2 = warp_sum_f(n2);
+        const float sc = rsqrtf(n2);
+        bar_named(1, NTC);   // every chain warp has read the un-scaled state
+        if (tr < DP) {
+          float2 v = sm.xs[p][len][tr];
+          v.x *= sc;
+          v.y *= sc;
+          sm.xs[p][len][tr] = v;   // the scaled state is what the trajectory / backward sees
+          vstart = v;
+        }
+        if (tr == 0 && scales) scales[(size_t)b * nchunks + c] = sc;
+      }
+      __syncthreads();   // chunk hand-over
+    }
+  } else {
+    // =================================== FILLER WARPS =========================================
+    float2 Sr[CPT];
+    load_slice<DP, NQ>(Sr, matS, i, jq);
+    double lossacc = 0.0;
+    for (int c = 0; c <= nchunks; ++c) {
+      if (c + 1 < nchunks) issue_loads(c + 1, NTC, tr);
+      cp_async_commit();
+      if (c >= 1) {
+        // ---- chunk c-1: expectation mat-vec for every step (no per-step synchronisation) ----
+        const int cc = c - 1, p = cc & 1, len = chunk_len(cc), k0 = cc * CHK;
+#ifndef AMPS_EXPERIMENT_NO_FILLER
+        for (int kk = 0; kk < len; ++kk) {
+          const float2 part = matvec1<DP, NQ>(Sr, sm.xps[p][kk], jq);
+          const float2 xpi = sm.xps[p][kk][i];
+          sm.es[kk][tr] = fmaf(xpi.x, part.x, xpi.y * part.y);
+        }
+#endif
+        bar_named(2, NTC);
+        {  // per-step scalars: G threads per step
+          const int kk = tr / G, g = tr % G;
+          float en = 0.f, nu2 = 0.f;
+          if (kk < len) {
+#pragma unroll 8
+            for (int r = 0; r < NTC / G; ++r) en += sm.es[kk][g + G * r];
+            for (int r = g; r < DP; r += G) nu2 += cabs2(sm.xs[p][kk][r]);
+          }
+#pragma unroll
+          for (int m = 1; m < G && m < 32; m <<= 1) {
+            en += __shfl_xor_sync(0xffffffffu, en, m);
+            nu2 += __shfl_xor_sync(0xffffffffu, nu2, m);
+          }
+          if (g == 0 && kk < len) {
+            const float E = en / nu2;                                  // model.py:324-325 on x'
+            const float z = (E * sm.incv[p][kk]) / A;                  // model.py:294
+            lossacc -= (double)log1pf(z);
+          }
+        }
+        if (traj) {   // flush x_{k0+1 .. k0+len}
+          const float4* src = reinterpret_cast<const float4*>(&sm.xs[p][1][0]);
+          float4* dst = reinterpret_cast<float4*>(traj + ((size_t)b * T + k0 + 1) * DP);
+          for (int idx = tr; idx < len * DP / 2; idx += NTC) dst[idx] = src[idx];
+        }
+      }
+      cp_async_wait<0>();
+      bar_named(2, NTC);   // chunk c+1's waveform has landed for every filler thread
+      if (c + 1 < nchunks) compute_s(c + 1, tr);
+      __syncthreads();     // chunk hand-over
+    }
+    // block reduction of the per-thread loss partials (filler warps only)
+    lossacc = warp_sum_d(lossacc);
+    if (lane == 0) sm.lred[tr >> 5] = lossacc;
+    bar_named(2, NTC);
+    if (tr == 0) {
+      double tot = 0.0;
+      for (int wv = 0; wv < NTC / 32; ++wv) tot += sm.lred[wv];
+      loss[b] = (float)tot;
+      if (lossd) lossd[b] = tot;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// K2: adjoint backward over the stored trajectory (replaces tf.gradients for train.py:89)
+//   per-clip outputs: G[b][0]=sum_k s_k mu_k x_k^dag, G[b][1]=sum_k mu_k x_k^dag,
+//                     G[b][2]=sum_k alpha_k x'_k x'_k^dag,  gf[b], lam0[b], gAdir[b]
+// Adjoint recursion (DESIGN.md "Adjoint"), k descending, lam = adjoint of x_{k+1}:
+//     mu_k  = c_k conj(q_k) lam + alpha_k S x'_k          alpha_k = 2 gE_k / |x_k|^2
+//     lam   = L_k^dag mu_k + beta_k x_k                   beta_k  = -alpha_k E_k
+// Slot c (c = nchunks .. -1):  CHAIN warps run the recursion over chunk c;  FILLER warps issue
+// the loads of chunk c-2, accumulate the rank-1 gradient tiles of chunk c+1 (its mu_k are
+// complete) and prepare chunk c-1 (x', S x', alpha, beta, packed per-row chain inputs).
+// -------------------------------------------------------------------------------------------
+template <int DP, int NQ>
+__global__ void __launch_bounds__(2 * DP * NQ)
+    psi_bwd_kernel(const float2* __restrict__ matN, const float2* __restrict__ matRH,
+                   const float2* __restrict__ matS, const float2* __restrict__ qtab,
+                   const float* __restrict__ ttab, const float* __restrict__ x, int T, float A,
+                   const float* __restrict__ w, const float2* __restrict__ traj,
+                   const float* __restrict__ scales, int nchunks, float2* __restrict__ Gout,
+                   float* __restrict__ gfout, float2* __restrict__ lam0out,
+                   double* __restrict__ gAdir) {
+  using M = Map<DP, NQ>;
+  using Sm = BwdSmem<DP, NQ>;
+  constexpr int NTC = M::NT;
+  constexpr int CPT = M::CPT;
+  constexpr int NP = M::NP;
+  constexpr int CHK = Sm::CHK;
+  constexpr int G = NTC / CHK, PER = DP / G;   // prep scalar phase: G threads per step
+  static_assert(DP % G == 0 && G <= 32, "scalar-phase grouping");
+  constexpr int LV = (NQ == 4) ? 2 : 3;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Sm& sm = *reinterpret_cast<Sm*>(smem_raw);
+
+  const int t = threadIdx.x;
+  const bool is_chain = t >= NTC;
+  const int tr = is_chain ? t - NTC : t;
+  const int i = tr / NQ, jq = tr % NQ, lane = t & 31;
+  const int b = blockIdx.x;
+  const int nsteps = T - 1;
+  auto chunk_len = [&](int c) { return min(CHK, nsteps - c * CHK); };
+
+  if (is_chain) {
+    // =================================== CHAIN WARPS ==========================================
+    float2 Nr[CPT], Hr[CPT];
+    load_slice<DP, NQ>(Nr, matN, i, jq);   // N is Hermitian: N^dag mu uses the same slices
+    load_slice<DP, NQ>(Hr, matRH, i, jq);  // R^dag
+    float2 lam = make_float2(0.f, 0.f);    // adjoint of x_{k+1}, replicated over the NQ lanes
+    float gf = 0.f;
+    const bool mu_on = jq == 0;
+    for (int c = nchunks; c >= -1; --c) {
+      if (c >= 0 && c < nchunks) {
+        const int ca = c & 1, len = chunk_len(c);
+        float2* const mu_st = &sm.mus[ca][0][i];
+        {  // adjoint of x' for the chunk's last step (its q carries the rescale c_k)
+          const float4 a4 = sm.cina[ca][len - 1][i];
+          float2 mu = cmul_ca(make_float2(a4.x, a4.y), lam);
+          mu.x += a4.z;
+          mu.y += a4.w;
+          sts_if(mu_on, mu_st + (len - 1) * DP, mu);
+        }
+        bar_named(1, NTC);
+        auto step = [&](int kk) {
+          float2 mv[CPT];
+#pragma unroll
+          for (int m = 0; m < NP; ++m) {
+            const float4 v = *reinterpret_cast<const float4*>(&sm.mus[ca][kk][2 * NQ * m + 2 * jq]);
+            mv[2 * m] = make_float2(v.x, v.y);
+            mv[2 * m + 1] = make_float2(v.z, v.w);
+          }
+          const float s = sm.sv[c % 3][kk];
+          const float4 b4 = sm.cinb[ca][kk][i];                    // { beta x_k , dtm x_k }
+          const float4 a4 = sm.cina[ca][kk > 0 ? kk - 1 : 0][i];   // { c q , alpha S x' } of step kk-1
+          float2 a0 = make_float2(0.f, 0.f), a1 = a0;
+#pragma unroll
+          for (int cc = 0; cc < CPT; cc += 2) {
+            const float2 l0 = make_float2(fmaf(s, Hr[cc].x, Nr[cc].x), fmaf(s, Hr[cc].y, Nr[cc].y));
+            const float2 l1 = make_float2(fmaf(s, Hr[cc + 1].x, Nr[cc + 1].x),
+                                          fmaf(s, Hr[cc + 1].y, Nr[cc + 1].y));
+            cmac(a0, l0, mv[cc]);
+            cmac(a1, l1, mv[cc + 1]);
+          }
+          float2 lp = make_float2(a0.x + a1.x, a0.y + a1.y);
+#pragma unroll
+          for (int lv = 0; lv < LV; ++lv) {
+            lp.x += __shfl_xor_sync(0xffffffffu, lp.x, 1 << lv);
+            lp.y += __shfl_xor_sync(0xffffffffu, lp.y, 1 << lv);
+          }
+          lam.x = lp.x + b4.x;
+          lam.y = lp.y + b4.y;
+          gf = fmaf(lam.x, b4.w, fmaf(-lam.y, b4.z, gf));   // dtm Im(conj(lam) x_k)
+          float2 mu = cmul_ca(make_float2(a4.x, a4.y), lam);
+          mu.x += a4.z;
+          mu.y += a4.w;
+          sts_if(mu_on && kk > 0, mu_st + (kk > 0 ? kk - 1 : 0) * DP, mu);
+          bar_named(1, NTC);
+        };
+        if (len == CHK) {
+#pragma unroll 2
+          for (int kk = CHK - 1; kk >= 0; --kk) step(kk);
+        } else {
+          for (int kk = len - 1; kk >= 0; --kk) step(kk);
+        }
+      }
+      __syncthreads();   // slot hand-over
+    }
+    if (jq == 0) {
+      gfout[(size_t)b * DP + i] = gf;
+      lam0out[(size_t)b * DP + i] = lam;
+    }
+  } else {
+    // =================================== FILLER WARPS =========================================
+    const float* xb = x + (size_t)b * T;
+    const float2* trb = traj + (size_t)b * T * DP;
+    const float wb = w[b];
+    float2 Sr[CPT];
+    load_slice<DP, NQ>(Sr, matS, i, jq);
+    float2 GR[CPT], GN[CPT], GE[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) GR[c] = GN[c] = GE[c] = make_float2(0.f, 0.f);
+    double gAacc = 0.0;
+
+    auto issue_loads = [&](int c) {
+      const int k0 = c * CHK, len = chunk_len(c);
+      const float2* xsrc = trb + (size_t)k0 * DP;
+      float2* xdst = &sm.xs[c & 3][0][0];
+      for (int idx = tr; idx < (len + 1) * DP / 2; idx += NTC) cp_async16(xdst + 2 * idx, xsrc + 2 * idx);
+      const float2* qsrc = qtab + (size_t)k0 * DP;
+      float2* qdst = &sm.qs[c & 1][0][0];
+      for (int idx = tr; idx < len * DP / 2; idx += NTC) cp_async16(qdst + 2 * idx, qsrc + 2 * idx);
+      for (int idx = tr; idx <= len; idx += NTC) {
+        cp_async4(&sm.wav[c & 1][idx], xb + k0 + idx);
+        // tt[0] = t_{k0-1} (t_0 for the first chunk: dtm_0 is forced to 0 there), tt[1+kk] = t_{k0+kk}
+        cp_async4(&sm.tt[c & 1][idx], ttab + (k0 + idx > 0 ? k0 + idx - 1 : 0));
+      }
+      if (tr == 0) cp_async4(&sm.scs[c & 1][0], scales + (size_t)b * nchunks + c);
+    };
+
+    // rank-1 gradient tiles of one finished chunk (its mu_k are all in shared memory)
+    auto tiles_chunk = [&](int c) {
+      const int len = chunk_len(c);
+      const float2(*xsb)[DP] = sm.xs[c & 3];
+      const float2(*xpb)[DP] = sm.xps[c % 3];
+      const float2(*mub)[DP] = sm.mus[c & 1];
+      for (int kk = 0; kk < len; ++kk) {
+        const float2 mui = mub[kk][i];
+        const float2 xpi = xpb[kk][i];
+        const float s = sm.sv[c % 3][kk];
+        const float al = sm.alphas[c % 3][kk];
+        const float2 u1 = make_float2(s * mui.x, s * mui.y);
+        const float2 u3 = make_float2(al * xpi.x, al * xpi.y);
+#pragma unroll
+        for (int m = 0; m < NP; ++m) {
+          const float4 xv = *reinterpret_cast<const float4*>(&xsb[kk][2 * NQ * m + 2 * jq]);
+          const float4 pv = *reinterpret_cast<const float4*>(&xpb[kk][2 * NQ * m + 2 * jq]);
+          const float2 x0 = make_float2(xv.x, xv.y), x1 = make_float2(xv.z, xv.w);
+          const float2 p0 = make_float2(pv.x, pv.y), p1 = make_float2(pv.z, pv.w);
+          cmac_cx(GR[2 * m], u1, x0);
+          cmac_cx(GR[2 * m + 1], u1, x1);
+          cmac_cx(GN[2 * m], mui, x0);
+          cmac_cx(GN[2 * m + 1], mui, x1);
+          cmac_cx(GE[2 * m], u3, p0);
+          cmac_cx(GE[2 * m + 1], u3, p1);
+        }
+      }
+    };
+
+    // everything the chain needs for one chunk, from the landed trajectory
+    auto prep_chunk = [&](int c) {
+      const int len = chunk_len(c), k0 = c * CHK;
+      const int lx = c & 3, lq = c & 1, lp3 = c % 3;
+      const float sc = sm.scs[lq][0];
+      const float inv_sc = 1.0f / sc;
+      if (tr < len) {
+        const float inc = sm.wav[lq][tr + 1] - sm.wav[lq][tr];
+        sm.incv[tr] = inc;
+        sm.sv[lp3][tr] = inc / A;
+        sm.dtm[tr] = (k0 + tr > 0) ? sm.tt[lq][tr + 1] - sm.tt[lq][tr] : 0.f;
+      }
+      // P1: x'_k = conj(q_k) x_{k+1} / c_k ; |x_k|^2
+      for (int idx = tr; idx < len * DP; idx += NTC) {
+        const int kk = idx / DP, r = idx % DP;
+        float2 xp = cmul_ca(sm.qs[lq][kk][r], sm.xs[lx][kk + 1][r]);
+        if (kk == len - 1) {
+          xp.x *= inv_sc;
+          xp.y *= inv_sc;
+        }
+        sm.xps[lp3][kk][r] = xp;
+        sm.ns[kk][r] = cabs2(sm.xs[lx][kk][r]);
+      }
+      bar_named(2, NTC);
+      // P2: S x' and e_i
+      for (int kk = 0; kk < len; ++kk) {
+        float2 part = matvec1<DP, NQ>(Sr, sm.xps[lp3][kk], jq);
+        part = group_sum<NQ>(part);
+        const float2 xpi = sm.xps[lp3][kk][i];
+        sts_if(jq == 1, &sm.sps[kk][i], part);
+        sts_if(jq == 2, &sm.es[kk][i], fmaf(xpi.x, part.x, xpi.y * part.y));
+      }
+      bar_named(2, NTC);
+      // P3: alpha_k, beta_k and the direct dL/dA term; G threads per step
+      {
+        const int kk = tr / G, g = tr % G;
+        float en = 0.f, nu2 = 0.f;
+        if (kk < len) {
+#pragma unroll
+          for (int r = 0; r < PER; ++r) {
+            en += sm.es[kk][g * PER + r];
+            nu2 += sm.ns[kk][g * PER + r];
+          }
+        }
+#pragma unroll
+        for (int m = 1; m < G; m <<= 1) {
+          en += __shfl_xor_sync(0xffffffffu, en, m);
+          nu2 += __shfl_xor_sync(0xffffffffu, nu2, m);
+        }
+        if (g == 0 && kk < len) {
+          const float E = en / nu2;
+          const float inc = sm.incv[kk];
+          const float arg = 1.0f + (E * inc) / A;
+          const float gE = wb * (-sm.sv[lp3][kk] / arg);
+          const float alpha = 2.0f * gE / nu2;
+          sm.alphas[lp3][kk] = alpha;
+          sm.betas[kk] = -alpha * E;
+          gAacc += (double)wb * (double)E * (double)inc / ((double)A * (double)A * (double)arg);
+        }
+      }
+      bar_named(2, NTC);
+      // P4: packed per-row chain inputs
+      for (int idx = tr; idx < len * DP; idx += NTC) {
+        const int kk = idx / DP, r = idx % DP;
+        float2 q = sm.qs[lq][kk][r];
+        if (kk == len - 1) {
+          q.x *= sc;
+          q.y *= sc;
+        }
+        const float al = sm.alphas[lp3][kk], be = sm.betas[kk], dt = sm.dtm[kk];
+        const float2 sp = sm.sps[kk][r];
+        const float2 xk = sm.xs[lx][kk][r];
+        sm.cina[lq][kk][r] = make_float4(q.x, q.y, al * sp.x, al * sp.y);
+        sm.cinb[lq][kk][r] = make_float4(be * xk.x, be * xk.y, dt * xk.x, dt * xk.y);
+      }
+    };
+
+    if (nchunks > 0) issue_loads(nchunks - 1);
+    cp_async_commit();
+    for (int c = nchunks; c >= -1; --c) {
+      if (c - 2 >= 0) issue_loads(c - 2);
+      cp_async_commit();
+      if (c + 1 >= 0 && c + 1 < nchunks) tiles_chunk(c + 1);
+      cp_async_wait<1>();    // the loads of chunk c-1 (issued one slot earlier) have landed
+      bar_named(2, NTC);
+      if (c - 1 >= 0) prep_chunk(c - 1);
+      __syncthreads();       // slot hand-over
+    }
+    cp_async_wait<0>();
+
+    // ---- per-clip outputs -------------------------------------------------------------------
+    float2* Gb = Gout + (size_t)b * 3 * DP * DP;
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      const int col = M::col(c, jq);
+      Gb[0 * DP * DP + i * DP + col] = GR[c];
+      Gb[1 * DP * DP + i * DP + col] = GN[c];
+      Gb[2 * DP * DP + i * DP + col] = GE[c];
+    }
+    gAacc = warp_sum_d(gAacc);
+    if (lane == 0) sm.lred[tr >> 5] = gAacc;
+    bar_named(2, NTC);
+    if (tr == 0) {
+      double tot = 0.0;
+      for (int wv = 0; wv < NTC / 32; ++wv) tot += sm.lred[wv];
+      gAdir[b] = tot;
+    }
+  }
+}
+
+// ===========================================================================================
+// Unified (non-specialised) variants
+// ===========================================================================================
+using TrueT = std::true_type;
+using FalseT = std::false_type;
+
+template <int DP, int NQ>
+struct alignas(16) FwdSmemUni {
+  static constexpr int NT = DP * NQ, G = NT / 32, ES = NT + G;
+  float2 xs[CH + 1][DP];        // x_{k0+kk}
+  float2 xps[CH][DP];           // x'_{k0+kk}
+  float2 qs[2][CH][DP];         // q_k, double buffered
+  float es[CH][ES];             // per-thread partial of Re(x'^dag S x'); row stride = G mod 32
+  float ns[2][CH + 1][DP + 1];  // |x_{k,i}|^2, by chunk parity
+  float wav[2][CH + 4];         // waveform samples k0..k0+len, double buffered
+  float sv[2][CH + 4];          // s_k
+  float incv[2][CH];            // inc_k
+  double lred[32];
+};
+
+template <int DP>
+struct alignas(16) BwdSmemUni {
   float2 xs[3][CH + 1][DP];  // trajectory chunk, triple buffered (chunk c, c-1 in use, c-2 landing)
   float2 qs[3][CH][DP];
   float2 xps[2][CH][DP];     // reconstructed x'_k      (chunk c and, being prepared, c-1)
@@ -57,58 +584,25 @@ struct alignas(16) BwdSmem {
   double lred[32];
 };
 
-template <int DP>
-struct alignas(16) SampleSmem {
-  float2 xs[2][DP];
-  float2 qs[2][CH][DP];
-  float nz[2][CH];
-  float outs[CH];
-  float wred[2][32][2];
-};
-
-// Per-step scalars, lane-parallel over the chunk: G = NT/32 threads share one step, each sums
-// DP/G entries of es / ns, finished with xor-shuffles.  Returns (sum es, sum ns) on every thread
-// of the group; kk is the step this thread works on.
-template <int DP, int NT>
-__device__ __forceinline__ void chunk_scalars(const float (*es)[DP + 1], const float (*ns)[DP + 1],
-                                              int len, int t, int& kk, bool& leader, float& en,
-                                              float& nu2) {
-  constexpr int G = NT / 32, PER = DP / G;
-  kk = t / G;
-  const int g = t % G;
-  leader = (g == 0) && (kk < len);
-  en = 0.f;
-  nu2 = 0.f;
-  if (kk < len) {
-#pragma unroll
-    for (int r = 0; r < PER; ++r) {
-      en += es[kk][g * PER + r];
-      nu2 += ns[kk][g * PER + r];
-    }
-  }
-#pragma unroll
-  for (int m = 1; m < G; m <<= 1) {
-    en += __shfl_xor_sync(0xffffffffu, en, m);
-    nu2 += __shfl_xor_sync(0xffffffffu, nu2, m);
-  }
-}
-
 // -------------------------------------------------------------------------------------------
-// K1: forward per-clip loss (model.py:257-267, 276-282, 293-334)
+// K1u: forward per-clip loss, UNIFIED variant (every warp does everything; used where the CTA
+// already has several warps per sub-partition, DP = 64)
+// K1u: forward per-clip loss (model.py:257-267, 276-282, 293-334)
 // -------------------------------------------------------------------------------------------
 template <int DP, int NQ>
 __global__ void __launch_bounds__(DP* NQ)
-    psi_fwd_kernel(const float2* __restrict__ matN, const float2* __restrict__ matR,
+    psi_fwd_uni_kernel(const float2* __restrict__ matN, const float2* __restrict__ matR,
                    const float2* __restrict__ matS, const float2* __restrict__ qtab,
                    const float2* __restrict__ psi0p, const float* __restrict__ x, int T, float A,
                    float* __restrict__ loss, double* __restrict__ lossd,
                    float2* __restrict__ traj, float* __restrict__ scales, int nchunks) {
   using M = Map<DP, NQ>;
+  using Sm = FwdSmemUni<DP, NQ>;
   constexpr int NT = M::NT;
   constexpr int CPT = M::CPT;
-  constexpr int NP = M::NP;
+  constexpr int G = Sm::G, PER = DP / G;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  FwdSmem<DP>& sm = *reinterpret_cast<FwdSmem<DP>*>(smem_raw);
+  Sm& sm = *reinterpret_cast<Sm*>(smem_raw);
 
   const int t = threadIdx.x, i = t / NQ, jq = t % NQ, lane = t & 31, warp = t >> 5;
   const int b = blockIdx.x;
@@ -143,6 +637,12 @@ __global__ void __launch_bounds__(DP* NQ)
     }
   };
 
+  // branch-free per-step stores: lane jq==0 writes x_{k+1,i}, jq==1 writes x'_{k,i} (same row
+  // stride), jq==2 writes |x_{k+1,i}|^2, every thread writes its partial of x'^dag S x'.
+  float2* const st2 = (jq == 0) ? &sm.xs[1][i] : &sm.xps[0][i];
+  const bool st2_on = jq < 2;
+  const bool stn_on = jq == 2;
+
   double lossacc = 0.0;
   if (nchunks > 0) {
     issue_loads(0, 0);
@@ -158,45 +658,68 @@ __global__ void __launch_bounds__(DP* NQ)
     const int len = min(CH, nsteps - k0);
     if (c + 1 < nchunks) issue_loads(c + 1, buf ^ 1);
     cp_async_commit();
-    __syncthreads();  // (D) sv/incv, xs[0], ns[0] of this chunk visible; last chunk's flush done
+    __syncthreads();  // (D) sv/incv, xs[0], ns[.][0] of this chunk visible; last chunk's flush done
 
+    float* const stn = &sm.ns[buf][1][i];
     float2 xp_prev = make_float2(0.f, 0.f);
-    // One step of the chain (critical path) with the expectation mat-vec of the PREVIOUS step
-    // software-pipelined into it.
+    float s_cur = sm.sv[buf][0];
+
+    // One step: chain mat-vec with L_k (critical path) + the S x' mat-vec of the previous step.
     auto step = [&](auto first_tag, int kk) {
       constexpr bool FIRST = decltype(first_tag)::value;
-      const float s = sm.sv[buf][kk];
-      const float2 q = sm.qs[buf][kk][i];
-      float2 a0 = make_float2(0.f, 0.f), a1 = a0, y0 = a0, y1 = a0, p0 = a0, p1 = a0;
+      float2 xv[CPT], pv[CPT];
 #pragma unroll
-      for (int m = 0; m < NP; ++m) {
-        const float4 xv = *reinterpret_cast<const float4*>(&sm.xs[kk][2 * NQ * m + 2 * jq]);
-        const float2 x0 = make_float2(xv.x, xv.y), x1 = make_float2(xv.z, xv.w);
-        cmac(a0, Nr[2 * m], x0);
-        cmac(a1, Nr[2 * m + 1], x1);
-        cmac(y0, Rr[2 * m], x0);
-        cmac(y1, Rr[2 * m + 1], x1);
-        if (!FIRST) {
-          const float4 pv = *reinterpret_cast<const float4*>(&sm.xps[kk - 1][2 * NQ * m + 2 * jq]);
-          cmac(p0, Sr[2 * m], make_float2(pv.x, pv.y));
-          cmac(p1, Sr[2 * m + 1], make_float2(pv.z, pv.w));
+      for (int m = 0; m < CPT / 2; ++m) {
+        const float4 v = *reinterpret_cast<const float4*>(&sm.xs[kk][2 * NQ * m + 2 * jq]);
+        xv[2 * m] = make_float2(v.x, v.y);
+        xv[2 * m + 1] = make_float2(v.z, v.w);
+      }
+      if (!FIRST) {
+#pragma unroll
+        for (int m = 0; m < CPT / 2; ++m) {
+          const float4 v = *reinterpret_cast<const float4*>(&sm.xps[kk - 1][2 * NQ * m + 2 * jq]);
+          pv[2 * m] = make_float2(v.x, v.y);
+          pv[2 * m + 1] = make_float2(v.z, v.w);
         }
       }
-      float2 xp = make_float2(fmaf(s, y0.x + y1.x, a0.x + a1.x), fmaf(s, y0.y + y1.y, a0.y + a1.y));
-      float e = 0.f;
-      if (!FIRST) e = fmaf(xp_prev.x, p0.x + p1.x, xp_prev.y * (p0.y + p1.y));
+      const float2 q = sm.qs[buf][kk][i];
+      const float s_next = sm.sv[buf][kk + 1];
+      // L_k slice, formed while the state loads are in flight
+      float2 L[CPT];
 #pragma unroll
-      for (int m = 1; m < NQ; m <<= 1) {
-        xp.x += __shfl_xor_sync(0xffffffffu, xp.x, m);
-        xp.y += __shfl_xor_sync(0xffffffffu, xp.y, m);
-        if (!FIRST) e += __shfl_xor_sync(0xffffffffu, e, m);
+      for (int cc = 0; cc < CPT; ++cc)
+        L[cc] = make_float2(fmaf(s_cur, Rr[cc].x, Nr[cc].x), fmaf(s_cur, Rr[cc].y, Nr[cc].y));
+      float2 a0 = make_float2(0.f, 0.f), a1 = a0;
+#pragma unroll
+      for (int cc = 0; cc < CPT; cc += 2) {
+        cmac(a0, L[cc], xv[cc]);
+        cmac(a1, L[cc + 1], xv[cc + 1]);
+      }
+      float2 xp = make_float2(a0.x + a1.x, a0.y + a1.y);
+      // group reduction, with the previous step's expectation FMAs in the shuffle shadows
+      float2 p0 = make_float2(0.f, 0.f), p1 = p0;
+      constexpr int LV = (NQ == 4) ? 2 : 3;
+      constexpr int CPL = (CPT + LV - 1) / LV;
+#pragma unroll
+      for (int lv = 0; lv < LV; ++lv) {
+        const float ox = __shfl_xor_sync(0xffffffffu, xp.x, 1 << lv);
+        const float oy = __shfl_xor_sync(0xffffffffu, xp.y, 1 << lv);
+        if (!FIRST) {
+#pragma unroll
+          for (int cc = lv * CPL; cc < (lv + 1) * CPL && cc < CPT; ++cc) {
+            if (cc & 1) cmac(p1, Sr[cc], pv[cc]);
+            else cmac(p0, Sr[cc], pv[cc]);
+          }
+        }
+        xp.x += ox;
+        xp.y += oy;
       }
       const float2 xn = cmul(q, xp);
-      if (jq == 0) sm.xs[kk + 1][i] = xn;
-      if (jq == 1) sm.xps[kk][i] = xp;
-      if (jq == 2) sm.ns[buf][kk + 1][i] = cabs2(xn);
-      if (!FIRST && jq == 3) sm.es[kk - 1][i] = e;
+      sts_if(st2_on, st2 + kk * DP, (jq == 0) ? xn : xp);
+      sts_if(stn_on, stn + kk * (DP + 1), cabs2(xn));
+      if (!FIRST) sm.es[kk - 1][t] = fmaf(xp_prev.x, p0.x + p1.x, xp_prev.y * (p0.y + p1.y));
       xp_prev = xp;
+      s_cur = s_next;
       __syncthreads();
     };
 
@@ -209,20 +732,26 @@ __global__ void __launch_bounds__(DP* NQ)
     }
     {  // expectation of the chunk's last step
       const float2 part = matvec1<DP, NQ>(Sr, sm.xps[len - 1], jq);
-      float e = fmaf(xp_prev.x, part.x, xp_prev.y * part.y);
-#pragma unroll
-      for (int m = 1; m < NQ; m <<= 1) e += __shfl_xor_sync(0xffffffffu, e, m);
-      if (jq == 3) sm.es[len - 1][i] = e;
+      sm.es[len - 1][t] = fmaf(xp_prev.x, part.x, xp_prev.y * part.y);
     }
     cp_async_wait<0>();
     __syncthreads();  // (A)
 
-    {  // per-step scalars, lane-parallel over the chunk
-      int kk;
-      bool leader;
-      float en, nu2;
-      chunk_scalars<DP, NT>(sm.es, sm.ns[buf], len, t, kk, leader, en, nu2);
-      if (leader) {
+    {  // per-step scalars, lane-parallel over the chunk: G threads per step
+      const int kk = t / G, g = t % G;
+      float en = 0.f, nu2 = 0.f;
+      if (kk < len) {
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) en += sm.es[kk][g + G * r];
+#pragma unroll
+        for (int r = 0; r < PER; ++r) nu2 += sm.ns[buf][kk][g * PER + r];
+      }
+#pragma unroll
+      for (int m = 1; m < G; m <<= 1) {
+        en += __shfl_xor_sync(0xffffffffu, en, m);
+        nu2 += __shfl_xor_sync(0xffffffffu, nu2, m);
+      }
+      if (g == 0 && kk < len) {
         const float E = en / nu2;                                  // model.py:324-325 on x'
         const float z = (E * sm.incv[buf][kk]) / A;                // model.py:294
         lossacc -= (double)log1pf(z);
@@ -264,18 +793,19 @@ __global__ void __launch_bounds__(DP* NQ)
 }
 
 // -------------------------------------------------------------------------------------------
+// K2u: adjoint backward, UNIFIED variant
 // K2: adjoint backward over the stored trajectory (replaces tf.gradients for train.py:89)
 //   per-clip outputs: G[b][0]=sum_k s_k mu_k x_k^dag, G[b][1]=sum_k mu_k x_k^dag,
 //                     G[b][2]=sum_k alpha_k x'_k x'_k^dag,  gf[b], lam0[b], gAdir[b]
 // Adjoint recursion (DESIGN.md "Adjoint"), k descending, lam = adjoint of x_{k+1}:
 //     mu_k  = c_k conj(q_k) lam + alpha_k S x'_k          alpha_k = 2 gE_k / |x_k|^2
-//     lam   = N mu_k + s_k R^dag mu_k + beta_k x_k        beta_k  = -alpha_k E_k
-// Pipeline per loop iteration kk of chunk c: chain step kk (critical path), the rank-1 tile
-// updates of step kk+1, and the S x' mat-vec of step kk of chunk c-1.
+//     lam   = L_k^dag mu_k + beta_k x_k                   beta_k  = -alpha_k E_k
+// Per loop iteration kk of chunk c: chain mat-vec of step kk (critical path) with, as filler, the
+// rank-1 tile updates of step kk and the S x' mat-vec of step kk of chunk c-1.
 // -------------------------------------------------------------------------------------------
 template <int DP, int NQ>
 __global__ void __launch_bounds__(DP* NQ)
-    psi_bwd_kernel(const float2* __restrict__ matN, const float2* __restrict__ matRH,
+    psi_bwd_uni_kernel(const float2* __restrict__ matN, const float2* __restrict__ matRH,
                    const float2* __restrict__ matS, const float2* __restrict__ qtab,
                    const float* __restrict__ ttab, const float* __restrict__ x, int T, float A,
                    const float* __restrict__ w, const float2* __restrict__ traj,
@@ -286,8 +816,9 @@ __global__ void __launch_bounds__(DP* NQ)
   constexpr int NT = M::NT;
   constexpr int CPT = M::CPT;
   constexpr int NP = M::NP;
+  constexpr int G = NT / 32, PER = DP / G;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  BwdSmem<DP>& sm = *reinterpret_cast<BwdSmem<DP>*>(smem_raw);
+  BwdSmemUni<DP>& sm = *reinterpret_cast<BwdSmemUni<DP>*>(smem_raw);
 
   const int t = threadIdx.x, i = t / NQ, jq = t % NQ, lane = t & 31, warp = t >> 5;
   const int b = blockIdx.x;
@@ -346,24 +877,34 @@ __global__ void __launch_bounds__(DP* NQ)
     }
   };
   // P2 of one step: S x' (stored) and e_i
+  float2* const sp_st = &sm.sps[0][0][i];
+  float* const es_st = &sm.es[0][i];
   auto expectation_step = [&](int ds, int kk) {
     float2 part = matvec1<DP, NQ>(Sr, sm.xps[ds][kk], jq);
     part = group_sum<NQ>(part);
-    if (jq == 0) sm.sps[ds][kk][i] = part;
-    if (jq == 1) {
-      const float2 xpi = sm.xps[ds][kk][i];
-      sm.es[kk][i] = fmaf(xpi.x, part.x, xpi.y * part.y);
-    }
+    const float2 xpi = sm.xps[ds][kk][i];
+    sts_if(jq == 1, sp_st + (ds * CH + kk) * DP, part);
+    sts_if(jq == 2, es_st + kk * (DP + 1), fmaf(xpi.x, part.x, xpi.y * part.y));
   };
   double gAacc = 0.0;
-  // P3 of chunk c: alpha_k, beta_k and the direct dL/dA term
+  // P3 of chunk c: alpha_k, beta_k and the direct dL/dA term; G threads per step
   auto prep_scalars = [&](int c) {
     const int ds = c & 1, len = chunk_len(c);
-    int kk;
-    bool leader;
-    float en, nu2;
-    chunk_scalars<DP, NT>(sm.es, sm.ns, len, t, kk, leader, en, nu2);
-    if (leader) {
+    const int kk = t / G, g = t % G;
+    float en = 0.f, nu2 = 0.f;
+    if (kk < len) {
+#pragma unroll
+      for (int r = 0; r < PER; ++r) {
+        en += sm.es[kk][g * PER + r];
+        nu2 += sm.ns[kk][g * PER + r];
+      }
+    }
+#pragma unroll
+    for (int m = 1; m < G; m <<= 1) {
+      en += __shfl_xor_sync(0xffffffffu, en, m);
+      nu2 += __shfl_xor_sync(0xffffffffu, nu2, m);
+    }
+    if (g == 0 && kk < len) {
       const float E = en / nu2;
       const float inc = sm.incv[ds][kk];
       const float arg = 1.0f + (E * inc) / A;
@@ -393,6 +934,9 @@ __global__ void __launch_bounds__(DP* NQ)
     prep_scalars(cl);
   }
 
+  float2* const mu_st = &sm.mus[0][i];
+  const bool mu_on = jq == 0;
+
   for (int c = nchunks - 1; c >= 0; --c) {
     const int lb = c % 3, ds = c & 1;
     const int len = chunk_len(c);
@@ -403,75 +947,107 @@ __global__ void __launch_bounds__(DP* NQ)
     cp_async_wait<1>();   // chunk c-1 has landed
     __syncthreads();      // (T1)
     if (has_prev) prep_elementwise(c - 1);
-    __syncthreads();      // (T2)
     const float sc = sm.scs[lb][0];
 
-    float2 mu_prev = make_float2(0.f, 0.f);
-    // tile update of step kk (its mu is mu_i, row values replicated in the group)
-    auto tiles = [&](int kk, float2 mui) {
-      const float2 xpi = sm.xps[ds][kk][i];
-      const float s = sm.sv[ds][kk];
-      const float al = sm.alphas[ds][kk];
-      const float2 u1 = make_float2(s * mui.x, s * mui.y);
-      const float2 u3 = make_float2(al * xpi.x, al * xpi.y);
-#pragma unroll
-      for (int m = 0; m < NP; ++m) {
-        const float4 xv = *reinterpret_cast<const float4*>(&sm.xs[lb][kk][2 * NQ * m + 2 * jq]);
-        const float4 pv = *reinterpret_cast<const float4*>(&sm.xps[ds][kk][2 * NQ * m + 2 * jq]);
-        const float2 x0 = make_float2(xv.x, xv.y), x1 = make_float2(xv.z, xv.w);
-        const float2 p0 = make_float2(pv.x, pv.y), p1 = make_float2(pv.z, pv.w);
-        cmac_cx(GR[2 * m], u1, x0);
-        cmac_cx(GR[2 * m + 1], u1, x1);
-        cmac_cx(GN[2 * m], mui, x0);
-        cmac_cx(GN[2 * m + 1], mui, x1);
-        cmac_cx(GE[2 * m], u3, p0);
-        cmac_cx(GE[2 * m + 1], u3, p1);
-      }
-    };
-
-    auto step = [&](auto first_tag, auto prev_tag, int kk) {
-      constexpr bool FIRST = decltype(first_tag)::value;   // first iteration of the chunk
-      constexpr bool PREV = decltype(prev_tag)::value;     // chunk c-1 exists and has step kk
-      const float2 q = sm.qs[lb][kk][i];
+    // adjoint of x' for the chunk's last step (carries the rescale c_k)
+    float2 mu;
+    {
+      const int kk = len - 1;
       const float2 xn = sm.xs[lb][kk + 1][i];
       gf = fmaf(sm.dtk[ds][kk], lam.x * xn.y - lam.y * xn.x, gf);   // Im(conj(lam) x_{k+1})
-      float2 mu = cmul_ca(q, lam);
-      if (FIRST) {
-        mu.x *= sc;
-        mu.y *= sc;
-      }
+      mu = cmul_ca(sm.qs[lb][kk][i], lam);
       const float al = sm.alphas[ds][kk];
       const float2 sp = sm.sps[ds][kk][i];
-      mu.x = fmaf(al, sp.x, mu.x);
-      mu.y = fmaf(al, sp.y, mu.y);
-      if (jq == 0) sm.mus[kk][i] = mu;
-      __syncthreads();
-      float2 a, h;
-      matvec2<DP, NQ>(Nr, Hr, sm.mus[kk], jq, a, h);
+      mu.x = fmaf(al, sp.x, mu.x * sc);
+      mu.y = fmaf(al, sp.y, mu.y * sc);
+      if (mu_on) mu_st[kk * DP] = mu;
+    }
+    __syncthreads();      // (T2)
+
+    auto step = [&](auto prev_tag, int kk) {
+      constexpr bool PREV = decltype(prev_tag)::value;     // chunk c-1 exists (expectation filler)
+      // ---- operand loads --------------------------------------------------------------
+      float2 mv[CPT];
+#pragma unroll
+      for (int m = 0; m < NP; ++m) {
+        const float4 v = *reinterpret_cast<const float4*>(&sm.mus[kk][2 * NQ * m + 2 * jq]);
+        mv[2 * m] = make_float2(v.x, v.y);
+        mv[2 * m + 1] = make_float2(v.z, v.w);
+      }
       const float s = sm.sv[ds][kk];
-      float2 lp = make_float2(fmaf(s, h.x, a.x), fmaf(s, h.y, a.y));
-      if (!FIRST) tiles(kk + 1, mu_prev);
-      if (PREV) expectation_step(pds, kk);
-      lp = group_sum<NQ>(lp);
       const float be = sm.betas[ds][kk];
       const float2 xk = sm.xs[lb][kk][i];
+      const int km = kk > 0 ? kk - 1 : 0;
+      const float2 q1 = sm.qs[lb][km][i];
+      const float al1 = sm.alphas[ds][km];
+      const float2 sp1 = sm.sps[ds][km][i];
+      const float dt1 = sm.dtk[ds][km];
+      // ---- chain: lam = L_k^dag mu + beta x_k -------------------------------------------
+      float2 a0 = make_float2(0.f, 0.f), a1 = a0;
+#pragma unroll
+      for (int cc = 0; cc < CPT; cc += 2) {
+        const float2 l0 = make_float2(fmaf(s, Hr[cc].x, Nr[cc].x), fmaf(s, Hr[cc].y, Nr[cc].y));
+        const float2 l1 = make_float2(fmaf(s, Hr[cc + 1].x, Nr[cc + 1].x), fmaf(s, Hr[cc + 1].y, Nr[cc + 1].y));
+        cmac(a0, l0, mv[cc]);
+        cmac(a1, l1, mv[cc + 1]);
+      }
+      float2 lp = make_float2(a0.x + a1.x, a0.y + a1.y);
+      float ox = __shfl_xor_sync(0xffffffffu, lp.x, 1);
+      float oy = __shfl_xor_sync(0xffffffffu, lp.y, 1);
+      // ---- filler 1: rank-1 tiles of step kk (mu_k is in registers) ---------------------
+      {
+        const float2 xpi = sm.xps[ds][kk][i];
+        const float al = sm.alphas[ds][kk];
+        const float2 u1 = make_float2(s * mu.x, s * mu.y);
+        const float2 u3 = make_float2(al * xpi.x, al * xpi.y);
+#pragma unroll
+        for (int m = 0; m < NP; ++m) {
+          const float4 xv = *reinterpret_cast<const float4*>(&sm.xs[lb][kk][2 * NQ * m + 2 * jq]);
+          const float4 pv = *reinterpret_cast<const float4*>(&sm.xps[ds][kk][2 * NQ * m + 2 * jq]);
+          const float2 x0 = make_float2(xv.x, xv.y), x1 = make_float2(xv.z, xv.w);
+          const float2 p0 = make_float2(pv.x, pv.y), p1 = make_float2(pv.z, pv.w);
+          cmac_cx(GR[2 * m], u1, x0);
+          cmac_cx(GR[2 * m + 1], u1, x1);
+          cmac_cx(GN[2 * m], mu, x0);
+          cmac_cx(GN[2 * m + 1], mu, x1);
+          cmac_cx(GE[2 * m], u3, p0);
+          cmac_cx(GE[2 * m + 1], u3, p1);
+        }
+      }
+      lp.x += ox;
+      lp.y += oy;
+      ox = __shfl_xor_sync(0xffffffffu, lp.x, 2);
+      oy = __shfl_xor_sync(0xffffffffu, lp.y, 2);
+      // ---- filler 2: S x' of step kk of chunk c-1 ---------------------------------------
+      if (PREV) expectation_step(pds, kk);
+      lp.x += ox;
+      lp.y += oy;
+      if (NQ == 8) {
+        lp.x += __shfl_xor_sync(0xffffffffu, lp.x, 4);
+        lp.y += __shfl_xor_sync(0xffffffffu, lp.y, 4);
+      }
       lam.x = fmaf(be, xk.x, lp.x);
       lam.y = fmaf(be, xk.y, lp.y);
-      mu_prev = mu;
+      // ---- adjoint of x' for step kk-1 --------------------------------------------------
+      if (kk > 0) {
+        gf = fmaf(dt1, lam.x * xk.y - lam.y * xk.x, gf);   // Im(conj(lam) x_k), x_k = x_{(k-1)+1}
+        mu = cmul_ca(q1, lam);
+        mu.x = fmaf(al1, sp1.x, mu.x);
+        mu.y = fmaf(al1, sp1.y, mu.y);
+      }
+      sts_if(mu_on && kk > 0, mu_st + km * DP, mu);
+      __syncthreads();
     };
 
     if (has_prev) {
-      step(TrueT{}, TrueT{}, len - 1);
-      for (int kk = len - 2; kk >= 0; --kk) step(FalseT{}, TrueT{}, kk);
+      for (int kk = len - 1; kk >= 0; --kk) step(TrueT{}, kk);
       // chunk c-1 is always full; finish its expectation steps if this chunk was short
       for (int kk = len; kk < CH; ++kk) expectation_step(pds, kk);
+      __syncthreads();    // (E1) es / sps of chunk c-1 complete
+      prep_scalars(c - 1);
     } else {
-      step(TrueT{}, FalseT{}, len - 1);
-      for (int kk = len - 2; kk >= 0; --kk) step(FalseT{}, FalseT{}, kk);
+      for (int kk = len - 1; kk >= 0; --kk) step(FalseT{}, kk);
     }
-    tiles(0, mu_prev);
-    __syncthreads();      // (E1) es / sps of chunk c-1 complete; mus free
-    if (has_prev) prep_scalars(c - 1);
   }
   cp_async_wait<0>();
 
