@@ -52,7 +52,7 @@ class HP:
     learning_rate: float = 0.001
 
 
-def test_hparams() -> HP:
+def ref_test_hparams() -> HP:
     """hparams of /root/reference/tests/test_model.py:13-14."""
     return HP(minibatch_size=8, bond_dim=7, delta_t=1 / 16000, sigma=0.0001,
               initial_rank=None, A=100.0,

@@ -1,0 +1,71 @@
+"""-m gpu: the CUDA path (through the C ABI) against the committed golden vectors, including
+BASELINE config[0] (D=8, 8 clips of 1 s at 16 kHz).  Tolerances: BASELINE.json north_star."""
+import numpy as np
+import pytest
+import torch
+
+from audio_mps_b200 import HParams, PsiCMPS, RhoCMPS
+from audio_mps_b200.train import regulariser
+from tests.golden_util import PSI_CASES, load, psi_case
+from tests.util import rel, relc, set_raw
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(hp, raw, cuda, cls=PsiCMPS, **kw):
+    php = HParams(minibatch_size=hp.minibatch_size, bond_dim=hp.bond_dim, delta_t=hp.delta_t,
+                  sigma=hp.sigma, h_reg=hp.h_reg, r_reg=hp.r_reg, initial_rank=None, A=hp.A,
+                  learning_rate=0.001)
+    m = cls(php, device=cuda, **kw)
+    set_raw(m, raw)
+    return m
+
+
+@pytest.mark.parametrize("name", PSI_CASES)
+def test_psi_loss_and_grads_vs_golden(cuda, lib, name):
+    hp, raw, data, g = psi_case(name)
+    m = _model(hp, raw, cuda)
+    lpc = m.loss_per_clip(data)
+    # per-clip log-likelihood: 1e-4 relative against the exact value of the reference's function
+    assert rel(lpc.detach().cpu().numpy(), g["loss_f64"]) <= 1e-4
+    # ... and no further from the reference's float32 run than that run's own rounding noise allows
+    assert rel(lpc.detach().cpu().numpy(), g["loss_f32"]) <= 1e-4 + 1.5 * rel(g["loss_f32"], g["loss_f64"])
+    obj = lpc.mean() + regulariser(m)
+    names = ["A", "Rx", "Ry", "freqs_raw", "psi_x", "psi_y"]
+    gs = torch.autograd.grad(obj, [getattr(m, n) for n in names])
+    for n, gg in zip(names, gs):
+        ref = g["grad_" + ("freqs" if n == "freqs_raw" else n) + "_f64"]
+        assert rel(gg.cpu().numpy(), ref) <= 1e-3, n
+
+
+def test_qubit_and_sampler_golden(cuda, lib):
+    g = load("qubit_sampling")
+    from oracle.cmps_oracle import HP
+    hp = HP(minibatch_size=8, bond_dim=2, delta_t=1 / 16000, sigma=1, initial_rank=None, A=1.,
+            h_reg=2 / (np.pi * 16000) ** 2, r_reg=2 / (np.pi * 16000) ** 2)
+    R = np.array([[0, 1], [0, 0]], dtype=np.complex64)
+    fr = np.array([10, -10], dtype=np.float32)
+    m = _model(hp, {"psi_x": g["psi_x"], "psi_y": g["psi_y"]}, cuda, R_in=R, freqs_in=fr)
+    out = m.sample_from_noise(g["noise"]).cpu().numpy()
+    assert out.shape == (2, 512)                                  # tests/test_model.py:158
+    assert rel(out, g["psi_sample_f64"]) <= 1e-3
+    r = _model(hp, {}, cuda, cls=RhoCMPS, W_in=g["W"], R_in=R, freqs_in=fr)
+    assert rel(r.sample_from_noise(g["noise"]).cpu().numpy(), g["rho_sample_f64"]) <= 1e-3
+    assert rel(r.purity(2, 512, noise=g["noise"]).cpu().numpy(), g["rho_purity_f64"]) <= 1e-3
+    for D in (7, 32):
+        s = load(f"psi_sample_d{D}")
+        from oracle.cmps_oracle import HP as HP2
+        hp2 = HP2(bond_dim=D)
+        raw = {k[4:]: s[k] for k in s if k.startswith("raw_")}
+        m2 = _model(hp2, raw, cuda)
+        assert rel(m2.sample_from_noise(s["noise"]).cpu().numpy(), s["sample_f64"]) <= 1e-3
+
+
+def test_rho_golden(cuda, lib):
+    from oracle.cmps_oracle import ref_test_hparams
+    g = load("rho_testhp_d7")
+    raw = {k[4:]: g[k] for k in g if k.startswith("raw_")}
+    m = _model(ref_test_hparams(), raw, cuda, cls=RhoCMPS)
+    assert rel(m.loss_per_clip(g["data"]).cpu().numpy(), g["loss_f64"]) <= 1e-4
+    tr = m.rho_evolve_with_data(g["data"]).cpu().numpy()
+    assert relc(tr[:, -1], g["traj_last"]) <= 1e-4

@@ -1,0 +1,162 @@
+"""CPU tests of the host side: hparams, raw->effective parameter chain, data formats, shard logic,
+and that the C-ABI library loads and exports every symbol include/audiomps.h declares
+(no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from audio_mps_b200 import HParams, PsiCMPS, RhoCMPS, _lib, default_hparams
+from audio_mps_b200 import data as D
+from audio_mps_b200.train import regulariser, shard_bounds
+from oracle.cmps_oracle import HP, PsiCMPSOracle, RhoCMPSOracle, damped_sine, random_raw_params, total_loss
+from tests.util import hp_pair, rel, relc, set_raw
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "audiomps.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(amps_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(raw, name), f"{name} declared in audiomps.h but not exported"
+        assert name in _lib.SYMBOLS, f"{name} has no ctypes binding"
+    assert set(_lib.SYMBOLS) == declared
+    assert lib.amps_version() == 100
+    assert lib.amps_psi_grad_count(32) == 2 * 32 * 32 + 3 * 32 + 2
+    assert lib.amps_psi_workspace_bytes(32, 64, 64000, 1) > 64 * 64000 * 32 * 8
+    assert lib.amps_psi_workspace_bytes(200, 1, 10, 0) == 0      # unsupported D reports 0
+
+
+def test_no_cpu_fallback():
+    hp = default_hparams()
+    m = PsiCMPS(hp, device="cpu")
+    with pytest.raises(RuntimeError):
+        m.loss_per_clip(np.zeros((2, 16), np.float32))
+    with pytest.raises(RuntimeError):
+        m.sample(2, 8)
+    with pytest.raises(RuntimeError):
+        RhoCMPS(hp, device="cpu").loss_per_clip(np.zeros((2, 16), np.float32))
+
+
+def test_hparams_parse():
+    hp = default_hparams()
+    hp.parse("bond_dim=32,minibatch_size=64,sigma=0.5,initial_rank=3")
+    assert (hp.bond_dim, hp.minibatch_size, hp.sigma, hp.initial_rank) == (32, 64, 0.5, 3)
+    assert isinstance(hp.bond_dim, int) and isinstance(hp.sigma, float)
+    with pytest.raises(ValueError):
+        hp.parse("nonexistent=1")
+    assert hp.delta_t == 1 / 16000 and hp.A == 100.
+
+
+@pytest.mark.parametrize("use_in", [False, True])
+def test_effective_parameters_match_oracle(use_in):
+    """model.py:31-52, 221-222: scale, the diagonal broadcast quirk, psi_0 normalisation."""
+    ohp, php = hp_pair(bond_dim=5)
+    rng = np.random.default_rng(0)
+    raw = random_raw_params(ohp, rng)
+    if use_in:
+        R_in = (rng.standard_normal((5, 5)) + 1j * rng.standard_normal((5, 5))).astype(np.complex64)
+        f_in = rng.standard_normal(5).astype(np.float32)
+        o = PsiCMPSOracle(ohp, raw, R_in=R_in, freqs_in=f_in)
+        m = PsiCMPS(php, R_in=R_in, freqs_in=f_in, device="cpu")
+        set_raw(m, {"psi_x": raw["psi_x"], "psi_y": raw["psi_y"]})
+    else:
+        o = PsiCMPSOracle(ohp, raw)
+        m = PsiCMPS(php, device="cpu")
+        set_raw(m, raw)
+    assert relc(m.R.detach().numpy(), o.R.detach().numpy()) <= 1e-6
+    assert rel(m.freqs.detach().numpy(), o.freqs.detach().numpy()) <= 1e-6
+    assert relc(m.psi_0.detach().numpy(), o.psi_0.detach().numpy()) <= 1e-6
+    assert np.abs(np.diag(m.R.detach().numpy())).max() == 0           # tests/test_model.py:19-25
+    # regulariser of train.py:55-60 and its gradient through the raw->effective chain
+    reg = regulariser(m)
+    oreg = ohp.h_reg * torch.sum(o.freqs ** 2) + ohp.r_reg * torch.sum(torch.conj(o.R) * o.R).real
+    assert rel(float(reg), float(oreg)) <= 1e-5
+    g = torch.autograd.grad(reg, [m.Rx, m.Ry, m.freqs_raw])
+    og = torch.autograd.grad(oreg, [o.vars["Rx"], o.vars["Ry"], o.vars["freqs"]])
+    for a, b in zip(g, og):
+        assert rel(a.numpy(), b.numpy()) <= 1e-5
+
+
+def test_rho0_matches_oracle():
+    ohp, php = hp_pair(bond_dim=4, initial_rank=3)
+    raw = random_raw_params(ohp, np.random.default_rng(1), rho=True)
+    assert raw["Wx"].shape == (3, 4)
+    o = RhoCMPSOracle(ohp, raw)
+    m = RhoCMPS(php, device="cpu")
+    set_raw(m, raw)
+    assert relc(m.rho_0.detach().numpy(), o.rho_0.detach().numpy()) <= 1e-6
+    r = m.rho_0.detach().numpy()
+    assert abs(np.trace(r) - 1) < 1e-6 and np.abs(r - r.conj().T).max() < 1e-6   # tests/test_model.py:41-48
+
+
+def test_single_step_primitives_trivial_update():
+    """tests/test_model.py:69-83, 124-138 (H = R = 0 leaves the state untouched)."""
+    _, php = hp_pair(bond_dim=7, h_reg=2 / (np.pi * 16000) ** 2, r_reg=2 / (np.pi * 16000))
+    z = np.zeros((7, 7), np.complex64)
+    f0 = np.zeros(7, np.float32)
+    sig = np.random.default_rng(0).random(8).astype(np.float32)
+    m = PsiCMPS(php, freqs_in=f0, R_in=z, device="cpu")
+    st = m.psi_0.unsqueeze(0).repeat(8, 1)
+    np.testing.assert_allclose(m._update_ancilla_psi(st, sig, 0.).detach().numpy(), st.detach().numpy(), rtol=1e-6)
+    r = RhoCMPS(php, freqs_in=f0, R_in=z, device="cpu")
+    sr = r.rho_0.unsqueeze(0).repeat(8, 1, 1)
+    np.testing.assert_allclose(r._update_ancilla_rho(sr, sig, 0.).detach().numpy(), sr.detach().numpy(), rtol=1e-6)
+
+
+def test_single_step_primitives_match_oracle():
+    ohp, php = hp_pair(bond_dim=6, sigma=0.3, A=2.0)
+    raw = random_raw_params(ohp, np.random.default_rng(2))
+    o = PsiCMPSOracle(ohp, raw)
+    m = PsiCMPS(php, device="cpu")
+    set_raw(m, raw)
+    psi = o.psi_0.unsqueeze(0).repeat(3, 1)
+    sig = np.array([0.1, -0.2, 0.05], np.float32)
+    a = m._update_ancilla_psi(psi.detach(), sig, 0.37).detach().numpy()
+    b = o._update_ancilla_psi(psi, torch.tensor(sig), np.float32(0.37)).detach().numpy()
+    assert relc(a, b) <= 1e-5
+    assert rel(m._expectation(psi.detach(), 0.37).detach().numpy(),
+               o._expectation(psi, np.float32(0.37)).detach().numpy()) <= 1e-5
+
+
+def test_damped_sine_matches_oracle_generator():
+    a = D.damped_sine(4, 300, 1 / 16000, np.random.default_rng(5))
+    b = damped_sine(4, 300, 1 / 16000, np.random.default_rng(5))
+    assert a.shape == (4, 300) and a.dtype == np.float32            # tests/test_data.py:12-16
+    np.testing.assert_array_equal(a, b)
+    assert np.abs(a).max() <= 1.0
+
+
+def test_tfrecord_roundtrip(tmp_path):
+    """{audio: float32[sample_duration]} TFRecords (data.py:27-43) without TensorFlow."""
+    clips = np.random.default_rng(0).standard_normal((5, 64)).astype(np.float32)
+    path = str(tmp_path / "guitar.tfrecords")
+    D.write_tfrecords(path, clips)
+    recs = list(D.iter_tfrecords(path))
+    assert len(recs) == 5
+    np.testing.assert_array_equal(D.parse_example_float_feature(recs[3], "audio"), clips[3])
+    with pytest.raises(KeyError):
+        D.parse_example_float_feature(recs[0], "pitch")
+    hp = HParams(minibatch_size=2, delta_t=1 / 16000)
+    it = D.get_audio(str(tmp_path), "guitar", hp, sample_duration=64)
+    b0, b1, b2, b3 = next(it), next(it), next(it), next(it)
+    assert b0.shape == (2, 64) and b2.shape == (1, 64)              # ragged last batch, then repeat
+    np.testing.assert_array_equal(b3, clips[:2])
+    with pytest.raises(ValueError):
+        next(D.get_audio(str(tmp_path), "guitar", hp, sample_duration=32))
+
+
+def test_shard_bounds():
+    for gb, world in ((2048, 8), (64, 1), (10, 4), (3, 4)):
+        spans = [shard_bounds(gb, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == gb
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1

@@ -1,0 +1,70 @@
+"""CPU: the oracle (PyTorch restatement) and its C port against the committed golden vectors.
+This is what pins the checker: the reference holds no numbers of its own."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cref
+from oracle.cmps_oracle import PsiCMPSOracle, RhoCMPSOracle, grads_of, ref_test_hparams, total_loss
+from tests.golden_util import PSI_CASES, load, psi_case
+from tests.util import rel, relc
+
+
+@pytest.mark.parametrize("name", ["psi_testhp_d7", "psi_d32_t600"])
+def test_torch_oracle_reproduces_golden(name):
+    hp, raw, data, g = psi_case(name)
+    for mode, tol in (("f64", 1e-11), ("f32", 2e-5)):
+        o = PsiCMPSOracle(hp, raw, mode=mode)
+        assert rel(o.loss_per_clip(data).detach().numpy(), g[f"loss_{mode}"]) <= tol
+    o = PsiCMPSOracle(hp, raw, mode="f64")
+    gr = grads_of(o, total_loss(o, data))
+    for k, v in gr.items():
+        assert rel(v, g[f"grad_{k}_f64"]) <= 1e-9, k
+
+
+@pytest.mark.parametrize("name", PSI_CASES)
+def test_c_port_matches_golden(name):
+    """The C port takes float32 effective parameters, so it sits at float32 parameter rounding
+    (~1e-7 relative) from the float64 golden values, far inside every tolerance it is used for."""
+    hp, raw, data, g = psi_case(name)
+    R, f, p0, A = g["R_eff"].astype(np.complex64), g["freqs_eff"].astype(np.float32), \
+        g["psi0"].astype(np.complex64), float(hp.A)
+    loss, gR, gf, gp, gA = cref.psi_loss_grad(R, f, p0, A, hp.sigma, hp.delta_t, data, mode="f64")
+    assert rel(loss, g["loss_f64"]) <= 2e-6
+    assert relc(gR, g["geff_R"]) <= 2e-5
+    assert rel(gf, g["geff_f"]) <= 2e-5
+    assert relc(gp, g["geff_psi0"]) <= 2e-5
+    assert rel(gA, g["geff_A"]) <= 2e-5
+    # float32 arithmetic mode against the float32 golden: same algorithm, different summation order
+    l32 = cref.psi_loss(R, f, p0, A, hp.sigma, hp.delta_t, data, mode="f32")
+    assert rel(l32, g["loss_f32"]) <= 5e-4
+
+
+def test_float32_noise_floor_of_the_reference():
+    """How far the reference's own float32 arithmetic sits from exact arithmetic on BASELINE
+    config[0] -- the context for the 1e-4 loss tolerance."""
+    g = load("psi_c0_d8_t16000")
+    assert 1e-6 < rel(g["loss_f32"], g["loss_f64"]) < 2e-3
+
+
+def test_qubit_sampling_golden():
+    g = load("qubit_sampling")
+    from oracle.cmps_oracle import HP
+    hp = HP(minibatch_size=8, bond_dim=2, delta_t=1 / 16000, sigma=1, initial_rank=None, A=1.,
+            h_reg=2 / (np.pi * 16000) ** 2, r_reg=2 / (np.pi * 16000) ** 2)
+    R = np.array([[0, 1], [0, 0]], dtype=np.complex64)
+    fr = np.array([10, -10], dtype=np.float32)
+    q = PsiCMPSOracle(hp, {"psi_x": g["psi_x"], "psi_y": g["psi_y"]}, R_in=R, freqs_in=fr, mode="f64")
+    assert rel(q.sample_from_noise(g["noise"]).detach().numpy(), g["psi_sample_f64"]) <= 1e-10
+    p0 = q.psi_0.detach().numpy().astype(np.complex64)
+    c = cref.psi_sample(R, fr, p0, 1.0, 1.0, hp.delta_t, g["noise"], mode="f64")
+    assert rel(c, g["psi_sample_f64"]) <= 1e-5
+    r = RhoCMPSOracle(hp, None, W_in=g["W"], R_in=R, freqs_in=fr, mode="f64")
+    assert rel(r.sample_from_noise(g["noise"]).detach().numpy(), g["rho_sample_f64"]) <= 1e-10
+
+
+def test_rho_golden():
+    g = load("rho_testhp_d7")
+    raw = {k[4:]: g[k] for k in g if k.startswith("raw_")}
+    o = RhoCMPSOracle(ref_test_hparams(), raw, mode="f64")
+    assert rel(o.loss_per_clip(g["data"]).detach().numpy(), g["loss_f64"]) <= 1e-10
