@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <type_traits>
@@ -11,12 +12,15 @@
 #include "../../include/audiomps.h"
 #include "amps_prep.cuh"
 #include "amps_psi.cuh"
+#include "amps_psi_cluster.cuh"
 #include "amps_rho.cuh"
 
 using namespace amps;
 
 struct amps_ctx {
   int device = 0;
+  int num_sms = 0;
+  bool use_clusters = true;   // AMPS_NO_CLUSTER=1 disables the 2-CTA cluster kernels
   char err[512] = {0};
   int64_t launches = 0;
   // cached float32 time table
@@ -249,10 +253,13 @@ int amps_create(int device, amps_ctx** out) {
   amps_ctx* ctx = new (std::nothrow) amps_ctx();
   if (!ctx) return AMPS_E_INVALID;
   ctx->device = device;
-  if (cudaSetDevice(device) != cudaSuccess) {
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
     delete ctx;
     return AMPS_E_CUDA;
   }
+  const char* nc = getenv("AMPS_NO_CLUSTER");
+  ctx->use_clusters = !(nc && nc[0] == '1');
   *out = ctx;
   return AMPS_OK;
 }
@@ -354,6 +361,33 @@ int amps_psi_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
   return dispatch_dp(DP, [&](auto dp, auto nq) -> int {
     constexpr int DPc = decltype(dp)::value, NQc = decltype(nq)::value;
     constexpr bool WS = DPc <= 32;   // warp-specialised chain/filler kernel
+    if (WS && ctx->use_clusters && 2 * B <= ctx->num_sms) {
+      // enough idle SMs: one 2-CTA cluster per clip (chain CTA + filler CTA on a second SM)
+      auto kcl = psi_fwd_cl_kernel<DPc, NQc>;
+      const size_t smem_cl = sizeof(FwdClSmem<DPc, NQc>);
+      CUDA_TRY(ctx, cudaFuncSetAttribute(kcl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cl));
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(2 * B);
+      cfg.blockDim = dim3(DPc * NQc + 32);
+      cfg.dynamicSmemBytes = smem_cl;
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      PROF_BEGIN(ctx, 0, st);
+      CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, kcl, (const float2*)(ws + L.matN), (const float2*)(ws + L.matR),
+                                       (const float2*)(ws + L.matS), (const float2*)(ws + L.qtab),
+                                       (const float2*)(ws + L.psi0p), x_dev, T, p->A, loss_dev,
+                                       (double*)(ws + L.lossd), save ? (float2*)(ws + L.traj) : (float2*)nullptr,
+                                       save ? (float*)(ws + L.scales) : (float*)nullptr, nchunks));
+      PROF_END(ctx, 0, st);
+      LAUNCH_CHECK(ctx, "psi_fwd_cl_kernel");
+      return AMPS_OK;
+    }
     auto kern = WS ? psi_fwd_kernel<DPc, NQc> : psi_fwd_uni_kernel<DPc, NQc>;
     const size_t smem = WS ? sizeof(FwdSmem<DPc, NQc>) : sizeof(FwdSmemUni<DPc, NQc>);
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -396,6 +430,33 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
   rc = dispatch_dp(DP, [&](auto dp, auto nq) -> int {
     constexpr int DPc = decltype(dp)::value, NQc = decltype(nq)::value;
     constexpr bool WS = DPc <= 32;
+    if (WS && ctx->use_clusters && 2 * B <= ctx->num_sms) {
+      auto kcl = psi_bwd_cl_kernel<DPc, NQc>;
+      const size_t smem_cl = sizeof(BwdClSmem<DPc, NQc>);
+      CUDA_TRY(ctx, cudaFuncSetAttribute(kcl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cl));
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(2 * B);
+      cfg.blockDim = dim3(2 * DPc * NQc);
+      cfg.dynamicSmemBytes = smem_cl;
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      PROF_BEGIN(ctx, 1, st);
+      CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, kcl, (const float2*)(ws + L.matN), (const float2*)(ws + L.matRH),
+                                       (const float2*)(ws + L.matS), (const float2*)(ws + L.qtab),
+                                       (const float*)ctx->ttab, x_dev, T, p->A, w_dev,
+                                       (const float2*)(ws + L.traj), (const float*)(ws + L.scales), nchunks,
+                                       (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0),
+                                       (double*)(ws + L.gAdir)));
+      PROF_END(ctx, 1, st);
+      LAUNCH_CHECK(ctx, "psi_bwd_cl_kernel");
+      return AMPS_OK;
+    }
     auto kern = WS ? psi_bwd_kernel<DPc, NQc> : psi_bwd_uni_kernel<DPc, NQc>;
     const size_t smem = WS ? sizeof(BwdSmem<DPc, NQc>) : sizeof(BwdSmemUni<DPc>);
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

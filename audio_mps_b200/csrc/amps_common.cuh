@@ -75,6 +75,19 @@ __device__ __forceinline__ float2 lds64(const float2* p) {
   return v;
 }
 
+// Scheduling aid: makes the first use of a freshly loaded register slice depend on EVERY 128-bit
+// load of that slice, so ptxas issues all the LDS back to back right after the barrier instead of
+// sinking each one next to its first use (which exposes one shared-memory latency per load on the
+// chain's critical path -- ncu, profiles/r1_chain_schedule.md).  fmaf(g, 0, x) is not foldable
+// without fast-math.
+template <int N>
+__device__ __forceinline__ void tie_loads(float2 (&v)[N]) {
+  float g = 0.f;
+#pragma unroll
+  for (int m = 2; m < N; m += 2) g += v[m].x;
+  v[0].x = fmaf(g, 0.0f, v[0].x);
+}
+
 // ---- thread map ---------------------------------------------------------------------------
 // A CTA of DP*NQ threads owns one clip.  Thread t = i*NQ + jq holds, for matrix row i, the
 // CPT = DP/NQ columns  col(c) = 2*NQ*(c/2) + 2*jq + (c&1)  in registers, so that for a fixed
@@ -155,4 +168,42 @@ __device__ __forceinline__ float warp_sum_f(float v) {
   return v;
 }
 
+}  // namespace amps
+
+// ---- thread-block cluster / distributed shared memory helpers --------------------------------
+namespace amps {
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+// shared::cluster address of the same shared-memory object in CTA `rank` of this cluster
+__device__ __forceinline__ unsigned dsmem_addr(const void* local, unsigned rank) {
+  const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(local));
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(a), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(unsigned addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_dsmem_f4(unsigned addr, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_dsmem_f1(unsigned addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;\n" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_arrive_release() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait_acquire() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
 }  // namespace amps

@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(2 * DP * NQ)
             xv[2 * m] = make_float2(v.x, v.y);
             xv[2 * m + 1] = make_float2(v.z, v.w);
           }
+          tie_loads(xv);
           const float2 q = sm.qs[p][kk][i];
           const float s_next = sm.sv[p][kk + 1];
           float2 a0 = make_float2(0.f, 0.f), a1 = a0;
@@ -341,6 +342,7 @@ __global__ void __launch_bounds__(2 * DP * NQ)
             mv[2 * m] = make_float2(v.x, v.y);
             mv[2 * m + 1] = make_float2(v.z, v.w);
           }
+          tie_loads(mv);
           const float s = sm.sv[c % 3][kk];
           const float4 b4 = sm.cinb[ca][kk][i];                    // { beta x_k , dtm x_k }
           const float4 a4 = sm.cina[ca][kk > 0 ? kk - 1 : 0][i];   // { c q , alpha S x' } of step kk-1

@@ -1,0 +1,545 @@
+// Cluster variants of the Psi scan kernels (sm_100a thread-block clusters + distributed shared
+// memory).  Used when the batch leaves SMs idle (2*B <= #SMs, e.g. BASELINE config C1: 64 clips on
+// 148 SMs): each clip gets a CLUSTER OF TWO CTAs on two SMs --
+//     rank 0  CHAIN CTA : nothing but the sequential recursion (4 chain warps + 1 loader warp)
+//     rank 1  FILLER CTA: everything else, on its own SM, so it no longer competes with the chain
+//                         for FMA issue slots or the shared-memory pipe
+// The filler pulls each finished 32-step chunk (x_k, x'_k rings) out of the chain CTA's shared
+// memory with ld.shared::cluster, and (backward) pushes the packed per-row chain inputs into it with
+// st.shared::cluster; the two CTAs meet at one barrier.cluster per chunk.
+// Measured motivation (profiles/): with the filler warps on the same SM the forward chain runs at
+// ~410 cycles/step, alone at ~297.
+#pragma once
+#include "amps_psi.cuh"
+
+namespace amps {
+
+template <int DP, int NQ>
+struct alignas(16) FwdClSmem {
+  static constexpr int NTC = DP * NQ, G = NTC / CH, ES = NTC + (G < 32 ? G : 0);
+  float2 xs[2][CH + 1][DP];   // chain CTA: rings by chunk parity; filler CTA: xs[0] = local copy
+  float2 xps[2][CH][DP];
+  float2 qs[2][CH][DP];       // chain CTA
+  float es[CH][ES];           // filler CTA
+  float wav[2][CH + 4];
+  float sv[2][CH + 4];
+  float incv[2][CH];
+  double lred[32];
+};
+
+// block = NTC + 32 threads; grid = 2*B CTAs in clusters of 2
+template <int DP, int NQ>
+__global__ void __launch_bounds__(DP* NQ + 32)
+    psi_fwd_cl_kernel(const float2* __restrict__ matN, const float2* __restrict__ matR,
+                      const float2* __restrict__ matS, const float2* __restrict__ qtab,
+                      const float2* __restrict__ psi0p, const float* __restrict__ x, int T, float A,
+                      float* __restrict__ loss, double* __restrict__ lossd,
+                      float2* __restrict__ traj, float* __restrict__ scales, int nchunks) {
+  using M = Map<DP, NQ>;
+  using Sm = FwdClSmem<DP, NQ>;
+  constexpr int NTC = M::NT;
+  constexpr int CPT = M::CPT;
+  constexpr int G = Sm::G;
+  constexpr int LV = (NQ == 4) ? 2 : 3;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Sm& sm = *reinterpret_cast<Sm*>(smem_raw);
+
+  const int t = threadIdx.x;
+  const unsigned rank = cluster_ctarank();
+  const int b = blockIdx.x >> 1;
+  const int nsteps = T - 1;
+  const float* xb = x + (size_t)b * T;
+  const int lane = t & 31;
+  auto chunk_len = [&](int c) { return min(CH, nsteps - c * CH); };
+
+  if (rank == 0) {
+    // ===================================== CHAIN CTA ==========================================
+    const bool is_loader = t >= NTC;           // last warp: prefetch of q_k / waveform, s_k
+    const int i = t / NQ, jq = t % NQ;         // (chain threads)
+    auto load_inputs = [&](int c) {            // loader warp only
+      const int buf = c & 1, k0 = c * CH, len = chunk_len(c);
+      const float2* qsrc = qtab + (size_t)k0 * DP;
+      float2* qdst = &sm.qs[buf][0][0];
+      for (int idx = lane; idx < len * DP / 2; idx += 32) cp_async16(qdst + 2 * idx, qsrc + 2 * idx);
+      for (int idx = lane; idx <= len; idx += 32) cp_async4(&sm.wav[buf][idx], xb + k0 + idx);
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncwarp();
+      if (lane < len) sm.sv[buf][lane] = (sm.wav[buf][lane + 1] - sm.wav[buf][lane]) / A;   // model.py:263,303
+    };
+    if (t < DP) {
+      const float2 p = psi0p[t];
+      sm.xs[0][0][t] = p;
+      if (traj) traj[(size_t)b * T * DP + t] = p;
+    }
+    if (is_loader && nchunks > 0) load_inputs(0);
+    __syncthreads();
+
+    float2 Nr[CPT], Rr[CPT];
+    if (!is_loader) {
+      load_slice<DP, NQ>(Nr, matN, i, jq);
+      load_slice<DP, NQ>(Rr, matR, i, jq);
+    }
+    float2 vstart = make_float2(0.f, 0.f);
+    for (int c = 0; c <= nchunks; ++c) {
+      if (c < nchunks) {
+        const int p = c & 1, len = chunk_len(c);
+        if (is_loader) {
+          if (c + 1 < nchunks) load_inputs(c + 1);
+        } else {
+          if (c > 0) {
+            if (t < DP) sm.xs[p][0][t] = vstart;
+            bar_named(1, NTC);
+          }
+          float2* const st2 = (jq == 0) ? &sm.xs[p][1][i] : &sm.xps[p][0][i];
+          const bool st2_on = jq < 2;
+          float s_cur = sm.sv[p][0];
+          auto step = [&](int kk) {
+            float2 xv[CPT];
+#pragma unroll
+            for (int m = 0; m < CPT / 2; ++m) {
+              const float4 v = *reinterpret_cast<const float4*>(&sm.xs[p][kk][2 * NQ * m + 2 * jq]);
+              xv[2 * m] = make_float2(v.x, v.y);
+              xv[2 * m + 1] = make_float2(v.z, v.w);
+            }
+            tie_loads(xv);
+            const float2 q = sm.qs[p][kk][i];
+            const float s_next = sm.sv[p][kk + 1];
+            float2 a0 = make_float2(0.f, 0.f), a1 = a0;
+#pragma unroll
+            for (int cc = 0; cc < CPT; cc += 2) {
+              const float2 l0 = make_float2(fmaf(s_cur, Rr[cc].x, Nr[cc].x), fmaf(s_cur, Rr[cc].y, Nr[cc].y));
+              const float2 l1 = make_float2(fmaf(s_cur, Rr[cc + 1].x, Nr[cc + 1].x),
+                                            fmaf(s_cur, Rr[cc + 1].y, Nr[cc + 1].y));
+              cmac(a0, l0, xv[cc]);
+              cmac(a1, l1, xv[cc + 1]);
+            }
+            float2 xp = make_float2(a0.x + a1.x, a0.y + a1.y);
+#pragma unroll
+            for (int lv = 0; lv < LV; ++lv) {
+              xp.x += __shfl_xor_sync(0xffffffffu, xp.x, 1 << lv);
+              xp.y += __shfl_xor_sync(0xffffffffu, xp.y, 1 << lv);
+            }
+            const float2 xn = cmul(q, xp);
+            sts_if(st2_on, st2 + kk * DP, (jq == 0) ? xn : xp);
+            s_cur = s_next;
+            bar_named(1, NTC);
+          };
+          if (len == CH) {
+#pragma unroll 2
+            for (int kk = 0; kk < CH; ++kk) step(kk);
+          } else {
+            for (int kk = 0; kk < len; ++kk) step(kk);
+          }
+          float n2 = 0.f;
+          for (int r = lane; r < DP; r += 32) n2 += cabs2(sm.xs[p][len][r]);
+          n2 = warp_sum_f(n2);
+          const float sc = rsqrtf(n2);
+          bar_named(1, NTC);
+          if (t < DP) {
+            float2 v = sm.xs[p][len][t];
+            v.x *= sc;
+            v.y *= sc;
+            sm.xs[p][len][t] = v;
+            vstart = v;
+          }
+          if (t == 0 && scales) scales[(size_t)b * nchunks + c] = sc;
+        }
+      }
+      __syncthreads();
+      cluster_arrive_release();   // chunk c is complete in ring c&1 ...
+      cluster_wait_acquire();     // ... and the filler CTA has copied chunk c-1 out of ring (c-1)&1
+    }
+  } else {
+    // ===================================== FILLER CTA =========================================
+    const int tr = t;
+    const bool work = tr < NTC;                // the extra warp only takes part in the barriers
+    const int i = (work ? tr : 0) / NQ, jq = tr % NQ;
+    float2 Sr[CPT];
+    if (work) load_slice<DP, NQ>(Sr, matS, i, jq);
+    double lossacc = 0.0;
+    __syncthreads();
+    for (int c = 0; c <= nchunks; ++c) {
+      if (c >= 1) {
+        const int cc = c - 1, p = cc & 1, len = chunk_len(cc), k0 = cc * CH;
+        // waveform of chunk cc (for inc_k)
+        for (int idx = t; idx <= len; idx += blockDim.x) cp_async4(&sm.wav[0][idx], xb + k0 + idx);
+        cp_async_commit();
+        // pull the chunk out of the chain CTA's rings (distributed shared memory)
+        {
+          const unsigned rx = dsmem_addr(&sm.xs[p][0][0], 0);
+          const unsigned rp = dsmem_addr(&sm.xps[p][0][0], 0);
+          float4* lx = reinterpret_cast<float4*>(&sm.xs[0][0][0]);
+          float4* lp = reinterpret_cast<float4*>(&sm.xps[0][0][0]);
+          for (int idx = t; idx < (len + 1) * DP / 2; idx += blockDim.x) lx[idx] = ld_dsmem_f4(rx + 16 * idx);
+          for (int idx = t; idx < len * DP / 2; idx += blockDim.x) lp[idx] = ld_dsmem_f4(rp + 16 * idx);
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+        if (t < len) sm.incv[0][t] = sm.wav[0][t + 1] - sm.wav[0][t];
+        if (work) {
+          for (int kk = 0; kk < len; ++kk) {
+            const float2 part = matvec1<DP, NQ>(Sr, sm.xps[0][kk], jq);
+            const float2 xpi = sm.xps[0][kk][i];
+            sm.es[kk][tr] = fmaf(xpi.x, part.x, xpi.y * part.y);
+          }
+        }
+        __syncthreads();
+        if (work) {
+          const int kk = tr / G, g = tr % G;
+          float en = 0.f, nu2 = 0.f;
+          if (kk < len) {
+#pragma unroll 8
+            for (int r = 0; r < NTC / G; ++r) en += sm.es[kk][g + G * r];
+            for (int r = g; r < DP; r += G) nu2 += cabs2(sm.xs[0][kk][r]);
+          }
+#pragma unroll
+          for (int m = 1; m < G && m < 32; m <<= 1) {
+            en += __shfl_xor_sync(0xffffffffu, en, m);
+            nu2 += __shfl_xor_sync(0xffffffffu, nu2, m);
+          }
+          if (g == 0 && kk < len) {
+            const float E = en / nu2;                                  // model.py:324-325 on x'
+            const float z = (E * sm.incv[0][kk]) / A;                  // model.py:294
+            lossacc -= (double)log1pf(z);
+          }
+        }
+        if (traj) {
+          const float4* src = reinterpret_cast<const float4*>(&sm.xs[0][1][0]);
+          float4* dst = reinterpret_cast<float4*>(traj + ((size_t)b * T + k0 + 1) * DP);
+          for (int idx = t; idx < len * DP / 2; idx += blockDim.x) dst[idx] = src[idx];
+        }
+      }
+      __syncthreads();
+      cluster_arrive_release();
+      cluster_wait_acquire();
+    }
+    lossacc = warp_sum_d(lossacc);
+    if (lane == 0) sm.lred[t >> 5] = lossacc;
+    __syncthreads();
+    if (t == 0) {
+      double tot = 0.0;
+      for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) tot += sm.lred[wv];
+      loss[b] = (float)tot;
+      if (lossd) lossd[b] = tot;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// backward, cluster variant.  block = 256 threads in both CTAs.
+//   rank 0 CHAIN CTA : threads 0..127 run the adjoint recursion; it only ever touches its own
+//                      shared memory (packed inputs pushed by the filler, mu ring).
+//   rank 1 FILLER CTA: threads 0..127 "prep" group  -- cp.async of trajectory / q / waveform, x', S x',
+//                      alpha, beta, packed rows pushed into the chain CTA (st.shared::cluster);
+//                      threads 128..255 "tiles" group -- pull the finished chunk's mu ring
+//                      (ld.shared::cluster) and accumulate the rank-1 gradient tiles.
+// Slot c (c = nchunks .. -1): chain runs chunk c; prep prepares chunk c-1 and loads chunk c-2;
+// tiles accumulate chunk c+1.  One barrier.cluster per slot.
+// -------------------------------------------------------------------------------------------
+template <int DP, int NQ>
+struct alignas(16) BwdClSmem {
+  // ---- chain CTA ----
+  float4 cina[2][CH][DP];      // { c_k q_k , alpha_k (S x'_k)_i }
+  float4 cinb[2][CH][DP];      // { beta_k x_k,i , dtm_k x_k,i }
+  float2 mus[2][CH][DP];       // adjoint of x'_k
+  float svc[2][CH];            // s_k for the chain
+  // ---- filler CTA ----
+  float2 xs[4][CH + 1][DP];
+  float2 qs[2][CH][DP];
+  float2 xps[3][CH][DP];
+  float2 mul[CH][DP];          // local copy of the pulled mu ring
+  float2 sps[CH][DP];
+  float es[CH][DP + 1];
+  float ns[CH][DP + 1];
+  float wav[2][CH + 4];
+  float tt[2][CH + 4];
+  float scs[2][4];
+  float sv[3][CH], alphas[3][CH];
+  float incv[CH], betas[CH], dtm[CH];
+  double lred[32];
+};
+
+template <int DP, int NQ>
+__global__ void __launch_bounds__(2 * DP * NQ)
+    psi_bwd_cl_kernel(const float2* __restrict__ matN, const float2* __restrict__ matRH,
+                      const float2* __restrict__ matS, const float2* __restrict__ qtab,
+                      const float* __restrict__ ttab, const float* __restrict__ x, int T, float A,
+                      const float* __restrict__ w, const float2* __restrict__ traj,
+                      const float* __restrict__ scales, int nchunks, float2* __restrict__ Gout,
+                      float* __restrict__ gfout, float2* __restrict__ lam0out,
+                      double* __restrict__ gAdir) {
+  using M = Map<DP, NQ>;
+  using Sm = BwdClSmem<DP, NQ>;
+  constexpr int NTC = M::NT;
+  constexpr int CPT = M::CPT;
+  constexpr int NP = M::NP;
+  constexpr int G = NTC / CH, PER = DP / G;
+  static_assert(DP % G == 0 && G <= 32, "scalar-phase grouping");
+  constexpr int LV = (NQ == 4) ? 2 : 3;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Sm& sm = *reinterpret_cast<Sm*>(smem_raw);
+
+  const int t = threadIdx.x;
+  const unsigned rank = cluster_ctarank();
+  const int b = blockIdx.x >> 1;
+  const int nsteps = T - 1;
+  const int lane = t & 31;
+  const int grp = t / NTC;                 // 0 or 1
+  const int tr = t - grp * NTC;
+  const int i = tr / NQ, jq = tr % NQ;
+  auto chunk_len = [&](int c) { return min(CH, nsteps - c * CH); };
+
+  if (rank == 0) {
+    // ===================================== CHAIN CTA ==========================================
+    float2 Nr[CPT], Hr[CPT];
+    float2 lam = make_float2(0.f, 0.f);
+    float gf = 0.f;
+    if (grp == 0) {
+      load_slice<DP, NQ>(Nr, matN, i, jq);
+      load_slice<DP, NQ>(Hr, matRH, i, jq);
+    }
+    const bool mu_on = jq == 0;
+    for (int c = nchunks; c >= -1; --c) {
+      if (grp == 0 && c >= 0 && c < nchunks) {
+        const int ca = c & 1, len = chunk_len(c);
+        float2* const mu_st = &sm.mus[ca][0][i];
+        {
+          const float4 a4 = sm.cina[ca][len - 1][i];
+          float2 mu = cmul_ca(make_float2(a4.x, a4.y), lam);
+          mu.x += a4.z;
+          mu.y += a4.w;
+          sts_if(mu_on, mu_st + (len - 1) * DP, mu);
+        }
+        bar_named(1, NTC);
+        auto step = [&](int kk) {
+          float2 mv[CPT];
+#pragma unroll
+          for (int m = 0; m < NP; ++m) {
+            const float4 v = *reinterpret_cast<const float4*>(&sm.mus[ca][kk][2 * NQ * m + 2 * jq]);
+            mv[2 * m] = make_float2(v.x, v.y);
+            mv[2 * m + 1] = make_float2(v.z, v.w);
+          }
+          tie_loads(mv);
+          const float s = sm.svc[ca][kk];
+          const float4 b4 = sm.cinb[ca][kk][i];
+          const float4 a4 = sm.cina[ca][kk > 0 ? kk - 1 : 0][i];
+          float2 a0 = make_float2(0.f, 0.f), a1 = a0;
+#pragma unroll
+          for (int cc = 0; cc < CPT; cc += 2) {
+            const float2 l0 = make_float2(fmaf(s, Hr[cc].x, Nr[cc].x), fmaf(s, Hr[cc].y, Nr[cc].y));
+            const float2 l1 = make_float2(fmaf(s, Hr[cc + 1].x, Nr[cc + 1].x),
+                                          fmaf(s, Hr[cc + 1].y, Nr[cc + 1].y));
+            cmac(a0, l0, mv[cc]);
+            cmac(a1, l1, mv[cc + 1]);
+          }
+          float2 lp = make_float2(a0.x + a1.x, a0.y + a1.y);
+#pragma unroll
+          for (int lv = 0; lv < LV; ++lv) {
+            lp.x += __shfl_xor_sync(0xffffffffu, lp.x, 1 << lv);
+            lp.y += __shfl_xor_sync(0xffffffffu, lp.y, 1 << lv);
+          }
+          lam.x = lp.x + b4.x;
+          lam.y = lp.y + b4.y;
+          gf = fmaf(lam.x, b4.w, fmaf(-lam.y, b4.z, gf));
+          float2 mu = cmul_ca(make_float2(a4.x, a4.y), lam);
+          mu.x += a4.z;
+          mu.y += a4.w;
+          sts_if(mu_on && kk > 0, mu_st + (kk > 0 ? kk - 1 : 0) * DP, mu);
+          bar_named(1, NTC);
+        };
+        if (len == CH) {
+#pragma unroll 2
+          for (int kk = CH - 1; kk >= 0; --kk) step(kk);
+        } else {
+          for (int kk = len - 1; kk >= 0; --kk) step(kk);
+        }
+      }
+      __syncthreads();
+      cluster_arrive_release();
+      cluster_wait_acquire();
+    }
+    if (grp == 0 && jq == 0) {
+      gfout[(size_t)b * DP + i] = gf;
+      lam0out[(size_t)b * DP + i] = lam;
+    }
+  } else {
+    // ===================================== FILLER CTA =========================================
+    const float* xb = x + (size_t)b * T;
+    const float2* trb = traj + (size_t)b * T * DP;
+    const float wb = w[b];
+    float2 Sr[CPT];
+    load_slice<DP, NQ>(Sr, matS, i, jq);
+    float2 GR[CPT], GN[CPT], GE[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) GR[c] = GN[c] = GE[c] = make_float2(0.f, 0.f);
+    double gAacc = 0.0;
+
+    auto issue_loads = [&](int c) {          // prep group
+      const int k0 = c * CH, len = chunk_len(c);
+      const float2* xsrc = trb + (size_t)k0 * DP;
+      float2* xdst = &sm.xs[c & 3][0][0];
+      for (int idx = tr; idx < (len + 1) * DP / 2; idx += NTC) cp_async16(xdst + 2 * idx, xsrc + 2 * idx);
+      const float2* qsrc = qtab + (size_t)k0 * DP;
+      float2* qdst = &sm.qs[c & 1][0][0];
+      for (int idx = tr; idx < len * DP / 2; idx += NTC) cp_async16(qdst + 2 * idx, qsrc + 2 * idx);
+      for (int idx = tr; idx <= len; idx += NTC) {
+        cp_async4(&sm.wav[c & 1][idx], xb + k0 + idx);
+        cp_async4(&sm.tt[c & 1][idx], ttab + (k0 + idx > 0 ? k0 + idx - 1 : 0));
+      }
+      if (tr == 0) cp_async4(&sm.scs[c & 1][0], scales + (size_t)b * nchunks + c);
+    };
+
+    auto tiles_chunk = [&](int c) {          // tiles group
+      const int len = chunk_len(c);
+      {  // pull the chunk's mu ring out of the chain CTA
+        const unsigned rm = dsmem_addr(&sm.mus[c & 1][0][0], 0);
+        float4* lm = reinterpret_cast<float4*>(&sm.mul[0][0]);
+        for (int idx = tr; idx < len * DP / 2; idx += NTC) lm[idx] = ld_dsmem_f4(rm + 16 * idx);
+      }
+      bar_named(3, NTC);
+      const float2(*xsb)[DP] = sm.xs[c & 3];
+      const float2(*xpb)[DP] = sm.xps[c % 3];
+      for (int kk = 0; kk < len; ++kk) {
+        const float2 mui = sm.mul[kk][i];
+        const float2 xpi = xpb[kk][i];
+        const float s = sm.sv[c % 3][kk];
+        const float al = sm.alphas[c % 3][kk];
+        const float2 u1 = make_float2(s * mui.x, s * mui.y);
+        const float2 u3 = make_float2(al * xpi.x, al * xpi.y);
+#pragma unroll
+        for (int m = 0; m < NP; ++m) {
+          const float4 xv = *reinterpret_cast<const float4*>(&xsb[kk][2 * NQ * m + 2 * jq]);
+          const float4 pv = *reinterpret_cast<const float4*>(&xpb[kk][2 * NQ * m + 2 * jq]);
+          const float2 x0 = make_float2(xv.x, xv.y), x1 = make_float2(xv.z, xv.w);
+          const float2 p0 = make_float2(pv.x, pv.y), p1 = make_float2(pv.z, pv.w);
+          cmac_cx(GR[2 * m], u1, x0);
+          cmac_cx(GR[2 * m + 1], u1, x1);
+          cmac_cx(GN[2 * m], mui, x0);
+          cmac_cx(GN[2 * m + 1], mui, x1);
+          cmac_cx(GE[2 * m], u3, p0);
+          cmac_cx(GE[2 * m + 1], u3, p1);
+        }
+      }
+    };
+
+    auto prep_chunk = [&](int c) {           // prep group
+      const int len = chunk_len(c), k0 = c * CH;
+      const int lx = c & 3, lq = c & 1, lp3 = c % 3;
+      const float sc = sm.scs[lq][0];
+      const float inv_sc = 1.0f / sc;
+      const unsigned ra = dsmem_addr(&sm.cina[lq][0][0], 0);
+      const unsigned rb = dsmem_addr(&sm.cinb[lq][0][0], 0);
+      const unsigned rs = dsmem_addr(&sm.svc[lq][0], 0);
+      if (tr < len) {
+        const float inc = sm.wav[lq][tr + 1] - sm.wav[lq][tr];
+        const float s = inc / A;
+        sm.incv[tr] = inc;
+        sm.sv[lp3][tr] = s;
+        st_dsmem_f1(rs + 4 * tr, s);
+        sm.dtm[tr] = (k0 + tr > 0) ? sm.tt[lq][tr + 1] - sm.tt[lq][tr] : 0.f;
+      }
+      for (int idx = tr; idx < len * DP; idx += NTC) {
+        const int kk = idx / DP, r = idx % DP;
+        float2 xp = cmul_ca(sm.qs[lq][kk][r], sm.xs[lx][kk + 1][r]);
+        if (kk == len - 1) {
+          xp.x *= inv_sc;
+          xp.y *= inv_sc;
+        }
+        sm.xps[lp3][kk][r] = xp;
+        sm.ns[kk][r] = cabs2(sm.xs[lx][kk][r]);
+      }
+      bar_named(2, NTC);
+      for (int kk = 0; kk < len; ++kk) {
+        float2 part = matvec1<DP, NQ>(Sr, sm.xps[lp3][kk], jq);
+        part = group_sum<NQ>(part);
+        const float2 xpi = sm.xps[lp3][kk][i];
+        sts_if(jq == 1, &sm.sps[kk][i], part);
+        sts_if(jq == 2, &sm.es[kk][i], fmaf(xpi.x, part.x, xpi.y * part.y));
+      }
+      bar_named(2, NTC);
+      {
+        const int kk = tr / G, g = tr % G;
+        float en = 0.f, nu2 = 0.f;
+        if (kk < len) {
+#pragma unroll
+          for (int r = 0; r < PER; ++r) {
+            en += sm.es[kk][g * PER + r];
+            nu2 += sm.ns[kk][g * PER + r];
+          }
+        }
+#pragma unroll
+        for (int m = 1; m < G; m <<= 1) {
+          en += __shfl_xor_sync(0xffffffffu, en, m);
+          nu2 += __shfl_xor_sync(0xffffffffu, nu2, m);
+        }
+        if (g == 0 && kk < len) {
+          const float E = en / nu2;
+          const float inc = sm.incv[kk];
+          const float arg = 1.0f + (E * inc) / A;
+          const float gE = wb * (-sm.sv[lp3][kk] / arg);
+          const float alpha = 2.0f * gE / nu2;
+          sm.alphas[lp3][kk] = alpha;
+          sm.betas[kk] = -alpha * E;
+          gAacc += (double)wb * (double)E * (double)inc / ((double)A * (double)A * (double)arg);
+        }
+      }
+      bar_named(2, NTC);
+      // packed per-row chain inputs, pushed straight into the chain CTA's shared memory
+      for (int idx = tr; idx < len * DP; idx += NTC) {
+        const int kk = idx / DP, r = idx % DP;
+        float2 q = sm.qs[lq][kk][r];
+        if (kk == len - 1) {
+          q.x *= sc;
+          q.y *= sc;
+        }
+        const float al = sm.alphas[lp3][kk], be = sm.betas[kk], dt = sm.dtm[kk];
+        const float2 sp = sm.sps[kk][r];
+        const float2 xk = sm.xs[lx][kk][r];
+        st_dsmem_f4(ra + 16 * idx, make_float4(q.x, q.y, al * sp.x, al * sp.y));
+        st_dsmem_f4(rb + 16 * idx, make_float4(be * xk.x, be * xk.y, dt * xk.x, dt * xk.y));
+      }
+    };
+
+    if (grp == 0) {
+      if (nchunks > 0) issue_loads(nchunks - 1);
+      cp_async_commit();
+    }
+    for (int c = nchunks; c >= -1; --c) {
+      if (grp == 0) {
+        if (c - 2 >= 0) issue_loads(c - 2);
+        cp_async_commit();
+        cp_async_wait<1>();
+        bar_named(2, NTC);
+        if (c - 1 >= 0) prep_chunk(c - 1);
+      } else {
+        if (c + 1 >= 0 && c + 1 < nchunks) tiles_chunk(c + 1);
+      }
+      __syncthreads();
+      cluster_arrive_release();
+      cluster_wait_acquire();
+    }
+    if (grp == 0) {
+      cp_async_wait<0>();
+      gAacc = warp_sum_d(gAacc);
+      if (lane == 0) sm.lred[tr >> 5] = gAacc;
+      bar_named(2, NTC);
+      if (tr == 0) {
+        double tot = 0.0;
+        for (int wv = 0; wv < NTC / 32; ++wv) tot += sm.lred[wv];
+        gAdir[b] = tot;
+      }
+    } else {
+      float2* Gb = Gout + (size_t)b * 3 * DP * DP;
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        const int col = M::col(c, jq);
+        Gb[0 * DP * DP + i * DP + col] = GR[c];
+        Gb[1 * DP * DP + i * DP + col] = GN[c];
+        Gb[2 * DP * DP + i * DP + col] = GE[c];
+      }
+    }
+  }
+}
+
+}  // namespace amps
