@@ -139,7 +139,7 @@ int dispatch_dp(int DP, F&& f) {
 
 struct PsiWs {
   size_t matN, matR, matRH, matS, psi0p, qtab, lossd;
-  size_t traj, scales, G, gf, lam0, gAdir, Gtot, gftot, lam0tot;
+  size_t traj, scales, G, gf, lam0, gAdir, Gtot, gftot, lam0tot, sptraj, ev;
   size_t total;
 };
 
@@ -171,6 +171,8 @@ PsiWs psi_ws_layout(int DP, int B, int nsteps_tab, int T, bool save) {
     w.Gtot = take(3 * mat);
     w.gftot = take((size_t)DP * sizeof(float));
     w.lam0tot = take((size_t)DP * sizeof(float2));
+    w.sptraj = take((size_t)B * T * DP * sizeof(float2));   // S x'_k (cluster kernels)
+    w.ev = take((size_t)B * T * sizeof(float2));            // (E_k, |x_k|^2)
   }
   w.total = off;
   return w;
@@ -383,7 +385,9 @@ int amps_psi_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
                                        (const float2*)(ws + L.matS), (const float2*)(ws + L.qtab),
                                        (const float2*)(ws + L.psi0p), x_dev, T, p->A, loss_dev,
                                        (double*)(ws + L.lossd), save ? (float2*)(ws + L.traj) : (float2*)nullptr,
-                                       save ? (float*)(ws + L.scales) : (float*)nullptr, nchunks));
+                                       save ? (float*)(ws + L.scales) : (float*)nullptr, nchunks,
+                                       save ? (float2*)(ws + L.sptraj) : (float2*)nullptr,
+                                       save ? (float2*)(ws + L.ev) : (float2*)nullptr));
       PROF_END(ctx, 0, st);
       LAUNCH_CHECK(ctx, "psi_fwd_cl_kernel");
       return AMPS_OK;
@@ -432,11 +436,11 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
     constexpr bool WS = DPc <= 32;
     if (WS && ctx->use_clusters && 2 * B <= ctx->num_sms) {
       auto kcl = psi_bwd_cl_kernel<DPc, NQc>;
-      const size_t smem_cl = sizeof(BwdClSmem<DPc, NQc>);
+      const size_t smem_cl = bwd_cl_smem_bytes<DPc, NQc>();
       CUDA_TRY(ctx, cudaFuncSetAttribute(kcl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cl));
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(2 * B);
-      cfg.blockDim = dim3(2 * DPc * NQc);
+      cfg.blockDim = dim3(3 * DPc * NQc);
       cfg.dynamicSmemBytes = smem_cl;
       cfg.stream = st;
       cudaLaunchAttribute at[1];
@@ -452,7 +456,8 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
                                        (const float*)ctx->ttab, x_dev, T, p->A, w_dev,
                                        (const float2*)(ws + L.traj), (const float*)(ws + L.scales), nchunks,
                                        (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0),
-                                       (double*)(ws + L.gAdir)));
+                                       (double*)(ws + L.gAdir), (const float2*)(ws + L.sptraj),
+                                       (const float2*)(ws + L.ev)));
       PROF_END(ctx, 1, st);
       LAUNCH_CHECK(ctx, "psi_bwd_cl_kernel");
       return AMPS_OK;

@@ -21,6 +21,7 @@ struct alignas(16) FwdClSmem {
   float2 xps[2][CH][DP];
   float2 qs[2][CH][DP];       // chain CTA
   float es[CH][ES];           // filler CTA
+  float2 spp[CH][NQ][DP];     // filler CTA: per-lane partials of S x'_k
   float wav[2][CH + 4];
   float sv[2][CH + 4];
   float incv[2][CH];
@@ -34,7 +35,8 @@ __global__ void __launch_bounds__(DP* NQ + 32)
                       const float2* __restrict__ matS, const float2* __restrict__ qtab,
                       const float2* __restrict__ psi0p, const float* __restrict__ x, int T, float A,
                       float* __restrict__ loss, double* __restrict__ lossd,
-                      float2* __restrict__ traj, float* __restrict__ scales, int nchunks) {
+                      float2* __restrict__ traj, float* __restrict__ scales, int nchunks,
+                      float2* __restrict__ sptraj, float2* __restrict__ evout) {
   using M = Map<DP, NQ>;
   using Sm = FwdClSmem<DP, NQ>;
   constexpr int NTC = M::NT;
@@ -181,6 +183,7 @@ __global__ void __launch_bounds__(DP* NQ + 32)
           for (int kk = 0; kk < len; ++kk) {
             const float2 part = matvec1<DP, NQ>(Sr, sm.xps[0][kk], jq);
             const float2 xpi = sm.xps[0][kk][i];
+            sm.spp[kk][jq][i] = part;
             sm.es[kk][tr] = fmaf(xpi.x, part.x, xpi.y * part.y);
           }
         }
@@ -202,12 +205,26 @@ __global__ void __launch_bounds__(DP* NQ + 32)
             const float E = en / nu2;                                  // model.py:324-325 on x'
             const float z = (E * sm.incv[0][kk]) / A;                  // model.py:294
             lossacc -= (double)log1pf(z);
+            if (evout) evout[(size_t)b * T + k0 + kk] = make_float2(E, nu2);   // for the adjoint sweep
           }
         }
         if (traj) {
           const float4* src = reinterpret_cast<const float4*>(&sm.xs[0][1][0]);
           float4* dst = reinterpret_cast<float4*>(traj + ((size_t)b * T + k0 + 1) * DP);
           for (int idx = t; idx < len * DP / 2; idx += blockDim.x) dst[idx] = src[idx];
+        }
+        if (sptraj) {   // S x'_k for the adjoint sweep (saves it the mat-vec)
+          float2* dst = sptraj + ((size_t)b * T + k0) * DP;
+          for (int idx = t; idx < len * DP; idx += blockDim.x) {
+            const int kk = idx / DP, r = idx % DP;
+            float2 sp = sm.spp[kk][0][r];
+#pragma unroll
+            for (int j = 1; j < NQ; ++j) {
+              sp.x += sm.spp[kk][j][r].x;
+              sp.y += sm.spp[kk][j][r].y;
+            }
+            dst[idx] = sp;
+          }
         }
       }
       __syncthreads();
@@ -227,31 +244,33 @@ __global__ void __launch_bounds__(DP* NQ + 32)
 }
 
 // -------------------------------------------------------------------------------------------
-// backward, cluster variant.  block = 256 threads in both CTAs.
+// backward, cluster variant.  block = 3*NTC threads in both CTAs (NTC = DP*NQ).
 //   rank 0 CHAIN CTA : threads 0..127 run the adjoint recursion; it only ever touches its own
 //                      shared memory (packed inputs pushed by the filler, mu ring).
 //   rank 1 FILLER CTA: threads 0..127 "prep" group  -- cp.async of trajectory / q / waveform, x', S x',
 //                      alpha, beta, packed rows pushed into the chain CTA (st.shared::cluster);
-//                      threads 128..255 "tiles" group -- pull the finished chunk's mu ring
-//                      (ld.shared::cluster) and accumulate the rank-1 gradient tiles.
+//                      two "tiles" groups of NTC threads -- pull the finished chunk's mu ring
+//                      (ld.shared::cluster) and accumulate the rank-1 gradient tiles, each over
+//                      half of the chunk's steps (their accumulators are summed at the end).
 // Slot c (c = nchunks .. -1): chain runs chunk c; prep prepares chunk c-1 and loads chunk c-2;
 // tiles accumulate chunk c+1.  One barrier.cluster per slot.
 // -------------------------------------------------------------------------------------------
 template <int DP, int NQ>
-struct alignas(16) BwdClSmem {
-  // ---- chain CTA ----
+struct alignas(16) BwdClChainSmem {   // what the CHAIN CTA keeps (and the filler addresses remotely)
   float4 cina[2][CH][DP];      // { c_k q_k , alpha_k (S x'_k)_i }
   float4 cinb[2][CH][DP];      // { beta_k x_k,i , dtm_k x_k,i }
   float2 mus[2][CH][DP];       // adjoint of x'_k
   float svc[2][CH];            // s_k for the chain
-  // ---- filler CTA ----
+};
+template <int DP, int NQ>
+struct alignas(16) BwdClFillSmem {    // FILLER CTA
+  static constexpr int NTC = DP * NQ, G = NTC / CH, ES = NTC + (G < 32 ? G : 0);
   float2 xs[4][CH + 1][DP];
   float2 qs[2][CH][DP];
   float2 xps[3][CH][DP];
   float2 mul[CH][DP];          // local copy of the pulled mu ring
-  float2 sps[CH][DP];
-  float es[CH][DP + 1];
-  float ns[CH][DP + 1];
+  float2 spl[2][CH][DP];       // S x'_k stored by the forward
+  float2 evl[2][CH];           // (E_k, |x_k|^2) stored by the forward
   float wav[2][CH + 4];
   float tt[2][CH + 4];
   float scs[2][4];
@@ -259,33 +278,38 @@ struct alignas(16) BwdClSmem {
   float incv[CH], betas[CH], dtm[CH];
   double lred[32];
 };
+template <int DP, int NQ>
+constexpr size_t bwd_cl_smem_bytes() {
+  return sizeof(BwdClChainSmem<DP, NQ>) > sizeof(BwdClFillSmem<DP, NQ>) ? sizeof(BwdClChainSmem<DP, NQ>)
+                                                                        : sizeof(BwdClFillSmem<DP, NQ>);
+}
 
 template <int DP, int NQ>
-__global__ void __launch_bounds__(2 * DP * NQ)
+__global__ void __launch_bounds__(3 * DP * NQ)
     psi_bwd_cl_kernel(const float2* __restrict__ matN, const float2* __restrict__ matRH,
                       const float2* __restrict__ matS, const float2* __restrict__ qtab,
                       const float* __restrict__ ttab, const float* __restrict__ x, int T, float A,
                       const float* __restrict__ w, const float2* __restrict__ traj,
                       const float* __restrict__ scales, int nchunks, float2* __restrict__ Gout,
                       float* __restrict__ gfout, float2* __restrict__ lam0out,
-                      double* __restrict__ gAdir) {
+                      double* __restrict__ gAdir, const float2* __restrict__ sptraj,
+                      const float2* __restrict__ evin) {
   using M = Map<DP, NQ>;
-  using Sm = BwdClSmem<DP, NQ>;
   constexpr int NTC = M::NT;
   constexpr int CPT = M::CPT;
   constexpr int NP = M::NP;
-  constexpr int G = NTC / CH, PER = DP / G;
-  static_assert(DP % G == 0 && G <= 32, "scalar-phase grouping");
   constexpr int LV = (NQ == 4) ? 2 : 3;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Sm& sm = *reinterpret_cast<Sm*>(smem_raw);
+  // both views alias the same buffer; each CTA uses one, the filler addresses the chain's remotely
+  BwdClChainSmem<DP, NQ>& cs = *reinterpret_cast<BwdClChainSmem<DP, NQ>*>(smem_raw);
+  BwdClFillSmem<DP, NQ>& sm = *reinterpret_cast<BwdClFillSmem<DP, NQ>*>(smem_raw);
 
   const int t = threadIdx.x;
   const unsigned rank = cluster_ctarank();
   const int b = blockIdx.x >> 1;
   const int nsteps = T - 1;
   const int lane = t & 31;
-  const int grp = t / NTC;                 // 0 or 1
+  const int grp = t / NTC;                 // chain CTA: 0 = chain; filler CTA: 0 = prep, 1..2 = tiles
   const int tr = t - grp * NTC;
   const int i = tr / NQ, jq = tr % NQ;
   auto chunk_len = [&](int c) { return min(CH, nsteps - c * CH); };
@@ -303,9 +327,9 @@ __global__ void __launch_bounds__(2 * DP * NQ)
     for (int c = nchunks; c >= -1; --c) {
       if (grp == 0 && c >= 0 && c < nchunks) {
         const int ca = c & 1, len = chunk_len(c);
-        float2* const mu_st = &sm.mus[ca][0][i];
+        float2* const mu_st = &cs.mus[ca][0][i];
         {
-          const float4 a4 = sm.cina[ca][len - 1][i];
+          const float4 a4 = cs.cina[ca][len - 1][i];
           float2 mu = cmul_ca(make_float2(a4.x, a4.y), lam);
           mu.x += a4.z;
           mu.y += a4.w;
@@ -316,14 +340,14 @@ __global__ void __launch_bounds__(2 * DP * NQ)
           float2 mv[CPT];
 #pragma unroll
           for (int m = 0; m < NP; ++m) {
-            const float4 v = *reinterpret_cast<const float4*>(&sm.mus[ca][kk][2 * NQ * m + 2 * jq]);
+            const float4 v = *reinterpret_cast<const float4*>(&cs.mus[ca][kk][2 * NQ * m + 2 * jq]);
             mv[2 * m] = make_float2(v.x, v.y);
             mv[2 * m + 1] = make_float2(v.z, v.w);
           }
           tie_loads(mv);
-          const float s = sm.svc[ca][kk];
-          const float4 b4 = sm.cinb[ca][kk][i];
-          const float4 a4 = sm.cina[ca][kk > 0 ? kk - 1 : 0][i];
+          const float s = cs.svc[ca][kk];
+          const float4 b4 = cs.cinb[ca][kk][i];
+          const float4 a4 = cs.cina[ca][kk > 0 ? kk - 1 : 0][i];
           float2 a0 = make_float2(0.f, 0.f), a1 = a0;
 #pragma unroll
           for (int cc = 0; cc < CPT; cc += 2) {
@@ -368,8 +392,6 @@ __global__ void __launch_bounds__(2 * DP * NQ)
     const float* xb = x + (size_t)b * T;
     const float2* trb = traj + (size_t)b * T * DP;
     const float wb = w[b];
-    float2 Sr[CPT];
-    load_slice<DP, NQ>(Sr, matS, i, jq);
     float2 GR[CPT], GN[CPT], GE[CPT];
 #pragma unroll
     for (int c = 0; c < CPT; ++c) GR[c] = GN[c] = GE[c] = make_float2(0.f, 0.f);
@@ -388,19 +410,28 @@ __global__ void __launch_bounds__(2 * DP * NQ)
         cp_async4(&sm.tt[c & 1][idx], ttab + (k0 + idx > 0 ? k0 + idx - 1 : 0));
       }
       if (tr == 0) cp_async4(&sm.scs[c & 1][0], scales + (size_t)b * nchunks + c);
+      const float2* ssrc = sptraj + ((size_t)b * T + k0) * DP;
+      float2* sdst = &sm.spl[c & 1][0][0];
+      for (int idx = tr; idx < len * DP / 2; idx += NTC) cp_async16(sdst + 2 * idx, ssrc + 2 * idx);
+      const float2* esrc = evin + (size_t)b * T + k0;   // 8-byte elements: two 4-byte copies each
+      for (int idx = tr; idx < 2 * len; idx += NTC)
+        cp_async4(reinterpret_cast<float*>(&sm.evl[c & 1][0]) + idx, reinterpret_cast<const float*>(esrc) + idx);
     };
 
     auto tiles_chunk = [&](int c) {          // tiles group
       const int len = chunk_len(c);
       {  // pull the chunk's mu ring out of the chain CTA
-        const unsigned rm = dsmem_addr(&sm.mus[c & 1][0][0], 0);
+        const unsigned rm = dsmem_addr(&cs.mus[c & 1][0][0], 0);
         float4* lm = reinterpret_cast<float4*>(&sm.mul[0][0]);
-        for (int idx = tr; idx < len * DP / 2; idx += NTC) lm[idx] = ld_dsmem_f4(rm + 16 * idx);
+        for (int idx = t - NTC; idx < len * DP / 2; idx += 2 * NTC) lm[idx] = ld_dsmem_f4(rm + 16 * idx);
       }
-      bar_named(3, NTC);
+      bar_named(3, 2 * NTC);
       const float2(*xsb)[DP] = sm.xs[c & 3];
       const float2(*xpb)[DP] = sm.xps[c % 3];
-      for (int kk = 0; kk < len; ++kk) {
+#ifdef AMPS_EXPERIMENT_NO_TILES
+      if (len > 100000)
+#endif
+      for (int kk = grp - 1; kk < len; kk += 2) {   // the two tile groups interleave the steps
         const float2 mui = sm.mul[kk][i];
         const float2 xpi = xpb[kk][i];
         const float s = sm.sv[c % 3][kk];
@@ -423,79 +454,46 @@ __global__ void __launch_bounds__(2 * DP * NQ)
       }
     };
 
-    auto prep_chunk = [&](int c) {           // prep group
+    auto prep_chunk = [&](int c) {           // prep group: elementwise only
       const int len = chunk_len(c), k0 = c * CH;
       const int lx = c & 3, lq = c & 1, lp3 = c % 3;
       const float sc = sm.scs[lq][0];
       const float inv_sc = 1.0f / sc;
-      const unsigned ra = dsmem_addr(&sm.cina[lq][0][0], 0);
-      const unsigned rb = dsmem_addr(&sm.cinb[lq][0][0], 0);
-      const unsigned rs = dsmem_addr(&sm.svc[lq][0], 0);
+      const unsigned ra = dsmem_addr(&cs.cina[lq][0][0], 0);
+      const unsigned rb = dsmem_addr(&cs.cinb[lq][0][0], 0);
+      const unsigned rs = dsmem_addr(&cs.svc[lq][0], 0);
       if (tr < len) {
         const float inc = sm.wav[lq][tr + 1] - sm.wav[lq][tr];
         const float s = inc / A;
-        sm.incv[tr] = inc;
         sm.sv[lp3][tr] = s;
         st_dsmem_f1(rs + 4 * tr, s);
         sm.dtm[tr] = (k0 + tr > 0) ? sm.tt[lq][tr + 1] - sm.tt[lq][tr] : 0.f;
-      }
-      for (int idx = tr; idx < len * DP; idx += NTC) {
-        const int kk = idx / DP, r = idx % DP;
-        float2 xp = cmul_ca(sm.qs[lq][kk][r], sm.xs[lx][kk + 1][r]);
-        if (kk == len - 1) {
-          xp.x *= inv_sc;
-          xp.y *= inv_sc;
-        }
-        sm.xps[lp3][kk][r] = xp;
-        sm.ns[kk][r] = cabs2(sm.xs[lx][kk][r]);
+        const float2 ev = sm.evl[lq][tr];          // (E_k, |x_k|^2) from the forward
+        const float E = ev.x, nu2 = ev.y;
+        const float arg = 1.0f + (E * inc) / A;
+        const float gE = wb * (-s / arg);
+        const float alpha = 2.0f * gE / nu2;
+        sm.alphas[lp3][tr] = alpha;
+        sm.betas[tr] = -alpha * E;
+        gAacc += (double)wb * (double)E * (double)inc / ((double)A * (double)A * (double)arg);
       }
       bar_named(2, NTC);
-      for (int kk = 0; kk < len; ++kk) {
-        float2 part = matvec1<DP, NQ>(Sr, sm.xps[lp3][kk], jq);
-        part = group_sum<NQ>(part);
-        const float2 xpi = sm.xps[lp3][kk][i];
-        sts_if(jq == 1, &sm.sps[kk][i], part);
-        sts_if(jq == 2, &sm.es[kk][i], fmaf(xpi.x, part.x, xpi.y * part.y));
-      }
-      bar_named(2, NTC);
-      {
-        const int kk = tr / G, g = tr % G;
-        float en = 0.f, nu2 = 0.f;
-        if (kk < len) {
-#pragma unroll
-          for (int r = 0; r < PER; ++r) {
-            en += sm.es[kk][g * PER + r];
-            nu2 += sm.ns[kk][g * PER + r];
-          }
-        }
-#pragma unroll
-        for (int m = 1; m < G; m <<= 1) {
-          en += __shfl_xor_sync(0xffffffffu, en, m);
-          nu2 += __shfl_xor_sync(0xffffffffu, nu2, m);
-        }
-        if (g == 0 && kk < len) {
-          const float E = en / nu2;
-          const float inc = sm.incv[kk];
-          const float arg = 1.0f + (E * inc) / A;
-          const float gE = wb * (-sm.sv[lp3][kk] / arg);
-          const float alpha = 2.0f * gE / nu2;
-          sm.alphas[lp3][kk] = alpha;
-          sm.betas[kk] = -alpha * E;
-          gAacc += (double)wb * (double)E * (double)inc / ((double)A * (double)A * (double)arg);
-        }
-      }
-      bar_named(2, NTC);
-      // packed per-row chain inputs, pushed straight into the chain CTA's shared memory
+      // x'_k = conj(q_k) x_{k+1} / c_k (for the tiles) and the packed per-row chain inputs,
+      // pushed straight into the chain CTA's shared memory
       for (int idx = tr; idx < len * DP; idx += NTC) {
         const int kk = idx / DP, r = idx % DP;
         float2 q = sm.qs[lq][kk][r];
+        const float2 xk = sm.xs[lx][kk][r];
+        float2 xp = cmul_ca(q, sm.xs[lx][kk + 1][r]);
         if (kk == len - 1) {
+          xp.x *= inv_sc;
+          xp.y *= inv_sc;
           q.x *= sc;
           q.y *= sc;
         }
+        sm.xps[lp3][kk][r] = xp;
         const float al = sm.alphas[lp3][kk], be = sm.betas[kk], dt = sm.dtm[kk];
-        const float2 sp = sm.sps[kk][r];
-        const float2 xk = sm.xs[lx][kk][r];
+        const float2 sp = sm.spl[lq][kk][r];
         st_dsmem_f4(ra + 16 * idx, make_float4(q.x, q.y, al * sp.x, al * sp.y));
         st_dsmem_f4(rb + 16 * idx, make_float4(be * xk.x, be * xk.y, dt * xk.x, dt * xk.y));
       }
@@ -530,13 +528,28 @@ __global__ void __launch_bounds__(2 * DP * NQ)
         gAdir[b] = tot;
       }
     } else {
-      float2* Gb = Gout + (size_t)b * 3 * DP * DP;
+      // sum the two tile groups' accumulators through shared memory (xs is free now)
+      float2* scratch = &sm.xs[0][0][0];
+      if (grp == 2) {
 #pragma unroll
-      for (int c = 0; c < CPT; ++c) {
-        const int col = M::col(c, jq);
-        Gb[0 * DP * DP + i * DP + col] = GR[c];
-        Gb[1 * DP * DP + i * DP + col] = GN[c];
-        Gb[2 * DP * DP + i * DP + col] = GE[c];
+        for (int c = 0; c < CPT; ++c) {
+          scratch[(0 * CPT + c) * NTC + tr] = GR[c];
+          scratch[(1 * CPT + c) * NTC + tr] = GN[c];
+          scratch[(2 * CPT + c) * NTC + tr] = GE[c];
+        }
+      }
+      bar_named(3, 2 * NTC);
+      if (grp == 1) {
+        float2* Gb = Gout + (size_t)b * 3 * DP * DP;
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          const int col = M::col(c, jq);
+          const float2 r = scratch[(0 * CPT + c) * NTC + tr], n = scratch[(1 * CPT + c) * NTC + tr],
+                       e = scratch[(2 * CPT + c) * NTC + tr];
+          Gb[0 * DP * DP + i * DP + col] = make_float2(GR[c].x + r.x, GR[c].y + r.y);
+          Gb[1 * DP * DP + i * DP + col] = make_float2(GN[c].x + n.x, GN[c].y + n.y);
+          Gb[2 * DP * DP + i * DP + col] = make_float2(GE[c].x + e.x, GE[c].y + e.y);
+        }
       }
     }
   }
