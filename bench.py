@@ -252,29 +252,42 @@ def run_ours(args):
         value = samples / (tot_ms * 1e-3)
         e2e_val = samples / (tot_e2e_ms * 1e-3)
         peaks, peak_src = measured_peaks()
-        # dominant kernel = psi_bwd_kernel; algorithmic traffic per (clip, sample), DESIGN.md:
-        #   forward  4 B waveform + 8*D B trajectory write ; backward 4 B + 8*D B trajectory read
+        # Algorithmic traffic per (clip, sample), DESIGN.md 4.6 (K = 1: the whole trajectory is kept):
+        #   forward  4 B waveform + 8*D B x_k + 8*D B S x'_k + 8 B (E_k, |x_k|^2) written
+        #   backward the same bytes read back
         bwd_t = float(np.mean(bwd_ms)) * 1e-3
         fwd_t = float(np.mean(fwd_ms)) * 1e-3
         units = B_PER_GPU * T
-        bwd_bytes = units * (4 + 8 * D)
-        fwd_bytes = units * (4 + 8 * D)
-        bwd_flops = units * (48 * D * D + 60 * D)      # executed: S x', chain [N;R^dag], 3 rank-1 tiles
-        fwd_flops = units * (24 * D * D + 36 * D)
+        per_unit_bytes = 12 + 16 * D
+        # executed flops: fwd = L_k formation 4D^2 + chain mat-vec 8D^2 + S x' 8D^2 ;
+        #                 bwd = L_k^dag formation 4D^2 + chain mat-vec 8D^2 + 3 rank-1 tiles 24D^2
+        fwd_flops = units * (20 * D * D + 40 * D)
+        bwd_flops = units * (36 * D * D + 60 * D)
         fma_peak = float(_lib.load().amps_fma_peak_tflops(_lib.context(local)))
-        roof = {"bound": "hbm", "kernel": "psi_bwd_kernel<32,4>",
-                "achieved": bwd_bytes / bwd_t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": bwd_bytes / bwd_t / 1e9 / peaks["hbm_gbs"], "traffic": None,
-                "peak_source": peak_src, "kernel_ms": bwd_t * 1e3,
-                "note": "path is FP32-issue/latency bound, not HBM bound (SURVEY 0.10); see fp32",
-                "fp32": {"bwd_achieved_tflops": bwd_flops / bwd_t / 1e12,
-                         "fwd_achieved_tflops": fwd_flops / fwd_t / 1e12,
-                         "peak_tflops": fma_peak, "peak_source": "FFMA microbenchmark in this run",
-                         "bwd_frac": bwd_flops / bwd_t / 1e12 / fma_peak if fma_peak > 0 else None,
-                         "fwd_frac": fwd_flops / fwd_t / 1e12 / fma_peak if fma_peak > 0 else None},
-                "fwd_kernel": {"kernel": "psi_fwd_kernel<32,4>", "kernel_ms": fwd_t * 1e3,
-                               "achieved": fwd_bytes / fwd_t / 1e9,
-                               "frac": fwd_bytes / fwd_t / 1e9 / peaks["hbm_gbs"]}}
+        clustered = 2 * B_PER_GPU <= 148 and os.environ.get("AMPS_NO_CLUSTER") != "1"
+        kn = "cl_kernel" if clustered else "kernel"
+        kinfo = {"fwd": (f"psi_fwd_{kn}<32,4>", fwd_t, fwd_flops), "bwd": (f"psi_bwd_{kn}<32,4>", bwd_t, bwd_flops)}
+        dom = "fwd" if fwd_t >= bwd_t else "bwd"
+        oth = "bwd" if dom == "fwd" else "fwd"
+
+        def entry(which):
+            name, tt, fl = kinfo[which]
+            return {"kernel": name, "kernel_ms": tt * 1e3, "achieved": units * per_unit_bytes / tt / 1e9,
+                    "frac": units * per_unit_bytes / tt / 1e9 / peaks["hbm_gbs"],
+                    "fp32_achieved_tflops": fl / tt / 1e12,
+                    "fp32_frac": fl / tt / 1e12 / fma_peak if fma_peak > 0 else None,
+                    "cycles_per_step_at_1965MHz": tt / (T - 1) * 1.965e9}
+        d = entry(dom)
+        roof = {"bound": "hbm", "kernel": d["kernel"], "achieved": d["achieved"], "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": d["frac"], "traffic": None, "peak_source": peak_src,
+                "kernel_ms": d["kernel_ms"],
+                "note": "the path is dependent-step-latency / FP32-issue bound, not HBM bound (SURVEY 0.10): "
+                        "one clip per SM pair advances one step per ~300-360 cycles; see fp32 and other_kernel",
+                "fp32": {"achieved_tflops": d["fp32_achieved_tflops"], "peak_tflops": fma_peak,
+                         "peak_source": "FFMA microbenchmark in this run (amps_fma_peak_tflops)",
+                         "frac": d["fp32_frac"]},
+                "cycles_per_step": d["cycles_per_step_at_1965MHz"],
+                "other_kernel": entry(oth)}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
