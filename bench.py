@@ -278,8 +278,12 @@ def run_ours(args):
                     "fp32_frac": fl / tt / 1e12 / fma_peak if fma_peak > 0 else None,
                     "cycles_per_step_at_1965MHz": tt / (T - 1) * 1.965e9}
         d = entry(dom)
+        # dram__bytes_read+write per launch of the same kernels at this exact workload, from the
+        # committed ncu --set full capture (profiles/r1_ncu_cluster.md)
+        ncu_traffic = {"fwd": 2.106e9, "bwd": 2.172e9} if clustered else {"fwd": None, "bwd": None}
         roof = {"bound": "hbm", "kernel": d["kernel"], "achieved": d["achieved"], "peak": peaks["hbm_gbs"],
-                "unit": "GB/s", "frac": d["frac"], "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": d["frac"], "traffic": ncu_traffic[dom],
+                "traffic_source": "profiles/r1_ncu_cluster.md", "peak_source": peak_src,
                 "kernel_ms": d["kernel_ms"],
                 "note": "the path is dependent-step-latency / FP32-issue bound, not HBM bound (SURVEY 0.10): "
                         "one clip per SM pair advances one step per ~300-360 cycles; see fp32 and other_kernel",
