@@ -26,6 +26,9 @@ struct alignas(16) FwdClSmem {
   float sv[2][CH + 4];
   float incv[2][CH];
   double lred[32];
+  float scv[2][4];                   // chain CTA: rescale factor of the chunk in ring p
+  unsigned long long full_bar[2];    // filler CTA: ring p of the chain CTA holds a finished chunk
+  unsigned long long empty_bar[2];   // chain CTA : the filler has pulled ring p
 };
 
 // block = NTC + 32 threads; grid = 2*B CTAs in clusters of 2
@@ -53,6 +56,17 @@ __global__ void __launch_bounds__(DP* NQ + 32)
   const float* xb = x + (size_t)b * T;
   const int lane = t & 31;
   auto chunk_len = [&](int c) { return min(CH, nsteps - c * CH); };
+
+  if (t == 0) {
+    mbar_init(&sm.full_bar[0], 1);
+    mbar_init(&sm.full_bar[1], 1);
+    mbar_init(&sm.empty_bar[0], 1);
+    mbar_init(&sm.empty_bar[1], 1);
+    mbar_fence_init_cluster();
+  }
+  __syncthreads();
+  cluster_arrive_release();   // both CTAs' barriers are initialised before any remote arrive
+  cluster_wait_acquire();
 
   if (rank == 0) {
     // ===================================== CHAIN CTA ==========================================
@@ -83,16 +97,13 @@ __global__ void __launch_bounds__(DP* NQ + 32)
       load_slice<DP, NQ>(Rr, matR, i, jq);
     }
     float2 vstart = make_float2(0.f, 0.f);
-    for (int c = 0; c <= nchunks; ++c) {
-      if (c < nchunks) {
+    const unsigned rfull = dsmem_addr(&sm.full_bar[0], 1);
+    for (int c = 0; c < nchunks; ++c) {
+      {
         const int p = c & 1, len = chunk_len(c);
         if (is_loader) {
           if (c + 1 < nchunks) load_inputs(c + 1);
         } else {
-          if (c > 0) {
-            if (t < DP) sm.xs[p][0][t] = vstart;
-            bar_named(1, NTC);
-          }
           float2* const st2 = (jq == 0) ? &sm.xs[p][1][i] : &sm.xps[p][0][i];
           const bool st2_on = jq < 2;
           float s_cur = sm.sv[p][0];
@@ -133,25 +144,29 @@ __global__ void __launch_bounds__(DP* NQ + 32)
           } else {
             for (int kk = 0; kk < len; ++kk) step(kk);
           }
+          // chunk boundary: the un-scaled x_{k0+len} stays in ring p (the filler applies the scale
+          // when it pulls the chunk); the scaled state goes straight into the next ring's slot 0
           float n2 = 0.f;
           for (int r = lane; r < DP; r += 32) n2 += cabs2(sm.xs[p][len][r]);
           n2 = warp_sum_f(n2);
           const float sc = rsqrtf(n2);
-          bar_named(1, NTC);
-          if (t < DP) {
-            float2 v = sm.xs[p][len][t];
-            v.x *= sc;
-            v.y *= sc;
-            sm.xs[p][len][t] = v;
-            vstart = v;
+          if (t == 0) {
+            sm.scv[p][0] = sc;
+            if (scales) scales[(size_t)b * nchunks + c] = sc;
+            mbar_arrive_remote(rfull + 8 * p);                 // ring p complete: tell the filler CTA
           }
-          if (t == 0 && scales) scales[(size_t)b * nchunks + c] = sc;
+          // ring p^1 is free once the filler has pulled chunk c-1 out of it
+          mbar_wait(&sm.empty_bar[p ^ 1], (((c + 1) >> 1) & 1) ^ 1);
+          if (t < DP) {
+            const float2 v = sm.xs[p][len][t];
+            sm.xs[p ^ 1][0][t] = make_float2(v.x * sc, v.y * sc);
+          }
         }
       }
-      __syncthreads();
-      cluster_arrive_release();   // chunk c is complete in ring c&1 ...
-      cluster_wait_acquire();     // ... and the filler CTA has copied chunk c-1 out of ring (c-1)&1
+      __syncthreads();   // loader hand-over of chunk c+1's q_k / s_k
     }
+    cluster_arrive_release();   // do not exit while the filler may still read this CTA's rings
+    cluster_wait_acquire();
   } else {
     // ===================================== FILLER CTA =========================================
     const int tr = t;
@@ -160,24 +175,37 @@ __global__ void __launch_bounds__(DP* NQ + 32)
     float2 Sr[CPT];
     if (work) load_slice<DP, NQ>(Sr, matS, i, jq);
     double lossacc = 0.0;
+    const unsigned rempty = dsmem_addr(&sm.empty_bar[0], 0);
     __syncthreads();
-    for (int c = 0; c <= nchunks; ++c) {
-      if (c >= 1) {
-        const int cc = c - 1, p = cc & 1, len = chunk_len(cc), k0 = cc * CH;
+    for (int cc = 0; cc < nchunks; ++cc) {
+      {
+        const int p = cc & 1, len = chunk_len(cc), k0 = cc * CH;
         // waveform of chunk cc (for inc_k)
         for (int idx = t; idx <= len; idx += blockDim.x) cp_async4(&sm.wav[0][idx], xb + k0 + idx);
         cp_async_commit();
-        // pull the chunk out of the chain CTA's rings (distributed shared memory)
+        // wait until the chain CTA has finished chunk cc, then pull it out of its rings
+        mbar_wait(&sm.full_bar[p], (cc >> 1) & 1);
         {
           const unsigned rx = dsmem_addr(&sm.xs[p][0][0], 0);
           const unsigned rp = dsmem_addr(&sm.xps[p][0][0], 0);
           float4* lx = reinterpret_cast<float4*>(&sm.xs[0][0][0]);
           float4* lp = reinterpret_cast<float4*>(&sm.xps[0][0][0]);
-          for (int idx = t; idx < (len + 1) * DP / 2; idx += blockDim.x) lx[idx] = ld_dsmem_f4(rx + 16 * idx);
+          const float scp = ld_dsmem_f4(dsmem_addr(&sm.scv[p][0], 0)).x;   // c_k of this chunk
+          for (int idx = t; idx < (len + 1) * DP / 2; idx += blockDim.x) {
+            float4 v = ld_dsmem_f4(rx + 16 * idx);
+            if (idx >= len * DP / 2) {     // row `len` = x_{k0+len}: stored un-scaled by the chain
+              v.x *= scp;
+              v.y *= scp;
+              v.z *= scp;
+              v.w *= scp;
+            }
+            lx[idx] = v;
+          }
           for (int idx = t; idx < len * DP / 2; idx += blockDim.x) lp[idx] = ld_dsmem_f4(rp + 16 * idx);
         }
         cp_async_wait<0>();
         __syncthreads();
+        if (t == 0) mbar_arrive_remote(rempty + 8 * p);       // ring p may be overwritten
         if (t < len) sm.incv[0][t] = sm.wav[0][t + 1] - sm.wav[0][t];
         if (work) {
           for (int kk = 0; kk < len; ++kk) {
@@ -228,9 +256,9 @@ __global__ void __launch_bounds__(DP* NQ + 32)
         }
       }
       __syncthreads();
-      cluster_arrive_release();
-      cluster_wait_acquire();
     }
+    cluster_arrive_release();
+    cluster_wait_acquire();
     lossacc = warp_sum_d(lossacc);
     if (lane == 0) sm.lred[t >> 5] = lossacc;
     __syncthreads();

@@ -1,0 +1,60 @@
+"""Timings of the other BASELINE configs (kernel + API level, CUDA events).
+usage: python profiles/time_configs.py [c2] [c4] [c0]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from audio_mps_b200 import HParams, PsiCMPS, _lib, damped_sine  # noqa: E402
+
+dev = torch.device("cuda", 0)
+which = sys.argv[1:] or ["c2", "c4", "c0"]
+
+
+def hp(D, B):
+    return HParams(minibatch_size=B, bond_dim=D, delta_t=1 / 16000, sigma=0.0001,
+                   h_reg=200 / (np.pi * 16000) ** 2, r_reg=0.1, initial_rank=None, A=100., learning_rate=0.001)
+
+
+def timed(fn, reps=3):
+    out = []
+    for _ in range(reps + 1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        out.append(e0.elapsed_time(e1))
+    return min(out[1:])
+
+
+if "c2" in which:   # sampling D=32, 256 samples, 4 s clips from a fixed noise tensor
+    D, n, L = 32, 256, 64000
+    m = PsiCMPS(hp(D, n), device=dev, seed=0)
+    noise = (torch.randn(L, n, generator=torch.Generator().manual_seed(2)) * m.sigma * np.sqrt(m.delta_t)).to(dev)
+    ms = timed(lambda: m.sample_from_noise(noise))
+    print(f"C2 sampler D={D} n={n} L={L}: {ms:.2f} ms  -> {n*L/ms*1e3:.3e} samples/s  ({ms*1e-3/L*1.965e9:.0f} cyc/step)")
+if "c4" in which:   # D=64, 256 clips per GPU (global 2048 over 8 GPUs), 4 s clips
+    D, B, T = 64, 256, 64000
+    m = PsiCMPS(hp(D, B), device=dev, seed=0)
+    x = torch.from_numpy(damped_sine(B, T, 1 / 16000, np.random.default_rng(1))).to(dev)
+    _lib.set_profiling(0, True)
+
+    def step():
+        m.zero_grad()
+        m.loss_fn(x).backward()
+    ms = timed(step, reps=2)
+    print(f"C4 per-GPU D={D} B={B} T={T}: step {ms:.1f} ms (fwd kernel {_lib.kernel_ms(0,0):.1f}, bwd kernel {_lib.kernel_ms(0,1):.1f}) "
+          f"-> {B*T/ms*1e3:.3e} samples/s")
+if "c0" in which:   # D=8, 8 clips of 1 s
+    D, B, T = 8, 8, 16000
+    m = PsiCMPS(hp(D, B), device=dev, seed=0)
+    x = torch.from_numpy(damped_sine(B, T, 1 / 16000, np.random.default_rng(1))).to(dev)
+
+    def step0():
+        m.zero_grad()
+        m.loss_fn(x).backward()
+    ms = timed(step0)
+    print(f"C0 D={D} B={B} T={T}: step {ms:.2f} ms -> {B*T/ms*1e3:.3e} samples/s")
