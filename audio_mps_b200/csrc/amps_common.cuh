@@ -116,6 +116,21 @@ __device__ __forceinline__ float2 group_sum(float2 v) {
   return v;
 }
 
+// Row-sum over the NQ lanes of a group on the chain's critical path.  For NQ = 4 the three partner
+// values are fetched with three INDEPENDENT shuffles per component (one shuffle latency, ~29 cycles on
+// B200) instead of two dependent butterfly levels (two latencies); the summation tree
+// (own + xor1) + (xor2 + xor3) is the same on every lane, so the replicated result is bit-identical.
+template <int NQ>
+__device__ __forceinline__ float2 group_sum_fast(float2 v) {
+  if (NQ == 4) {
+    const float x1 = __shfl_xor_sync(0xffffffffu, v.x, 1), y1 = __shfl_xor_sync(0xffffffffu, v.y, 1);
+    const float x2 = __shfl_xor_sync(0xffffffffu, v.x, 2), y2 = __shfl_xor_sync(0xffffffffu, v.y, 2);
+    const float x3 = __shfl_xor_sync(0xffffffffu, v.x, 3), y3 = __shfl_xor_sync(0xffffffffu, v.y, 3);
+    return make_float2((v.x + x1) + (x2 + x3), (v.y + y1) + (y2 + y3));
+  }
+  return group_sum<NQ>(v);
+}
+
 // Load this thread's register slice of row i of a [DP][DP] complex matrix.
 template <int DP, int NQ>
 __device__ __forceinline__ void load_slice(float2 (&dst)[DP / NQ], const float2* __restrict__ mat,

@@ -128,11 +128,7 @@ __global__ void __launch_bounds__(DP* NQ + 32)
               cmac(a1, l1, xv[cc + 1]);
             }
             float2 xp = make_float2(a0.x + a1.x, a0.y + a1.y);
-#pragma unroll
-            for (int lv = 0; lv < LV; ++lv) {
-              xp.x += __shfl_xor_sync(0xffffffffu, xp.x, 1 << lv);
-              xp.y += __shfl_xor_sync(0xffffffffu, xp.y, 1 << lv);
-            }
+            xp = group_sum_fast<NQ>(xp);
             const float2 xn = cmul(q, xp);
             sts_if(st2_on, st2 + kk * DP, (jq == 0) ? xn : xp);
             s_cur = s_next;
@@ -386,11 +382,7 @@ __global__ void __launch_bounds__(3 * DP * NQ)
             cmac(a1, l1, mv[cc + 1]);
           }
           float2 lp = make_float2(a0.x + a1.x, a0.y + a1.y);
-#pragma unroll
-          for (int lv = 0; lv < LV; ++lv) {
-            lp.x += __shfl_xor_sync(0xffffffffu, lp.x, 1 << lv);
-            lp.y += __shfl_xor_sync(0xffffffffu, lp.y, 1 << lv);
-          }
+          lp = group_sum_fast<NQ>(lp);
           lam.x = lp.x + b4.x;
           lam.y = lp.y + b4.y;
           gf = fmaf(lam.x, b4.w, fmaf(-lam.y, b4.z, gf));
