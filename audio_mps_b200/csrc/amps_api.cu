@@ -363,7 +363,7 @@ int amps_psi_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
   return dispatch_dp(DP, [&](auto dp, auto nq) -> int {
     constexpr int DPc = decltype(dp)::value, NQc = decltype(nq)::value;
     constexpr bool WS = DPc <= 32;   // warp-specialised chain/filler kernel
-    if (WS && ctx->use_clusters && 2 * B <= ctx->num_sms) {
+    if constexpr (WS) if (ctx->use_clusters && 2 * B <= ctx->num_sms) {
       // enough idle SMs: one 2-CTA cluster per clip (chain CTA + filler CTA on a second SM)
       auto kcl = psi_fwd_cl_kernel<DPc, NQc>;
       const size_t smem_cl = sizeof(FwdClSmem<DPc, NQc>);
@@ -392,15 +392,27 @@ int amps_psi_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
       LAUNCH_CHECK(ctx, "psi_fwd_cl_kernel");
       return AMPS_OK;
     }
-    auto kern = WS ? psi_fwd_kernel<DPc, NQc> : psi_fwd_uni_kernel<DPc, NQc>;
     const size_t smem = WS ? sizeof(FwdSmem<DPc, NQc>) : sizeof(FwdSmemUni<DPc, NQc>);
-    CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if constexpr (WS) {
+      CUDA_TRY(ctx, cudaFuncSetAttribute(psi_fwd_kernel<DPc, NQc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    } else {
+      CUDA_TRY(ctx, cudaFuncSetAttribute(psi_fwd_uni_kernel<DPc, NQc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     PROF_BEGIN(ctx, 0, st);
-    kern<<<B, (WS ? 2 : 1) * DPc * NQc, smem, st>>>(
-        (const float2*)(ws + L.matN), (const float2*)(ws + L.matR), (const float2*)(ws + L.matS),
-        (const float2*)(ws + L.qtab), (const float2*)(ws + L.psi0p), x_dev, T, p->A, loss_dev,
-        (double*)(ws + L.lossd), save ? (float2*)(ws + L.traj) : nullptr,
-        save ? (float*)(ws + L.scales) : nullptr, nchunks);
+    if constexpr (WS) {
+      psi_fwd_kernel<DPc, NQc><<<B, 2 * DPc * NQc, smem, st>>>(
+          (const float2*)(ws + L.matN), (const float2*)(ws + L.matR), (const float2*)(ws + L.matS),
+          (const float2*)(ws + L.qtab), (const float2*)(ws + L.psi0p), x_dev, T, p->A, loss_dev,
+          (double*)(ws + L.lossd), save ? (float2*)(ws + L.traj) : nullptr,
+          save ? (float*)(ws + L.scales) : nullptr, nchunks,
+          save ? (float2*)(ws + L.sptraj) : nullptr, save ? (float2*)(ws + L.ev) : nullptr);
+    } else {
+      psi_fwd_uni_kernel<DPc, NQc><<<B, DPc * NQc, smem, st>>>(
+          (const float2*)(ws + L.matN), (const float2*)(ws + L.matR), (const float2*)(ws + L.matS),
+          (const float2*)(ws + L.qtab), (const float2*)(ws + L.psi0p), x_dev, T, p->A, loss_dev,
+          (double*)(ws + L.lossd), save ? (float2*)(ws + L.traj) : nullptr,
+          save ? (float*)(ws + L.scales) : nullptr, nchunks);
+    }
     PROF_END(ctx, 0, st);
     LAUNCH_CHECK(ctx, "psi_fwd_kernel");
     return AMPS_OK;
@@ -434,7 +446,7 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
   rc = dispatch_dp(DP, [&](auto dp, auto nq) -> int {
     constexpr int DPc = decltype(dp)::value, NQc = decltype(nq)::value;
     constexpr bool WS = DPc <= 32;
-    if (WS && ctx->use_clusters && 2 * B <= ctx->num_sms) {
+    if constexpr (WS) if (ctx->use_clusters && 2 * B <= ctx->num_sms) {
       auto kcl = psi_bwd_cl_kernel<DPc, NQc>;
       const size_t smem_cl = bwd_cl_smem_bytes<DPc, NQc>();
       CUDA_TRY(ctx, cudaFuncSetAttribute(kcl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cl));
@@ -462,15 +474,27 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
       LAUNCH_CHECK(ctx, "psi_bwd_cl_kernel");
       return AMPS_OK;
     }
-    auto kern = WS ? psi_bwd_kernel<DPc, NQc> : psi_bwd_uni_kernel<DPc, NQc>;
     const size_t smem = WS ? sizeof(BwdSmem<DPc, NQc>) : sizeof(BwdSmemUni<DPc>);
-    CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if constexpr (WS) {
+      CUDA_TRY(ctx, cudaFuncSetAttribute(psi_bwd_kernel<DPc, NQc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    } else {
+      CUDA_TRY(ctx, cudaFuncSetAttribute(psi_bwd_uni_kernel<DPc, NQc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     PROF_BEGIN(ctx, 1, st);
-    kern<<<B, (WS ? 2 : 1) * DPc * NQc, smem, st>>>(
-        (const float2*)(ws + L.matN), (const float2*)(ws + L.matRH), (const float2*)(ws + L.matS),
-        (const float2*)(ws + L.qtab), ctx->ttab, x_dev, T, p->A, w_dev,
-        (const float2*)(ws + L.traj), (const float*)(ws + L.scales), nchunks,
-        (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0), (double*)(ws + L.gAdir));
+    if constexpr (WS) {
+      psi_bwd_kernel<DPc, NQc><<<B, 2 * DPc * NQc, smem, st>>>(
+          (const float2*)(ws + L.matN), (const float2*)(ws + L.matRH), (const float2*)(ws + L.matS),
+          (const float2*)(ws + L.qtab), ctx->ttab, x_dev, T, p->A, w_dev,
+          (const float2*)(ws + L.traj), (const float*)(ws + L.scales), nchunks,
+          (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0), (double*)(ws + L.gAdir),
+          (const float2*)(ws + L.sptraj), (const float2*)(ws + L.ev));
+    } else {
+      psi_bwd_uni_kernel<DPc, NQc><<<B, DPc * NQc, smem, st>>>(
+          (const float2*)(ws + L.matN), (const float2*)(ws + L.matRH), (const float2*)(ws + L.matS),
+          (const float2*)(ws + L.qtab), ctx->ttab, x_dev, T, p->A, w_dev,
+          (const float2*)(ws + L.traj), (const float*)(ws + L.scales), nchunks,
+          (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0), (double*)(ws + L.gAdir));
+    }
     PROF_END(ctx, 1, st);
     LAUNCH_CHECK(ctx, "psi_bwd_kernel");
     return AMPS_OK;

@@ -47,6 +47,7 @@ struct alignas(16) FwdSmem {
   float2 xps[2][CHK][DP];      // x'_{k0+kk}
   float2 qs[2][CHK][DP];       // q_k
   float es[CHK][ES];           // per-thread partial of Re(x'^dag S x')
+  float2 spp[CHK][NQ][DP];     // per-lane partials of S x'_k (summed when flushed for the backward)
   float wav[2][CHK + 4];       // waveform samples k0..k0+len
   float sv[2][CHK + 4];        // s_k
   float incv[2][CHK];          // inc_k
@@ -62,9 +63,8 @@ struct alignas(16) BwdSmem {
   float4 cina[2][CHK][DP];     // chain inputs (chunk & 1): { c_k q_k , alpha_k (S x'_k)_i }
   float4 cinb[2][CHK][DP];     //                           { beta_k x_k,i , dtm_k x_k,i }
   float2 mus[2][CHK][DP];      // adjoint of x'_k (chunk & 1): chain writes, tiles read
-  float2 sps[CHK][DP];         // S x'_k (prep scratch)
-  float es[CHK][DP + 1];       // prep scratch
-  float ns[CHK][DP + 1];       // prep scratch
+  float2 spl[2][CHK][DP];      // S x'_k stored by the forward (chunk & 1): landing / prep
+  float2 evl[2][CHK];          // (E_k, |x_k|^2) stored by the forward
   float wav[2][CHK + 4];
   float tt[2][CHK + 4];        // tt[.][0] = t_{k0-1}, tt[.][1+kk] = t_{k0+kk}
   float scs[2][4];
@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(2 * DP * NQ)
                    const float2* __restrict__ matS, const float2* __restrict__ qtab,
                    const float2* __restrict__ psi0p, const float* __restrict__ x, int T, float A,
                    float* __restrict__ loss, double* __restrict__ lossd,
-                   float2* __restrict__ traj, float* __restrict__ scales, int nchunks) {
+                   float2* __restrict__ traj, float* __restrict__ scales, int nchunks,
+                   float2* __restrict__ sptraj, float2* __restrict__ evout) {
   using M = Map<DP, NQ>;
   using Sm = FwdSmem<DP, NQ>;
   constexpr int NTC = M::NT;       // threads per role
@@ -223,6 +224,7 @@ __global__ void __launch_bounds__(2 * DP * NQ)
         for (int kk = 0; kk < len; ++kk) {
           const float2 part = matvec1<DP, NQ>(Sr, sm.xps[p][kk], jq);
           const float2 xpi = sm.xps[p][kk][i];
+          sm.spp[kk][jq][i] = part;
           sm.es[kk][tr] = fmaf(xpi.x, part.x, xpi.y * part.y);
         }
 #endif
@@ -244,12 +246,26 @@ __global__ void __launch_bounds__(2 * DP * NQ)
             const float E = en / nu2;                                  // model.py:324-325 on x'
             const float z = (E * sm.incv[p][kk]) / A;                  // model.py:294
             lossacc -= (double)log1pf(z);
+            if (evout) evout[(size_t)b * T + k0 + kk] = make_float2(E, nu2);   // for the adjoint sweep
           }
         }
         if (traj) {   // flush x_{k0+1 .. k0+len}
           const float4* src = reinterpret_cast<const float4*>(&sm.xs[p][1][0]);
           float4* dst = reinterpret_cast<float4*>(traj + ((size_t)b * T + k0 + 1) * DP);
           for (int idx = tr; idx < len * DP / 2; idx += NTC) dst[idx] = src[idx];
+        }
+        if (sptraj) {   // S x'_k for the adjoint sweep (saves it the mat-vec)
+          float2* dst = sptraj + ((size_t)b * T + k0) * DP;
+          for (int idx = tr; idx < len * DP; idx += NTC) {
+            const int kk = idx / DP, r = idx % DP;
+            float2 sp = sm.spp[kk][0][r];
+#pragma unroll
+            for (int j = 1; j < NQ; ++j) {
+              sp.x += sm.spp[kk][j][r].x;
+              sp.y += sm.spp[kk][j][r].y;
+            }
+            dst[idx] = sp;
+          }
         }
       }
       cp_async_wait<0>();
@@ -289,15 +305,14 @@ __global__ void __launch_bounds__(2 * DP * NQ)
                    const float* __restrict__ w, const float2* __restrict__ traj,
                    const float* __restrict__ scales, int nchunks, float2* __restrict__ Gout,
                    float* __restrict__ gfout, float2* __restrict__ lam0out,
-                   double* __restrict__ gAdir) {
+                   double* __restrict__ gAdir, const float2* __restrict__ sptraj,
+                   const float2* __restrict__ evin) {
   using M = Map<DP, NQ>;
   using Sm = BwdSmem<DP, NQ>;
   constexpr int NTC = M::NT;
   constexpr int CPT = M::CPT;
   constexpr int NP = M::NP;
   constexpr int CHK = Sm::CHK;
-  constexpr int G = NTC / CHK, PER = DP / G;   // prep scalar phase: G threads per step
-  static_assert(DP % G == 0 && G <= 32, "scalar-phase grouping");
   constexpr int LV = (NQ == 4) ? 2 : 3;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Sm& sm = *reinterpret_cast<Sm*>(smem_raw);
@@ -380,8 +395,6 @@ __global__ void __launch_bounds__(2 * DP * NQ)
     const float* xb = x + (size_t)b * T;
     const float2* trb = traj + (size_t)b * T * DP;
     const float wb = w[b];
-    float2 Sr[CPT];
-    load_slice<DP, NQ>(Sr, matS, i, jq);
     float2 GR[CPT], GN[CPT], GE[CPT];
 #pragma unroll
     for (int c = 0; c < CPT; ++c) GR[c] = GN[c] = GE[c] = make_float2(0.f, 0.f);
@@ -401,6 +414,12 @@ __global__ void __launch_bounds__(2 * DP * NQ)
         cp_async4(&sm.tt[c & 1][idx], ttab + (k0 + idx > 0 ? k0 + idx - 1 : 0));
       }
       if (tr == 0) cp_async4(&sm.scs[c & 1][0], scales + (size_t)b * nchunks + c);
+      const float2* ssrc = sptraj + ((size_t)b * T + k0) * DP;
+      float2* sdst = &sm.spl[c & 1][0][0];
+      for (int idx = tr; idx < len * DP / 2; idx += NTC) cp_async16(sdst + 2 * idx, ssrc + 2 * idx);
+      const float2* esrc = evin + (size_t)b * T + k0;
+      for (int idx = tr; idx < 2 * len; idx += NTC)
+        cp_async4(reinterpret_cast<float*>(&sm.evl[c & 1][0]) + idx, reinterpret_cast<const float*>(esrc) + idx);
     };
 
     // rank-1 gradient tiles of one finished chunk (its mu_k are all in shared memory)
@@ -432,7 +451,8 @@ __global__ void __launch_bounds__(2 * DP * NQ)
       }
     };
 
-    // everything the chain needs for one chunk, from the landed trajectory
+    // everything the chain needs for one chunk, from the landed trajectory (elementwise: S x'_k,
+    // E_k and |x_k|^2 were stored by the forward)
     auto prep_chunk = [&](int c) {
       const int len = chunk_len(c), k0 = c * CHK;
       const int lx = c & 3, lq = c & 1, lp3 = c % 3;
@@ -440,70 +460,33 @@ __global__ void __launch_bounds__(2 * DP * NQ)
       const float inv_sc = 1.0f / sc;
       if (tr < len) {
         const float inc = sm.wav[lq][tr + 1] - sm.wav[lq][tr];
-        sm.incv[tr] = inc;
-        sm.sv[lp3][tr] = inc / A;
+        const float s = inc / A;
+        sm.sv[lp3][tr] = s;
         sm.dtm[tr] = (k0 + tr > 0) ? sm.tt[lq][tr + 1] - sm.tt[lq][tr] : 0.f;
-      }
-      // P1: x'_k = conj(q_k) x_{k+1} / c_k ; |x_k|^2
-      for (int idx = tr; idx < len * DP; idx += NTC) {
-        const int kk = idx / DP, r = idx % DP;
-        float2 xp = cmul_ca(sm.qs[lq][kk][r], sm.xs[lx][kk + 1][r]);
-        if (kk == len - 1) {
-          xp.x *= inv_sc;
-          xp.y *= inv_sc;
-        }
-        sm.xps[lp3][kk][r] = xp;
-        sm.ns[kk][r] = cabs2(sm.xs[lx][kk][r]);
+        const float2 ev = sm.evl[lq][tr];
+        const float E = ev.x, nu2 = ev.y;
+        const float arg = 1.0f + (E * inc) / A;
+        const float gE = wb * (-s / arg);
+        const float alpha = 2.0f * gE / nu2;
+        sm.alphas[lp3][tr] = alpha;
+        sm.betas[tr] = -alpha * E;
+        gAacc += (double)wb * (double)E * (double)inc / ((double)A * (double)A * (double)arg);
       }
       bar_named(2, NTC);
-      // P2: S x' and e_i
-      for (int kk = 0; kk < len; ++kk) {
-        float2 part = matvec1<DP, NQ>(Sr, sm.xps[lp3][kk], jq);
-        part = group_sum<NQ>(part);
-        const float2 xpi = sm.xps[lp3][kk][i];
-        sts_if(jq == 1, &sm.sps[kk][i], part);
-        sts_if(jq == 2, &sm.es[kk][i], fmaf(xpi.x, part.x, xpi.y * part.y));
-      }
-      bar_named(2, NTC);
-      // P3: alpha_k, beta_k and the direct dL/dA term; G threads per step
-      {
-        const int kk = tr / G, g = tr % G;
-        float en = 0.f, nu2 = 0.f;
-        if (kk < len) {
-#pragma unroll
-          for (int r = 0; r < PER; ++r) {
-            en += sm.es[kk][g * PER + r];
-            nu2 += sm.ns[kk][g * PER + r];
-          }
-        }
-#pragma unroll
-        for (int m = 1; m < G; m <<= 1) {
-          en += __shfl_xor_sync(0xffffffffu, en, m);
-          nu2 += __shfl_xor_sync(0xffffffffu, nu2, m);
-        }
-        if (g == 0 && kk < len) {
-          const float E = en / nu2;
-          const float inc = sm.incv[kk];
-          const float arg = 1.0f + (E * inc) / A;
-          const float gE = wb * (-sm.sv[lp3][kk] / arg);
-          const float alpha = 2.0f * gE / nu2;
-          sm.alphas[lp3][kk] = alpha;
-          sm.betas[kk] = -alpha * E;
-          gAacc += (double)wb * (double)E * (double)inc / ((double)A * (double)A * (double)arg);
-        }
-      }
-      bar_named(2, NTC);
-      // P4: packed per-row chain inputs
       for (int idx = tr; idx < len * DP; idx += NTC) {
         const int kk = idx / DP, r = idx % DP;
         float2 q = sm.qs[lq][kk][r];
+        const float2 xk = sm.xs[lx][kk][r];
+        float2 xp = cmul_ca(q, sm.xs[lx][kk + 1][r]);
         if (kk == len - 1) {
+          xp.x *= inv_sc;
+          xp.y *= inv_sc;
           q.x *= sc;
           q.y *= sc;
         }
+        sm.xps[lp3][kk][r] = xp;
         const float al = sm.alphas[lp3][kk], be = sm.betas[kk], dt = sm.dtm[kk];
-        const float2 sp = sm.sps[kk][r];
-        const float2 xk = sm.xs[lx][kk][r];
+        const float2 sp = sm.spl[lq][kk][r];
         sm.cina[lq][kk][r] = make_float4(q.x, q.y, al * sp.x, al * sp.y);
         sm.cinb[lq][kk][r] = make_float4(be * xk.x, be * xk.y, dt * xk.x, dt * xk.y);
       }
