@@ -14,6 +14,7 @@
 #include "amps_psi.cuh"
 #include "amps_psi_cluster.cuh"
 #include "amps_rho.cuh"
+#include "amps_scan_tc.cuh"
 
 using namespace amps;
 
@@ -411,7 +412,7 @@ int amps_psi_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
           (const float2*)(ws + L.matN), (const float2*)(ws + L.matR), (const float2*)(ws + L.matS),
           (const float2*)(ws + L.qtab), (const float2*)(ws + L.psi0p), x_dev, T, p->A, loss_dev,
           (double*)(ws + L.lossd), save ? (float2*)(ws + L.traj) : nullptr,
-          save ? (float*)(ws + L.scales) : nullptr, nchunks);
+          save ? (float*)(ws + L.scales) : nullptr, nchunks, (const float2*)nullptr, 0, 0);
     }
     PROF_END(ctx, 0, st);
     LAUNCH_CHECK(ctx, "psi_fwd_kernel");
@@ -512,6 +513,92 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
         (const float2*)(ws + L.matR), p->D, DP, cprime, p->A, grad_dev);
     LAUNCH_CHECK(ctx, "psi_grad_finalize_kernel");
   }
+  return AMPS_OK;
+}
+
+// ---- parallel-in-time forward (tcgen05 operator scan), D <= 64 -------------------------------
+namespace {
+struct ScanWs {
+  PsiWs base;
+  size_t ops, ystart, lossv, total;
+  int nvc, m_steps;
+};
+ScanWs scan_ws_layout(int B, int T, int num_sms) {
+  ScanWs w{};
+  w.base = psi_ws_layout(64, B, T - 1, T, false);
+  const int nsteps = T - 1;
+  int nvc = B > 0 ? (num_sms + B - 1) / B : 1;               // virtual clips per clip: fill the GPU once
+  int m = nsteps > 0 ? (nsteps + nvc - 1) / nvc : CH;
+  m = ((m + CH - 1) / CH) * CH;                                // whole 32-step chunks
+  nvc = nsteps > 0 ? (nsteps + m - 1) / m : 1;
+  w.nvc = nvc;
+  w.m_steps = m;
+  size_t off = w.base.total;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += align_up(bytes);
+    return o;
+  };
+  w.ops = take((size_t)B * nvc * TC_N * TC_N * sizeof(float));
+  w.ystart = take((size_t)B * nvc * TC_D * sizeof(float2));
+  w.lossv = take((size_t)B * nvc * sizeof(double));
+  w.total = off;
+  return w;
+}
+}  // namespace
+
+size_t amps_psi_scan_workspace_bytes(int D, int B, int T) {
+  if (D <= 0 || D > 64 || B <= 0 || T < 1) return 0;
+  return scan_ws_layout(B, T, 148).total + (size_t)B * 160 * (TC_N * TC_N * 4 + TC_D * 8 + 8);
+}
+
+int amps_psi_loss_fwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T,
+                           float* loss_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+  int rc = check_common(ctx, p);
+  if (rc) return rc;
+  if (!p->psi0_dev) return fail(ctx, AMPS_E_INVALID, "psi0_dev is NULL");
+  if (B < 0 || T < 1) return fail(ctx, AMPS_E_INVALID, "bad shape B=%d T=%d", B, T);
+  if (B == 0) return AMPS_OK;
+  if (!x_dev || !loss_dev || !ws_dev) return fail(ctx, AMPS_E_INVALID, "NULL buffer");
+  if (p->D > 64) return fail(ctx, AMPS_E_UNSUPPORTED, "the tensor-core scan supports D <= 64 (got %d)", p->D);
+  const ScanWs L = scan_ws_layout(B, T, ctx->num_sms);
+  if (ws_bytes < L.total)
+    return fail(ctx, AMPS_E_WORKSPACE, "workspace %zu < required %zu bytes", ws_bytes, L.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)ws_dev;
+  const int DP = 64;   // every bond dimension is zero-padded to the UMMA shape
+  rc = psi_prepare(ctx, p, DP, ws, L.base, T - 1, st);
+  if (rc) return rc;
+  const int nv = B * L.nvc;
+  {
+    const size_t smem = sizeof(ScanTcSmem) + 1024;
+    CUDA_TRY(ctx, cudaFuncSetAttribute(psi_compose_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PROF_BEGIN(ctx, 2, st);
+    psi_compose_tc_kernel<<<nv, 256, smem, st>>>((const float2*)(ws + L.base.matN), (const float2*)(ws + L.base.matR),
+                                                 (const float2*)(ws + L.base.qtab), x_dev, T, p->A, L.nvc,
+                                                 L.m_steps, (float*)(ws + L.ops));
+    PROF_END(ctx, 2, st);
+    LAUNCH_CHECK(ctx, "psi_compose_tc_kernel");
+  }
+  psi_scan_boundary_kernel<<<B, 128, 0, st>>>((const float*)(ws + L.ops), (const float2*)(ws + L.base.psi0p), L.nvc,
+                                              (float2*)(ws + L.ystart));
+  LAUNCH_CHECK(ctx, "psi_scan_boundary_kernel");
+  {
+    auto kern = psi_fwd_uni_kernel<64, 8, true>;
+    const size_t smem = sizeof(FwdSmemUni<64, 8>);
+    CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PROF_BEGIN(ctx, 0, st);
+    kern<<<nv, 64 * 8, smem, st>>>((const float2*)(ws + L.base.matN), (const float2*)(ws + L.base.matR),
+                                   (const float2*)(ws + L.base.matS), (const float2*)(ws + L.base.qtab),
+                                   (const float2*)(ws + L.base.psi0p), x_dev, T, p->A, (float*)nullptr,
+                                   (double*)(ws + L.lossv), (float2*)nullptr, (float*)nullptr, 0,
+                                   (const float2*)(ws + L.ystart), L.nvc, L.m_steps);
+    PROF_END(ctx, 0, st);
+    LAUNCH_CHECK(ctx, "psi_fwd_uni_kernel<virtual clips>");
+  }
+  psi_scan_sum_kernel<<<(B + 127) / 128, 128, 0, st>>>((const double*)(ws + L.lossv), B, L.nvc, loss_dev,
+                                                       (double*)(ws + L.base.lossd));
+  LAUNCH_CHECK(ctx, "psi_scan_sum_kernel");
   return AMPS_OK;
 }
 

@@ -566,13 +566,17 @@ struct alignas(16) BwdSmemUni {
 // already has several warps per sub-partition, DP = 64)
 // K1u: forward per-clip loss (model.py:257-267, 276-282, 293-334)
 // -------------------------------------------------------------------------------------------
-template <int DP, int NQ>
+// VIRT: "virtual clip" mode of the parallel-in-time scan (amps_scan_tc.cuh): block b replays time
+// chunk (b % nvc) of clip (b / nvc) -- m_steps steps from global step (b % nvc) * m_steps -- starting
+// from its own state psi0v[b]; the per-chunk loss goes to lossd[b].
+template <int DP, int NQ, bool VIRT = false>
 __global__ void __launch_bounds__(DP* NQ)
     psi_fwd_uni_kernel(const float2* __restrict__ matN, const float2* __restrict__ matR,
-                   const float2* __restrict__ matS, const float2* __restrict__ qtab,
-                   const float2* __restrict__ psi0p, const float* __restrict__ x, int T, float A,
+                   const float2* __restrict__ matS, const float2* __restrict__ qtab_,
+                   const float2* __restrict__ psi0p_, const float* __restrict__ x, int T, float A,
                    float* __restrict__ loss, double* __restrict__ lossd,
-                   float2* __restrict__ traj, float* __restrict__ scales, int nchunks) {
+                   float2* __restrict__ traj, float* __restrict__ scales, int nchunks,
+                   const float2* __restrict__ psi0v, int nvc, int m_steps) {
   using M = Map<DP, NQ>;
   using Sm = FwdSmemUni<DP, NQ>;
   constexpr int NT = M::NT;
@@ -583,8 +587,18 @@ __global__ void __launch_bounds__(DP* NQ)
 
   const int t = threadIdx.x, i = t / NQ, jq = t % NQ, lane = t & 31, warp = t >> 5;
   const int b = blockIdx.x;
-  const int nsteps = T - 1;
+  int nsteps = T - 1;
   const float* xb = x + (size_t)b * T;
+  const float2* qtab = qtab_;
+  const float2* psi0p = psi0p_;
+  if (VIRT) {
+    const int clip = b / nvc, kbeg = (b % nvc) * m_steps;
+    nsteps = max(0, min(m_steps, T - 1 - kbeg));
+    xb = x + (size_t)clip * T + kbeg;
+    qtab = qtab_ + (size_t)kbeg * DP;
+    psi0p = psi0v + (size_t)b * DP;
+    nchunks = (nsteps + CH - 1) / CH;
+  }
 
   float2 Nr[CPT], Rr[CPT], Sr[CPT];
   load_slice<DP, NQ>(Nr, matN, i, jq);
@@ -764,7 +778,7 @@ __global__ void __launch_bounds__(DP* NQ)
   if (t == 0) {
     double tot = 0.0;
     for (int wv = 0; wv < NT / 32; ++wv) tot += sm.lred[wv];
-    loss[b] = (float)tot;
+    if (loss) loss[b] = (float)tot;
     if (lossd) lossd[b] = tot;
   }
 }

@@ -1,0 +1,305 @@
+// Parallel-in-time forward scan for small batches (K4): the clip is cut into `nvc` time chunks;
+//   1. psi_compose_tc_kernel  -- one CTA per (clip, chunk) composes the chunk's step operators
+//        C_j = W_{k0+m-1} ... W_{k0},   W_k = diag(q_k) (I + E_k),   E_k = c' R^dag R + s_k R
+//      on the 5th-generation tensor cores: complex D x D operators as real 2D x 2D matrices
+//      (D = 64 -> UMMA M = N = K = 128, kind::tf32).  The running product lives in TENSOR MEMORY
+//      and is fed back as the A operand (TS mode); E_k is formed in shared memory (K-major,
+//      128-byte swizzle) as a tf32 hi/lo pair, and three MMA passes (P_hi E_hi + P_lo E_hi + P_hi E_lo)
+//      accumulate P^T E^T ON TOP of an exact fp32 copy of P^T, so only the small correction E P
+//      (|E| ~ 3e-2) goes through tf32 products: per-step error ~1e-8 |P|.  The diagonal phase
+//      rotation q_k is applied in fp32 by the epilogue warps (tcgen05.ld / tcgen05.st).
+//   2. psi_scan_boundary_kernel -- sequential over the nvc chunk operators: chunk start states.
+//   3. the sequential forward kernel replays every chunk from its start state as an independent
+//      "virtual clip" (loss terms, optional trajectory).
+// Costs 8 D^3 flops per step instead of 24 D^2 (x21 at D = 64) but turns ONE latency-bound chain of
+// T steps into 148 chains of T/148 steps: worthwhile only when the batch cannot fill the GPU.
+#pragma once
+#include "amps_common.cuh"
+
+namespace amps {
+
+constexpr int TC_D = 64;               // complex bond dimension handled here (smaller D is zero-padded)
+constexpr int TC_N = 2 * TC_D;         // real-form dimension = UMMA M = N = K
+constexpr int TC_KB = 32;              // floats per 128-byte swizzle row
+constexpr int TC_NKB = TC_N / TC_KB;   // K blocks per operand
+constexpr int TC_TILE = TC_N * 128;    // bytes of one K block (128 rows x 128 B)
+
+struct alignas(1024) ScanTcSmem {
+  uint8_t bhi[TC_NKB * TC_TILE];   // E_k truncated to tf32      (real form, K-major, SWIZZLE_128B)
+  uint8_t blo[TC_NKB * TC_TILE];   // E_k - trunc(E_k)
+  float2 cM[TC_D][TC_D];           // c' R^dag R  ( = N - I )
+  float2 Rm[TC_D][TC_D];
+  float2 qv[2][TC_D];              // q_k, by step parity
+  unsigned long long mbar;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout)
+__device__ __forceinline__ uint64_t tc_make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);   // start address            [0,14)
+  d |= (uint64_t)1 << 16;                    // leading byte offset      [16,30) (unused: swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset       [32,46): 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                    // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, kind::tf32, issued by one thread
+__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc,
+                                          uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+      "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+      "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+      "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+      "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+}
+__device__ __forceinline__ float tc_trunc_tf32(float x) {
+  return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+}
+
+// TMEM column map (512 columns allocated): X = running product P^T (A operand), Z = its tf32 residual,
+// Dacc = exact fp32 copy of P^T that the MMAs accumulate P^T E^T onto.
+constexpr uint32_t TC_COL_X = 0, TC_COL_Z = 128, TC_COL_D = 256;
+
+// grid = B * nvc CTAs, block = 256 threads: warps 0-3 own the 128 TMEM lanes (epilogue),
+// warps 4-7 form E_k in shared memory; thread 0 issues the MMAs.
+__global__ void __launch_bounds__(256)
+    psi_compose_tc_kernel(const float2* __restrict__ matN, const float2* __restrict__ matR,
+                          const float2* __restrict__ qtab, const float* __restrict__ x, int T, float A,
+                          int nvc, int m_steps, float* __restrict__ opsT) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // SWIZZLE_128B operands need a 1024-byte aligned base (the launch reserves 1 KB of slack)
+  unsigned char* smem_al = smem_raw + ((1024u - (tc_smem_u32(smem_raw) & 1023u)) & 1023u);
+  ScanTcSmem& sm = *reinterpret_cast<ScanTcSmem*>(smem_al);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int vc = blockIdx.x, clip = vc / nvc, jc = vc % nvc;
+  const int nsteps = T - 1;
+  const int k_begin = jc * m_steps;
+  const int nloc = max(0, min(m_steps, nsteps - k_begin));
+  const float* xb = x + (size_t)clip * T + k_begin;
+  const float2* qb = qtab + (size_t)k_begin * TC_D;
+
+  for (int idx = tid; idx < TC_D * TC_D; idx += 256) {
+    const int a = idx / TC_D, c = idx % TC_D;
+    float2 n = matN[idx];
+    if (a == c) n.x -= 1.0f;          // c' R^dag R = N - I (exact for N_aa ~ 1)
+    sm.cM[a][c] = n;
+    sm.Rm[a][c] = matR[idx];
+  }
+  if (tid == 0) {
+    mbar_init(&sm.mbar, 1);
+    mbar_fence_init_cluster();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(tc_smem_u32(&sm.tmem_base)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = sm.tmem_base;
+  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);   // (epilogue warps)
+
+  if (tid < 128) {   // P^T = I : X = I, Dacc = I, Z = 0
+    float v[32], z[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) z[j] = 0.f;
+    for (int c0 = 0; c0 < TC_N; c0 += 32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = (c0 + j == tid) ? 1.0f : 0.0f;
+      tc_st32(lane_base + TC_COL_X + c0, v);
+      tc_st32(lane_base + TC_COL_D + c0, v);
+      tc_st32(lane_base + TC_COL_Z + c0, z);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+  }
+
+  // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_N >> 4) << 24);
+
+  for (int kk = 0; kk <= nloc; ++kk) {
+    if (kk > 0) mbar_wait(&sm.mbar, (kk - 1) & 1);     // the MMAs of step kk-1 are complete
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    if (tid >= 128) {
+      if (kk < nloc) {
+        // ---- producers: E_k = c' R^dag R + s_k R in real form [[Er,-Ei],[Ei,Er]], hi/lo, swizzled ----
+        const int pt = tid - 128;
+        const float s = (xb[kk + 1] - xb[kk]) / A;                       // model.py:263, 303
+        if (pt < TC_D) sm.qv[kk & 1][pt] = qb[(size_t)kk * TC_D + pt];
+        for (int idx = pt; idx < TC_N * (TC_N / 4); idx += 128) {        // 16-byte chunks of a row
+          const int n = idx / (TC_N / 4), c = idx % (TC_N / 4);
+          const int a = n & (TC_D - 1);
+          const bool lower = n >= TC_D;                                   // rows a+D : [Ei, Er]
+          const int k0 = 4 * c;
+          const bool right = k0 >= TC_D;                                  // columns b+D
+          const int b0 = k0 & (TC_D - 1);
+          float hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 m = sm.cM[a][b0 + e], r = sm.Rm[a][b0 + e];
+            const float er = fmaf(s, r.x, m.x), ei = fmaf(s, r.y, m.y);
+            // [ Er  -Ei ]
+            // [ Ei   Er ]
+            const float v = lower ? (right ? er : ei) : (right ? -ei : er);
+            hi[e] = tc_trunc_tf32(v);
+            lo[e] = v - hi[e];
+          }
+          const int kb = c / 8, cc = c % 8;
+          const int off = kb * TC_TILE + n * 128 + ((cc ^ (n & 7)) * 16);
+          *reinterpret_cast<float4*>(sm.bhi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4*>(sm.blo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      }
+    } else if (kk > 0) {
+      // ---- epilogue of step kk-1: Dacc = (P + E P)^T ; rotate column pairs (a, a+D) by q_a ----
+      const float2* q = sm.qv[(kk - 1) & 1];
+      for (int h = 0; h < 2; ++h) {
+        float ya[32], yb[32];
+        tc_ld32(lane_base + TC_COL_D + 32 * h, ya);
+        tc_ld32(lane_base + TC_COL_D + TC_D + 32 * h, yb);
+        float lo[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float2 qa = q[32 * h + j];
+          const float va = qa.x * ya[j] - qa.y * yb[j];
+          const float vb = fmaf(qa.y, ya[j], qa.x * yb[j]);
+          ya[j] = va;
+          yb[j] = vb;
+        }
+        tc_st32(lane_base + TC_COL_X + 32 * h, ya);
+        tc_st32(lane_base + TC_COL_D + 32 * h, ya);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) lo[j] = ya[j] - tc_trunc_tf32(ya[j]);
+        tc_st32(lane_base + TC_COL_Z + 32 * h, lo);
+        tc_st32(lane_base + TC_COL_X + TC_D + 32 * h, yb);
+        tc_st32(lane_base + TC_COL_D + TC_D + 32 * h, yb);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) lo[j] = yb[j] - tc_trunc_tf32(yb[j]);
+        tc_st32(lane_base + TC_COL_Z + TC_D + 32 * h, lo);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    if (tid == 0 && kk < nloc) {
+      // Dacc += P_hi^T E_hi^T + P_lo^T E_hi^T + P_hi^T E_lo^T   (A from tensor memory, B from smem)
+#pragma unroll 1
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t acol = tmem + ((pass == 1) ? TC_COL_Z : TC_COL_X);
+        const uint8_t* bsm = (pass == 2) ? sm.blo : sm.bhi;
+#pragma unroll 1
+        for (int kb = 0; kb < TC_NKB; ++kb) {
+          const uint64_t db0 = tc_make_desc(tc_smem_u32(bsm + kb * TC_TILE));
+#pragma unroll
+          for (int ks = 0; ks < TC_KB / 8; ++ks)      // UMMA_K = 8 tf32: 8 TMEM columns / 32 smem bytes
+            tc_mma_ts(tmem + TC_COL_D, acol + kb * TC_KB + ks * 8, db0 + 2 * ks, idesc, 1u);
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
+                       tc_smem_u32(&sm.mbar))
+                   : "memory");
+    }
+  }
+
+  // chunk operator out: opsT[vc][m][n] = P^T[m][n]
+  if (tid < 128) {
+    float* dst = opsT + ((size_t)vc * TC_N + tid) * TC_N;
+    for (int c0 = 0; c0 < TC_N; c0 += 32) {
+      float v[32];
+      tc_ld32(lane_base + TC_COL_X + c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem));
+}
+
+// Sequential pass over the chunk operators of one clip: normalised chunk start states.
+// grid = B, block = 128 (one thread per real-form row).
+__global__ void __launch_bounds__(128)
+    psi_scan_boundary_kernel(const float* __restrict__ opsT, const float2* __restrict__ psi0p, int nvc,
+                             float2* __restrict__ ystart) {
+  __shared__ float y[TC_N];
+  __shared__ float red[4];
+  const int t = threadIdx.x, b = blockIdx.x;
+  if (t < TC_D) {
+    const float2 p = psi0p[t];
+    y[t] = p.x;
+    y[t + TC_D] = p.y;
+  }
+  __syncthreads();
+  for (int j = 0; j < nvc; ++j) {
+    float n2 = warp_sum_f(y[t] * y[t]);
+    if ((t & 31) == 0) red[t >> 5] = n2;
+    __syncthreads();
+    const float rn = rsqrtf(red[0] + red[1] + red[2] + red[3]);
+    const float yn = y[t] * rn;
+    __syncthreads();
+    y[t] = yn;
+    __syncthreads();
+    if (t < TC_D) ystart[((size_t)b * nvc + j) * TC_D + t] = make_float2(y[t], y[t + TC_D]);
+    // y_new[n] = sum_m P^T[m][n] y[m]
+    const float* PT = opsT + ((size_t)b * nvc + j) * TC_N * TC_N;
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 8
+    for (int m = 0; m < TC_N; m += 2) {
+      acc0 = fmaf(PT[(size_t)m * TC_N + t], y[m], acc0);
+      acc1 = fmaf(PT[(size_t)(m + 1) * TC_N + t], y[m + 1], acc1);
+    }
+    __syncthreads();
+    y[t] = acc0 + acc1;
+    __syncthreads();
+  }
+}
+
+// per-clip loss = sum over the clip's virtual clips
+__global__ void psi_scan_sum_kernel(const double* __restrict__ lossv, int B, int nvc, float* __restrict__ loss,
+                                    double* __restrict__ lossd) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) {
+    double s = 0.0;
+    for (int j = 0; j < nvc; ++j) s += lossv[(size_t)b * nvc + j];
+    loss[b] = (float)s;
+    if (lossd) lossd[b] = s;
+  }
+}
+
+}  // namespace amps

@@ -259,6 +259,30 @@ class PsiCMPS(CMPS):
         gs = torch.autograd.grad(tot, [p for _, p in self.named_parameters()], allow_unused=True)
         return {self.TF_NAMES.get(n, n): g for n, g in zip(names, gs)}
 
+    @torch.no_grad()
+    def loss_per_clip_scan(self, data=None) -> torch.Tensor:
+        """Same values as ``loss_per_clip`` computed with the parallel-in-time tensor-core scan
+        (amps_psi_loss_fwd_scan): for batches far smaller than the SM count, D <= 64, forward only."""
+        self._require_cuda()
+        x = self._batch(data)
+        B, T = x.shape
+        lib, h = _lib.load(), self._ctx()
+        R_ri = torch.view_as_real(self.R).contiguous()
+        f = self.freqs.contiguous()
+        p0 = torch.view_as_real(self.psi_0).contiguous()
+        p = _lib.AmpsParams(D=self.bond_d, reserved=0, R_dev=R_ri.data_ptr(), freqs_dev=f.data_ptr(),
+                            psi0_dev=p0.data_ptr(), rho0_dev=None, A=float(self.A),
+                            sigma=float(self.sigma), delta_t=float(self.delta_t))
+        nbytes = lib.amps_psi_scan_workspace_bytes(self.bond_d, B, T)
+        if nbytes == 0:
+            raise _lib.AmpsError(-2, f"bond dimension {self.bond_d} is not supported by the tensor-core scan")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        loss = torch.empty(B, dtype=torch.float32, device=self.device)
+        rc = lib.amps_psi_loss_fwd_scan(h, C.byref(p), _ptr(x), B, T, _ptr(loss), _ptr(ws), nbytes,
+                                        _stream(self.device))
+        _lib.check(h, rc)
+        return loss
+
     def sample(self, num_samples, length, temp=1, noise=None, generator=None) -> torch.Tensor:
         """[num_samples, length] cumulative X_t scaled by A (model.py:242-251)."""
         return self.sample_from_noise(self._noise(num_samples, length, temp, noise, generator))

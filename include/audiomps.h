@@ -106,6 +106,16 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
                       void* stream);
 size_t amps_psi_grad_count(int D); /* = 2*D*D + 3*D + 2 */
 
+/* Parallel-in-time forward loss for SMALL batches (same result as amps_psi_loss_fwd; D <= 64, zero
+ * padded to 64): the clip is cut into ~#SMs/B time chunks whose step operators are composed on the
+ * tcgen05 tensor cores (complex DxD as real 2Dx2D, kind::tf32 with a 3-pass hi/lo split, running
+ * product in tensor memory), a short sequential pass over the chunk operators gives the chunk start
+ * states, and every chunk is then replayed in parallel by the sequential kernel.  8 D^3 instead of
+ * 24 D^2 flops per step: use it only when B is far below the SM count.  Forward only. */
+size_t amps_psi_scan_workspace_bytes(int D, int B, int T);
+int amps_psi_loss_fwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T,
+                           float* loss_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
 /* PsiCMPS.sample / _psi_and_sample_update (model.py:242-251, 284-291) with the noise tensor
  * supplied by the caller (the reference draws it once, model.py:246).
  *   noise_dev float32 [L,n] (time-major, as tf.random_normal([length, num_samples]))
