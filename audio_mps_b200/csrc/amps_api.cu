@@ -574,14 +574,18 @@ int amps_psi_loss_fwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
     const size_t smem = sizeof(ScanTcSmem) + 1024;
     CUDA_TRY(ctx, cudaFuncSetAttribute(psi_compose_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PROF_BEGIN(ctx, 2, st);
-    psi_compose_tc_kernel<<<nv, 256, smem, st>>>((const float2*)(ws + L.base.matN), (const float2*)(ws + L.base.matR),
+    psi_compose_tc_kernel<<<nv, TC_THREADS, smem, st>>>((const float2*)(ws + L.base.matN), (const float2*)(ws + L.base.matR),
                                                  (const float2*)(ws + L.base.qtab), x_dev, T, p->A, L.nvc,
                                                  L.m_steps, (float*)(ws + L.ops));
     PROF_END(ctx, 2, st);
     LAUNCH_CHECK(ctx, "psi_compose_tc_kernel");
   }
-  psi_scan_boundary_kernel<<<B, 128, 0, st>>>((const float*)(ws + L.ops), (const float2*)(ws + L.base.psi0p), L.nvc,
-                                              (float2*)(ws + L.ystart));
+  {
+    const size_t bsm = (size_t)(2 * TC_N * TC_N + 3 * TC_N + 8) * sizeof(float);
+    CUDA_TRY(ctx, cudaFuncSetAttribute(psi_scan_boundary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+    psi_scan_boundary_kernel<<<B, 256, bsm, st>>>((const float*)(ws + L.ops), (const float2*)(ws + L.base.psi0p),
+                                                  L.nvc, (float2*)(ws + L.ystart));
+  }
   LAUNCH_CHECK(ctx, "psi_scan_boundary_kernel");
   {
     auto kern = psi_fwd_uni_kernel<64, 8, true>;

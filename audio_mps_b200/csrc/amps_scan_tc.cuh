@@ -94,9 +94,10 @@ __device__ __forceinline__ float tc_trunc_tf32(float x) {
 // Dacc = exact fp32 copy of P^T that the MMAs accumulate P^T E^T onto.
 constexpr uint32_t TC_COL_X = 0, TC_COL_Z = 128, TC_COL_D = 256;
 
-// grid = B * nvc CTAs, block = 256 threads: warps 0-3 own the 128 TMEM lanes (epilogue),
-// warps 4-7 form E_k in shared memory; thread 0 issues the MMAs.
-__global__ void __launch_bounds__(256)
+// grid = B * nvc CTAs, block = 512 threads: warps 0-3 own the 128 TMEM lanes (epilogue),
+// warps 4-15 form E_k in shared memory; thread 0 issues the MMAs.
+constexpr int TC_THREADS = 512;
+__global__ void __launch_bounds__(TC_THREADS)
     psi_compose_tc_kernel(const float2* __restrict__ matN, const float2* __restrict__ matR,
                           const float2* __restrict__ qtab, const float* __restrict__ x, int T, float A,
                           int nvc, int m_steps, float* __restrict__ opsT) {
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(256)
   const float* xb = x + (size_t)clip * T + k_begin;
   const float2* qb = qtab + (size_t)k_begin * TC_D;
 
-  for (int idx = tid; idx < TC_D * TC_D; idx += 256) {
+  for (int idx = tid; idx < TC_D * TC_D; idx += TC_THREADS) {
     const int a = idx / TC_D, c = idx % TC_D;
     float2 n = matN[idx];
     if (a == c) n.x -= 1.0f;          // c' R^dag R = N - I (exact for N_aa ~ 1)
@@ -159,28 +160,41 @@ __global__ void __launch_bounds__(256)
         const int pt = tid - 128;
         const float s = (xb[kk + 1] - xb[kk]) / A;                       // model.py:263, 303
         if (pt < TC_D) sm.qv[kk & 1][pt] = qb[(size_t)kk * TC_D + pt];
-        for (int idx = pt; idx < TC_N * (TC_N / 4); idx += 128) {        // 16-byte chunks of a row
-          const int n = idx / (TC_N / 4), c = idx % (TC_N / 4);
-          const int a = n & (TC_D - 1);
-          const bool lower = n >= TC_D;                                   // rows a+D : [Ei, Er]
-          const int k0 = 4 * c;
-          const bool right = k0 >= TC_D;                                  // columns b+D
-          const int b0 = k0 & (TC_D - 1);
-          float hi[4], lo[4];
+        // one thread per (row a, 4 consecutive columns b): the complex element is computed once and
+        // written to its four real-form positions  [ Er -Ei ; Ei Er ], hi and lo
+        for (int idx = pt; idx < TC_D * (TC_D / 4); idx += TC_THREADS - 128) {
+          const int a = idx / (TC_D / 4), c = idx % (TC_D / 4);           // c: 16-byte chunk within [0, D)
+          float er[4], ei[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float2 m = sm.cM[a][b0 + e], r = sm.Rm[a][b0 + e];
-            const float er = fmaf(s, r.x, m.x), ei = fmaf(s, r.y, m.y);
-            // [ Er  -Ei ]
-            // [ Ei   Er ]
-            const float v = lower ? (right ? er : ei) : (right ? -ei : er);
-            hi[e] = tc_trunc_tf32(v);
-            lo[e] = v - hi[e];
+            const float2 m = sm.cM[a][4 * c + e], r = sm.Rm[a][4 * c + e];
+            er[e] = fmaf(s, r.x, m.x);
+            ei[e] = fmaf(s, r.y, m.y);
           }
-          const int kb = c / 8, cc = c % 8;
-          const int off = kb * TC_TILE + n * 128 + ((cc ^ (n & 7)) * 16);
-          *reinterpret_cast<float4*>(sm.bhi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<float4*>(sm.blo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+          float4 erh, erl, eih, eil, nih, nil_;
+          float* ph[6] = {&erh.x, &erl.x, &eih.x, &eil.x, &nih.x, &nil_.x};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float h1 = tc_trunc_tf32(er[e]), h2 = tc_trunc_tf32(ei[e]);
+            ph[0][e] = h1;
+            ph[1][e] = er[e] - h1;
+            ph[2][e] = h2;
+            ph[3][e] = ei[e] - h2;
+            ph[4][e] = -h2;
+            ph[5][e] = -(ei[e] - h2);
+          }
+          // chunk index within a 128-column row: left half c, right half c + 16
+          const int cl = c, cr = c + TC_D / 4;
+          const int rt = a, rb = a + TC_D;
+          auto off = [](int n, int cch) { return (cch / 8) * TC_TILE + n * 128 + (((cch % 8) ^ (n & 7)) * 16); };
+          *reinterpret_cast<float4*>(sm.bhi + off(rt, cl)) = erh;    // top-left      Er
+          *reinterpret_cast<float4*>(sm.blo + off(rt, cl)) = erl;
+          *reinterpret_cast<float4*>(sm.bhi + off(rt, cr)) = nih;    // top-right    -Ei
+          *reinterpret_cast<float4*>(sm.blo + off(rt, cr)) = nil_;
+          *reinterpret_cast<float4*>(sm.bhi + off(rb, cl)) = eih;    // bottom-left   Ei
+          *reinterpret_cast<float4*>(sm.blo + off(rb, cl)) = eil;
+          *reinterpret_cast<float4*>(sm.bhi + off(rb, cr)) = erh;    // bottom-right  Er
+          *reinterpret_cast<float4*>(sm.blo + off(rb, cr)) = erl;
         }
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
       }
@@ -253,41 +267,58 @@ __global__ void __launch_bounds__(256)
 }
 
 // Sequential pass over the chunk operators of one clip: normalised chunk start states.
-// grid = B, block = 128 (one thread per real-form row).
-__global__ void __launch_bounds__(128)
+// grid = B, block = 256; the next chunk operator (64 KB) streams into shared memory with cp.async
+// while the current mat-vec runs.
+__global__ void __launch_bounds__(256)
     psi_scan_boundary_kernel(const float* __restrict__ opsT, const float2* __restrict__ psi0p, int nvc,
                              float2* __restrict__ ystart) {
-  __shared__ float y[TC_N];
-  __shared__ float red[4];
+  extern __shared__ __align__(16) unsigned char bsm_raw[];
+  float* pt = reinterpret_cast<float*>(bsm_raw);          // [2][128][128]
+  float* y = pt + 2 * TC_N * TC_N;                        // [128]
+  float* part = y + TC_N;                                 // [2][128]
+  float* red = part + 2 * TC_N;                           // [8]
   const int t = threadIdx.x, b = blockIdx.x;
+  const int n = t & (TC_N - 1), half = t >> 7;            // column n, rows [64*half, 64*half+64)
+  auto issue = [&](int j) {
+    const float* src = opsT + ((size_t)b * nvc + j) * TC_N * TC_N;
+    float* dst = pt + (j & 1) * TC_N * TC_N;
+    for (int idx = t; idx < TC_N * TC_N / 4; idx += 256) cp_async16(dst + 4 * idx, src + 4 * idx);
+  };
   if (t < TC_D) {
     const float2 p = psi0p[t];
     y[t] = p.x;
     y[t + TC_D] = p.y;
   }
+  if (nvc > 0) issue(0);
+  cp_async_commit();
   __syncthreads();
   for (int j = 0; j < nvc; ++j) {
-    float n2 = warp_sum_f(y[t] * y[t]);
+    if (j + 1 < nvc) issue(j + 1);
+    cp_async_commit();
+    // normalise and emit the start state of chunk j
+    float n2 = (t < TC_N) ? y[t] * y[t] : 0.f;
+    n2 = warp_sum_f(n2);
     if ((t & 31) == 0) red[t >> 5] = n2;
     __syncthreads();
     const float rn = rsqrtf(red[0] + red[1] + red[2] + red[3]);
-    const float yn = y[t] * rn;
-    __syncthreads();
-    y[t] = yn;
+    if (t < TC_N) y[t] *= rn;
+    cp_async_wait<1>();
     __syncthreads();
     if (t < TC_D) ystart[((size_t)b * nvc + j) * TC_D + t] = make_float2(y[t], y[t + TC_D]);
-    // y_new[n] = sum_m P^T[m][n] y[m]
-    const float* PT = opsT + ((size_t)b * nvc + j) * TC_N * TC_N;
+    // y_new[n] = sum_m P^T[m][n] y[m], the m range split over the two thread halves
+    const float* PT = pt + (j & 1) * TC_N * TC_N;
     float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll 8
-    for (int m = 0; m < TC_N; m += 2) {
-      acc0 = fmaf(PT[(size_t)m * TC_N + t], y[m], acc0);
-      acc1 = fmaf(PT[(size_t)(m + 1) * TC_N + t], y[m + 1], acc1);
+    for (int m = 64 * half; m < 64 * half + 64; m += 2) {
+      acc0 = fmaf(PT[m * TC_N + n], y[m], acc0);
+      acc1 = fmaf(PT[(m + 1) * TC_N + n], y[m + 1], acc1);
     }
+    part[half * TC_N + n] = acc0 + acc1;
     __syncthreads();
-    y[t] = acc0 + acc1;
+    if (t < TC_N) y[t] = part[t] + part[TC_N + t];
     __syncthreads();
   }
+  cp_async_wait<0>();
 }
 
 // per-clip loss = sum over the clip's virtual clips
