@@ -70,9 +70,12 @@ SYMBOLS = {
                                   C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "amps_psi_loss_grad_host": (C.c_int, [C.c_void_p, C.POINTER(AmpsHostParams), C.c_void_p, C.c_int,
                                           C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
-    "amps_rho_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "amps_rho_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "amps_rho_grad_count": (C.c_size_t, [C.c_int]),
     "amps_rho_loss_fwd": (C.c_int, [C.c_void_p, C.POINTER(AmpsParams), C.c_void_p, C.c_int, C.c_int,
-                                    C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+                                    C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "amps_rho_loss_bwd": (C.c_int, [C.c_void_p, C.POINTER(AmpsParams), C.c_void_p, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "amps_rho_evolve": (C.c_int, [C.c_void_p, C.POINTER(AmpsParams), C.c_void_p, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "amps_rho_sample": (C.c_int, [C.c_void_p, C.POINTER(AmpsParams), C.c_void_p, C.c_int, C.c_int,

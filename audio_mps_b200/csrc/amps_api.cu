@@ -718,25 +718,53 @@ int amps_psi_loss_grad_host(amps_ctx* ctx, const amps_host_params* hp, const flo
 }
 
 // ---- RhoCMPS -----------------------------------------------------------------------------
-size_t amps_rho_workspace_bytes(int D, int B, int T) { return rho_workspace_bytes(D, B, T); }
+size_t amps_rho_workspace_bytes(int D, int B, int T, int save_for_bwd) {
+  return rho_workspace_bytes(D, B, T, save_for_bwd != 0);
+}
+size_t amps_rho_grad_count(int D) { return D > 0 ? (size_t)4 * D * D + (size_t)D + 2 : 0; }
 
 int amps_rho_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T,
-                      float* loss_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+                      float* loss_dev, void* ws_dev, size_t ws_bytes, int save_for_bwd, void* stream) {
   int rc = check_common(ctx, p);
   if (rc) return rc;
   if (!p->rho0_dev) return fail(ctx, AMPS_E_INVALID, "rho0_dev is NULL");
   if (B < 0 || T < 1) return fail(ctx, AMPS_E_INVALID, "bad shape B=%d T=%d", B, T);
   if (B == 0) return AMPS_OK;
-  if (!x_dev || !loss_dev) return fail(ctx, AMPS_E_INVALID, "NULL buffer");
+  if (!x_dev || !loss_dev || !ws_dev) return fail(ctx, AMPS_E_INVALID, "NULL buffer");
   if (p->D > RHO_MAX_D) return fail(ctx, AMPS_E_UNSUPPORTED, "rho kernels support D <= %d", RHO_MAX_D);
-  if (ws_bytes < rho_workspace_bytes(p->D, B, T))
-    return fail(ctx, AMPS_E_WORKSPACE, "workspace too small");
+  const bool save = save_for_bwd != 0;
+  const RhoWs L = rho_ws_layout(p->D, B, T, save);
+  if (ws_bytes < L.total) return fail(ctx, AMPS_E_WORKSPACE, "workspace %zu < required %zu bytes", ws_bytes, L.total);
   cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)ws_dev;
   rc = ensure_ttab(ctx, T + 1, (float)p->delta_t, st);
   if (rc) return rc;
-  rc = rho_launch_data(p, ctx->ttab, x_dev, B, T, loss_dev, nullptr, ws_dev, st);
+  rc = rho_launch_data(p, ctx->ttab, x_dev, B, T, loss_dev, nullptr, save ? (float2*)(ws + L.ftraj) : nullptr,
+                       (double*)(ws + L.lossd), st);
   if (rc) return fail(ctx, rc, "rho kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   ctx->launches++;
+  return AMPS_OK;
+}
+
+int amps_rho_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T,
+                      const float* w_dev, void* ws_dev, size_t ws_bytes, float* grad_dev, void* stream) {
+  int rc = check_common(ctx, p);
+  if (rc) return rc;
+  if (B < 0 || T < 1) return fail(ctx, AMPS_E_INVALID, "bad shape B=%d T=%d", B, T);
+  if (!grad_dev) return fail(ctx, AMPS_E_INVALID, "grad_dev is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B == 0) {
+    CUDA_TRY(ctx, cudaMemsetAsync(grad_dev, 0, amps_rho_grad_count(p->D) * sizeof(float), st));
+    return AMPS_OK;
+  }
+  if (!x_dev || !w_dev || !ws_dev) return fail(ctx, AMPS_E_INVALID, "NULL buffer");
+  if (p->D > RHO_MAX_D) return fail(ctx, AMPS_E_UNSUPPORTED, "rho kernels support D <= %d", RHO_MAX_D);
+  const RhoWs L = rho_ws_layout(p->D, B, T, true);
+  if (ws_bytes < L.total) return fail(ctx, AMPS_E_WORKSPACE, "workspace %zu < required %zu bytes", ws_bytes, L.total);
+  if (!ctx->ttab || ctx->ttab_n < T) return fail(ctx, AMPS_E_STATE, "backward without a saving forward");
+  rc = rho_launch_bwd(p, ctx->ttab, x_dev, B, T, w_dev, (char*)ws_dev, L, grad_dev, st);
+  if (rc) return fail(ctx, rc, "rho backward launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  ctx->launches += 2;
   return AMPS_OK;
 }
 
@@ -754,7 +782,7 @@ int amps_rho_evolve(amps_ctx* ctx, const amps_params* p, const float* x_dev, int
   cudaStream_t st = (cudaStream_t)stream;
   rc = ensure_ttab(ctx, T + 1, (float)p->delta_t, st);
   if (rc) return rc;
-  rc = rho_launch_data(p, ctx->ttab, x_dev, B, T, nullptr, (float2*)traj_dev, ws_dev, st);
+  rc = rho_launch_data(p, ctx->ttab, x_dev, B, T, nullptr, (float2*)traj_dev, nullptr, nullptr, st);
   if (rc) return fail(ctx, rc, "rho kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   ctx->launches++;
   return AMPS_OK;

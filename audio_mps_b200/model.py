@@ -105,6 +105,61 @@ class _PsiLossFn(torch.autograd.Function):
         return gR, gf, gp, gA, None, None
 
 
+class _RhoLossFn(torch.autograd.Function):
+    """Per-clip RhoCMPS loss through amps_rho_loss_fwd / amps_rho_loss_bwd."""
+
+    @staticmethod
+    def forward(ctx, R_ri, freqs, rho0_ri, A, x, model):
+        dev = x.device
+        if dev.type != "cuda":
+            raise RuntimeError("RhoCMPS scan requires a CUDA device (no CPU fallback)")
+        lib = _lib.load()
+        h = _lib.context(dev.index if dev.index is not None else torch.cuda.current_device())
+        B, T = x.shape
+        D = freqs.shape[0]
+        need_grad = any(ctx.needs_input_grad[:4])
+        R_ri = R_ri.detach().contiguous().float()
+        freqs = freqs.detach().contiguous().float()
+        rho0_ri = rho0_ri.detach().contiguous().float()
+        p = _lib.AmpsParams(D=D, reserved=0, R_dev=R_ri.data_ptr(), freqs_dev=freqs.data_ptr(),
+                            psi0_dev=None, rho0_dev=rho0_ri.data_ptr(), A=float(A.detach()),
+                            sigma=float(model.sigma), delta_t=float(model.delta_t))
+        nbytes = lib.amps_rho_workspace_bytes(D, B, T, 1 if need_grad else 0)
+        if nbytes == 0:
+            raise _lib.AmpsError(-2, f"bond dimension {D} is not supported by the Rho kernels")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        loss = torch.empty(B, dtype=torch.float32, device=dev)
+        rc = lib.amps_rho_loss_fwd(h, C.byref(p), _ptr(x), B, T, _ptr(loss), _ptr(ws), nbytes,
+                                   1 if need_grad else 0, _stream(dev))
+        _lib.check(h, rc)
+        if need_grad:
+            ctx.keep = (R_ri, freqs, rho0_ri, x, ws, p, h, model)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        R_ri, freqs, rho0_ri, x, ws, p, h, model = ctx.keep
+        lib = _lib.load()
+        dev = x.device
+        B, T = x.shape
+        D = freqs.shape[0]
+        w = gloss.detach().contiguous().float()
+        packed = torch.empty(int(lib.amps_rho_grad_count(D)), dtype=torch.float32, device=dev)
+        rc = lib.amps_rho_loss_bwd(h, C.byref(p), _ptr(x), B, T, _ptr(w), _ptr(ws), ws.numel(),
+                                   _ptr(packed), _stream(dev))
+        _lib.check(h, rc)
+        dp = getattr(model, "_dp_group", None)
+        if dp is not None:
+            torch.distributed.all_reduce(packed, op=torch.distributed.ReduceOp.SUM, group=dp)
+        model._last_packed = packed
+        n = 2 * D * D
+        gR = packed[:n].view(D, D, 2).clone()
+        gf = packed[n:n + D].clone()
+        gr0 = packed[n + D:2 * n + D].clone().view(D, D, 2)
+        gA = packed[2 * n + D].clone()
+        return gR, gf, gr0, gA, None, None
+
+
 # --------------------------------------------------------------------------------------------
 class CMPS(torch.nn.Module):
     """Continuous Matrix Product State (model.py:5-52)."""
@@ -385,23 +440,12 @@ class RhoCMPS(CMPS):
                                freqs_dev=f.data_ptr(), psi0_dev=None, rho0_dev=r0.data_ptr(),
                                A=float(self.A), sigma=float(self.sigma), delta_t=float(self.delta_t))
 
-    @torch.no_grad()
     def loss_per_clip(self, data=None) -> torch.Tensor:
-        """Forward value only: the Rho adjoint kernel is not built yet (scope)."""
+        """loss_b of the rho fold, before the reduce_mean (model.py:132-142); differentiable."""
         self._require_cuda()
         x = self._batch(data)
-        B, T = x.shape
-        lib, h, keep = _lib.load(), self._ctx(), []
-        p = self._params(keep)
-        nbytes = lib.amps_rho_workspace_bytes(self.bond_d, B, T)
-        if nbytes == 0:
-            raise _lib.AmpsError(-2, f"bond dimension {self.bond_d} is not supported by the Rho kernels")
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-        loss = torch.empty(B, dtype=torch.float32, device=self.device)
-        rc = lib.amps_rho_loss_fwd(h, C.byref(p), _ptr(x), B, T, _ptr(loss), _ptr(ws), nbytes,
-                                   _stream(self.device))
-        _lib.check(h, rc)
-        return loss
+        return _RhoLossFn.apply(torch.view_as_real(self.R), self.freqs,
+                                torch.view_as_real(self.rho_0), self.A, x, self)
 
     def loss_fn(self, data=None):
         return self.loss_per_clip(data).mean()                               # model.py:142
@@ -419,7 +463,7 @@ class RhoCMPS(CMPS):
         D = self.bond_d
         lib, h, keep = _lib.load(), self._ctx(), []
         p = self._params(keep)
-        nbytes = lib.amps_rho_workspace_bytes(D, B, T)
+        nbytes = lib.amps_rho_workspace_bytes(D, B, T, 0)
         if nbytes == 0:
             raise _lib.AmpsError(-2, f"bond dimension {D} is not supported by the Rho kernels")
         ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
@@ -437,7 +481,7 @@ class RhoCMPS(CMPS):
         D = self.bond_d
         lib, h, keep = _lib.load(), self._ctx(), []
         p = self._params(keep)
-        nbytes = lib.amps_rho_workspace_bytes(D, n, L + 1)
+        nbytes = lib.amps_rho_workspace_bytes(D, n, L + 1, 0)
         if nbytes == 0:
             raise _lib.AmpsError(-2, f"bond dimension {D} is not supported by the Rho kernels")
         ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)

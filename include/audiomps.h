@@ -148,12 +148,20 @@ int amps_psi_loss_grad_host(amps_ctx* ctx, const amps_host_params* p, const floa
 
 /* ---- RhoCMPS --------------------------------------------------------------------------- */
 
-size_t amps_rho_workspace_bytes(int D, int B, int T);
+size_t amps_rho_workspace_bytes(int D, int B, int T, int save_for_bwd);
 
 /* RhoCMPS._build_loss_rho / _rho_and_loss_update (model.py:132-142, 152-158, 169-203):
- * per-clip loss before the reduce_mean. */
+ * per-clip loss before the reduce_mean.  With save_for_bwd the workspace keeps the interaction-frame
+ * density matrix at the start of every step (B*T*D*D complex64) for amps_rho_loss_bwd. */
 int amps_rho_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T,
-                      float* loss_dev, void* ws_dev, size_t ws_bytes, void* stream);
+                      float* loss_dev, void* ws_dev, size_t ws_bytes, int save_for_bwd, void* stream);
+
+/* Gradient of sum_b w_b loss_b wrt the effective parameters of RhoCMPS (replaces tf.gradients for
+ * train.py:89 with --mps_model=rho_mps).  grad_dev float32 [4*D*D + D + 2] packed:
+ *   gR (complex64 [D,D]) | gfreqs [D] | grho0 (complex64 [D,D]) | gA [1] | sum_b w_b*loss_b [1] */
+int amps_rho_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T,
+                      const float* w_dev, void* ws_dev, size_t ws_bytes, float* grad_dev, void* stream);
+size_t amps_rho_grad_count(int D); /* = 4*D*D + D + 2 */
 
 /* RhoCMPS.rho_evolve_with_data (model.py:76-85): traj_dev complex64 [B, T-1, D, D]. */
 int amps_rho_evolve(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T,

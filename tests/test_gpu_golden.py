@@ -66,6 +66,6 @@ def test_rho_golden(cuda, lib):
     g = load("rho_testhp_d7")
     raw = {k[4:]: g[k] for k in g if k.startswith("raw_")}
     m = _model(ref_test_hparams(), raw, cuda, cls=RhoCMPS)
-    assert rel(m.loss_per_clip(g["data"]).cpu().numpy(), g["loss_f64"]) <= 1e-4
+    assert rel(m.loss_per_clip(g["data"]).detach().cpu().numpy(), g["loss_f64"]) <= 1e-4
     tr = m.rho_evolve_with_data(g["data"]).cpu().numpy()
     assert relc(tr[:, -1], g["traj_last"]) <= 1e-4

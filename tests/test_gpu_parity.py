@@ -123,7 +123,7 @@ def test_rho_loss_and_traj(cuda, lib, D, B, T, over):
     o = RhoCMPSOracle(ohp, raw, mode="f64")
     model = RhoCMPS(php, device=cuda)
     set_raw(model, raw)
-    got = model.loss_per_clip(data).cpu().numpy()
+    got = model.loss_per_clip(data).detach().cpu().numpy()
     ref = o.loss_per_clip(data).detach().numpy()
     assert rel(got, ref) <= LOSS_TOL
     tr = model.rho_evolve_with_data(data).cpu().numpy()
@@ -146,3 +146,25 @@ def test_rho_sampling(cuda, lib):
     np.testing.assert_allclose(np.trace(tr, axis1=-2, axis2=-1).real, 1.0, rtol=1e-4)  # tests/test_model.py:59-67
     pu = model.purity(5, 256, noise=noise).cpu().numpy()
     assert rel(pu, o.purity_from_noise(noise).detach().numpy()) <= 1e-4
+
+
+@pytest.mark.parametrize("D,B,T,over", [(7, 8, 256, dict(h_reg=2 / (np.pi * 16000) ** 2, r_reg=2 / (np.pi * 16000))),
+                                        (4, 3, 150, dict(sigma=0.3, A=3.0)), (8, 2, 700, dict()),
+                                        (16, 2, 120, dict())])
+def test_rho_grads_raw(cuda, lib, D, B, T, over):
+    """Gradient of the regularised rho loss wrt the raw variables (train.py:49-60 with rho_mps)."""
+    ohp, php = hp_pair(bond_dim=D, minibatch_size=B, **over)
+    raw = random_raw_params(ohp, np.random.default_rng(11), rho=True)
+    data = damped_sine(B, T, ohp.delta_t, np.random.default_rng(12))
+    if D == 4:
+        data = data * np.float32(0.2)
+    o = RhoCMPSOracle(ohp, raw, mode="f64")
+    gref = grads_of(o, total_loss(o, data))
+    m = RhoCMPS(php, device=cuda)
+    set_raw(m, raw)
+    obj = m.loss_fn(data) + regulariser(m)
+    names = ["A", "Rx", "Ry", "freqs_raw", "Wx", "Wy"]
+    gs = torch.autograd.grad(obj, [getattr(m, n) for n in names])
+    for n, g in zip(names, gs):
+        r = gref["freqs" if n == "freqs_raw" else n]
+        assert rel(g.cpu().numpy(), r) <= GRAD_TOL, (n, rel(g.cpu().numpy(), r))
