@@ -1,0 +1,101 @@
+"""Command-line trainer with the flags of the reference's ``train.py`` (train.py:18-33, 36-94):
+
+    python -m audio_mps_b200.train_cli --mps_model=psi_mps --dataset=damped_sine \\
+        --sample_duration=65536 --hparams=bond_dim=32,minibatch_size=64 --logdir=/tmp/amps --steps=100
+
+Launch under ``torchrun`` for batch data parallelism (one process per GPU; the batch is sharded and the
+packed kernel gradient is all-reduced once per step).  Scalars that the reference sends to TensorBoard
+(train.py:62-72) are written as JSON lines to ``{logdir}/scalars.jsonl``; a checkpoint
+(``model.pt``: raw variables under the reference's names, Adam state, global_step) is written every
+``--save_checkpoint_secs`` (60 s in the reference, train.py:93) and restored on restart.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import HParams, PsiCMPS, RhoCMPS, default_hparams, get_audio
+from .train import Trainer, regulariser, shard_bounds
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--mps_model", default="psi_mps", choices=["rho_mps", "psi_mps"])                # train.py:18
+    ap.add_argument("--dataset", default="damped_sine", choices=["damped_sine", "guitar", "organ", "nsynth"])
+    ap.add_argument("--sample_duration", type=int, default=2 ** 16)                                  # train.py:27
+    ap.add_argument("--sample_rate", type=int, default=16000)
+    ap.add_argument("--num_samples", type=int, default=3)
+    ap.add_argument("--hparams", default="")
+    ap.add_argument("--datadir", default="./data")
+    ap.add_argument("--logdir", default="../logging/audio_mps")
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--save_checkpoint_secs", type=float, default=60.0)
+    ap.add_argument("--seed", type=int, default=0)
+    args = ap.parse_args(argv)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    hp = default_hparams(args.sample_rate)
+    hp.parse(args.hparams)                                                                           # train.py:44
+    cls = RhoCMPS if args.mps_model == "rho_mps" else PsiCMPS
+    model = cls(hp, device=dev, seed=args.seed)                     # same seed on every rank: replicas
+    trainer = Trainer(model)
+    logdir = os.path.join(args.logdir, args.dataset, f"{hp.bond_dim}_{hp.delta_t}_{hp.minibatch_size}")  # train.py:94
+    ckpt = os.path.join(logdir, "model.pt")
+    if rank == 0:
+        os.makedirs(logdir, exist_ok=True)
+    if os.path.exists(ckpt):                                        # MonitoredTrainingSession-style restore
+        trainer.load_state_dict(torch.load(ckpt, map_location=dev))
+    rng = np.random.default_rng(args.seed + 1)
+    source = get_audio(args.datadir, args.dataset, hp, sample_duration=args.sample_duration, rng=rng)
+    gb = hp.minibatch_size
+    lo, hi = shard_bounds(gb, rank, world)
+    last_save = time.time()
+    log = open(os.path.join(logdir, "scalars.jsonl"), "a") if rank == 0 else None
+    for _ in range(args.steps):
+        batch = source if isinstance(source, np.ndarray) else next(source)
+        if isinstance(source, np.ndarray):                          # a fresh random-onset batch per step
+            source = get_audio(args.datadir, args.dataset, hp, sample_duration=args.sample_duration, rng=rng)
+        model_loss = float(trainer.step(batch[lo:hi], global_batch=batch.shape[0]))
+        if rank == 0:
+            with torch.no_grad():
+                R, f = model.R, model.freqs
+                h_l2 = float(torch.sum(f * f))
+                r_l2 = float(torch.sum(torch.conj(R) * R).real)
+                rec = {"step": trainer.global_step, "model_loss": model_loss,
+                       "total_loss": model_loss + hp.h_reg * h_l2 + hp.r_reg * r_l2,
+                       "A": float(model.A), "sigma": float(model.sigma),
+                       "h_l2norm": math.sqrt(h_l2), "r_l2norm": math.sqrt(r_l2),
+                       "gr_decay_time": 1.0 / (2 * math.pi * hp.sigma ** 2 * r_l2 / hp.bond_dim)}   # train.py:66-67
+            log.write(json.dumps(rec) + "\n")
+            log.flush()
+            if time.time() - last_save >= args.save_checkpoint_secs:
+                torch.save(trainer.state_dict(), ckpt)
+                last_save = time.time()
+    if rank == 0:
+        torch.save(trainer.state_dict(), ckpt)
+        if args.num_samples:
+            w = model.sample(args.num_samples, args.sample_duration)                                 # train.py:83
+            np.save(os.path.join(logdir, "samples.npy"), w.cpu().numpy())
+        log.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

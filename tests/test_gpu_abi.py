@@ -117,3 +117,23 @@ def test_full_length_properties(cuda, lib):
     assert tr.shape == (2, T - 1, D)
     n = torch.linalg.vector_norm(tr, dim=-1)
     assert float((n - 1).abs().max()) <= 1e-5                       # tests/test_model.py:115-122
+
+
+def test_train_cli_trains_and_resumes(cuda, lib, tmp_path):
+    """train.py's flow end to end: flags, hparams override, Adam steps, checkpoint + restore, samples."""
+    import json
+    from audio_mps_b200 import train_cli
+    argv = ["--dataset=damped_sine", "--sample_duration=512", "--hparams=bond_dim=8,minibatch_size=4",
+            f"--logdir={tmp_path}", "--steps=6", "--num_samples=2", "--save_checkpoint_secs=0"]
+    train_cli.main(argv)
+    logdir = tmp_path / "damped_sine" / f"8_{1/16000}_4"
+    recs = [json.loads(l) for l in open(logdir / "scalars.jsonl")]
+    assert [r["step"] for r in recs] == [1, 2, 3, 4, 5, 6]
+    assert all(np.isfinite(r["total_loss"]) for r in recs)
+    assert np.load(logdir / "samples.npy").shape == (2, 512)
+    train_cli.main(argv[:4] + ["--steps=2", "--num_samples=0"])          # resumes from model.pt
+    recs = [json.loads(l) for l in open(logdir / "scalars.jsonl")]
+    assert recs[-1]["step"] == 8
+    for mdl in ("rho_mps",):
+        train_cli.main(["--mps_model=" + mdl, "--sample_duration=128", "--hparams=bond_dim=4,minibatch_size=2",
+                        f"--logdir={tmp_path}/rho", "--steps=3", "--num_samples=0"])
