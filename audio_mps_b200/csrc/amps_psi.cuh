@@ -1117,8 +1117,8 @@ __global__ void __launch_bounds__(DP* NQ)
     for (int kk = 0; kk < len; ++kk) {
       float2 a, y;
       matvec2<DP, NQ>(Nr, Rr, sm.xs[cur], jq, a, y);
-      a = group_sum<NQ>(a);
-      y = group_sum<NQ>(y);
+      a = group_sum_fast<NQ>(a);
+      y = group_sum_fast<NQ>(y);
       const float2 xi = sm.xs[cur][i];
       // <x, R x> and |x|^2 over rows: values are replicated over the NQ lanes of a group
       float e = fmaf(xi.x, y.x, xi.y * y.y);
