@@ -69,3 +69,31 @@ def test_rho_golden(cuda, lib):
     assert rel(m.loss_per_clip(g["data"]).detach().cpu().numpy(), g["loss_f64"]) <= 1e-4
     tr = m.rho_evolve_with_data(g["data"]).cpu().numpy()
     assert relc(tr[:, -1], g["traj_last"]) <= 1e-4
+
+
+def test_psi_c1_full_size_golden(cuda, lib):
+    """BASELINE config[1] at FULL size (D=32, 64 clips x 64000 samples) against the float64 run of the
+    independent C restatement (oracle/mint_golden_c1.py): per-clip loss 1e-4, gradients wrt the
+    effective parameters 1e-3 (north_star tolerances)."""
+    from audio_mps_b200.model import _PsiLossFn
+    from oracle.cmps_oracle import HP, damped_sine, random_raw_params
+    g = load("psi_c1_full")
+    D, B, T, seed = int(g["D"]), int(g["B"]), int(g["T"]), int(g["seed"])
+    hp = HP(bond_dim=D, minibatch_size=B)
+    raw = random_raw_params(hp, np.random.default_rng(seed))
+    data = damped_sine(B, T, hp.delta_t, np.random.default_rng(seed + 1))
+    assert abs(np.abs(data.astype(np.float64)).sum() - float(g["data_checksum"])) <= 1e-9 * float(g["data_checksum"])
+    m = _model(hp, raw, cuda)
+    assert relc(m.R.detach().cpu().numpy(), g["R_eff"]) <= 1e-6
+    R = torch.view_as_real(m.R.detach()).clone().requires_grad_()
+    f = m.freqs.detach().clone().requires_grad_()
+    p0 = torch.view_as_real(m.psi_0.detach()).clone().requires_grad_()
+    A = m.A.detach().clone().requires_grad_()
+    x = torch.as_tensor(data, device=cuda)
+    lpc = _PsiLossFn.apply(R, f, p0, A, x, m)
+    assert rel(lpc.detach().cpu().numpy(), g["loss_f64"]) <= 1e-4
+    gR, gf, gp, gA = torch.autograd.grad(lpc.mean(), [R, f, p0, A])
+    assert relc(torch.view_as_complex(gR).cpu().numpy(), g["geff_R"]) <= 1e-3
+    assert rel(gf.cpu().numpy(), g["geff_f"]) <= 1e-3
+    assert relc(torch.view_as_complex(gp).cpu().numpy(), g["geff_psi0"]) <= 1e-3
+    assert rel(gA.cpu().numpy(), g["geff_A"]) <= 1e-3
