@@ -61,9 +61,11 @@ SYMBOLS = {
                                     C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "amps_psi_loss_bwd": (C.c_int, [C.c_void_p, C.POINTER(AmpsParams), C.c_void_p, C.c_int, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
-    "amps_psi_scan_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "amps_psi_scan_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "amps_psi_loss_fwd_scan": (C.c_int, [C.c_void_p, C.POINTER(AmpsParams), C.c_void_p, C.c_int, C.c_int,
-                                         C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+                                         C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "amps_psi_loss_bwd_scan": (C.c_int, [C.c_void_p, C.POINTER(AmpsParams), C.c_void_p, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "amps_psi_sample": (C.c_int, [C.c_void_p, C.POINTER(AmpsParams), C.c_void_p, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p]),
     "amps_psi_evolve": (C.c_int, [C.c_void_p, C.POINTER(AmpsParams), C.c_void_p, C.c_int, C.c_int,

@@ -494,7 +494,8 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
           (const float2*)(ws + L.matN), (const float2*)(ws + L.matRH), (const float2*)(ws + L.matS),
           (const float2*)(ws + L.qtab), ctx->ttab, x_dev, T, p->A, w_dev,
           (const float2*)(ws + L.traj), (const float*)(ws + L.scales), nchunks,
-          (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0), (double*)(ws + L.gAdir));
+          (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0), (double*)(ws + L.gAdir),
+          (const float2*)nullptr, 0, 0);
     }
     PROF_END(ctx, 1, st);
     LAUNCH_CHECK(ctx, "psi_bwd_kernel");
@@ -516,18 +517,22 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
   return AMPS_OK;
 }
 
-// ---- parallel-in-time forward (tcgen05 operator scan), D <= 64 -------------------------------
+// ---- parallel-in-time loss / gradient (tcgen05 operator scan), D <= 64 -------------------------
 namespace {
+constexpr int kScanCtas = 148;   // virtual clips aim at one CTA per B200 SM (fixed: the workspace
+                                 // size must not depend on the context)
 struct ScanWs {
   PsiWs base;
-  size_t ops, ystart, lossv, total;
+  size_t ops, ystart, lossv, rnv;
+  size_t traj, scales, G, gf, lam0, gAdir, lamend, wv, Gtot, gftot, lam0tot;
+  size_t total;
   int nvc, m_steps;
 };
-ScanWs scan_ws_layout(int B, int T, int num_sms) {
+ScanWs scan_ws_layout(int B, int T, bool save) {
   ScanWs w{};
   w.base = psi_ws_layout(64, B, T - 1, T, false);
   const int nsteps = T - 1;
-  int nvc = B > 0 ? (num_sms + B - 1) / B : 1;               // virtual clips per clip: fill the GPU once
+  int nvc = B > 0 ? (kScanCtas + B - 1) / B : 1;              // virtual clips per clip: fill the GPU once
   int m = nsteps > 0 ? (nsteps + nvc - 1) / nvc : CH;
   m = ((m + CH - 1) / CH) * CH;                                // whole 32-step chunks
   nvc = nsteps > 0 ? (nsteps + m - 1) / m : 1;
@@ -539,21 +544,38 @@ ScanWs scan_ws_layout(int B, int T, int num_sms) {
     off += align_up(bytes);
     return o;
   };
-  w.ops = take((size_t)B * nvc * TC_N * TC_N * sizeof(float));
-  w.ystart = take((size_t)B * nvc * TC_D * sizeof(float2));
-  w.lossv = take((size_t)B * nvc * sizeof(double));
+  const size_t nv = (size_t)B * nvc;
+  const size_t mat = (size_t)TC_D * TC_D * sizeof(float2);
+  w.ops = take(nv * TC_N * TC_N * sizeof(float));
+  w.ystart = take(nv * TC_D * sizeof(float2));
+  w.lossv = take(nv * sizeof(double));
+  w.rnv = take(nv * sizeof(float));
+  if (save) {
+    w.traj = take(nv * (size_t)(m + 1) * TC_D * sizeof(float2));
+    w.scales = take(nv * (size_t)(m / CH) * sizeof(float));
+    w.G = take(nv * 3 * mat);
+    w.gf = take(nv * TC_D * sizeof(float));
+    w.lam0 = take(nv * TC_D * sizeof(float2));
+    w.gAdir = take(nv * sizeof(double));
+    w.lamend = take(nv * TC_D * sizeof(float2));
+    w.wv = take(nv * sizeof(float));
+    w.Gtot = take(3 * mat);
+    w.gftot = take((size_t)TC_D * sizeof(float));
+    w.lam0tot = take((size_t)TC_D * sizeof(float2));
+  }
   w.total = off;
   return w;
 }
 }  // namespace
 
-size_t amps_psi_scan_workspace_bytes(int D, int B, int T) {
+size_t amps_psi_scan_workspace_bytes(int D, int B, int T, int save_for_bwd) {
   if (D <= 0 || D > 64 || B <= 0 || T < 1) return 0;
-  return scan_ws_layout(B, T, 148).total + (size_t)B * 160 * (TC_N * TC_N * 4 + TC_D * 8 + 8);
+  return scan_ws_layout(B, T, save_for_bwd != 0).total;
 }
 
 int amps_psi_loss_fwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T,
-                           float* loss_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+                           float* loss_dev, void* ws_dev, size_t ws_bytes, int save_for_bwd,
+                           void* stream) {
   int rc = check_common(ctx, p);
   if (rc) return rc;
   if (!p->psi0_dev) return fail(ctx, AMPS_E_INVALID, "psi0_dev is NULL");
@@ -561,7 +583,8 @@ int amps_psi_loss_fwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
   if (B == 0) return AMPS_OK;
   if (!x_dev || !loss_dev || !ws_dev) return fail(ctx, AMPS_E_INVALID, "NULL buffer");
   if (p->D > 64) return fail(ctx, AMPS_E_UNSUPPORTED, "the tensor-core scan supports D <= 64 (got %d)", p->D);
-  const ScanWs L = scan_ws_layout(B, T, ctx->num_sms);
+  const bool save = save_for_bwd != 0;
+  const ScanWs L = scan_ws_layout(B, T, save);
   if (ws_bytes < L.total)
     return fail(ctx, AMPS_E_WORKSPACE, "workspace %zu < required %zu bytes", ws_bytes, L.total);
   cudaStream_t st = (cudaStream_t)stream;
@@ -584,7 +607,7 @@ int amps_psi_loss_fwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
     const size_t bsm = (size_t)(2 * TC_N * TC_N + 3 * TC_N + 8) * sizeof(float);
     CUDA_TRY(ctx, cudaFuncSetAttribute(psi_scan_boundary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
     psi_scan_boundary_kernel<<<B, 256, bsm, st>>>((const float*)(ws + L.ops), (const float2*)(ws + L.base.psi0p),
-                                                  L.nvc, (float2*)(ws + L.ystart));
+                                                  L.nvc, (float2*)(ws + L.ystart), (float*)(ws + L.rnv));
   }
   LAUNCH_CHECK(ctx, "psi_scan_boundary_kernel");
   {
@@ -595,7 +618,8 @@ int amps_psi_loss_fwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
     kern<<<nv, 64 * 8, smem, st>>>((const float2*)(ws + L.base.matN), (const float2*)(ws + L.base.matR),
                                    (const float2*)(ws + L.base.matS), (const float2*)(ws + L.base.qtab),
                                    (const float2*)(ws + L.base.psi0p), x_dev, T, p->A, (float*)nullptr,
-                                   (double*)(ws + L.lossv), (float2*)nullptr, (float*)nullptr, 0,
+                                   (double*)(ws + L.lossv), save ? (float2*)(ws + L.traj) : (float2*)nullptr,
+                                   save ? (float*)(ws + L.scales) : (float*)nullptr, 0,
                                    (const float2*)(ws + L.ystart), L.nvc, L.m_steps);
     PROF_END(ctx, 0, st);
     LAUNCH_CHECK(ctx, "psi_fwd_uni_kernel<virtual clips>");
@@ -603,6 +627,71 @@ int amps_psi_loss_fwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
   psi_scan_sum_kernel<<<(B + 127) / 128, 128, 0, st>>>((const double*)(ws + L.lossv), B, L.nvc, loss_dev,
                                                        (double*)(ws + L.base.lossd));
   LAUNCH_CHECK(ctx, "psi_scan_sum_kernel");
+  return AMPS_OK;
+}
+
+int amps_psi_loss_bwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T,
+                           const float* w_dev, void* ws_dev, size_t ws_bytes, float* grad_dev,
+                           void* stream) {
+  int rc = check_common(ctx, p);
+  if (rc) return rc;
+  if (B < 0 || T < 1) return fail(ctx, AMPS_E_INVALID, "bad shape B=%d T=%d", B, T);
+  if (!grad_dev) return fail(ctx, AMPS_E_INVALID, "grad_dev is NULL");
+  if (p->D > 64) return fail(ctx, AMPS_E_UNSUPPORTED, "the tensor-core scan supports D <= 64 (got %d)", p->D);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t ng = amps_psi_grad_count(p->D);
+  if (B == 0) {
+    CUDA_TRY(ctx, cudaMemsetAsync(grad_dev, 0, ng * sizeof(float), st));
+    return AMPS_OK;
+  }
+  if (!x_dev || !w_dev || !ws_dev) return fail(ctx, AMPS_E_INVALID, "NULL buffer");
+  const ScanWs L = scan_ws_layout(B, T, true);
+  if (ws_bytes < L.total)
+    return fail(ctx, AMPS_E_WORKSPACE, "workspace %zu < required %zu bytes", ws_bytes, L.total);
+  if (!ctx->ttab || ctx->ttab_n < T) return fail(ctx, AMPS_E_STATE, "backward without a saving forward");
+  char* ws = (char*)ws_dev;
+  const int DP = 64;
+  const int nv = B * L.nvc;
+  const double cprime = -p->delta_t * (double)p->sigma * (double)p->sigma / 2.0;
+  psi_scan_expand_w_kernel<<<(nv + 127) / 128, 128, 0, st>>>(w_dev, B, L.nvc, (float*)(ws + L.wv));
+  LAUNCH_CHECK(ctx, "psi_scan_expand_w_kernel");
+  auto kern = psi_bwd_uni_kernel<64, 8, true>;
+  const size_t smem = sizeof(BwdSmemUni<64>);
+  CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto adjoint_pass = [&](const float2* lam_end) {
+    kern<<<nv, 64 * 8, smem, st>>>((const float2*)(ws + L.base.matN), (const float2*)(ws + L.base.matRH),
+                                   (const float2*)(ws + L.base.matS), (const float2*)(ws + L.base.qtab),
+                                   (const float*)ctx->ttab, x_dev, T, p->A, w_dev,
+                                   (const float2*)(ws + L.traj), (const float*)(ws + L.scales), 0,
+                                   (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0),
+                                   (double*)(ws + L.gAdir), lam_end, L.nvc, L.m_steps);
+  };
+  PROF_BEGIN(ctx, 1, st);
+  adjoint_pass(nullptr);                                   // d_j: chunk adjoints with a zero end condition
+  LAUNCH_CHECK(ctx, "psi_bwd_uni_kernel<virtual clips, pass 1>");
+  {
+    const size_t bsm = (size_t)(2 * TC_N * TC_N + TC_N) * sizeof(float);
+    CUDA_TRY(ctx, cudaFuncSetAttribute(psi_scan_boundary_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+    psi_scan_boundary_bwd_kernel<<<B, 256, bsm, st>>>((const float*)(ws + L.ops), (const float*)(ws + L.rnv),
+                                                      (const float2*)(ws + L.lam0), L.nvc,
+                                                      (float2*)(ws + L.lamend));
+    LAUNCH_CHECK(ctx, "psi_scan_boundary_bwd_kernel");
+  }
+  adjoint_pass((const float2*)(ws + L.lamend));            // true end conditions: tiles, g_f, g_A, Lam_0
+  PROF_END(ctx, 1, st);
+  LAUNCH_CHECK(ctx, "psi_bwd_uni_kernel<virtual clips, pass 2>");
+  {
+    const int total = 3 * DP * DP + 2 * DP;
+    psi_reduce_clips_kernel<<<(total + 127) / 128, 128, 0, st>>>(
+        (const float2*)(ws + L.G), (const float*)(ws + L.gf), (const float2*)(ws + L.lam0), nv, DP,
+        (float2*)(ws + L.Gtot), (float*)(ws + L.gftot), (float2*)(ws + L.lam0tot), L.nvc);
+    LAUNCH_CHECK(ctx, "psi_reduce_clips_kernel");
+    psi_grad_finalize_kernel<<<1, 256, 0, st>>>(
+        (const float2*)(ws + L.Gtot), (const float*)(ws + L.gftot), (const float2*)(ws + L.lam0tot),
+        (const double*)(ws + L.gAdir), (const double*)(ws + L.lossv), (const float*)(ws + L.wv), nv,
+        (const float2*)(ws + L.base.matR), p->D, DP, cprime, p->A, grad_dev);
+    LAUNCH_CHECK(ctx, "psi_grad_finalize_kernel");
+  }
   return AMPS_OK;
 }
 

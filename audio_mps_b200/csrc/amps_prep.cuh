@@ -82,7 +82,7 @@ __global__ void prep_qtab_kernel(const float* __restrict__ freqs, int D, int DP,
 __global__ void psi_reduce_clips_kernel(const float2* __restrict__ G, const float* __restrict__ gf,
                                         const float2* __restrict__ lam0, int B, int DP,
                                         float2* __restrict__ Gtot, float* __restrict__ gftot,
-                                        float2* __restrict__ lam0tot) {
+                                        float2* __restrict__ lam0tot, int lam_step = 1) {
   const int nG = 3 * DP * DP;
   const int total = nG + 2 * DP;
   for (int e = threadIdx.x + blockIdx.x * blockDim.x; e < total; e += blockDim.x * gridDim.x) {
@@ -102,7 +102,7 @@ __global__ void psi_reduce_clips_kernel(const float2* __restrict__ G, const floa
     } else {
       const int c = e - nG - DP;
       double sx = 0.0, sy = 0.0;
-      for (int b = 0; b < B; ++b) {
+      for (int b = 0; b < B; b += lam_step) {   // virtual clips: only a clip's first chunk starts from psi_0
         const float2 v = lam0[(size_t)b * DP + c];
         sx += v.x;
         sy += v.y;

@@ -591,6 +591,8 @@ __global__ void __launch_bounds__(DP* NQ)
   const float* xb = x + (size_t)b * T;
   const float2* qtab = qtab_;
   const float2* psi0p = psi0p_;
+  size_t tstride = T;        // trajectory rows / rescale factors per (virtual) clip
+  int sstride = nchunks;
   if (VIRT) {
     const int clip = b / nvc, kbeg = (b % nvc) * m_steps;
     nsteps = max(0, min(m_steps, T - 1 - kbeg));
@@ -598,6 +600,8 @@ __global__ void __launch_bounds__(DP* NQ)
     qtab = qtab_ + (size_t)kbeg * DP;
     psi0p = psi0v + (size_t)b * DP;
     nchunks = (nsteps + CH - 1) / CH;
+    tstride = m_steps + 1;
+    sstride = m_steps / CH;
   }
 
   float2 Nr[CPT], Rr[CPT], Sr[CPT];
@@ -609,7 +613,7 @@ __global__ void __launch_bounds__(DP* NQ)
     const float2 p = psi0p[t];
     sm.xs[0][t] = p;
     sm.ns[0][0][t] = cabs2(p);
-    if (traj) traj[(size_t)b * T * DP + t] = p;
+    if (traj) traj[(size_t)b * tstride * DP + t] = p;
   }
 
   auto issue_loads = [&](int c, int buf) {
@@ -762,11 +766,11 @@ __global__ void __launch_bounds__(DP* NQ)
       sm.xs[0][t] = v;
       sm.ns[buf ^ 1][0][t] = cabs2(v);
     }
-    if (t == 0 && scales) scales[(size_t)b * nchunks + c] = sc;
+    if (t == 0 && scales) scales[(size_t)b * sstride + c] = sc;
     if (traj) {
       __syncthreads();  // (B) scaled x_{k0+len} visible
       const float4* src = reinterpret_cast<const float4*>(&sm.xs[1][0]);
-      float4* dst = reinterpret_cast<float4*>(traj + ((size_t)b * T + k0 + 1) * DP);
+      float4* dst = reinterpret_cast<float4*>(traj + ((size_t)b * tstride + k0 + 1) * DP);
       for (int idx = t; idx < len * DP / 2; idx += NT) dst[idx] = src[idx];
     }
   }
@@ -794,15 +798,19 @@ __global__ void __launch_bounds__(DP* NQ)
 // Per loop iteration kk of chunk c: chain mat-vec of step kk (critical path) with, as filler, the
 // rank-1 tile updates of step kk and the S x' mat-vec of step kk of chunk c-1.
 // -------------------------------------------------------------------------------------------
-template <int DP, int NQ>
+// VIRT: virtual-clip mode of the parallel-in-time scan: block b runs the adjoint of time chunk
+// (b % nvc) of clip (b / nvc) over the trajectory the VIRT forward stored for it, starting from the
+// adjoint lam_end[b] of the chunk's (normalised) end state (zero when lam_end is NULL).
+template <int DP, int NQ, bool VIRT = false>
 __global__ void __launch_bounds__(DP* NQ)
     psi_bwd_uni_kernel(const float2* __restrict__ matN, const float2* __restrict__ matRH,
-                   const float2* __restrict__ matS, const float2* __restrict__ qtab,
-                   const float* __restrict__ ttab, const float* __restrict__ x, int T, float A,
+                   const float2* __restrict__ matS, const float2* __restrict__ qtab_,
+                   const float* __restrict__ ttab_, const float* __restrict__ x, int T, float A,
                    const float* __restrict__ w, const float2* __restrict__ traj,
-                   const float* __restrict__ scales, int nchunks, float2* __restrict__ Gout,
+                   const float* __restrict__ scales_, int nchunks, float2* __restrict__ Gout,
                    float* __restrict__ gfout, float2* __restrict__ lam0out,
-                   double* __restrict__ gAdir) {
+                   double* __restrict__ gAdir, const float2* __restrict__ lam_end, int nvc,
+                   int m_steps) {
   using M = Map<DP, NQ>;
   constexpr int NT = M::NT;
   constexpr int CPT = M::CPT;
@@ -813,10 +821,26 @@ __global__ void __launch_bounds__(DP* NQ)
 
   const int t = threadIdx.x, i = t / NQ, jq = t % NQ, lane = t & 31, warp = t >> 5;
   const int b = blockIdx.x;
-  const int nsteps = T - 1;
+  int nsteps = T - 1;
   const float* xb = x + (size_t)b * T;
   const float2* trb = traj + (size_t)b * T * DP;
-  const float wb = w[b];
+  const float2* qtab = qtab_;
+  const float* ttab = ttab_;
+  const float* scales = scales_ + (size_t)b * nchunks;
+  float wb;
+  if (VIRT) {
+    const int clip = b / nvc, kbeg = (b % nvc) * m_steps;
+    nsteps = max(0, min(m_steps, T - 1 - kbeg));
+    xb = x + (size_t)clip * T + kbeg;
+    trb = traj + (size_t)b * (m_steps + 1) * DP;
+    qtab = qtab_ + (size_t)kbeg * DP;
+    ttab = ttab_ + kbeg;
+    scales = scales_ + (size_t)b * (m_steps / CH);
+    nchunks = (nsteps + CH - 1) / CH;
+    wb = w[clip];
+  } else {
+    wb = w[b];
+  }
 
   float2 Nr[CPT], Hr[CPT], Sr[CPT];
   load_slice<DP, NQ>(Nr, matN, i, jq);   // N is Hermitian: N^dag mu uses the same slices
@@ -843,7 +867,7 @@ __global__ void __launch_bounds__(DP* NQ)
       cp_async4(&sm.wav[lb][idx], xb + k0 + idx);
       cp_async4(&sm.tt[lb][idx], ttab + k0 + idx);
     }
-    if (t == 0) cp_async4(&sm.scs[lb][0], scales + (size_t)b * nchunks + c);
+    if (t == 0) cp_async4(&sm.scs[lb][0], scales + c);
   };
 
   // P0 + P1 of chunk c: s, inc, dt; x'_k = conj(q_k) x_{k+1} / c_k ; |x_k|^2
@@ -908,6 +932,7 @@ __global__ void __launch_bounds__(DP* NQ)
   };
 
   float2 lam = make_float2(0.f, 0.f);  // adjoint of x_{k+1}, replicated over the NQ lanes
+  if (VIRT) if (lam_end) lam = lam_end[(size_t)b * DP + i];
   float gf = 0.f;
 
   if (nchunks > 0) {

@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(TC_THREADS)
 // while the current mat-vec runs.
 __global__ void __launch_bounds__(256)
     psi_scan_boundary_kernel(const float* __restrict__ opsT, const float2* __restrict__ psi0p, int nvc,
-                             float2* __restrict__ ystart) {
+                             float2* __restrict__ ystart, float* __restrict__ rnv) {
   extern __shared__ __align__(16) unsigned char bsm_raw[];
   float* pt = reinterpret_cast<float*>(bsm_raw);          // [2][128][128]
   float* y = pt + 2 * TC_N * TC_N;                        // [128]
@@ -305,6 +305,7 @@ __global__ void __launch_bounds__(256)
     cp_async_wait<1>();
     __syncthreads();
     if (t < TC_D) ystart[((size_t)b * nvc + j) * TC_D + t] = make_float2(y[t], y[t + TC_D]);
+    if (t == 0 && rnv) rnv[(size_t)b * nvc + j] = rn;     // 1 / |C_{j-1} y_{j-1}|  (adjoint pass)
     // y_new[n] = sum_m P^T[m][n] y[m], the m range split over the two thread halves
     const float* PT = pt + (j & 1) * TC_N * TC_N;
     float acc0 = 0.f, acc1 = 0.f;
@@ -319,6 +320,66 @@ __global__ void __launch_bounds__(256)
     __syncthreads();
   }
   cp_async_wait<0>();
+}
+
+// Adjoint of the boundary pass.  With F_j = the loss of chunks j.. as a (scale-invariant) function of
+// the start state y_j of chunk j, y_{j+1} = C_j y_j / |C_j y_j|:
+//     Lam_j = d_j + C_j^dag Lam_{j+1} / |C_j y_j|,        Lam_nvc = 0,
+// d_j = the adjoint of y_j from chunk j's own loss terms (virtual-clip backward run with a zero end
+// adjoint).  Emits lamend[j] = Lam_{j+1}, the end adjoint the second virtual-clip backward starts
+// chunk j from.  grid = B, block = 256 (8 warps x 16 rows of P^T, lanes across the columns).
+__global__ void __launch_bounds__(256)
+    psi_scan_boundary_bwd_kernel(const float* __restrict__ opsT, const float* __restrict__ rnv,
+                                 const float2* __restrict__ dvec, int nvc, float2* __restrict__ lamend) {
+  extern __shared__ __align__(16) unsigned char bsm_raw[];
+  float* pt = reinterpret_cast<float*>(bsm_raw);          // [2][128][128]
+  float* v = pt + 2 * TC_N * TC_N;                        // [128]  Lam_{j+1}, real form (Re | Im)
+  const int t = threadIdx.x, b = blockIdx.x, lane = t & 31, warp = t >> 5;
+  auto issue = [&](int j) {
+    const float* src = opsT + ((size_t)b * nvc + j) * TC_N * TC_N;
+    float* dst = pt + (j & 1) * TC_N * TC_N;
+    for (int idx = t; idx < TC_N * TC_N / 4; idx += 256) cp_async16(dst + 4 * idx, src + 4 * idx);
+  };
+  if (t < TC_N) v[t] = 0.f;
+  if (t < TC_D) lamend[((size_t)b * nvc + nvc - 1) * TC_D + t] = make_float2(0.f, 0.f);
+  if (nvc >= 2) issue(nvc - 1);
+  cp_async_commit();
+  for (int j = nvc - 1; j >= 1; --j) {
+    if (j - 1 >= 1) issue(j - 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();   // operator j landed; v complete
+    const float* PT = pt + (j & 1) * TC_N * TC_N;
+    const float sc = (j + 1 < nvc) ? rnv[(size_t)b * nvc + j + 1] : 0.f;
+    float vr[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) vr[r] = v[lane + 32 * r];
+    float mine = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+      const float* row = PT + (warp * 16 + rr) * TC_N;     // (C^dag lam)[m] = sum_n P^T[m][n] lam[n]
+      float acc = 0.f;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc = fmaf(row[lane + 32 * r], vr[r], acc);
+      acc = warp_sum_f(acc);
+      if (rr == lane) mine = acc;
+    }
+    __syncthreads();   // every read of v done
+    if (lane < 16) {
+      const int m = warp * 16 + lane;
+      const float2 d = dvec[((size_t)b * nvc + j) * TC_D + (m & (TC_D - 1))];
+      v[m] = fmaf(sc, mine, m < TC_D ? d.x : d.y);
+    }
+    __syncthreads();
+    if (t < TC_D) lamend[((size_t)b * nvc + j - 1) * TC_D + t] = make_float2(v[t], v[t + TC_D]);
+  }
+  cp_async_wait<0>();
+}
+
+// per-virtual-clip weights for the shared gradient epilogue: wv[b * nvc + j] = w[b]
+__global__ void psi_scan_expand_w_kernel(const float* __restrict__ w, int B, int nvc, float* __restrict__ wv) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < B * nvc) wv[v] = w[v / nvc];
 }
 
 // per-clip loss = sum over the clip's virtual clips

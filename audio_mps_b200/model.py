@@ -51,7 +51,7 @@ def _as_device_f32(obj, device) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------
 class _PsiLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, R_ri, freqs, psi0_ri, A, x, model):
+    def forward(ctx, R_ri, freqs, psi0_ri, A, x, model, scan=False):
         dev = x.device
         if dev.type != "cuda":
             raise RuntimeError("PsiCMPS scan requires a CUDA device (no CPU fallback)")
@@ -67,21 +67,25 @@ class _PsiLossFn(torch.autograd.Function):
         p = _lib.AmpsParams(D=D, reserved=0, R_dev=R_ri.data_ptr(), freqs_dev=freqs.data_ptr(),
                             psi0_dev=psi0_ri.data_ptr(), rho0_dev=None, A=a_val,
                             sigma=float(model.sigma), delta_t=float(model.delta_t))
-        nbytes = lib.amps_psi_workspace_bytes(D, B, T, 1 if need_grad else 0)
+        # scan=True: the parallel-in-time tensor-core path (small batches, D <= 64)
+        ws_bytes = lib.amps_psi_scan_workspace_bytes if scan else lib.amps_psi_workspace_bytes
+        fwd = lib.amps_psi_loss_fwd_scan if scan else lib.amps_psi_loss_fwd
+        nbytes = ws_bytes(D, B, T, 1 if need_grad else 0)
         if nbytes == 0:
-            raise _lib.AmpsError(-2, f"bond dimension {D} is not supported by the Psi kernels")
+            raise _lib.AmpsError(-2, f"bond dimension {D} is not supported by the Psi "
+                                     f"{'tensor-core scan' if scan else 'kernels'}")
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         loss = torch.empty(B, dtype=torch.float32, device=dev)
-        rc = lib.amps_psi_loss_fwd(h, C.byref(p), _ptr(x), B, T, _ptr(loss), _ptr(ws), nbytes,
-                                   1 if need_grad else 0, _stream(dev))
+        rc = fwd(h, C.byref(p), _ptr(x), B, T, _ptr(loss), _ptr(ws), nbytes,
+                 1 if need_grad else 0, _stream(dev))
         _lib.check(h, rc)
         if need_grad:
-            ctx.keep = (R_ri, freqs, psi0_ri, x, ws, p, h, model)
+            ctx.keep = (R_ri, freqs, psi0_ri, x, ws, p, h, model, scan)
         return loss
 
     @staticmethod
     def backward(ctx, gloss):
-        R_ri, freqs, psi0_ri, x, ws, p, h, model = ctx.keep
+        R_ri, freqs, psi0_ri, x, ws, p, h, model, scan = ctx.keep
         lib = _lib.load()
         dev = x.device
         B, T = x.shape
@@ -89,8 +93,8 @@ class _PsiLossFn(torch.autograd.Function):
         w = gloss.detach().contiguous().float()
         ng = int(lib.amps_psi_grad_count(D))
         packed = torch.empty(ng, dtype=torch.float32, device=dev)
-        rc = lib.amps_psi_loss_bwd(h, C.byref(p), _ptr(x), B, T, _ptr(w), _ptr(ws), ws.numel(),
-                                   _ptr(packed), _stream(dev))
+        bwd = lib.amps_psi_loss_bwd_scan if scan else lib.amps_psi_loss_bwd
+        rc = bwd(h, C.byref(p), _ptr(x), B, T, _ptr(w), _ptr(ws), ws.numel(), _ptr(packed), _stream(dev))
         _lib.check(h, rc)
         dp = getattr(model, "_dp_group", None)
         if dp is not None:
@@ -102,7 +106,7 @@ class _PsiLossFn(torch.autograd.Function):
         gf = packed[2 * D * D: 2 * D * D + D].clone()
         gp = packed[2 * D * D + D: 2 * D * D + 3 * D].clone().view(D, 2)
         gA = packed[2 * D * D + 3 * D].clone()
-        return gR, gf, gp, gA, None, None
+        return gR, gf, gp, gA, None, None, None
 
 
 class _RhoLossFn(torch.autograd.Function):
@@ -314,29 +318,14 @@ class PsiCMPS(CMPS):
         gs = torch.autograd.grad(tot, [p for _, p in self.named_parameters()], allow_unused=True)
         return {self.TF_NAMES.get(n, n): g for n, g in zip(names, gs)}
 
-    @torch.no_grad()
     def loss_per_clip_scan(self, data=None) -> torch.Tensor:
-        """Same values as ``loss_per_clip`` computed with the parallel-in-time tensor-core scan
-        (amps_psi_loss_fwd_scan): for batches far smaller than the SM count, D <= 64, forward only."""
+        """Same values (and gradients) as ``loss_per_clip`` computed with the parallel-in-time
+        tensor-core scan (amps_psi_loss_fwd_scan / amps_psi_loss_bwd_scan): for batches far smaller
+        than the SM count, D <= 64; differentiable."""
         self._require_cuda()
         x = self._batch(data)
-        B, T = x.shape
-        lib, h = _lib.load(), self._ctx()
-        R_ri = torch.view_as_real(self.R).contiguous()
-        f = self.freqs.contiguous()
-        p0 = torch.view_as_real(self.psi_0).contiguous()
-        p = _lib.AmpsParams(D=self.bond_d, reserved=0, R_dev=R_ri.data_ptr(), freqs_dev=f.data_ptr(),
-                            psi0_dev=p0.data_ptr(), rho0_dev=None, A=float(self.A),
-                            sigma=float(self.sigma), delta_t=float(self.delta_t))
-        nbytes = lib.amps_psi_scan_workspace_bytes(self.bond_d, B, T)
-        if nbytes == 0:
-            raise _lib.AmpsError(-2, f"bond dimension {self.bond_d} is not supported by the tensor-core scan")
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-        loss = torch.empty(B, dtype=torch.float32, device=self.device)
-        rc = lib.amps_psi_loss_fwd_scan(h, C.byref(p), _ptr(x), B, T, _ptr(loss), _ptr(ws), nbytes,
-                                        _stream(self.device))
-        _lib.check(h, rc)
-        return loss
+        return _PsiLossFn.apply(torch.view_as_real(self.R), self.freqs,
+                                torch.view_as_real(self.psi_0), self.A, x, self, True)
 
     def sample(self, num_samples, length, temp=1, noise=None, generator=None) -> torch.Tensor:
         """[num_samples, length] cumulative X_t scaled by A (model.py:242-251)."""

@@ -106,15 +106,23 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
                       void* stream);
 size_t amps_psi_grad_count(int D); /* = 2*D*D + 3*D + 2 */
 
-/* Parallel-in-time forward loss for SMALL batches (same result as amps_psi_loss_fwd; D <= 64, zero
- * padded to 64): the clip is cut into ~#SMs/B time chunks whose step operators are composed on the
- * tcgen05 tensor cores (complex DxD as real 2Dx2D, kind::tf32 with a 3-pass hi/lo split, running
- * product in tensor memory), a short sequential pass over the chunk operators gives the chunk start
- * states, and every chunk is then replayed in parallel by the sequential kernel.  8 D^3 instead of
- * 24 D^2 flops per step: use it only when B is far below the SM count.  Forward only. */
-size_t amps_psi_scan_workspace_bytes(int D, int B, int T);
+/* Parallel-in-time loss (and gradient) for SMALL batches (same results as amps_psi_loss_fwd / _bwd;
+ * D <= 64, zero padded to 64): the clip is cut into ~#SMs/B time chunks whose step operators are
+ * composed on the tcgen05 tensor cores (complex DxD as real 2Dx2D, kind::tf32 with a 3-pass hi/lo
+ * split, running product in tensor memory), a short sequential pass over the chunk operators gives
+ * the chunk start states, and every chunk is then replayed in parallel by the sequential kernel as
+ * a "virtual clip".  8 D^3 instead of 24 D^2 flops per step: use it only when B is far below the SM
+ * count.  With save_for_bwd != 0 the replay keeps its trajectories and amps_psi_loss_bwd_scan runs
+ * the adjoint the same way: per-chunk adjoints with a zero end condition, a sequential adjoint pass
+ * over the chunk operators (Lam_j = d_j + C_j^dag Lam_{j+1} / |C_j y_j|), then per-chunk adjoints from
+ * the true end conditions, all chunks in parallel.  grad_dev as for amps_psi_loss_bwd. */
+size_t amps_psi_scan_workspace_bytes(int D, int B, int T, int save_for_bwd);
 int amps_psi_loss_fwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T,
-                           float* loss_dev, void* ws_dev, size_t ws_bytes, void* stream);
+                           float* loss_dev, void* ws_dev, size_t ws_bytes, int save_for_bwd,
+                           void* stream);
+int amps_psi_loss_bwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T,
+                           const float* w_dev, void* ws_dev, size_t ws_bytes, float* grad_dev,
+                           void* stream);
 
 /* PsiCMPS.sample / _psi_and_sample_update (model.py:242-251, 284-291) with the noise tensor
  * supplied by the caller (the reference draws it once, model.py:246).

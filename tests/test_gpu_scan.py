@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from audio_mps_b200 import PsiCMPS
-from oracle.cmps_oracle import PsiCMPSOracle, damped_sine, random_raw_params
+from oracle.cmps_oracle import PsiCMPSOracle, damped_sine, grads_of, random_raw_params
 from tests.util import hp_pair, rel, set_raw
 
 pytestmark = pytest.mark.gpu
@@ -19,7 +19,7 @@ def test_scan_matches_sequential(cuda, lib, D, B, T):
     m = PsiCMPS(php, device=cuda)
     set_raw(m, raw)
     seq = m.loss_per_clip(data).detach().cpu().numpy()
-    scan = m.loss_per_clip_scan(data).cpu().numpy()
+    scan = m.loss_per_clip_scan(data).detach().cpu().numpy()
     assert np.all(np.isfinite(scan))
     assert rel(scan, seq) <= 1e-4, (scan, seq)
 
@@ -32,4 +32,40 @@ def test_scan_matches_oracle(cuda, lib):
     m = PsiCMPS(php, device=cuda)
     set_raw(m, raw)
     ref = PsiCMPSOracle(ohp, raw, mode="f64").loss_per_clip(data).detach().numpy()
-    assert rel(m.loss_per_clip_scan(data).cpu().numpy(), ref) <= 1e-4
+    assert rel(m.loss_per_clip_scan(data).detach().cpu().numpy(), ref) <= 1e-4
+
+
+NAMES = ["A", "Rx", "Ry", "freqs_raw", "psi_x", "psi_y"]
+
+
+@pytest.mark.parametrize("D,B,T", [(64, 1, 6000), (64, 3, 2500), (32, 2, 4000), (7, 1, 1200), (64, 1, 40),
+                                   (16, 5, 999)])
+def test_scan_gradients_match_sequential(cuda, lib, D, B, T):
+    """amps_psi_loss_bwd_scan (chunk adjoints + operator-adjoint boundary pass) against the sequential
+    adjoint kernel on the same inputs, with non-uniform clip weights."""
+    ohp, php = hp_pair(bond_dim=D, minibatch_size=B)
+    raw = random_raw_params(ohp, np.random.default_rng(D + 1))
+    data = damped_sine(B, T, ohp.delta_t, np.random.default_rng(T + 1))
+    m = PsiCMPS(php, device=cuda)
+    set_raw(m, raw)
+    w = torch.linspace(0.5, 1.5, B, device=cuda) / B
+    ps = [getattr(m, n) for n in NAMES]
+    g_seq = torch.autograd.grad((m.loss_per_clip(data) * w).sum(), ps)
+    g_scan = torch.autograd.grad((m.loss_per_clip_scan(data) * w).sum(), ps)
+    for n, a, b in zip(NAMES, g_scan, g_seq):
+        assert torch.isfinite(a).all(), n
+        assert rel(a.cpu().numpy(), b.cpu().numpy()) <= 1e-3, n
+
+
+def test_scan_gradients_match_oracle(cuda, lib):
+    D, B, T = 64, 2, 700
+    ohp, php = hp_pair(bond_dim=D, minibatch_size=B)
+    raw = random_raw_params(ohp, np.random.default_rng(1))
+    data = damped_sine(B, T, ohp.delta_t, np.random.default_rng(2))
+    m = PsiCMPS(php, device=cuda)
+    set_raw(m, raw)
+    o = PsiCMPSOracle(ohp, raw, mode="f64")
+    gref = grads_of(o, o.loss_per_clip(data).mean())
+    gs = torch.autograd.grad(m.loss_per_clip_scan(data).mean(), [getattr(m, n) for n in NAMES])
+    for n, g in zip(NAMES, gs):
+        assert rel(g.cpu().numpy(), gref["freqs" if n == "freqs_raw" else n]) <= 1e-3, n
