@@ -532,7 +532,7 @@ ScanWs scan_ws_layout(int B, int T, bool save) {
   ScanWs w{};
   w.base = psi_ws_layout(64, B, T - 1, T, false);
   const int nsteps = T - 1;
-  int nvc = B > 0 ? (kScanCtas + B - 1) / B : 1;              // virtual clips per clip: fill the GPU once
+  int nvc = B > 0 && B < kScanCtas ? kScanCtas / B : 1;       // virtual clips per clip: at most ONE wave of CTAs
   int m = nsteps > 0 ? (nsteps + nvc - 1) / nvc : CH;
   m = ((m + CH - 1) / CH) * CH;                                // whole 32-step chunks
   nvc = nsteps > 0 ? (nsteps + m - 1) / m : 1;

@@ -295,12 +295,30 @@ class PsiCMPS(CMPS):
         return self._normalize_psi(torch.complex(self.psi_x, self.psi_y))   # model.py:221-222
 
     # ---- public ------------------------------------------------------------------------
-    def loss_per_clip(self, data=None) -> torch.Tensor:
-        """loss_b of the fold, before the reduce_mean (model.py:257-267); differentiable."""
+    #: "auto" | "never" | "always": when ``loss_per_clip`` takes the parallel-in-time tensor-core scan
+    #: instead of the one-chain-per-clip kernels.  Both meet the parity tolerances; "auto" picks the
+    #: scan where it measured faster on B200 (profiles/r1_scan_timings.md): few long clips, D <= 64.
+    time_parallel = "auto"
+
+    def _use_scan(self, B: int, T: int, need_grad: bool) -> bool:
+        if self.time_parallel == "always":
+            return True
+        if self.time_parallel != "auto" or self.bond_d > 64 or T < 4096 or B < 1:
+            return False
+        if self.bond_d > 32:
+            return B <= (16 if need_grad else 8)
+        return B <= 4
+
+    def loss_per_clip(self, data=None, time_parallel: Optional[bool] = None) -> torch.Tensor:
+        """loss_b of the fold, before the reduce_mean (model.py:257-267); differentiable.
+        ``time_parallel``: force (True) or forbid (False) the parallel-in-time scan; None = policy."""
         self._require_cuda()
         x = self._batch(data)
+        if time_parallel is None:
+            need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+            time_parallel = self._use_scan(x.shape[0], x.shape[1], need_grad)
         return _PsiLossFn.apply(torch.view_as_real(self.R), self.freqs,
-                                torch.view_as_real(self.psi_0), self.A, x, self)
+                                torch.view_as_real(self.psi_0), self.A, x, self, bool(time_parallel))
 
     def loss_fn(self, data=None) -> torch.Tensor:
         return self.loss_per_clip(data).mean()                              # model.py:267
@@ -319,13 +337,9 @@ class PsiCMPS(CMPS):
         return {self.TF_NAMES.get(n, n): g for n, g in zip(names, gs)}
 
     def loss_per_clip_scan(self, data=None) -> torch.Tensor:
-        """Same values (and gradients) as ``loss_per_clip`` computed with the parallel-in-time
-        tensor-core scan (amps_psi_loss_fwd_scan / amps_psi_loss_bwd_scan): for batches far smaller
-        than the SM count, D <= 64; differentiable."""
-        self._require_cuda()
-        x = self._batch(data)
-        return _PsiLossFn.apply(torch.view_as_real(self.R), self.freqs,
-                                torch.view_as_real(self.psi_0), self.A, x, self, True)
+        """``loss_per_clip`` forced onto the parallel-in-time tensor-core scan (amps_psi_loss_fwd_scan /
+        amps_psi_loss_bwd_scan): same values and gradients, D <= 64; differentiable."""
+        return self.loss_per_clip(data, time_parallel=True)
 
     def sample(self, num_samples, length, temp=1, noise=None, generator=None) -> torch.Tensor:
         """[num_samples, length] cumulative X_t scaled by A (model.py:242-251)."""

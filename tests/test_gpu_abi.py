@@ -38,7 +38,7 @@ def test_host_entry_point_matches_oracle(cuda, lib):
     assert rel(grad[n:n + D], gf.numpy()) <= 1e-3
     assert relc(grad[n + D:n + 3 * D].reshape(D, 2) @ np.array([1, 1j]), gp.numpy()) <= 1e-3
     assert rel(grad[n + 3 * D], float(gA)) <= 1e-3
-    assert rel(grad[n + 3 * D + 1], float(lpc.mean())) <= 1e-4
+    assert rel(grad[n + 3 * D + 1], float(lpc.detach().mean())) <= 1e-4
 
 
 def test_error_codes(cuda, lib):
@@ -94,6 +94,7 @@ def test_full_length_properties(cuda, lib):
     D, B, T = 32, 6, 64000
     ohp, php = hp_pair(bond_dim=D, minibatch_size=B)
     m = PsiCMPS(php, device=cuda, seed=3)
+    m.time_parallel = "never"      # properties of the one-chain-per-clip kernels (the scan regroups the sums)
     x = torch.from_numpy(damped_sine(B, T, ohp.delta_t, np.random.default_rng(9))).to(cuda)
     l1 = m.loss_per_clip(x)
     perm = torch.tensor([3, 0, 5, 1, 4, 2], device=cuda)

@@ -18,7 +18,7 @@ def test_scan_matches_sequential(cuda, lib, D, B, T):
     data = damped_sine(B, T, ohp.delta_t, np.random.default_rng(T))
     m = PsiCMPS(php, device=cuda)
     set_raw(m, raw)
-    seq = m.loss_per_clip(data).detach().cpu().numpy()
+    seq = m.loss_per_clip(data, time_parallel=False).detach().cpu().numpy()
     scan = m.loss_per_clip_scan(data).detach().cpu().numpy()
     assert np.all(np.isfinite(scan))
     assert rel(scan, seq) <= 1e-4, (scan, seq)
@@ -50,7 +50,7 @@ def test_scan_gradients_match_sequential(cuda, lib, D, B, T):
     set_raw(m, raw)
     w = torch.linspace(0.5, 1.5, B, device=cuda) / B
     ps = [getattr(m, n) for n in NAMES]
-    g_seq = torch.autograd.grad((m.loss_per_clip(data) * w).sum(), ps)
+    g_seq = torch.autograd.grad((m.loss_per_clip(data, time_parallel=False) * w).sum(), ps)
     g_scan = torch.autograd.grad((m.loss_per_clip_scan(data) * w).sum(), ps)
     for n, a, b in zip(NAMES, g_scan, g_seq):
         assert torch.isfinite(a).all(), n
@@ -69,3 +69,17 @@ def test_scan_gradients_match_oracle(cuda, lib):
     gs = torch.autograd.grad(m.loss_per_clip_scan(data).mean(), [getattr(m, n) for n in NAMES])
     for n, g in zip(NAMES, gs):
         assert rel(g.cpu().numpy(), gref["freqs" if n == "freqs_raw" else n]) <= 1e-3, n
+
+
+def test_time_parallel_policy(cuda, lib):
+    """host logic of the "auto" policy: few long clips -> scan; batches that fill the GPU -> chains."""
+    _, php = hp_pair(bond_dim=64, minibatch_size=1)
+    m = PsiCMPS(php, device=cuda)
+    assert m._use_scan(1, 64000, True) and m._use_scan(16, 64000, True)
+    assert not m._use_scan(32, 64000, True) and not m._use_scan(1, 1000, True)
+    assert not m._use_scan(16, 64000, False)
+    m.time_parallel = "never"
+    assert not m._use_scan(1, 64000, True)
+    _, php32 = hp_pair(bond_dim=32, minibatch_size=1)
+    m32 = PsiCMPS(php32, device=cuda)
+    assert m32._use_scan(4, 64000, True) and not m32._use_scan(8, 64000, True)
