@@ -14,6 +14,7 @@
 #include "amps_psi.cuh"
 #include "amps_psi_cluster.cuh"
 #include "amps_rho.cuh"
+#include "amps_psi_c4.cuh"
 #include "amps_scan_tc.cuh"
 
 using namespace amps;
@@ -120,8 +121,11 @@ int padded_dim(int D) {
   if (D <= 16) return 16;
   if (D <= 32) return 32;
   if (D <= 64) return 64;
+  if (D <= 128) return 128;   // row-split 4-CTA cluster kernels (amps_psi_c4.cuh): loss / gradient / trajectory
   return -1;
 }
+// time-chunk length (rescale period) of the kernels serving a padded bond dimension
+int chunk_len_of(int DP) { return DP == 128 ? CH4 : CH; }
 
 template <int V>
 using IC = std::integral_constant<int, V>;
@@ -162,7 +166,8 @@ PsiWs psi_ws_layout(int DP, int B, int nsteps_tab, int T, bool save) {
   w.lossd = take((size_t)(B > 0 ? B : 1) * sizeof(double));
   if (save) {
     const int nsteps = T - 1;
-    const int nchunks = nsteps > 0 ? (nsteps + CH - 1) / CH : 0;
+    const int chl = chunk_len_of(DP);
+    const int nchunks = nsteps > 0 ? (nsteps + chl - 1) / chl : 0;
     w.traj = take((size_t)B * T * DP * sizeof(float2));
     w.scales = take((size_t)B * (nchunks > 0 ? nchunks : 1) * sizeof(float));
     w.G = take((size_t)B * 3 * mat);
@@ -172,8 +177,10 @@ PsiWs psi_ws_layout(int DP, int B, int nsteps_tab, int T, bool save) {
     w.Gtot = take(3 * mat);
     w.gftot = take((size_t)DP * sizeof(float));
     w.lam0tot = take((size_t)DP * sizeof(float2));
-    w.sptraj = take((size_t)B * T * DP * sizeof(float2));   // S x'_k (cluster kernels)
-    w.ev = take((size_t)B * T * sizeof(float2));            // (E_k, |x_k|^2)
+    if (DP <= 32) {   // only the warp-specialised / 2-CTA kernels keep these
+      w.sptraj = take((size_t)B * T * DP * sizeof(float2));   // S x'_k
+      w.ev = take((size_t)B * T * sizeof(float2));            // (E_k, |x_k|^2)
+    }
   }
   w.total = off;
   return w;
@@ -240,6 +247,27 @@ int psi_prepare(amps_ctx* ctx, const amps_params* p, int DP, char* ws, const Psi
   }
   return AMPS_OK;
 }
+
+// launch `kern` as `nclusters` thread-block clusters of CL CTAs
+template <class K, class... Args>
+cudaError_t launch_cluster(K kern, int nclusters, int CL, int threads, size_t smem, cudaStream_t st, Args... args) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(nclusters * CL);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+constexpr int C4_CL = 4;
 
 }  // namespace
 
@@ -350,7 +378,7 @@ int amps_psi_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
   if (B == 0) return AMPS_OK;
   if (!x_dev || !loss_dev || !ws_dev) return fail(ctx, AMPS_E_INVALID, "NULL buffer");
   const int DP = padded_dim(p->D);
-  if (DP < 0) return fail(ctx, AMPS_E_UNSUPPORTED, "bond dimension %d > 64 not supported by the sequential kernel", p->D);
+  if (DP < 0) return fail(ctx, AMPS_E_UNSUPPORTED, "bond dimension %d > 128 not supported", p->D);
   const bool save = save_for_bwd != 0;
   const PsiWs L = psi_ws_layout(DP, B, T - 1, T, save);
   if (ws_bytes < L.total)
@@ -358,9 +386,23 @@ int amps_psi_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)ws_dev;
   const int nsteps = T - 1;
-  const int nchunks = (nsteps + CH - 1) / CH;
+  const int chl = chunk_len_of(DP);
+  const int nchunks = (nsteps + chl - 1) / chl;
   rc = psi_prepare(ctx, p, DP, ws, L, nsteps, st);
   if (rc) return rc;
+  if (DP == 128) {   // rows of N, R, S split over a 4-CTA cluster per clip
+    PROF_BEGIN(ctx, 0, st);
+    CUDA_TRY(ctx, launch_cluster(psi_fwd_c4_kernel<128, C4_CL, false>, B, C4_CL, 512, sizeof(FwdC4Smem<128, C4_CL>), st,
+                                 (const float2*)(ws + L.matN), (const float2*)(ws + L.matR),
+                                 (const float2*)(ws + L.matS), (const float2*)(ws + L.qtab),
+                                 (const float2*)(ws + L.psi0p), x_dev, T, p->A, loss_dev,
+                                 (double*)(ws + L.lossd), save ? (float2*)(ws + L.traj) : (float2*)nullptr,
+                                 save ? (float*)(ws + L.scales) : (float*)nullptr, nchunks,
+                                 (const float2*)nullptr, 0, 0));
+    PROF_END(ctx, 0, st);
+    LAUNCH_CHECK(ctx, "psi_fwd_c4_kernel");
+    return AMPS_OK;
+  }
   return dispatch_dp(DP, [&](auto dp, auto nq) -> int {
     constexpr int DPc = decltype(dp)::value, NQc = decltype(nq)::value;
     constexpr bool WS = DPc <= 32;   // warp-specialised chain/filler kernel
@@ -435,15 +477,29 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
   }
   if (!x_dev || !w_dev || !ws_dev) return fail(ctx, AMPS_E_INVALID, "NULL buffer");
   const int DP = padded_dim(p->D);
-  if (DP < 0) return fail(ctx, AMPS_E_UNSUPPORTED, "bond dimension %d > 64 not supported by the sequential kernel", p->D);
+  if (DP < 0) return fail(ctx, AMPS_E_UNSUPPORTED, "bond dimension %d > 128 not supported", p->D);
   const PsiWs L = psi_ws_layout(DP, B, T - 1, T, true);
   if (ws_bytes < L.total)
     return fail(ctx, AMPS_E_WORKSPACE, "workspace %zu < required %zu bytes", ws_bytes, L.total);
   char* ws = (char*)ws_dev;
   const int nsteps = T - 1;
-  const int nchunks = (nsteps + CH - 1) / CH;
+  const int chl = chunk_len_of(DP);
+  const int nchunks = (nsteps + chl - 1) / chl;
   const double cprime = -p->delta_t * (double)p->sigma * (double)p->sigma / 2.0;
   if (!ctx->ttab || ctx->ttab_n < T) return fail(ctx, AMPS_E_STATE, "backward without a saving forward");
+  if (DP == 128) {
+    PROF_BEGIN(ctx, 1, st);
+    CUDA_TRY(ctx, launch_cluster(psi_bwd_c4_kernel<128, C4_CL, false>, B, C4_CL, 512, sizeof(BwdC4Smem<128, C4_CL>), st,
+                                 (const float2*)(ws + L.matN), (const float2*)(ws + L.matRH),
+                                 (const float2*)(ws + L.matS), (const float2*)(ws + L.qtab),
+                                 (const float*)ctx->ttab, x_dev, T, p->A, w_dev,
+                                 (const float2*)(ws + L.traj), (const float*)(ws + L.scales), nchunks,
+                                 (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0),
+                                 (double*)(ws + L.gAdir), (const float2*)nullptr, 0, 0));
+    PROF_END(ctx, 1, st);
+    LAUNCH_CHECK(ctx, "psi_bwd_c4_kernel");
+    rc = AMPS_OK;
+  } else
   rc = dispatch_dp(DP, [&](auto dp, auto nq) -> int {
     constexpr int DPc = decltype(dp)::value, NQc = decltype(nq)::value;
     constexpr bool WS = DPc <= 32;
@@ -704,7 +760,7 @@ int amps_psi_sample(amps_ctx* ctx, const amps_params* p, const float* noise_dev,
   if (L_ == 0 || n == 0) return AMPS_OK;
   if (!noise_dev || !out_dev) return fail(ctx, AMPS_E_INVALID, "NULL buffer");
   const int DP = padded_dim(p->D);
-  if (DP < 0) return fail(ctx, AMPS_E_UNSUPPORTED, "bond dimension %d > 64 not supported by the sequential kernel", p->D);
+  if (DP < 0 || DP > 64) return fail(ctx, AMPS_E_UNSUPPORTED, "bond dimension %d > 64 not supported by the sampler", p->D);
   const PsiWs L = psi_ws_layout(DP, 0, L_, 0, false);
   rc = ensure_scratch(ctx, L.total);
   if (rc) return rc;

@@ -100,7 +100,7 @@ struct Map {
   static constexpr int NP = CPT / 2;
   static_assert(DP % (2 * NQ) == 0, "DP must be a multiple of 2*NQ");
   static_assert(NT % 32 == 0, "CTA must be whole warps");
-  static_assert(NQ == 4 || NQ == 8, "NQ in {4,8}");
+  static_assert(NQ == 4 || NQ == 8 || NQ == 16, "NQ in {4,8,16}");
   __device__ static __forceinline__ int col(int c, int jq) {
     return 2 * NQ * (c >> 1) + 2 * jq + (c & 1);
   }
@@ -215,11 +215,23 @@ __device__ __forceinline__ void st_dsmem_f4(unsigned addr, float4 v) {
 __device__ __forceinline__ void st_dsmem_f1(unsigned addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;\n" ::"r"(addr), "f"(v) : "memory");
 }
+// predicated 8-byte store into another CTA's shared memory (no divergent branch on the chain)
+__device__ __forceinline__ void st_dsmem_f2_if(bool on, unsigned addr, float2 v) {
+  asm volatile(
+      "{\n\t.reg .pred pp;\n\tsetp.ne.b32 pp, %0, 0;\n\t@pp st.shared::cluster.v2.f32 [%1], {%2, %3};\n\t}\n" ::"r"((int)on),
+      "r"(addr), "f"(v.x), "f"(v.y)
+      : "memory");
+}
 __device__ __forceinline__ void cluster_arrive_release() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
 }
 __device__ __forceinline__ void cluster_wait_acquire() {
   asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// full cluster barrier: every thread of every CTA; orders shared::cta and shared::cluster accesses
+__device__ __forceinline__ void cluster_sync_all() {
+  cluster_arrive_release();
+  cluster_wait_acquire();
 }
 }  // namespace amps
 

@@ -1,0 +1,582 @@
+// Psi scan for bond dimensions 65..128 (DP = 128): one clip per 4-CTA thread-block cluster.
+//
+// At D = 128 the step matrices N, R, S (128 KB each) no longer fit the register file of one SM, so
+// the ROWS of the matrices are split over the CL = 4 CTAs of a cluster: CTA `rank` owns rows
+// [32 rank, 32 rank + 32), 16 lanes per row, 8 complex columns of N, R (R^dag), S per thread -- the
+// same per-thread shape as the D = 64 kernels.  Every CTA keeps the FULL state vector of the
+// current chunk in its own shared memory; each step ends with the owners broadcasting their 32 new
+// entries into all four CTAs through distributed shared memory (st.shared::cluster) and ONE
+// barrier.cluster, which replaces the __syncthreads of the single-CTA kernels.  Scalars that need all
+// rows (E_k = x'^dag S x') are combined once per 16-step chunk by exchanging per-CTA partial sums.
+//
+//   model.py:257-267, 276-282, 293-334 (forward), train.py:89 (adjoint) -- same chain form and
+//   adjoint as amps_psi.cuh; chunk length CH4 = 16 (rescale / exchange period).
+#pragma once
+#include "amps_common.cuh"
+#include "amps_psi.cuh"
+
+namespace amps {
+
+constexpr int CH4 = 16;
+
+template <int DP, int CL>
+struct C4 {
+  static constexpr int RP = DP / CL;      // rows per CTA
+  static constexpr int NTL = 512;         // threads per CTA
+  static constexpr int NQ = NTL / RP;     // lanes per row
+  static constexpr int CPT = DP / NQ;     // complex columns per thread
+  static constexpr int NP = CPT / 2;
+  static_assert(NTL / 32 == CH4, "one warp per step in the chunk-end scalar passes");
+  static_assert(RP == 32, "own-row partial sums are one warp wide");
+  static_assert(2 * CL <= NQ, "broadcast lanes");
+};
+
+template <int DP, int CL>
+struct alignas(16) FwdC4Smem {
+  float2 xs[CH4 + 1][DP];             // x_{k0+kk}, full vector (own rows local, the rest written by peers)
+  float2 xps[CH4][DP];                // x'_{k0+kk}, full vector
+  float2 qs[2][CH4][DP];              // q_k, double buffered
+  float es[CH4][C4<DP, CL>::NTL];     // per-thread partial of Re(x'^dag S x') over this CTA's rows
+  float enx[CL][CH4];                 // per-CTA partial sums of every CTA of the cluster
+  float wav[2][CH4 + 4];
+  float sv[2][CH4 + 4];
+  float incv[2][CH4];
+  double lred[16];
+};
+
+// grid = CL * (number of clips or virtual clips), cluster = CL, block = 512.
+// VIRT: virtual-clip mode of the parallel-in-time scan, as in psi_fwd_uni_kernel.
+template <int DP, int CL, bool VIRT>
+__global__ void __launch_bounds__(512)
+    psi_fwd_c4_kernel(const float2* __restrict__ matN, const float2* __restrict__ matR,
+                      const float2* __restrict__ matS, const float2* __restrict__ qtab_,
+                      const float2* __restrict__ psi0p_, const float* __restrict__ x, int T, float A,
+                      float* __restrict__ loss, double* __restrict__ lossd,
+                      float2* __restrict__ traj, float* __restrict__ scales, int nchunks,
+                      const float2* __restrict__ psi0v, int nvc, int m_steps) {
+  using Cf = C4<DP, CL>;
+  constexpr int NQ = Cf::NQ, CPT = Cf::CPT, RP = Cf::RP, NTL = Cf::NTL;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FwdC4Smem<DP, CL>& sm = *reinterpret_cast<FwdC4Smem<DP, CL>*>(smem_raw);
+
+  const int t = threadIdx.x, il = t / NQ, jq = t % NQ, lane = t & 31, warp = t >> 5;
+  const unsigned rank = cluster_ctarank();
+  const int b = blockIdx.x / CL;
+  const int i = (int)rank * RP + il;     // global matrix row of this thread
+  int nsteps = T - 1;
+  const float* xb = x + (size_t)b * T;
+  const float2* qtab = qtab_;
+  const float2* psi0p = psi0p_;
+  size_t tstride = T;
+  int sstride = nchunks;
+  if (VIRT) {
+    const int clip = b / nvc, kbeg = (b % nvc) * m_steps;
+    nsteps = max(0, min(m_steps, T - 1 - kbeg));
+    xb = x + (size_t)clip * T + kbeg;
+    qtab = qtab_ + (size_t)kbeg * DP;
+    psi0p = psi0v + (size_t)b * DP;
+    nchunks = (nsteps + CH4 - 1) / CH4;
+    tstride = m_steps + 1;
+    sstride = m_steps / CH4;
+  }
+
+  float2 Nr[CPT], Rr[CPT], Sr[CPT];
+  load_slice<DP, NQ>(Nr, matN, i, jq);
+  load_slice<DP, NQ>(Rr, matR, i, jq);
+  load_slice<DP, NQ>(Sr, matS, i, jq);
+
+  if (t < DP) {
+    const float2 p = psi0p[t];
+    sm.xs[0][t] = p;
+    if (traj && rank == 0) traj[(size_t)b * tstride * DP + t] = p;
+  }
+
+  auto issue_loads = [&](int c, int buf) {
+    const int k0 = c * CH4;
+    const int len = min(CH4, nsteps - k0);
+    const float2* qsrc = qtab + (size_t)k0 * DP;
+    float2* qdst = &sm.qs[buf][0][0];
+    for (int idx = t; idx < len * DP / 2; idx += NTL) cp_async16(qdst + 2 * idx, qsrc + 2 * idx);
+    for (int idx = t; idx <= len; idx += NTL) cp_async4(&sm.wav[buf][idx], xb + k0 + idx);
+  };
+  auto compute_s = [&](int buf, int len) {
+    if (t < len) {
+      const float inc = sm.wav[buf][t + 1] - sm.wav[buf][t];   // model.py:263
+      sm.incv[buf][t] = inc;
+      sm.sv[buf][t] = inc / A;                                  // model.py:303
+    }
+  };
+
+  // per-step broadcast: lane jq < CL writes x_{k+1,i} into CTA jq, lane CL <= jq < 2CL writes
+  // x'_{k,i} into CTA jq - CL (own CTA included: one code path, no local store).
+  const bool st_on = jq < 2 * CL, st_x = jq < CL;
+  const unsigned st_addr0 = dsmem_addr(st_x ? (const void*)&sm.xs[1][i] : (const void*)&sm.xps[0][i],
+                                       (unsigned)(jq & (CL - 1)));
+
+  double lossacc = 0.0;
+  if (nchunks > 0) {
+    issue_loads(0, 0);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    compute_s(0, min(CH4, nsteps));
+  }
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int buf = c & 1;
+    const int k0 = c * CH4;
+    const int len = min(CH4, nsteps - k0);
+    if (c + 1 < nchunks) issue_loads(c + 1, buf ^ 1);
+    cp_async_commit();
+    // (D) sv/incv and xs[0] of this chunk visible; EVERY CTA is done with the previous chunk, so its
+    // xs / xps / enx may be overwritten remotely from here on
+    cluster_sync_all();
+
+    float2 xp_prev = make_float2(0.f, 0.f);
+    float s_cur = sm.sv[buf][0];
+
+    auto step = [&](auto first_tag, int kk) {
+      constexpr bool FIRST = decltype(first_tag)::value;
+      float2 xv[CPT], pv[CPT];
+#pragma unroll
+      for (int m = 0; m < CPT / 2; ++m) {
+        const float4 v = *reinterpret_cast<const float4*>(&sm.xs[kk][2 * NQ * m + 2 * jq]);
+        xv[2 * m] = make_float2(v.x, v.y);
+        xv[2 * m + 1] = make_float2(v.z, v.w);
+      }
+      if (!FIRST) {
+#pragma unroll
+        for (int m = 0; m < CPT / 2; ++m) {
+          const float4 v = *reinterpret_cast<const float4*>(&sm.xps[kk - 1][2 * NQ * m + 2 * jq]);
+          pv[2 * m] = make_float2(v.x, v.y);
+          pv[2 * m + 1] = make_float2(v.z, v.w);
+        }
+      }
+      const float2 q = sm.qs[buf][kk][i];
+      const float s_next = sm.sv[buf][kk + 1];
+      float2 L[CPT];
+#pragma unroll
+      for (int cc = 0; cc < CPT; ++cc)
+        L[cc] = make_float2(fmaf(s_cur, Rr[cc].x, Nr[cc].x), fmaf(s_cur, Rr[cc].y, Nr[cc].y));
+      float2 a0 = make_float2(0.f, 0.f), a1 = a0;
+#pragma unroll
+      for (int cc = 0; cc < CPT; cc += 2) {
+        cmac(a0, L[cc], xv[cc]);
+        cmac(a1, L[cc + 1], xv[cc + 1]);
+      }
+      float2 xp = make_float2(a0.x + a1.x, a0.y + a1.y);
+      // 16-lane row reduction, the previous step's S x' FMAs in the shuffle shadows
+      float2 p0 = make_float2(0.f, 0.f), p1 = p0;
+      constexpr int LV = 4;
+      constexpr int CPL = (CPT + LV - 1) / LV;
+#pragma unroll
+      for (int lv = 0; lv < LV; ++lv) {
+        const float ox = __shfl_xor_sync(0xffffffffu, xp.x, 1 << lv);
+        const float oy = __shfl_xor_sync(0xffffffffu, xp.y, 1 << lv);
+        if (!FIRST) {
+#pragma unroll
+          for (int cc = lv * CPL; cc < (lv + 1) * CPL && cc < CPT; ++cc) {
+            if (cc & 1) cmac(p1, Sr[cc], pv[cc]);
+            else cmac(p0, Sr[cc], pv[cc]);
+          }
+        }
+        xp.x += ox;
+        xp.y += oy;
+      }
+      const float2 xn = cmul(q, xp);
+      st_dsmem_f2_if(st_on, st_addr0 + (unsigned)(kk * DP * (int)sizeof(float2)), st_x ? xn : xp);
+      if (!FIRST) sm.es[kk - 1][t] = fmaf(xp_prev.x, p0.x + p1.x, xp_prev.y * (p0.y + p1.y));
+      xp_prev = xp;
+      s_cur = s_next;
+      cluster_sync_all();
+    };
+
+    step(TrueT{}, 0);
+    if (len == CH4) {
+#pragma unroll 2
+      for (int kk = 1; kk < CH4; ++kk) step(FalseT{}, kk);
+    } else {
+      for (int kk = 1; kk < len; ++kk) step(FalseT{}, kk);
+    }
+    {  // expectation partial of the chunk's last step
+      const float2 part = matvec1<DP, NQ>(Sr, sm.xps[len - 1], jq);
+      sm.es[len - 1][t] = fmaf(xp_prev.x, part.x, xp_prev.y * part.y);
+    }
+    cp_async_wait<0>();
+    __syncthreads();  // (A)
+
+    {  // this CTA's partial of Re(x'^dag S x') for step `warp`, handed to every CTA of the cluster
+      const int kk = warp;
+      float en = 0.f;
+      if (kk < len) {
+#pragma unroll
+        for (int r = 0; r < NTL / 32; ++r) en += sm.es[kk][lane + 32 * r];
+      }
+      en = warp_sum_f(en);
+      if (lane < CL && kk < len) st_dsmem_f1(dsmem_addr(&sm.enx[rank][kk], (unsigned)lane), en);
+    }
+    cluster_sync_all();  // (X1)
+    {  // per-step scalars, identical on every CTA (same operands, same order)
+      const int kk = warp;
+      float nu2 = 0.f;
+      if (kk < len) {
+#pragma unroll
+        for (int r = 0; r < DP / 32; ++r) nu2 += cabs2(sm.xs[kk][lane + 32 * r]);
+      }
+      nu2 = warp_sum_f(nu2);
+      if (lane == 0 && kk < len) {
+        float en = 0.f;
+#pragma unroll
+        for (int r = 0; r < CL; ++r) en += sm.enx[r][kk];
+        const float E = en / nu2;                                  // model.py:324-325 on x'
+        const float z = (E * sm.incv[buf][kk]) / A;                // model.py:294
+        lossacc -= (double)log1pf(z);
+      }
+    }
+    if (c + 1 < nchunks) compute_s(buf ^ 1, min(CH4, nsteps - (k0 + CH4)));
+    // rescale by 1/|x_{k0+len}| (every warp of every CTA computes the same norm)
+    float n2 = 0.f;
+    for (int r = lane; r < DP; r += 32) n2 += cabs2(sm.xs[len][r]);
+    n2 = warp_sum_f(n2);
+    const float sc = rsqrtf(n2);
+    __syncthreads();  // every read of xs[0..len] above is done
+    if (t < DP) {
+      float2 v = sm.xs[len][t];
+      v.x *= sc;
+      v.y *= sc;
+      sm.xs[len][t] = v;
+      sm.xs[0][t] = v;
+    }
+    if (t == 0 && rank == 0 && scales) scales[(size_t)b * sstride + c] = sc;
+    if (traj) {
+      __syncthreads();  // (B) scaled x_{k0+len} visible
+      const float4* src = reinterpret_cast<const float4*>(&sm.xs[1][0]);
+      float4* dst = reinterpret_cast<float4*>(traj + ((size_t)b * tstride + k0 + 1) * DP);
+      for (int idx = t + (int)rank * NTL; idx < len * DP / 2; idx += NTL * CL) dst[idx] = src[idx];
+    }
+  }
+
+  lossacc = warp_sum_d(lossacc);
+  if (lane == 0) sm.lred[warp] = lossacc;
+  __syncthreads();
+  if (t == 0 && rank == 0) {
+    double tot = 0.0;
+    for (int wv = 0; wv < NTL / 32; ++wv) tot += sm.lred[wv];
+    if (loss) loss[b] = (float)tot;
+    if (lossd) lossd[b] = tot;
+  }
+  cluster_sync_all();  // no CTA leaves while a peer could still address its shared memory
+}
+
+template <int DP, int CL>
+struct alignas(16) BwdC4Smem {
+  static constexpr int RP = C4<DP, CL>::RP;
+  float2 xs[3][CH4 + 1][DP];   // trajectory chunk, triple buffered (chunk c, c-1 in use, c-2 landing)
+  float2 qs[3][CH4][DP];
+  float2 xps[2][CH4][DP];      // reconstructed x'_k, full vector
+  float2 sps[2][CH4][RP];      // (S x'_k)_i, own rows
+  float2 mus[CH4][DP];         // adjoint of x'_k, full vector (own rows local, the rest from peers)
+  float es[CH4][RP + 1];       // Re(conj(x'_i) (S x')_i), own rows
+  float enx[CL][CH4];
+  float wav[3][CH4 + 4];
+  float tt[3][CH4 + 4];
+  float scs[3][4];
+  float sv[2][CH4], incv[2][CH4], dtk[2][CH4], alphas[2][CH4], betas[2][CH4];
+  double lred[16];
+};
+
+// Adjoint backward, same recursion and outputs as psi_bwd_uni_kernel; rows split over the cluster.
+template <int DP, int CL, bool VIRT>
+__global__ void __launch_bounds__(512)
+    psi_bwd_c4_kernel(const float2* __restrict__ matN, const float2* __restrict__ matRH,
+                      const float2* __restrict__ matS, const float2* __restrict__ qtab_,
+                      const float* __restrict__ ttab_, const float* __restrict__ x, int T, float A,
+                      const float* __restrict__ w, const float2* __restrict__ traj,
+                      const float* __restrict__ scales_, int nchunks, float2* __restrict__ Gout,
+                      float* __restrict__ gfout, float2* __restrict__ lam0out,
+                      double* __restrict__ gAdir, const float2* __restrict__ lam_end, int nvc,
+                      int m_steps) {
+  using Cf = C4<DP, CL>;
+  constexpr int NQ = Cf::NQ, CPT = Cf::CPT, NP = Cf::NP, RP = Cf::RP, NTL = Cf::NTL;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BwdC4Smem<DP, CL>& sm = *reinterpret_cast<BwdC4Smem<DP, CL>*>(smem_raw);
+
+  const int t = threadIdx.x, il = t / NQ, jq = t % NQ, lane = t & 31, warp = t >> 5;
+  const unsigned rank = cluster_ctarank();
+  const int b = blockIdx.x / CL;
+  const int i = (int)rank * RP + il;
+  int nsteps = T - 1;
+  const float* xb = x + (size_t)b * T;
+  const float2* trb = traj + (size_t)b * T * DP;
+  const float2* qtab = qtab_;
+  const float* ttab = ttab_;
+  const float* scales = scales_ + (size_t)b * nchunks;
+  float wb;
+  if (VIRT) {
+    const int clip = b / nvc, kbeg = (b % nvc) * m_steps;
+    nsteps = max(0, min(m_steps, T - 1 - kbeg));
+    xb = x + (size_t)clip * T + kbeg;
+    trb = traj + (size_t)b * (m_steps + 1) * DP;
+    qtab = qtab_ + (size_t)kbeg * DP;
+    ttab = ttab_ + kbeg;
+    scales = scales_ + (size_t)b * (m_steps / CH4);
+    nchunks = (nsteps + CH4 - 1) / CH4;
+    wb = w[clip];
+  } else {
+    wb = w[b];
+  }
+
+  float2 Nr[CPT], Hr[CPT], Sr[CPT];
+  load_slice<DP, NQ>(Nr, matN, i, jq);   // N is Hermitian: N^dag mu uses the same slices
+  load_slice<DP, NQ>(Hr, matRH, i, jq);  // R^dag
+  load_slice<DP, NQ>(Sr, matS, i, jq);
+
+  float2 GR[CPT], GN[CPT], GE[CPT];
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) GR[c] = GN[c] = GE[c] = make_float2(0.f, 0.f);
+
+  auto chunk_len = [&](int c) { return min(CH4, nsteps - c * CH4); };
+
+  auto issue_loads = [&](int c) {
+    const int lb = c % 3;
+    const int k0 = c * CH4;
+    const int len = chunk_len(c);
+    const float2* xsrc = trb + (size_t)k0 * DP;
+    float2* xdst = &sm.xs[lb][0][0];
+    for (int idx = t; idx < (len + 1) * DP / 2; idx += NTL) cp_async16(xdst + 2 * idx, xsrc + 2 * idx);
+    const float2* qsrc = qtab + (size_t)k0 * DP;
+    float2* qdst = &sm.qs[lb][0][0];
+    for (int idx = t; idx < len * DP / 2; idx += NTL) cp_async16(qdst + 2 * idx, qsrc + 2 * idx);
+    for (int idx = t; idx <= len; idx += NTL) {
+      cp_async4(&sm.wav[lb][idx], xb + k0 + idx);
+      cp_async4(&sm.tt[lb][idx], ttab + k0 + idx);
+    }
+    if (t == 0) cp_async4(&sm.scs[lb][0], scales + c);
+  };
+
+  // s, inc, dt; x'_k = conj(q_k) x_{k+1} / c_k (full vector, every CTA)
+  auto prep_elementwise = [&](int c) {
+    const int lb = c % 3, ds = c & 1, len = chunk_len(c);
+    if (t < len) {
+      const float inc = sm.wav[lb][t + 1] - sm.wav[lb][t];
+      sm.incv[ds][t] = inc;
+      sm.sv[ds][t] = inc / A;
+      sm.dtk[ds][t] = sm.tt[lb][t + 1] - sm.tt[lb][t];
+    }
+    const float inv_sc = 1.0f / sm.scs[lb][0];
+    for (int idx = t; idx < len * DP; idx += NTL) {
+      const int kk = idx / DP, r = idx % DP;
+      float2 xp = cmul_ca(sm.qs[lb][kk][r], sm.xs[lb][kk + 1][r]);
+      if (kk == len - 1) {
+        xp.x *= inv_sc;
+        xp.y *= inv_sc;
+      }
+      sm.xps[ds][kk][r] = xp;
+    }
+  };
+  // (S x')_i and e_i for this CTA's rows
+  auto expectation_step = [&](int ds, int kk) {
+    float2 part = matvec1<DP, NQ>(Sr, sm.xps[ds][kk], jq);
+    part = group_sum<NQ>(part);
+    const float2 xpi = sm.xps[ds][kk][i];
+    sts_if(jq == 1, &sm.sps[ds][kk][il], part);
+    sts_if(jq == 2, &sm.es[kk][il], fmaf(xpi.x, part.x, xpi.y * part.y));
+  };
+  // this CTA's partial of Re(x'^dag S x') per step -> every CTA
+  auto prep_partial = [&](int c) {
+    const int len = chunk_len(c), kk = warp;
+    float en = (kk < len) ? sm.es[kk][lane] : 0.f;
+    en = warp_sum_f(en);
+    if (lane < CL && kk < len) st_dsmem_f1(dsmem_addr(&sm.enx[rank][kk], (unsigned)lane), en);
+  };
+  double gAacc = 0.0;
+  // alpha_k, beta_k and the direct dL/dA term (identical on every CTA)
+  auto prep_totals = [&](int c) {
+    const int lb = c % 3, ds = c & 1, len = chunk_len(c), kk = warp;
+    float nu2 = 0.f;
+    if (kk < len) {
+#pragma unroll
+      for (int r = 0; r < DP / 32; ++r) nu2 += cabs2(sm.xs[lb][kk][lane + 32 * r]);
+    }
+    nu2 = warp_sum_f(nu2);
+    if (lane == 0 && kk < len) {
+      float en = 0.f;
+#pragma unroll
+      for (int r = 0; r < CL; ++r) en += sm.enx[r][kk];
+      const float E = en / nu2;
+      const float inc = sm.incv[ds][kk];
+      const float arg = 1.0f + (E * inc) / A;
+      const float gE = wb * (-sm.sv[ds][kk] / arg);
+      const float alpha = 2.0f * gE / nu2;
+      sm.alphas[ds][kk] = alpha;
+      sm.betas[ds][kk] = -alpha * E;
+      gAacc += (double)wb * (double)E * (double)inc / ((double)A * (double)A * (double)arg);
+    }
+  };
+
+  float2 lam = make_float2(0.f, 0.f);  // adjoint of x_{k+1,i}, replicated over the NQ lanes
+  if (VIRT) if (lam_end) lam = lam_end[(size_t)b * DP + i];
+  float gf = 0.f;
+
+  if (nchunks > 0) {
+    const int cl = nchunks - 1;
+    issue_loads(cl);
+    cp_async_commit();
+    if (cl >= 1) issue_loads(cl - 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    prep_elementwise(cl);
+    __syncthreads();
+    for (int kk = 0; kk < chunk_len(cl); ++kk) expectation_step(cl & 1, kk);
+    __syncthreads();
+    cluster_sync_all();   // every CTA of the cluster has started: remote shared memory is addressable
+    prep_partial(cl);
+    cluster_sync_all();
+    prep_totals(cl);
+  }
+
+  // lanes jq < CL broadcast mu_{k,i} into CTA jq
+  const bool mu_on = jq < CL;
+  const unsigned mu_addr0 = dsmem_addr(&sm.mus[0][i], (unsigned)(jq & (CL - 1)));
+  constexpr unsigned MU_ROW = DP * sizeof(float2);
+
+  for (int c = nchunks - 1; c >= 0; --c) {
+    const int lb = c % 3, ds = c & 1;
+    const int len = chunk_len(c);
+    const bool has_prev = c >= 1;
+    const int pds = ds ^ 1;
+    if (c >= 2) issue_loads(c - 2);
+    cp_async_commit();
+    cp_async_wait<1>();   // chunk c-1 has landed
+    __syncthreads();      // (T1) alphas/betas of chunk c visible
+    if (has_prev) prep_elementwise(c - 1);
+    const float sc = sm.scs[lb][0];
+
+    float2 mu;
+    {  // adjoint of x' for the chunk's last step (carries the rescale c_k)
+      const int kk = len - 1;
+      const float2 xn = sm.xs[lb][kk + 1][i];
+      gf = fmaf(sm.dtk[ds][kk], lam.x * xn.y - lam.y * xn.x, gf);   // Im(conj(lam) x_{k+1})
+      mu = cmul_ca(sm.qs[lb][kk][i], lam);
+      const float al = sm.alphas[ds][kk];
+      const float2 sp = sm.sps[ds][kk][il];
+      mu.x = fmaf(al, sp.x, mu.x * sc);
+      mu.y = fmaf(al, sp.y, mu.y * sc);
+      st_dsmem_f2_if(mu_on, mu_addr0 + (unsigned)kk * MU_ROW, mu);
+    }
+    cluster_sync_all();   // (T2) mu of the last step everywhere; x' of chunk c-1 visible
+
+    auto step = [&](auto prev_tag, int kk) {
+      constexpr bool PREV = decltype(prev_tag)::value;     // chunk c-1 exists (expectation filler)
+      float2 mv[CPT];
+#pragma unroll
+      for (int m = 0; m < NP; ++m) {
+        const float4 v = *reinterpret_cast<const float4*>(&sm.mus[kk][2 * NQ * m + 2 * jq]);
+        mv[2 * m] = make_float2(v.x, v.y);
+        mv[2 * m + 1] = make_float2(v.z, v.w);
+      }
+      const float s = sm.sv[ds][kk];
+      const float be = sm.betas[ds][kk];
+      const float2 xk = sm.xs[lb][kk][i];
+      const int km = kk > 0 ? kk - 1 : 0;
+      const float2 q1 = sm.qs[lb][km][i];
+      const float al1 = sm.alphas[ds][km];
+      const float2 sp1 = sm.sps[ds][km][il];
+      const float dt1 = sm.dtk[ds][km];
+      // ---- chain: lam_i = (L_k^dag mu)_i + beta x_{k,i} ----------------------------------
+      float2 a0 = make_float2(0.f, 0.f), a1 = a0;
+#pragma unroll
+      for (int cc = 0; cc < CPT; cc += 2) {
+        const float2 l0 = make_float2(fmaf(s, Hr[cc].x, Nr[cc].x), fmaf(s, Hr[cc].y, Nr[cc].y));
+        const float2 l1 = make_float2(fmaf(s, Hr[cc + 1].x, Nr[cc + 1].x), fmaf(s, Hr[cc + 1].y, Nr[cc + 1].y));
+        cmac(a0, l0, mv[cc]);
+        cmac(a1, l1, mv[cc + 1]);
+      }
+      float2 lp = make_float2(a0.x + a1.x, a0.y + a1.y);
+      float ox = __shfl_xor_sync(0xffffffffu, lp.x, 1);
+      float oy = __shfl_xor_sync(0xffffffffu, lp.y, 1);
+      // ---- filler 1: rank-1 tiles of step kk (rows of this CTA) -------------------------
+      {
+        const float2 xpi = sm.xps[ds][kk][i];
+        const float al = sm.alphas[ds][kk];
+        const float2 u1 = make_float2(s * mu.x, s * mu.y);
+        const float2 u3 = make_float2(al * xpi.x, al * xpi.y);
+#pragma unroll
+        for (int m = 0; m < NP; ++m) {
+          const float4 xv = *reinterpret_cast<const float4*>(&sm.xs[lb][kk][2 * NQ * m + 2 * jq]);
+          const float4 pv = *reinterpret_cast<const float4*>(&sm.xps[ds][kk][2 * NQ * m + 2 * jq]);
+          const float2 x0 = make_float2(xv.x, xv.y), x1 = make_float2(xv.z, xv.w);
+          const float2 p0 = make_float2(pv.x, pv.y), p1 = make_float2(pv.z, pv.w);
+          cmac_cx(GR[2 * m], u1, x0);
+          cmac_cx(GR[2 * m + 1], u1, x1);
+          cmac_cx(GN[2 * m], mu, x0);
+          cmac_cx(GN[2 * m + 1], mu, x1);
+          cmac_cx(GE[2 * m], u3, p0);
+          cmac_cx(GE[2 * m + 1], u3, p1);
+        }
+      }
+      lp.x += ox;
+      lp.y += oy;
+      ox = __shfl_xor_sync(0xffffffffu, lp.x, 2);
+      oy = __shfl_xor_sync(0xffffffffu, lp.y, 2);
+      // ---- filler 2: S x' of step kk of chunk c-1 ---------------------------------------
+      if (PREV) expectation_step(pds, kk);
+      lp.x += ox;
+      lp.y += oy;
+      lp.x += __shfl_xor_sync(0xffffffffu, lp.x, 4);
+      lp.y += __shfl_xor_sync(0xffffffffu, lp.y, 4);
+      lp.x += __shfl_xor_sync(0xffffffffu, lp.x, 8);
+      lp.y += __shfl_xor_sync(0xffffffffu, lp.y, 8);
+      lam.x = fmaf(be, xk.x, lp.x);
+      lam.y = fmaf(be, xk.y, lp.y);
+      // ---- adjoint of x' for step kk-1 --------------------------------------------------
+      if (kk > 0) {
+        gf = fmaf(dt1, lam.x * xk.y - lam.y * xk.x, gf);   // Im(conj(lam) x_k), x_k = x_{(k-1)+1}
+        mu = cmul_ca(q1, lam);
+        mu.x = fmaf(al1, sp1.x, mu.x);
+        mu.y = fmaf(al1, sp1.y, mu.y);
+      }
+      st_dsmem_f2_if(mu_on && kk > 0, mu_addr0 + (unsigned)km * MU_ROW, mu);
+      cluster_sync_all();
+    };
+
+    if (has_prev) {
+      for (int kk = len - 1; kk >= 0; --kk) step(TrueT{}, kk);
+      // chunk c-1 is always full; finish its expectation steps if this chunk was short
+      for (int kk = len; kk < CH4; ++kk) expectation_step(pds, kk);
+      __syncthreads();    // (E1) es / sps of chunk c-1 complete
+      prep_partial(c - 1);
+      cluster_sync_all(); // (X1)
+      prep_totals(c - 1);
+    } else {
+      for (int kk = len - 1; kk >= 0; --kk) step(FalseT{}, kk);
+    }
+  }
+  cp_async_wait<0>();
+
+  // ---- per-clip outputs (rows of this CTA) ---------------------------------------------------
+  float2* Gb = Gout + (size_t)b * 3 * DP * DP;
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) {
+    const int col = Map<DP, NQ>::col(c, jq);
+    Gb[0 * DP * DP + i * DP + col] = GR[c];
+    Gb[1 * DP * DP + i * DP + col] = GN[c];
+    Gb[2 * DP * DP + i * DP + col] = GE[c];
+  }
+  if (jq == 0) {
+    gfout[(size_t)b * DP + i] = gf;
+    lam0out[(size_t)b * DP + i] = lam;
+  }
+  gAacc = warp_sum_d(gAacc);
+  if (lane == 0) sm.lred[warp] = gAacc;
+  __syncthreads();
+  if (t == 0 && rank == 0) {
+    double tot = 0.0;
+    for (int wv = 0; wv < NTL / 32; ++wv) tot += sm.lred[wv];
+    gAdir[b] = tot;
+  }
+  cluster_sync_all();
+}
+
+}  // namespace amps

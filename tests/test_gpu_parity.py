@@ -26,6 +26,9 @@ CASES = [
     (16, 5, 333, dict(sigma=0.05)),
     (32, 4, 700, dict()),
     (64, 3, 200, dict()),
+    (128, 3, 150, dict()),    # row-split 4-CTA cluster kernels (BASELINE config C3's bond dimension)
+    (100, 2, 49, dict(sigma=0.05)),   # padded to 128; 3 chunks + 1 step
+    (128, 1, 17, dict()),     # one chunk
     (5, 2, 33, dict()),       # one chunk + one step
     (8, 1, 2, dict()),        # single step
 ]
@@ -78,7 +81,7 @@ def test_psi_weighted_grads_effective(cuda, lib):
     assert rel(packed[n:n + D], gf.numpy()) <= GRAD_TOL
     assert relc(packed[n + D:n + 3 * D].reshape(D, 2) @ np.array([1, 1j]), gp.numpy()) <= GRAD_TOL
     assert rel(packed[n + 3 * D], float(gA)) <= GRAD_TOL
-    assert rel(packed[n + 3 * D + 1], float(tot)) <= LOSS_TOL
+    assert rel(packed[n + 3 * D + 1], float(tot.detach())) <= LOSS_TOL
 
 
 @pytest.mark.parametrize("D,n,L,over", [(2, 2, 512, dict(sigma=1.0, A=1.0)), (7, 5, 256, dict()),
