@@ -80,7 +80,11 @@ double amps_fma_peak_tflops2(amps_ctx* ctx, int packed);
 
 /* ---- PsiCMPS --------------------------------------------------------------------------- */
 
-/* bytes of caller-owned workspace for the Psi loss forward/backward at (D, B clips, T samples).
+/* Bond dimensions: loss, gradient and trajectory 1 <= D <= 128 (zero-padded to 8/16/32/64/128; above
+ * 64 the matrices are row-split over a 4-CTA cluster); sampler and tensor-core scan D <= 64; Rho
+ * D <= 32.  Anything else returns AMPS_E_UNSUPPORTED (and a workspace size of 0).
+ *
+ * bytes of caller-owned workspace for the Psi loss forward/backward at (D, B clips, T samples).
  * save_for_bwd != 0 adds the state trajectory the adjoint sweep consumes. */
 size_t amps_psi_workspace_bytes(int D, int B, int T, int save_for_bwd);
 

@@ -1,5 +1,5 @@
 """Timings of the other BASELINE configs (kernel + API level, CUDA events).
-usage: python profiles/time_configs.py [c2] [c4] [c0]"""
+usage: python profiles/time_configs.py [c2] [c3] [c4] [c0]"""
 import os
 import sys
 
@@ -58,3 +58,21 @@ if "c0" in which:   # D=8, 8 clips of 1 s
         m.loss_fn(x).backward()
     ms = timed(step0)
     print(f"C0 D={D} B={B} T={T}: step {ms:.2f} ms -> {B*T/ms*1e3:.3e} samples/s")
+if "c3" in which:   # D=128, 128 clips, 4 s clips: row-split 4-CTA cluster kernels
+    D, T = 128, 64000
+    for B in (1, 37, 128):
+        m = PsiCMPS(hp(D, B), device=dev, seed=0)
+        m.time_parallel = "never"
+        x = torch.from_numpy(damped_sine(B, T, 1 / 16000, np.random.default_rng(1))).to(dev)
+        _lib.set_profiling(0, True)
+
+        def step3():
+            m.zero_grad()
+            m.loss_fn(x).backward()
+        ms = timed(step3, reps=2)
+        f, bw = _lib.kernel_ms(0, 0), _lib.kernel_ms(0, 1)
+        print(f"C3 D={D} B={B} T={T}: step {ms:.1f} ms (fwd kernel {f:.1f}, bwd kernel {bw:.1f}) "
+              f"-> {B*T/ms*1e3:.3e} samples/s; waves {-(-B*4//148)}; "
+              f"fwd {f*1e-3/T*1.965e9/max(1,-(-B*4//148)):.0f} cyc/step/wave, bwd {bw*1e-3/T*1.965e9/max(1,-(-B*4//148)):.0f}")
+        del m, x
+        torch.cuda.empty_cache()
