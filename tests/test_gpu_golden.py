@@ -71,13 +71,19 @@ def test_rho_golden(cuda, lib):
     assert relc(tr[:, -1], g["traj_last"]) <= 1e-4
 
 
-def test_psi_c1_full_size_golden(cuda, lib):
-    """BASELINE config[1] at FULL size (D=32, 64 clips x 64000 samples) against the float64 run of the
-    independent C restatement (oracle/mint_golden_c1.py): per-clip loss 1e-4, gradients wrt the
-    effective parameters 1e-3 (north_star tolerances)."""
+FULL = [("psi_c1_full", False), ("psi_c4_d64_full_length", False), ("psi_c4_d64_full_length", True),
+        ("psi_c3_d128_full_length", False)]
+
+
+@pytest.mark.parametrize("name,scan", FULL)
+def test_psi_full_length_golden(cuda, lib, name, scan):
+    """Full-length (64000-sample) clips against the float64 run of the independent C restatement
+    (oracle/mint_golden_c1.py): BASELINE config[1] at FULL size (D=32, 64 clips), and 4 clips at the
+    bond dimensions of config[4] (64: chain kernels and the tensor-core scan) and config[3] (128:
+    row-split cluster kernels).  Per-clip loss 1e-4, effective-parameter gradients 1e-3."""
     from audio_mps_b200.model import _PsiLossFn
     from oracle.cmps_oracle import HP, damped_sine, random_raw_params
-    g = load("psi_c1_full")
+    g = load(name)
     D, B, T, seed = int(g["D"]), int(g["B"]), int(g["T"]), int(g["seed"])
     hp = HP(bond_dim=D, minibatch_size=B)
     raw = random_raw_params(hp, np.random.default_rng(seed))
@@ -90,7 +96,7 @@ def test_psi_c1_full_size_golden(cuda, lib):
     p0 = torch.view_as_real(m.psi_0.detach()).clone().requires_grad_()
     A = m.A.detach().clone().requires_grad_()
     x = torch.as_tensor(data, device=cuda)
-    lpc = _PsiLossFn.apply(R, f, p0, A, x, m)
+    lpc = _PsiLossFn.apply(R, f, p0, A, x, m, scan)
     assert rel(lpc.detach().cpu().numpy(), g["loss_f64"]) <= 1e-4
     gR, gf, gp, gA = torch.autograd.grad(lpc.mean(), [R, f, p0, A])
     assert relc(torch.view_as_complex(gR).cpu().numpy(), g["geff_R"]) <= 1e-3

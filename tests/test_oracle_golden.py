@@ -70,13 +70,16 @@ def test_rho_golden():
     assert rel(o.loss_per_clip(g["data"]).detach().numpy(), g["loss_f64"]) <= 1e-10
 
 
-def test_c1_full_golden_inputs_regenerate():
-    """The full-size C1 fixture stores only outputs; its inputs must regenerate from the recorded seed."""
+@pytest.mark.parametrize("name,shape", [("psi_c1_full", (32, 64, 64000)),
+                                        ("psi_c4_d64_full_length", (64, 4, 64000)),
+                                        ("psi_c3_d128_full_length", (128, 4, 64000))])
+def test_full_length_golden_inputs_regenerate(name, shape):
+    """The full-length fixtures store only outputs; their inputs must regenerate from the recorded seed."""
     from oracle.cmps_oracle import HP, PsiCMPSOracle, damped_sine, random_raw_params
     from oracle import cref
-    g = load("psi_c1_full")
+    g = load(name)
     D, B, T, seed = int(g["D"]), int(g["B"]), int(g["T"]), int(g["seed"])
-    assert (D, B, T) == (32, 64, 64000)
+    assert (D, B, T) == shape
     hp = HP(bond_dim=D, minibatch_size=B)
     raw = random_raw_params(hp, np.random.default_rng(seed))
     data = damped_sine(B, T, hp.delta_t, np.random.default_rng(seed + 1))
@@ -84,7 +87,7 @@ def test_c1_full_golden_inputs_regenerate():
     o = PsiCMPSOracle(hp, raw, mode="f32", requires_grad=False)
     R, f, p0, A = cref.effective_from_oracle(o)
     assert np.array_equal(R, g["R_eff"]) and np.array_equal(f, g["freqs_eff"]) and np.array_equal(p0, g["psi0"])
-    # the C restatement reproduces the stored float64 loss on the first two clips' first 2000 samples
+    # the C restatement reproduces the stored float64 loss on the first two clips' first 500 samples
     # only as a smoke check of the fixture's provenance (same function, shorter input => different value)
-    l2 = cref.psi_loss(R, f, p0, A, hp.sigma, hp.delta_t, data[:2, :2000], mode="f64")
+    l2 = cref.psi_loss(R, f, p0, A, hp.sigma, hp.delta_t, data[:2, :500], mode="f64")
     assert np.all(np.isfinite(l2)) and g["loss_f64"].shape == (B,)
