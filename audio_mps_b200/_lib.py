@@ -35,7 +35,8 @@ class AmpsParams(C.Structure):
     _fields_ = [("D", C.c_int32), ("reserved", C.c_int32),
                 ("R_dev", C.c_void_p), ("freqs_dev", C.c_void_p),
                 ("psi0_dev", C.c_void_p), ("rho0_dev", C.c_void_p),
-                ("A", C.c_float), ("sigma", C.c_float), ("delta_t", C.c_double)]
+                ("A", C.c_float), ("sigma", C.c_float), ("delta_t", C.c_double),
+                ("A_dev", C.c_void_p)]
 
 
 class AmpsHostParams(C.Structure):

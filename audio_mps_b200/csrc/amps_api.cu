@@ -127,6 +127,9 @@ int padded_dim(int D) {
 // time-chunk length (rescale period) of the kernels serving a padded bond dimension
 int chunk_len_of(int DP) { return DP == 128 ? CH4 : CH; }
 
+// A by value, or by device pointer when the caller supplies one (no host read-back per step)
+AVal aval(const amps_params* p) { return AVal{p->A, p->A_dev}; }
+
 template <int V>
 using IC = std::integral_constant<int, V>;
 
@@ -220,7 +223,7 @@ int check_common(amps_ctx* ctx, const amps_params* p) {
   if (!p) return fail(ctx, AMPS_E_INVALID, "params is NULL");
   if (p->D <= 0) return fail(ctx, AMPS_E_INVALID, "bond dimension D=%d must be positive", p->D);
   if (!p->R_dev || !p->freqs_dev) return fail(ctx, AMPS_E_INVALID, "R_dev/freqs_dev is NULL");
-  if (!(p->A == p->A) || p->A == 0.0f) return fail(ctx, AMPS_E_INVALID, "A must be non-zero");
+  if (!p->A_dev && (!(p->A == p->A) || p->A == 0.0f)) return fail(ctx, AMPS_E_INVALID, "A must be non-zero");
   return AMPS_OK;
 }
 
@@ -395,7 +398,7 @@ int amps_psi_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
     CUDA_TRY(ctx, launch_cluster(psi_fwd_c4_kernel<128, C4_CL, false>, B, C4_CL, 512, sizeof(FwdC4Smem<128, C4_CL>), st,
                                  (const float2*)(ws + L.matN), (const float2*)(ws + L.matR),
                                  (const float2*)(ws + L.matS), (const float2*)(ws + L.qtab),
-                                 (const float2*)(ws + L.psi0p), x_dev, T, p->A, loss_dev,
+                                 (const float2*)(ws + L.psi0p), x_dev, T, aval(p), loss_dev,
                                  (double*)(ws + L.lossd), save ? (float2*)(ws + L.traj) : (float2*)nullptr,
                                  save ? (float*)(ws + L.scales) : (float*)nullptr, nchunks,
                                  (const float2*)nullptr, 0, 0));
@@ -426,7 +429,7 @@ int amps_psi_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
       PROF_BEGIN(ctx, 0, st);
       CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, kcl, (const float2*)(ws + L.matN), (const float2*)(ws + L.matR),
                                        (const float2*)(ws + L.matS), (const float2*)(ws + L.qtab),
-                                       (const float2*)(ws + L.psi0p), x_dev, T, p->A, loss_dev,
+                                       (const float2*)(ws + L.psi0p), x_dev, T, aval(p), loss_dev,
                                        (double*)(ws + L.lossd), save ? (float2*)(ws + L.traj) : (float2*)nullptr,
                                        save ? (float*)(ws + L.scales) : (float*)nullptr, nchunks,
                                        save ? (float2*)(ws + L.sptraj) : (float2*)nullptr,
@@ -445,14 +448,14 @@ int amps_psi_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
     if constexpr (WS) {
       psi_fwd_kernel<DPc, NQc><<<B, 2 * DPc * NQc, smem, st>>>(
           (const float2*)(ws + L.matN), (const float2*)(ws + L.matR), (const float2*)(ws + L.matS),
-          (const float2*)(ws + L.qtab), (const float2*)(ws + L.psi0p), x_dev, T, p->A, loss_dev,
+          (const float2*)(ws + L.qtab), (const float2*)(ws + L.psi0p), x_dev, T, aval(p), loss_dev,
           (double*)(ws + L.lossd), save ? (float2*)(ws + L.traj) : nullptr,
           save ? (float*)(ws + L.scales) : nullptr, nchunks,
           save ? (float2*)(ws + L.sptraj) : nullptr, save ? (float2*)(ws + L.ev) : nullptr);
     } else {
       psi_fwd_uni_kernel<DPc, NQc><<<B, DPc * NQc, smem, st>>>(
           (const float2*)(ws + L.matN), (const float2*)(ws + L.matR), (const float2*)(ws + L.matS),
-          (const float2*)(ws + L.qtab), (const float2*)(ws + L.psi0p), x_dev, T, p->A, loss_dev,
+          (const float2*)(ws + L.qtab), (const float2*)(ws + L.psi0p), x_dev, T, aval(p), loss_dev,
           (double*)(ws + L.lossd), save ? (float2*)(ws + L.traj) : nullptr,
           save ? (float*)(ws + L.scales) : nullptr, nchunks, (const float2*)nullptr, 0, 0);
     }
@@ -492,7 +495,7 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
     CUDA_TRY(ctx, launch_cluster(psi_bwd_c4_kernel<128, C4_CL, false>, B, C4_CL, 512, sizeof(BwdC4Smem<128, C4_CL>), st,
                                  (const float2*)(ws + L.matN), (const float2*)(ws + L.matRH),
                                  (const float2*)(ws + L.matS), (const float2*)(ws + L.qtab),
-                                 (const float*)ctx->ttab, x_dev, T, p->A, w_dev,
+                                 (const float*)ctx->ttab, x_dev, T, aval(p), w_dev,
                                  (const float2*)(ws + L.traj), (const float*)(ws + L.scales), nchunks,
                                  (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0),
                                  (double*)(ws + L.gAdir), (const float2*)nullptr, 0, 0));
@@ -522,7 +525,7 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
       PROF_BEGIN(ctx, 1, st);
       CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, kcl, (const float2*)(ws + L.matN), (const float2*)(ws + L.matRH),
                                        (const float2*)(ws + L.matS), (const float2*)(ws + L.qtab),
-                                       (const float*)ctx->ttab, x_dev, T, p->A, w_dev,
+                                       (const float*)ctx->ttab, x_dev, T, aval(p), w_dev,
                                        (const float2*)(ws + L.traj), (const float*)(ws + L.scales), nchunks,
                                        (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0),
                                        (double*)(ws + L.gAdir), (const float2*)(ws + L.sptraj),
@@ -541,14 +544,14 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
     if constexpr (WS) {
       psi_bwd_kernel<DPc, NQc><<<B, 2 * DPc * NQc, smem, st>>>(
           (const float2*)(ws + L.matN), (const float2*)(ws + L.matRH), (const float2*)(ws + L.matS),
-          (const float2*)(ws + L.qtab), ctx->ttab, x_dev, T, p->A, w_dev,
+          (const float2*)(ws + L.qtab), ctx->ttab, x_dev, T, aval(p), w_dev,
           (const float2*)(ws + L.traj), (const float*)(ws + L.scales), nchunks,
           (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0), (double*)(ws + L.gAdir),
           (const float2*)(ws + L.sptraj), (const float2*)(ws + L.ev));
     } else {
       psi_bwd_uni_kernel<DPc, NQc><<<B, DPc * NQc, smem, st>>>(
           (const float2*)(ws + L.matN), (const float2*)(ws + L.matRH), (const float2*)(ws + L.matS),
-          (const float2*)(ws + L.qtab), ctx->ttab, x_dev, T, p->A, w_dev,
+          (const float2*)(ws + L.qtab), ctx->ttab, x_dev, T, aval(p), w_dev,
           (const float2*)(ws + L.traj), (const float*)(ws + L.scales), nchunks,
           (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0), (double*)(ws + L.gAdir),
           (const float2*)nullptr, 0, 0);
@@ -567,7 +570,7 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
     psi_grad_finalize_kernel<<<1, 256, 0, st>>>(
         (const float2*)(ws + L.Gtot), (const float*)(ws + L.gftot), (const float2*)(ws + L.lam0tot),
         (const double*)(ws + L.gAdir), (const double*)(ws + L.lossd), w_dev, B,
-        (const float2*)(ws + L.matR), p->D, DP, cprime, p->A, grad_dev);
+        (const float2*)(ws + L.matR), p->D, DP, cprime, aval(p), grad_dev);
     LAUNCH_CHECK(ctx, "psi_grad_finalize_kernel");
   }
   return AMPS_OK;
@@ -654,7 +657,7 @@ int amps_psi_loss_fwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
     CUDA_TRY(ctx, cudaFuncSetAttribute(psi_compose_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PROF_BEGIN(ctx, 2, st);
     psi_compose_tc_kernel<<<nv, TC_THREADS, smem, st>>>((const float2*)(ws + L.base.matN), (const float2*)(ws + L.base.matR),
-                                                 (const float2*)(ws + L.base.qtab), x_dev, T, p->A, L.nvc,
+                                                 (const float2*)(ws + L.base.qtab), x_dev, T, aval(p), L.nvc,
                                                  L.m_steps, (float*)(ws + L.ops));
     PROF_END(ctx, 2, st);
     LAUNCH_CHECK(ctx, "psi_compose_tc_kernel");
@@ -673,7 +676,7 @@ int amps_psi_loss_fwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
     PROF_BEGIN(ctx, 0, st);
     kern<<<nv, 64 * 8, smem, st>>>((const float2*)(ws + L.base.matN), (const float2*)(ws + L.base.matR),
                                    (const float2*)(ws + L.base.matS), (const float2*)(ws + L.base.qtab),
-                                   (const float2*)(ws + L.base.psi0p), x_dev, T, p->A, (float*)nullptr,
+                                   (const float2*)(ws + L.base.psi0p), x_dev, T, aval(p), (float*)nullptr,
                                    (double*)(ws + L.lossv), save ? (float2*)(ws + L.traj) : (float2*)nullptr,
                                    save ? (float*)(ws + L.scales) : (float*)nullptr, 0,
                                    (const float2*)(ws + L.ystart), L.nvc, L.m_steps);
@@ -717,7 +720,7 @@ int amps_psi_loss_bwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
   auto adjoint_pass = [&](const float2* lam_end) {
     kern<<<nv, 64 * 8, smem, st>>>((const float2*)(ws + L.base.matN), (const float2*)(ws + L.base.matRH),
                                    (const float2*)(ws + L.base.matS), (const float2*)(ws + L.base.qtab),
-                                   (const float*)ctx->ttab, x_dev, T, p->A, w_dev,
+                                   (const float*)ctx->ttab, x_dev, T, aval(p), w_dev,
                                    (const float2*)(ws + L.traj), (const float*)(ws + L.scales), 0,
                                    (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0),
                                    (double*)(ws + L.gAdir), lam_end, L.nvc, L.m_steps);
@@ -745,7 +748,7 @@ int amps_psi_loss_bwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
     psi_grad_finalize_kernel<<<1, 256, 0, st>>>(
         (const float2*)(ws + L.Gtot), (const float*)(ws + L.gftot), (const float2*)(ws + L.lam0tot),
         (const double*)(ws + L.gAdir), (const double*)(ws + L.lossv), (const float*)(ws + L.wv), nv,
-        (const float2*)(ws + L.base.matR), p->D, DP, cprime, p->A, grad_dev);
+        (const float2*)(ws + L.base.matR), p->D, DP, cprime, aval(p), grad_dev);
     LAUNCH_CHECK(ctx, "psi_grad_finalize_kernel");
   }
   return AMPS_OK;

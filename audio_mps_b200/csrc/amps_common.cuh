@@ -88,6 +88,14 @@ __device__ __forceinline__ void tie_loads(float2 (&v)[N]) {
   v[0].x = fmaf(g, 0.0f, v[0].x);
 }
 
+// The trainable scalar A (model.py:19) reaches the kernels either by value (host float) or through a
+// device pointer, so that a training loop never has to read the parameter back to the host.
+struct AVal {
+  float host;
+  const float* dev;
+};
+__device__ __forceinline__ float a_get(AVal a) { return a.dev ? __ldg(a.dev) : a.host; }
+
 // ---- thread map ---------------------------------------------------------------------------
 // A CTA of DP*NQ threads owns one clip.  Thread t = i*NQ + jq holds, for matrix row i, the
 // CPT = DP/NQ columns  col(c) = 2*NQ*(c/2) + 2*jq + (c&1)  in registers, so that for a fixed

@@ -123,7 +123,8 @@ __global__ void psi_grad_finalize_kernel(const float2* __restrict__ Gtot,
                                          const double* __restrict__ lossd,
                                          const float* __restrict__ w, int B,
                                          const float2* __restrict__ matR, int D, int DP,
-                                         double cprime, float A, float* __restrict__ out) {
+                                         double cprime, AVal A_, float* __restrict__ out) {
+  const float A = a_get(A_);
   __shared__ double red[32];
   const float2* GR = Gtot;
   const float2* GN = Gtot + DP * DP;

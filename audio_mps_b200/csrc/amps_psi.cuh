@@ -89,10 +89,11 @@ template <int DP, int NQ>
 __global__ void __launch_bounds__(2 * DP * NQ)
     psi_fwd_kernel(const float2* __restrict__ matN, const float2* __restrict__ matR,
                    const float2* __restrict__ matS, const float2* __restrict__ qtab,
-                   const float2* __restrict__ psi0p, const float* __restrict__ x, int T, float A,
+                   const float2* __restrict__ psi0p, const float* __restrict__ x, int T, AVal A_,
                    float* __restrict__ loss, double* __restrict__ lossd,
                    float2* __restrict__ traj, float* __restrict__ scales, int nchunks,
                    float2* __restrict__ sptraj, float2* __restrict__ evout) {
+  const float A = a_get(A_);
   using M = Map<DP, NQ>;
   using Sm = FwdSmem<DP, NQ>;
   constexpr int NTC = M::NT;       // threads per role
@@ -301,12 +302,13 @@ template <int DP, int NQ>
 __global__ void __launch_bounds__(2 * DP * NQ)
     psi_bwd_kernel(const float2* __restrict__ matN, const float2* __restrict__ matRH,
                    const float2* __restrict__ matS, const float2* __restrict__ qtab,
-                   const float* __restrict__ ttab, const float* __restrict__ x, int T, float A,
+                   const float* __restrict__ ttab, const float* __restrict__ x, int T, AVal A_,
                    const float* __restrict__ w, const float2* __restrict__ traj,
                    const float* __restrict__ scales, int nchunks, float2* __restrict__ Gout,
                    float* __restrict__ gfout, float2* __restrict__ lam0out,
                    double* __restrict__ gAdir, const float2* __restrict__ sptraj,
                    const float2* __restrict__ evin) {
+  const float A = a_get(A_);
   using M = Map<DP, NQ>;
   using Sm = BwdSmem<DP, NQ>;
   constexpr int NTC = M::NT;
@@ -573,10 +575,11 @@ template <int DP, int NQ, bool VIRT = false>
 __global__ void __launch_bounds__(DP* NQ)
     psi_fwd_uni_kernel(const float2* __restrict__ matN, const float2* __restrict__ matR,
                    const float2* __restrict__ matS, const float2* __restrict__ qtab_,
-                   const float2* __restrict__ psi0p_, const float* __restrict__ x, int T, float A,
+                   const float2* __restrict__ psi0p_, const float* __restrict__ x, int T, AVal A_,
                    float* __restrict__ loss, double* __restrict__ lossd,
                    float2* __restrict__ traj, float* __restrict__ scales, int nchunks,
                    const float2* __restrict__ psi0v, int nvc, int m_steps) {
+  const float A = a_get(A_);
   using M = Map<DP, NQ>;
   using Sm = FwdSmemUni<DP, NQ>;
   constexpr int NT = M::NT;
@@ -805,12 +808,13 @@ template <int DP, int NQ, bool VIRT = false>
 __global__ void __launch_bounds__(DP* NQ)
     psi_bwd_uni_kernel(const float2* __restrict__ matN, const float2* __restrict__ matRH,
                    const float2* __restrict__ matS, const float2* __restrict__ qtab_,
-                   const float* __restrict__ ttab_, const float* __restrict__ x, int T, float A,
+                   const float* __restrict__ ttab_, const float* __restrict__ x, int T, AVal A_,
                    const float* __restrict__ w, const float2* __restrict__ traj,
                    const float* __restrict__ scales_, int nchunks, float2* __restrict__ Gout,
                    float* __restrict__ gfout, float2* __restrict__ lam0out,
                    double* __restrict__ gAdir, const float2* __restrict__ lam_end, int nvc,
                    int m_steps) {
+  const float A = a_get(A_);
   using M = Map<DP, NQ>;
   constexpr int NT = M::NT;
   constexpr int CPT = M::CPT;

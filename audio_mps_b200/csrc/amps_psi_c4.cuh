@@ -50,10 +50,11 @@ template <int DP, int CL, bool VIRT>
 __global__ void __launch_bounds__(512)
     psi_fwd_c4_kernel(const float2* __restrict__ matN, const float2* __restrict__ matR,
                       const float2* __restrict__ matS, const float2* __restrict__ qtab_,
-                      const float2* __restrict__ psi0p_, const float* __restrict__ x, int T, float A,
+                      const float2* __restrict__ psi0p_, const float* __restrict__ x, int T, AVal A_,
                       float* __restrict__ loss, double* __restrict__ lossd,
                       float2* __restrict__ traj, float* __restrict__ scales, int nchunks,
                       const float2* __restrict__ psi0v, int nvc, int m_steps) {
+  const float A = a_get(A_);
   using Cf = C4<DP, CL>;
   constexpr int NQ = Cf::NQ, CPT = Cf::CPT, RP = Cf::RP, NTL = Cf::NTL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -290,12 +291,13 @@ template <int DP, int CL, bool VIRT>
 __global__ void __launch_bounds__(512)
     psi_bwd_c4_kernel(const float2* __restrict__ matN, const float2* __restrict__ matRH,
                       const float2* __restrict__ matS, const float2* __restrict__ qtab_,
-                      const float* __restrict__ ttab_, const float* __restrict__ x, int T, float A,
+                      const float* __restrict__ ttab_, const float* __restrict__ x, int T, AVal A_,
                       const float* __restrict__ w, const float2* __restrict__ traj,
                       const float* __restrict__ scales_, int nchunks, float2* __restrict__ Gout,
                       float* __restrict__ gfout, float2* __restrict__ lam0out,
                       double* __restrict__ gAdir, const float2* __restrict__ lam_end, int nvc,
                       int m_steps) {
+  const float A = a_get(A_);
   using Cf = C4<DP, CL>;
   constexpr int NQ = Cf::NQ, CPT = Cf::CPT, NP = Cf::NP, RP = Cf::RP, NTL = Cf::NTL;
   extern __shared__ __align__(16) unsigned char smem_raw[];

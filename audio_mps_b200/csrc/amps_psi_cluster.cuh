@@ -36,10 +36,11 @@ template <int DP, int NQ>
 __global__ void __launch_bounds__(DP* NQ + 32)
     psi_fwd_cl_kernel(const float2* __restrict__ matN, const float2* __restrict__ matR,
                       const float2* __restrict__ matS, const float2* __restrict__ qtab,
-                      const float2* __restrict__ psi0p, const float* __restrict__ x, int T, float A,
+                      const float2* __restrict__ psi0p, const float* __restrict__ x, int T, AVal A_,
                       float* __restrict__ loss, double* __restrict__ lossd,
                       float2* __restrict__ traj, float* __restrict__ scales, int nchunks,
                       float2* __restrict__ sptraj, float2* __restrict__ evout) {
+  const float A = a_get(A_);
   using M = Map<DP, NQ>;
   using Sm = FwdClSmem<DP, NQ>;
   constexpr int NTC = M::NT;
@@ -312,12 +313,13 @@ template <int DP, int NQ>
 __global__ void __launch_bounds__(3 * DP * NQ)
     psi_bwd_cl_kernel(const float2* __restrict__ matN, const float2* __restrict__ matRH,
                       const float2* __restrict__ matS, const float2* __restrict__ qtab,
-                      const float* __restrict__ ttab, const float* __restrict__ x, int T, float A,
+                      const float* __restrict__ ttab, const float* __restrict__ x, int T, AVal A_,
                       const float* __restrict__ w, const float2* __restrict__ traj,
                       const float* __restrict__ scales, int nchunks, float2* __restrict__ Gout,
                       float* __restrict__ gfout, float2* __restrict__ lam0out,
                       double* __restrict__ gAdir, const float2* __restrict__ sptraj,
                       const float2* __restrict__ evin) {
+  const float A = a_get(A_);
   using M = Map<DP, NQ>;
   constexpr int NTC = M::NT;
   constexpr int CPT = M::CPT;

@@ -99,8 +99,9 @@ constexpr uint32_t TC_COL_X = 0, TC_COL_Z = 128, TC_COL_D = 256;
 constexpr int TC_THREADS = 512;
 __global__ void __launch_bounds__(TC_THREADS)
     psi_compose_tc_kernel(const float2* __restrict__ matN, const float2* __restrict__ matR,
-                          const float2* __restrict__ qtab, const float* __restrict__ x, int T, float A,
+                          const float2* __restrict__ qtab, const float* __restrict__ x, int T, AVal A_,
                           int nvc, int m_steps, float* __restrict__ opsT) {
+  const float A = a_get(A_);
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // SWIZZLE_128B operands need a 1024-byte aligned base (the launch reserves 1 KB of slack)
   unsigned char* smem_al = smem_raw + ((1024u - (tc_smem_u32(smem_raw) & 1023u)) & 1023u);

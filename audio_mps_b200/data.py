@@ -151,3 +151,59 @@ def get_audio(datadir, dataset, hps, sample_duration: int = 2 ** 16, rng=None):
     if dataset == "damped_sine":
         return damped_sine(hps.minibatch_size, sample_duration, hps.delta_t, rng)
     return tfrecord_batches(f"{datadir}/{dataset}.tfrecords", hps.minibatch_size, sample_duration)
+
+
+class DeviceBatchPrefetcher:
+    """Double-buffered host -> device staging of [B, T] float32 batches for the training loop: the
+    copy of the next batch (pinned host memory, its own CUDA stream) overlaps the scan kernels of
+    the current step; the compute stream only waits on the copy's event.
+
+        pf = DeviceBatchPrefetcher(device, (B, T))
+        pf.submit(first_host_batch)
+        for ...:
+            x = pf.next()                # device tensor, ready on the current stream
+            pf.submit(next_host_batch)   # starts copying while the step below runs
+            trainer.step(x)
+    """
+
+    def __init__(self, device, shape):
+        import torch
+        self._torch = torch
+        self.device = device
+        self._bufs = [torch.empty(shape, dtype=torch.float32, device=device) for _ in range(2)]
+        self._ready = [torch.cuda.Event() for _ in range(2)]
+        self._free = [torch.cuda.Event() for _ in range(2)]
+        self._stream = torch.cuda.Stream(device)
+        self._head = 0      # next buffer to fill
+        self._tail = 0      # next buffer to hand out
+        self._pending = 0
+
+    def submit(self, host_batch) -> None:
+        torch = self._torch
+        if self._pending >= 2:
+            raise RuntimeError("both staging buffers are in flight: call next() first")
+        if not host_batch.is_pinned():
+            host_batch = host_batch.pin_memory()
+        i = self._head
+        with torch.cuda.stream(self._stream):
+            self._stream.wait_event(self._free[i])          # the step that used this buffer is done
+            self._bufs[i].copy_(host_batch, non_blocking=True)
+            self._ready[i].record(self._stream)
+        self._head ^= 1
+        self._pending += 1
+
+    def next(self):
+        torch = self._torch
+        if self._pending == 0:
+            raise RuntimeError("no batch submitted")
+        i = self._tail
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self._ready[i])
+        self._tail ^= 1
+        self._pending -= 1
+        self._last = i
+        return self._bufs[i]
+
+    def release(self) -> None:
+        """Mark the batch handed out by the last next() as consumed (call after the step is enqueued)."""
+        self._free[self._last].record(self._torch.cuda.current_stream(self.device))

@@ -63,10 +63,12 @@ class _PsiLossFn(torch.autograd.Function):
         R_ri = R_ri.detach().contiguous().float()
         freqs = freqs.detach().contiguous().float()
         psi0_ri = psi0_ri.detach().contiguous().float()
-        a_val = float(A.detach())
+        # A goes down by device pointer: no host read-back (= stream sync) per training step
+        a_dev = A.detach().reshape(1).contiguous().float()
         p = _lib.AmpsParams(D=D, reserved=0, R_dev=R_ri.data_ptr(), freqs_dev=freqs.data_ptr(),
-                            psi0_dev=psi0_ri.data_ptr(), rho0_dev=None, A=a_val,
-                            sigma=float(model.sigma), delta_t=float(model.delta_t))
+                            psi0_dev=psi0_ri.data_ptr(), rho0_dev=None, A=0.0,
+                            sigma=float(model.sigma), delta_t=float(model.delta_t),
+                            A_dev=a_dev.data_ptr())
         # scan=True: the parallel-in-time tensor-core path (small batches, D <= 64)
         ws_bytes = lib.amps_psi_scan_workspace_bytes if scan else lib.amps_psi_workspace_bytes
         fwd = lib.amps_psi_loss_fwd_scan if scan else lib.amps_psi_loss_fwd
@@ -80,12 +82,12 @@ class _PsiLossFn(torch.autograd.Function):
                  1 if need_grad else 0, _stream(dev))
         _lib.check(h, rc)
         if need_grad:
-            ctx.keep = (R_ri, freqs, psi0_ri, x, ws, p, h, model, scan)
+            ctx.keep = (R_ri, freqs, psi0_ri, x, ws, p, h, model, scan, a_dev)
         return loss
 
     @staticmethod
     def backward(ctx, gloss):
-        R_ri, freqs, psi0_ri, x, ws, p, h, model, scan = ctx.keep
+        R_ri, freqs, psi0_ri, x, ws, p, h, model, scan, _a_dev = ctx.keep
         lib = _lib.load()
         dev = x.device
         B, T = x.shape

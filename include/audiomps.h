@@ -57,6 +57,10 @@ typedef struct amps_params {
   float A;                /* model.py:19 (trainable scalar, value at this step)             */
   float sigma;            /* model.py:21                                                    */
   double delta_t;         /* model.py:15 (python double; dt32 = (float)delta_t, model.py:16)*/
+  const float* A_dev;     /* optional: device float32 holding A; when non-NULL the Psi loss /
+                           * gradient / scan entry points read A from it and ignore `A`, so a
+                           * training loop never reads the parameter back to the host (the
+                           * sampler and the Rho entry points use the host value)          */
 } amps_params;
 
 /* ---- lifecycle ------------------------------------------------------------------------- */

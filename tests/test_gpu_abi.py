@@ -42,11 +42,19 @@ def test_host_entry_point_matches_oracle(cuda, lib):
 
 
 def test_error_codes(cuda, lib):
-    _, php = hp_pair(bond_dim=100)
+    _, php = hp_pair(bond_dim=129)                                  # loss / gradient cover D <= 128
     m = PsiCMPS(php, device=cuda)
     with pytest.raises(_lib.AmpsError) as e:
         m.loss_per_clip(np.zeros((2, 16), np.float32))
     assert e.value.code == -2                                       # AMPS_E_UNSUPPORTED
+    _, php = hp_pair(bond_dim=100)                                  # the sampler stops at D = 64
+    m = PsiCMPS(php, device=cuda)
+    with pytest.raises(_lib.AmpsError) as e:
+        m.sample(2, 16)
+    assert e.value.code == -2
+    with pytest.raises(_lib.AmpsError) as e:                        # ... and so does the tensor-core scan
+        m.loss_per_clip_scan(np.zeros((2, 16), np.float32))
+    assert e.value.code == -2
     h = _lib.context(0)
     _, php = hp_pair(bond_dim=8)
     m = PsiCMPS(php, device=cuda)
@@ -74,7 +82,7 @@ def test_edge_shapes(cuda, lib):
     set_raw(m, raw)
     # T = 1: no step at all -> loss 0, gradient 0
     l = m.loss_per_clip(np.zeros((3, 1), np.float32))
-    assert l.shape == (3,) and float(l.abs().max()) == 0.0
+    assert l.shape == (3,) and float(l.detach().abs().max()) == 0.0
     l.sum().backward()
     assert float(m.Rx.grad.abs().max()) == 0.0
     # chunk-boundary lengths (32-step chunks): 32, 33, 34, 64, 65 steps
