@@ -215,6 +215,23 @@ class CMPS(torch.nn.Module):
     TF_NAMES = {"A": "A", "Rx": "Rx", "Ry": "Ry", "freqs_raw": "freqs", "psi_x": "psi_x",
                 "psi_y": "psi_y", "Wx": "Wx", "Wy": "Wy"}
 
+    # ---- TensorFlow V2 checkpoints by the reference's variable names -------------
+    def save_tf_checkpoint(self, prefix: str, global_step: int = 0) -> None:
+        from . import tf_checkpoint as tfc
+        tfc.write_tf_checkpoint(prefix, tfc.model_to_tf_variables(self, global_step))
+
+    def load_tf_checkpoint(self, prefix_or_dir: str) -> int:
+        """Load `model/Rx, Ry, freqs, psi_x, psi_y | Wx, Wy, A` from a TF checkpoint prefix, or from
+        the latest checkpoint of a directory (its `checkpoint` state file); returns global_step."""
+        import os
+        from . import tf_checkpoint as tfc
+        prefix = prefix_or_dir
+        if os.path.isdir(prefix_or_dir):
+            prefix = tfc.latest_checkpoint(prefix_or_dir)
+            if prefix is None:
+                raise FileNotFoundError(f"no `checkpoint` state file in {prefix_or_dir}")
+        return tfc.load_tf_variables(self, tfc.read_tf_checkpoint(prefix))
+
     @property
     def R(self) -> torch.Tensor:
         """Effective complex R (model.py:41-42): R[i,j] - R[j,j] (the broadcast quirk)."""

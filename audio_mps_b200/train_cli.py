@@ -38,6 +38,10 @@ def main(argv=None):
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--save_checkpoint_secs", type=float, default=60.0)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--init_tf_checkpoint", default="",
+                    help="TensorFlow V2 checkpoint prefix or directory (the reference's logdir) to start from")
+    ap.add_argument("--save_tf_checkpoint", action="store_true",
+                    help="also write model.ckpt-<step> in TensorFlow V2 format at the end of the run")
     args = ap.parse_args(argv)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -60,6 +64,8 @@ def main(argv=None):
         os.makedirs(logdir, exist_ok=True)
     if os.path.exists(ckpt):                                        # MonitoredTrainingSession-style restore
         trainer.load_state_dict(torch.load(ckpt, map_location=dev))
+    elif args.init_tf_checkpoint:                                   # weights trained by the reference
+        trainer.global_step = model.load_tf_checkpoint(args.init_tf_checkpoint)
     rng = np.random.default_rng(args.seed + 1)
     source = get_audio(args.datadir, args.dataset, hp, sample_duration=args.sample_duration, rng=rng)
     gb = hp.minibatch_size
@@ -88,6 +94,8 @@ def main(argv=None):
                 last_save = time.time()
     if rank == 0:
         torch.save(trainer.state_dict(), ckpt)
+        if args.save_tf_checkpoint:
+            model.save_tf_checkpoint(os.path.join(logdir, f"model.ckpt-{trainer.global_step}"), trainer.global_step)
         if args.num_samples:
             w = model.sample(args.num_samples, args.sample_duration)                                 # train.py:83
             np.save(os.path.join(logdir, "samples.npy"), w.cpu().numpy())

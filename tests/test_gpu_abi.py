@@ -146,3 +146,13 @@ def test_train_cli_trains_and_resumes(cuda, lib, tmp_path):
     for mdl in ("rho_mps",):
         train_cli.main(["--mps_model=" + mdl, "--sample_duration=128", "--hparams=bond_dim=4,minibatch_size=2",
                         f"--logdir={tmp_path}/rho", "--steps=3", "--num_samples=0"])
+    # TensorFlow-format checkpoint out, and a fresh run initialised from it (by directory)
+    train_cli.main(argv[:4] + ["--steps=1", "--num_samples=0", "--save_tf_checkpoint"])
+    from audio_mps_b200 import tf_checkpoint as tfc
+    prefix = tfc.latest_checkpoint(str(logdir))
+    got = tfc.read_tf_checkpoint(prefix)
+    assert int(got["global_step"]) == 9 and got["model/Rx"].shape == (8, 8)
+    train_cli.main(argv[:3] + [f"--logdir={tmp_path}/fromtf", f"--init_tf_checkpoint={logdir}", "--steps=1",
+                               "--num_samples=0"])
+    recs2 = [json.loads(l) for l in open(tmp_path / "fromtf" / "damped_sine" / f"8_{1/16000}_4" / "scalars.jsonl")]
+    assert recs2[0]["step"] == 10

@@ -160,3 +160,67 @@ def test_shard_bounds():
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
         sizes = [hi - lo for lo, hi in spans]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_tf_checkpoint_round_trip(tmp_path):
+    """TensorFlow V2 checkpoint (tensor bundle) writer/reader: table structure, checksums, names."""
+    import struct
+    from audio_mps_b200 import tf_checkpoint as tfc
+    assert tfc.crc32c(b"123456789") == 0xE3069283                    # CRC-32C check value
+    rng = np.random.default_rng(0)
+    tensors = {"model/Rx": rng.standard_normal((7, 7)).astype(np.float32),
+               "model/Ry": rng.standard_normal((7, 7)).astype(np.float32),
+               "model/freqs": rng.standard_normal(7).astype(np.float32),
+               "model/psi_x": rng.standard_normal(7).astype(np.float32),
+               "model/psi_y": rng.standard_normal(7).astype(np.float32),
+               "model/A": np.float32(100.0), "global_step": np.int64(1617),
+               "model/Rx/Adam": np.zeros((7, 7), np.float32), "beta1_power": np.float32(0.9)}
+    for i in range(40):                                              # several restart intervals
+        tensors[f"extra/v{i:02d}"] = rng.standard_normal(3).astype(np.float32)
+    prefix = str(tmp_path / "model.ckpt-1617")
+    tfc.write_tf_checkpoint(prefix, tensors)
+    idx = open(prefix + ".index", "rb").read()
+    assert struct.unpack("<Q", idx[-8:])[0] == 0xDB4775248B80FB57    # LevelDB table magic
+    back = tfc.read_tf_checkpoint(prefix)
+    assert set(back) == set(tensors)
+    for k, v in tensors.items():
+        assert back[k].dtype == np.asarray(v).dtype and np.array_equal(back[k], np.asarray(v)), k
+    assert tfc.latest_checkpoint(str(tmp_path)) == prefix
+    # corruption is detected
+    bad = bytearray(open(prefix + ".data-00000-of-00001", "rb").read())
+    bad[5] ^= 0xFF
+    open(prefix + ".data-00000-of-00001", "wb").write(bytes(bad))
+    with pytest.raises(ValueError):
+        tfc.read_tf_checkpoint(prefix)
+
+
+def test_tf_checkpoint_state_file_of_the_reference(tmp_path):
+    """`checkpoint` state files as TF writes them (the layout of /root/reference/logging/checkpoint)."""
+    from audio_mps_b200 import tf_checkpoint as tfc
+    (tmp_path / "checkpoint").write_text('model_checkpoint_path: "model.ckpt-1617"\n'
+                                         'all_model_checkpoint_paths: "model.ckpt-1436"\n'
+                                         'all_model_checkpoint_paths: "model.ckpt-1617"\n')
+    assert tfc.latest_checkpoint(str(tmp_path)) == str(tmp_path / "model.ckpt-1617")
+    assert tfc.latest_checkpoint(str(tmp_path / "nothing")) is None
+
+
+def test_model_tf_checkpoint_names(tmp_path):
+    """Psi and Rho models save / load under the reference's variable names (model.py:19,32-50,122-126,
+    215-219; scope "model", train.py:49)."""
+    from audio_mps_b200 import HParams, PsiCMPS, RhoCMPS, tf_checkpoint as tfc
+    hp = HParams(minibatch_size=2, bond_dim=5, delta_t=1 / 16000, sigma=1e-4, h_reg=1e-9, r_reg=0.1,
+                 initial_rank=3, A=100., learning_rate=1e-3)
+    for cls, names in ((PsiCMPS, {"A", "Rx", "Ry", "freqs", "psi_x", "psi_y"}),
+                       (RhoCMPS, {"A", "Rx", "Ry", "freqs", "Wx", "Wy"})):
+        m = cls(hp, device="cpu", seed=1)
+        prefix = str(tmp_path / cls.__name__ / "model.ckpt-7")
+        m.save_tf_checkpoint(prefix, global_step=7)
+        got = tfc.read_tf_checkpoint(prefix)
+        assert set(got) == {"model/" + n for n in names} | {"global_step"}
+        m2 = cls(hp, device="cpu", seed=2)
+        assert m2.load_tf_checkpoint(str(tmp_path / cls.__name__)) == 7     # via the state file
+        for (n, a), (_, b) in zip(m.named_parameters(), m2.named_parameters()):
+            assert torch.equal(a, b), n
+    with pytest.raises(ValueError):                                  # shape mismatch is an error
+        PsiCMPS(HParams(**{**hp.values(), "bond_dim": 6}), device="cpu").load_tf_checkpoint(
+            str(tmp_path / "PsiCMPS" / "model.ckpt-7"))
