@@ -252,6 +252,21 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned coun
 __device__ __forceinline__ void mbar_fence_init_cluster() {
   asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
 }
+// local arrive that also announces `bytes` of st.async traffic for the current phase
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(a), "r"(bytes) : "memory");
+}
+// predicated 8-byte store into (possibly another) CTA's shared memory that completes `8` bytes on the
+// mbarrier `mbar_addr` of the SAME target CTA (both shared::cluster addresses): data and signal in one
+// instruction, no release fence / cluster barrier on the sender's critical path.
+__device__ __forceinline__ void st_async_f2_if(bool on, unsigned addr, float2 v, unsigned mbar_addr) {
+  asm volatile(
+      "{\n\t.reg .pred pp;\n\tsetp.ne.b32 pp, %0, 0;\n\t"
+      "@pp st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%1], {%2, %3}, [%4];\n\t}\n" ::"r"((int)on),
+      "r"(addr), "f"(v.x), "f"(v.y), "r"(mbar_addr)
+      : "memory");
+}
 // arrive (release, cluster scope) on an mbarrier that lives in another CTA of the cluster
 __device__ __forceinline__ void mbar_arrive_remote(unsigned remote_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(remote_addr) : "memory");

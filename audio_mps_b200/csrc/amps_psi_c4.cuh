@@ -42,6 +42,7 @@ struct alignas(16) FwdC4Smem {
   float sv[2][CH4 + 4];
   float incv[2][CH4];
   double lred[16];
+  unsigned long long xbar[2];         // "step s's broadcast has fully arrived", by step parity
 };
 
 // grid = CL * (number of clips or virtual clips), cluster = CL, block = 512.
@@ -110,9 +111,19 @@ __global__ void __launch_bounds__(512)
 
   // per-step broadcast: lane jq < CL writes x_{k+1,i} into CTA jq, lane CL <= jq < 2CL writes
   // x'_{k,i} into CTA jq - CL (own CTA included: one code path, no local store).
+  // Data and completion travel together: st.async ... mbarrier::complete_tx on the TARGET's xbar[s & 1];
+  // the consumer waits on its own mbarrier, so no barrier.cluster sits on the per-step critical path.
   const bool st_on = jq < 2 * CL, st_x = jq < CL;
   const unsigned st_addr0 = dsmem_addr(st_x ? (const void*)&sm.xs[1][i] : (const void*)&sm.xps[0][i],
                                        (unsigned)(jq & (CL - 1)));
+  const unsigned st_bar0 = dsmem_addr(&sm.xbar[0], (unsigned)(jq & (CL - 1)));
+  constexpr unsigned STEP_TX = 2 * DP * sizeof(float2);   // x_{k+1} and x'_k, all rows
+  if (t == 0) {
+    mbar_init(&sm.xbar[0], 1);
+    mbar_init(&sm.xbar[1], 1);
+    mbar_fence_init_cluster();
+  }
+  int sg = 0;   // steps taken so far by this (virtual) clip: barrier index sg & 1, phase (sg >> 1) & 1
 
   double lossacc = 0.0;
   if (nchunks > 0) {
@@ -138,6 +149,8 @@ __global__ void __launch_bounds__(512)
 
     auto step = [&](auto first_tag, int kk) {
       constexpr bool FIRST = decltype(first_tag)::value;
+      if (t == 0) mbar_arrive_expect_tx(&sm.xbar[sg & 1], STEP_TX);          // arm this step's phase
+      if (!FIRST) mbar_wait(&sm.xbar[(sg - 1) & 1], ((sg - 1) >> 1) & 1);    // previous step's rows are in
       float2 xv[CPT], pv[CPT];
 #pragma unroll
       for (int m = 0; m < CPT / 2; ++m) {
@@ -185,11 +198,12 @@ __global__ void __launch_bounds__(512)
         xp.y += oy;
       }
       const float2 xn = cmul(q, xp);
-      st_dsmem_f2_if(st_on, st_addr0 + (unsigned)(kk * DP * (int)sizeof(float2)), st_x ? xn : xp);
+      st_async_f2_if(st_on, st_addr0 + (unsigned)(kk * DP * (int)sizeof(float2)), st_x ? xn : xp,
+                     st_bar0 + (unsigned)((sg & 1) * sizeof(unsigned long long)));
       if (!FIRST) sm.es[kk - 1][t] = fmaf(xp_prev.x, p0.x + p1.x, xp_prev.y * (p0.y + p1.y));
       xp_prev = xp;
       s_cur = s_next;
-      cluster_sync_all();
+      ++sg;
     };
 
     step(TrueT{}, 0);
@@ -199,6 +213,7 @@ __global__ void __launch_bounds__(512)
     } else {
       for (int kk = 1; kk < len; ++kk) step(FalseT{}, kk);
     }
+    mbar_wait(&sm.xbar[(sg - 1) & 1], ((sg - 1) >> 1) & 1);   // the chunk's last broadcast has landed
     {  // expectation partial of the chunk's last step
       const float2 part = matvec1<DP, NQ>(Sr, sm.xps[len - 1], jq);
       sm.es[len - 1][t] = fmaf(xp_prev.x, part.x, xp_prev.y * part.y);
@@ -284,6 +299,7 @@ struct alignas(16) BwdC4Smem {
   float scs[3][4];
   float sv[2][CH4], incv[2][CH4], dtk[2][CH4], alphas[2][CH4], betas[2][CH4];
   double lred[16];
+  unsigned long long mbar[2];  // "mu broadcast number p has fully arrived", by parity of p
 };
 
 // Adjoint backward, same recursion and outputs as psi_bwd_uni_kernel; rows split over the cluster.
@@ -419,6 +435,11 @@ __global__ void __launch_bounds__(512)
   float2 lam = make_float2(0.f, 0.f);  // adjoint of x_{k+1,i}, replicated over the NQ lanes
   if (VIRT) if (lam_end) lam = lam_end[(size_t)b * DP + i];
   float gf = 0.f;
+  if (t == 0) {
+    mbar_init(&sm.mbar[0], 1);
+    mbar_init(&sm.mbar[1], 1);
+    mbar_fence_init_cluster();
+  }
 
   if (nchunks > 0) {
     const int cl = nchunks - 1;
@@ -438,10 +459,12 @@ __global__ void __launch_bounds__(512)
     prep_totals(cl);
   }
 
-  // lanes jq < CL broadcast mu_{k,i} into CTA jq
+  // lanes jq < CL broadcast mu_{k,i} into CTA jq: st.async completing on the target's mbar[p & 1]
   const bool mu_on = jq < CL;
   const unsigned mu_addr0 = dsmem_addr(&sm.mus[0][i], (unsigned)(jq & (CL - 1)));
+  const unsigned mu_bar0 = dsmem_addr(&sm.mbar[0], (unsigned)(jq & (CL - 1)));
   constexpr unsigned MU_ROW = DP * sizeof(float2);
+  int pg = 0;   // mu broadcasts so far: barrier index pg & 1, phase (pg >> 1) & 1
 
   for (int c = nchunks - 1; c >= 0; --c) {
     const int lb = c % 3, ds = c & 1;
@@ -465,12 +488,17 @@ __global__ void __launch_bounds__(512)
       const float2 sp = sm.sps[ds][kk][il];
       mu.x = fmaf(al, sp.x, mu.x * sc);
       mu.y = fmaf(al, sp.y, mu.y * sc);
-      st_dsmem_f2_if(mu_on, mu_addr0 + (unsigned)kk * MU_ROW, mu);
+      if (t == 0) mbar_arrive_expect_tx(&sm.mbar[pg & 1], MU_ROW);
+      st_async_f2_if(mu_on, mu_addr0 + (unsigned)kk * MU_ROW, mu,
+                     mu_bar0 + (unsigned)((pg & 1) * sizeof(unsigned long long)));
+      ++pg;
     }
-    cluster_sync_all();   // (T2) mu of the last step everywhere; x' of chunk c-1 visible
+    __syncthreads();      // (T2) x' of chunk c-1 visible (the mu broadcast is awaited per step)
 
     auto step = [&](auto prev_tag, int kk) {
       constexpr bool PREV = decltype(prev_tag)::value;     // chunk c-1 exists (expectation filler)
+      if (t == 0 && kk > 0) mbar_arrive_expect_tx(&sm.mbar[pg & 1], MU_ROW);   // arm this step's broadcast
+      mbar_wait(&sm.mbar[(pg - 1) & 1], ((pg - 1) >> 1) & 1);                  // mu_kk is in
       float2 mv[CPT];
 #pragma unroll
       for (int m = 0; m < NP; ++m) {
@@ -539,8 +567,9 @@ __global__ void __launch_bounds__(512)
         mu.x = fmaf(al1, sp1.x, mu.x);
         mu.y = fmaf(al1, sp1.y, mu.y);
       }
-      st_dsmem_f2_if(mu_on && kk > 0, mu_addr0 + (unsigned)km * MU_ROW, mu);
-      cluster_sync_all();
+      st_async_f2_if(mu_on && kk > 0, mu_addr0 + (unsigned)km * MU_ROW, mu,
+                     mu_bar0 + (unsigned)((pg & 1) * sizeof(unsigned long long)));
+      if (kk > 0) ++pg;
     };
 
     if (has_prev) {
