@@ -106,7 +106,7 @@ def test_psi_sample_from_noise(cuda, lib, D, n, L, over):
     assert rel(got, ref) <= SAMPLE_TOL
 
 
-@pytest.mark.parametrize("D,B,T", [(7, 8, 256), (32, 2, 100)])
+@pytest.mark.parametrize("D,B,T", [(7, 8, 256), (32, 2, 100), (64, 2, 70), (100, 2, 60)])
 def test_psi_evolve(cuda, lib, D, B, T):
     ohp, raw, data, model = build(D, B, T, dict(), cuda)
     ref = PsiCMPSOracle(ohp, raw, mode="f64").psi_evolve_with_data(data).detach().numpy()
