@@ -658,7 +658,7 @@ int amps_psi_loss_fwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
     PROF_BEGIN(ctx, 2, st);
     psi_compose_tc_kernel<<<nv, TC_THREADS, smem, st>>>((const float2*)(ws + L.base.matN), (const float2*)(ws + L.base.matR),
                                                  (const float2*)(ws + L.base.qtab), x_dev, T, aval(p), L.nvc,
-                                                 L.m_steps, (float*)(ws + L.ops));
+                                                 L.m_steps, (float*)(ws + L.ops), p->D);
     PROF_END(ctx, 2, st);
     LAUNCH_CHECK(ctx, "psi_compose_tc_kernel");
   }

@@ -100,8 +100,11 @@ constexpr int TC_THREADS = 512;
 __global__ void __launch_bounds__(TC_THREADS)
     psi_compose_tc_kernel(const float2* __restrict__ matN, const float2* __restrict__ matR,
                           const float2* __restrict__ qtab, const float* __restrict__ x, int T, AVal A_,
-                          int nvc, int m_steps, float* __restrict__ opsT) {
+                          int nvc, int m_steps, float* __restrict__ opsT, int D) {
   const float A = a_get(A_);
+  // D <= 32: E_k is zero outside rows/columns [0,32) of each real-form quadrant, i.e. K blocks 1 and 3
+  // of the B operand never change from zero -- they are neither re-formed nor multiplied.
+  const int Dq = (D <= 32) ? 32 : TC_D;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // SWIZZLE_128B operands need a 1024-byte aligned base (the launch reserves 1 KB of slack)
   unsigned char* smem_al = smem_raw + ((1024u - (tc_smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -120,6 +123,12 @@ __global__ void __launch_bounds__(TC_THREADS)
     if (a == c) n.x -= 1.0f;          // c' R^dag R = N - I (exact for N_aa ~ 1)
     sm.cM[a][c] = n;
     sm.Rm[a][c] = matR[idx];
+  }
+  if (Dq < TC_D) {
+    for (int idx = tid; idx < TC_NKB * TC_TILE / 16; idx += TC_THREADS) {
+      reinterpret_cast<float4*>(sm.bhi)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+      reinterpret_cast<float4*>(sm.blo)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
   if (tid == 0) {
     mbar_init(&sm.mbar, 1);
@@ -163,8 +172,9 @@ __global__ void __launch_bounds__(TC_THREADS)
         if (pt < TC_D) sm.qv[kk & 1][pt] = qb[(size_t)kk * TC_D + pt];
         // one thread per (row a, 4 consecutive columns b): the complex element is computed once and
         // written to its four real-form positions  [ Er -Ei ; Ei Er ], hi and lo
-        for (int idx = pt; idx < TC_D * (TC_D / 4); idx += TC_THREADS - 128) {
-          const int a = idx / (TC_D / 4), c = idx % (TC_D / 4);           // c: 16-byte chunk within [0, D)
+        const int cq = Dq / 4;
+        for (int idx = pt; idx < Dq * cq; idx += TC_THREADS - 128) {
+          const int a = idx / cq, c = idx % cq;                           // c: 16-byte chunk within [0, D)
           float er[4], ei[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -239,6 +249,7 @@ __global__ void __launch_bounds__(TC_THREADS)
         const uint8_t* bsm = (pass == 2) ? sm.blo : sm.bhi;
 #pragma unroll 1
         for (int kb = 0; kb < TC_NKB; ++kb) {
+          if (Dq < TC_D && (kb & 1)) continue;          // all-zero K block of E_k^T
           const uint64_t db0 = tc_make_desc(tc_smem_u32(bsm + kb * TC_TILE));
 #pragma unroll
           for (int ks = 0; ks < TC_KB / 8; ++ks)      // UMMA_K = 8 tf32: 8 TMEM columns / 32 smem bytes
