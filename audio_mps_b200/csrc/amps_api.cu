@@ -654,11 +654,12 @@ int amps_psi_loss_fwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
   const int nv = B * L.nvc;
   {
     const size_t smem = sizeof(ScanTcSmem) + 1024;
-    CUDA_TRY(ctx, cudaFuncSetAttribute(psi_compose_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kcomp = p->D <= 32 ? psi_compose_tc_kernel<true> : psi_compose_tc_kernel<false>;
+    CUDA_TRY(ctx, cudaFuncSetAttribute(kcomp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PROF_BEGIN(ctx, 2, st);
-    psi_compose_tc_kernel<<<nv, TC_THREADS, smem, st>>>((const float2*)(ws + L.base.matN), (const float2*)(ws + L.base.matR),
-                                                 (const float2*)(ws + L.base.qtab), x_dev, T, aval(p), L.nvc,
-                                                 L.m_steps, (float*)(ws + L.ops), p->D);
+    kcomp<<<nv, TC_THREADS, smem, st>>>((const float2*)(ws + L.base.matN), (const float2*)(ws + L.base.matR),
+                                        (const float2*)(ws + L.base.qtab), x_dev, T, aval(p), L.nvc,
+                                        L.m_steps, (float*)(ws + L.ops));
     PROF_END(ctx, 2, st);
     LAUNCH_CHECK(ctx, "psi_compose_tc_kernel");
   }
@@ -714,10 +715,13 @@ int amps_psi_loss_bwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
   const double cprime = -p->delta_t * (double)p->sigma * (double)p->sigma / 2.0;
   psi_scan_expand_w_kernel<<<(nv + 127) / 128, 128, 0, st>>>(w_dev, B, L.nvc, (float*)(ws + L.wv));
   LAUNCH_CHECK(ctx, "psi_scan_expand_w_kernel");
-  auto kern = psi_bwd_uni_kernel<64, 8, true>;
+  auto kern_chain = psi_bwd_uni_kernel<64, 8, true, false>;   // pass 1: adjoint chain only
+  auto kern_full = psi_bwd_uni_kernel<64, 8, true, true>;     // pass 2: chain + gradient tiles
   const size_t smem = sizeof(BwdSmemUni<64>);
-  CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(kern_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(kern_full, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   auto adjoint_pass = [&](const float2* lam_end) {
+    auto kern = lam_end ? kern_full : kern_chain;
     kern<<<nv, 64 * 8, smem, st>>>((const float2*)(ws + L.base.matN), (const float2*)(ws + L.base.matRH),
                                    (const float2*)(ws + L.base.matS), (const float2*)(ws + L.base.qtab),
                                    (const float*)ctx->ttab, x_dev, T, aval(p), w_dev,

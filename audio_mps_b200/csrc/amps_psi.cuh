@@ -804,7 +804,9 @@ __global__ void __launch_bounds__(DP* NQ)
 // VIRT: virtual-clip mode of the parallel-in-time scan: block b runs the adjoint of time chunk
 // (b % nvc) of clip (b / nvc) over the trajectory the VIRT forward stored for it, starting from the
 // adjoint lam_end[b] of the chunk's (normalised) end state (zero when lam_end is NULL).
-template <int DP, int NQ, bool VIRT = false>
+// TILES = false: adjoint chain only (no gradient tiles) -- the first pass of the scan backward, which
+// needs nothing but the adjoint of each chunk's start state.
+template <int DP, int NQ, bool VIRT = false, bool TILES = true>
 __global__ void __launch_bounds__(DP* NQ)
     psi_bwd_uni_kernel(const float2* __restrict__ matN, const float2* __restrict__ matRH,
                    const float2* __restrict__ matS, const float2* __restrict__ qtab_,
@@ -1015,7 +1017,7 @@ __global__ void __launch_bounds__(DP* NQ)
       float ox = __shfl_xor_sync(0xffffffffu, lp.x, 1);
       float oy = __shfl_xor_sync(0xffffffffu, lp.y, 1);
       // ---- filler 1: rank-1 tiles of step kk (mu_k is in registers) ---------------------
-      {
+      if (TILES) {
         const float2 xpi = sm.xps[ds][kk][i];
         const float al = sm.alphas[ds][kk];
         const float2 u1 = make_float2(s * mu.x, s * mu.y);
@@ -1072,13 +1074,15 @@ __global__ void __launch_bounds__(DP* NQ)
   cp_async_wait<0>();
 
   // ---- per-clip outputs -------------------------------------------------------------------
-  float2* Gb = Gout + (size_t)b * 3 * DP * DP;
+  if (TILES) {
+    float2* Gb = Gout + (size_t)b * 3 * DP * DP;
 #pragma unroll
-  for (int c = 0; c < CPT; ++c) {
-    const int col = M::col(c, jq);
-    Gb[0 * DP * DP + i * DP + col] = GR[c];
-    Gb[1 * DP * DP + i * DP + col] = GN[c];
-    Gb[2 * DP * DP + i * DP + col] = GE[c];
+    for (int c = 0; c < CPT; ++c) {
+      const int col = M::col(c, jq);
+      Gb[0 * DP * DP + i * DP + col] = GR[c];
+      Gb[1 * DP * DP + i * DP + col] = GN[c];
+      Gb[2 * DP * DP + i * DP + col] = GE[c];
+    }
   }
   if (jq == 0) {
     gfout[(size_t)b * DP + i] = gf;

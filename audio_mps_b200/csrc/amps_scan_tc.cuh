@@ -97,14 +97,15 @@ constexpr uint32_t TC_COL_X = 0, TC_COL_Z = 128, TC_COL_D = 256;
 // grid = B * nvc CTAs, block = 512 threads: warps 0-3 own the 128 TMEM lanes (epilogue),
 // warps 4-15 form E_k in shared memory; thread 0 issues the MMAs.
 constexpr int TC_THREADS = 512;
+// HALF (bond dimension <= 32): E_k is zero outside rows/columns [0,32) of each real-form quadrant, i.e.
+// K blocks 1 and 3 of the B operand never change from zero -- they are neither re-formed nor multiplied.
+template <bool HALF>
 __global__ void __launch_bounds__(TC_THREADS)
     psi_compose_tc_kernel(const float2* __restrict__ matN, const float2* __restrict__ matR,
                           const float2* __restrict__ qtab, const float* __restrict__ x, int T, AVal A_,
-                          int nvc, int m_steps, float* __restrict__ opsT, int D) {
+                          int nvc, int m_steps, float* __restrict__ opsT) {
   const float A = a_get(A_);
-  // D <= 32: E_k is zero outside rows/columns [0,32) of each real-form quadrant, i.e. K blocks 1 and 3
-  // of the B operand never change from zero -- they are neither re-formed nor multiplied.
-  const int Dq = (D <= 32) ? 32 : TC_D;
+  constexpr int Dq = HALF ? 32 : TC_D;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // SWIZZLE_128B operands need a 1024-byte aligned base (the launch reserves 1 KB of slack)
   unsigned char* smem_al = smem_raw + ((1024u - (tc_smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(TC_THREADS)
         if (pt < TC_D) sm.qv[kk & 1][pt] = qb[(size_t)kk * TC_D + pt];
         // one thread per (row a, 4 consecutive columns b): the complex element is computed once and
         // written to its four real-form positions  [ Er -Ei ; Ei Er ], hi and lo
-        const int cq = Dq / 4;
+        constexpr int cq = Dq / 4;
         for (int idx = pt; idx < Dq * cq; idx += TC_THREADS - 128) {
           const int a = idx / cq, c = idx % cq;                           // c: 16-byte chunk within [0, D)
           float er[4], ei[4];
