@@ -83,3 +83,26 @@ def test_time_parallel_policy(cuda, lib):
     _, php32 = hp_pair(bond_dim=32, minibatch_size=1)
     m32 = PsiCMPS(php32, device=cuda)
     assert m32._use_scan(4, 64000, True) and not m32._use_scan(8, 64000, True)
+
+
+@pytest.mark.parametrize("T", [1, 2, 3, 33])
+def test_scan_degenerate_lengths(cuda, lib, T):
+    """T = 1 (no step), a single step, and lengths around one chunk, through the scan entry points."""
+    D, B = 16, 2
+    ohp, php = hp_pair(bond_dim=D, minibatch_size=B)
+    raw = random_raw_params(ohp, np.random.default_rng(3))
+    data = damped_sine(B, max(T, 2), ohp.delta_t, np.random.default_rng(4))[:, :T]
+    m = PsiCMPS(php, device=cuda)
+    set_raw(m, raw)
+    ps = [getattr(m, n) for n in NAMES]
+    l_scan = m.loss_per_clip(data, time_parallel=True)
+    l_seq = m.loss_per_clip(data, time_parallel=False)
+    assert l_scan.shape == (B,)
+    if T == 1:
+        assert float(l_scan.detach().abs().max()) == 0.0
+        return
+    assert rel(l_scan.detach().cpu().numpy(), l_seq.detach().cpu().numpy()) <= 1e-4
+    g_scan = torch.autograd.grad(l_scan.mean(), ps)
+    g_seq = torch.autograd.grad(l_seq.mean(), ps)
+    for n, a, b in zip(NAMES, g_scan, g_seq):
+        assert rel(a.cpu().numpy(), b.cpu().numpy()) <= 1e-3, n
