@@ -76,3 +76,18 @@ if "c3" in which:   # D=128, 128 clips, 4 s clips: row-split 4-CTA cluster kerne
               f"fwd {f*1e-3/T*1.965e9/max(1,-(-B*4//148)):.0f} cyc/step/wave, bwd {bw*1e-3/T*1.965e9/max(1,-(-B*4//148)):.0f}")
         del m, x
         torch.cuda.empty_cache()
+if "big" in which:   # batches beyond one clip per SM pair, D=32 (warp-specialised single-CTA kernels)
+    D, T = 32, 16000
+    for B in (64, 74, 148, 296, 592, 1184):
+        m = PsiCMPS(hp(D, B), device=dev, seed=0)
+        x = torch.from_numpy(damped_sine(B, T, 1 / 16000, np.random.default_rng(1))).to(dev)
+        _lib.set_profiling(0, True)
+
+        def stepb():
+            m.zero_grad()
+            m.loss_fn(x).backward()
+        ms = timed(stepb, reps=2)
+        print(f"big D={D} B={B} T={T}: step {ms:.1f} ms (fwd kernel {_lib.kernel_ms(0,0):.1f}, bwd kernel {_lib.kernel_ms(0,1):.1f}) "
+              f"-> {B*T/ms*1e3:.3e} samples/s")
+        del m, x
+        torch.cuda.empty_cache()
