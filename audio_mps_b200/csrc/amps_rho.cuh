@@ -70,7 +70,7 @@ struct RhoArgs {
 };
 
 template <bool SAMPLE>
-__global__ void rho_scan_kernel(RhoArgs g) {
+__global__ void __launch_bounds__(RHO_MAX_D * RHO_MAX_D) rho_scan_kernel(RhoArgs g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int D = g.D, DD = D * D;
   float2* rho = reinterpret_cast<float2*>(smem_raw);  // [D][D] frame density matrix
@@ -235,7 +235,8 @@ struct RhoBwdArgs {
   double* gAdir;        // [B]
 };
 
-__global__ void rho_bwd_kernel(RhoBwdArgs g) {
+// launch bounds: D = 32 runs 1024 threads, i.e. at most 64 registers per thread
+__global__ void __launch_bounds__(RHO_MAX_D * RHO_MAX_D) rho_bwd_kernel(RhoBwdArgs g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int D = g.D, DD = D * D;
   float2* rho = reinterpret_cast<float2*>(smem_raw);

@@ -118,7 +118,8 @@ def test_psi_evolve(cuda, lib, D, B, T):
 
 
 @pytest.mark.parametrize("D,B,T,over", [(7, 8, 256, dict(h_reg=2 / (np.pi * 16000) ** 2, r_reg=2 / (np.pi * 16000))),
-                                        (8, 3, 500, dict()), (2, 2, 64, dict(sigma=1.0, A=1.0))])
+                                        (8, 3, 500, dict()), (2, 2, 64, dict(sigma=1.0, A=1.0)),
+                                        (32, 2, 60, dict())])
 def test_rho_loss_and_traj(cuda, lib, D, B, T, over):
     ohp, php = hp_pair(bond_dim=D, minibatch_size=B, **over)
     raw = random_raw_params(ohp, np.random.default_rng(5), rho=True)
@@ -153,7 +154,7 @@ def test_rho_sampling(cuda, lib):
 
 @pytest.mark.parametrize("D,B,T,over", [(7, 8, 256, dict(h_reg=2 / (np.pi * 16000) ** 2, r_reg=2 / (np.pi * 16000))),
                                         (4, 3, 150, dict(sigma=0.3, A=3.0)), (8, 2, 700, dict()),
-                                        (16, 2, 120, dict())])
+                                        (16, 2, 120, dict()), (32, 2, 40, dict()), (29, 1, 33, dict())])
 def test_rho_grads_raw(cuda, lib, D, B, T, over):
     """Gradient of the regularised rho loss wrt the raw variables (train.py:49-60 with rho_mps)."""
     ohp, php = hp_pair(bond_dim=D, minibatch_size=B, **over)
