@@ -72,18 +72,20 @@ struct RhoArgs {
 template <bool SAMPLE>
 __global__ void __launch_bounds__(RHO_MAX_D * RHO_MAX_D) rho_scan_kernel(RhoArgs g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int D = g.D, DD = D * D;
+  // shared matrices have row stride LD = D + 1: column-indexed reads (X[c * LD + m], consecutive c per
+  // lane) then hit distinct banks instead of a D-way conflict
+  const int D = g.D, DD = D * D, LD = D + 1, DL = D * LD;
   float2* rho = reinterpret_cast<float2*>(smem_raw);  // [D][D] frame density matrix
-  float2* Lm = rho + DD;                              // L = N + s R
-  float2* Y = Lm + DD;                                // L rho
-  float2* qv = Y + DD;                                // [D] q_k
+  float2* Lm = rho + DL;                              // L = N + s R
+  float2* Y = Lm + DL;                                // L rho
+  float2* qv = Y + DL;                                // [D] q_k
   float2* pv = qv + D;                                // [D] p_{k+1}
   float* red = reinterpret_cast<float*>(pv + D);      // [32][2]
 
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
   const int b = blockIdx.x;
   const bool act = t < DD;
-  const int a = act ? t / D : 0, c = act ? t % D : 0;
+  const int a = act ? t / D : 0, c = act ? t % D : 0, ts = a * LD + c;
   const int nsteps = SAMPLE ? g.L : g.T - 1;
 
   // this thread's elements of R, N, S
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(RHO_MAX_D * RHO_MAX_D) rho_scan_kernel(RhoArgs
       mi += (double)u.x * v.y - (double)u.y * v.x;
     }
     Nab = make_float2((float)((a == c ? 1.0 : 0.0) + g.cprime * mr), (float)(g.cprime * mi));
-    rho[t] = g.rho0[t];
+    rho[ts] = g.rho0[t];
     if (!SAMPLE && g.ftraj) g.ftraj[(size_t)b * g.T * DD + t] = g.rho0[t];
   }
   float X = 0.f;
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(RHO_MAX_D * RHO_MAX_D) rho_scan_kernel(RhoArgs
       // E on the current normalised rho (model.py:162)
       float e = 0.f, dummy = 0.f;
       if (act) {
-        const float2 r = rho[t];  // rho_ab, pairs with S_ba
+        const float2 r = rho[ts];  // rho_ab, pairs with S_ba
         e = Sba.x * r.x - Sba.y * r.y;
       }
       float E, d2;
@@ -156,18 +158,18 @@ __global__ void __launch_bounds__(RHO_MAX_D * RHO_MAX_D) rho_scan_kernel(RhoArgs
       inc = xb[k + 1] - xb[k];
     }
     const float s = inc / g.A;
-    if (act) Lm[t] = make_float2(fmaf(s, Rab.x, Nab.x), fmaf(s, Rab.y, Nab.y));
+    if (act) Lm[ts] = make_float2(fmaf(s, Rab.x, Nab.x), fmaf(s, Rab.y, Nab.y));
     __syncthreads();
     if (act) {
       float2 acc = make_float2(0.f, 0.f);
-      for (int m = 0; m < D; ++m) cmac(acc, Lm[a * D + m], rho[m * D + c]);
-      Y[t] = acc;
+      for (int m = 0; m < D; ++m) cmac(acc, Lm[a * LD + m], rho[m * LD + c]);
+      Y[ts] = acc;
     }
     __syncthreads();
     float2 rp = make_float2(0.f, 0.f);
     float e = 0.f, tr = 0.f;
     if (act) {
-      for (int m = 0; m < D; ++m) cmac_cx(rp, Y[a * D + m], Lm[c * D + m]);
+      for (int m = 0; m < D; ++m) cmac_cx(rp, Y[a * LD + m], Lm[c * LD + m]);
       e = Sba.x * rp.x - Sba.y * rp.y;  // Re(S_ba rho'_ab)
       tr = (a == c) ? rp.x : 0.f;
     }
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(RHO_MAX_D * RHO_MAX_D) rho_scan_kernel(RhoArgs
       rn = cmul(qv[a], rn);
       rn = cmul_ca(qv[c], make_float2(rn.x, rn.y));
       // cmul_ca(q, z) = conj(q) * z
-      rho[t] = rn;
+      rho[ts] = rn;
       if (!SAMPLE && g.ftraj) g.ftraj[((size_t)b * g.T + k + 1) * DD + t] = rn;
     }
     __syncthreads();
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(RHO_MAX_D * RHO_MAX_D) rho_scan_kernel(RhoArgs
       if (g.purity) {
         float pz = 0.f, dummy = 0.f;
         if (act) {
-          const float2 r1 = rho[t], r2 = rho[c * D + a];
+          const float2 r1 = rho[ts], r2 = rho[c * LD + a];
           pz = r1.x * r2.x - r1.y * r2.y;  // Re(rho_ab rho_ba)
         }
         float P, d2;
@@ -238,21 +240,21 @@ struct RhoBwdArgs {
 // launch bounds: D = 32 runs 1024 threads, i.e. at most 64 registers per thread
 __global__ void __launch_bounds__(RHO_MAX_D * RHO_MAX_D) rho_bwd_kernel(RhoBwdArgs g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int D = g.D, DD = D * D;
+  const int D = g.D, DD = D * D, LD = D + 1, DL = D * LD;   // padded row stride, as in rho_scan_kernel
   float2* rho = reinterpret_cast<float2*>(smem_raw);
-  float2* Lm = rho + DD;
-  float2* Y = Lm + DD;      // L rho
-  float2* Y2 = Y + DD;      // L rho^dag
-  float2* Ps = Y2 + DD;     // P
-  float2* GPs = Ps + DD;    // adjoint of P
-  float2* Z1 = GPs + DD;    // GP L
-  float2* qv = Z1 + DD;     // [D]
+  float2* Lm = rho + DL;
+  float2* Y = Lm + DL;      // L rho
+  float2* Y2 = Y + DL;      // L rho^dag
+  float2* Ps = Y2 + DL;     // P
+  float2* GPs = Ps + DL;    // adjoint of P
+  float2* Z1 = GPs + DL;    // GP L
+  float2* qv = Z1 + DL;     // [D]
   float* red = reinterpret_cast<float*>(qv + D);   // [32][3]
 
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
   const int b = blockIdx.x;
   const bool act = t < DD;
-  const int a = act ? t / D : 0, c = act ? t % D : 0;
+  const int a = act ? t / D : 0, c = act ? t % D : 0, ts = a * LD + c;
   const int nsteps = g.T - 1;
   const float wb = g.w[b];
   const float* xb = g.x + (size_t)b * g.T;
@@ -304,9 +306,9 @@ __global__ void __launch_bounds__(RHO_MAX_D * RHO_MAX_D) rho_bwd_kernel(RhoBwdAr
     const float dl = g.ttab[k] - g.ttab[k + 1];
     float2 rn = make_float2(0.f, 0.f);
     if (act) {
-      rho[t] = fb[(size_t)k * DD + t];
+      rho[ts] = fb[(size_t)k * DD + t];
       rn = fb[(size_t)(k + 1) * DD + t];
-      Lm[t] = make_float2(fmaf(s, Rac.x, Nac.x), fmaf(s, Rac.y, Nac.y));
+      Lm[ts] = make_float2(fmaf(s, Rac.x, Nac.x), fmaf(s, Rac.y, Nac.y));
     }
     if (t < D) {
       const float f = g.freqs[t];
@@ -319,18 +321,18 @@ __global__ void __launch_bounds__(RHO_MAX_D * RHO_MAX_D) rho_bwd_kernel(RhoBwdAr
     if (act) {
       float2 y = make_float2(0.f, 0.f), y2 = y;
       for (int m = 0; m < D; ++m) {
-        cmac(y, Lm[a * D + m], rho[m * D + c]);
-        cmac_cx(y2, Lm[a * D + m], rho[c * D + m]);
+        cmac(y, Lm[a * LD + m], rho[m * LD + c]);
+        cmac_cx(y2, Lm[a * LD + m], rho[c * LD + m]);
       }
-      Y[t] = y;
-      Y2[t] = y2;
+      Y[ts] = y;
+      Y2[ts] = y2;
     }
     __syncthreads();
     float2 p = make_float2(0.f, 0.f), grp = p;
     float e = 0.f, tr = 0.f, dot = 0.f;
     if (act) {
-      for (int m = 0; m < D; ++m) cmac_cx(p, Y[a * D + m], Lm[c * D + m]);
-      Ps[t] = p;
+      for (int m = 0; m < D; ++m) cmac_cx(p, Y[a * LD + m], Lm[c * LD + m]);
+      Ps[ts] = p;
       e = Sca.x * p.x - Sca.y * p.y;                      // Re(S_ca P_ac)
       tr = (a == c) ? p.x : 0.f;
       grp = cmul(cmul_ca(qv[a], Lam), qv[c]);             // conj(q_a) q_c Lam
@@ -345,8 +347,8 @@ __global__ void __launch_bounds__(RHO_MAX_D * RHO_MAX_D) rho_bwd_kernel(RhoBwdAr
       const float it = 1.0f / TAU;
       float2 gp = make_float2(grp.x * it + gE * Sac.x, grp.y * it + gE * Sac.y);
       if (a == c) gp.x -= DOT * it * it;
-      GPs[t] = gp;
-      const float2 pca = Ps[c * D + a];
+      GPs[ts] = gp;
+      const float2 pca = Ps[c * LD + a];
       GPacc.x = fmaf(gE, p.x + pca.x, GPacc.x);
       GPacc.y = fmaf(gE, p.y - pca.y, GPacc.y);
     }
@@ -354,14 +356,14 @@ __global__ void __launch_bounds__(RHO_MAX_D * RHO_MAX_D) rho_bwd_kernel(RhoBwdAr
     if (act) {
       float2 z = make_float2(0.f, 0.f), gl = z;
       for (int m = 0; m < D; ++m) {
-        cmac(z, GPs[a * D + m], Lm[m * D + c]);
-        cmac(gl, GPs[a * D + m], Y2[m * D + c]);
+        cmac(z, GPs[a * LD + m], Lm[m * LD + c]);
+        cmac(gl, GPs[a * LD + m], Y2[m * LD + c]);
         // GP^dag Y : conj(GP[m][a]) Y[m][c]
-        const float2 gm = GPs[m * D + a], ym = Y[m * D + c];
+        const float2 gm = GPs[m * LD + a], ym = Y[m * LD + c];
         gl.x = fmaf(gm.x, ym.x, fmaf(gm.y, ym.y, gl.x));
         gl.y = fmaf(gm.x, ym.y, fmaf(-gm.y, ym.x, gl.y));
       }
-      Z1[t] = z;
+      Z1[ts] = z;
       GLs.x = fmaf(s, gl.x, GLs.x);
       GLs.y = fmaf(s, gl.y, GLs.y);
       GL1.x += gl.x;
@@ -371,7 +373,7 @@ __global__ void __launch_bounds__(RHO_MAX_D * RHO_MAX_D) rho_bwd_kernel(RhoBwdAr
     if (act) {
       float2 ln = make_float2(0.f, 0.f);
       for (int m = 0; m < D; ++m) {                       // L^dag Z1 : conj(L[m][a]) Z1[m][c]
-        const float2 lm = Lm[m * D + a], zm = Z1[m * D + c];
+        const float2 lm = Lm[m * LD + a], zm = Z1[m * LD + c];
         ln.x = fmaf(lm.x, zm.x, fmaf(lm.y, zm.y, ln.x));
         ln.y = fmaf(lm.x, zm.y, fmaf(-lm.y, zm.x, ln.y));
       }
@@ -462,13 +464,13 @@ __global__ void rho_grad_finalize_kernel(const float2* __restrict__ G, const flo
 }
 
 inline size_t rho_smem_bytes(int D) {
-  return (size_t)(3 * D * D + 2 * D) * sizeof(float2) + (64 + 8) * sizeof(float);
+  return (size_t)(3 * D * (D + 1) + 2 * D) * sizeof(float2) + (64 + 8) * sizeof(float);
 }
 
 inline int rho_block(int D) { return ((D * D + 31) / 32) * 32; }
 
 inline size_t rho_bwd_smem_bytes(int D) {
-  return (size_t)(7 * D * D + D) * sizeof(float2) + 96 * sizeof(float);
+  return (size_t)(7 * D * (D + 1) + D) * sizeof(float2) + 96 * sizeof(float);
 }
 
 inline int rho_launch_bwd(const amps_params* p, const float* ttab, const float* x, int B, int T,
