@@ -272,6 +272,25 @@ cudaError_t launch_cluster(K kern, int nclusters, int CL, int threads, size_t sm
 }
 constexpr int C4_CL = 4;
 
+// Rho phase tables (q_k, and p_{k+1} when a lab-frame trajectory is wanted) in the context scratch
+int rho_phase_tables(amps_ctx* ctx, const amps_params* p, int nsteps, bool need_p, cudaStream_t st,
+                     const float2** qtab, const float2** ptab) {
+  const size_t n = (size_t)(nsteps > 0 ? nsteps : 1) * p->D;
+  int rc = ensure_scratch(ctx, align_up(n * sizeof(float2)) * (need_p ? 2 : 1));
+  if (rc) return rc;
+  float2* q = (float2*)ctx->scratch;
+  float2* pp = need_p ? (float2*)((char*)ctx->scratch + align_up(n * sizeof(float2))) : nullptr;
+  if (nsteps > 0) {
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    rho_prep_phase_kernel<<<blocks, 256, 0, st>>>(p->freqs_dev, ctx->ttab, nsteps, p->D, q, pp);
+    LAUNCH_CHECK(ctx, "rho_prep_phase_kernel");
+  }
+  *qtab = q;
+  *ptab = pp;
+  return AMPS_OK;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -891,8 +910,11 @@ int amps_rho_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
   char* ws = (char*)ws_dev;
   rc = ensure_ttab(ctx, T + 1, (float)p->delta_t, st);
   if (rc) return rc;
-  rc = rho_launch_data(p, ctx->ttab, x_dev, B, T, loss_dev, nullptr, save ? (float2*)(ws + L.ftraj) : nullptr,
-                       (double*)(ws + L.lossd), st);
+  const float2 *qtab, *ptab;
+  rc = rho_phase_tables(ctx, p, T - 1, false, st, &qtab, &ptab);
+  if (rc) return rc;
+  rc = rho_launch_data(p, ctx->ttab, qtab, ptab, x_dev, B, T, loss_dev, nullptr,
+                       save ? (float2*)(ws + L.ftraj) : nullptr, (double*)(ws + L.lossd), st);
   if (rc) return fail(ctx, rc, "rho kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   ctx->launches++;
   return AMPS_OK;
@@ -914,7 +936,10 @@ int amps_rho_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
   const RhoWs L = rho_ws_layout(p->D, B, T, true);
   if (ws_bytes < L.total) return fail(ctx, AMPS_E_WORKSPACE, "workspace %zu < required %zu bytes", ws_bytes, L.total);
   if (!ctx->ttab || ctx->ttab_n < T) return fail(ctx, AMPS_E_STATE, "backward without a saving forward");
-  rc = rho_launch_bwd(p, ctx->ttab, x_dev, B, T, w_dev, (char*)ws_dev, L, grad_dev, st);
+  const float2 *qtab, *ptab;
+  rc = rho_phase_tables(ctx, p, T - 1, false, st, &qtab, &ptab);
+  if (rc) return rc;
+  rc = rho_launch_bwd(p, ctx->ttab, qtab, x_dev, B, T, w_dev, (char*)ws_dev, L, grad_dev, st);
   if (rc) return fail(ctx, rc, "rho backward launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   ctx->launches += 2;
   return AMPS_OK;
@@ -934,7 +959,10 @@ int amps_rho_evolve(amps_ctx* ctx, const amps_params* p, const float* x_dev, int
   cudaStream_t st = (cudaStream_t)stream;
   rc = ensure_ttab(ctx, T + 1, (float)p->delta_t, st);
   if (rc) return rc;
-  rc = rho_launch_data(p, ctx->ttab, x_dev, B, T, nullptr, (float2*)traj_dev, nullptr, nullptr, st);
+  const float2 *qtab, *ptab;
+  rc = rho_phase_tables(ctx, p, T - 1, true, st, &qtab, &ptab);
+  if (rc) return rc;
+  rc = rho_launch_data(p, ctx->ttab, qtab, ptab, x_dev, B, T, nullptr, (float2*)traj_dev, nullptr, nullptr, st);
   if (rc) return fail(ctx, rc, "rho kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   ctx->launches++;
   return AMPS_OK;
@@ -955,7 +983,10 @@ int amps_rho_sample(amps_ctx* ctx, const amps_params* p, const float* noise_dev,
   cudaStream_t st = (cudaStream_t)stream;
   rc = ensure_ttab(ctx, L + 1, (float)p->delta_t, st);
   if (rc) return rc;
-  rc = rho_launch_sample(p, ctx->ttab, noise_dev, L, n, out_dev, (float2*)traj_dev, purity_dev,
+  const float2 *qtab, *ptab;
+  rc = rho_phase_tables(ctx, p, L, traj_dev != nullptr, st, &qtab, &ptab);
+  if (rc) return rc;
+  rc = rho_launch_sample(p, ctx->ttab, qtab, ptab, noise_dev, L, n, out_dev, (float2*)traj_dev, purity_dev,
                          ws_dev, st);
   if (rc) return fail(ctx, rc, "rho kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   ctx->launches++;

@@ -46,11 +46,34 @@ __global__ void fill_kernel(float* __restrict__ p, int n, float v) {
   if (i < n) p[i] = v;
 }
 
+// Phase tables of a call: q_k = exp(i (fl32(f t_k) - fl32(f t_{k+1}))) and (optionally) p_{k+1} =
+// exp(i fl32(f t_{k+1})), from the float32 angles of the reference (model.py:178-179), evaluated in
+// double and rounded once.
+__global__ void rho_prep_phase_kernel(const float* __restrict__ freqs, const float* __restrict__ ttab,
+                                      int nsteps, int D, float2* __restrict__ qtab, float2* __restrict__ ptab) {
+  const size_t total = (size_t)nsteps * D;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx / D), c = (int)(idx % D);
+    const float f = freqs[c];
+    const double th0 = (double)__fmul_rn(f, ttab[k]);
+    const double th1 = (double)__fmul_rn(f, ttab[k + 1]);
+    double sn, cs;
+    sincos(th0 - th1, &sn, &cs);
+    qtab[idx] = make_float2((float)cs, (float)sn);
+    if (ptab) {
+      sincos(th1, &sn, &cs);
+      ptab[idx] = make_float2((float)cs, (float)sn);
+    }
+  }
+}
+
 struct RhoArgs {
   const float2* R;      // [D][D]
   const float* freqs;   // [D]
   const float2* rho0;   // [D][D]
   const float* ttab;    // float32 time table
+  const float2* qtab;   // [nsteps][D] q_k = p_k conj(p_{k+1})   (rho_prep_phase_kernel)
+  const float2* ptab;   // [nsteps][D] p_{k+1}, only when a lab-frame trajectory is requested
   int D;
   float A, dtf;
   double cprime;
@@ -127,18 +150,30 @@ __global__ void __launch_bounds__(RHO_MAX_D * RHO_MAX_D) rho_scan_kernel(RhoArgs
     __syncthreads();
   };
 
+  // The per-step global inputs (waveform / noise sample, phases) are fetched ONE STEP AHEAD into
+  // registers, so their L2 latency is off the step's critical path.
+  const float* xb = SAMPLE ? nullptr : g.x + (size_t)b * g.T;
+  auto in_at = [&](int k) -> float {
+    if (k >= nsteps) return 0.f;
+    if (SAMPLE) return g.noise[(size_t)k * g.n + b];
+    return xb[k + 1] - xb[k];                                              // model.py:134-135
+  };
+  float in_next = in_at(0);
+  float2 q_next = make_float2(1.f, 0.f), p_next = q_next;
+  if (t < D && nsteps > 0) {
+    q_next = g.qtab[t];
+    if (g.traj) p_next = g.ptab[t];
+  }
   for (int k = 0; k < nsteps; ++k) {
     // phases for this step (threads < D): q_k = p_k conj(p_{k+1}),  p_{k+1} for the lab frame
+    const float in_cur = in_next;
+    in_next = in_at(k + 1);
     if (t < D) {
-      const float f = g.freqs[t];
-      const double th0 = (double)__fmul_rn(f, g.ttab[k]);
-      const double th1 = (double)__fmul_rn(f, g.ttab[k + 1]);
-      double sn, cs;
-      sincos(th0 - th1, &sn, &cs);
-      qv[t] = make_float2((float)cs, (float)sn);
-      if (g.traj) {
-        sincos(th1, &sn, &cs);
-        pv[t] = make_float2((float)cs, (float)sn);
+      qv[t] = q_next;
+      if (g.traj) pv[t] = p_next;
+      if (k + 1 < nsteps) {
+        q_next = g.qtab[(size_t)(k + 1) * D + t];
+        if (g.traj) p_next = g.ptab[(size_t)(k + 1) * D + t];
       }
     }
     float inc;
@@ -151,11 +186,10 @@ __global__ void __launch_bounds__(RHO_MAX_D * RHO_MAX_D) rho_scan_kernel(RhoArgs
       }
       float E, d2;
       block_sum2(e, dummy, E, d2);
-      inc = __fadd_rn(__fmul_rn(E, g.dtf), g.noise[(size_t)k * g.n + b]);
+      inc = __fadd_rn(__fmul_rn(E, g.dtf), in_cur);
       X = __fadd_rn(X, inc);
     } else {
-      const float* xb = g.x + (size_t)b * g.T;
-      inc = xb[k + 1] - xb[k];
+      inc = in_cur;
     }
     const float s = inc / g.A;
     if (act) Lm[ts] = make_float2(fmaf(s, Rab.x, Nab.x), fmaf(s, Rab.y, Nab.y));
@@ -175,7 +209,7 @@ __global__ void __launch_bounds__(RHO_MAX_D * RHO_MAX_D) rho_scan_kernel(RhoArgs
     }
     float E, TR;
     block_sum2(e, tr, E, TR);
-    if (!SAMPLE && t == 0) lossacc -= log1p((double)((E * inc) / g.A));   // model.py:169-170
+    if (!SAMPLE && t == 0) lossacc -= (double)log1pf((E * inc) / g.A);    // model.py:169-170 (fp32 log, fp64 sum)
     const float inv = 1.0f / fmaxf(TR, 1e-12f);                            // model.py:198-203
     float2 rn = make_float2(0.f, 0.f);
     if (act) {
@@ -225,6 +259,7 @@ struct RhoBwdArgs {
   const float2* R;
   const float* freqs;
   const float* ttab;
+  const float2* qtab;   // [nsteps][D]
   const float* x;       // [B][T]
   const float* w;       // [B]
   const float2* ftraj;  // [B][T][D][D]
@@ -300,21 +335,34 @@ __global__ void __launch_bounds__(RHO_MAX_D * RHO_MAX_D) rho_bwd_kernel(RhoBwdAr
     __syncthreads();
   };
 
-  for (int k = nsteps - 1; k >= 0; --k) {
-    const float inc = xb[k + 1] - xb[k];
-    const float s = inc / g.A;
-    const float dl = g.ttab[k] - g.ttab[k + 1];
-    float2 rn = make_float2(0.f, 0.f);
+  // inputs of step k-1 are fetched during step k (registers): waveform increment, time difference,
+  // phases and the stored rho~_{k-1}; rho~_{k+1} of a step is the previous step's rho~_k.
+  auto inc_at = [&](int k) { return k >= 0 ? xb[k + 1] - xb[k] : 0.f; };
+  auto dl_at = [&](int k) { return k >= 0 ? g.ttab[k] - g.ttab[k + 1] : 0.f; };
+  float inc_next = inc_at(nsteps - 1), dl_next = dl_at(nsteps - 1);
+  float2 q_next = make_float2(1.f, 0.f), rho_next = make_float2(0.f, 0.f), rho_prev = rho_next;
+  if (nsteps > 0) {
+    if (t < D) q_next = g.qtab[(size_t)(nsteps - 1) * D + t];
     if (act) {
-      rho[ts] = fb[(size_t)k * DD + t];
-      rn = fb[(size_t)(k + 1) * DD + t];
-      Lm[ts] = make_float2(fmaf(s, Rac.x, Nac.x), fmaf(s, Rac.y, Nac.y));
+      rho_next = fb[(size_t)(nsteps - 1) * DD + t];
+      rho_prev = fb[(size_t)nsteps * DD + t];
     }
+  }
+  for (int k = nsteps - 1; k >= 0; --k) {
+    const float inc = inc_next, dl = dl_next;
+    const float s = inc / g.A;
+    const float2 rk = rho_next, rn = rho_prev;
+    inc_next = inc_at(k - 1);
+    dl_next = dl_at(k - 1);
+    if (act) {
+      rho[ts] = rk;
+      Lm[ts] = make_float2(fmaf(s, Rac.x, Nac.x), fmaf(s, Rac.y, Nac.y));
+      if (k > 0) rho_next = fb[(size_t)(k - 1) * DD + t];
+    }
+    rho_prev = rk;
     if (t < D) {
-      const float f = g.freqs[t];
-      double sn, cs;
-      sincos((double)__fmul_rn(f, g.ttab[k]) - (double)__fmul_rn(f, g.ttab[k + 1]), &sn, &cs);
-      qv[t] = make_float2((float)cs, (float)sn);
+      qv[t] = q_next;
+      if (k > 0) q_next = g.qtab[(size_t)(k - 1) * D + t];
     }
     __syncthreads();
     acc = fmaf(dl, Lam.x * rn.y - Lam.y * rn.x, acc);     // dl Im(conj(Lam) rho~_{k+1})
@@ -342,7 +390,7 @@ __global__ void __launch_bounds__(RHO_MAX_D * RHO_MAX_D) rho_bwd_kernel(RhoBwdAr
     block_sum3(e, tr, dot, E, TAU, DOT);
     const float arg = 1.0f + (E * inc) / g.A;
     const float gE = wb * (-s / arg);
-    if (t == 0) gAacc += (double)wb * (double)E * (double)inc / ((double)g.A * (double)g.A * (double)arg);
+    if (t == 0) gAacc += (double)(wb * E * inc / (g.A * g.A * arg));
     if (act) {
       const float it = 1.0f / TAU;
       float2 gp = make_float2(grp.x * it + gE * Sac.x, grp.y * it + gE * Sac.y);
@@ -473,9 +521,10 @@ inline size_t rho_bwd_smem_bytes(int D) {
   return (size_t)(7 * D * (D + 1) + D) * sizeof(float2) + 96 * sizeof(float);
 }
 
-inline int rho_launch_bwd(const amps_params* p, const float* ttab, const float* x, int B, int T,
+inline int rho_launch_bwd(const amps_params* p, const float* ttab, const float2* qtab, const float* x, int B, int T,
                           const float* w, char* ws, const RhoWs& L, float* grad, cudaStream_t st) {
   RhoBwdArgs g{};
+  g.qtab = qtab;
   g.R = (const float2*)p->R_dev;
   g.freqs = p->freqs_dev;
   g.ttab = ttab;
@@ -502,9 +551,12 @@ inline int rho_launch_bwd(const amps_params* p, const float* ttab, const float* 
   return cudaGetLastError() == cudaSuccess ? 0 : AMPS_E_CUDA;
 }
 
-inline int rho_launch_data(const amps_params* p, const float* ttab, const float* x, int B, int T,
+inline int rho_launch_data(const amps_params* p, const float* ttab, const float2* qtab, const float2* ptab,
+                           const float* x, int B, int T,
                            float* loss, float2* traj, float2* ftraj, double* lossd, cudaStream_t st) {
   RhoArgs g{};
+  g.qtab = qtab;
+  g.ptab = ptab;
   g.ftraj = ftraj;
   g.lossd = lossd;
   g.R = (const float2*)p->R_dev;
@@ -523,11 +575,14 @@ inline int rho_launch_data(const amps_params* p, const float* ttab, const float*
   return cudaGetLastError() == cudaSuccess ? 0 : AMPS_E_CUDA;
 }
 
-inline int rho_launch_sample(const amps_params* p, const float* ttab, const float* noise, int L,
+inline int rho_launch_sample(const amps_params* p, const float* ttab, const float2* qtab, const float2* ptab,
+                             const float* noise, int L,
                              int n, float* out, float2* traj, float* purity, void* ws,
                              cudaStream_t st) {
   (void)ws;
   RhoArgs g{};
+  g.qtab = qtab;
+  g.ptab = ptab;
   g.R = (const float2*)p->R_dev;
   g.freqs = p->freqs_dev;
   g.rho0 = (const float2*)p->rho0_dev;
