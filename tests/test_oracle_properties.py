@@ -107,3 +107,27 @@ def test_get_audio_correct_shape():                    # tests/test_data.py:12-1
     hp = HP(minibatch_size=8, bond_dim=8, delta_t=0.001)
     assert damped_sine(hp.minibatch_size, SAMPLE_DURATION, hp.delta_t, np.random.default_rng(0)).shape == \
         (hp.minibatch_size, SAMPLE_DURATION)
+
+
+def test_oracle_gradient_against_finite_differences():
+    """finite-difference spot check of the oracle's gradient (float64 mode, central
+    differences along random directions of Rx, Ry, psi_x, psi_y, A; freqs is excluded because the
+    reference's float32 phase-angle rounding makes the loss piecewise in it).  The raw variables are
+    float32 values, so the perturbed points are rounded to float32 and the exact displacement is used."""
+    from oracle.cmps_oracle import grads_of, total_loss
+    hp = HP(bond_dim=4, minibatch_size=2)
+    rng = np.random.default_rng(21)
+    raw = random_raw_params(hp, rng)
+    data = damped_sine(2, 60, hp.delta_t, np.random.default_rng(22))
+    o = PsiCMPSOracle(hp, raw, mode="f64")
+    g = grads_of(o, total_loss(o, data))
+    for name in ("Rx", "Ry", "psi_x", "psi_y", "A"):
+        base = np.asarray(raw.get(name, hp.A), np.float32)
+        v = rng.standard_normal(base.shape)
+        eps = 1e-3 * (np.abs(base).max() + 1e-3)
+        plus = (base.astype(np.float64) + eps * v).astype(np.float32)
+        minus = (base.astype(np.float64) - eps * v).astype(np.float32)
+        lp = float(total_loss(PsiCMPSOracle(hp, {**raw, name: plus}, mode="f64", requires_grad=False), data))
+        lm = float(total_loss(PsiCMPSOracle(hp, {**raw, name: minus}, mode="f64", requires_grad=False), data))
+        an = float(np.sum(np.asarray(g[name]) * (plus.astype(np.float64) - minus.astype(np.float64))))
+        assert abs((lp - lm) - an) <= 2e-5 * max(abs(an), abs(lp - lm)) + 1e-12, (name, lp - lm, an)
