@@ -67,6 +67,10 @@ SYMBOLS = {
                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "amps_psi_loss_bwd_scan": (C.c_int, [C.c_void_p, C.POINTER(AmpsParams), C.c_void_p, C.c_int, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "amps_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "amps_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "amps_allreduce_grads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "amps_comm_destroy": (C.c_int, [C.c_void_p]),
     "amps_psi_sample": (C.c_int, [C.c_void_p, C.POINTER(AmpsParams), C.c_void_p, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p]),
     "amps_psi_evolve": (C.c_int, [C.c_void_p, C.POINTER(AmpsParams), C.c_void_p, C.c_int, C.c_int,

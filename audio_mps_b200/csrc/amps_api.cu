@@ -9,6 +9,8 @@
 #include <new>
 #include <type_traits>
 
+#include <dlfcn.h>
+
 #include "../../include/audiomps.h"
 #include "amps_prep.cuh"
 #include "amps_psi.cuh"
@@ -40,6 +42,9 @@ struct amps_ctx {
   bool prof = false;
   cudaEvent_t ev[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
   bool ev_valid[3] = {false, false, false};
+  // data-parallel communicator (NCCL, resolved at run time; see amps_comm_init)
+  void* nccl_comm = nullptr;
+  int comm_rank = 0, comm_size = 1;
 };
 
 namespace {
@@ -114,6 +119,40 @@ __global__ void fma2_peak_kernel(float* out, int iters, float a, float b) {
 }
 
 inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// ---- NCCL, bound at run time ---------------------------------------------------------------
+// The library does not link against NCCL: amps_comm_* resolve the few entry points they need from
+// the libnccl.so.2 already loaded in the process (PyTorch ships one) or found by the dynamic loader
+// (AMPS_NCCL_LIB overrides the name).  Types mirror nccl.h (2.x ABI).
+struct NcclId {
+  char internal[128];
+};
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api.handle ? &api : nullptr;
+  tried = true;
+  const char* name = getenv("AMPS_NCCL_LIB");
+  void* h = dlopen(name && name[0] ? name : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return nullptr;
+  api.GetUniqueId = (int (*)(NcclId*))dlsym(h, "ncclGetUniqueId");
+  api.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(h, "ncclCommInitRank");
+  api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+  api.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+  api.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) return nullptr;
+  api.handle = h;
+  return &api;
+}
+constexpr int kNcclFloat = 7, kNcclSum = 0;   // ncclFloat32, ncclSum
 
 int padded_dim(int D) {
   if (D <= 0) return -1;
@@ -320,6 +359,7 @@ int amps_create(int device, amps_ctx** out) {
 int amps_destroy(amps_ctx* ctx) {
   if (!ctx) return AMPS_E_INVALID;
   cudaSetDevice(ctx->device);
+  if (ctx->nccl_comm) amps_comm_destroy(ctx);
   if (ctx->ttab) cudaFree(ctx->ttab);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->hbuf) cudaFree(ctx->hbuf);
@@ -990,6 +1030,58 @@ int amps_rho_sample(amps_ctx* ctx, const amps_params* p, const float* noise_dev,
                          ws_dev, st);
   if (rc) return fail(ctx, rc, "rho kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   ctx->launches++;
+  return AMPS_OK;
+}
+
+// ---- data-parallel communicator over NCCL (NVLink / NVSwitch) --------------------------------
+int amps_comm_unique_id(void* id_out) {
+  if (!id_out) return AMPS_E_INVALID;
+  NcclApi* n = nccl_api();
+  if (!n) return AMPS_E_UNSUPPORTED;
+  NcclId id;
+  if (n->GetUniqueId(&id) != 0) return AMPS_E_CUDA;
+  memcpy(id_out, &id, sizeof(id));
+  return AMPS_OK;
+}
+
+int amps_comm_init(amps_ctx* ctx, const void* id, int rank, int nranks) {
+  if (!ctx) return AMPS_E_INVALID;
+  if (!id || nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, AMPS_E_INVALID, "bad communicator arguments");
+  if (ctx->nccl_comm) return fail(ctx, AMPS_E_STATE, "communicator already initialised");
+  NcclApi* n = nccl_api();
+  if (!n) return fail(ctx, AMPS_E_UNSUPPORTED, "libnccl.so.2 not found (set AMPS_NCCL_LIB)");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  NcclId nid;
+  memcpy(&nid, id, sizeof(nid));
+  void* comm = nullptr;
+  const int rc = n->CommInitRank(&comm, nranks, nid, rank);
+  if (rc != 0) return fail(ctx, AMPS_E_CUDA, "ncclCommInitRank: %s", n->GetErrorString ? n->GetErrorString(rc) : "error");
+  ctx->nccl_comm = comm;
+  ctx->comm_rank = rank;
+  ctx->comm_size = nranks;
+  return AMPS_OK;
+}
+
+int amps_allreduce_grads(amps_ctx* ctx, float* packed_dev, size_t count, void* stream) {
+  if (!ctx) return AMPS_E_INVALID;
+  if (!ctx->nccl_comm) return fail(ctx, AMPS_E_STATE, "amps_comm_init has not been called");
+  if (!packed_dev && count) return fail(ctx, AMPS_E_INVALID, "packed_dev is NULL");
+  if (count == 0) return AMPS_OK;
+  NcclApi* n = nccl_api();
+  const int rc = n->AllReduce(packed_dev, packed_dev, count, kNcclFloat, kNcclSum, ctx->nccl_comm, (cudaStream_t)stream);
+  if (rc != 0) return fail(ctx, AMPS_E_CUDA, "ncclAllReduce: %s", n->GetErrorString ? n->GetErrorString(rc) : "error");
+  return AMPS_OK;
+}
+
+int amps_comm_destroy(amps_ctx* ctx) {
+  if (!ctx) return AMPS_E_INVALID;
+  if (ctx->nccl_comm) {
+    NcclApi* n = nccl_api();
+    if (n) n->CommDestroy(ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+    ctx->comm_size = 1;
+    ctx->comm_rank = 0;
+  }
   return AMPS_OK;
 }
 

@@ -99,7 +99,10 @@ class _PsiLossFn(torch.autograd.Function):
         rc = bwd(h, C.byref(p), _ptr(x), B, T, _ptr(w), _ptr(ws), ws.numel(), _ptr(packed), _stream(dev))
         _lib.check(h, rc)
         dp = getattr(model, "_dp_group", None)
-        if dp is not None:
+        if getattr(model, "_dp_native", False):
+            # data parallel through the C ABI's own NCCL communicator (amps_comm_init)
+            _lib.check(h, lib.amps_allreduce_grads(h, _ptr(packed), ng, _stream(dev)))
+        elif dp is not None:
             # data parallel: ONE all-reduce of the packed effective-parameter gradient
             torch.distributed.all_reduce(packed, op=torch.distributed.ReduceOp.SUM, group=dp)
         model._last_packed = packed
@@ -285,9 +288,26 @@ class CMPS(torch.nn.Module):
             raise ValueError(f"noise must be [length, num_samples]={length, num_samples}, got {tuple(noise.shape)}")
         return noise
 
-    def set_data_parallel(self, group):
-        """All-reduce (sum) the packed kernel gradient over ``group`` inside backward."""
+    def set_data_parallel(self, group, native: bool = False):
+        """All-reduce (sum) the packed kernel gradient over ``group`` inside backward.
+
+        ``native=True``: the reduction runs on the library's own NCCL communicator
+        (amps_comm_init / amps_allreduce_grads); ``group`` is then used once, to hand rank 0's
+        ncclUniqueId to the other ranks."""
         self._dp_group = group
+        self._dp_native = False
+        if native:
+            import torch.distributed as dist
+            lib, h = _lib.load(), self._ctx()
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+            buf = (C.c_ubyte * 128)()
+            if rank == 0:
+                _lib.check(h, lib.amps_comm_unique_id(buf))
+            ids = [bytes(buf)]
+            dist.broadcast_object_list(ids, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            raw = (C.c_ubyte * 128).from_buffer_copy(ids[0])
+            _lib.check(h, lib.amps_comm_init(h, raw, rank, world))
+            self._dp_native = True
 
 
 # --------------------------------------------------------------------------------------------

@@ -37,14 +37,14 @@ class Trainer:
     parameter-only regulariser gradient is computed redundantly on every rank.
     """
 
-    def __init__(self, model, learning_rate: Optional[float] = None, group=None):
+    def __init__(self, model, learning_rate: Optional[float] = None, group=None, native_comm: bool = False):
         self.model = model
         lr = learning_rate if learning_rate is not None else getattr(model.hparams, "learning_rate", 1e-3)
         self.opt = torch.optim.Adam(model.parameters(), lr=lr, betas=(0.9, 0.999), eps=1e-8)
         self.group = group
         self.world = dist.get_world_size(group) if (group is not None or dist.is_initialized()) else 1
         if self.world > 1:
-            model.set_data_parallel(group if group is not None else dist.group.WORLD)
+            model.set_data_parallel(group if group is not None else dist.group.WORLD, native=native_comm)
         self.global_step = 0
 
     def step(self, x_local, global_batch: Optional[int] = None, regularise: bool = True):

@@ -192,6 +192,22 @@ int amps_rho_sample(amps_ctx* ctx, const amps_params* p, const float* noise_dev,
                     float* out_dev, float* traj_dev, float* purity_dev, void* ws_dev,
                     size_t ws_bytes, void* stream);
 
+/* ---- data parallelism: ONE all-reduce of the packed gradient per step ------------------------
+ * Batch is the only shard axis (model.py:258-267): every rank runs amps_psi_loss_fwd/_bwd on its clips
+ * with w_b = 1/B_global and sums the packed buffer [gR | gfreqs | gpsi0 | gA | sum_b w_b loss_b]
+ * (2*D*D + 3*D + 2 floats) across ranks.  The communicator is NCCL (NVLink 5 / NVSwitch), resolved at
+ * run time from the libnccl.so.2 of the process (no link-time dependency; AMPS_NCCL_LIB overrides).
+ *   amps_comm_unique_id: rank 0 fills AMPS_COMM_ID_BYTES bytes (an ncclUniqueId) and hands them to the
+ *                        other ranks out of band (file, socket, torch.distributed, MPI ...)
+ *   amps_comm_init:      collective over the nranks contexts (one per GPU / process)
+ *   amps_allreduce_grads: in-place float32 sum on `stream`
+ * A host that already has a communicator (torch.distributed) may all-reduce the buffer itself. */
+#define AMPS_COMM_ID_BYTES 128
+int amps_comm_unique_id(void* id_out);
+int amps_comm_init(amps_ctx* ctx, const void* id, int rank, int nranks);
+int amps_allreduce_grads(amps_ctx* ctx, float* packed_dev, size_t count, void* stream);
+int amps_comm_destroy(amps_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,7 +10,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, native=False):
     import torch.distributed as dist
     from audio_mps_b200 import HParams, PsiCMPS, damped_sine
     from audio_mps_b200.train import Trainer, shard_bounds
@@ -23,7 +23,7 @@ def _worker(rank, world, port, q):
                  h_reg=200 / (np.pi * 16000) ** 2, r_reg=0.1, initial_rank=None, A=100., learning_rate=0.001)
     data = damped_sine(6, 700, hp.delta_t, np.random.default_rng(1))
     model = PsiCMPS(hp, device=dev, seed=0)
-    tr = Trainer(model)
+    tr = Trainer(model, native_comm=native)      # native: the C ABI's own NCCL communicator
     lo, hi = shard_bounds(6, rank, world)
     losses = [float(tr.step(data[lo:hi], global_batch=6)) for _ in range(3)]
     q.put((rank, losses, {n: p.detach().cpu().numpy() for n, p in model.named_parameters()}))
@@ -31,7 +31,8 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_gpu_training_matches_single_gpu(lib):
+@pytest.mark.parametrize("native", [False, True])
+def test_two_gpu_training_matches_single_gpu(lib, native):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
@@ -43,7 +44,7 @@ def test_two_gpu_training_matches_single_gpu(lib):
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, native)) for r in range(2)]
     for p in procs:
         p.start()
     got = {}
