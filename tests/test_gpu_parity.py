@@ -172,3 +172,29 @@ def test_rho_grads_raw(cuda, lib, D, B, T, over):
     for n, g in zip(names, gs):
         r = gref["freqs" if n == "freqs_raw" else n]
         assert rel(g.cpu().numpy(), r) <= GRAD_TOL, (n, rel(g.cpu().numpy(), r))
+
+
+def test_psi_random_shapes(cuda, lib):
+    """Seeded sweep over odd shapes: every padded bond dimension (1..128 -> 8/16/32/64/128), batches that
+    do and do not fit the cluster kernels, lengths around the 16- and 32-step chunk boundaries."""
+    rng = np.random.default_rng(1234)
+    dims = [1, 2, 3, 5, 9, 13, 17, 24, 31, 33, 48, 63, 65, 90, 127, 128]
+    for n, D in enumerate(dims):
+        B = int(rng.integers(1, 6)) if n % 3 else int(rng.integers(75, 80))     # 2*B > 148 -> single-CTA kernels
+        T = int(rng.choice([2, 3, 16, 17, 18, 31, 32, 33, 34, 47, 48, 49, 64, 65, 66, 97, 130]))
+        if D > 64:
+            B = min(B, 3)
+        ohp, raw, data, model = build(D, B, T, dict(), cuda, seed=100 + n)
+        o = PsiCMPSOracle(ohp, raw, mode="f64")
+        ref = o.loss_per_clip(data)
+        got = model.loss_per_clip(data)
+        assert rel(got.detach().cpu().numpy(), ref.detach().numpy()) <= LOSS_TOL, (D, B, T)
+        gref = grads_of(o, ref.mean())
+        names = ["A", "Rx", "Ry", "freqs_raw", "psi_x", "psi_y"]
+        gs = torch.autograd.grad(got.mean(), [getattr(model, k) for k in names])
+        for k, g in zip(names, gs):
+            r = gref["freqs" if k == "freqs_raw" else k]
+            if np.abs(r).max() == 0:
+                assert float(g.abs().max()) == 0.0
+                continue
+            assert rel(g.cpu().numpy(), r) <= GRAD_TOL, (D, B, T, k, rel(g.cpu().numpy(), r))
