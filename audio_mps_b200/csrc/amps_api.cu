@@ -219,7 +219,7 @@ PsiWs psi_ws_layout(int DP, int B, int nsteps_tab, int T, bool save) {
     w.Gtot = take(3 * mat);
     w.gftot = take((size_t)DP * sizeof(float));
     w.lam0tot = take((size_t)DP * sizeof(float2));
-    if (DP <= 32) {   // only the warp-specialised / 2-CTA kernels keep these
+    if (DP <= 64) {   // S x'_k and (E_k, |x_k|^2) from the forward (not the 4-CTA D = 128 kernels)
       w.sptraj = take((size_t)B * T * DP * sizeof(float2));   // S x'_k
       w.ev = take((size_t)B * T * sizeof(float2));            // (E_k, |x_k|^2)
     }
@@ -516,7 +516,8 @@ int amps_psi_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
           (const float2*)(ws + L.matN), (const float2*)(ws + L.matR), (const float2*)(ws + L.matS),
           (const float2*)(ws + L.qtab), (const float2*)(ws + L.psi0p), x_dev, T, aval(p), loss_dev,
           (double*)(ws + L.lossd), save ? (float2*)(ws + L.traj) : nullptr,
-          save ? (float*)(ws + L.scales) : nullptr, nchunks, (const float2*)nullptr, 0, 0);
+          save ? (float*)(ws + L.scales) : nullptr, nchunks, (const float2*)nullptr, 0, 0,
+          save ? (float2*)(ws + L.sptraj) : nullptr, save ? (float2*)(ws + L.ev) : nullptr);
     }
     PROF_END(ctx, 0, st);
     LAUNCH_CHECK(ctx, "psi_fwd_kernel");
@@ -613,7 +614,7 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
           (const float2*)(ws + L.qtab), ctx->ttab, x_dev, T, aval(p), w_dev,
           (const float2*)(ws + L.traj), (const float*)(ws + L.scales), nchunks,
           (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0), (double*)(ws + L.gAdir),
-          (const float2*)nullptr, 0, 0);
+          (const float2*)nullptr, 0, 0, (const float2*)(ws + L.sptraj), (const float2*)(ws + L.ev));
     }
     PROF_END(ctx, 1, st);
     LAUNCH_CHECK(ctx, "psi_bwd_kernel");
@@ -642,7 +643,7 @@ constexpr int kScanCtas = 148;   // virtual clips aim at one CTA per B200 SM (fi
 struct ScanWs {
   PsiWs base;
   size_t ops, ystart, lossv, rnv;
-  size_t traj, scales, G, gf, lam0, gAdir, lamend, wv, Gtot, gftot, lam0tot;
+  size_t traj, sptraj, ev, scales, G, gf, lam0, gAdir, lamend, wv, Gtot, gftot, lam0tot;
   size_t total;
   int nvc, m_steps;
 };
@@ -670,6 +671,8 @@ ScanWs scan_ws_layout(int B, int T, bool save) {
   w.rnv = take(nv * sizeof(float));
   if (save) {
     w.traj = take(nv * (size_t)(m + 1) * TC_D * sizeof(float2));
+    w.sptraj = take(nv * (size_t)(m + 1) * TC_D * sizeof(float2));
+    w.ev = take(nv * (size_t)(m + 1) * sizeof(float2));
     w.scales = take(nv * (size_t)(m / CH) * sizeof(float));
     w.G = take(nv * 3 * mat);
     w.gf = take(nv * TC_D * sizeof(float));
@@ -739,7 +742,9 @@ int amps_psi_loss_fwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
                                    (const float2*)(ws + L.base.psi0p), x_dev, T, aval(p), (float*)nullptr,
                                    (double*)(ws + L.lossv), save ? (float2*)(ws + L.traj) : (float2*)nullptr,
                                    save ? (float*)(ws + L.scales) : (float*)nullptr, 0,
-                                   (const float2*)(ws + L.ystart), L.nvc, L.m_steps);
+                                   (const float2*)(ws + L.ystart), L.nvc, L.m_steps,
+                                   save ? (float2*)(ws + L.sptraj) : (float2*)nullptr,
+                                   save ? (float2*)(ws + L.ev) : (float2*)nullptr);
     PROF_END(ctx, 0, st);
     LAUNCH_CHECK(ctx, "psi_fwd_uni_kernel<virtual clips>");
   }
@@ -786,7 +791,8 @@ int amps_psi_loss_bwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
                                    (const float*)ctx->ttab, x_dev, T, aval(p), w_dev,
                                    (const float2*)(ws + L.traj), (const float*)(ws + L.scales), 0,
                                    (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0),
-                                   (double*)(ws + L.gAdir), lam_end, L.nvc, L.m_steps);
+                                   (double*)(ws + L.gAdir), lam_end, L.nvc, L.m_steps,
+                                   (const float2*)(ws + L.sptraj), (const float2*)(ws + L.ev));
   };
   PROF_BEGIN(ctx, 1, st);
   adjoint_pass(nullptr);                                   // d_j: chunk adjoints with a zero end condition

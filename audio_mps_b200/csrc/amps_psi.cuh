@@ -535,12 +535,14 @@ using FalseT = std::false_type;
 
 template <int DP, int NQ>
 struct alignas(16) FwdSmemUni {
-  static constexpr int NT = DP * NQ, G = NT / 32, ES = NT + G;
+  static constexpr int NT = DP * NQ, G = NT / 32;
   float2 xs[CH + 1][DP];        // x_{k0+kk}
   float2 xps[CH][DP];           // x'_{k0+kk}
   float2 qs[2][CH][DP];         // q_k, double buffered
-  float es[CH][ES];             // per-thread partial of Re(x'^dag S x'); row stride = G mod 32
+  float2 sps[CH][DP];           // S x'_{k0+kk} (chunk-end pass; kept for the backward)
+  float esr[CH][DP + 1];        // Re(conj(x'_i) (S x')_i)
   float ns[2][CH + 1][DP + 1];  // |x_{k,i}|^2, by chunk parity
+  float2 evs[CH];               // (E_k, |x_k|^2)
   float wav[2][CH + 4];         // waveform samples k0..k0+len, double buffered
   float sv[2][CH + 4];          // s_k
   float incv[2][CH];            // inc_k
@@ -551,11 +553,10 @@ template <int DP>
 struct alignas(16) BwdSmemUni {
   float2 xs[3][CH + 1][DP];  // trajectory chunk, triple buffered (chunk c, c-1 in use, c-2 landing)
   float2 qs[3][CH][DP];
+  float2 spl[3][CH][DP];     // S x'_k stored by the forward
+  float2 evl[3][CH];         // (E_k, |x_k|^2) stored by the forward
   float2 xps[2][CH][DP];     // reconstructed x'_k      (chunk c and, being prepared, c-1)
-  float2 sps[2][CH][DP];     // S x'_k
   float2 mus[CH][DP];        // adjoint of x'_k
-  float es[CH][DP + 1];
-  float ns[CH][DP + 1];
   float wav[3][CH + 4];
   float tt[3][CH + 4];
   float scs[3][4];
@@ -578,7 +579,8 @@ __global__ void __launch_bounds__(DP* NQ)
                    const float2* __restrict__ psi0p_, const float* __restrict__ x, int T, AVal A_,
                    float* __restrict__ loss, double* __restrict__ lossd,
                    float2* __restrict__ traj, float* __restrict__ scales, int nchunks,
-                   const float2* __restrict__ psi0v, int nvc, int m_steps) {
+                   const float2* __restrict__ psi0v, int nvc, int m_steps,
+                   float2* __restrict__ sptraj, float2* __restrict__ evout) {
   const float A = a_get(A_);
   using M = Map<DP, NQ>;
   using Sm = FwdSmemUni<DP, NQ>;
@@ -636,7 +638,8 @@ __global__ void __launch_bounds__(DP* NQ)
   };
 
   // branch-free per-step stores: lane jq==0 writes x_{k+1,i}, jq==1 writes x'_{k,i} (same row
-  // stride), jq==2 writes |x_{k+1,i}|^2, every thread writes its partial of x'^dag S x'.
+  // stride), jq==2 writes |x_{k+1,i}|^2.  The step loop carries ONLY the chain; everything that does
+  // not feed the next state (S x', E_k, the loss) runs once per chunk, barrier-free, below.
   float2* const st2 = (jq == 0) ? &sm.xs[1][i] : &sm.xps[0][i];
   const bool st2_on = jq < 2;
   const bool stn_on = jq == 2;
@@ -659,90 +662,72 @@ __global__ void __launch_bounds__(DP* NQ)
     __syncthreads();  // (D) sv/incv, xs[0], ns[.][0] of this chunk visible; last chunk's flush done
 
     float* const stn = &sm.ns[buf][1][i];
-    float2 xp_prev = make_float2(0.f, 0.f);
     float s_cur = sm.sv[buf][0];
 
-    // One step: chain mat-vec with L_k (critical path) + the S x' mat-vec of the previous step.
-    auto step = [&](auto first_tag, int kk) {
-      constexpr bool FIRST = decltype(first_tag)::value;
-      float2 xv[CPT], pv[CPT];
+    auto step = [&](int kk) {
+      float2 xv[CPT];
 #pragma unroll
       for (int m = 0; m < CPT / 2; ++m) {
         const float4 v = *reinterpret_cast<const float4*>(&sm.xs[kk][2 * NQ * m + 2 * jq]);
         xv[2 * m] = make_float2(v.x, v.y);
         xv[2 * m + 1] = make_float2(v.z, v.w);
       }
-      if (!FIRST) {
-#pragma unroll
-        for (int m = 0; m < CPT / 2; ++m) {
-          const float4 v = *reinterpret_cast<const float4*>(&sm.xps[kk - 1][2 * NQ * m + 2 * jq]);
-          pv[2 * m] = make_float2(v.x, v.y);
-          pv[2 * m + 1] = make_float2(v.z, v.w);
-        }
-      }
       const float2 q = sm.qs[buf][kk][i];
       const float s_next = sm.sv[buf][kk + 1];
-      // L_k slice, formed while the state loads are in flight
-      float2 L[CPT];
-#pragma unroll
-      for (int cc = 0; cc < CPT; ++cc)
-        L[cc] = make_float2(fmaf(s_cur, Rr[cc].x, Nr[cc].x), fmaf(s_cur, Rr[cc].y, Nr[cc].y));
       float2 a0 = make_float2(0.f, 0.f), a1 = a0;
 #pragma unroll
       for (int cc = 0; cc < CPT; cc += 2) {
-        cmac(a0, L[cc], xv[cc]);
-        cmac(a1, L[cc + 1], xv[cc + 1]);
+        const float2 l0 = make_float2(fmaf(s_cur, Rr[cc].x, Nr[cc].x), fmaf(s_cur, Rr[cc].y, Nr[cc].y));
+        const float2 l1 = make_float2(fmaf(s_cur, Rr[cc + 1].x, Nr[cc + 1].x), fmaf(s_cur, Rr[cc + 1].y, Nr[cc + 1].y));
+        cmac(a0, l0, xv[cc]);
+        cmac(a1, l1, xv[cc + 1]);
       }
       float2 xp = make_float2(a0.x + a1.x, a0.y + a1.y);
-      // group reduction, with the previous step's expectation FMAs in the shuffle shadows
-      float2 p0 = make_float2(0.f, 0.f), p1 = p0;
-      constexpr int LV = (NQ == 4) ? 2 : 3;
-      constexpr int CPL = (CPT + LV - 1) / LV;
-#pragma unroll
-      for (int lv = 0; lv < LV; ++lv) {
-        const float ox = __shfl_xor_sync(0xffffffffu, xp.x, 1 << lv);
-        const float oy = __shfl_xor_sync(0xffffffffu, xp.y, 1 << lv);
-        if (!FIRST) {
-#pragma unroll
-          for (int cc = lv * CPL; cc < (lv + 1) * CPL && cc < CPT; ++cc) {
-            if (cc & 1) cmac(p1, Sr[cc], pv[cc]);
-            else cmac(p0, Sr[cc], pv[cc]);
-          }
-        }
-        xp.x += ox;
-        xp.y += oy;
-      }
+      xp = group_sum<NQ>(xp);
       const float2 xn = cmul(q, xp);
       sts_if(st2_on, st2 + kk * DP, (jq == 0) ? xn : xp);
       sts_if(stn_on, stn + kk * (DP + 1), cabs2(xn));
-      if (!FIRST) sm.es[kk - 1][t] = fmaf(xp_prev.x, p0.x + p1.x, xp_prev.y * (p0.y + p1.y));
-      xp_prev = xp;
       s_cur = s_next;
       __syncthreads();
     };
 
-    step(TrueT{}, 0);
     if (len == CH) {
 #pragma unroll 2
-      for (int kk = 1; kk < CH; ++kk) step(FalseT{}, kk);
+      for (int kk = 0; kk < CH; ++kk) step(kk);
     } else {
-      for (int kk = 1; kk < len; ++kk) step(FalseT{}, kk);
-    }
-    {  // expectation of the chunk's last step
-      const float2 part = matvec1<DP, NQ>(Sr, sm.xps[len - 1], jq);
-      sm.es[len - 1][t] = fmaf(xp_prev.x, part.x, xp_prev.y * part.y);
+      for (int kk = 0; kk < len; ++kk) step(kk);
     }
     cp_async_wait<0>();
+
+    // ---- chunk-end pass: S x'_k and e_i for the whole chunk (independent steps: full ILP) -------
+    {
+      float2* const sp_st = &sm.sps[0][i];
+      float* const es_st = &sm.esr[0][i];
+      auto expect = [&](int kk) {
+        float2 part = matvec1<DP, NQ>(Sr, sm.xps[kk], jq);
+        part = group_sum<NQ>(part);
+        const float2 xpi = sm.xps[kk][i];
+        sts_if(jq == 0, sp_st + kk * DP, part);
+        sts_if(jq == 1, es_st + kk * (DP + 1), fmaf(xpi.x, part.x, xpi.y * part.y));
+      };
+      if (len == CH) {
+#pragma unroll 4
+        for (int kk = 0; kk < CH; ++kk) expect(kk);
+      } else {
+        for (int kk = 0; kk < len; ++kk) expect(kk);
+      }
+    }
     __syncthreads();  // (A)
 
     {  // per-step scalars, lane-parallel over the chunk: G threads per step
       const int kk = t / G, g = t % G;
       float en = 0.f, nu2 = 0.f;
       if (kk < len) {
-#pragma unroll 8
-        for (int r = 0; r < 32; ++r) en += sm.es[kk][g + G * r];
 #pragma unroll
-        for (int r = 0; r < PER; ++r) nu2 += sm.ns[buf][kk][g * PER + r];
+        for (int r = 0; r < PER; ++r) {
+          en += sm.esr[kk][g * PER + r];
+          nu2 += sm.ns[buf][kk][g * PER + r];
+        }
       }
 #pragma unroll
       for (int m = 1; m < G; m <<= 1) {
@@ -753,6 +738,7 @@ __global__ void __launch_bounds__(DP* NQ)
         const float E = en / nu2;                                  // model.py:324-325 on x'
         const float z = (E * sm.incv[buf][kk]) / A;                // model.py:294
         lossacc -= (double)log1pf(z);
+        sm.evs[kk] = make_float2(E, nu2);
       }
     }
     if (c + 1 < nchunks) compute_s(buf ^ 1, min(CH, nsteps - (k0 + CH)));
@@ -775,6 +761,12 @@ __global__ void __launch_bounds__(DP* NQ)
       const float4* src = reinterpret_cast<const float4*>(&sm.xs[1][0]);
       float4* dst = reinterpret_cast<float4*>(traj + ((size_t)b * tstride + k0 + 1) * DP);
       for (int idx = t; idx < len * DP / 2; idx += NT) dst[idx] = src[idx];
+      if (sptraj) {   // S x'_k and (E_k, |x_k|^2) for the adjoint: row k of the (virtual) clip
+        const float4* ssrc = reinterpret_cast<const float4*>(&sm.sps[0][0]);
+        float4* sdst = reinterpret_cast<float4*>(sptraj + ((size_t)b * tstride + k0) * DP);
+        for (int idx = t; idx < len * DP / 2; idx += NT) sdst[idx] = ssrc[idx];
+        if (t < len) evout[(size_t)b * tstride + k0 + t] = sm.evs[t];
+      }
     }
   }
 
@@ -815,13 +807,12 @@ __global__ void __launch_bounds__(DP* NQ)
                    const float* __restrict__ scales_, int nchunks, float2* __restrict__ Gout,
                    float* __restrict__ gfout, float2* __restrict__ lam0out,
                    double* __restrict__ gAdir, const float2* __restrict__ lam_end, int nvc,
-                   int m_steps) {
+                   int m_steps, const float2* __restrict__ sptraj, const float2* __restrict__ evin) {
   const float A = a_get(A_);
   using M = Map<DP, NQ>;
   constexpr int NT = M::NT;
   constexpr int CPT = M::CPT;
   constexpr int NP = M::NP;
-  constexpr int G = NT / 32, PER = DP / G;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdSmemUni<DP>& sm = *reinterpret_cast<BwdSmemUni<DP>*>(smem_raw);
 
@@ -829,7 +820,7 @@ __global__ void __launch_bounds__(DP* NQ)
   const int b = blockIdx.x;
   int nsteps = T - 1;
   const float* xb = x + (size_t)b * T;
-  const float2* trb = traj + (size_t)b * T * DP;
+  size_t rows = T;                       // trajectory rows per (virtual) clip
   const float2* qtab = qtab_;
   const float* ttab = ttab_;
   const float* scales = scales_ + (size_t)b * nchunks;
@@ -838,7 +829,7 @@ __global__ void __launch_bounds__(DP* NQ)
     const int clip = b / nvc, kbeg = (b % nvc) * m_steps;
     nsteps = max(0, min(m_steps, T - 1 - kbeg));
     xb = x + (size_t)clip * T + kbeg;
-    trb = traj + (size_t)b * (m_steps + 1) * DP;
+    rows = m_steps + 1;
     qtab = qtab_ + (size_t)kbeg * DP;
     ttab = ttab_ + kbeg;
     scales = scales_ + (size_t)b * (m_steps / CH);
@@ -847,11 +838,13 @@ __global__ void __launch_bounds__(DP* NQ)
   } else {
     wb = w[b];
   }
+  const float2* trb = traj + (size_t)b * rows * DP;
+  const float2* spb = sptraj + (size_t)b * rows * DP;
+  const float2* evb = evin + (size_t)b * rows;
 
-  float2 Nr[CPT], Hr[CPT], Sr[CPT];
+  float2 Nr[CPT], Hr[CPT];
   load_slice<DP, NQ>(Nr, matN, i, jq);   // N is Hermitian: N^dag mu uses the same slices
   load_slice<DP, NQ>(Hr, matRH, i, jq);  // R^dag
-  load_slice<DP, NQ>(Sr, matS, i, jq);
 
   float2 GR[CPT], GN[CPT], GE[CPT];
 #pragma unroll
@@ -868,22 +861,39 @@ __global__ void __launch_bounds__(DP* NQ)
     for (int idx = t; idx < (len + 1) * DP / 2; idx += NT) cp_async16(xdst + 2 * idx, xsrc + 2 * idx);
     const float2* qsrc = qtab + (size_t)k0 * DP;
     float2* qdst = &sm.qs[lb][0][0];
-    for (int idx = t; idx < len * DP / 2; idx += NT) cp_async16(qdst + 2 * idx, qsrc + 2 * idx);
+    const float2* ssrc = spb + (size_t)k0 * DP;
+    float2* sdst = &sm.spl[lb][0][0];
+    for (int idx = t; idx < len * DP / 2; idx += NT) {
+      cp_async16(qdst + 2 * idx, qsrc + 2 * idx);
+      cp_async16(sdst + 2 * idx, ssrc + 2 * idx);
+    }
     for (int idx = t; idx <= len; idx += NT) {
       cp_async4(&sm.wav[lb][idx], xb + k0 + idx);
       cp_async4(&sm.tt[lb][idx], ttab + k0 + idx);
     }
+    for (int idx = t; idx < len; idx += NT) cp_async8(&sm.evl[lb][idx], evb + k0 + idx);
     if (t == 0) cp_async4(&sm.scs[lb][0], scales + c);
   };
 
-  // P0 + P1 of chunk c: s, inc, dt; x'_k = conj(q_k) x_{k+1} / c_k ; |x_k|^2
+  double gAacc = 0.0;
+  // chunk c: s, inc, dt, alpha_k, beta_k, the direct dL/dA term (from the forward's (E_k, |x_k|^2));
+  // x'_k = conj(q_k) x_{k+1} / c_k
   auto prep_elementwise = [&](int c) {
     const int lb = c % 3, ds = c & 1, len = chunk_len(c);
     if (t < len) {
       const float inc = sm.wav[lb][t + 1] - sm.wav[lb][t];
+      const float s = inc / A;
       sm.incv[ds][t] = inc;
-      sm.sv[ds][t] = inc / A;
+      sm.sv[ds][t] = s;
       sm.dtk[ds][t] = sm.tt[lb][t + 1] - sm.tt[lb][t];
+      const float2 ev = sm.evl[lb][t];
+      const float E = ev.x, nu2 = ev.y;
+      const float arg = 1.0f + (E * inc) / A;
+      const float gE = wb * (-s / arg);
+      const float alpha = 2.0f * gE / nu2;
+      sm.alphas[ds][t] = alpha;
+      sm.betas[ds][t] = -alpha * E;
+      gAacc += (double)wb * (double)E * (double)inc / ((double)A * (double)A * (double)arg);
     }
     const float inv_sc = 1.0f / sm.scs[lb][0];
     for (int idx = t; idx < len * DP; idx += NT) {
@@ -894,46 +904,6 @@ __global__ void __launch_bounds__(DP* NQ)
         xp.y *= inv_sc;
       }
       sm.xps[ds][kk][r] = xp;
-      sm.ns[kk][r] = cabs2(sm.xs[lb][kk][r]);
-    }
-  };
-  // P2 of one step: S x' (stored) and e_i
-  float2* const sp_st = &sm.sps[0][0][i];
-  float* const es_st = &sm.es[0][i];
-  auto expectation_step = [&](int ds, int kk) {
-    float2 part = matvec1<DP, NQ>(Sr, sm.xps[ds][kk], jq);
-    part = group_sum<NQ>(part);
-    const float2 xpi = sm.xps[ds][kk][i];
-    sts_if(jq == 1, sp_st + (ds * CH + kk) * DP, part);
-    sts_if(jq == 2, es_st + kk * (DP + 1), fmaf(xpi.x, part.x, xpi.y * part.y));
-  };
-  double gAacc = 0.0;
-  // P3 of chunk c: alpha_k, beta_k and the direct dL/dA term; G threads per step
-  auto prep_scalars = [&](int c) {
-    const int ds = c & 1, len = chunk_len(c);
-    const int kk = t / G, g = t % G;
-    float en = 0.f, nu2 = 0.f;
-    if (kk < len) {
-#pragma unroll
-      for (int r = 0; r < PER; ++r) {
-        en += sm.es[kk][g * PER + r];
-        nu2 += sm.ns[kk][g * PER + r];
-      }
-    }
-#pragma unroll
-    for (int m = 1; m < G; m <<= 1) {
-      en += __shfl_xor_sync(0xffffffffu, en, m);
-      nu2 += __shfl_xor_sync(0xffffffffu, nu2, m);
-    }
-    if (g == 0 && kk < len) {
-      const float E = en / nu2;
-      const float inc = sm.incv[ds][kk];
-      const float arg = 1.0f + (E * inc) / A;
-      const float gE = wb * (-sm.sv[ds][kk] / arg);
-      const float alpha = 2.0f * gE / nu2;
-      sm.alphas[ds][kk] = alpha;
-      sm.betas[ds][kk] = -alpha * E;
-      gAacc += (double)wb * (double)E * (double)inc / ((double)A * (double)A * (double)arg);
     }
   };
 
@@ -950,10 +920,6 @@ __global__ void __launch_bounds__(DP* NQ)
     cp_async_wait<1>();
     __syncthreads();
     prep_elementwise(cl);
-    __syncthreads();
-    for (int kk = 0; kk < chunk_len(cl); ++kk) expectation_step(cl & 1, kk);
-    __syncthreads();
-    prep_scalars(cl);
   }
 
   float2* const mu_st = &sm.mus[0][i];
@@ -962,13 +928,11 @@ __global__ void __launch_bounds__(DP* NQ)
   for (int c = nchunks - 1; c >= 0; --c) {
     const int lb = c % 3, ds = c & 1;
     const int len = chunk_len(c);
-    const bool has_prev = c >= 1;
-    const int pds = ds ^ 1;
     if (c >= 2) issue_loads(c - 2);
     cp_async_commit();
     cp_async_wait<1>();   // chunk c-1 has landed
-    __syncthreads();      // (T1)
-    if (has_prev) prep_elementwise(c - 1);
+    __syncthreads();      // (T1) prep of chunk c (previous iteration / prologue) visible
+    if (c >= 1) prep_elementwise(c - 1);
     const float sc = sm.scs[lb][0];
 
     // adjoint of x' for the chunk's last step (carries the rescale c_k)
@@ -979,15 +943,14 @@ __global__ void __launch_bounds__(DP* NQ)
       gf = fmaf(sm.dtk[ds][kk], lam.x * xn.y - lam.y * xn.x, gf);   // Im(conj(lam) x_{k+1})
       mu = cmul_ca(sm.qs[lb][kk][i], lam);
       const float al = sm.alphas[ds][kk];
-      const float2 sp = sm.sps[ds][kk][i];
+      const float2 sp = sm.spl[lb][kk][i];
       mu.x = fmaf(al, sp.x, mu.x * sc);
       mu.y = fmaf(al, sp.y, mu.y * sc);
       if (mu_on) mu_st[kk * DP] = mu;
     }
     __syncthreads();      // (T2)
 
-    auto step = [&](auto prev_tag, int kk) {
-      constexpr bool PREV = decltype(prev_tag)::value;     // chunk c-1 exists (expectation filler)
+    auto step = [&](int kk) {
       // ---- operand loads --------------------------------------------------------------
       float2 mv[CPT];
 #pragma unroll
@@ -1002,7 +965,7 @@ __global__ void __launch_bounds__(DP* NQ)
       const int km = kk > 0 ? kk - 1 : 0;
       const float2 q1 = sm.qs[lb][km][i];
       const float al1 = sm.alphas[ds][km];
-      const float2 sp1 = sm.sps[ds][km][i];
+      const float2 sp1 = sm.spl[lb][km][i];
       const float dt1 = sm.dtk[ds][km];
       // ---- chain: lam = L_k^dag mu + beta x_k -------------------------------------------
       float2 a0 = make_float2(0.f, 0.f), a1 = a0;
@@ -1016,7 +979,7 @@ __global__ void __launch_bounds__(DP* NQ)
       float2 lp = make_float2(a0.x + a1.x, a0.y + a1.y);
       float ox = __shfl_xor_sync(0xffffffffu, lp.x, 1);
       float oy = __shfl_xor_sync(0xffffffffu, lp.y, 1);
-      // ---- filler 1: rank-1 tiles of step kk (mu_k is in registers) ---------------------
+      // ---- filler: rank-1 tiles of step kk (mu_k is in registers), in the shuffle shadows ----
       if (TILES) {
         const float2 xpi = sm.xps[ds][kk][i];
         const float al = sm.alphas[ds][kk];
@@ -1038,12 +1001,8 @@ __global__ void __launch_bounds__(DP* NQ)
       }
       lp.x += ox;
       lp.y += oy;
-      ox = __shfl_xor_sync(0xffffffffu, lp.x, 2);
-      oy = __shfl_xor_sync(0xffffffffu, lp.y, 2);
-      // ---- filler 2: S x' of step kk of chunk c-1 ---------------------------------------
-      if (PREV) expectation_step(pds, kk);
-      lp.x += ox;
-      lp.y += oy;
+      lp.x += __shfl_xor_sync(0xffffffffu, lp.x, 2);
+      lp.y += __shfl_xor_sync(0xffffffffu, lp.y, 2);
       if (NQ == 8) {
         lp.x += __shfl_xor_sync(0xffffffffu, lp.x, 4);
         lp.y += __shfl_xor_sync(0xffffffffu, lp.y, 4);
@@ -1061,15 +1020,7 @@ __global__ void __launch_bounds__(DP* NQ)
       __syncthreads();
     };
 
-    if (has_prev) {
-      for (int kk = len - 1; kk >= 0; --kk) step(TrueT{}, kk);
-      // chunk c-1 is always full; finish its expectation steps if this chunk was short
-      for (int kk = len; kk < CH; ++kk) expectation_step(pds, kk);
-      __syncthreads();    // (E1) es / sps of chunk c-1 complete
-      prep_scalars(c - 1);
-    } else {
-      for (int kk = len - 1; kk >= 0; --kk) step(FalseT{}, kk);
-    }
+    for (int kk = len - 1; kk >= 0; --kk) step(kk);
   }
   cp_async_wait<0>();
 
