@@ -128,6 +128,19 @@ __device__ __forceinline__ float2 group_sum(float2 v) {
   return v;
 }
 
+// Row-sum of a COMPLEX partial over the NQ lanes with half the shuffles: after the first level the even
+// lanes carry only the real part and the odd lanes only the imaginary part (SHFL issues at one warp
+// instruction per cycle per SM, so with 16 warps per SM every shuffle per thread costs 16 cycles per
+// step).  Returns Re(sum) on even lanes, Im(sum) on odd lanes.
+template <int NQ>
+__device__ __forceinline__ float pair_reduce(float2 v, int jq) {
+  const bool odd = jq & 1;
+  float r = (odd ? v.y : v.x) + __shfl_xor_sync(0xffffffffu, odd ? v.x : v.y, 1);
+#pragma unroll
+  for (int m = 2; m < NQ; m <<= 1) r += __shfl_xor_sync(0xffffffffu, r, m);
+  return r;
+}
+
 // Row-sum over the NQ lanes of a group on the chain's critical path.  For NQ = 4 the three partner
 // values are fetched with three INDEPENDENT shuffles per component (one shuffle latency, ~29 cycles on
 // B200) instead of two dependent butterfly levels (two latencies); the summation tree

@@ -532,6 +532,9 @@ __global__ void __launch_bounds__(2 * DP * NQ)
 // ===========================================================================================
 using TrueT = std::true_type;
 using FalseT = std::false_type;
+using IC0 = std::integral_constant<int, 0>;
+using IC1 = std::integral_constant<int, 1>;
+using IC2 = std::integral_constant<int, 2>;
 
 template <int DP, int NQ>
 struct alignas(16) FwdSmemUni {
@@ -540,7 +543,7 @@ struct alignas(16) FwdSmemUni {
   float2 xps[CH][DP];           // x'_{k0+kk}
   float2 qs[2][CH][DP];         // q_k, double buffered
   float2 sps[CH][DP];           // S x'_{k0+kk} (chunk-end pass; kept for the backward)
-  float esr[CH][DP + 1];        // Re(conj(x'_i) (S x')_i)
+  float esr[CH][2 * DP + 2];    // Re x'_i Re(S x')_i and Im x'_i Im(S x')_i (even / odd lane of the row)
   float ns[2][CH + 1][DP + 1];  // |x_{k,i}|^2, by chunk parity
   float2 evs[CH];               // (E_k, |x_k|^2)
   float wav[2][CH + 4];         // waveform samples k0..k0+len, double buffered
@@ -662,18 +665,52 @@ __global__ void __launch_bounds__(DP* NQ)
     __syncthreads();  // (D) sv/incv, xs[0], ns[.][0] of this chunk visible; last chunk's flush done
 
     float* const stn = &sm.ns[buf][1][i];
+    float2* const sp_st = &sm.sps[0][i];
     float s_cur = sm.sv[buf][0];
+    float2 part_pp = make_float2(0.f, 0.f);   // per-thread partial of (S x'_{kk-2})_i, reduced in step kk
 
-    auto step = [&](int kk) {
-      float2 xv[CPT];
+    // One step: the chain mat-vec with L_k on the critical path.  In the shadows of its loads and
+    // shuffles run, software-pipelined, the expectation of EARLIER steps: (stage >= 1) the partial
+    // mat-vec S x'_{kk-1}, (stage >= 2) the row reduction of the partial of step kk-2 and its stores.
+    // lane 0 of a row ends with Re (S x')_i, lane 1 with Im (S x')_i (pair_reduce); each stores its
+    // component of S x' and its half of Re(conj(x'_i) (S x')_i)
+    float* const spf_st = reinterpret_cast<float*>(sp_st) + (jq & 1);
+    float* const esf_st = &sm.esr[0][2 * i + (jq & 1)];
+    const bool ex_on = jq < 2;
+    auto finish_expect = [&](float2 part, int kk) {       // part: per-thread partial of (S x'_kk)_i
+      const float r = pair_reduce<NQ>(part, jq);
+      const float2 xpi = sm.xps[kk][i];
+      sts_if(ex_on, spf_st + kk * (2 * DP), r);
+      sts_if(ex_on, esf_st + kk * (2 * DP + 2), ((jq & 1) ? xpi.y : xpi.x) * r);
+    };
+    auto step = [&](auto stage_tag, int kk) {
+      constexpr int STAGE = decltype(stage_tag)::value;
+      float2 xv[CPT], pv[CPT];
 #pragma unroll
       for (int m = 0; m < CPT / 2; ++m) {
         const float4 v = *reinterpret_cast<const float4*>(&sm.xs[kk][2 * NQ * m + 2 * jq]);
         xv[2 * m] = make_float2(v.x, v.y);
         xv[2 * m + 1] = make_float2(v.z, v.w);
       }
+      if (STAGE >= 1) {
+#pragma unroll
+        for (int m = 0; m < CPT / 2; ++m) {
+          const float4 v = *reinterpret_cast<const float4*>(&sm.xps[kk - 1][2 * NQ * m + 2 * jq]);
+          pv[2 * m] = make_float2(v.x, v.y);
+          pv[2 * m + 1] = make_float2(v.z, v.w);
+        }
+      }
       const float2 q = sm.qs[buf][kk][i];
       const float s_next = sm.sv[buf][kk + 1];
+      // row reduction of step kk-2's partial: three dependent shuffle levels, started first so that
+      // they ride under the chain's own latency
+      float red = 0.f;
+      float2 xpi2 = make_float2(0.f, 0.f);
+      if (STAGE >= 2) {
+        xpi2 = sm.xps[kk - 2][i];
+        const bool odd = jq & 1;       // pair_reduce, level 1
+        red = (odd ? part_pp.y : part_pp.x) + __shfl_xor_sync(0xffffffffu, odd ? part_pp.x : part_pp.y, 1);
+      }
       float2 a0 = make_float2(0.f, 0.f), a1 = a0;
 #pragma unroll
       for (int cc = 0; cc < CPT; cc += 2) {
@@ -683,40 +720,50 @@ __global__ void __launch_bounds__(DP* NQ)
         cmac(a1, l1, xv[cc + 1]);
       }
       float2 xp = make_float2(a0.x + a1.x, a0.y + a1.y);
-      xp = group_sum<NQ>(xp);
+      if (STAGE >= 2) red += __shfl_xor_sync(0xffffffffu, red, 2);
+      // chain row reduction, the S x'_{kk-1} FMAs in the shuffle shadows
+      float2 p0 = make_float2(0.f, 0.f), p1 = p0;
+      constexpr int LV = (NQ == 4) ? 2 : 3;
+      constexpr int CPL = (CPT + LV - 1) / LV;
+#pragma unroll
+      for (int lv = 0; lv < LV; ++lv) {
+        const float ox = __shfl_xor_sync(0xffffffffu, xp.x, 1 << lv);
+        const float oy = __shfl_xor_sync(0xffffffffu, xp.y, 1 << lv);
+        if (STAGE >= 1) {
+#pragma unroll
+          for (int cc = lv * CPL; cc < (lv + 1) * CPL && cc < CPT; ++cc) {
+            if (cc & 1) cmac(p1, Sr[cc], pv[cc]);
+            else cmac(p0, Sr[cc], pv[cc]);
+          }
+        }
+        xp.x += ox;
+        xp.y += oy;
+      }
       const float2 xn = cmul(q, xp);
       sts_if(st2_on, st2 + kk * DP, (jq == 0) ? xn : xp);
       sts_if(stn_on, stn + kk * (DP + 1), cabs2(xn));
+      if (STAGE >= 2) {
+        if (NQ == 8) red += __shfl_xor_sync(0xffffffffu, red, 4);
+        sts_if(ex_on, spf_st + (kk - 2) * (2 * DP), red);
+        sts_if(ex_on, esf_st + (kk - 2) * (2 * DP + 2), ((jq & 1) ? xpi2.y : xpi2.x) * red);
+      }
+      if (STAGE >= 1) part_pp = make_float2(p0.x + p1.x, p0.y + p1.y);
       s_cur = s_next;
       __syncthreads();
     };
 
+    step(IC0{}, 0);
+    if (len > 1) step(IC1{}, 1);
     if (len == CH) {
 #pragma unroll 2
-      for (int kk = 0; kk < CH; ++kk) step(kk);
+      for (int kk = 2; kk < CH; ++kk) step(IC2{}, kk);
     } else {
-      for (int kk = 0; kk < len; ++kk) step(kk);
+      for (int kk = 2; kk < len; ++kk) step(IC2{}, kk);
     }
     cp_async_wait<0>();
-
-    // ---- chunk-end pass: S x'_k and e_i for the whole chunk (independent steps: full ILP) -------
-    {
-      float2* const sp_st = &sm.sps[0][i];
-      float* const es_st = &sm.esr[0][i];
-      auto expect = [&](int kk) {
-        float2 part = matvec1<DP, NQ>(Sr, sm.xps[kk], jq);
-        part = group_sum<NQ>(part);
-        const float2 xpi = sm.xps[kk][i];
-        sts_if(jq == 0, sp_st + kk * DP, part);
-        sts_if(jq == 1, es_st + kk * (DP + 1), fmaf(xpi.x, part.x, xpi.y * part.y));
-      };
-      if (len == CH) {
-#pragma unroll 4
-        for (int kk = 0; kk < CH; ++kk) expect(kk);
-      } else {
-        for (int kk = 0; kk < len; ++kk) expect(kk);
-      }
-    }
+    // drain the expectation pipeline: step len-2's partial is in part_pp, step len-1 has none yet
+    if (len >= 2) finish_expect(part_pp, len - 2);
+    finish_expect(matvec1<DP, NQ>(Sr, sm.xps[len - 1], jq), len - 1);
     __syncthreads();  // (A)
 
     {  // per-step scalars, lane-parallel over the chunk: G threads per step
@@ -725,7 +772,7 @@ __global__ void __launch_bounds__(DP* NQ)
       if (kk < len) {
 #pragma unroll
         for (int r = 0; r < PER; ++r) {
-          en += sm.esr[kk][g * PER + r];
+          en += sm.esr[kk][2 * (g * PER + r)] + sm.esr[kk][2 * (g * PER + r) + 1];
           nu2 += sm.ns[buf][kk][g * PER + r];
         }
       }
