@@ -219,7 +219,7 @@ PsiWs psi_ws_layout(int DP, int B, int nsteps_tab, int T, bool save) {
     w.Gtot = take(3 * mat);
     w.gftot = take((size_t)DP * sizeof(float));
     w.lam0tot = take((size_t)DP * sizeof(float2));
-    if (DP <= 64) {   // S x'_k and (E_k, |x_k|^2) from the forward (not the 4-CTA D = 128 kernels)
+    {   // S x'_k and (E_k, |x_k|^2) from the forward
       w.sptraj = take((size_t)B * T * DP * sizeof(float2));   // S x'_k
       w.ev = take((size_t)B * T * sizeof(float2));            // (E_k, |x_k|^2)
     }
@@ -460,7 +460,9 @@ int amps_psi_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
                                  (const float2*)(ws + L.psi0p), x_dev, T, aval(p), loss_dev,
                                  (double*)(ws + L.lossd), save ? (float2*)(ws + L.traj) : (float2*)nullptr,
                                  save ? (float*)(ws + L.scales) : (float*)nullptr, nchunks,
-                                 (const float2*)nullptr, 0, 0));
+                                 (const float2*)nullptr, 0, 0,
+                                 save ? (float2*)(ws + L.sptraj) : (float2*)nullptr,
+                                 save ? (float2*)(ws + L.ev) : (float2*)nullptr));
     PROF_END(ctx, 0, st);
     LAUNCH_CHECK(ctx, "psi_fwd_c4_kernel");
     return AMPS_OK;
@@ -558,7 +560,8 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
                                  (const float*)ctx->ttab, x_dev, T, aval(p), w_dev,
                                  (const float2*)(ws + L.traj), (const float*)(ws + L.scales), nchunks,
                                  (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0),
-                                 (double*)(ws + L.gAdir), (const float2*)nullptr, 0, 0));
+                                 (double*)(ws + L.gAdir), (const float2*)nullptr, 0, 0,
+                                 (const float2*)(ws + L.sptraj), (const float2*)(ws + L.ev)));
     PROF_END(ctx, 1, st);
     LAUNCH_CHECK(ctx, "psi_bwd_c4_kernel");
     rc = AMPS_OK;

@@ -38,6 +38,8 @@ struct alignas(16) FwdC4Smem {
   float2 qs[2][CH4][DP];              // q_k, double buffered
   float es[CH4][C4<DP, CL>::NTL];     // per-thread partial of Re(x'^dag S x') over this CTA's rows
   float enx[CL][CH4];                 // per-CTA partial sums of every CTA of the cluster
+  float2 sps[CH4][C4<DP, CL>::RP];    // (S x'_k)_i for this CTA's rows (kept for the backward)
+  float2 evs[CH4];                    // (E_k, |x_k|^2)
   float wav[2][CH4 + 4];
   float sv[2][CH4 + 4];
   float incv[2][CH4];
@@ -54,7 +56,8 @@ __global__ void __launch_bounds__(512)
                       const float2* __restrict__ psi0p_, const float* __restrict__ x, int T, AVal A_,
                       float* __restrict__ loss, double* __restrict__ lossd,
                       float2* __restrict__ traj, float* __restrict__ scales, int nchunks,
-                      const float2* __restrict__ psi0v, int nvc, int m_steps) {
+                      const float2* __restrict__ psi0v, int nvc, int m_steps,
+                      float2* __restrict__ sptraj, float2* __restrict__ evout) {
   const float A = a_get(A_);
   using Cf = C4<DP, CL>;
   constexpr int NQ = Cf::NQ, CPT = Cf::CPT, RP = Cf::RP, NTL = Cf::NTL;
@@ -146,9 +149,15 @@ __global__ void __launch_bounds__(512)
 
     float2 xp_prev = make_float2(0.f, 0.f);
     float s_cur = sm.sv[buf][0];
+    // (S x')_i of this CTA's rows, software-pipelined two steps behind the chain: lane 0 of a row ends
+    // with the real part, lane 1 with the imaginary part (pair_reduce)
+    float2 part_pp = make_float2(0.f, 0.f);
+    float* const spf_st = reinterpret_cast<float*>(&sm.sps[0][il]) + (jq & 1);
+    const bool ex_on = jq < 2;
 
-    auto step = [&](auto first_tag, int kk) {
-      constexpr bool FIRST = decltype(first_tag)::value;
+    auto step = [&](auto stage_tag, int kk) {
+      constexpr int STAGE = decltype(stage_tag)::value;
+      constexpr bool FIRST = STAGE == 0;
       if (t == 0) mbar_arrive_expect_tx(&sm.xbar[sg & 1], STEP_TX);          // arm this step's phase
       if (!FIRST) mbar_wait(&sm.xbar[(sg - 1) & 1], ((sg - 1) >> 1) & 1);    // previous step's rows are in
       float2 xv[CPT], pv[CPT];
@@ -168,6 +177,11 @@ __global__ void __launch_bounds__(512)
       }
       const float2 q = sm.qs[buf][kk][i];
       const float s_next = sm.sv[buf][kk + 1];
+      float red = 0.f;
+      if (STAGE >= 2) {   // row reduction of step kk-2's partial, level 1
+        const bool odd = jq & 1;
+        red = (odd ? part_pp.y : part_pp.x) + __shfl_xor_sync(0xffffffffu, odd ? part_pp.x : part_pp.y, 1);
+      }
       float2 L[CPT];
 #pragma unroll
       for (int cc = 0; cc < CPT; ++cc)
@@ -179,6 +193,10 @@ __global__ void __launch_bounds__(512)
         cmac(a1, L[cc + 1], xv[cc + 1]);
       }
       float2 xp = make_float2(a0.x + a1.x, a0.y + a1.y);
+      if (STAGE >= 2) {
+        red += __shfl_xor_sync(0xffffffffu, red, 2);
+        red += __shfl_xor_sync(0xffffffffu, red, 4);
+      }
       // 16-lane row reduction, the previous step's S x' FMAs in the shuffle shadows
       float2 p0 = make_float2(0.f, 0.f), p1 = p0;
       constexpr int LV = 4;
@@ -201,22 +219,30 @@ __global__ void __launch_bounds__(512)
       st_async_f2_if(st_on, st_addr0 + (unsigned)(kk * DP * (int)sizeof(float2)), st_x ? xn : xp,
                      st_bar0 + (unsigned)((sg & 1) * sizeof(unsigned long long)));
       if (!FIRST) sm.es[kk - 1][t] = fmaf(xp_prev.x, p0.x + p1.x, xp_prev.y * (p0.y + p1.y));
+      if (STAGE >= 2) {
+        red += __shfl_xor_sync(0xffffffffu, red, 8);
+        sts_if(ex_on, spf_st + (kk - 2) * (2 * RP), red);
+      }
+      if (!FIRST) part_pp = make_float2(p0.x + p1.x, p0.y + p1.y);
       xp_prev = xp;
       s_cur = s_next;
       ++sg;
     };
 
-    step(TrueT{}, 0);
+    step(IC0{}, 0);
+    if (len > 1) step(IC1{}, 1);
     if (len == CH4) {
 #pragma unroll 2
-      for (int kk = 1; kk < CH4; ++kk) step(FalseT{}, kk);
+      for (int kk = 2; kk < CH4; ++kk) step(IC2{}, kk);
     } else {
-      for (int kk = 1; kk < len; ++kk) step(FalseT{}, kk);
+      for (int kk = 2; kk < len; ++kk) step(IC2{}, kk);
     }
     mbar_wait(&sm.xbar[(sg - 1) & 1], ((sg - 1) >> 1) & 1);   // the chunk's last broadcast has landed
-    {  // expectation partial of the chunk's last step
+    {  // drain: step len-2's partial is in part_pp; the chunk's last step has none yet
+      if (len >= 2) sts_if(ex_on, spf_st + (len - 2) * (2 * RP), pair_reduce<NQ>(part_pp, jq));
       const float2 part = matvec1<DP, NQ>(Sr, sm.xps[len - 1], jq);
       sm.es[len - 1][t] = fmaf(xp_prev.x, part.x, xp_prev.y * part.y);
+      sts_if(ex_on, spf_st + (len - 1) * (2 * RP), pair_reduce<NQ>(part, jq));
     }
     cp_async_wait<0>();
     __syncthreads();  // (A)
@@ -247,6 +273,7 @@ __global__ void __launch_bounds__(512)
         const float E = en / nu2;                                  // model.py:324-325 on x'
         const float z = (E * sm.incv[buf][kk]) / A;                // model.py:294
         lossacc -= (double)log1pf(z);
+        sm.evs[kk] = make_float2(E, nu2);
       }
     }
     if (c + 1 < nchunks) compute_s(buf ^ 1, min(CH4, nsteps - (k0 + CH4)));
@@ -269,6 +296,14 @@ __global__ void __launch_bounds__(512)
       const float4* src = reinterpret_cast<const float4*>(&sm.xs[1][0]);
       float4* dst = reinterpret_cast<float4*>(traj + ((size_t)b * tstride + k0 + 1) * DP);
       for (int idx = t + (int)rank * NTL; idx < len * DP / 2; idx += NTL * CL) dst[idx] = src[idx];
+      if (sptraj) {   // S x'_k (this CTA's rows) and, from rank 0, (E_k, |x_k|^2): row k of the (virtual) clip
+        for (int idx = t; idx < len * RP / 2; idx += NTL) {
+          const int kk = idx / (RP / 2), r2 = idx % (RP / 2);
+          *reinterpret_cast<float4*>(sptraj + ((size_t)b * tstride + k0 + kk) * DP + (int)rank * RP + 2 * r2) =
+              *reinterpret_cast<const float4*>(&sm.sps[kk][2 * r2]);
+        }
+        if (rank == 0 && t < len) evout[(size_t)b * tstride + k0 + t] = sm.evs[t];
+      }
     }
   }
 
@@ -289,11 +324,10 @@ struct alignas(16) BwdC4Smem {
   static constexpr int RP = C4<DP, CL>::RP;
   float2 xs[3][CH4 + 1][DP];   // trajectory chunk, triple buffered (chunk c, c-1 in use, c-2 landing)
   float2 qs[3][CH4][DP];
+  float2 spl[3][CH4][RP];      // (S x'_k)_i stored by the forward, own rows
+  float2 evl[3][CH4];          // (E_k, |x_k|^2) stored by the forward
   float2 xps[2][CH4][DP];      // reconstructed x'_k, full vector
-  float2 sps[2][CH4][RP];      // (S x'_k)_i, own rows
   float2 mus[CH4][DP];         // adjoint of x'_k, full vector (own rows local, the rest from peers)
-  float es[CH4][RP + 1];       // Re(conj(x'_i) (S x')_i), own rows
-  float enx[CL][CH4];
   float wav[3][CH4 + 4];
   float tt[3][CH4 + 4];
   float scs[3][4];
@@ -312,7 +346,7 @@ __global__ void __launch_bounds__(512)
                       const float* __restrict__ scales_, int nchunks, float2* __restrict__ Gout,
                       float* __restrict__ gfout, float2* __restrict__ lam0out,
                       double* __restrict__ gAdir, const float2* __restrict__ lam_end, int nvc,
-                      int m_steps) {
+                      int m_steps, const float2* __restrict__ sptraj, const float2* __restrict__ evin) {
   const float A = a_get(A_);
   using Cf = C4<DP, CL>;
   constexpr int NQ = Cf::NQ, CPT = Cf::CPT, NP = Cf::NP, RP = Cf::RP, NTL = Cf::NTL;
@@ -325,7 +359,7 @@ __global__ void __launch_bounds__(512)
   const int i = (int)rank * RP + il;
   int nsteps = T - 1;
   const float* xb = x + (size_t)b * T;
-  const float2* trb = traj + (size_t)b * T * DP;
+  size_t rows = T;
   const float2* qtab = qtab_;
   const float* ttab = ttab_;
   const float* scales = scales_ + (size_t)b * nchunks;
@@ -334,7 +368,7 @@ __global__ void __launch_bounds__(512)
     const int clip = b / nvc, kbeg = (b % nvc) * m_steps;
     nsteps = max(0, min(m_steps, T - 1 - kbeg));
     xb = x + (size_t)clip * T + kbeg;
-    trb = traj + (size_t)b * (m_steps + 1) * DP;
+    rows = m_steps + 1;
     qtab = qtab_ + (size_t)kbeg * DP;
     ttab = ttab_ + kbeg;
     scales = scales_ + (size_t)b * (m_steps / CH4);
@@ -343,11 +377,14 @@ __global__ void __launch_bounds__(512)
   } else {
     wb = w[b];
   }
+  const float2* trb = traj + (size_t)b * rows * DP;
+  const float2* spb = sptraj + (size_t)b * rows * DP + (int)rank * RP;   // this CTA's rows of S x'
+  const float2* evb = evin + (size_t)b * rows;
+  (void)matS;
 
-  float2 Nr[CPT], Hr[CPT], Sr[CPT];
+  float2 Nr[CPT], Hr[CPT];
   load_slice<DP, NQ>(Nr, matN, i, jq);   // N is Hermitian: N^dag mu uses the same slices
   load_slice<DP, NQ>(Hr, matRH, i, jq);  // R^dag
-  load_slice<DP, NQ>(Sr, matS, i, jq);
 
   float2 GR[CPT], GN[CPT], GE[CPT];
 #pragma unroll
@@ -365,21 +402,37 @@ __global__ void __launch_bounds__(512)
     const float2* qsrc = qtab + (size_t)k0 * DP;
     float2* qdst = &sm.qs[lb][0][0];
     for (int idx = t; idx < len * DP / 2; idx += NTL) cp_async16(qdst + 2 * idx, qsrc + 2 * idx);
+    for (int idx = t; idx < len * RP / 2; idx += NTL) {
+      const int kk = idx / (RP / 2), r2 = idx % (RP / 2);
+      cp_async16(&sm.spl[lb][kk][2 * r2], spb + (size_t)(k0 + kk) * DP + 2 * r2);
+    }
     for (int idx = t; idx <= len; idx += NTL) {
       cp_async4(&sm.wav[lb][idx], xb + k0 + idx);
       cp_async4(&sm.tt[lb][idx], ttab + k0 + idx);
     }
+    for (int idx = t; idx < len; idx += NTL) cp_async8(&sm.evl[lb][idx], evb + k0 + idx);
     if (t == 0) cp_async4(&sm.scs[lb][0], scales + c);
   };
 
-  // s, inc, dt; x'_k = conj(q_k) x_{k+1} / c_k (full vector, every CTA)
+  double gAacc = 0.0;
+  // s, inc, dt, alpha_k, beta_k, the direct dL/dA term (from the forward's (E_k, |x_k|^2));
+  // x'_k = conj(q_k) x_{k+1} / c_k (full vector, every CTA)
   auto prep_elementwise = [&](int c) {
     const int lb = c % 3, ds = c & 1, len = chunk_len(c);
     if (t < len) {
       const float inc = sm.wav[lb][t + 1] - sm.wav[lb][t];
+      const float s = inc / A;
       sm.incv[ds][t] = inc;
-      sm.sv[ds][t] = inc / A;
+      sm.sv[ds][t] = s;
       sm.dtk[ds][t] = sm.tt[lb][t + 1] - sm.tt[lb][t];
+      const float2 ev = sm.evl[lb][t];
+      const float E = ev.x, nu2 = ev.y;
+      const float arg = 1.0f + (E * inc) / A;
+      const float gE = wb * (-s / arg);
+      const float alpha = 2.0f * gE / nu2;
+      sm.alphas[ds][t] = alpha;
+      sm.betas[ds][t] = -alpha * E;
+      gAacc += (double)wb * (double)E * (double)inc / ((double)A * (double)A * (double)arg);
     }
     const float inv_sc = 1.0f / sm.scs[lb][0];
     for (int idx = t; idx < len * DP; idx += NTL) {
@@ -392,46 +445,6 @@ __global__ void __launch_bounds__(512)
       sm.xps[ds][kk][r] = xp;
     }
   };
-  // (S x')_i and e_i for this CTA's rows
-  auto expectation_step = [&](int ds, int kk) {
-    float2 part = matvec1<DP, NQ>(Sr, sm.xps[ds][kk], jq);
-    part = group_sum<NQ>(part);
-    const float2 xpi = sm.xps[ds][kk][i];
-    sts_if(jq == 1, &sm.sps[ds][kk][il], part);
-    sts_if(jq == 2, &sm.es[kk][il], fmaf(xpi.x, part.x, xpi.y * part.y));
-  };
-  // this CTA's partial of Re(x'^dag S x') per step -> every CTA
-  auto prep_partial = [&](int c) {
-    const int len = chunk_len(c), kk = warp;
-    float en = (kk < len) ? sm.es[kk][lane] : 0.f;
-    en = warp_sum_f(en);
-    if (lane < CL && kk < len) st_dsmem_f1(dsmem_addr(&sm.enx[rank][kk], (unsigned)lane), en);
-  };
-  double gAacc = 0.0;
-  // alpha_k, beta_k and the direct dL/dA term (identical on every CTA)
-  auto prep_totals = [&](int c) {
-    const int lb = c % 3, ds = c & 1, len = chunk_len(c), kk = warp;
-    float nu2 = 0.f;
-    if (kk < len) {
-#pragma unroll
-      for (int r = 0; r < DP / 32; ++r) nu2 += cabs2(sm.xs[lb][kk][lane + 32 * r]);
-    }
-    nu2 = warp_sum_f(nu2);
-    if (lane == 0 && kk < len) {
-      float en = 0.f;
-#pragma unroll
-      for (int r = 0; r < CL; ++r) en += sm.enx[r][kk];
-      const float E = en / nu2;
-      const float inc = sm.incv[ds][kk];
-      const float arg = 1.0f + (E * inc) / A;
-      const float gE = wb * (-sm.sv[ds][kk] / arg);
-      const float alpha = 2.0f * gE / nu2;
-      sm.alphas[ds][kk] = alpha;
-      sm.betas[ds][kk] = -alpha * E;
-      gAacc += (double)wb * (double)E * (double)inc / ((double)A * (double)A * (double)arg);
-    }
-  };
-
   float2 lam = make_float2(0.f, 0.f);  // adjoint of x_{k+1,i}, replicated over the NQ lanes
   if (VIRT) if (lam_end) lam = lam_end[(size_t)b * DP + i];
   float gf = 0.f;
@@ -450,13 +463,7 @@ __global__ void __launch_bounds__(512)
     cp_async_wait<1>();
     __syncthreads();
     prep_elementwise(cl);
-    __syncthreads();
-    for (int kk = 0; kk < chunk_len(cl); ++kk) expectation_step(cl & 1, kk);
-    __syncthreads();
     cluster_sync_all();   // every CTA of the cluster has started: remote shared memory is addressable
-    prep_partial(cl);
-    cluster_sync_all();
-    prep_totals(cl);
   }
 
   // lanes jq < CL broadcast mu_{k,i} into CTA jq: st.async completing on the target's mbar[p & 1]
@@ -469,13 +476,11 @@ __global__ void __launch_bounds__(512)
   for (int c = nchunks - 1; c >= 0; --c) {
     const int lb = c % 3, ds = c & 1;
     const int len = chunk_len(c);
-    const bool has_prev = c >= 1;
-    const int pds = ds ^ 1;
     if (c >= 2) issue_loads(c - 2);
     cp_async_commit();
     cp_async_wait<1>();   // chunk c-1 has landed
     __syncthreads();      // (T1) alphas/betas of chunk c visible
-    if (has_prev) prep_elementwise(c - 1);
+    if (c >= 1) prep_elementwise(c - 1);
     const float sc = sm.scs[lb][0];
 
     float2 mu;
@@ -485,7 +490,7 @@ __global__ void __launch_bounds__(512)
       gf = fmaf(sm.dtk[ds][kk], lam.x * xn.y - lam.y * xn.x, gf);   // Im(conj(lam) x_{k+1})
       mu = cmul_ca(sm.qs[lb][kk][i], lam);
       const float al = sm.alphas[ds][kk];
-      const float2 sp = sm.sps[ds][kk][il];
+      const float2 sp = sm.spl[lb][kk][il];
       mu.x = fmaf(al, sp.x, mu.x * sc);
       mu.y = fmaf(al, sp.y, mu.y * sc);
       if (t == 0) mbar_arrive_expect_tx(&sm.mbar[pg & 1], MU_ROW);
@@ -495,8 +500,7 @@ __global__ void __launch_bounds__(512)
     }
     __syncthreads();      // (T2) x' of chunk c-1 visible (the mu broadcast is awaited per step)
 
-    auto step = [&](auto prev_tag, int kk) {
-      constexpr bool PREV = decltype(prev_tag)::value;     // chunk c-1 exists (expectation filler)
+    auto step = [&](int kk) {
       if (t == 0 && kk > 0) mbar_arrive_expect_tx(&sm.mbar[pg & 1], MU_ROW);   // arm this step's broadcast
       mbar_wait(&sm.mbar[(pg - 1) & 1], ((pg - 1) >> 1) & 1);                  // mu_kk is in
       float2 mv[CPT];
@@ -512,7 +516,7 @@ __global__ void __launch_bounds__(512)
       const int km = kk > 0 ? kk - 1 : 0;
       const float2 q1 = sm.qs[lb][km][i];
       const float al1 = sm.alphas[ds][km];
-      const float2 sp1 = sm.sps[ds][km][il];
+      const float2 sp1 = sm.spl[lb][km][il];
       const float dt1 = sm.dtk[ds][km];
       // ---- chain: lam_i = (L_k^dag mu)_i + beta x_{k,i} ----------------------------------
       float2 a0 = make_float2(0.f, 0.f), a1 = a0;
@@ -550,8 +554,6 @@ __global__ void __launch_bounds__(512)
       lp.y += oy;
       ox = __shfl_xor_sync(0xffffffffu, lp.x, 2);
       oy = __shfl_xor_sync(0xffffffffu, lp.y, 2);
-      // ---- filler 2: S x' of step kk of chunk c-1 ---------------------------------------
-      if (PREV) expectation_step(pds, kk);
       lp.x += ox;
       lp.y += oy;
       lp.x += __shfl_xor_sync(0xffffffffu, lp.x, 4);
@@ -572,17 +574,7 @@ __global__ void __launch_bounds__(512)
       if (kk > 0) ++pg;
     };
 
-    if (has_prev) {
-      for (int kk = len - 1; kk >= 0; --kk) step(TrueT{}, kk);
-      // chunk c-1 is always full; finish its expectation steps if this chunk was short
-      for (int kk = len; kk < CH4; ++kk) expectation_step(pds, kk);
-      __syncthreads();    // (E1) es / sps of chunk c-1 complete
-      prep_partial(c - 1);
-      cluster_sync_all(); // (X1)
-      prep_totals(c - 1);
-    } else {
-      for (int kk = len - 1; kk >= 0; --kk) step(FalseT{}, kk);
-    }
+    for (int kk = len - 1; kk >= 0; --kk) step(kk);
   }
   cp_async_wait<0>();
 
