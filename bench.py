@@ -55,7 +55,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -216,7 +216,6 @@ def run_ours(args):
     barrier()
     step_ms = [a.elapsed_time(b) for a, b in evs]
     launches = _lib.launch_count(local) - launches0
-    clocks = sampler.stop()
 
     # ---- kernel durations (library event pairs on the launch stream), a few extra synchronised steps
     _lib.set_profiling(local, True)
@@ -261,6 +260,7 @@ def run_ours(args):
     e2e_ms = [a.elapsed_time(b) for a, b in marks]
     e2e_ms[0] = max(e2e_ms[0], e0a.elapsed_time(marks[0][1]))
     final_loss = float(loss_host[0])
+    clocks = sampler.stop()       # sampled from the start of the timed region to the end of the e2e arm
 
     tot = torch.tensor([sum(step_ms), sum(e2e_ms)], dtype=torch.float64, device=dev)
     if world > 1:
