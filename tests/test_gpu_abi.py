@@ -156,3 +156,25 @@ def test_train_cli_trains_and_resumes(cuda, lib, tmp_path):
                                "--num_samples=0"])
     recs2 = [json.loads(l) for l in open(tmp_path / "fromtf" / "damped_sine" / f"8_{1/16000}_4" / "scalars.jsonl")]
     assert recs2[0]["step"] == 10
+
+
+def test_device_batch_prefetcher(cuda, lib):
+    """Double-buffered host -> device staging: batches come out in submission order, intact, and a
+    third submit without a next() is refused."""
+    from audio_mps_b200 import DeviceBatchPrefetcher
+    pf = DeviceBatchPrefetcher(cuda, (3, 1000))
+    hosts = [torch.full((3, 1000), float(k)).pin_memory() + torch.arange(1000)[None, :] for k in range(5)]
+    pf.submit(hosts[0])
+    for k in range(5):
+        x = pf.next()
+        if k + 1 < 5:
+            pf.submit(hosts[k + 1])
+        y = (x * 2).sum()                      # consume on the compute stream
+        pf.release()
+        assert torch.equal(x.cpu(), hosts[k]) and float(y) == float(hosts[k].sum() * 2)
+    pf.submit(hosts[0])
+    pf.submit(hosts[1])
+    with pytest.raises(RuntimeError):
+        pf.submit(hosts[2])
+    with pytest.raises(RuntimeError):
+        DeviceBatchPrefetcher(cuda, (1, 4)).next()
