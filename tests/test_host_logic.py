@@ -224,3 +224,44 @@ def test_model_tf_checkpoint_names(tmp_path):
     with pytest.raises(ValueError):                                  # shape mismatch is an error
         PsiCMPS(HParams(**{**hp.values(), "bond_dim": 6}), device="cpu").load_tf_checkpoint(
             str(tmp_path / "PsiCMPS" / "model.ckpt-7"))
+
+
+def test_tf_checkpoint_reads_snappy_compressed_index(tmp_path):
+    """Index tables written with snappy block compression (type byte 1) are decoded too: rewrite a
+    checkpoint's index with its data block stored as snappy (literals plus one back-reference)."""
+    import struct
+    from audio_mps_b200 import tf_checkpoint as tfc
+    # the decompressor itself: literal "abcd", copy(offset 4, len 8) -> "abcdabcdabcd", long literal
+    raw = b"abcd" * 3 + bytes(range(70))
+    comp = tfc._put_varint(len(raw)) + bytes([(4 - 1) << 2]) + b"abcd" + bytes([((8 - 4) << 2) | 1, 4]) \
+        + bytes([60 << 2, 70 - 1]) + bytes(range(70))
+    assert tfc._snappy_decompress(comp) == raw
+    # a whole index file with a compressed data block
+    tensors = {"model/A": np.float32(3.5), "model/freqs": np.arange(5, dtype=np.float32)}
+    prefix = str(tmp_path / "m.ckpt-1")
+    tfc.write_tf_checkpoint(prefix, tensors)
+    idx = open(prefix + ".index", "rb").read()
+    footer = idx[-48:]
+    _, p = tfc._get_varint(footer, 0)
+    _, p = tfc._get_varint(footer, p)
+    ioff, p = tfc._get_varint(footer, p)
+    isz, p = tfc._get_varint(footer, p)
+    (_, handle), = list(tfc._block_entries(tfc._read_block(idx, ioff, isz)))
+    boff, q = tfc._get_varint(handle, 0)
+    bsz, q = tfc._get_varint(handle, q)
+    block = idx[boff:boff + bsz]
+    lit = b""                                      # literal-only snappy stream, 60-byte pieces
+    for s0 in range(0, len(block), 60):
+        piece = block[s0:s0 + 60]
+        lit += bytes([(len(piece) - 1) << 2]) + piece
+    cblock = tfc._put_varint(len(block)) + lit
+    f = bytearray()
+    f += cblock + b"\x01" + struct.pack("<I", tfc.masked_crc32c(cblock + b"\x01"))
+    dh = tfc._put_varint(0) + tfc._put_varint(len(cblock))
+    mh = tfc._emit_block(f, tfc._build_block([]))
+    ih = tfc._emit_block(f, tfc._build_block([(b"\xff", dh)], restart_interval=1))
+    foot = mh + ih
+    f += foot + b"\x00" * (40 - len(foot)) + struct.pack("<Q", 0xDB4775248B80FB57)
+    open(prefix + ".index", "wb").write(bytes(f))
+    back = tfc.read_tf_checkpoint(prefix)
+    assert float(back["model/A"]) == 3.5 and np.array_equal(back["model/freqs"], tensors["model/freqs"])
