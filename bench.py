@@ -3,6 +3,7 @@
 
   python bench.py --gpus N --steps K --warmup W           # this repo's CUDA path
   python bench.py --impl reference --gpus N ...           # the reference's CPU algorithm (oracle port)
+  python bench.py --config c3|c4 ...                      # the other training configs of BASELINE.json
 
 A "step" is one training step of the hot path over one batch of synthetic clips: per-clip loss
 (forward scan), adjoint backward, raw-parameter chain + regulariser (train.py:55-60) and Adam
@@ -32,6 +33,22 @@ METRIC = "AudioMPS fwd+bwd audio samples/s (D=32, 4 s 16 kHz clips)"
 UNIT = "samples/s"
 D, B_PER_GPU, T = 32, 64, 64000
 WORKLOAD = "C1: PsiCMPS training step D=32, 64 clips/GPU x 64000 samples (4 s @ 16 kHz), damped-sine clips"
+# --config: the other training configs of BASELINE.json through the same harness (default: C1, the
+# configuration the metric is quoted on)
+CONFIGS = {
+    "c1": (32, 64, "C1"),
+    "c3": (128, 128, "C3 (bond dimension and batch; run on the row-split cluster kernels)"),
+    "c4": (64, 256, "C4 (per-GPU share of the global batch 2048 at 8 GPUs)"),
+}
+
+
+def select_config(name):
+    global D, B_PER_GPU, WORKLOAD, METRIC
+    D, B_PER_GPU, tag = CONFIGS[name]
+    if name != "c1":
+        METRIC = f"AudioMPS fwd+bwd audio samples/s (D={D}, 4 s 16 kHz clips)"
+        WORKLOAD = (f"{tag}: PsiCMPS training step D={D}, {B_PER_GPU} clips/GPU x {T} samples "
+                    f"(4 s @ 16 kHz), damped-sine clips")
 
 
 def hparams_kw():
@@ -139,7 +156,7 @@ def run_reference(args):
         return 0
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    t_sample = args.ref_tsample
+    t_sample = max(100, int(args.ref_tsample * (32 / D) ** 2 * 64 / B_PER_GPU))
     for _ in range(args.warmup):
         cpu_port_step(min(t_sample, 200))
     times = [cpu_port_step(t_sample) for _ in range(args.steps)]
@@ -285,9 +302,10 @@ def run_ours(args):
         fwd_flops = units * (20 * D * D + 40 * D)
         bwd_flops = units * (36 * D * D + 60 * D)
         fma_peak = float(_lib.load().amps_fma_peak_tflops(_lib.context(local)))
-        clustered = 2 * B_PER_GPU <= 148 and os.environ.get("AMPS_NO_CLUSTER") != "1"
-        kn = "cl_kernel" if clustered else "kernel"
-        kinfo = {"fwd": (f"psi_fwd_{kn}<32,4>", fwd_t, fwd_flops), "bwd": (f"psi_bwd_{kn}<32,4>", bwd_t, bwd_flops)}
+        clustered = D <= 32 and 2 * B_PER_GPU <= 148 and os.environ.get("AMPS_NO_CLUSTER") != "1"
+        kn = ("cl_kernel<%d,4>" % D) if clustered else ("kernel<%d,4>" % D) if D <= 32 else \
+            "uni_kernel<64,8>" if D <= 64 else "c4_kernel<128,4>"
+        kinfo = {"fwd": (f"psi_fwd_{kn}", fwd_t, fwd_flops), "bwd": (f"psi_bwd_{kn}", bwd_t, bwd_flops)}
         dom = "fwd" if fwd_t >= bwd_t else "bwd"
         oth = "bwd" if dom == "fwd" else "fwd"
 
@@ -301,13 +319,16 @@ def run_ours(args):
         d = entry(dom)
         # dram__bytes_read+write per launch of the same kernels at this exact workload, from the
         # committed ncu --set full capture (profiles/r1_ncu_cluster.md)
-        ncu_traffic = {"fwd": 2.106e9, "bwd": 2.172e9} if clustered else {"fwd": None, "bwd": None}
+        ncu_traffic = {"fwd": 2.106e9, "bwd": 2.172e9} if (clustered and D == 32 and B_PER_GPU == 64) \
+            else {"fwd": None, "bwd": None}
         roof = {"bound": "hbm", "kernel": d["kernel"], "achieved": d["achieved"], "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": d["frac"], "traffic": ncu_traffic[dom],
                 "traffic_source": "profiles/r1_ncu_cluster.md", "peak_source": peak_src,
                 "kernel_ms": d["kernel_ms"],
-                "note": "the path is dependent-step-latency / FP32-issue bound, not HBM bound (SURVEY 0.10): "
-                        "one clip per SM pair advances one step per ~300-360 cycles; see fp32 and other_kernel",
+                "note": ("the path is dependent-step-latency / FP32-issue bound, not HBM bound (SURVEY 0.10): "
+                         "one clip per SM pair advances one step per ~300-360 cycles; see fp32 and other_kernel")
+                if D <= 32 else ("not HBM bound: the 16-warp D >= 64 kernels are bound by the LSU data pipe "
+                                 "(profiles/r1_ncu_uni.md); see fp32 and other_kernel"),
                 "fp32": {"achieved_tflops": d["fp32_achieved_tflops"], "peak_tflops": fma_peak,
                          "peak_source": "FFMA microbenchmark in this run (amps_fma_peak_tflops)",
                          "frac": d["fp32_frac"]},
@@ -317,7 +338,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
-            ts = args.ref_tsample
+            ts = max(100, int(args.ref_tsample * (32 / D) ** 2 * 64 / B_PER_GPU))
             cpu_port_step(100)
             sec = cpu_port_step(ts)
             cpu = {"value": B_PER_GPU * ts / sec, "unit": UNIT, "cores": cores, "kind": "port",
@@ -353,7 +374,10 @@ def main():
     ap.add_argument("--ref-tsample", type=int, default=1500,
                     help="time steps per CPU-baseline step (bounded sample of the 64000-sample clips)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c1", choices=sorted(CONFIGS),
+                    help="BASELINE.json training config (default c1 = the one the metric is quoted on)")
     args = ap.parse_args()
+    select_config(args.config)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
