@@ -67,6 +67,8 @@ SYMBOLS = {
                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "amps_psi_loss_bwd_scan": (C.c_int, [C.c_void_p, C.POINTER(AmpsParams), C.c_void_p, C.c_int, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "amps_psi_params_fwd": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_float] * 4 + [C.c_void_p] * 5),
+    "amps_psi_params_bwd": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_float] * 4 + [C.c_void_p] * 11),
     "amps_comm_unique_id": (C.c_int, [C.c_void_p]),
     "amps_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "amps_allreduce_grads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

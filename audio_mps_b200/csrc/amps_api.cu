@@ -1042,6 +1042,42 @@ int amps_rho_sample(amps_ctx* ctx, const amps_params* p, const float* noise_dev,
   return AMPS_OK;
 }
 
+// ---- a1 / a2: raw variables <-> effective parameters, regulariser --------------------------------
+int amps_psi_params_fwd(amps_ctx* ctx, int D, const float* Rx_dev, const float* Ry_dev,
+                        const float* freqs_raw_dev, const float* psi_x_dev, const float* psi_y_dev,
+                        float r_scale, float f_scale, float h_reg, float r_reg, float* R_eff_dev,
+                        float* freqs_eff_dev, float* psi0_dev, float* aux_dev, void* stream) {
+  if (!ctx) return AMPS_E_INVALID;
+  if (D <= 0) return fail(ctx, AMPS_E_INVALID, "bond dimension D=%d must be positive", D);
+  if (!Rx_dev || !Ry_dev || !freqs_raw_dev || !psi_x_dev || !psi_y_dev || !R_eff_dev || !freqs_eff_dev ||
+      !psi0_dev || !aux_dev)
+    return fail(ctx, AMPS_E_INVALID, "NULL buffer");
+  psi_params_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(Rx_dev, Ry_dev, freqs_raw_dev, psi_x_dev, psi_y_dev, D,
+                                                             r_scale, f_scale, h_reg, r_reg, (float2*)R_eff_dev,
+                                                             freqs_eff_dev, (float2*)psi0_dev, aux_dev);
+  LAUNCH_CHECK(ctx, "psi_params_fwd_kernel");
+  return AMPS_OK;
+}
+
+int amps_psi_params_bwd(amps_ctx* ctx, int D, const float* Rx_dev, const float* Ry_dev,
+                        const float* freqs_raw_dev, const float* psi_x_dev, const float* psi_y_dev,
+                        float r_scale, float f_scale, float h_reg, float r_reg, const float* aux_dev,
+                        const float* gR_dev, const float* gfreqs_dev, const float* gpsi0_dev,
+                        const float* greg_dev, float* gRx_dev, float* gRy_dev, float* gfreqs_raw_dev,
+                        float* gpsi_x_dev, float* gpsi_y_dev, void* stream) {
+  if (!ctx) return AMPS_E_INVALID;
+  if (D <= 0) return fail(ctx, AMPS_E_INVALID, "bond dimension D=%d must be positive", D);
+  if (!Rx_dev || !Ry_dev || !freqs_raw_dev || !psi_x_dev || !psi_y_dev || !aux_dev || !gR_dev || !gfreqs_dev ||
+      !gpsi0_dev || !gRx_dev || !gRy_dev || !gfreqs_raw_dev || !gpsi_x_dev || !gpsi_y_dev)
+    return fail(ctx, AMPS_E_INVALID, "NULL buffer");
+  psi_params_bwd_kernel<<<1, 256, (size_t)D * sizeof(float2), (cudaStream_t)stream>>>(
+      Rx_dev, Ry_dev, freqs_raw_dev, psi_x_dev, psi_y_dev, D, r_scale, f_scale, h_reg, r_reg, aux_dev,
+      (const float2*)gR_dev, gfreqs_dev, (const float2*)gpsi0_dev, greg_dev, gRx_dev, gRy_dev, gfreqs_raw_dev,
+      gpsi_x_dev, gpsi_y_dev);
+  LAUNCH_CHECK(ctx, "psi_params_bwd_kernel");
+  return AMPS_OK;
+}
+
 // ---- data-parallel communicator over NCCL (NVLink / NVSwitch) --------------------------------
 int amps_comm_unique_id(void* id_out) {
   if (!id_out) return AMPS_E_INVALID;

@@ -196,4 +196,112 @@ __global__ void psi_lab_traj_kernel(const float2* __restrict__ traj, const float
   }
 }
 
+// -------------------------------------------------------------------------------------------
+// a1 / a2 of the path in ONE launch each way: raw variables -> effective parameters and the
+// regulariser (model.py:36-50, 218-222, 327-334; train.py:55-60), and the reverse chain.  Replaces
+// ~60 tiny framework kernels per training step.  Single CTA; sums in double.
+//   R = r_s (Rx + i Ry),  R_eff[i][j] = R[i][j] - R[j][j]  (the diagonal-broadcast quirk, model.py:42)
+//   f_eff = f_s f_raw;   psi0 = z rsqrt(max(sum |z|^2, 1e-12)),  z = psi_x + i psi_y
+//   reg = h_reg sum f_eff^2 + r_reg sum |R_eff|^2
+// aux[0] = reg, aux[1] = rsqrt(max(|z|^2, eps)), aux[2] = 1 if the clamp is inactive
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum_d(double v, double* red) {
+  v = warp_sum_d(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double tot = 0.0;
+  for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) tot += red[wv];
+  __syncthreads();
+  return tot;
+}
+
+__global__ void psi_params_fwd_kernel(const float* __restrict__ Rx, const float* __restrict__ Ry,
+                                      const float* __restrict__ fraw, const float* __restrict__ px,
+                                      const float* __restrict__ py, int D, float r_s, float f_s, float h_reg,
+                                      float r_reg, float2* __restrict__ R_eff, float* __restrict__ f_eff,
+                                      float2* __restrict__ psi0, float* __restrict__ aux) {
+  __shared__ double red[32];
+  double accR = 0.0, accF = 0.0, accP = 0.0;
+  for (int idx = threadIdx.x; idx < D * D; idx += blockDim.x) {
+    const int j = idx % D;
+    const float rx = __fsub_rn(__fmul_rn(r_s, Rx[idx]), __fmul_rn(r_s, Rx[j * D + j]));
+    const float ry = __fsub_rn(__fmul_rn(r_s, Ry[idx]), __fmul_rn(r_s, Ry[j * D + j]));
+    R_eff[idx] = make_float2(rx, ry);
+    accR += (double)rx * rx + (double)ry * ry;
+  }
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    const float f = __fmul_rn(f_s, fraw[c]);
+    f_eff[c] = f;
+    accF += (double)f * f;
+    const float n = hypotf(px[c], py[c]);      // |z| via complex abs, then squared (model.py:331-334)
+    accP += (double)__fmul_rn(n, n);
+  }
+  accR = block_sum_d(accR, red);
+  accF = block_sum_d(accF, red);
+  accP = block_sum_d(accP, red);
+  const float n2 = (float)accP;
+  const float rs = rsqrtf(fmaxf(n2, 1e-12f));
+  for (int c = threadIdx.x; c < D; c += blockDim.x) psi0[c] = make_float2(px[c] * rs, py[c] * rs);
+  if (threadIdx.x == 0) {
+    aux[0] = (float)((double)h_reg * accF + (double)r_reg * accR);
+    aux[1] = rs;
+    aux[2] = n2 > 1e-12f ? 1.f : 0.f;
+  }
+}
+
+// gR, gpsi0: dL/dRe + i dL/dIm of the effective tensors; greg: dL/dreg (device scalar)
+__global__ void psi_params_bwd_kernel(const float* __restrict__ Rx, const float* __restrict__ Ry,
+                                      const float* __restrict__ fraw, const float* __restrict__ px,
+                                      const float* __restrict__ py, int D, float r_s, float f_s, float h_reg,
+                                      float r_reg, const float* __restrict__ aux, const float2* __restrict__ gR,
+                                      const float* __restrict__ gf, const float2* __restrict__ gp,
+                                      const float* __restrict__ greg, float* __restrict__ gRx,
+                                      float* __restrict__ gRy, float* __restrict__ gfraw,
+                                      float* __restrict__ gpx, float* __restrict__ gpy) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* cs = reinterpret_cast<float2*>(smem_raw);      // [D] column sums of G
+  __shared__ double red[32];
+  const float gr = greg ? greg[0] : 0.f;
+  const float kR = 2.0f * r_reg * gr;
+  auto G = [&](int k, int j) {
+    const float rx = __fsub_rn(__fmul_rn(r_s, Rx[k * D + j]), __fmul_rn(r_s, Rx[j * D + j]));
+    const float ry = __fsub_rn(__fmul_rn(r_s, Ry[k * D + j]), __fmul_rn(r_s, Ry[j * D + j]));
+    const float2 g = gR[k * D + j];
+    return make_float2(fmaf(kR, rx, g.x), fmaf(kR, ry, g.y));
+  };
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    double sx = 0.0, sy = 0.0;
+    for (int k = 0; k < D; ++k) {
+      const float2 g = G(k, j);
+      sx += g.x;
+      sy += g.y;
+    }
+    cs[j] = make_float2((float)sx, (float)sy);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < D * D; idx += blockDim.x) {
+    const int i = idx / D, j = idx % D;
+    float2 g = G(i, j);
+    if (i == j) {                                  // R_eff[k][j] = R[k][j] - R[j][j] for every k
+      g.x -= cs[j].x;
+      g.y -= cs[j].y;
+    }
+    gRx[idx] = r_s * g.x;
+    gRy[idx] = r_s * g.y;
+  }
+  const float rs = aux[1];
+  const bool free_norm = aux[2] != 0.f;
+  double dot = 0.0;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    gfraw[c] = f_s * fmaf(2.0f * h_reg * gr, __fmul_rn(f_s, fraw[c]), gf[c]);
+    dot += (double)(px[c] * rs) * gp[c].x + (double)(py[c] * rs) * gp[c].y;   // Re <psi0, g>
+  }
+  dot = block_sum_d(dot, red);
+  const float dt = free_norm ? (float)dot : 0.f;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    gpx[c] = (gp[c].x - (px[c] * rs) * dt) * rs;
+    gpy[c] = (gp[c].y - (py[c] * rs) * dt) * rs;
+  }
+}
+
 }  // namespace amps

@@ -114,6 +114,45 @@ class _PsiLossFn(torch.autograd.Function):
         return gR, gf, gp, gA, None, None, None
 
 
+class _PsiParamsFn(torch.autograd.Function):
+    """Raw variables -> (R_eff, freqs_eff, psi_0, regulariser) in one kernel each way
+    (amps_psi_params_fwd / _bwd): model.py:36-50, 218-222; train.py:55-60."""
+
+    @staticmethod
+    def forward(ctx, Rx, Ry, fraw, px, py, model):
+        dev = Rx.device
+        lib = _lib.load()
+        h = _lib.context(dev.index if dev.index is not None else torch.cuda.current_device())
+        D = fraw.shape[0]
+        raws = [t.detach().contiguous().float() for t in (Rx, Ry, fraw, px, py)]
+        R_ri = torch.empty(D, D, 2, dtype=torch.float32, device=dev)
+        f = torch.empty(D, dtype=torch.float32, device=dev)
+        p0 = torch.empty(D, 2, dtype=torch.float32, device=dev)
+        aux = torch.empty(4, dtype=torch.float32, device=dev)
+        sc = (float(model._r_scale), float(model._f_scale), float(model.h_reg), float(model.r_reg))
+        rc = lib.amps_psi_params_fwd(h, D, *[_ptr(t) for t in raws], *sc, _ptr(R_ri), _ptr(f), _ptr(p0),
+                                     _ptr(aux), _stream(dev))
+        _lib.check(h, rc)
+        ctx.keep = (raws, aux, sc, h, D)
+        ctx.mark_non_differentiable(aux)
+        return R_ri, f, p0, aux[0], aux
+
+    @staticmethod
+    def backward(ctx, gR, gf, gp, greg, _gaux):
+        raws, aux, sc, h, D = ctx.keep
+        lib = _lib.load()
+        dev = aux.device
+        gR = gR.contiguous().float()
+        gf = gf.contiguous().float()
+        gp = gp.contiguous().float()
+        greg = greg.reshape(1).contiguous().float()
+        outs = [torch.empty_like(t) for t in raws]
+        rc = lib.amps_psi_params_bwd(h, D, *[_ptr(t) for t in raws], *sc, _ptr(aux), _ptr(gR), _ptr(gf),
+                                     _ptr(gp), _ptr(greg), *[_ptr(t) for t in outs], _stream(dev))
+        _lib.check(h, rc)
+        return (*outs, None)
+
+
 class _RhoLossFn(torch.autograd.Function):
     """Per-clip RhoCMPS loss through amps_rho_loss_fwd / amps_rho_loss_bwd."""
 
@@ -351,13 +390,20 @@ class PsiCMPS(CMPS):
     def loss_per_clip(self, data=None, time_parallel: Optional[bool] = None) -> torch.Tensor:
         """loss_b of the fold, before the reduce_mean (model.py:257-267); differentiable.
         ``time_parallel``: force (True) or forbid (False) the parallel-in-time scan; None = policy."""
+        return self.loss_per_clip_and_regulariser(data, time_parallel)[0]
+
+    def loss_per_clip_and_regulariser(self, data=None, time_parallel: Optional[bool] = None):
+        """(loss_b [B], h_reg |freqs|^2 + r_reg |R|^2): the raw -> effective parameter chain of
+        model.py:36-50, 218-222 and the regulariser of train.py:55-60 come from one fused kernel
+        (amps_psi_params_fwd) instead of a few dozen framework launches; both are differentiable."""
         self._require_cuda()
         x = self._batch(data)
         if time_parallel is None:
             need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
             time_parallel = self._use_scan(x.shape[0], x.shape[1], need_grad)
-        return _PsiLossFn.apply(torch.view_as_real(self.R), self.freqs,
-                                torch.view_as_real(self.psi_0), self.A, x, self, bool(time_parallel))
+        R_ri, f, p0_ri, reg, _ = _PsiParamsFn.apply(self.Rx, self.Ry, self.freqs_raw, self.psi_x, self.psi_y, self)
+        lpc = _PsiLossFn.apply(R_ri, f, p0_ri, self.A, x, self, bool(time_parallel))
+        return lpc, reg
 
     def loss_fn(self, data=None) -> torch.Tensor:
         return self.loss_per_clip(data).mean()                              # model.py:267

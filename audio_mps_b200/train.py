@@ -40,7 +40,9 @@ class Trainer:
     def __init__(self, model, learning_rate: Optional[float] = None, group=None, native_comm: bool = False):
         self.model = model
         lr = learning_rate if learning_rate is not None else getattr(model.hparams, "learning_rate", 1e-3)
-        self.opt = torch.optim.Adam(model.parameters(), lr=lr, betas=(0.9, 0.999), eps=1e-8)
+        on_gpu = all(p.is_cuda for p in model.parameters())
+        self.opt = torch.optim.Adam(model.parameters(), lr=lr, betas=(0.9, 0.999), eps=1e-8,
+                                    fused=True if on_gpu else None)      # one launch per step on the GPU
         self.group = group
         self.world = dist.get_world_size(group) if (group is not None or dist.is_initialized()) else 1
         if self.world > 1:
@@ -49,11 +51,14 @@ class Trainer:
 
     def step(self, x_local, global_batch: Optional[int] = None, regularise: bool = True):
         m = self.model
-        lpc = m.loss_per_clip(x_local)
+        if hasattr(m, "loss_per_clip_and_regulariser"):      # Psi: parameter chain + regulariser fused
+            lpc, reg = m.loss_per_clip_and_regulariser(x_local)
+        else:
+            lpc, reg = m.loss_per_clip(x_local), (regulariser(m) if regularise else None)
         gb = global_batch if global_batch is not None else lpc.shape[0] * self.world
         data_term = lpc.sum() / gb
         self.opt.zero_grad(set_to_none=True)
-        obj = data_term + regulariser(m) if regularise else data_term
+        obj = data_term + reg if regularise else data_term
         obj.backward()
         self.opt.step()
         self.global_step += 1

@@ -192,6 +192,26 @@ int amps_rho_sample(amps_ctx* ctx, const amps_params* p, const float* noise_dev,
                     float* out_dev, float* traj_dev, float* purity_dev, void* ws_dev,
                     size_t ws_bytes, void* stream);
 
+/* CMPS.__init__ / PsiCMPS.__init__ parameterisation (model.py:36-50, 218-222, 327-334) and the
+ * regulariser of train.py:55-60 in one launch, and its reverse chain -- so that a training step does
+ * not spend ~60 framework launches on O(D^2) bookkeeping.
+ *   R_eff[i,j] = r_scale*(Rx+iRy)[i,j] - r_scale*(Rx+iRy)[j,j]   (r_scale = rsqrt(r_reg), or 1 with R_in)
+ *   freqs_eff  = f_scale*freqs_raw                                (f_scale = rsqrt(h_reg), or 1 with freqs_in)
+ *   psi0       = (psi_x+i psi_y) * rsqrt(max(sum|.|^2, 1e-12))
+ *   aux_dev float32[4]: [0] = h_reg*sum freqs_eff^2 + r_reg*sum |R_eff|^2, [1..2] = state for the backward
+ * Backward: gR/gpsi0 complex64 (dL/dRe + i dL/dIm), gfreqs float32, greg_dev = dL/d aux[0] (device scalar,
+ * may be NULL = 0); outputs are the gradients wrt the raw variables. */
+int amps_psi_params_fwd(amps_ctx* ctx, int D, const float* Rx_dev, const float* Ry_dev,
+                        const float* freqs_raw_dev, const float* psi_x_dev, const float* psi_y_dev,
+                        float r_scale, float f_scale, float h_reg, float r_reg, float* R_eff_dev,
+                        float* freqs_eff_dev, float* psi0_dev, float* aux_dev, void* stream);
+int amps_psi_params_bwd(amps_ctx* ctx, int D, const float* Rx_dev, const float* Ry_dev,
+                        const float* freqs_raw_dev, const float* psi_x_dev, const float* psi_y_dev,
+                        float r_scale, float f_scale, float h_reg, float r_reg, const float* aux_dev,
+                        const float* gR_dev, const float* gfreqs_dev, const float* gpsi0_dev,
+                        const float* greg_dev, float* gRx_dev, float* gRy_dev, float* gfreqs_raw_dev,
+                        float* gpsi_x_dev, float* gpsi_y_dev, void* stream);
+
 /* ---- data parallelism: ONE all-reduce of the packed gradient per step ------------------------
  * Batch is the only shard axis (model.py:258-267): every rank runs amps_psi_loss_fwd/_bwd on its clips
  * with w_b = 1/B_global and sums the packed buffer [gR | gfreqs | gpsi0 | gA | sum_b w_b loss_b]
