@@ -630,7 +630,7 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
         (const float2*)(ws + L.G), (const float*)(ws + L.gf), (const float2*)(ws + L.lam0), B, DP,
         (float2*)(ws + L.Gtot), (float*)(ws + L.gftot), (float2*)(ws + L.lam0tot));
     LAUNCH_CHECK(ctx, "psi_reduce_clips_kernel");
-    psi_grad_finalize_kernel<<<1, 256, 0, st>>>(
+    psi_grad_finalize_kernel<<<p->D, 128, 0, st>>>(
         (const float2*)(ws + L.Gtot), (const float*)(ws + L.gftot), (const float2*)(ws + L.lam0tot),
         (const double*)(ws + L.gAdir), (const double*)(ws + L.lossd), w_dev, B,
         (const float2*)(ws + L.matR), p->D, DP, cprime, aval(p), grad_dev);
@@ -817,7 +817,7 @@ int amps_psi_loss_bwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
         (const float2*)(ws + L.G), (const float*)(ws + L.gf), (const float2*)(ws + L.lam0), nv, DP,
         (float2*)(ws + L.Gtot), (float*)(ws + L.gftot), (float2*)(ws + L.lam0tot), L.nvc);
     LAUNCH_CHECK(ctx, "psi_reduce_clips_kernel");
-    psi_grad_finalize_kernel<<<1, 256, 0, st>>>(
+    psi_grad_finalize_kernel<<<p->D, 128, 0, st>>>(
         (const float2*)(ws + L.Gtot), (const float*)(ws + L.gftot), (const float2*)(ws + L.lam0tot),
         (const double*)(ws + L.gAdir), (const double*)(ws + L.lossv), (const float*)(ws + L.wv), nv,
         (const float2*)(ws + L.base.matR), p->D, DP, cprime, aval(p), grad_dev);

@@ -112,7 +112,7 @@ __global__ void psi_reduce_clips_kernel(const float2* __restrict__ G, const floa
   }
 }
 
-// Packed gradient wrt the effective parameters (single CTA):
+// Packed gradient wrt the effective parameters (grid = D CTAs, one row of gR each):
 //   gR = G_R + G_E + cprime * R (G_N + G_N^dag)
 //   gA = -(1/A) Re sum conj(G_R) R + sum_b gAdir[b]
 //   out = [ gR (2 D^2) | gf (D) | gpsi0 (2 D) | gA | sum_b w_b loss_b ]
@@ -129,9 +129,10 @@ __global__ void psi_grad_finalize_kernel(const float2* __restrict__ Gtot,
   const float2* GR = Gtot;
   const float2* GN = Gtot + DP * DP;
   const float2* GE = Gtot + 2 * DP * DP;
-  double part = 0.0;  // Re sum conj(GR) R
-  for (int idx = threadIdx.x; idx < D * D; idx += blockDim.x) {
-    const int i = idx / D, j = idx % D;
+  // grid = D CTAs: CTA i writes row i of gR; CTA 0 also writes the vector / scalar slots
+  const int i = blockIdx.x;
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    const int idx = i * D + j;
     double cr = 0.0, ci = 0.0;  // (R H)_ij, H = GN + GN^dag
     for (int m = 0; m < D; ++m) {
       const float2 r = matR[i * DP + m];
@@ -143,7 +144,12 @@ __global__ void psi_grad_finalize_kernel(const float2* __restrict__ Gtot,
     const float2 gr = GR[i * DP + j], ge = GE[i * DP + j];
     out[2 * idx] = (float)((double)gr.x + ge.x + cprime * cr);
     out[2 * idx + 1] = (float)((double)gr.y + ge.y + cprime * ci);
-    const float2 r = matR[i * DP + j];
+  }
+  if (blockIdx.x != 0) return;
+  double part = 0.0;  // Re sum conj(GR) R
+  for (int idx = threadIdx.x; idx < D * D; idx += blockDim.x) {
+    const int a = idx / D, c = idx % D;
+    const float2 gr = GR[a * DP + c], r = matR[a * DP + c];
     part += (double)gr.x * r.x + (double)gr.y * r.y;
   }
   float* o = out + 2 * D * D;
