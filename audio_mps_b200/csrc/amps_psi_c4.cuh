@@ -5,9 +5,11 @@
 // [32 rank, 32 rank + 32), 16 lanes per row, 8 complex columns of N, R (R^dag), S per thread -- the
 // same per-thread shape as the D = 64 kernels.  Every CTA keeps the FULL state vector of the
 // current chunk in its own shared memory; each step ends with the owners broadcasting their 32 new
-// entries into all four CTAs through distributed shared memory (st.shared::cluster) and ONE
-// barrier.cluster, which replaces the __syncthreads of the single-CTA kernels.  Scalars that need all
-// rows (E_k = x'^dag S x') are combined once per 16-step chunk by exchanging per-CTA partial sums.
+// entries into all four CTAs through distributed shared memory with st.async ... mbarrier::complete_tx
+// (data and completion signal in one instruction); consumers wait on their own mbarrier, so neither a
+// barrier.cluster nor a __syncthreads sits on the per-step path.  The forward combines the scalars
+// that need all rows (E_k = x'^dag S x') once per 16-step chunk by exchanging per-CTA partial sums and
+// stores (S x'_k)_i (own rows) and (E_k, |x_k|^2) for the backward, which then needs no exchange.
 //
 //   model.py:257-267, 276-282, 293-334 (forward), train.py:89 (adjoint) -- same chain form and
 //   adjoint as amps_psi.cuh; chunk length CH4 = 16 (rescale / exchange period).
