@@ -1,4 +1,4 @@
-// Parallel-in-time forward scan for small batches (K4): the clip is cut into `nvc` time chunks;
+// Parallel-in-time scan for small batches (K4), forward and adjoint: the clip is cut into `nvc` time chunks;
 //   1. psi_compose_tc_kernel  -- one CTA per (clip, chunk) composes the chunk's step operators
 //        C_j = W_{k0+m-1} ... W_{k0},   W_k = diag(q_k) (I + E_k),   E_k = c' R^dag R + s_k R
 //      on the 5th-generation tensor cores: complex D x D operators as real 2D x 2D matrices
@@ -11,6 +11,9 @@
 //   2. psi_scan_boundary_kernel -- sequential over the nvc chunk operators: chunk start states.
 //   3. the sequential forward kernel replays every chunk from its start state as an independent
 //      "virtual clip" (loss terms, optional trajectory).
+//   backward (amps_psi_loss_bwd_scan): 4. virtual-clip adjoint with a zero end condition (chain only) ->
+//      d_j;  5. psi_scan_boundary_bwd_kernel: Lam_j = d_j + C_j^dag Lam_{j+1} / |C_j y_j|, sequential over
+//      the stored chunk operators;  6. virtual-clip adjoint from the true end adjoints (gradient tiles).
 // Costs 8 D^3 flops per step instead of 24 D^2 (x21 at D = 64) but turns ONE latency-bound chain of
 // T steps into 148 chains of T/148 steps: worthwhile only when the batch cannot fill the GPU.
 #pragma once
