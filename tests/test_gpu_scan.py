@@ -106,3 +106,27 @@ def test_scan_degenerate_lengths(cuda, lib, T):
     g_seq = torch.autograd.grad(l_seq.mean(), ps)
     for n, a, b in zip(NAMES, g_scan, g_seq):
         assert rel(a.cpu().numpy(), b.cpu().numpy()) <= 1e-3, n
+
+
+def test_scan_random_shapes(cuda, lib):
+    """Seeded sweep of the scan's chunking arithmetic (virtual clips per clip = floor(148 / B), chunk
+    lengths rounded to 32 steps): odd bond dimensions, batches around the 74 / 148 boundaries, short and
+    ragged lengths; loss and gradients against the one-chain-per-clip kernels."""
+    rng = np.random.default_rng(77)
+    cases = [(3, 1, 97), (8, 2, 1500), (17, 3, 640), (32, 5, 2049), (33, 7, 333), (64, 16, 700),
+             (12, 20, 130), (64, 37, 65), (16, 74, 100), (9, 75, 64), (5, 149, 40), (64, 2, 4097)]
+    for D, B, T in cases:
+        ohp, php = hp_pair(bond_dim=D, minibatch_size=B)
+        raw = random_raw_params(ohp, np.random.default_rng(int(rng.integers(1 << 30))))
+        data = damped_sine(B, T, ohp.delta_t, np.random.default_rng(int(rng.integers(1 << 30))))
+        m = PsiCMPS(php, device=cuda)
+        set_raw(m, raw)
+        ps = [getattr(m, n) for n in NAMES]
+        w = torch.linspace(0.7, 1.3, B, device=cuda) / B
+        l_seq = m.loss_per_clip(data, time_parallel=False)
+        l_scan = m.loss_per_clip(data, time_parallel=True)
+        assert rel(l_scan.detach().cpu().numpy(), l_seq.detach().cpu().numpy()) <= 1e-4, (D, B, T)
+        g_seq = torch.autograd.grad((l_seq * w).sum(), ps)
+        g_scan = torch.autograd.grad((l_scan * w).sum(), ps)
+        for n, a, b in zip(NAMES, g_scan, g_seq):
+            assert rel(a.cpu().numpy(), b.cpu().numpy()) <= 1e-3, (D, B, T, n)
