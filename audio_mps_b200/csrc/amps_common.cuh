@@ -79,6 +79,25 @@ __device__ __forceinline__ float2 lds64(const float2* p) {
   return v;
 }
 
+// 128-bit shared load as a volatile asm statement: volatile asms keep their relative order, so a run of
+// these is issued back to back exactly where it is written (ptxas otherwise sinks each LDS next to
+// its first use and exposes one shared-memory latency per load on the chain's critical path), without
+// the dependent FADD chain that tie_loads() needs for the same effect (ncu source page: ~30 cycles per
+// step, profiles/r1_chain_source.md).  `saddr` is a shared-window address (see smem_addr_pinned).
+__device__ __forceinline__ float4 lds128v(unsigned saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+// Shared-window address of `p`, made opaque to the optimiser: without this ptxas re-derives the
+// per-thread address from %tid inside the step loop (an S2R + three ALU ops on the critical path
+// after every second barrier).
+__device__ __forceinline__ unsigned smem_addr_pinned(const void* p) {
+  unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(p));
+  asm volatile("" : "+r"(a));
+  return a;
+}
+
 // Scheduling aid: makes the first use of a freshly loaded register slice depend on EVERY 128-bit
 // load of that slice, so ptxas issues all the LDS back to back right after the barrier instead of
 // sinking each one next to its first use (which exposes one shared-memory latency per load on the
