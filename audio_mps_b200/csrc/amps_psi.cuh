@@ -160,15 +160,15 @@ __global__ void __launch_bounds__(2 * DP * NQ)
         float2* const st2 = (jq == 0) ? &sm.xs[p][1][i] : &sm.xps[p][0][i];
         const bool st2_on = jq < 2;
         float s_cur = sm.sv[p][0];
+        const unsigned xs_addr = smem_addr_pinned(&sm.xs[p][0][2 * jq]);
         auto step = [&](int kk) {
           float2 xv[CPT];
 #pragma unroll
           for (int m = 0; m < CPT / 2; ++m) {
-            const float4 v = *reinterpret_cast<const float4*>(&sm.xs[p][kk][2 * NQ * m + 2 * jq]);
+            const float4 v = lds128v(xs_addr + (unsigned)((kk * DP + 2 * NQ * m) * sizeof(float2)));
             xv[2 * m] = make_float2(v.x, v.y);
             xv[2 * m + 1] = make_float2(v.z, v.w);
           }
-          tie_loads(xv);
           const float2 q = sm.qs[p][kk][i];
           const float s_next = sm.sv[p][kk + 1];
           float2 a0 = make_float2(0.f, 0.f), a1 = a0;
@@ -347,15 +347,15 @@ __global__ void __launch_bounds__(2 * DP * NQ)
           sts_if(mu_on, mu_st + (len - 1) * DP, mu);
         }
         bar_named(1, NTC);
+        const unsigned mus_addr = smem_addr_pinned(&sm.mus[ca][0][2 * jq]);
         auto step = [&](int kk) {
           float2 mv[CPT];
 #pragma unroll
           for (int m = 0; m < NP; ++m) {
-            const float4 v = *reinterpret_cast<const float4*>(&sm.mus[ca][kk][2 * NQ * m + 2 * jq]);
+            const float4 v = lds128v(mus_addr + (unsigned)((kk * DP + 2 * NQ * m) * sizeof(float2)));
             mv[2 * m] = make_float2(v.x, v.y);
             mv[2 * m + 1] = make_float2(v.z, v.w);
           }
-          tie_loads(mv);
           const float s = sm.sv[c % 3][kk];
           const float4 b4 = sm.cinb[ca][kk][i];                    // { beta x_k , dtm x_k }
           const float4 a4 = sm.cina[ca][kk > 0 ? kk - 1 : 0][i];   // { c q , alpha S x' } of step kk-1
