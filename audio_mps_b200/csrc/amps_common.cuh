@@ -98,6 +98,29 @@ __device__ __forceinline__ unsigned smem_addr_pinned(const void* p) {
   return a;
 }
 
+// Address-based shared-memory accessors (32-bit shared-window addresses, see smem_addr_pinned): hot
+// loops that index shared memory through generic pointers make the compiler convert generic ->
+// shared inside the loop, which on sm_100 re-reads %cluster_ctaid (S2UR/S2R, tens of cycles).
+__device__ __forceinline__ float lds32a(unsigned a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float2 lds64a(unsigned a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts32a_if(bool on, unsigned a, float v) {
+  asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.b32 pp, %0, 0;\n\t@pp st.shared.f32 [%1], %2;\n\t}\n" ::"r"((int)on), "r"(a), "f"(v)
+               : "memory");
+}
+__device__ __forceinline__ void sts64a_if(bool on, unsigned a, float2 v) {
+  asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.b32 pp, %0, 0;\n\t@pp st.shared.v2.f32 [%1], {%2, %3};\n\t}\n" ::"r"((int)on), "r"(a),
+               "f"(v.x), "f"(v.y)
+               : "memory");
+}
+
 // Scheduling aid: makes the first use of a freshly loaded register slice depend on EVERY 128-bit
 // load of that slice, so ptxas issues all the LDS back to back right after the barrier instead of
 // sinking each one next to its first use (which exposes one shared-memory latency per load on the

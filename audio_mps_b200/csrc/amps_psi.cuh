@@ -1131,8 +1131,11 @@ __global__ void __launch_bounds__(DP* NQ)
       cp_async4(&sm.nz[buf][idx], noise + (size_t)(k0 + idx) * n + b);
   };
 
+  // shared-window addresses of the step loop's arrays, computed once (see lds64a)
+  const unsigned xs_a = smem_addr_pinned(&sm.xs[0][0]), wred_a = smem_addr_pinned(&sm.wred[0][0][0]);
+  const unsigned qs_a = smem_addr_pinned(&sm.qs[0][0][0]), nz_a = smem_addr_pinned(&sm.nz[0][0]);
+  const unsigned outs_a = smem_addr_pinned(&sm.outs[0]);
   float X = 0.f;  // cumulative sample, replicated in every thread (identical arithmetic)
-  int cur = 0;
   if (nchunks > 0) issue_loads(0, 0);
   cp_async_commit();
 
@@ -1145,12 +1148,32 @@ __global__ void __launch_bounds__(DP* NQ)
     cp_async_wait<1>();
     __syncthreads();
 
-    for (int kk = 0; kk < len; ++kk) {
-      float2 a, y;
-      matvec2<DP, NQ>(Nr, Rr, sm.xs[cur], jq, a, y);
+    // One step reads state buffer CUR and writes CUR ^ 1.  CUR is a compile-time constant (steps are
+    // issued in pairs; every chunk but the last has an even length, so a chunk always starts at 0):
+    // with a run-time buffer index the compiler formed generic pointers into shared memory and
+    // re-read %cluster_ctaid (S2UR/S2R, ~40 cycles each) inside every step to convert them back
+    // (ncu source page, profiles/r1_chain_source.md).
+    const unsigned qs_b = qs_a + (unsigned)(buf * CH * DP * sizeof(float2));
+    const unsigned nz_b = nz_a + (unsigned)(buf * CH * sizeof(float));
+    auto step = [&](auto cur_tag, int kk) {
+      constexpr int CUR = decltype(cur_tag)::value;
+      constexpr unsigned XO = CUR * DP * sizeof(float2), XN = (CUR ^ 1) * DP * sizeof(float2);
+      constexpr unsigned WO = CUR * 32 * 2 * sizeof(float);
+      // a = N x, y = R x (partial over this thread's columns), state read with ordered 128-bit loads
+      float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+#pragma unroll
+      for (int m = 0; m < CPT / 2; ++m) {
+        const float4 xv = lds128v(xs_a + XO + (unsigned)((2 * NQ * m + 2 * jq) * sizeof(float2)));
+        const float2 x0 = make_float2(xv.x, xv.y), x1 = make_float2(xv.z, xv.w);
+        cmac(a0, Nr[2 * m], x0);
+        cmac(a1, Nr[2 * m + 1], x1);
+        cmac(b0, Rr[2 * m], x0);
+        cmac(b1, Rr[2 * m + 1], x1);
+      }
+      float2 a = make_float2(a0.x + a1.x, a0.y + a1.y), y = make_float2(b0.x + b1.x, b0.y + b1.y);
       a = group_sum_fast<NQ>(a);
       y = group_sum_fast<NQ>(y);
-      const float2 xi = sm.xs[cur][i];
+      const float2 xi = lds64a(xs_a + XO + (unsigned)(i * sizeof(float2)));
       // <x, R x> and |x|^2 over rows: values are replicated over the NQ lanes of a group
       float e = fmaf(xi.x, y.x, xi.y * y.y);
       float nn = cabs2(xi);
@@ -1159,29 +1182,29 @@ __global__ void __launch_bounds__(DP* NQ)
         e += __shfl_xor_sync(0xffffffffu, e, m);
         nn += __shfl_xor_sync(0xffffffffu, nn, m);
       }
-      const int par = kk & 1;
-      if (lane == 0) {
-        sm.wred[par][warp][0] = e;
-        sm.wred[par][warp][1] = nn;
-      }
+      sts64a_if(lane == 0, wred_a + WO + (unsigned)(warp * 2 * sizeof(float)), make_float2(e, nn));
       __syncthreads();
       float es = 0.f, nsum = 0.f;
 #pragma unroll
       for (int wv = 0; wv < NW; ++wv) {
-        es += sm.wred[par][wv][0];
-        nsum += sm.wred[par][wv][1];
+        const float2 w2 = lds64a(wred_a + WO + (unsigned)(wv * 2 * sizeof(float)));
+        es += w2.x;
+        nsum += w2.y;
       }
       const float E = 2.0f * es / nsum;                                  // model.py:319-325
-      const float inc = __fadd_rn(__fmul_rn(E, dtf), sm.nz[buf][kk]);    // model.py:286
+      const float inc = __fadd_rn(__fmul_rn(E, dtf), lds32a(nz_b + (unsigned)(kk * sizeof(float))));   // model.py:286
       X = __fadd_rn(X, inc);                                             // model.py:287
       const float s = inc / A;                                           // model.py:303
       const float rn = rsqrtf(nsum);   // lagged normalisation keeps |x| ~ 1
       float2 xp = make_float2(fmaf(s, y.x, a.x) * rn, fmaf(s, y.y, a.y) * rn);
-      const float2 xn = cmul(sm.qs[buf][kk][i], xp);
-      if (jq == 0) sm.xs[cur ^ 1][i] = xn;
-      if (t == 0) sm.outs[kk] = A * X;                                   // model.py:251
-      cur ^= 1;
+      const float2 xn = cmul(lds64a(qs_b + (unsigned)((kk * DP + i) * sizeof(float2))), xp);
+      sts64a_if(jq == 0, xs_a + XN + (unsigned)(i * sizeof(float2)), xn);
+      sts32a_if(t == 0, outs_a + (unsigned)(kk * sizeof(float)), A * X);   // model.py:251
       __syncthreads();
+    };
+    for (int kk = 0; kk < len; kk += 2) {
+      step(IC0{}, kk);
+      if (kk + 1 < len) step(IC1{}, kk + 1);
     }
     if (t < len) out[(size_t)b * L + k0 + t] = sm.outs[t];
     // outs is rewritten only after the next chunk's first two barriers
