@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(512)
       constexpr int STAGE = decltype(stage_tag)::value;
       constexpr bool FIRST = STAGE == 0;
       if (t == 0) mbar_arrive_expect_tx(&sm.xbar[sg & 1], STEP_TX);          // arm this step's phase
-      if (!FIRST) mbar_wait(&sm.xbar[(sg - 1) & 1], ((sg - 1) >> 1) & 1);    // previous step's rows are in
+      if (!FIRST) mbar_wait_cta(&sm.xbar[(sg - 1) & 1], ((sg - 1) >> 1) & 1);    // previous step's rows are in
       float2 xv[CPT], pv[CPT];
 #pragma unroll
       for (int m = 0; m < CPT / 2; ++m) {
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(512)
     } else {
       for (int kk = 2; kk < len; ++kk) step(IC2{}, kk);
     }
-    mbar_wait(&sm.xbar[(sg - 1) & 1], ((sg - 1) >> 1) & 1);   // the chunk's last broadcast has landed
+    mbar_wait_cta(&sm.xbar[(sg - 1) & 1], ((sg - 1) >> 1) & 1);   // the chunk's last broadcast has landed
     {  // drain: step len-2's partial is in part_pp; the chunk's last step has none yet
       if (len >= 2) sts_if(ex_on, spf_st + (len - 2) * (2 * RP), pair_reduce<NQ>(part_pp, jq));
       const float2 part = matvec1<DP, NQ>(Sr, sm.xps[len - 1], jq);
@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(512)
 
     auto step = [&](int kk) {
       if (t == 0 && kk > 0) mbar_arrive_expect_tx(&sm.mbar[pg & 1], MU_ROW);   // arm this step's broadcast
-      mbar_wait(&sm.mbar[(pg - 1) & 1], ((pg - 1) >> 1) & 1);                  // mu_kk is in
+      mbar_wait_cta(&sm.mbar[(pg - 1) & 1], ((pg - 1) >> 1) & 1);                  // mu_kk is in
       float2 mv[CPT];
 #pragma unroll
       for (int m = 0; m < NP; ++m) {
