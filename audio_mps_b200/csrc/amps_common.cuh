@@ -68,21 +68,10 @@ __device__ __forceinline__ void sts_if(bool on, float* p, float v) {
                : "memory");
 }
 
-// 64-bit shared load that the compiler may not fuse into LDS.128: on sm_100a an LDS.128 is always
-// issued as 4 quarter-warp wavefronts, while an LDS.64 whose lanes read <= 128 distinct bytes is a
-// single wavefront (ncu, profiles/r1_smem_wavefronts.md) -- the chain's state-vector loads are
-// 8-lane broadcasts, so two LDS.64 cost half the shared-memory pipe time of one LDS.128.
-__device__ __forceinline__ float2 lds64(const float2* p) {
-  const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(p));
-  float2 v;
-  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "r"(a));
-  return v;
-}
-
 // 128-bit shared load as a volatile asm statement: volatile asms keep their relative order, so a run of
 // these is issued back to back exactly where it is written (ptxas otherwise sinks each LDS next to
 // its first use and exposes one shared-memory latency per load on the chain's critical path), without
-// the dependent FADD chain that tie_loads() needs for the same effect (ncu source page: ~30 cycles per
+// a dependent FADD chain tying the loads together, which an earlier version used (ncu source page: ~30 cycles per
 // step, profiles/r1_chain_source.md).  `saddr` is a shared-window address (see smem_addr_pinned).
 __device__ __forceinline__ float4 lds128v(unsigned saddr) {
   float4 v;
@@ -119,19 +108,6 @@ __device__ __forceinline__ void sts64a_if(bool on, unsigned a, float2 v) {
   asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.b32 pp, %0, 0;\n\t@pp st.shared.v2.f32 [%1], {%2, %3};\n\t}\n" ::"r"((int)on), "r"(a),
                "f"(v.x), "f"(v.y)
                : "memory");
-}
-
-// Scheduling aid: makes the first use of a freshly loaded register slice depend on EVERY 128-bit
-// load of that slice, so ptxas issues all the LDS back to back right after the barrier instead of
-// sinking each one next to its first use (which exposes one shared-memory latency per load on the
-// chain's critical path -- ncu, profiles/r1_chain_schedule.md).  fmaf(g, 0, x) is not foldable
-// without fast-math.
-template <int N>
-__device__ __forceinline__ void tie_loads(float2 (&v)[N]) {
-  float g = 0.f;
-#pragma unroll
-  for (int m = 2; m < N; m += 2) g += v[m].x;
-  v[0].x = fmaf(g, 0.0f, v[0].x);
 }
 
 // The trainable scalar A (model.py:19) reaches the kernels either by value (host float) or through a
