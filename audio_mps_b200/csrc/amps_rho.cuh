@@ -153,12 +153,14 @@ __global__ void __launch_bounds__(RHO_MAX_D * RHO_MAX_D) rho_scan_kernel(RhoArgs
   // The per-step global inputs (waveform / noise sample, phases) are fetched ONE STEP AHEAD into
   // registers, so their L2 latency is off the step's critical path.
   const float* xb = SAMPLE ? nullptr : g.x + (size_t)b * g.T;
-  auto in_at = [&](int k) -> float {
+  // (raw loads only: the increment x[k+1] - x[k] is formed when it is used, one step later, so that no
+  // instruction of the current step waits on the prefetch)
+  auto raw_at = [&](int k) -> float {          // noise[k] (sampling) or waveform sample x[k + 1] (data)
     if (k >= nsteps) return 0.f;
-    if (SAMPLE) return g.noise[(size_t)k * g.n + b];
-    return xb[k + 1] - xb[k];                                              // model.py:134-135
+    return SAMPLE ? g.noise[(size_t)k * g.n + b] : xb[k + 1];
   };
-  float in_next = in_at(0);
+  float x_lo = (SAMPLE || nsteps == 0) ? 0.f : xb[0];
+  float raw_next = raw_at(0);
   float2 q_next = make_float2(1.f, 0.f), p_next = q_next;
   if (t < D && nsteps > 0) {
     q_next = g.qtab[t];
@@ -166,8 +168,10 @@ __global__ void __launch_bounds__(RHO_MAX_D * RHO_MAX_D) rho_scan_kernel(RhoArgs
   }
   for (int k = 0; k < nsteps; ++k) {
     // phases for this step (threads < D): q_k = p_k conj(p_{k+1}),  p_{k+1} for the lab frame
-    const float in_cur = in_next;
-    in_next = in_at(k + 1);
+    const float raw_cur = raw_next;
+    raw_next = raw_at(k + 1);
+    const float in_cur = SAMPLE ? raw_cur : raw_cur - x_lo;                // model.py:134-135
+    x_lo = raw_cur;
     if (t < D) {
       qv[t] = q_next;
       if (g.traj) pv[t] = p_next;
@@ -337,9 +341,9 @@ __global__ void __launch_bounds__(RHO_MAX_D * RHO_MAX_D) rho_bwd_kernel(RhoBwdAr
 
   // inputs of step k-1 are fetched during step k (registers): waveform increment, time difference,
   // phases and the stored rho~_{k-1}; rho~_{k+1} of a step is the previous step's rho~_k.
-  auto inc_at = [&](int k) { return k >= 0 ? xb[k + 1] - xb[k] : 0.f; };
-  auto dl_at = [&](int k) { return k >= 0 ? g.ttab[k] - g.ttab[k + 1] : 0.f; };
-  float inc_next = inc_at(nsteps - 1), dl_next = dl_at(nsteps - 1);
+  // raw loads only (x[k], t_k of the NEXT step); differences are formed when used
+  float x_hi = nsteps > 0 ? xb[nsteps] : 0.f, t_hi = nsteps > 0 ? g.ttab[nsteps] : 0.f;
+  float x_next = nsteps > 0 ? xb[nsteps - 1] : 0.f, t_next = nsteps > 0 ? g.ttab[nsteps - 1] : 0.f;
   float2 q_next = make_float2(1.f, 0.f), rho_next = make_float2(0.f, 0.f), rho_prev = rho_next;
   if (nsteps > 0) {
     if (t < D) q_next = g.qtab[(size_t)(nsteps - 1) * D + t];
@@ -349,11 +353,16 @@ __global__ void __launch_bounds__(RHO_MAX_D * RHO_MAX_D) rho_bwd_kernel(RhoBwdAr
     }
   }
   for (int k = nsteps - 1; k >= 0; --k) {
-    const float inc = inc_next, dl = dl_next;
+    const float x_k = x_next, t_k = t_next;
+    const float inc = x_hi - x_k, dl = t_k - t_hi;       // x[k+1] - x[k],  t_k - t_{k+1}
+    x_hi = x_k;
+    t_hi = t_k;
+    if (k > 0) {
+      x_next = xb[k - 1];
+      t_next = g.ttab[k - 1];
+    }
     const float s = inc / g.A;
     const float2 rk = rho_next, rn = rho_prev;
-    inc_next = inc_at(k - 1);
-    dl_next = dl_at(k - 1);
     if (act) {
       rho[ts] = rk;
       Lm[ts] = make_float2(fmaf(s, Rac.x, Nac.x), fmaf(s, Rac.y, Nac.y));
