@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(TC_THREADS)
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_N >> 4) << 24);
 
   for (int kk = 0; kk <= nloc; ++kk) {
-    if (kk > 0) mbar_wait(&sm.mbar, (kk - 1) & 1);     // the MMAs of step kk-1 are complete
+    if (kk > 0) mbar_wait_cta(&sm.mbar, (kk - 1) & 1); // the MMAs of step kk-1 are complete (tcgen05.commit)
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     if (tid >= 128) {
       if (kk < nloc) {

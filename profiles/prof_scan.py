@@ -17,4 +17,4 @@ x = torch.from_numpy(damped_sine(B, T, hp.delta_t, np.random.default_rng(1))).to
 for _ in range(2):
     l = m.loss_per_clip_scan(x)
 torch.cuda.synchronize()
-print("scan loss", l.cpu().numpy())
+print("scan loss", l.detach().cpu().numpy())
