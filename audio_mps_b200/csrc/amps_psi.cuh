@@ -338,13 +338,18 @@ __global__ void __launch_bounds__(2 * DP * NQ)
     for (int c = nchunks; c >= -1; --c) {
       if (c >= 0 && c < nchunks) {
         const int ca = c & 1, len = chunk_len(c);
-        float2* const mu_st = &sm.mus[ca][0][i];
+        // shared-window addresses of this chunk's chain inputs, computed once (see lds64a)
+        const unsigned mu_a = smem_addr_pinned(&sm.mus[ca][0][i]);
+        const unsigned cina_a = smem_addr_pinned(&sm.cina[ca][0][i]);
+        const unsigned cinb_a = smem_addr_pinned(&sm.cinb[ca][0][i]);
+        const unsigned sv_a = smem_addr_pinned(&sm.sv[c % 3][0]);
+        constexpr unsigned ROW4 = DP * sizeof(float4), ROW2 = DP * sizeof(float2);
         {  // adjoint of x' for the chunk's last step (its q carries the rescale c_k)
-          const float4 a4 = sm.cina[ca][len - 1][i];
+          const float4 a4 = lds128v(cina_a + (unsigned)(len - 1) * ROW4);
           float2 mu = cmul_ca(make_float2(a4.x, a4.y), lam);
           mu.x += a4.z;
           mu.y += a4.w;
-          sts_if(mu_on, mu_st + (len - 1) * DP, mu);
+          sts64a_if(mu_on, mu_a + (unsigned)(len - 1) * ROW2, mu);
         }
         bar_named(1, NTC);
         const unsigned mus_addr = smem_addr_pinned(&sm.mus[ca][0][2 * jq]);
@@ -356,9 +361,10 @@ __global__ void __launch_bounds__(2 * DP * NQ)
             mv[2 * m] = make_float2(v.x, v.y);
             mv[2 * m + 1] = make_float2(v.z, v.w);
           }
-          const float s = sm.sv[c % 3][kk];
-          const float4 b4 = sm.cinb[ca][kk][i];                    // { beta x_k , dtm x_k }
-          const float4 a4 = sm.cina[ca][kk > 0 ? kk - 1 : 0][i];   // { c q , alpha S x' } of step kk-1
+          const unsigned km = (unsigned)(kk > 0 ? kk - 1 : 0);
+          const float s = lds32a(sv_a + (unsigned)kk * (unsigned)sizeof(float));
+          const float4 b4 = lds128v(cinb_a + (unsigned)kk * ROW4);   // { beta x_k , dtm x_k }
+          const float4 a4 = lds128v(cina_a + km * ROW4);             // { c q , alpha S x' } of step kk-1
           float2 a0 = make_float2(0.f, 0.f), a1 = a0;
 #pragma unroll
           for (int cc = 0; cc < CPT; cc += 2) {
@@ -376,7 +382,7 @@ __global__ void __launch_bounds__(2 * DP * NQ)
           float2 mu = cmul_ca(make_float2(a4.x, a4.y), lam);
           mu.x += a4.z;
           mu.y += a4.w;
-          sts_if(mu_on && kk > 0, mu_st + (kk > 0 ? kk - 1 : 0) * DP, mu);
+          sts64a_if(mu_on && kk > 0, mu_a + km * ROW2, mu);
           bar_named(1, NTC);
         };
         if (len == CHK) {
