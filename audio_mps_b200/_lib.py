@@ -73,8 +73,10 @@ SYMBOLS = {
     "amps_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "amps_allreduce_grads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "amps_comm_destroy": (C.c_int, [C.c_void_p]),
+    "amps_time_table_host": (C.c_int, [C.c_double, C.c_int, C.c_void_p]),
+    "amps_psi_sample_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "amps_psi_sample": (C.c_int, [C.c_void_p, C.POINTER(AmpsParams), C.c_void_p, C.c_int, C.c_int,
-                                  C.c_void_p, C.c_void_p]),
+                                  C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "amps_psi_evolve": (C.c_int, [C.c_void_p, C.POINTER(AmpsParams), C.c_void_p, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "amps_psi_loss_grad_host": (C.c_int, [C.c_void_p, C.POINTER(AmpsHostParams), C.c_void_p, C.c_int,
@@ -130,7 +132,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError if the symbol is not exported
             fn.restype = restype
             fn.argtypes = argtypes
-        if lib.amps_version() < 100:
+        if lib.amps_version() < 200:
             raise ImportError("libaudiomps.so is older than this Python package")
         _lib = lib
         return lib

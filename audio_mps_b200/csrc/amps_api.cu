@@ -27,14 +27,7 @@ struct amps_ctx {
   bool use_clusters = true;   // AMPS_NO_CLUSTER=1 disables the 2-CTA cluster kernels
   char err[512] = {0};
   int64_t launches = 0;
-  // cached float32 time table
-  float* ttab = nullptr;
-  int ttab_n = 0;
-  uint32_t ttab_dtbits = 0;
-  // context-owned scratch for entry points without a caller workspace
-  void* scratch = nullptr;
-  size_t scratch_bytes = 0;
-  // host-entry buffers
+  // host-entry buffers (amps_psi_loss_grad_host only; the device entry points own no memory)
   void* hbuf = nullptr;
   size_t hbuf_bytes = 0;
   cudaStream_t hstream = nullptr;
@@ -185,7 +178,7 @@ int dispatch_dp(int DP, F&& f) {
 }
 
 struct PsiWs {
-  size_t matN, matR, matRH, matS, psi0p, qtab, lossd;
+  size_t matN, matR, matRH, matS, psi0p, ttab, qtab, lossd;
   size_t traj, scales, G, gf, lam0, gAdir, Gtot, gftot, lam0tot, sptraj, ev;
   size_t total;
 };
@@ -204,6 +197,7 @@ PsiWs psi_ws_layout(int DP, int B, int nsteps_tab, int T, bool save) {
   w.matRH = take(mat);
   w.matS = take(mat);
   w.psi0p = take((size_t)DP * sizeof(float2));
+  w.ttab = take((size_t)(nsteps_tab > 0 ? nsteps_tab + 2 : 2) * sizeof(float));   // t_k, k = 0..nsteps_tab
   w.qtab = take((size_t)(nsteps_tab > 0 ? nsteps_tab : 1) * DP * sizeof(float2));
   w.lossd = take((size_t)(B > 0 ? B : 1) * sizeof(double));
   if (save) {
@@ -228,35 +222,6 @@ PsiWs psi_ws_layout(int DP, int B, int nsteps_tab, int T, bool save) {
   return w;
 }
 
-int ensure_ttab(amps_ctx* ctx, int n, float dt32, cudaStream_t st) {
-  uint32_t bits;
-  memcpy(&bits, &dt32, 4);
-  if (ctx->ttab && ctx->ttab_n >= n && ctx->ttab_dtbits == bits) return AMPS_OK;
-  if (ctx->ttab) {
-    CUDA_TRY(ctx, cudaFree(ctx->ttab));
-    ctx->ttab = nullptr;
-  }
-  int cap = n < 70000 ? 70000 : n + n / 4;
-  CUDA_TRY(ctx, cudaMalloc(&ctx->ttab, (size_t)cap * sizeof(float)));
-  prep_ttab_kernel<<<1, 32, 0, st>>>(dt32, cap, ctx->ttab);
-  LAUNCH_CHECK(ctx, "prep_ttab_kernel");
-  ctx->ttab_n = cap;
-  ctx->ttab_dtbits = bits;
-  return AMPS_OK;
-}
-
-int ensure_scratch(amps_ctx* ctx, size_t bytes) {
-  if (ctx->scratch_bytes >= bytes) return AMPS_OK;
-  if (ctx->scratch) {
-    CUDA_TRY(ctx, cudaFree(ctx->scratch));
-    ctx->scratch = nullptr;
-    ctx->scratch_bytes = 0;
-  }
-  CUDA_TRY(ctx, cudaMalloc(&ctx->scratch, bytes));
-  ctx->scratch_bytes = bytes;
-  return AMPS_OK;
-}
-
 int check_common(amps_ctx* ctx, const amps_params* p) {
   if (!ctx) return AMPS_E_INVALID;
   if (!p) return fail(ctx, AMPS_E_INVALID, "params is NULL");
@@ -270,8 +235,10 @@ int check_common(amps_ctx* ctx, const amps_params* p) {
 int psi_prepare(amps_ctx* ctx, const amps_params* p, int DP, char* ws, const PsiWs& L,
                 int nsteps_tab, cudaStream_t st) {
   const double cprime = -p->delta_t * (double)p->sigma * (double)p->sigma / 2.0;  // model.py:312
-  int rc = ensure_ttab(ctx, nsteps_tab + 1, (float)p->delta_t, st);
-  if (rc) return rc;
+  // float32 time table of THIS call (model.py:16,281), into the caller's workspace: the backward and the
+  // trajectory kernels read it from there, so no entry point depends on context state
+  prep_ttab_kernel<<<1, 1024, 0, st>>>((float)p->delta_t, nsteps_tab + 1, (float*)(ws + L.ttab));
+  LAUNCH_CHECK(ctx, "prep_ttab_kernel");
   prep_mats_kernel<<<(DP * DP + 255) / 256, 256, 0, st>>>(
       (const float2*)p->R_dev, p->D, DP, cprime, (float2*)(ws + L.matN), (float2*)(ws + L.matR),
       (float2*)(ws + L.matRH), (float2*)(ws + L.matS));
@@ -283,7 +250,7 @@ int psi_prepare(amps_ctx* ctx, const amps_params* p, int DP, char* ws, const Psi
     const size_t total = (size_t)nsteps_tab * DP;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    prep_qtab_kernel<<<blocks, 256, 0, st>>>(p->freqs_dev, p->D, DP, ctx->ttab, nsteps_tab,
+    prep_qtab_kernel<<<blocks, 256, 0, st>>>(p->freqs_dev, p->D, DP, (const float*)(ws + L.ttab), nsteps_tab,
                                              (float2*)(ws + L.qtab));
     LAUNCH_CHECK(ctx, "prep_qtab_kernel");
   }
@@ -311,22 +278,20 @@ cudaError_t launch_cluster(K kern, int nclusters, int CL, int threads, size_t sm
 }
 constexpr int C4_CL = 4;
 
-// Rho phase tables (q_k, and p_{k+1} when a lab-frame trajectory is wanted) in the context scratch
-int rho_phase_tables(amps_ctx* ctx, const amps_params* p, int nsteps, bool need_p, cudaStream_t st,
-                     const float2** qtab, const float2** ptab) {
-  const size_t n = (size_t)(nsteps > 0 ? nsteps : 1) * p->D;
-  int rc = ensure_scratch(ctx, align_up(n * sizeof(float2)) * (need_p ? 2 : 1));
-  if (rc) return rc;
-  float2* q = (float2*)ctx->scratch;
-  float2* pp = need_p ? (float2*)((char*)ctx->scratch + align_up(n * sizeof(float2))) : nullptr;
+// Rho tables of one call -- float32 t_k, q_k, and p_{k+1} when a lab-frame trajectory is wanted -- into
+// the caller's workspace
+int rho_tables(amps_ctx* ctx, const amps_params* p, int nsteps, bool need_p, char* ws, const RhoWs& L,
+               cudaStream_t st) {
+  prep_ttab_kernel<<<1, 1024, 0, st>>>((float)p->delta_t, nsteps + 1, (float*)(ws + L.ttab));
+  LAUNCH_CHECK(ctx, "prep_ttab_kernel");
   if (nsteps > 0) {
+    const size_t n = (size_t)nsteps * p->D;
     int blocks = (int)((n + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    rho_prep_phase_kernel<<<blocks, 256, 0, st>>>(p->freqs_dev, ctx->ttab, nsteps, p->D, q, pp);
+    rho_prep_phase_kernel<<<blocks, 256, 0, st>>>(p->freqs_dev, (const float*)(ws + L.ttab), nsteps, p->D,
+                                                  (float2*)(ws + L.qtab), need_p ? (float2*)(ws + L.ptab) : nullptr);
     LAUNCH_CHECK(ctx, "rho_prep_phase_kernel");
   }
-  *qtab = q;
-  *ptab = pp;
   return AMPS_OK;
 }
 
@@ -360,8 +325,6 @@ int amps_destroy(amps_ctx* ctx) {
   if (!ctx) return AMPS_E_INVALID;
   cudaSetDevice(ctx->device);
   if (ctx->nccl_comm) amps_comm_destroy(ctx);
-  if (ctx->ttab) cudaFree(ctx->ttab);
-  if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->hbuf) cudaFree(ctx->hbuf);
   if (ctx->hstream) cudaStreamDestroy(ctx->hstream);
   for (int i = 0; i < 3; ++i)
@@ -421,6 +384,17 @@ double amps_fma_peak_tflops2(amps_ctx* ctx, int packed) {
 
 const char* amps_last_error(const amps_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 int64_t amps_launch_count(const amps_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// float32 running-sum time table on the HOST (same piecewise-exact generator as the device kernel)
+int amps_time_table_host(double delta_t, int n, float* out) {
+  if (n < 0 || (n > 0 && !out)) return AMPS_E_INVALID;
+  TtSeg segs[TT_MAXSEG];
+  const int nseg = tt_build((float)delta_t, n, out, segs, TT_MAXSEG);
+  for (int s = 0; s < nseg; ++s)
+    for (int j = 1; j <= segs[s].m; ++j)
+      out[segs[s].k0 + j] = (float)((double)segs[s].t0 + (double)j * (double)segs[s].inc);
+  return AMPS_OK;
+}
 
 size_t amps_psi_grad_count(int D) { return D > 0 ? (size_t)2 * D * D + 3 * (size_t)D + 2 : 0; }
 
@@ -551,13 +525,12 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
   const int chl = chunk_len_of(DP);
   const int nchunks = (nsteps + chl - 1) / chl;
   const double cprime = -p->delta_t * (double)p->sigma * (double)p->sigma / 2.0;
-  if (!ctx->ttab || ctx->ttab_n < T) return fail(ctx, AMPS_E_STATE, "backward without a saving forward");
   if (DP == 128) {
     PROF_BEGIN(ctx, 1, st);
     CUDA_TRY(ctx, launch_cluster(psi_bwd_c4_kernel<128, C4_CL, false>, B, C4_CL, 512, sizeof(BwdC4Smem<128, C4_CL>), st,
                                  (const float2*)(ws + L.matN), (const float2*)(ws + L.matRH),
                                  (const float2*)(ws + L.matS), (const float2*)(ws + L.qtab),
-                                 (const float*)ctx->ttab, x_dev, T, aval(p), w_dev,
+                                 (const float*)(ws + L.ttab), x_dev, T, aval(p), w_dev,
                                  (const float2*)(ws + L.traj), (const float*)(ws + L.scales), nchunks,
                                  (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0),
                                  (double*)(ws + L.gAdir), (const float2*)nullptr, 0, 0,
@@ -588,7 +561,7 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
       PROF_BEGIN(ctx, 1, st);
       CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, kcl, (const float2*)(ws + L.matN), (const float2*)(ws + L.matRH),
                                        (const float2*)(ws + L.matS), (const float2*)(ws + L.qtab),
-                                       (const float*)ctx->ttab, x_dev, T, aval(p), w_dev,
+                                       (const float*)(ws + L.ttab), x_dev, T, aval(p), w_dev,
                                        (const float2*)(ws + L.traj), (const float*)(ws + L.scales), nchunks,
                                        (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0),
                                        (double*)(ws + L.gAdir), (const float2*)(ws + L.sptraj),
@@ -607,14 +580,14 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
     if constexpr (WS) {
       psi_bwd_kernel<DPc, NQc><<<B, 2 * DPc * NQc, smem, st>>>(
           (const float2*)(ws + L.matN), (const float2*)(ws + L.matRH), (const float2*)(ws + L.matS),
-          (const float2*)(ws + L.qtab), ctx->ttab, x_dev, T, aval(p), w_dev,
+          (const float2*)(ws + L.qtab), (const float*)(ws + L.ttab), x_dev, T, aval(p), w_dev,
           (const float2*)(ws + L.traj), (const float*)(ws + L.scales), nchunks,
           (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0), (double*)(ws + L.gAdir),
           (const float2*)(ws + L.sptraj), (const float2*)(ws + L.ev));
     } else {
       psi_bwd_uni_kernel<DPc, NQc><<<B, DPc * NQc, smem, st>>>(
           (const float2*)(ws + L.matN), (const float2*)(ws + L.matRH), (const float2*)(ws + L.matS),
-          (const float2*)(ws + L.qtab), ctx->ttab, x_dev, T, aval(p), w_dev,
+          (const float2*)(ws + L.qtab), (const float*)(ws + L.ttab), x_dev, T, aval(p), w_dev,
           (const float2*)(ws + L.traj), (const float*)(ws + L.scales), nchunks,
           (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0), (double*)(ws + L.gAdir),
           (const float2*)nullptr, 0, 0, (const float2*)(ws + L.sptraj), (const float2*)(ws + L.ev));
@@ -775,7 +748,6 @@ int amps_psi_loss_bwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
   const ScanWs L = scan_ws_layout(B, T, true);
   if (ws_bytes < L.total)
     return fail(ctx, AMPS_E_WORKSPACE, "workspace %zu < required %zu bytes", ws_bytes, L.total);
-  if (!ctx->ttab || ctx->ttab_n < T) return fail(ctx, AMPS_E_STATE, "backward without a saving forward");
   char* ws = (char*)ws_dev;
   const int DP = 64;
   const int nv = B * L.nvc;
@@ -791,7 +763,7 @@ int amps_psi_loss_bwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
     auto kern = lam_end ? kern_full : kern_chain;
     kern<<<nv, 64 * 8, smem, st>>>((const float2*)(ws + L.base.matN), (const float2*)(ws + L.base.matRH),
                                    (const float2*)(ws + L.base.matS), (const float2*)(ws + L.base.qtab),
-                                   (const float*)ctx->ttab, x_dev, T, aval(p), w_dev,
+                                   (const float*)(ws + L.base.ttab), x_dev, T, aval(p), w_dev,
                                    (const float2*)(ws + L.traj), (const float*)(ws + L.scales), 0,
                                    (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0),
                                    (double*)(ws + L.gAdir), lam_end, L.nvc, L.m_steps,
@@ -826,8 +798,14 @@ int amps_psi_loss_bwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
   return AMPS_OK;
 }
 
+size_t amps_psi_sample_workspace_bytes(int D, int L, int n) {
+  const int DP = padded_dim(D);
+  if (DP < 0 || L < 0 || n < 0) return 0;
+  return psi_ws_layout(DP, 0, L, 0, false).total;
+}
+
 int amps_psi_sample(amps_ctx* ctx, const amps_params* p, const float* noise_dev, int L_, int n,
-                    float* out_dev, void* stream) {
+                    float* out_dev, void* ws_dev, size_t ws_bytes, void* stream) {
   int rc = check_common(ctx, p);
   if (rc) return rc;
   if (!p->psi0_dev) return fail(ctx, AMPS_E_INVALID, "psi0_dev is NULL");
@@ -837,10 +815,10 @@ int amps_psi_sample(amps_ctx* ctx, const amps_params* p, const float* noise_dev,
   const int DP = padded_dim(p->D);
   if (DP < 0 || DP > 64) return fail(ctx, AMPS_E_UNSUPPORTED, "bond dimension %d > 64 not supported by the sampler", p->D);
   const PsiWs L = psi_ws_layout(DP, 0, L_, 0, false);
-  rc = ensure_scratch(ctx, L.total);
-  if (rc) return rc;
+  if (!ws_dev || ws_bytes < L.total)
+    return fail(ctx, AMPS_E_WORKSPACE, "workspace %zu < required %zu bytes", ws_bytes, L.total);
   cudaStream_t st = (cudaStream_t)stream;
-  char* ws = (char*)ctx->scratch;
+  char* ws = (char*)ws_dev;
   rc = psi_prepare(ctx, p, DP, ws, L, L_, st);
   if (rc) return rc;
   return dispatch_dp(DP, [&](auto dp, auto nq) -> int {
@@ -876,7 +854,7 @@ int amps_psi_evolve(amps_ctx* ctx, const amps_params* p, const float* x_dev, int
   const size_t items = (size_t)B * (T - 1);
   int blocks = (int)((items * 32 + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  psi_lab_traj_kernel<<<blocks, 256, 0, st>>>((const float2*)(ws + L.traj), p->freqs_dev, ctx->ttab,
+  psi_lab_traj_kernel<<<blocks, 256, 0, st>>>((const float2*)(ws + L.traj), p->freqs_dev, (const float*)(ws + L.ttab),
                                               B, T, p->D, DP, (float2*)traj_dev);
   LAUNCH_CHECK(ctx, "psi_lab_traj_kernel");
   return AMPS_OK;
@@ -957,12 +935,9 @@ int amps_rho_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
   if (ws_bytes < L.total) return fail(ctx, AMPS_E_WORKSPACE, "workspace %zu < required %zu bytes", ws_bytes, L.total);
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)ws_dev;
-  rc = ensure_ttab(ctx, T + 1, (float)p->delta_t, st);
+  rc = rho_tables(ctx, p, T - 1, false, ws, L, st);
   if (rc) return rc;
-  const float2 *qtab, *ptab;
-  rc = rho_phase_tables(ctx, p, T - 1, false, st, &qtab, &ptab);
-  if (rc) return rc;
-  rc = rho_launch_data(p, ctx->ttab, qtab, ptab, x_dev, B, T, loss_dev, nullptr,
+  rc = rho_launch_data(p, (const float*)(ws + L.ttab), (const float2*)(ws + L.qtab), nullptr, x_dev, B, T, loss_dev, nullptr,
                        save ? (float2*)(ws + L.ftraj) : nullptr, (double*)(ws + L.lossd), st);
   if (rc) return fail(ctx, rc, "rho kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   ctx->launches++;
@@ -984,11 +959,9 @@ int amps_rho_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
   if (p->D > RHO_MAX_D) return fail(ctx, AMPS_E_UNSUPPORTED, "rho kernels support D <= %d", RHO_MAX_D);
   const RhoWs L = rho_ws_layout(p->D, B, T, true);
   if (ws_bytes < L.total) return fail(ctx, AMPS_E_WORKSPACE, "workspace %zu < required %zu bytes", ws_bytes, L.total);
-  if (!ctx->ttab || ctx->ttab_n < T) return fail(ctx, AMPS_E_STATE, "backward without a saving forward");
-  const float2 *qtab, *ptab;
-  rc = rho_phase_tables(ctx, p, T - 1, false, st, &qtab, &ptab);
-  if (rc) return rc;
-  rc = rho_launch_bwd(p, ctx->ttab, qtab, x_dev, B, T, w_dev, (char*)ws_dev, L, grad_dev, st);
+  // t_k and q_k are the ones the saving forward left in this workspace
+  rc = rho_launch_bwd(p, (const float*)((char*)ws_dev + L.ttab), (const float2*)((char*)ws_dev + L.qtab), x_dev, B, T,
+                      w_dev, (char*)ws_dev, L, grad_dev, st);
   if (rc) return fail(ctx, rc, "rho backward launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   ctx->launches += 2;
   return AMPS_OK;
@@ -1003,15 +976,14 @@ int amps_rho_evolve(amps_ctx* ctx, const amps_params* p, const float* x_dev, int
   if (B == 0 || T == 1) return AMPS_OK;
   if (!x_dev || !traj_dev) return fail(ctx, AMPS_E_INVALID, "NULL buffer");
   if (p->D > RHO_MAX_D) return fail(ctx, AMPS_E_UNSUPPORTED, "rho kernels support D <= %d", RHO_MAX_D);
-  if (ws_bytes < rho_workspace_bytes(p->D, B, T))
-    return fail(ctx, AMPS_E_WORKSPACE, "workspace too small");
+  const RhoWs L = rho_ws_layout(p->D, B, T, false);
+  if (!ws_dev || ws_bytes < L.total) return fail(ctx, AMPS_E_WORKSPACE, "workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  rc = ensure_ttab(ctx, T + 1, (float)p->delta_t, st);
+  char* ws = (char*)ws_dev;
+  rc = rho_tables(ctx, p, T - 1, true, ws, L, st);
   if (rc) return rc;
-  const float2 *qtab, *ptab;
-  rc = rho_phase_tables(ctx, p, T - 1, true, st, &qtab, &ptab);
-  if (rc) return rc;
-  rc = rho_launch_data(p, ctx->ttab, qtab, ptab, x_dev, B, T, nullptr, (float2*)traj_dev, nullptr, nullptr, st);
+  rc = rho_launch_data(p, (const float*)(ws + L.ttab), (const float2*)(ws + L.qtab), (const float2*)(ws + L.ptab), x_dev, B,
+                       T, nullptr, (float2*)traj_dev, nullptr, nullptr, st);
   if (rc) return fail(ctx, rc, "rho kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   ctx->launches++;
   return AMPS_OK;
@@ -1027,16 +999,15 @@ int amps_rho_sample(amps_ctx* ctx, const amps_params* p, const float* noise_dev,
   if (L == 0 || n == 0) return AMPS_OK;
   if (!noise_dev) return fail(ctx, AMPS_E_INVALID, "noise_dev is NULL");
   if (p->D > RHO_MAX_D) return fail(ctx, AMPS_E_UNSUPPORTED, "rho kernels support D <= %d", RHO_MAX_D);
-  if (ws_bytes < rho_workspace_bytes(p->D, n, L + 1))
-    return fail(ctx, AMPS_E_WORKSPACE, "workspace too small");
+  const RhoWs Lw = rho_ws_layout(p->D, n, L + 1, false);
+  if (!ws_dev || ws_bytes < Lw.total) return fail(ctx, AMPS_E_WORKSPACE, "workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  rc = ensure_ttab(ctx, L + 1, (float)p->delta_t, st);
+  char* ws = (char*)ws_dev;
+  rc = rho_tables(ctx, p, L, traj_dev != nullptr, ws, Lw, st);
   if (rc) return rc;
-  const float2 *qtab, *ptab;
-  rc = rho_phase_tables(ctx, p, L, traj_dev != nullptr, st, &qtab, &ptab);
-  if (rc) return rc;
-  rc = rho_launch_sample(p, ctx->ttab, qtab, ptab, noise_dev, L, n, out_dev, (float2*)traj_dev, purity_dev,
-                         ws_dev, st);
+  rc = rho_launch_sample(p, (const float*)(ws + Lw.ttab), (const float2*)(ws + Lw.qtab),
+                         traj_dev ? (const float2*)(ws + Lw.ptab) : nullptr, noise_dev, L, n, out_dev,
+                         (float2*)traj_dev, purity_dev, ws_dev, st);
   if (rc) return fail(ctx, rc, "rho kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   ctx->launches++;
   return AMPS_OK;

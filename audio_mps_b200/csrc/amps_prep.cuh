@@ -6,14 +6,88 @@
 namespace amps {
 
 // t_0 = 0, t_{k+1} = fl32(t_k + dt32): the float32 running sum of model.py:16,157,281.
-// Strictly sequential by definition; run once per (n, dt32) and cached by the context.
-__global__ void prep_ttab_kernel(float dt32, int n, float* __restrict__ ttab) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    float t = 0.f;
-    for (int k = 0; k < n; ++k) {
-      ttab[k] = t;
-      t = __fadd_rn(t, dt32);
+// Sequential by definition, but piecewise LINEAR in exact arithmetic: while t stays inside one
+// binade (ulp u) and dt32/u is not a rounding tie, fl32(t + dt32) = t + rn(dt32/u)*u exactly.  One
+// thread walks the <= ~40 binades (the steps that cross a binade boundary, the first steps and the
+// one binade where dt32/u IS a tie are done with real float adds), then every thread fills the
+// linear stretches in double (exact) -- so the table is rebuilt into the CALLER's workspace on every
+// forward call in a few microseconds and no entry point depends on context-cached state.
+struct TtSeg {
+  int k0, m;     // out[k0 + j] = t0 + j*inc for j = 1..m
+  float t0, inc;
+};
+constexpr int TT_MAXSEG = 96;
+
+__host__ __device__ inline unsigned tt_bits(float v) {
+#ifdef __CUDA_ARCH__
+  return __float_as_uint(v);
+#else
+  unsigned b;
+  memcpy(&b, &v, 4);
+  return b;
+#endif
+}
+__host__ __device__ inline float tt_fadd(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fadd_rn(a, b);
+#else
+  volatile float r = a + b;   // IEEE single add, no contraction / excess precision
+  return r;
+#endif
+}
+
+// Writes the non-linear entries of out[0..n) directly and returns the linear stretches in segs.
+__host__ __device__ inline int tt_build(float d, int n, float* out, TtSeg* segs, int maxseg) {
+  int nseg = 0;
+  if (n <= 0) return 0;
+  float t = 0.f;
+  out[0] = t;
+  int k = 0;
+  const unsigned db = tt_bits(d);
+  const int dexp = (int)((db >> 23) & 0xff);
+  const bool regular = d > 0.f && dexp > 0 && dexp < 255;       // positive normal step
+  unsigned M = (db & 0x7fffffu) | 0x800000u;
+  int tz = 0;
+  while (tz < 24 && !((M >> tz) & 1u)) ++tz;
+  while (k < n - 1) {
+    const unsigned tb = tt_bits(t);
+    const int texp = (int)((tb >> 23) & 0xff);
+    const int j = texp - dexp;                                   // log2(ulp(t) / ulp(d))
+    if (regular && t > 0.f && texp < 254 && j >= 1 && j != tz + 1 && nseg < maxseg) {
+      // q = rn(d / u) as an integer (no tie here), a = (2^(E+1) - t) / u
+      const unsigned long long q = j > 24 ? 0ull : (((unsigned long long)M + (1ull << (j - 1))) >> j);
+      if (q == 0) {                                              // t no longer moves
+        segs[nseg++] = TtSeg{k, n - 1 - k, t, 0.f};
+        k = n - 1;
+        break;
+      }
+      const unsigned long long a = (1ull << 24) - ((tb & 0x7fffffu) | 0x800000u);
+      long long m = (long long)((a - 1) / q);                    // steps that stay below the binade top
+      if (m > n - 1 - k) m = n - 1 - k;
+      if (m > 0) {
+        const double u = ldexp(1.0, texp - 127 - 23);
+        const float inc = (float)((double)q * u);
+        segs[nseg++] = TtSeg{k, (int)m, t, inc};
+        t = (float)((double)t + (double)m * (double)inc);
+        k += (int)m;
+        if (k >= n - 1) break;
+      }
     }
+    t = tt_fadd(t, d);                                           // boundary / tie / start-up step
+    out[++k] = t;
+  }
+  return nseg;
+}
+
+__global__ void prep_ttab_kernel(float dt32, int n, float* __restrict__ ttab) {
+  __shared__ TtSeg segs[TT_MAXSEG];
+  __shared__ int nseg;
+  if (threadIdx.x == 0) nseg = tt_build(dt32, n, ttab, segs, TT_MAXSEG);
+  __syncthreads();
+  for (int s = 0; s < nseg; ++s) {
+    const TtSeg g = segs[s];
+    for (int j = 1 + (int)threadIdx.x; j <= g.m; j += (int)blockDim.x)
+      ttab[g.k0 + j] = (float)((double)g.t0 + (double)j * (double)g.inc);
   }
 }
 

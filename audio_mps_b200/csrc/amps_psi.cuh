@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(2 * DP * NQ)
         float n2 = 0.f;
         for (int r = lane; r < DP; r += 32) n2 += cabs2(sm.xs[p][len][r]);
         n2 = warp_sum_f(n2);
-        const float sc = rsqrtf(n2);
+        const float sc = rsqrtf(fmaxf(n2, 1e-12f));   // clamp of model.py:331-333
         bar_named(1, NTC);   // every chain warp has read the un-scaled state
         if (tr < DP) {
           float2 v = sm.xs[p][len][tr];
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(2 * DP * NQ)
             nu2 += __shfl_xor_sync(0xffffffffu, nu2, m);
           }
           if (g == 0 && kk < len) {
-            const float E = en / nu2;                                  // model.py:324-325 on x'
+            const float E = en / fmaxf(nu2, 1e-12f);                                  // model.py:324-325 on x'
             const float z = (E * sm.incv[p][kk]) / A;                  // model.py:294
             lossacc -= (double)log1pf(z);
             if (evout) evout[(size_t)b * T + k0 + kk] = make_float2(E, nu2);   // for the adjoint sweep
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(2 * DP * NQ)
         const float E = ev.x, nu2 = ev.y;
         const float arg = 1.0f + (E * inc) / A;
         const float gE = wb * (-s / arg);
-        const float alpha = 2.0f * gE / nu2;
+        const float alpha = 2.0f * gE / fmaxf(nu2, 1e-12f);
         sm.alphas[lp3][tr] = alpha;
         sm.betas[tr] = -alpha * E;
         gAacc += (double)wb * (double)E * (double)inc / ((double)A * (double)A * (double)arg);
@@ -788,7 +788,7 @@ __global__ void __launch_bounds__(DP* NQ)
         nu2 += __shfl_xor_sync(0xffffffffu, nu2, m);
       }
       if (g == 0 && kk < len) {
-        const float E = en / nu2;                                  // model.py:324-325 on x'
+        const float E = en / fmaxf(nu2, 1e-12f);                                  // model.py:324-325 on x'
         const float z = (E * sm.incv[buf][kk]) / A;                // model.py:294
         lossacc -= (double)log1pf(z);
         sm.evs[kk] = make_float2(E, nu2);
@@ -799,7 +799,7 @@ __global__ void __launch_bounds__(DP* NQ)
     float n2 = 0.f;
     for (int r = lane; r < DP; r += 32) n2 += sm.ns[buf][len][r];
     n2 = warp_sum_f(n2);
-    const float sc = rsqrtf(n2);
+    const float sc = rsqrtf(fmaxf(n2, 1e-12f));   // clamp of model.py:331-333
     if (t < DP) {
       float2 v = sm.xs[len][t];
       v.x *= sc;
@@ -943,7 +943,7 @@ __global__ void __launch_bounds__(DP* NQ)
       const float E = ev.x, nu2 = ev.y;
       const float arg = 1.0f + (E * inc) / A;
       const float gE = wb * (-s / arg);
-      const float alpha = 2.0f * gE / nu2;
+      const float alpha = 2.0f * gE / fmaxf(nu2, 1e-12f);
       sm.alphas[ds][t] = alpha;
       sm.betas[ds][t] = -alpha * E;
       gAacc += (double)wb * (double)E * (double)inc / ((double)A * (double)A * (double)arg);
@@ -1197,11 +1197,11 @@ __global__ void __launch_bounds__(DP* NQ)
         es += w2.x;
         nsum += w2.y;
       }
-      const float E = 2.0f * es / nsum;                                  // model.py:319-325
+      const float E = 2.0f * es / fmaxf(nsum, 1e-12f);                                  // model.py:319-325
       const float inc = __fadd_rn(__fmul_rn(E, dtf), lds32a(nz_b + (unsigned)(kk * sizeof(float))));   // model.py:286
       X = __fadd_rn(X, inc);                                             // model.py:287
       const float s = inc / A;                                           // model.py:303
-      const float rn = rsqrtf(nsum);   // lagged normalisation keeps |x| ~ 1
+      const float rn = rsqrtf(fmaxf(nsum, 1e-12f));   // lagged normalisation keeps |x| ~ 1
       float2 xp = make_float2(fmaf(s, y.x, a.x) * rn, fmaf(s, y.y, a.y) * rn);
       const float2 xn = cmul(lds64a(qs_b + (unsigned)((kk * DP + i) * sizeof(float2))), xp);
       sts64a_if(jq == 0, xs_a + XN + (unsigned)(i * sizeof(float2)), xn);

@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(512)
         float en = 0.f;
 #pragma unroll
         for (int r = 0; r < CL; ++r) en += sm.enx[r][kk];
-        const float E = en / nu2;                                  // model.py:324-325 on x'
+        const float E = en / fmaxf(nu2, 1e-12f);                                  // model.py:324-325 on x'
         const float z = (E * sm.incv[buf][kk]) / A;                // model.py:294
         lossacc -= (double)log1pf(z);
         sm.evs[kk] = make_float2(E, nu2);
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(512)
     float n2 = 0.f;
     for (int r = lane; r < DP; r += 32) n2 += cabs2(sm.xs[len][r]);
     n2 = warp_sum_f(n2);
-    const float sc = rsqrtf(n2);
+    const float sc = rsqrtf(fmaxf(n2, 1e-12f));   // clamp of model.py:331-333
     __syncthreads();  // every read of xs[0..len] above is done
     if (t < DP) {
       float2 v = sm.xs[len][t];
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(512)
       const float E = ev.x, nu2 = ev.y;
       const float arg = 1.0f + (E * inc) / A;
       const float gE = wb * (-s / arg);
-      const float alpha = 2.0f * gE / nu2;
+      const float alpha = 2.0f * gE / fmaxf(nu2, 1e-12f);
       sm.alphas[ds][t] = alpha;
       sm.betas[ds][t] = -alpha * E;
       gAacc += (double)wb * (double)E * (double)inc / ((double)A * (double)A * (double)arg);

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(DP* NQ + 32)
           float n2 = 0.f;
           for (int r = lane; r < DP; r += 32) n2 += cabs2(sm.xs[p][len][r]);
           n2 = warp_sum_f(n2);
-          const float sc = rsqrtf(n2);
+          const float sc = rsqrtf(fmaxf(n2, 1e-12f));   // clamp of model.py:331-333
           if (t == 0) {
             sm.scv[p][0] = sc;
             if (scales) scales[(size_t)b * nchunks + c] = sc;
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(DP* NQ + 32)
             nu2 += __shfl_xor_sync(0xffffffffu, nu2, m);
           }
           if (g == 0 && kk < len) {
-            const float E = en / nu2;                                  // model.py:324-325 on x'
+            const float E = en / fmaxf(nu2, 1e-12f);                                  // model.py:324-325 on x'
             const float z = (E * sm.incv[0][kk]) / A;                  // model.py:294
             lossacc -= (double)log1pf(z);
             if (evout) evout[(size_t)b * T + k0 + kk] = make_float2(E, nu2);   // for the adjoint sweep
@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(3 * DP * NQ)
         const float E = ev.x, nu2 = ev.y;
         const float arg = 1.0f + (E * inc) / A;
         const float gE = wb * (-s / arg);
-        const float alpha = 2.0f * gE / nu2;
+        const float alpha = 2.0f * gE / fmaxf(nu2, 1e-12f);
         sm.alphas[lp3][tr] = alpha;
         sm.betas[tr] = -alpha * E;
         gAacc += (double)wb * (double)E * (double)inc / ((double)A * (double)A * (double)arg);

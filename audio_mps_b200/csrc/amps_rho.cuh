@@ -14,7 +14,7 @@ namespace amps {
 constexpr int RHO_MAX_D = 32;
 
 struct RhoWs {
-  size_t ftraj, G, acc, lam0, gAdir, lossd, scratch, total;
+  size_t ttab, qtab, ptab, ftraj, G, acc, lam0, gAdir, lossd, scratch, total;
 };
 inline RhoWs rho_ws_layout(int D, int B, int T, bool save) {
   RhoWs w{};
@@ -26,6 +26,10 @@ inline RhoWs rho_ws_layout(int D, int B, int T, bool save) {
   };
   const size_t DD = (size_t)D * D;
   w.lossd = take((size_t)(B > 0 ? B : 1) * sizeof(double));
+  // tables of one call (float32 t_k, q_k, p_{k+1}): in the caller's workspace, rebuilt by every forward
+  w.ttab = take((size_t)(T + 2) * sizeof(float));
+  w.qtab = take((size_t)(T > 0 ? T : 1) * D * sizeof(float2));
+  w.ptab = take((size_t)(T > 0 ? T : 1) * D * sizeof(float2));
   if (save) {
     w.ftraj = take((size_t)B * T * DD * sizeof(float2));
     w.G = take((size_t)B * 3 * DD * sizeof(float2));

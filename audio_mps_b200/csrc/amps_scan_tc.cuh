@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(256)
     n2 = warp_sum_f(n2);
     if ((t & 31) == 0) red[t >> 5] = n2;
     __syncthreads();
-    const float rn = rsqrtf(red[0] + red[1] + red[2] + red[3]);
+    const float rn = rsqrtf(fmaxf(red[0] + red[1] + red[2] + red[3], 1e-12f));
     if (t < TC_N) y[t] *= rn;
     cp_async_wait<1>();
     __syncthreads();

@@ -22,6 +22,27 @@ def damped_sine(batch: int, length: int, delta_t: float, rng: Optional[np.random
     return wave.astype(np.float32)
 
 
+def random_raw_params(bond_dim: int, A: float, rng: np.random.Generator) -> dict:
+    """Raw Psi trainables drawn with the reference's initialisers (model.py:36-39, 49-50, 218-219:
+    standard normal Rx, Ry, freqs; glorot-uniform psi_x, psi_y on a [D] vector), in the draw order the
+    synthetic benchmark / golden inputs are defined with (default_rng(seed))."""
+    D = int(bond_dim)
+    lim = float(np.sqrt(3.0 / D))
+    return {"Rx": rng.standard_normal((D, D)).astype(np.float32),
+            "Ry": rng.standard_normal((D, D)).astype(np.float32),
+            "freqs": rng.standard_normal(D).astype(np.float32),
+            "A": np.float32(A),
+            "psi_x": rng.uniform(-lim, lim, D).astype(np.float32),
+            "psi_y": rng.uniform(-lim, lim, D).astype(np.float32)}
+
+
+def sample_noise(sigma: float, delta_t: float, length: int, num_samples: int, seed: int, temp: float = 1.0) -> np.ndarray:
+    """The sampler's noise tensor [length, num_samples] ~ N(0, sigma^2 * temp * delta_t), drawn once
+    (model.py:246), from a recorded seed."""
+    z = np.random.default_rng(seed).standard_normal((length, num_samples)).astype(np.float32)
+    return z * np.float32(sigma * np.sqrt(temp * delta_t))
+
+
 # ---- TFRecord / tf.train.Example parsing without TensorFlow --------------------------------
 def _read_varint(buf: bytes, pos: int):
     out, shift = 0, 0

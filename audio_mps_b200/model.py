@@ -46,6 +46,16 @@ def _as_device_f32(obj, device) -> torch.Tensor:
     return t.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
 
 
+def _allreduce_packed(model, packed, h, dev):
+    """Data parallel: ONE all-reduce (sum) of the packed effective-parameter gradient, either on the
+    C ABI's own NCCL communicator (amps_comm_init) or on a torch.distributed group.  Used by the Psi
+    AND the Rho backward, so that replicas cannot diverge between the two models."""
+    if getattr(model, "_dp_native", False):
+        _lib.check(h, _lib.load().amps_allreduce_grads(h, _ptr(packed), packed.numel(), _stream(dev)))
+    elif getattr(model, "_dp_group", None) is not None:
+        torch.distributed.all_reduce(packed, op=torch.distributed.ReduceOp.SUM, group=model._dp_group)
+
+
 # --------------------------------------------------------------------------------------------
 # autograd bridge: per-clip loss through amps_psi_loss_fwd / amps_psi_loss_bwd
 # --------------------------------------------------------------------------------------------
@@ -64,7 +74,9 @@ class _PsiLossFn(torch.autograd.Function):
         freqs = freqs.detach().contiguous().float()
         psi0_ri = psi0_ri.detach().contiguous().float()
         # A goes down by device pointer: no host read-back (= stream sync) per training step
-        a_dev = A.detach().reshape(1).contiguous().float()
+        # (a private copy: an in-place parameter update between forward and backward must not change
+        # the A the backward sees)
+        a_dev = A.detach().reshape(1).float().clone()
         p = _lib.AmpsParams(D=D, reserved=0, R_dev=R_ri.data_ptr(), freqs_dev=freqs.data_ptr(),
                             psi0_dev=psi0_ri.data_ptr(), rho0_dev=None, A=0.0,
                             sigma=float(model.sigma), delta_t=float(model.delta_t),
@@ -98,13 +110,7 @@ class _PsiLossFn(torch.autograd.Function):
         bwd = lib.amps_psi_loss_bwd_scan if scan else lib.amps_psi_loss_bwd
         rc = bwd(h, C.byref(p), _ptr(x), B, T, _ptr(w), _ptr(ws), ws.numel(), _ptr(packed), _stream(dev))
         _lib.check(h, rc)
-        dp = getattr(model, "_dp_group", None)
-        if getattr(model, "_dp_native", False):
-            # data parallel through the C ABI's own NCCL communicator (amps_comm_init)
-            _lib.check(h, lib.amps_allreduce_grads(h, _ptr(packed), ng, _stream(dev)))
-        elif dp is not None:
-            # data parallel: ONE all-reduce of the packed effective-parameter gradient
-            torch.distributed.all_reduce(packed, op=torch.distributed.ReduceOp.SUM, group=dp)
+        _allreduce_packed(model, packed, h, dev)
         model._last_packed = packed
         # clones: view_as_real's backward needs an even storage offset (odd D breaks a view)
         gR = packed[: 2 * D * D].view(D, D, 2).clone()
@@ -196,9 +202,7 @@ class _RhoLossFn(torch.autograd.Function):
         rc = lib.amps_rho_loss_bwd(h, C.byref(p), _ptr(x), B, T, _ptr(w), _ptr(ws), ws.numel(),
                                    _ptr(packed), _stream(dev))
         _lib.check(h, rc)
-        dp = getattr(model, "_dp_group", None)
-        if dp is not None:
-            torch.distributed.all_reduce(packed, op=torch.distributed.ReduceOp.SUM, group=dp)
+        _allreduce_packed(model, packed, h, dev)
         model._last_packed = packed
         n = 2 * D * D
         gR = packed[:n].view(D, D, 2).clone()
@@ -228,6 +232,7 @@ class CMPS(torch.nn.Module):
         self.sigma = hparams.sigma                           # :21
         self.data_iterator = data_iterator                   # :25
         self._dp_group = None
+        self._dp_native = False
         self._last_packed = None
         gen = torch.Generator(device="cpu").manual_seed(seed)
         self._gen = gen
@@ -333,10 +338,12 @@ class CMPS(torch.nn.Module):
         ``native=True``: the reduction runs on the library's own NCCL communicator
         (amps_comm_init / amps_allreduce_grads); ``group`` is then used once, to hand rank 0's
         ncclUniqueId to the other ranks."""
+        import torch.distributed as dist
+        if group is None and dist.is_available() and dist.is_initialized():
+            group = dist.group.WORLD          # "default group" is represented explicitly, never as None
         self._dp_group = group
         self._dp_native = False
         if native:
-            import torch.distributed as dist
             lib, h = _lib.load(), self._ctx()
             rank, world = dist.get_rank(group), dist.get_world_size(group)
             buf = (C.c_ubyte * 128)()
@@ -443,7 +450,12 @@ class PsiCMPS(CMPS):
                             psi0_dev=p0.data_ptr(), rho0_dev=None, A=float(self.A),
                             sigma=float(self.sigma), delta_t=float(self.delta_t))
         out = torch.empty(n, L, dtype=torch.float32, device=self.device)
-        rc = lib.amps_psi_sample(h, C.byref(p), _ptr(noise), L, n, _ptr(out), _stream(self.device))
+        nbytes = lib.amps_psi_sample_workspace_bytes(self.bond_d, L, n)
+        if nbytes == 0:
+            raise _lib.AmpsError(-2, f"bond dimension {self.bond_d} is not supported by the Psi sampler")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        rc = lib.amps_psi_sample(h, C.byref(p), _ptr(noise), L, n, _ptr(out), _ptr(ws), nbytes,
+                                 _stream(self.device))
         _lib.check(h, rc)
         return out
 

@@ -48,6 +48,7 @@ class Trainer:
         if self.world > 1:
             model.set_data_parallel(group if group is not None else dist.group.WORLD, native=native_comm)
         self.global_step = 0
+        self.last_reg = None           # regulariser value of the parameters the last step was taken FROM
 
     def step(self, x_local, global_batch: Optional[int] = None, regularise: bool = True):
         m = self.model
@@ -59,6 +60,7 @@ class Trainer:
         data_term = lpc.sum() / gb
         self.opt.zero_grad(set_to_none=True)
         obj = data_term + reg if regularise else data_term
+        self.last_reg = reg.detach() if reg is not None else None
         obj.backward()
         self.opt.step()
         self.global_step += 1

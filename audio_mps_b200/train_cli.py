@@ -72,6 +72,20 @@ def main(argv=None):
     lo, hi = shard_bounds(gb, rank, world)
     last_save = time.time()
     log = open(os.path.join(logdir, "scalars.jsonl"), "a") if rank == 0 else None
+    tb = None
+    if rank == 0:
+        try:                                                        # the scalars of train.py:62-72 as event files
+            from torch.utils.tensorboard import SummaryWriter
+            tb = SummaryWriter(logdir)
+        except Exception:
+            tb = None
+
+    def save():
+        tmp = ckpt + ".tmp"                                         # atomic: never leave a torn model.pt behind
+        torch.save(trainer.state_dict(), tmp)
+        os.replace(tmp, ckpt)
+        if args.save_tf_checkpoint:
+            model.save_tf_checkpoint(os.path.join(logdir, f"model.ckpt-{trainer.global_step}"), trainer.global_step)
     for _ in range(args.steps):
         batch = source if isinstance(source, np.ndarray) else next(source)
         if isinstance(source, np.ndarray):                          # a fresh random-onset batch per step
@@ -82,20 +96,26 @@ def main(argv=None):
                 R, f = model.R, model.freqs
                 h_l2 = float(torch.sum(f * f))
                 r_l2 = float(torch.sum(torch.conj(R) * R).real)
+                # total_loss pairs the step's model loss with the regulariser of the SAME (pre-update) parameters
+                reg = float(trainer.last_reg) if trainer.last_reg is not None else hp.h_reg * h_l2 + hp.r_reg * r_l2
                 rec = {"step": trainer.global_step, "model_loss": model_loss,
-                       "total_loss": model_loss + hp.h_reg * h_l2 + hp.r_reg * r_l2,
+                       "total_loss": model_loss + reg,
                        "A": float(model.A), "sigma": float(model.sigma),
                        "h_l2norm": math.sqrt(h_l2), "r_l2norm": math.sqrt(r_l2),
                        "gr_decay_time": 1.0 / (2 * math.pi * hp.sigma ** 2 * r_l2 / hp.bond_dim)}   # train.py:66-67
             log.write(json.dumps(rec) + "\n")
             log.flush()
+            if tb is not None:
+                for k, v in rec.items():
+                    if k != "step":
+                        tb.add_scalar(k, v, trainer.global_step)
             if time.time() - last_save >= args.save_checkpoint_secs:
-                torch.save(trainer.state_dict(), ckpt)
+                save()
                 last_save = time.time()
     if rank == 0:
-        torch.save(trainer.state_dict(), ckpt)
-        if args.save_tf_checkpoint:
-            model.save_tf_checkpoint(os.path.join(logdir, f"model.ckpt-{trainer.global_step}"), trainer.global_step)
+        save()
+        if tb is not None:
+            tb.close()
         if args.num_samples:
             w = model.sample(args.num_samples, args.sample_duration)                                 # train.py:83
             np.save(os.path.join(logdir, "samples.npy"), w.cpu().numpy())

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define AMPS_VERSION 100 /* 0.1.0 */
+#define AMPS_VERSION 200 /* 0.2.0 */
 
 enum {
   AMPS_OK = 0,
@@ -70,6 +70,11 @@ int amps_destroy(amps_ctx* ctx);
 const char* amps_last_error(const amps_ctx* ctx);
 /* number of kernels the context has launched so far (bench.py's gpu_launches evidence) */
 int64_t amps_launch_count(const amps_ctx* ctx);
+
+/* The float32 running-sum time table t_0 = 0, t_{k+1} = fl32(t_k + fl32(delta_t)) of model.py:16,157,281,
+ * out[0..n), computed on the host by the same piecewise-exact generator the device entry points use
+ * (bit-identical to the sequential sum; tests/test_host_logic.py). */
+int amps_time_table_host(double delta_t, int n, float* out);
 
 /* ---- measurement helpers (bench.py) ------------------------------------------------------ */
 /* When enabled, the context brackets the dominant kernel of each entry point with CUDA events on
@@ -135,9 +140,12 @@ int amps_psi_loss_bwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
 /* PsiCMPS.sample / _psi_and_sample_update (model.py:242-251, 284-291) with the noise tensor
  * supplied by the caller (the reference draws it once, model.py:246).
  *   noise_dev float32 [L,n] (time-major, as tf.random_normal([length, num_samples]))
- *   out_dev   float32 [n,L] = A * cumulative X_t (model.py:251) */
+ *   out_dev   float32 [n,L] = A * cumulative X_t (model.py:251)
+ *   ws_dev    caller-owned workspace of amps_psi_sample_workspace_bytes(D, L, n) bytes (step
+ *             operators, t_k and q_k tables of this call) */
+size_t amps_psi_sample_workspace_bytes(int D, int L, int n);
 int amps_psi_sample(amps_ctx* ctx, const amps_params* p, const float* noise_dev, int L, int n,
-                    float* out_dev, void* stream);
+                    float* out_dev, void* ws_dev, size_t ws_bytes, void* stream);
 
 /* PsiCMPS.psi_evolve_with_data / _psi_update (model.py:231-240, 269-274):
  *   traj_dev complex64 [B, T-1, D] normalised lab-frame psi after every step.

@@ -8,7 +8,7 @@ import torch
 
 from audio_mps_b200 import HParams, PsiCMPS, _lib
 from oracle.cmps_oracle import PsiCMPSOracle, damped_sine, random_raw_params
-from tests.util import hp_pair, rel, relc, set_raw
+from tests.util import hp_pair, rel, rel_clip, relc, set_raw
 
 pytestmark = pytest.mark.gpu
 
@@ -32,7 +32,7 @@ def test_host_entry_point_matches_oracle(cuda, lib):
     h = _lib.context(0)
     _lib.check(h, lib.amps_psi_loss_grad_host(h, C.byref(hp), x.ctypes.data, B, T, 1.0 / B,
                                               loss.ctypes.data, grad.ctypes.data))
-    assert rel(loss, lpc.detach().numpy()) <= 1e-4
+    assert rel_clip(loss, lpc.detach().numpy()) <= 1e-4
     n = 2 * D * D
     assert relc(grad[:n].reshape(D, D, 2) @ np.array([1, 1j]), gR.numpy()) <= 1e-3
     assert rel(grad[n:n + D], gf.numpy()) <= 1e-3
@@ -89,7 +89,7 @@ def test_edge_shapes(cuda, lib):
     for T in (33, 34, 35, 65, 66):
         data = damped_sine(2, T, ohp.delta_t, np.random.default_rng(T))
         ref = PsiCMPSOracle(ohp, raw, mode="f64").loss_per_clip(data).detach().numpy()
-        assert rel(m.loss_per_clip(data).detach().cpu().numpy(), ref) <= 1e-4, T
+        assert rel_clip(m.loss_per_clip(data).detach().cpu().numpy(), ref) <= 1e-4, T
     # zero signal: inc = 0 -> every term is -log(1) = 0
     assert float(m.loss_per_clip(np.ones((2, 100), np.float32)).abs().max()) == 0.0
     assert m.sample(0, 16).shape == (0, 16)

@@ -1,0 +1,128 @@
+"""-m gpu: round-2 ABI / parity cases -- self-contained workspaces (no context-cached tables), the
+zero-state clamp of model.py:331-333, the fused parameter chain + regulariser the Trainer uses, and
+"no device allocation after amps_create" on the device entry points."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from audio_mps_b200 import HParams, PsiCMPS, RhoCMPS, _lib
+from audio_mps_b200.train import Trainer
+from oracle.cmps_oracle import PsiCMPSOracle, RhoCMPSOracle, damped_sine, grads_of, random_raw_params, total_loss
+from tests.util import hp_pair, rel, rel_clip, relc, set_raw
+
+pytestmark = pytest.mark.gpu
+
+
+def test_two_models_with_different_delta_t_interleaved(cuda, lib):
+    """fwd(A, dt1) -> fwd(B, dt2) -> bwd(A) -> bwd(B): each backward must see ITS OWN float32 time
+    table (it lives in the caller's workspace, not in the context)."""
+    D, B, T = 8, 3, 700
+    models, refs, losses = [], [], []
+    for dt, seed in ((1 / 16000, 0), (1 / 11025, 5)):
+        ohp, php = hp_pair(bond_dim=D, minibatch_size=B, delta_t=dt)
+        raw = random_raw_params(ohp, np.random.default_rng(seed))
+        data = damped_sine(B, T, ohp.delta_t, np.random.default_rng(seed + 1))
+        m = PsiCMPS(php, device=cuda)
+        set_raw(m, raw)
+        o = PsiCMPSOracle(ohp, raw, mode="f64")
+        refs.append(grads_of(o, o.loss_per_clip(data).mean()))
+        models.append(m)
+        losses.append(m.loss_per_clip(data))          # both forwards first
+    for m, l, gref in zip(models, losses, refs):      # then both backwards
+        l.mean().backward()
+        for n in ("Rx", "Ry", "freqs_raw", "psi_x", "psi_y", "A"):
+            r = gref["freqs" if n == "freqs_raw" else n]
+            assert rel(getattr(m, n).grad.cpu().numpy(), r) <= 1e-3, n
+
+
+def test_rho_two_models_interleaved(cuda, lib):
+    D, B, T = 4, 2, 200
+    models, refs, losses = [], [], []
+    for dt, seed in ((1 / 16000, 0), (1 / 8000, 3)):
+        ohp, php = hp_pair(bond_dim=D, minibatch_size=B, delta_t=dt)
+        raw = random_raw_params(ohp, np.random.default_rng(seed), rho=True)
+        data = damped_sine(B, T, ohp.delta_t, np.random.default_rng(seed + 1))
+        m = RhoCMPS(php, device=cuda)
+        set_raw(m, raw)
+        o = RhoCMPSOracle(ohp, raw, mode="f64")
+        refs.append(grads_of(o, o.loss_per_clip(data).mean()))
+        models.append(m)
+        losses.append(m.loss_per_clip(data))
+    for m, l, gref in zip(models, losses, refs):
+        l.mean().backward()
+        for n in ("Rx", "Ry", "freqs_raw", "Wx", "Wy", "A"):
+            r = gref["freqs" if n == "freqs_raw" else n]
+            assert rel(getattr(m, n).grad.cpu().numpy(), r) <= 1e-3, n
+
+
+@pytest.mark.parametrize("D", [8, 32, 64, 128])
+def test_zero_state_is_finite_like_the_reference(cuda, lib, D):
+    """psi_0 = 0: the reference's clamp max(sum|.|^2, 1e-12) (model.py:331-333) keeps everything finite
+    (loss 0, gradient 0); so must every kernel family."""
+    ohp, php = hp_pair(bond_dim=D, minibatch_size=2)
+    raw = random_raw_params(ohp, np.random.default_rng(0))
+    raw["psi_x"] = np.zeros(D, np.float32)
+    raw["psi_y"] = np.zeros(D, np.float32)
+    data = damped_sine(2, 150, ohp.delta_t, np.random.default_rng(1))
+    o = PsiCMPSOracle(ohp, raw, mode="f64")
+    ref = o.loss_per_clip(data)
+    assert float(ref.detach().abs().max()) == 0.0
+    m = PsiCMPS(php, device=cuda)
+    set_raw(m, raw)
+    l = m.loss_per_clip(data)
+    assert torch.isfinite(l).all() and float(l.detach().abs().max()) == 0.0
+    l.mean().backward()
+    for n in ("Rx", "Ry", "freqs_raw", "psi_x", "psi_y", "A"):
+        g = getattr(m, n).grad
+        assert torch.isfinite(g).all(), n
+        assert float(g.abs().max()) == 0.0, n
+    if D <= 64:
+        assert torch.isfinite(m.sample(2, 64)).all()
+
+
+@pytest.mark.parametrize("D", [8, 32])
+def test_fused_parameter_chain_and_regulariser_vs_oracle(cuda, lib, D):
+    """Trainer.step trains through loss_per_clip_and_regulariser (amps_psi_params_fwd/_bwd): value and
+    raw-variable gradients of mean(loss) + regulariser against the oracle's total_loss (train.py:55-60)."""
+    B, T = 4, 600
+    ohp, php = hp_pair(bond_dim=D, minibatch_size=B)
+    raw = random_raw_params(ohp, np.random.default_rng(7))
+    data = damped_sine(B, T, ohp.delta_t, np.random.default_rng(8))
+    o = PsiCMPSOracle(ohp, raw, mode="f64")
+    tot = total_loss(o, data)
+    gref = grads_of(o, tot)
+    m = PsiCMPS(php, device=cuda)
+    set_raw(m, raw)
+    lpc, reg = m.loss_per_clip_and_regulariser(data)
+    obj = lpc.mean() + reg
+    assert rel(float(obj.detach()), float(tot.detach())) <= 1e-5
+    oreg = float(tot.detach()) - float(o.loss_per_clip(data).mean().detach())
+    assert rel(float(reg.detach()), oreg) <= 1e-5
+    obj.backward()
+    for n in ("Rx", "Ry", "freqs_raw", "psi_x", "psi_y", "A"):
+        r = gref["freqs" if n == "freqs_raw" else n]
+        assert rel(getattr(m, n).grad.cpu().numpy(), r) <= 1e-3, n
+
+
+def test_device_entry_points_allocate_nothing(cuda, lib):
+    """the caller owns every buffer; after amps_create the device entry points allocate
+    nothing.  100 training steps + samples must leave the driver's free-memory figure unchanged once
+    the framework's caching allocator is warm (the library itself never calls cudaMalloc there)."""
+    _, php = hp_pair(bond_dim=16, minibatch_size=4)
+    m = PsiCMPS(php, device=cuda)
+    tr = Trainer(m)
+    x = torch.as_tensor(damped_sine(4, 800, php.delta_t, np.random.default_rng(0)), device=cuda)
+    noise = torch.randn(256, 3, device=cuda) * 1e-6
+    for _ in range(3):
+        tr.step(x)
+        m.sample_from_noise(noise)
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info(cuda)
+    for _ in range(100):
+        tr.step(x)
+    m.sample_from_noise(noise)
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info(cuda)
+    assert free1 == free0, (free0, free1)

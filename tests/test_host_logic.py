@@ -28,10 +28,26 @@ def test_abi_exports_every_declared_symbol(lib):
         assert hasattr(raw, name), f"{name} declared in audiomps.h but not exported"
         assert name in _lib.SYMBOLS, f"{name} has no ctypes binding"
     assert set(_lib.SYMBOLS) == declared
-    assert lib.amps_version() == 100
+    assert lib.amps_version() == 200
     assert lib.amps_psi_grad_count(32) == 2 * 32 * 32 + 3 * 32 + 2
     assert lib.amps_psi_workspace_bytes(32, 64, 64000, 1) > 64 * 64000 * 32 * 8
     assert lib.amps_psi_workspace_bytes(200, 1, 10, 0) == 0      # unsupported D reports 0
+
+
+@pytest.mark.parametrize("dt", [1 / 16000, 1 / 8000, 1 / 44100, 1e-3, 2.0 ** -14, 7.3e-5,
+                                float(np.float32(0x800008 * 2.0 ** -37)), float(np.float32(0xC00400 * 2.0 ** -37))])
+def test_time_table_is_the_float32_running_sum(lib, dt):
+    """t_{k+1} = fl32(t_k + fl32(delta_t)) (model.py:16,281): the library's piecewise-exact generator
+    (host twin of prep_ttab_kernel) against the sequential float32 sum, bit for bit."""
+    n = 70000
+    out = np.empty(n, np.float32)
+    assert lib.amps_time_table_host(ctypes.c_double(dt), n, out.ctypes.data_as(ctypes.c_void_p)) == 0
+    d, t = np.float32(dt), np.float32(0)
+    ref = np.empty(n, np.float32)
+    for k in range(n):
+        ref[k] = t
+        t = np.float32(t + d)
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
 
 
 def test_no_cpu_fallback():
@@ -265,3 +281,14 @@ def test_tf_checkpoint_reads_snappy_compressed_index(tmp_path):
     open(prefix + ".index", "wb").write(bytes(f))
     back = tfc.read_tf_checkpoint(prefix)
     assert float(back["model/A"]) == 3.5 and np.array_equal(back["model/freqs"], tensors["model/freqs"])
+
+
+def test_host_generators_match_the_oracle_generators():
+    """audio_mps_b200.data.random_raw_params / sample_noise (what bench.py feeds the CUDA path) draw the
+    same numbers as the oracle-side generators the goldens were minted with."""
+    from audio_mps_b200.data import random_raw_params as prp, sample_noise as psn
+    from oracle.mint_golden_r2 import sample_noise as osn
+    hp = HP(bond_dim=16)
+    a, b = prp(16, hp.A, np.random.default_rng(3)), random_raw_params(hp, np.random.default_rng(3))
+    assert set(a) == set(b) and all(np.array_equal(a[k], b[k]) for k in b)
+    assert np.array_equal(psn(hp.sigma, hp.delta_t, 100, 3, 5), osn(hp, 100, 3, 5))

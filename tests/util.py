@@ -23,13 +23,46 @@ def set_raw(model, raw):
             getattr(model, name).copy_(torch.as_tensor(np.asarray(v, np.float32)))
 
 
-def rel(a, b):
-    a = np.asarray(a, dtype=np.float64)
-    b = np.asarray(b, dtype=np.float64)
-    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
-
-
-def relc(a, b):
+def _rows(a, b, floor):
+    """worst row (first axis) of max|a_r - b_r| / max(max|b_r|, floor * max|b|)"""
     a = np.asarray(a)
     b = np.asarray(b)
-    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+    scale = max(float(np.abs(b).max()) if b.size else 0.0, 1e-300)
+    if a.ndim < 2:
+        return float(np.abs(a - b).max() / scale) if a.size else 0.0
+    ar = a.reshape(a.shape[0], -1)
+    br = b.reshape(b.shape[0], -1)
+    den = np.maximum(np.abs(br).max(axis=1), floor * scale)
+    return float((np.abs(ar - br).max(axis=1) / den).max())
+
+
+def rel(a, b, floor=1e-3):
+    """Relative error of a real array against its reference.  Arrays with >= 2 axes (gradient
+    matrices, sample paths [n, L], trajectories [B, ...]) are judged ROW BY ROW (first axis), so a
+    small row is not hidden behind a large one; vectors and scalars by their max-norm."""
+    return _rows(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64), floor)
+
+
+def relc(a, b, floor=1e-3):
+    return _rows(np.asarray(a), np.asarray(b), floor)
+
+
+def rel_clip(a, b, floor=1e-2):
+    """PER-CLIP relative error (north_star: "per-clip log-likelihood within 1e-4 relative"):
+    max_b |a_b - r_b| / max(|r_b|, floor * max|r|).  Returns (worst error, worst clip)."""
+    a = np.asarray(a, dtype=np.float64).reshape(-1)
+    b = np.asarray(b, dtype=np.float64).reshape(-1)
+    if a.size == 0:
+        return 0.0
+    den = np.maximum(np.abs(b), floor * max(float(np.abs(b).max()), 1e-300))
+    e = np.abs(a - b) / den
+    return float(e.max())
+
+
+def worst_clip(a, b, floor=1e-2):
+    a = np.asarray(a, dtype=np.float64).reshape(-1)
+    b = np.asarray(b, dtype=np.float64).reshape(-1)
+    den = np.maximum(np.abs(b), floor * max(float(np.abs(b).max()), 1e-300))
+    e = np.abs(a - b) / den
+    i = int(e.argmax())
+    return i, float(e[i]), float(a[i]), float(b[i])
