@@ -11,7 +11,8 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaudiomps.so")
+# AMPS_LIB: alternative build of the same library (A/B timing of kernel variants, profiles/build_variants.sh)
+LIB_PATH = os.environ.get("AMPS_LIB") or os.path.join(_HERE, "libaudiomps.so")
 CSRC = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "audiomps.h")
 
@@ -62,6 +63,12 @@ SYMBOLS = {
                                     C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "amps_psi_loss_bwd": (C.c_int, [C.c_void_p, C.POINTER(AmpsParams), C.c_void_p, C.c_int, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "amps_psi_ckpt_interval": (C.c_int, [C.c_int, C.c_int]),
+    "amps_psi_workspace_bytes_k": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "amps_psi_loss_fwd_k": (C.c_int, [C.c_void_p, C.POINTER(AmpsParams), C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "amps_psi_loss_bwd_k": (C.c_int, [C.c_void_p, C.POINTER(AmpsParams), C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "amps_psi_scan_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "amps_psi_loss_fwd_scan": (C.c_int, [C.c_void_p, C.POINTER(AmpsParams), C.c_void_p, C.c_int, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),

@@ -38,6 +38,11 @@ struct amps_ctx {
   // data-parallel communicator (NCCL, resolved at run time; see amps_comm_init)
   void* nccl_comm = nullptr;
   int comm_rank = 0, comm_size = 1;
+  // checkpointed backward (amps_psi_loss_bwd_k): the forward replay of time window j-1 runs on this
+  // second stream, next to the adjoint sweep of window j on the caller's stream
+  cudaStream_t aux_stream = nullptr;
+  bool ckpt_overlap = true;   // AMPS_CKPT_SERIAL=1: replay on the caller's stream (measurement aid)
+  cudaEvent_t ev_fork = nullptr, ev_replay[2] = {nullptr, nullptr}, ev_bwd[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -162,6 +167,10 @@ int chunk_len_of(int DP) { return DP == 128 ? CH4 : CH; }
 // A by value, or by device pointer when the caller supplies one (no host read-back per step)
 AVal aval(const amps_params* p) { return AVal{p->A, p->A_dev}; }
 
+// whole-clip launch of a scan kernel (no time window, no checkpoints)
+SegFwd seg_full_f(int T) { return SegFwd{T, nullptr, 0, nullptr, 1, 0}; }
+SegBwd seg_full_b(int T) { return SegBwd{T, nullptr, 0, 0}; }
+
 template <int V>
 using IC = std::integral_constant<int, V>;
 
@@ -247,12 +256,10 @@ int psi_prepare(amps_ctx* ctx, const amps_params* p, int DP, char* ws, const Psi
                                         (float2*)(ws + L.psi0p));
   LAUNCH_CHECK(ctx, "prep_pad_vec_kernel");
   if (nsteps_tab > 0) {
-    const size_t total = (size_t)nsteps_tab * DP;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    prep_qtab_kernel<<<blocks, 256, 0, st>>>(p->freqs_dev, p->D, DP, (const float*)(ws + L.ttab), nsteps_tab,
-                                             (float2*)(ws + L.qtab));
-    LAUNCH_CHECK(ctx, "prep_qtab_kernel");
+    const dim3 grid((nsteps_tab + QG - 1) / QG, (DP + QC - 1) / QC);
+    prep_phase_tables_kernel<<<grid, 256, sizeof(PhaseSmem), st>>>(p->freqs_dev, p->D, DP, (const float*)(ws + L.ttab),
+                                                                 nsteps_tab, (float2*)(ws + L.qtab), (float2*)nullptr);
+    LAUNCH_CHECK(ctx, "prep_phase_tables_kernel");
   }
   return AMPS_OK;
 }
@@ -260,8 +267,6 @@ int psi_prepare(amps_ctx* ctx, const amps_params* p, int DP, char* ws, const Psi
 // launch `kern` as `nclusters` thread-block clusters of CL CTAs
 template <class K, class... Args>
 cudaError_t launch_cluster(K kern, int nclusters, int CL, int threads, size_t smem, cudaStream_t st, Args... args) {
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(nclusters * CL);
   cfg.blockDim = dim3(threads);
@@ -285,17 +290,18 @@ int rho_tables(amps_ctx* ctx, const amps_params* p, int nsteps, bool need_p, cha
   prep_ttab_kernel<<<1, 1024, 0, st>>>((float)p->delta_t, nsteps + 1, (float*)(ws + L.ttab));
   LAUNCH_CHECK(ctx, "prep_ttab_kernel");
   if (nsteps > 0) {
-    const size_t n = (size_t)nsteps * p->D;
-    int blocks = (int)((n + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    rho_prep_phase_kernel<<<blocks, 256, 0, st>>>(p->freqs_dev, (const float*)(ws + L.ttab), nsteps, p->D,
-                                                  (float2*)(ws + L.qtab), need_p ? (float2*)(ws + L.ptab) : nullptr);
-    LAUNCH_CHECK(ctx, "rho_prep_phase_kernel");
+    const dim3 grid((nsteps + QG - 1) / QG, (p->D + QC - 1) / QC);
+    prep_phase_tables_kernel<<<grid, 256, sizeof(PhaseSmem), st>>>(p->freqs_dev, p->D, p->D, (const float*)(ws + L.ttab),
+                                                                 nsteps, (float2*)(ws + L.qtab),
+                                                                 need_p ? (float2*)(ws + L.ptab) : (float2*)nullptr);
+    LAUNCH_CHECK(ctx, "prep_phase_tables_kernel");
   }
   return AMPS_OK;
 }
 
 }  // namespace
+
+cudaError_t amps_set_all_func_attrs();   // defined with the launch helpers below
 
 // ------------------------------------------------------------------------------------------
 extern "C" {
@@ -317,6 +323,20 @@ int amps_create(int device, amps_ctx** out) {
   }
   const char* nc = getenv("AMPS_NO_CLUSTER");
   ctx->use_clusters = !(nc && nc[0] == '1');
+  const char* cs = getenv("AMPS_CKPT_SERIAL");
+  ctx->ckpt_overlap = !(cs && cs[0] == '1');
+  // everything the device entry points need besides the caller's buffers is created HERE: kernel
+  // attributes, the replay stream and its events (no allocation, no attribute call per launch)
+  bool ok = amps_set_all_func_attrs() == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; i < 2 && ok; ++i)
+    ok = cudaEventCreateWithFlags(&ctx->ev_replay[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ctx->ev_bwd[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
+    amps_destroy(ctx);
+    return AMPS_E_CUDA;
+  }
   *out = ctx;
   return AMPS_OK;
 }
@@ -327,6 +347,12 @@ int amps_destroy(amps_ctx* ctx) {
   if (ctx->nccl_comm) amps_comm_destroy(ctx);
   if (ctx->hbuf) cudaFree(ctx->hbuf);
   if (ctx->hstream) cudaStreamDestroy(ctx->hstream);
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->ev_replay[i]) cudaEventDestroy(ctx->ev_replay[i]);
+    if (ctx->ev_bwd[i]) cudaEventDestroy(ctx->ev_bwd[i]);
+  }
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 2; ++j)
       if (ctx->ev[i][j]) cudaEventDestroy(ctx->ev[i][j]);
@@ -404,101 +430,221 @@ size_t amps_psi_workspace_bytes(int D, int B, int T, int save_for_bwd) {
   return psi_ws_layout(DP, B, T > 0 ? T - 1 : 0, T, save_for_bwd != 0).total;
 }
 
-int amps_psi_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T,
-                      float* loss_dev, void* ws_dev, size_t ws_bytes, int save_for_bwd,
-                      void* stream) {
+}  // extern "C" (the scan launch helpers below are internal)
+
+// ---- launch of the sequential scan kernels (whole clip or one time window) -----------------------
+namespace {
+struct FwdArgs {
+  const float2 *matN, *matR, *matS, *qtab, *psi0p;
+  const float* x;
+  int T;                 // samples of the launch (window: steps + 1)
+  AVal A;
+  float* loss;
+  double* lossd;
+  float2* traj;          // null: nothing is kept for a backward
+  float* scales;
+  float2* sptraj;
+  float2* ev;
+  SegFwd seg;
+};
+struct BwdArgs {
+  const float2 *matN, *matRH, *matS, *qtab;
+  const float* ttab;
+  const float* x;
+  int T;
+  AVal A;
+  const float* w;
+  const float2* traj;
+  const float* scales;
+  float2* G;
+  float* gf;
+  float2* lam0;
+  double* gAdir;
+  const float2* sptraj;
+  const float2* ev;
+  SegBwd seg;
+};
+
+// which kernel family serves (DP, B) on this context
+enum class Fam { C4, CL, WS, UNI };
+Fam family_of(const amps_ctx* ctx, int DP, int B) {
+  if (DP == 128) return Fam::C4;
+  if (DP == 64) return Fam::UNI;
+  return (ctx->use_clusters && 2 * B <= ctx->num_sms) ? Fam::CL : Fam::WS;
+}
+
+// opt-in dynamic shared memory of every scan kernel, once per context (amps_create).  The carveout is
+// pinned to "max shared" for all of them: an SM only co-hosts CTAs of two kernels (the checkpointed
+// backward runs the replay next to the adjoint) if it does not have to be drained to change its
+// L1/shared split.
+template <class Kern>
+cudaError_t set_smem(Kern k, size_t bytes) {
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+}
+template <int DPc, int NQc>
+cudaError_t set_attrs_ws() {
+  cudaError_t e;
+  if ((e = set_smem(psi_fwd_cl_kernel<DPc, NQc>, sizeof(FwdClSmem<DPc, NQc>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_bwd_cl_kernel<DPc, NQc>, bwd_cl_smem_bytes<DPc, NQc>())) != cudaSuccess) return e;
+  if ((e = set_smem(psi_fwd_kernel<DPc, NQc>, sizeof(FwdSmem<DPc, NQc>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_bwd_kernel<DPc, NQc>, sizeof(BwdSmem<DPc, NQc>))) != cudaSuccess) return e;
+  return set_smem(psi_sample_kernel<DPc, NQc>, sizeof(SampleSmem<DPc>));
+}
+}  // namespace
+cudaError_t amps_set_all_func_attrs() {
+  using namespace amps;
+  cudaError_t e;
+  if ((e = set_attrs_ws<8, 4>()) != cudaSuccess) return e;
+  if ((e = set_attrs_ws<16, 4>()) != cudaSuccess) return e;
+  if ((e = set_attrs_ws<32, 4>()) != cudaSuccess) return e;
+  if ((e = set_smem(psi_fwd_uni_kernel<64, 8>, sizeof(FwdSmemUni<64, 8>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_fwd_uni_kernel<64, 8, true>, sizeof(FwdSmemUni<64, 8>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_bwd_uni_kernel<64, 8>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_bwd_uni_kernel<64, 8, true, false>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_bwd_uni_kernel<64, 8, true, true>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_sample_kernel<64, 8>, sizeof(SampleSmem<64>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_fwd_c4_kernel<128, C4_CL, false>, sizeof(FwdC4Smem<128, C4_CL>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_bwd_c4_kernel<128, C4_CL, false>, sizeof(BwdC4Smem<128, C4_CL>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_compose_tc_kernel<true>, sizeof(ScanTcSmem) + 1024)) != cudaSuccess) return e;
+  if ((e = set_smem(psi_compose_tc_kernel<false>, sizeof(ScanTcSmem) + 1024)) != cudaSuccess) return e;
+  if ((e = set_smem(psi_scan_boundary_kernel, (2 * TC_N * TC_N + 3 * TC_N + 8) * sizeof(float))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_scan_boundary_bwd_kernel, (2 * TC_N * TC_N + TC_N) * sizeof(float))) != cudaSuccess) return e;
+  if ((e = set_smem(prep_phase_tables_kernel, sizeof(PhaseSmem))) != cudaSuccess) return e;
+  if ((e = set_smem(rho_bwd_kernel, rho_bwd_smem_bytes(RHO_MAX_D))) != cudaSuccess) return e;
+  if ((e = set_smem(rho_scan_kernel<false>, rho_smem_bytes(RHO_MAX_D))) != cudaSuccess) return e;
+  if ((e = set_smem(rho_scan_kernel<true>, rho_smem_bytes(RHO_MAX_D))) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+namespace {
+
+int launch_psi_fwd(amps_ctx* ctx, int DP, int B, const FwdArgs& a, cudaStream_t st) {
+  const int nsteps = a.T - 1;
+  const int chl = chunk_len_of(DP);
+  const int nchunks = (nsteps + chl - 1) / chl;
+  const Fam fam = family_of(ctx, DP, B);
+  if (fam == Fam::C4) {   // rows of N, R, S split over a 4-CTA cluster per clip
+    CUDA_TRY(ctx, launch_cluster(psi_fwd_c4_kernel<128, C4_CL, false>, B, C4_CL, 512, sizeof(FwdC4Smem<128, C4_CL>), st,
+                                 a.matN, a.matR, a.matS, a.qtab, a.psi0p, a.x, a.T, a.A, a.loss, a.lossd, a.traj,
+                                 a.scales, nchunks, (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg));
+    LAUNCH_CHECK(ctx, "psi_fwd_c4_kernel");
+    return AMPS_OK;
+  }
+  return dispatch_dp(DP, [&](auto dp, auto nq) -> int {
+    constexpr int DPc = decltype(dp)::value, NQc = decltype(nq)::value;
+    if constexpr (DPc <= 32) {   // warp-specialised chain/filler kernels
+      if (fam == Fam::CL) {
+        // enough idle SMs: one 2-CTA cluster per clip (chain CTA + filler CTA on a second SM)
+        CUDA_TRY(ctx, launch_cluster(psi_fwd_cl_kernel<DPc, NQc>, B, 2, 2 * DPc * NQc + 32, sizeof(FwdClSmem<DPc, NQc>), st,
+                                     a.matN, a.matR, a.matS, a.qtab, a.psi0p, a.x, a.T, a.A, a.loss, a.lossd,
+                                     a.traj, a.scales, nchunks, a.sptraj, a.ev, a.seg));
+        LAUNCH_CHECK(ctx, "psi_fwd_cl_kernel");
+        return AMPS_OK;
+      }
+      psi_fwd_kernel<DPc, NQc><<<B, 2 * DPc * NQc, sizeof(FwdSmem<DPc, NQc>), st>>>(
+          a.matN, a.matR, a.matS, a.qtab, a.psi0p, a.x, a.T, a.A, a.loss, a.lossd, a.traj, a.scales, nchunks,
+          a.sptraj, a.ev, a.seg);
+    } else {
+      psi_fwd_uni_kernel<DPc, NQc><<<B, DPc * NQc, sizeof(FwdSmemUni<DPc, NQc>), st>>>(
+          a.matN, a.matR, a.matS, a.qtab, a.psi0p, a.x, a.T, a.A, a.loss, a.lossd, a.traj, a.scales, nchunks,
+          (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg);
+    }
+    LAUNCH_CHECK(ctx, "psi_fwd_kernel");
+    return AMPS_OK;
+  });
+}
+
+int launch_psi_bwd(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t st) {
+  const int nsteps = a.T - 1;
+  const int chl = chunk_len_of(DP);
+  const int nchunks = (nsteps + chl - 1) / chl;
+  const Fam fam = family_of(ctx, DP, B);
+  if (fam == Fam::C4) {
+    CUDA_TRY(ctx, launch_cluster(psi_bwd_c4_kernel<128, C4_CL, false>, B, C4_CL, 512, sizeof(BwdC4Smem<128, C4_CL>), st,
+                                 a.matN, a.matRH, a.matS, a.qtab, a.ttab, a.x, a.T, a.A, a.w, a.traj, a.scales, nchunks,
+                                 a.G, a.gf, a.lam0, a.gAdir, (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg));
+    LAUNCH_CHECK(ctx, "psi_bwd_c4_kernel");
+    return AMPS_OK;
+  }
+  return dispatch_dp(DP, [&](auto dp, auto nq) -> int {
+    constexpr int DPc = decltype(dp)::value, NQc = decltype(nq)::value;
+    if constexpr (DPc <= 32) {
+      if (fam == Fam::CL) {
+        CUDA_TRY(ctx, launch_cluster(psi_bwd_cl_kernel<DPc, NQc>, B, 2, 3 * DPc * NQc, bwd_cl_smem_bytes<DPc, NQc>(), st,
+                                     a.matN, a.matRH, a.matS, a.qtab, a.ttab, a.x, a.T, a.A, a.w, a.traj, a.scales,
+                                     nchunks, a.G, a.gf, a.lam0, a.gAdir, a.sptraj, a.ev, a.seg));
+        LAUNCH_CHECK(ctx, "psi_bwd_cl_kernel");
+        return AMPS_OK;
+      }
+      psi_bwd_kernel<DPc, NQc><<<B, 2 * DPc * NQc, sizeof(BwdSmem<DPc, NQc>), st>>>(
+          a.matN, a.matRH, a.matS, a.qtab, a.ttab, a.x, a.T, a.A, a.w, a.traj, a.scales, nchunks, a.G, a.gf,
+          a.lam0, a.gAdir, a.sptraj, a.ev, a.seg);
+    } else {
+      psi_bwd_uni_kernel<DPc, NQc><<<B, DPc * NQc, sizeof(BwdSmemUni<DPc>), st>>>(
+          a.matN, a.matRH, a.matS, a.qtab, a.ttab, a.x, a.T, a.A, a.w, a.traj, a.scales, nchunks, a.G, a.gf,
+          a.lam0, a.gAdir, (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg);
+    }
+    LAUNCH_CHECK(ctx, "psi_bwd_kernel");
+    return AMPS_OK;
+  });
+}
+
+// clip reduction + finalize: packed effective-parameter gradient
+int psi_finalize(amps_ctx* ctx, const amps_params* p, int DP, int B, char* ws, const PsiWs& L, const float* w_dev,
+                 float* grad_dev, cudaStream_t st) {
+  const double cprime = -p->delta_t * (double)p->sigma * (double)p->sigma / 2.0;
+  const int total = 3 * DP * DP + 2 * DP;
+  psi_reduce_clips_kernel<<<(total + 127) / 128, 128, 0, st>>>(
+      (const float2*)(ws + L.G), (const float*)(ws + L.gf), (const float2*)(ws + L.lam0), B, DP,
+      (float2*)(ws + L.Gtot), (float*)(ws + L.gftot), (float2*)(ws + L.lam0tot));
+  LAUNCH_CHECK(ctx, "psi_reduce_clips_kernel");
+  psi_grad_finalize_kernel<<<p->D, 128, 0, st>>>(
+      (const float2*)(ws + L.Gtot), (const float*)(ws + L.gftot), (const float2*)(ws + L.lam0tot),
+      (const double*)(ws + L.gAdir), (const double*)(ws + L.lossd), w_dev, B,
+      (const float2*)(ws + L.matR), p->D, DP, cprime, aval(p), grad_dev);
+  LAUNCH_CHECK(ctx, "psi_grad_finalize_kernel");
+  return AMPS_OK;
+}
+
+int check_fwd_args(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T, const float* loss_dev,
+                   const void* ws_dev) {
   int rc = check_common(ctx, p);
   if (rc) return rc;
   if (!p->psi0_dev) return fail(ctx, AMPS_E_INVALID, "psi0_dev is NULL");
   if (B < 0 || T < 1) return fail(ctx, AMPS_E_INVALID, "bad shape B=%d T=%d (need B>=0, T>=1)", B, T);
+  if (B > 0 && (!x_dev || !loss_dev || !ws_dev)) return fail(ctx, AMPS_E_INVALID, "NULL buffer");
+  if (padded_dim(p->D) < 0) return fail(ctx, AMPS_E_UNSUPPORTED, "bond dimension %d > 128 not supported", p->D);
+  return AMPS_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int amps_psi_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T,
+                      float* loss_dev, void* ws_dev, size_t ws_bytes, int save_for_bwd,
+                      void* stream) {
+  int rc = check_fwd_args(ctx, p, x_dev, B, T, loss_dev, ws_dev);
+  if (rc) return rc;
   if (B == 0) return AMPS_OK;
-  if (!x_dev || !loss_dev || !ws_dev) return fail(ctx, AMPS_E_INVALID, "NULL buffer");
   const int DP = padded_dim(p->D);
-  if (DP < 0) return fail(ctx, AMPS_E_UNSUPPORTED, "bond dimension %d > 128 not supported", p->D);
   const bool save = save_for_bwd != 0;
   const PsiWs L = psi_ws_layout(DP, B, T - 1, T, save);
   if (ws_bytes < L.total)
     return fail(ctx, AMPS_E_WORKSPACE, "workspace %zu < required %zu bytes", ws_bytes, L.total);
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)ws_dev;
-  const int nsteps = T - 1;
-  const int chl = chunk_len_of(DP);
-  const int nchunks = (nsteps + chl - 1) / chl;
-  rc = psi_prepare(ctx, p, DP, ws, L, nsteps, st);
+  rc = psi_prepare(ctx, p, DP, ws, L, T - 1, st);
   if (rc) return rc;
-  if (DP == 128) {   // rows of N, R, S split over a 4-CTA cluster per clip
-    PROF_BEGIN(ctx, 0, st);
-    CUDA_TRY(ctx, launch_cluster(psi_fwd_c4_kernel<128, C4_CL, false>, B, C4_CL, 512, sizeof(FwdC4Smem<128, C4_CL>), st,
-                                 (const float2*)(ws + L.matN), (const float2*)(ws + L.matR),
-                                 (const float2*)(ws + L.matS), (const float2*)(ws + L.qtab),
-                                 (const float2*)(ws + L.psi0p), x_dev, T, aval(p), loss_dev,
-                                 (double*)(ws + L.lossd), save ? (float2*)(ws + L.traj) : (float2*)nullptr,
-                                 save ? (float*)(ws + L.scales) : (float*)nullptr, nchunks,
-                                 (const float2*)nullptr, 0, 0,
-                                 save ? (float2*)(ws + L.sptraj) : (float2*)nullptr,
-                                 save ? (float2*)(ws + L.ev) : (float2*)nullptr));
-    PROF_END(ctx, 0, st);
-    LAUNCH_CHECK(ctx, "psi_fwd_c4_kernel");
-    return AMPS_OK;
-  }
-  return dispatch_dp(DP, [&](auto dp, auto nq) -> int {
-    constexpr int DPc = decltype(dp)::value, NQc = decltype(nq)::value;
-    constexpr bool WS = DPc <= 32;   // warp-specialised chain/filler kernel
-    if constexpr (WS) if (ctx->use_clusters && 2 * B <= ctx->num_sms) {
-      // enough idle SMs: one 2-CTA cluster per clip (chain CTA + filler CTA on a second SM)
-      auto kcl = psi_fwd_cl_kernel<DPc, NQc>;
-      const size_t smem_cl = sizeof(FwdClSmem<DPc, NQc>);
-      CUDA_TRY(ctx, cudaFuncSetAttribute(kcl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cl));
-      cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(2 * B);
-      cfg.blockDim = dim3(DPc * NQc + 32);
-      cfg.dynamicSmemBytes = smem_cl;
-      cfg.stream = st;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = 2;
-      at[0].val.clusterDim.y = 1;
-      at[0].val.clusterDim.z = 1;
-      cfg.attrs = at;
-      cfg.numAttrs = 1;
-      PROF_BEGIN(ctx, 0, st);
-      CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, kcl, (const float2*)(ws + L.matN), (const float2*)(ws + L.matR),
-                                       (const float2*)(ws + L.matS), (const float2*)(ws + L.qtab),
-                                       (const float2*)(ws + L.psi0p), x_dev, T, aval(p), loss_dev,
-                                       (double*)(ws + L.lossd), save ? (float2*)(ws + L.traj) : (float2*)nullptr,
-                                       save ? (float*)(ws + L.scales) : (float*)nullptr, nchunks,
-                                       save ? (float2*)(ws + L.sptraj) : (float2*)nullptr,
-                                       save ? (float2*)(ws + L.ev) : (float2*)nullptr));
-      PROF_END(ctx, 0, st);
-      LAUNCH_CHECK(ctx, "psi_fwd_cl_kernel");
-      return AMPS_OK;
-    }
-    const size_t smem = WS ? sizeof(FwdSmem<DPc, NQc>) : sizeof(FwdSmemUni<DPc, NQc>);
-    if constexpr (WS) {
-      CUDA_TRY(ctx, cudaFuncSetAttribute(psi_fwd_kernel<DPc, NQc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    } else {
-      CUDA_TRY(ctx, cudaFuncSetAttribute(psi_fwd_uni_kernel<DPc, NQc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
-    PROF_BEGIN(ctx, 0, st);
-    if constexpr (WS) {
-      psi_fwd_kernel<DPc, NQc><<<B, 2 * DPc * NQc, smem, st>>>(
-          (const float2*)(ws + L.matN), (const float2*)(ws + L.matR), (const float2*)(ws + L.matS),
-          (const float2*)(ws + L.qtab), (const float2*)(ws + L.psi0p), x_dev, T, aval(p), loss_dev,
-          (double*)(ws + L.lossd), save ? (float2*)(ws + L.traj) : nullptr,
-          save ? (float*)(ws + L.scales) : nullptr, nchunks,
-          save ? (float2*)(ws + L.sptraj) : nullptr, save ? (float2*)(ws + L.ev) : nullptr);
-    } else {
-      psi_fwd_uni_kernel<DPc, NQc><<<B, DPc * NQc, smem, st>>>(
-          (const float2*)(ws + L.matN), (const float2*)(ws + L.matR), (const float2*)(ws + L.matS),
-          (const float2*)(ws + L.qtab), (const float2*)(ws + L.psi0p), x_dev, T, aval(p), loss_dev,
-          (double*)(ws + L.lossd), save ? (float2*)(ws + L.traj) : nullptr,
-          save ? (float*)(ws + L.scales) : nullptr, nchunks, (const float2*)nullptr, 0, 0,
-          save ? (float2*)(ws + L.sptraj) : nullptr, save ? (float2*)(ws + L.ev) : nullptr);
-    }
-    PROF_END(ctx, 0, st);
-    LAUNCH_CHECK(ctx, "psi_fwd_kernel");
-    return AMPS_OK;
-  });
+  FwdArgs a{(const float2*)(ws + L.matN), (const float2*)(ws + L.matR), (const float2*)(ws + L.matS),
+            (const float2*)(ws + L.qtab), (const float2*)(ws + L.psi0p), x_dev, T, aval(p), loss_dev,
+            (double*)(ws + L.lossd), save ? (float2*)(ws + L.traj) : nullptr,
+            save ? (float*)(ws + L.scales) : nullptr, save ? (float2*)(ws + L.sptraj) : nullptr,
+            save ? (float2*)(ws + L.ev) : nullptr, seg_full_f(T)};
+  PROF_BEGIN(ctx, 0, st);
+  rc = launch_psi_fwd(ctx, DP, B, a, st);
+  PROF_END(ctx, 0, st);
+  return rc;
 }
 
 int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T,
@@ -521,96 +667,195 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
   if (ws_bytes < L.total)
     return fail(ctx, AMPS_E_WORKSPACE, "workspace %zu < required %zu bytes", ws_bytes, L.total);
   char* ws = (char*)ws_dev;
-  const int nsteps = T - 1;
-  const int chl = chunk_len_of(DP);
-  const int nchunks = (nsteps + chl - 1) / chl;
-  const double cprime = -p->delta_t * (double)p->sigma * (double)p->sigma / 2.0;
-  if (DP == 128) {
-    PROF_BEGIN(ctx, 1, st);
-    CUDA_TRY(ctx, launch_cluster(psi_bwd_c4_kernel<128, C4_CL, false>, B, C4_CL, 512, sizeof(BwdC4Smem<128, C4_CL>), st,
-                                 (const float2*)(ws + L.matN), (const float2*)(ws + L.matRH),
-                                 (const float2*)(ws + L.matS), (const float2*)(ws + L.qtab),
-                                 (const float*)(ws + L.ttab), x_dev, T, aval(p), w_dev,
-                                 (const float2*)(ws + L.traj), (const float*)(ws + L.scales), nchunks,
-                                 (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0),
-                                 (double*)(ws + L.gAdir), (const float2*)nullptr, 0, 0,
-                                 (const float2*)(ws + L.sptraj), (const float2*)(ws + L.ev)));
-    PROF_END(ctx, 1, st);
-    LAUNCH_CHECK(ctx, "psi_bwd_c4_kernel");
-    rc = AMPS_OK;
-  } else
-  rc = dispatch_dp(DP, [&](auto dp, auto nq) -> int {
-    constexpr int DPc = decltype(dp)::value, NQc = decltype(nq)::value;
-    constexpr bool WS = DPc <= 32;
-    if constexpr (WS) if (ctx->use_clusters && 2 * B <= ctx->num_sms) {
-      auto kcl = psi_bwd_cl_kernel<DPc, NQc>;
-      const size_t smem_cl = bwd_cl_smem_bytes<DPc, NQc>();
-      CUDA_TRY(ctx, cudaFuncSetAttribute(kcl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cl));
-      cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(2 * B);
-      cfg.blockDim = dim3(3 * DPc * NQc);
-      cfg.dynamicSmemBytes = smem_cl;
-      cfg.stream = st;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = 2;
-      at[0].val.clusterDim.y = 1;
-      at[0].val.clusterDim.z = 1;
-      cfg.attrs = at;
-      cfg.numAttrs = 1;
-      PROF_BEGIN(ctx, 1, st);
-      CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, kcl, (const float2*)(ws + L.matN), (const float2*)(ws + L.matRH),
-                                       (const float2*)(ws + L.matS), (const float2*)(ws + L.qtab),
-                                       (const float*)(ws + L.ttab), x_dev, T, aval(p), w_dev,
-                                       (const float2*)(ws + L.traj), (const float*)(ws + L.scales), nchunks,
-                                       (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0),
-                                       (double*)(ws + L.gAdir), (const float2*)(ws + L.sptraj),
-                                       (const float2*)(ws + L.ev)));
-      PROF_END(ctx, 1, st);
-      LAUNCH_CHECK(ctx, "psi_bwd_cl_kernel");
-      return AMPS_OK;
-    }
-    const size_t smem = WS ? sizeof(BwdSmem<DPc, NQc>) : sizeof(BwdSmemUni<DPc>);
-    if constexpr (WS) {
-      CUDA_TRY(ctx, cudaFuncSetAttribute(psi_bwd_kernel<DPc, NQc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    } else {
-      CUDA_TRY(ctx, cudaFuncSetAttribute(psi_bwd_uni_kernel<DPc, NQc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
-    PROF_BEGIN(ctx, 1, st);
-    if constexpr (WS) {
-      psi_bwd_kernel<DPc, NQc><<<B, 2 * DPc * NQc, smem, st>>>(
-          (const float2*)(ws + L.matN), (const float2*)(ws + L.matRH), (const float2*)(ws + L.matS),
-          (const float2*)(ws + L.qtab), (const float*)(ws + L.ttab), x_dev, T, aval(p), w_dev,
-          (const float2*)(ws + L.traj), (const float*)(ws + L.scales), nchunks,
-          (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0), (double*)(ws + L.gAdir),
-          (const float2*)(ws + L.sptraj), (const float2*)(ws + L.ev));
-    } else {
-      psi_bwd_uni_kernel<DPc, NQc><<<B, DPc * NQc, smem, st>>>(
-          (const float2*)(ws + L.matN), (const float2*)(ws + L.matRH), (const float2*)(ws + L.matS),
-          (const float2*)(ws + L.qtab), (const float*)(ws + L.ttab), x_dev, T, aval(p), w_dev,
-          (const float2*)(ws + L.traj), (const float*)(ws + L.scales), nchunks,
-          (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0), (double*)(ws + L.gAdir),
-          (const float2*)nullptr, 0, 0, (const float2*)(ws + L.sptraj), (const float2*)(ws + L.ev));
-    }
-    PROF_END(ctx, 1, st);
-    LAUNCH_CHECK(ctx, "psi_bwd_kernel");
-    return AMPS_OK;
-  });
+  BwdArgs a{(const float2*)(ws + L.matN), (const float2*)(ws + L.matRH), (const float2*)(ws + L.matS),
+            (const float2*)(ws + L.qtab), (const float*)(ws + L.ttab), x_dev, T, aval(p), w_dev,
+            (const float2*)(ws + L.traj), (const float*)(ws + L.scales), (float2*)(ws + L.G), (float*)(ws + L.gf),
+            (float2*)(ws + L.lam0), (double*)(ws + L.gAdir), (const float2*)(ws + L.sptraj),
+            (const float2*)(ws + L.ev), seg_full_b(T)};
+  PROF_BEGIN(ctx, 1, st);
+  rc = launch_psi_bwd(ctx, DP, B, a, st);
+  PROF_END(ctx, 1, st);
   if (rc) return rc;
-  {
-    const int total = 3 * DP * DP + 2 * DP;
-    psi_reduce_clips_kernel<<<(total + 127) / 128, 128, 0, st>>>(
-        (const float2*)(ws + L.G), (const float*)(ws + L.gf), (const float2*)(ws + L.lam0), B, DP,
-        (float2*)(ws + L.Gtot), (float*)(ws + L.gftot), (float2*)(ws + L.lam0tot));
-    LAUNCH_CHECK(ctx, "psi_reduce_clips_kernel");
-    psi_grad_finalize_kernel<<<p->D, 128, 0, st>>>(
-        (const float2*)(ws + L.Gtot), (const float*)(ws + L.gftot), (const float2*)(ws + L.lam0tot),
-        (const double*)(ws + L.gAdir), (const double*)(ws + L.lossd), w_dev, B,
-        (const float2*)(ws + L.matR), p->D, DP, cprime, aval(p), grad_dev);
-    LAUNCH_CHECK(ctx, "psi_grad_finalize_kernel");
-  }
-  return AMPS_OK;
+  return psi_finalize(ctx, p, DP, B, ws, L, w_dev, grad_dev, st);
 }
+
+}  // extern "C"
+
+// ---- checkpointed loss / gradient: the state is kept every K steps only ---------------------------
+// Forward: one whole-clip launch that stores x at the start of every K-step window (nothing else).
+// Backward, windows j = last .. 0: the forward kernel REPLAYS window j from its checkpoint into one of two
+// window-sized trajectory buffers (x_k, S x'_k, (E_k,|x_k|^2), c_k), the adjoint kernel sweeps the window
+// from the adjoint the next window left (Lam of its start state) and continues the gradient sums.  The
+// replay of window j-1 runs on the context's second stream while the adjoint of window j runs on the
+// caller's: where the batch leaves room on the SMs (C1: a 160-thread replay CTA next to a 384-thread
+// adjoint CTA) the recompute hides behind the latency-bound adjoint chain.
+namespace {
+struct CkWs {
+  PsiWs base;               // mats, psi0p, ttab, qtab, lossd | G, gf, lam0, gAdir, Gtot, gftot, lam0tot
+  size_t ckpt;              // c64 [B][nwin][DP]
+  size_t loss_scr, lossd_scr;
+  size_t traj[2], sptraj[2], ev[2], scales[2];
+  size_t total;
+  int W, nwin;
+};
+// effective checkpoint interval: K rounded up to whole rescale chunks of the kernels serving D
+int ck_interval(int DP, int K) {
+  const int chl = chunk_len_of(DP);
+  return ((K + chl - 1) / chl) * chl;
+}
+CkWs ck_ws_layout(int DP, int B, int T, int K) {
+  CkWs w{};
+  const int nsteps = T - 1;
+  w.W = ck_interval(DP, K);
+  w.nwin = nsteps > 0 ? (nsteps + w.W - 1) / w.W : 1;
+  w.base = psi_ws_layout(DP, B, nsteps, T, false);
+  size_t off = w.base.total;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += align_up(bytes);
+    return o;
+  };
+  const size_t mat = (size_t)DP * DP * sizeof(float2);
+  const int Wt = (nsteps < w.W ? nsteps : w.W) + 1;   // samples of a window
+  const int wch = (w.W + chunk_len_of(DP) - 1) / chunk_len_of(DP);
+  w.ckpt = take((size_t)B * w.nwin * DP * sizeof(float2));
+  w.loss_scr = take((size_t)B * sizeof(float));
+  w.lossd_scr = take((size_t)B * sizeof(double));
+  for (int i = 0; i < 2; ++i) {
+    w.traj[i] = take((size_t)B * Wt * DP * sizeof(float2));
+    w.sptraj[i] = take((size_t)B * Wt * DP * sizeof(float2));
+    w.ev[i] = take((size_t)B * Wt * sizeof(float2));
+    w.scales[i] = take((size_t)B * wch * sizeof(float));
+  }
+  w.base.G = take((size_t)B * 3 * mat);
+  w.base.gf = take((size_t)B * DP * sizeof(float));
+  w.base.lam0 = take((size_t)B * DP * sizeof(float2));
+  w.base.gAdir = take((size_t)B * sizeof(double));
+  w.base.Gtot = take(3 * mat);
+  w.base.gftot = take((size_t)DP * sizeof(float));
+  w.base.lam0tot = take((size_t)DP * sizeof(float2));
+  w.total = off;
+  return w;
+}
+}  // namespace
+
+extern "C" {
+
+int amps_psi_ckpt_interval(int D, int K) {
+  const int DP = padded_dim(D);
+  if (DP < 0 || K < 1) return 0;
+  return K == 1 ? 1 : ck_interval(DP, K);
+}
+
+size_t amps_psi_workspace_bytes_k(int D, int B, int T, int K) {
+  const int DP = padded_dim(D);
+  if (DP < 0 || B < 0 || T < 0 || K < 1) return 0;
+  if (K == 1) return psi_ws_layout(DP, B, T > 0 ? T - 1 : 0, T, true).total;
+  return ck_ws_layout(DP, B, T > 0 ? T : 1, K).total;
+}
+
+int amps_psi_loss_fwd_k(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T, int K,
+                        float* loss_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+  if (K == 1) return amps_psi_loss_fwd(ctx, p, x_dev, B, T, loss_dev, ws_dev, ws_bytes, 1, stream);
+  int rc = check_fwd_args(ctx, p, x_dev, B, T, loss_dev, ws_dev);
+  if (rc) return rc;
+  if (K < 1) return fail(ctx, AMPS_E_INVALID, "checkpoint interval K=%d must be >= 1", K);
+  if (B == 0) return AMPS_OK;
+  const int DP = padded_dim(p->D);
+  const CkWs L = ck_ws_layout(DP, B, T, K);
+  if (ws_bytes < L.total)
+    return fail(ctx, AMPS_E_WORKSPACE, "workspace %zu < required %zu bytes", ws_bytes, L.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)ws_dev;
+  rc = psi_prepare(ctx, p, DP, ws, L.base, T - 1, st);
+  if (rc) return rc;
+  SegFwd seg = seg_full_f(T);
+  seg.ckpt = (float2*)(ws + L.ckpt);
+  seg.ck_chunks = L.W / chunk_len_of(DP);
+  seg.ck_stride = L.nwin * DP;
+  FwdArgs a{(const float2*)(ws + L.base.matN), (const float2*)(ws + L.base.matR), (const float2*)(ws + L.base.matS),
+            (const float2*)(ws + L.base.qtab), (const float2*)(ws + L.base.psi0p), x_dev, T, aval(p), loss_dev,
+            (double*)(ws + L.base.lossd), nullptr, nullptr, nullptr, nullptr, seg};
+  PROF_BEGIN(ctx, 0, st);
+  rc = launch_psi_fwd(ctx, DP, B, a, st);
+  PROF_END(ctx, 0, st);
+  return rc;
+}
+
+int amps_psi_loss_bwd_k(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T, int K,
+                        const float* w_dev, void* ws_dev, size_t ws_bytes, float* grad_dev, void* stream) {
+  if (K == 1) return amps_psi_loss_bwd(ctx, p, x_dev, B, T, w_dev, ws_dev, ws_bytes, grad_dev, stream);
+  int rc = check_common(ctx, p);
+  if (rc) return rc;
+  if (B < 0 || T < 1) return fail(ctx, AMPS_E_INVALID, "bad shape B=%d T=%d", B, T);
+  if (K < 1) return fail(ctx, AMPS_E_INVALID, "checkpoint interval K=%d must be >= 1", K);
+  if (!grad_dev) return fail(ctx, AMPS_E_INVALID, "grad_dev is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B == 0) {
+    CUDA_TRY(ctx, cudaMemsetAsync(grad_dev, 0, amps_psi_grad_count(p->D) * sizeof(float), st));
+    return AMPS_OK;
+  }
+  if (!x_dev || !w_dev || !ws_dev) return fail(ctx, AMPS_E_INVALID, "NULL buffer");
+  const int DP = padded_dim(p->D);
+  if (DP < 0) return fail(ctx, AMPS_E_UNSUPPORTED, "bond dimension %d > 128 not supported", p->D);
+  const CkWs L = ck_ws_layout(DP, B, T, K);
+  if (ws_bytes < L.total)
+    return fail(ctx, AMPS_E_WORKSPACE, "workspace %zu < required %zu bytes", ws_bytes, L.total);
+  char* ws = (char*)ws_dev;
+  const int nsteps = T - 1;
+  if (nsteps == 0) {   // nothing to sweep: Lam_0 = 0, all sums zero
+    const size_t mat = (size_t)DP * DP * sizeof(float2);
+    CUDA_TRY(ctx, cudaMemsetAsync(ws + L.base.G, 0, (size_t)B * 3 * mat, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ws + L.base.gf, 0, (size_t)B * DP * sizeof(float), st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ws + L.base.lam0, 0, (size_t)B * DP * sizeof(float2), st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ws + L.base.gAdir, 0, (size_t)B * sizeof(double), st));
+    return psi_finalize(ctx, p, DP, B, ws, L.base, w_dev, grad_dev, st);
+  }
+  cudaStream_t s2 = ctx->ckpt_overlap ? ctx->aux_stream : st;
+  const float2* qtab = (const float2*)(ws + L.base.qtab);
+  const float* ttab = (const float*)(ws + L.base.ttab);
+  auto wlen = [&](int j) { return (nsteps - j * L.W < L.W) ? nsteps - j * L.W : L.W; };
+  auto replay = [&](int j) -> int {     // forward of window j from its checkpoint, on the second stream
+    const int i = j & 1;
+    SegFwd seg{T, (const float2*)(ws + L.ckpt) + (size_t)j * DP, L.nwin * DP, nullptr, 1, 0};
+    FwdArgs a{(const float2*)(ws + L.base.matN), (const float2*)(ws + L.base.matR), (const float2*)(ws + L.base.matS),
+              qtab + (size_t)j * L.W * DP, (const float2*)(ws + L.base.psi0p), x_dev + (size_t)j * L.W, wlen(j) + 1,
+              aval(p), (float*)(ws + L.loss_scr), (double*)(ws + L.lossd_scr), (float2*)(ws + L.traj[i]),
+              (float*)(ws + L.scales[i]), (float2*)(ws + L.sptraj[i]), (float2*)(ws + L.ev[i]), seg};
+    return launch_psi_fwd(ctx, DP, B, a, s2);
+  };
+  auto adjoint = [&](int j) -> int {
+    const int i = j & 1;
+    const bool last = j == L.nwin - 1;
+    SegBwd seg{T, last ? nullptr : (const float2*)(ws + L.base.lam0), last ? 0 : 1, j > 0 ? 1 : 0};
+    BwdArgs a{(const float2*)(ws + L.base.matN), (const float2*)(ws + L.base.matRH), (const float2*)(ws + L.base.matS),
+              qtab + (size_t)j * L.W * DP, ttab + (size_t)j * L.W, x_dev + (size_t)j * L.W, wlen(j) + 1, aval(p), w_dev,
+              (const float2*)(ws + L.traj[i]), (const float*)(ws + L.scales[i]), (float2*)(ws + L.base.G),
+              (float*)(ws + L.base.gf), (float2*)(ws + L.base.lam0), (double*)(ws + L.base.gAdir),
+              (const float2*)(ws + L.sptraj[i]), (const float2*)(ws + L.ev[i]), seg};
+    return launch_psi_bwd(ctx, DP, B, a, st);
+  };
+  PROF_BEGIN(ctx, 1, st);
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));          // the replay stream joins behind the forward
+  CUDA_TRY(ctx, cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
+  if ((rc = replay(L.nwin - 1))) return rc;
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_replay[(L.nwin - 1) & 1], s2));
+  for (int j = L.nwin - 1; j >= 0; --j) {
+    CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_replay[j & 1], 0));
+    if (j > 0) {
+      // window j-1 lands in the buffer the adjoint of window j+1 has just read
+      if (j + 1 < L.nwin) CUDA_TRY(ctx, cudaStreamWaitEvent(s2, ctx->ev_bwd[(j + 1) & 1], 0));
+      if ((rc = replay(j - 1))) return rc;
+      CUDA_TRY(ctx, cudaEventRecord(ctx->ev_replay[(j - 1) & 1], s2));
+    }
+    if ((rc = adjoint(j))) return rc;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_bwd[j & 1], st));
+  }
+  PROF_END(ctx, 1, st);
+  return psi_finalize(ctx, p, DP, B, ws, L.base, w_dev, grad_dev, st);
+}
+
+}  // extern "C"
 
 // ---- parallel-in-time loss / gradient (tcgen05 operator scan), D <= 64 -------------------------
 namespace {
@@ -665,6 +910,8 @@ ScanWs scan_ws_layout(int B, int T, bool save) {
 }
 }  // namespace
 
+extern "C" {
+
 size_t amps_psi_scan_workspace_bytes(int D, int B, int T, int save_for_bwd) {
   if (D <= 0 || D > 64 || B <= 0 || T < 1) return 0;
   return scan_ws_layout(B, T, save_for_bwd != 0).total;
@@ -693,7 +940,6 @@ int amps_psi_loss_fwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
   {
     const size_t smem = sizeof(ScanTcSmem) + 1024;
     auto kcomp = p->D <= 32 ? psi_compose_tc_kernel<true> : psi_compose_tc_kernel<false>;
-    CUDA_TRY(ctx, cudaFuncSetAttribute(kcomp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PROF_BEGIN(ctx, 2, st);
     kcomp<<<nv, TC_THREADS, smem, st>>>((const float2*)(ws + L.base.matN), (const float2*)(ws + L.base.matR),
                                         (const float2*)(ws + L.base.qtab), x_dev, T, aval(p), L.nvc,
@@ -703,7 +949,6 @@ int amps_psi_loss_fwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
   }
   {
     const size_t bsm = (size_t)(2 * TC_N * TC_N + 3 * TC_N + 8) * sizeof(float);
-    CUDA_TRY(ctx, cudaFuncSetAttribute(psi_scan_boundary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
     psi_scan_boundary_kernel<<<B, 256, bsm, st>>>((const float*)(ws + L.ops), (const float2*)(ws + L.base.psi0p),
                                                   L.nvc, (float2*)(ws + L.ystart), (float*)(ws + L.rnv));
   }
@@ -711,7 +956,6 @@ int amps_psi_loss_fwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
   {
     auto kern = psi_fwd_uni_kernel<64, 8, true>;
     const size_t smem = sizeof(FwdSmemUni<64, 8>);
-    CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PROF_BEGIN(ctx, 0, st);
     kern<<<nv, 64 * 8, smem, st>>>((const float2*)(ws + L.base.matN), (const float2*)(ws + L.base.matR),
                                    (const float2*)(ws + L.base.matS), (const float2*)(ws + L.base.qtab),
@@ -720,7 +964,7 @@ int amps_psi_loss_fwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
                                    save ? (float*)(ws + L.scales) : (float*)nullptr, 0,
                                    (const float2*)(ws + L.ystart), L.nvc, L.m_steps,
                                    save ? (float2*)(ws + L.sptraj) : (float2*)nullptr,
-                                   save ? (float2*)(ws + L.ev) : (float2*)nullptr);
+                                   save ? (float2*)(ws + L.ev) : (float2*)nullptr, seg_full_f(T));
     PROF_END(ctx, 0, st);
     LAUNCH_CHECK(ctx, "psi_fwd_uni_kernel<virtual clips>");
   }
@@ -757,8 +1001,6 @@ int amps_psi_loss_bwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
   auto kern_chain = psi_bwd_uni_kernel<64, 8, true, false>;   // pass 1: adjoint chain only
   auto kern_full = psi_bwd_uni_kernel<64, 8, true, true>;     // pass 2: chain + gradient tiles
   const size_t smem = sizeof(BwdSmemUni<64>);
-  CUDA_TRY(ctx, cudaFuncSetAttribute(kern_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CUDA_TRY(ctx, cudaFuncSetAttribute(kern_full, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   auto adjoint_pass = [&](const float2* lam_end) {
     auto kern = lam_end ? kern_full : kern_chain;
     kern<<<nv, 64 * 8, smem, st>>>((const float2*)(ws + L.base.matN), (const float2*)(ws + L.base.matRH),
@@ -767,14 +1009,13 @@ int amps_psi_loss_bwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
                                    (const float2*)(ws + L.traj), (const float*)(ws + L.scales), 0,
                                    (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0),
                                    (double*)(ws + L.gAdir), lam_end, L.nvc, L.m_steps,
-                                   (const float2*)(ws + L.sptraj), (const float2*)(ws + L.ev));
+                                   (const float2*)(ws + L.sptraj), (const float2*)(ws + L.ev), seg_full_b(T));
   };
   PROF_BEGIN(ctx, 1, st);
   adjoint_pass(nullptr);                                   // d_j: chunk adjoints with a zero end condition
   LAUNCH_CHECK(ctx, "psi_bwd_uni_kernel<virtual clips, pass 1>");
   {
     const size_t bsm = (size_t)(2 * TC_N * TC_N + TC_N) * sizeof(float);
-    CUDA_TRY(ctx, cudaFuncSetAttribute(psi_scan_boundary_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
     psi_scan_boundary_bwd_kernel<<<B, 256, bsm, st>>>((const float*)(ws + L.ops), (const float*)(ws + L.rnv),
                                                       (const float2*)(ws + L.lam0), L.nvc,
                                                       (float2*)(ws + L.lamend));
@@ -825,7 +1066,6 @@ int amps_psi_sample(amps_ctx* ctx, const amps_params* p, const float* noise_dev,
     constexpr int DPc = decltype(dp)::value, NQc = decltype(nq)::value;
     auto kern = psi_sample_kernel<DPc, NQc>;
     const size_t smem = sizeof(SampleSmem<DPc>);
-    CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PROF_BEGIN(ctx, 2, st);
     kern<<<n, DPc * NQc, smem, st>>>((const float2*)(ws + L.matN), (const float2*)(ws + L.matR),
                                      (const float2*)(ws + L.qtab), (const float2*)(ws + L.psi0p),

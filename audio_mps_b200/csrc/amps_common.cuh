@@ -118,6 +118,25 @@ struct AVal {
 };
 __device__ __forceinline__ float a_get(AVal a) { return a.dev ? __ldg(a.dev) : a.host; }
 
+// Time-window ("segment") launch of the scan kernels: the checkpointed backward replays and
+// differentiates one window of K steps at a time.  The host passes x / q_k / t_k pointers already
+// offset to the window's first step; the kernels then only need the row stride of the waveform, the
+// per-clip start states and end adjoints, and whether their gradient outputs continue a running sum.
+struct SegFwd {
+  int xstride;            // samples between consecutive clips of x (= the full clip length)
+  const float2* x0;       // per-clip start state, x0[b * x0_stride + r] (null: the shared psi_0)
+  int x0_stride;          // in float2 units
+  float2* ckpt;           // checkpoint out: state at the start of every ck_chunks-th chunk (null: none)
+  int ck_chunks;          // checkpoint interval in chunks
+  int ck_stride;          // float2 units between consecutive clips' checkpoint rows
+};
+struct SegBwd {
+  int xstride;
+  const float2* lam_end;  // per-clip adjoint of the window's end state [B][DP] (null: zero)
+  int accumulate;         // G / g_f / dA outputs continue the sums already in the output buffers
+  int tprev_valid;        // t_{k-1} exists for the window's first step (window does not start at step 0)
+};
+
 // ---- thread map ---------------------------------------------------------------------------
 // A CTA of DP*NQ threads owns one clip.  Thread t = i*NQ + jq holds, for matrix row i, the
 // CPT = DP/NQ columns  col(c) = 2*NQ*(c/2) + 2*jq + (c&1)  in registers, so that for a fixed

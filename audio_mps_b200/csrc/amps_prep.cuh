@@ -128,26 +128,88 @@ __global__ void prep_pad_vec_kernel(const float2* __restrict__ v, int D, int DP,
   if (i < DP) vp[i] = (i < D) ? v[i] : make_float2(0.f, 0.f);
 }
 
-// q_k[c] = p_k[c] conj(p_{k+1}[c]),  p_k[c] = exp(i * fl32(f_c * t_k))  (model.py:304-305).
-// The two float32 angles are exact in double; their difference and the sincos are done in
-// double and rounded once.
-__global__ void prep_qtab_kernel(const float* __restrict__ freqs, int D, int DP,
-                                 const float* __restrict__ ttab, int nsteps,
-                                 float2* __restrict__ qtab) {
-  const size_t total = (size_t)nsteps * DP;
-  for (size_t idx = threadIdx.x + (size_t)blockIdx.x * blockDim.x; idx < total;
-       idx += (size_t)blockDim.x * gridDim.x) {
-    const int k = (int)(idx / DP), c = (int)(idx % DP);
-    float2 q = make_float2(1.f, 0.f);
-    if (c < D) {
-      const float f = freqs[c];
-      const double th0 = (double)__fmul_rn(f, ttab[k]);
-      const double th1 = (double)__fmul_rn(f, ttab[k + 1]);
-      double sn, cs;
-      sincos(th0 - th1, &sn, &cs);
-      q = make_float2((float)cs, (float)sn);
+// q_k[c] = p_k[c] conj(p_{k+1}[c]),  p_k[c] = exp(i * fl32(f_c * t_k))  (model.py:304-305), from the two
+// float32 angles (exact in double), evaluated in double.
+// The chain multiplies the state by q_k at EVERY step, so the accumulated phase is the PRODUCT of the
+// ROUNDED table entries -- and their rounding errors are not random: fl32(f t_k) moves on a coarse grid
+// (ulp ~1e-3 rad at 14000 rad), so q_k takes only two or three distinct values per component for
+// thousands of steps and the same ~1.4e-8 rad rounding error repeats, i.e. accumulates LINEARLY
+// (9e-4 rad over 64000 steps; it showed as 1.1e-3 in the full-length sampler golden, where E(psi) is a
+// small residual of large terms and is fed back).  Fix: error feedback.  One thread walks QG
+// consecutive steps of one component and keeps the double-precision product Q_j of the entries it has
+// already rounded; entry j is  fl32( exp(i (theta_{k0} - theta_{k0+j+1})) / Q_j ),  so the product of
+// the rounded entries tracks the exact rotation to ONE rounding (phase and modulus) anywhere inside a
+// group, and the group boundaries add at most 1.5e-8 rad each (125 groups over 64000 steps).
+// Measured (CPU emulation of the sampler arithmetic, 64000 steps): accumulated phase error 9e-4 ->
+// 9e-7 rad, full-length sample error 1.1e-3 -> 2.6e-5 (the reference's own float32 run: 3.9e-5).
+// Two phases per block (one group of QG steps x up to 32 components), software-pipelined over sub-tiles
+// of QT steps: warps 1..7 evaluate the exact rotations exp(i (theta_first - theta_{j+1})) in double
+// (independent, the expensive sincos) into shared memory; warp 0, one lane per component, runs the
+// strictly sequential feedback recurrence over them (a few dependent FP64 FMAs per entry) and stores the
+// rounded entries, 256 coalesced bytes per step.  ~35k cycles per group instead of ~800k for one thread
+// doing both.
+constexpr int QG = 512;    // steps per error-feedback group
+constexpr int QT = 64;     // steps per pipeline sub-tile
+constexpr int QC = 32;     // components per block (one lane of warp 0 each)
+struct alignas(16) PhaseSmem {
+  double2 ex[2][QT][QC];   // exact rotation from the group's first step to step j+1
+};
+// grid = (ceil(nsteps / QG), ceil(ld / QC)), block = 256.  Components c >= D (zero padding up to the row
+// stride ld) get q = 1.  ptab (optional, Rho trajectories): p_{k+1} = exp(i fl32(f t_{k+1})).
+__global__ void __launch_bounds__(256)
+    prep_phase_tables_kernel(const float* __restrict__ freqs, int D, int ld, const float* __restrict__ ttab,
+                             int nsteps, float2* __restrict__ qtab, float2* __restrict__ ptab) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PhaseSmem& sm = *reinterpret_cast<PhaseSmem*>(smem_raw);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int k0 = blockIdx.x * QG, n = min(QG, nsteps - k0);
+  const int c0 = blockIdx.y * QC;
+  const int ntiles = (n + QT - 1) / QT;
+  const float* tt = ttab + k0;
+
+  // exact rotations of sub-tile s, by the threads [first, first + nthr) of the block
+  auto produce = [&](int s, int first, int nthr) {
+    const int j0 = s * QT, len = min(QT, n - j0);
+    for (int idx = t - first; idx < len * QC; idx += nthr) {
+      const int j = idx / QC, cl = idx % QC, c = c0 + cl;
+      double2 e = make_double2(1.0, 0.0);
+      if (c < D) {
+        const float f = freqs[c];
+        const double th_first = (double)__fmul_rn(f, tt[0]);
+        const double th = (double)__fmul_rn(f, tt[j0 + j + 1]);
+        sincos(th_first - th, &e.y, &e.x);
+        if (ptab) {
+          double sn, cs;
+          sincos(th, &sn, &cs);
+          ptab[(size_t)(k0 + j0 + j) * ld + c] = make_float2((float)cs, (float)sn);
+        }
+      }
+      sm.ex[s & 1][j][cl] = e;
     }
-    qtab[idx] = q;
+  };
+
+  produce(0, 0, 256);
+  __syncthreads();
+  double Qx = 1.0, Qy = 0.0;            // product of the entries rounded so far (warp 0: one component per lane)
+  for (int s = 0; s < ntiles; ++s) {
+    if (warp == 0) {
+      const int j0 = s * QT, len = min(QT, n - j0);
+      const int c = c0 + lane;
+      float2* dst = qtab + (size_t)(k0 + j0) * ld + c;
+      for (int j = 0; j < len; ++j) {
+        const double2 e = sm.ex[s & 1][j][lane];
+        // entry = fl32(e / Q);  1/|Q|^2 = 2 - |Q|^2 to 1e-14 (|Q|^2 - 1 ~ 1e-7)
+        const double inv = 2.0 - (Qx * Qx + Qy * Qy);
+        const float2 q = make_float2((float)((e.x * Qx + e.y * Qy) * inv), (float)((e.y * Qx - e.x * Qy) * inv));
+        const double nx = Qx * (double)q.x - Qy * (double)q.y, ny = Qx * (double)q.y + Qy * (double)q.x;
+        Qx = nx;
+        Qy = ny;
+        if (c < ld) dst[(size_t)j * ld] = (c < D) ? q : make_float2(1.f, 0.f);
+      }
+    } else if (s + 1 < ntiles) {
+      produce(s + 1, 32, 224);
+    }
+    __syncthreads();
   }
 }
 

@@ -86,13 +86,13 @@ struct alignas(16) SampleSmem {
 // K1: forward per-clip loss (model.py:257-267, 276-282, 293-334)
 // -------------------------------------------------------------------------------------------
 template <int DP, int NQ>
-__global__ void __launch_bounds__(2 * DP * NQ)
+__global__ void __launch_bounds__(2 * DP * NQ, 1)
     psi_fwd_kernel(const float2* __restrict__ matN, const float2* __restrict__ matR,
                    const float2* __restrict__ matS, const float2* __restrict__ qtab,
                    const float2* __restrict__ psi0p, const float* __restrict__ x, int T, AVal A_,
                    float* __restrict__ loss, double* __restrict__ lossd,
                    float2* __restrict__ traj, float* __restrict__ scales, int nchunks,
-                   float2* __restrict__ sptraj, float2* __restrict__ evout) {
+                   float2* __restrict__ sptraj, float2* __restrict__ evout, SegFwd seg) {
   const float A = a_get(A_);
   using M = Map<DP, NQ>;
   using Sm = FwdSmem<DP, NQ>;
@@ -110,12 +110,12 @@ __global__ void __launch_bounds__(2 * DP * NQ)
   const int i = tr / NQ, jq = tr % NQ, lane = t & 31;
   const int b = blockIdx.x;
   const int nsteps = T - 1;
-  const float* xb = x + (size_t)b * T;
+  const float* xb = x + (size_t)b * seg.xstride;
   auto chunk_len = [&](int c) { return min(CHK, nsteps - c * CHK); };
 
   // ---- prologue (all threads): inputs of chunk 0, start state ------------------------------
   if (t < DP) {
-    const float2 p = psi0p[t];
+    const float2 p = seg.x0 ? seg.x0[(size_t)b * seg.x0_stride + t] : psi0p[t];
     sm.xs[0][0][t] = p;
     if (traj) traj[(size_t)b * T * DP + t] = p;
   }
@@ -250,6 +250,8 @@ __global__ void __launch_bounds__(2 * DP * NQ)
             if (evout) evout[(size_t)b * T + k0 + kk] = make_float2(E, nu2);   // for the adjoint sweep
           }
         }
+        if (seg.ckpt && cc % seg.ck_chunks == 0 && tr < DP)   // state checkpoint: x at the start of chunk cc
+          seg.ckpt[(size_t)b * seg.ck_stride + (size_t)(cc / seg.ck_chunks) * DP + tr] = sm.xs[p][0][tr];
         if (traj) {   // flush x_{k0+1 .. k0+len}
           const float4* src = reinterpret_cast<const float4*>(&sm.xs[p][1][0]);
           float4* dst = reinterpret_cast<float4*>(traj + ((size_t)b * T + k0 + 1) * DP);
@@ -299,7 +301,7 @@ __global__ void __launch_bounds__(2 * DP * NQ)
 // complete) and prepare chunk c-1 (x', S x', alpha, beta, packed per-row chain inputs).
 // -------------------------------------------------------------------------------------------
 template <int DP, int NQ>
-__global__ void __launch_bounds__(2 * DP * NQ)
+__global__ void __launch_bounds__(2 * DP * NQ, 1)
     psi_bwd_kernel(const float2* __restrict__ matN, const float2* __restrict__ matRH,
                    const float2* __restrict__ matS, const float2* __restrict__ qtab,
                    const float* __restrict__ ttab, const float* __restrict__ x, int T, AVal A_,
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(2 * DP * NQ)
                    const float* __restrict__ scales, int nchunks, float2* __restrict__ Gout,
                    float* __restrict__ gfout, float2* __restrict__ lam0out,
                    double* __restrict__ gAdir, const float2* __restrict__ sptraj,
-                   const float2* __restrict__ evin) {
+                   const float2* __restrict__ evin, SegBwd seg) {
   const float A = a_get(A_);
   using M = Map<DP, NQ>;
   using Sm = BwdSmem<DP, NQ>;
@@ -333,7 +335,8 @@ __global__ void __launch_bounds__(2 * DP * NQ)
     load_slice<DP, NQ>(Nr, matN, i, jq);   // N is Hermitian: N^dag mu uses the same slices
     load_slice<DP, NQ>(Hr, matRH, i, jq);  // R^dag
     float2 lam = make_float2(0.f, 0.f);    // adjoint of x_{k+1}, replicated over the NQ lanes
-    float gf = 0.f;
+    if (seg.lam_end) lam = seg.lam_end[(size_t)b * DP + i];
+    float gf = seg.accumulate ? gfout[(size_t)b * DP + i] : 0.f;
     const bool mu_on = jq == 0;
     for (int c = nchunks; c >= -1; --c) {
       if (c >= 0 && c < nchunks) {
@@ -400,13 +403,22 @@ __global__ void __launch_bounds__(2 * DP * NQ)
     }
   } else {
     // =================================== FILLER WARPS =========================================
-    const float* xb = x + (size_t)b * T;
+    const float* xb = x + (size_t)b * seg.xstride;
     const float2* trb = traj + (size_t)b * T * DP;
     const float wb = w[b];
     float2 GR[CPT], GN[CPT], GE[CPT];
+    {
+      const float2* Gb = Gout + (size_t)b * 3 * DP * DP;
 #pragma unroll
-    for (int c = 0; c < CPT; ++c) GR[c] = GN[c] = GE[c] = make_float2(0.f, 0.f);
+      for (int c = 0; c < CPT; ++c) {
+        const int col = M::col(c, jq);
+        GR[c] = seg.accumulate ? Gb[0 * DP * DP + i * DP + col] : make_float2(0.f, 0.f);
+        GN[c] = seg.accumulate ? Gb[1 * DP * DP + i * DP + col] : make_float2(0.f, 0.f);
+        GE[c] = seg.accumulate ? Gb[2 * DP * DP + i * DP + col] : make_float2(0.f, 0.f);
+      }
+    }
     double gAacc = 0.0;
+    const bool tpv = seg.tprev_valid != 0;
 
     auto issue_loads = [&](int c) {
       const int k0 = c * CHK, len = chunk_len(c);
@@ -418,8 +430,8 @@ __global__ void __launch_bounds__(2 * DP * NQ)
       for (int idx = tr; idx < len * DP / 2; idx += NTC) cp_async16(qdst + 2 * idx, qsrc + 2 * idx);
       for (int idx = tr; idx <= len; idx += NTC) {
         cp_async4(&sm.wav[c & 1][idx], xb + k0 + idx);
-        // tt[0] = t_{k0-1} (t_0 for the first chunk: dtm_0 is forced to 0 there), tt[1+kk] = t_{k0+kk}
-        cp_async4(&sm.tt[c & 1][idx], ttab + (k0 + idx > 0 ? k0 + idx - 1 : 0));
+        // tt[0] = t_{k0-1} (t_0 for the clip's first chunk: dtm_0 is forced to 0 there), tt[1+kk] = t_{k0+kk}
+        cp_async4(&sm.tt[c & 1][idx], ttab + ((k0 + idx > 0 || tpv) ? k0 + idx - 1 : 0));
       }
       if (tr == 0) cp_async4(&sm.scs[c & 1][0], scales + (size_t)b * nchunks + c);
       const float2* ssrc = sptraj + ((size_t)b * T + k0) * DP;
@@ -470,7 +482,7 @@ __global__ void __launch_bounds__(2 * DP * NQ)
         const float inc = sm.wav[lq][tr + 1] - sm.wav[lq][tr];
         const float s = inc / A;
         sm.sv[lp3][tr] = s;
-        sm.dtm[tr] = (k0 + tr > 0) ? sm.tt[lq][tr + 1] - sm.tt[lq][tr] : 0.f;
+        sm.dtm[tr] = (k0 + tr > 0 || tpv) ? sm.tt[lq][tr + 1] - sm.tt[lq][tr] : 0.f;
         const float2 ev = sm.evl[lq][tr];
         const float E = ev.x, nu2 = ev.y;
         const float arg = 1.0f + (E * inc) / A;
@@ -526,7 +538,7 @@ __global__ void __launch_bounds__(2 * DP * NQ)
     if (lane == 0) sm.lred[tr >> 5] = gAacc;
     bar_named(2, NTC);
     if (tr == 0) {
-      double tot = 0.0;
+      double tot = seg.accumulate ? gAdir[b] : 0.0;
       for (int wv = 0; wv < NTC / 32; ++wv) tot += sm.lred[wv];
       gAdir[b] = tot;
     }
@@ -589,7 +601,7 @@ __global__ void __launch_bounds__(DP* NQ)
                    float* __restrict__ loss, double* __restrict__ lossd,
                    float2* __restrict__ traj, float* __restrict__ scales, int nchunks,
                    const float2* __restrict__ psi0v, int nvc, int m_steps,
-                   float2* __restrict__ sptraj, float2* __restrict__ evout) {
+                   float2* __restrict__ sptraj, float2* __restrict__ evout, SegFwd seg) {
   const float A = a_get(A_);
   using M = Map<DP, NQ>;
   using Sm = FwdSmemUni<DP, NQ>;
@@ -602,9 +614,9 @@ __global__ void __launch_bounds__(DP* NQ)
   const int t = threadIdx.x, i = t / NQ, jq = t % NQ, lane = t & 31, warp = t >> 5;
   const int b = blockIdx.x;
   int nsteps = T - 1;
-  const float* xb = x + (size_t)b * T;
+  const float* xb = x + (size_t)b * (VIRT ? T : seg.xstride);
   const float2* qtab = qtab_;
-  const float2* psi0p = psi0p_;
+  const float2* psi0p = (!VIRT && seg.x0) ? seg.x0 + (size_t)b * seg.x0_stride : psi0p_;
   size_t tstride = T;        // trajectory rows / rescale factors per (virtual) clip
   int sstride = nchunks;
   if (VIRT) {
@@ -669,6 +681,8 @@ __global__ void __launch_bounds__(DP* NQ)
     if (c + 1 < nchunks) issue_loads(c + 1, buf ^ 1);
     cp_async_commit();
     __syncthreads();  // (D) sv/incv, xs[0], ns[.][0] of this chunk visible; last chunk's flush done
+    if (!VIRT) if (seg.ckpt && c % seg.ck_chunks == 0 && t < DP)   // state checkpoint: x at the start of chunk c
+      seg.ckpt[(size_t)b * seg.ck_stride + (size_t)(c / seg.ck_chunks) * DP + t] = sm.xs[0][t];
 
     float* const stn = &sm.ns[buf][1][i];
     float2* const sp_st = &sm.sps[0][i];
@@ -860,7 +874,8 @@ __global__ void __launch_bounds__(DP* NQ)
                    const float* __restrict__ scales_, int nchunks, float2* __restrict__ Gout,
                    float* __restrict__ gfout, float2* __restrict__ lam0out,
                    double* __restrict__ gAdir, const float2* __restrict__ lam_end, int nvc,
-                   int m_steps, const float2* __restrict__ sptraj, const float2* __restrict__ evin) {
+                   int m_steps, const float2* __restrict__ sptraj, const float2* __restrict__ evin,
+                   SegBwd seg) {
   const float A = a_get(A_);
   using M = Map<DP, NQ>;
   constexpr int NT = M::NT;
@@ -872,7 +887,8 @@ __global__ void __launch_bounds__(DP* NQ)
   const int t = threadIdx.x, i = t / NQ, jq = t % NQ, lane = t & 31, warp = t >> 5;
   const int b = blockIdx.x;
   int nsteps = T - 1;
-  const float* xb = x + (size_t)b * T;
+  const float* xb = x + (size_t)b * (VIRT ? T : seg.xstride);
+  const bool accum = !VIRT && seg.accumulate;
   size_t rows = T;                       // trajectory rows per (virtual) clip
   const float2* qtab = qtab_;
   const float* ttab = ttab_;
@@ -900,8 +916,16 @@ __global__ void __launch_bounds__(DP* NQ)
   load_slice<DP, NQ>(Hr, matRH, i, jq);  // R^dag
 
   float2 GR[CPT], GN[CPT], GE[CPT];
+  {
+    const float2* Gb = Gout + (size_t)b * 3 * DP * DP;
 #pragma unroll
-  for (int c = 0; c < CPT; ++c) GR[c] = GN[c] = GE[c] = make_float2(0.f, 0.f);
+    for (int c = 0; c < CPT; ++c) {
+      const int col = M::col(c, jq);
+      GR[c] = (TILES && accum) ? Gb[0 * DP * DP + i * DP + col] : make_float2(0.f, 0.f);
+      GN[c] = (TILES && accum) ? Gb[1 * DP * DP + i * DP + col] : make_float2(0.f, 0.f);
+      GE[c] = (TILES && accum) ? Gb[2 * DP * DP + i * DP + col] : make_float2(0.f, 0.f);
+    }
+  }
 
   auto chunk_len = [&](int c) { return min(CH, nsteps - c * CH); };
 
@@ -961,8 +985,12 @@ __global__ void __launch_bounds__(DP* NQ)
   };
 
   float2 lam = make_float2(0.f, 0.f);  // adjoint of x_{k+1}, replicated over the NQ lanes
-  if (VIRT) if (lam_end) lam = lam_end[(size_t)b * DP + i];
-  float gf = 0.f;
+  if (VIRT) {
+    if (lam_end) lam = lam_end[(size_t)b * DP + i];
+  } else if (seg.lam_end) {
+    lam = seg.lam_end[(size_t)b * DP + i];
+  }
+  float gf = accum ? gfout[(size_t)b * DP + i] : 0.f;
 
   if (nchunks > 0) {
     const int cl = nchunks - 1;
@@ -1096,7 +1124,7 @@ __global__ void __launch_bounds__(DP* NQ)
   if (lane == 0) sm.lred[warp] = gAacc;
   __syncthreads();
   if (t == 0) {
-    double tot = 0.0;
+    double tot = accum ? gAdir[b] : 0.0;
     for (int wv = 0; wv < NT / 32; ++wv) tot += sm.lred[wv];
     gAdir[b] = tot;
   }

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(512)
                       float* __restrict__ loss, double* __restrict__ lossd,
                       float2* __restrict__ traj, float* __restrict__ scales, int nchunks,
                       const float2* __restrict__ psi0v, int nvc, int m_steps,
-                      float2* __restrict__ sptraj, float2* __restrict__ evout) {
+                      float2* __restrict__ sptraj, float2* __restrict__ evout, SegFwd seg) {
   const float A = a_get(A_);
   using Cf = C4<DP, CL>;
   constexpr int NQ = Cf::NQ, CPT = Cf::CPT, RP = Cf::RP, NTL = Cf::NTL;
@@ -71,9 +71,9 @@ __global__ void __launch_bounds__(512)
   const int b = blockIdx.x / CL;
   const int i = (int)rank * RP + il;     // global matrix row of this thread
   int nsteps = T - 1;
-  const float* xb = x + (size_t)b * T;
+  const float* xb = x + (size_t)b * (VIRT ? T : seg.xstride);
   const float2* qtab = qtab_;
-  const float2* psi0p = psi0p_;
+  const float2* psi0p = (!VIRT && seg.x0) ? seg.x0 + (size_t)b * seg.x0_stride : psi0p_;
   size_t tstride = T;
   int sstride = nchunks;
   if (VIRT) {
@@ -148,6 +148,8 @@ __global__ void __launch_bounds__(512)
     // (D) sv/incv and xs[0] of this chunk visible; EVERY CTA is done with the previous chunk, so its
     // xs / xps / enx may be overwritten remotely from here on
     cluster_sync_all();
+    if (!VIRT) if (seg.ckpt && rank == 0 && c % seg.ck_chunks == 0 && t < DP)   // state checkpoint
+      seg.ckpt[(size_t)b * seg.ck_stride + (size_t)(c / seg.ck_chunks) * DP + t] = sm.xs[0][t];
 
     float2 xp_prev = make_float2(0.f, 0.f);
     float s_cur = sm.sv[buf][0];
@@ -348,7 +350,8 @@ __global__ void __launch_bounds__(512)
                       const float* __restrict__ scales_, int nchunks, float2* __restrict__ Gout,
                       float* __restrict__ gfout, float2* __restrict__ lam0out,
                       double* __restrict__ gAdir, const float2* __restrict__ lam_end, int nvc,
-                      int m_steps, const float2* __restrict__ sptraj, const float2* __restrict__ evin) {
+                      int m_steps, const float2* __restrict__ sptraj, const float2* __restrict__ evin,
+                      SegBwd seg) {
   const float A = a_get(A_);
   using Cf = C4<DP, CL>;
   constexpr int NQ = Cf::NQ, CPT = Cf::CPT, NP = Cf::NP, RP = Cf::RP, NTL = Cf::NTL;
@@ -360,7 +363,8 @@ __global__ void __launch_bounds__(512)
   const int b = blockIdx.x / CL;
   const int i = (int)rank * RP + il;
   int nsteps = T - 1;
-  const float* xb = x + (size_t)b * T;
+  const float* xb = x + (size_t)b * (VIRT ? T : seg.xstride);
+  const bool accum = !VIRT && seg.accumulate;
   size_t rows = T;
   const float2* qtab = qtab_;
   const float* ttab = ttab_;
@@ -389,8 +393,16 @@ __global__ void __launch_bounds__(512)
   load_slice<DP, NQ>(Hr, matRH, i, jq);  // R^dag
 
   float2 GR[CPT], GN[CPT], GE[CPT];
+  {
+    const float2* Gb = Gout + (size_t)b * 3 * DP * DP;
 #pragma unroll
-  for (int c = 0; c < CPT; ++c) GR[c] = GN[c] = GE[c] = make_float2(0.f, 0.f);
+    for (int c = 0; c < CPT; ++c) {
+      const int col = Map<DP, NQ>::col(c, jq);
+      GR[c] = accum ? Gb[0 * DP * DP + i * DP + col] : make_float2(0.f, 0.f);
+      GN[c] = accum ? Gb[1 * DP * DP + i * DP + col] : make_float2(0.f, 0.f);
+      GE[c] = accum ? Gb[2 * DP * DP + i * DP + col] : make_float2(0.f, 0.f);
+    }
+  }
 
   auto chunk_len = [&](int c) { return min(CH4, nsteps - c * CH4); };
 
@@ -448,8 +460,12 @@ __global__ void __launch_bounds__(512)
     }
   };
   float2 lam = make_float2(0.f, 0.f);  // adjoint of x_{k+1,i}, replicated over the NQ lanes
-  if (VIRT) if (lam_end) lam = lam_end[(size_t)b * DP + i];
-  float gf = 0.f;
+  if (VIRT) {
+    if (lam_end) lam = lam_end[(size_t)b * DP + i];
+  } else if (seg.lam_end) {
+    lam = seg.lam_end[(size_t)b * DP + i];
+  }
+  float gf = accum ? gfout[(size_t)b * DP + i] : 0.f;
   if (t == 0) {
     mbar_init(&sm.mbar[0], 1);
     mbar_init(&sm.mbar[1], 1);
@@ -597,7 +613,7 @@ __global__ void __launch_bounds__(512)
   if (lane == 0) sm.lred[warp] = gAacc;
   __syncthreads();
   if (t == 0 && rank == 0) {
-    double tot = 0.0;
+    double tot = accum ? gAdir[b] : 0.0;
     for (int wv = 0; wv < NTL / 32; ++wv) tot += sm.lred[wv];
     gAdir[b] = tot;
   }

@@ -31,15 +31,19 @@ struct alignas(16) FwdClSmem {
   unsigned long long empty_bar[2];   // chain CTA : the filler has pulled ring p
 };
 
-// block = NTC + 32 threads; grid = 2*B CTAs in clusters of 2
+// block = 2*NTC + 32 threads; grid = 2*B CTAs in clusters of 2.  The block size is set by the FILLER CTA: with
+// one work group of NTC threads its per-chunk work (pull, S x', E_k, loss, trajectory / S x' / (E, nu^2) stores)
+// took longer than the chain's 32 steps when everything is kept for the backward (308 instead of 280
+// cycles per step); two work groups share the steps of a chunk.  In the chain CTA the extra warps only
+// attend the per-chunk __syncthreads.
 template <int DP, int NQ>
-__global__ void __launch_bounds__(DP* NQ + 32)
+__global__ void __launch_bounds__(2 * DP * NQ + 32, 1)
     psi_fwd_cl_kernel(const float2* __restrict__ matN, const float2* __restrict__ matR,
                       const float2* __restrict__ matS, const float2* __restrict__ qtab,
                       const float2* __restrict__ psi0p, const float* __restrict__ x, int T, AVal A_,
                       float* __restrict__ loss, double* __restrict__ lossd,
                       float2* __restrict__ traj, float* __restrict__ scales, int nchunks,
-                      float2* __restrict__ sptraj, float2* __restrict__ evout) {
+                      float2* __restrict__ sptraj, float2* __restrict__ evout, SegFwd seg) {
   const float A = a_get(A_);
   using M = Map<DP, NQ>;
   using Sm = FwdClSmem<DP, NQ>;
@@ -54,7 +58,7 @@ __global__ void __launch_bounds__(DP* NQ + 32)
   const unsigned rank = cluster_ctarank();
   const int b = blockIdx.x >> 1;
   const int nsteps = T - 1;
-  const float* xb = x + (size_t)b * T;
+  const float* xb = x + (size_t)b * seg.xstride;
   const int lane = t & 31;
   auto chunk_len = [&](int c) { return min(CH, nsteps - c * CH); };
 
@@ -71,7 +75,8 @@ __global__ void __launch_bounds__(DP* NQ + 32)
 
   if (rank == 0) {
     // ===================================== CHAIN CTA ==========================================
-    const bool is_loader = t >= NTC;           // last warp: prefetch of q_k / waveform, s_k
+    const bool is_loader = t >= NTC && t < NTC + 32;   // one warp: prefetch of q_k / waveform, s_k
+    const bool is_chain = t < NTC;
     const int i = t / NQ, jq = t % NQ;         // (chain threads)
     auto load_inputs = [&](int c) {            // loader warp only
       const int buf = c & 1, k0 = c * CH, len = chunk_len(c);
@@ -85,7 +90,7 @@ __global__ void __launch_bounds__(DP* NQ + 32)
       if (lane < len) sm.sv[buf][lane] = (sm.wav[buf][lane + 1] - sm.wav[buf][lane]) / A;   // model.py:263,303
     };
     if (t < DP) {
-      const float2 p = psi0p[t];
+      const float2 p = seg.x0 ? seg.x0[(size_t)b * seg.x0_stride + t] : psi0p[t];
       sm.xs[0][0][t] = p;
       if (traj) traj[(size_t)b * T * DP + t] = p;
     }
@@ -93,7 +98,7 @@ __global__ void __launch_bounds__(DP* NQ + 32)
     __syncthreads();
 
     float2 Nr[CPT], Rr[CPT];
-    if (!is_loader) {
+    if (is_chain) {
       load_slice<DP, NQ>(Nr, matN, i, jq);
       load_slice<DP, NQ>(Rr, matR, i, jq);
     }
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(DP* NQ + 32)
         const int p = c & 1, len = chunk_len(c);
         if (is_loader) {
           if (c + 1 < nchunks) load_inputs(c + 1);
-        } else {
+        } else if (is_chain) {
           float2* const st2 = (jq == 0) ? &sm.xs[p][1][i] : &sm.xps[p][0][i];
           const bool st2_on = jq < 2;
           float s_cur = sm.sv[p][0];
@@ -167,8 +172,10 @@ __global__ void __launch_bounds__(DP* NQ + 32)
   } else {
     // ===================================== FILLER CTA =========================================
     const int tr = t;
-    const bool work = tr < NTC;                // the extra warp only takes part in the barriers
-    const int i = (work ? tr : 0) / NQ, jq = tr % NQ;
+    const bool work = tr < 2 * NTC;            // two work groups; the extra warp only copies and takes part in the barriers
+    const int wg = tr / NTC;                   // work group: steps wg, wg + 2, ... of a chunk
+    const int tl = tr % NTC;
+    const int i = tl / NQ, jq = tl % NQ;
     float2 Sr[CPT];
     if (work) load_slice<DP, NQ>(Sr, matS, i, jq);
     double lossacc = 0.0;
@@ -204,16 +211,19 @@ __global__ void __launch_bounds__(DP* NQ + 32)
         __syncthreads();
         if (t == 0) mbar_arrive_remote(rempty + 8 * p);       // ring p may be overwritten
         if (t < len) sm.incv[0][t] = sm.wav[0][t + 1] - sm.wav[0][t];
+#ifdef AMPS_EXP_FWD_NOFILL
+        if (len > 100000)
+#endif
         if (work) {
-          for (int kk = 0; kk < len; ++kk) {
+          for (int kk = wg; kk < len; kk += 2) {
             const float2 part = matvec1<DP, NQ>(Sr, sm.xps[0][kk], jq);
             const float2 xpi = sm.xps[0][kk][i];
             sm.spp[kk][jq][i] = part;
-            sm.es[kk][tr] = fmaf(xpi.x, part.x, xpi.y * part.y);
+            sm.es[kk][tl] = fmaf(xpi.x, part.x, xpi.y * part.y);
           }
         }
         __syncthreads();
-        if (work) {
+        if (tr < NTC) {
           const int kk = tr / G, g = tr % G;
           float en = 0.f, nu2 = 0.f;
           if (kk < len) {
@@ -233,11 +243,19 @@ __global__ void __launch_bounds__(DP* NQ + 32)
             if (evout) evout[(size_t)b * T + k0 + kk] = make_float2(E, nu2);   // for the adjoint sweep
           }
         }
+        if (seg.ckpt && cc % seg.ck_chunks == 0 && t < DP)    // state checkpoint: x at the start of chunk cc
+          seg.ckpt[(size_t)b * seg.ck_stride + (size_t)(cc / seg.ck_chunks) * DP + t] = sm.xs[0][0][t];
+#ifdef AMPS_EXP_FWD_NOFILL
+        if (len > 100000)
+#endif
         if (traj) {
           const float4* src = reinterpret_cast<const float4*>(&sm.xs[0][1][0]);
           float4* dst = reinterpret_cast<float4*>(traj + ((size_t)b * T + k0 + 1) * DP);
           for (int idx = t; idx < len * DP / 2; idx += blockDim.x) dst[idx] = src[idx];
         }
+#ifdef AMPS_EXP_FWD_NOFILL
+        if (len > 100000)
+#endif
         if (sptraj) {   // S x'_k for the adjoint sweep (saves it the mat-vec)
           float2* dst = sptraj + ((size_t)b * T + k0) * DP;
           for (int idx = t; idx < len * DP; idx += blockDim.x) {
@@ -278,7 +296,13 @@ __global__ void __launch_bounds__(DP* NQ + 32)
 //                      (ld.shared::cluster) and accumulate the rank-1 gradient tiles, each over
 //                      half of the chunk's steps (their accumulators are summed at the end).
 // Slot c (c = nchunks .. -1): chain runs chunk c; prep prepares chunk c-1 and loads chunk c-2;
-// tiles accumulate chunk c+1.  One barrier.cluster per slot.
+// tiles accumulate chunk c+1.  Hand-off by mbarriers in each other's shared memory (remote
+// mbarrier.arrive.release.cluster, local try_wait), two buffers by chunk parity:
+//   done_bar[p] (filler CTA): the chain has finished the chunk in buffer p -- its mu ring is complete and
+//                             its pushed inputs are dead; the filler then pulls the ring and pushes the
+//                             inputs of the chunk two further down into the same buffer
+//   in_full[p]  (chain CTA) : both of those have happened: the chain may run the next chunk in buffer p
+// The chain never waits on a cluster-wide barrier (one barrier.cluster per chunk cost ~1000 cycles).
 // -------------------------------------------------------------------------------------------
 template <int DP, int NQ>
 struct alignas(16) BwdClChainSmem {   // what the CHAIN CTA keeps (and the filler addresses remotely)
@@ -286,6 +310,7 @@ struct alignas(16) BwdClChainSmem {   // what the CHAIN CTA keeps (and the fille
   float4 cinb[2][CH][DP];      // { beta_k x_k,i , dtm_k x_k,i }
   float2 mus[2][CH][DP];       // adjoint of x'_k
   float svc[2][CH];            // s_k for the chain
+  unsigned long long in_full[2];   // buffer p holds the pushed inputs of a chunk AND its mu ring has been pulled
 };
 template <int DP, int NQ>
 struct alignas(16) BwdClFillSmem {    // FILLER CTA
@@ -302,6 +327,7 @@ struct alignas(16) BwdClFillSmem {    // FILLER CTA
   float sv[3][CH], alphas[3][CH];
   float incv[CH], betas[CH], dtm[CH];
   double lred[32];
+  unsigned long long done_bar[2];  // the chain CTA has finished the chunk in buffer p
 };
 template <int DP, int NQ>
 constexpr size_t bwd_cl_smem_bytes() {
@@ -309,8 +335,23 @@ constexpr size_t bwd_cl_smem_bytes() {
                                                                         : sizeof(BwdClFillSmem<DP, NQ>);
 }
 
+// launch bound 512 (the kernel runs 3*DP*NQ <= 384 threads): caps the chain at 128 registers, so that a
+// 160-thread forward-replay CTA still fits next to a 384-thread adjoint CTA on one SM (checkpointed backward)
+#ifndef AMPS_BWD_CL_MAXT
+#define AMPS_BWD_CL_MAXT 384
+#endif
+#ifndef AMPS_BWD_CL_MINB
+#define AMPS_BWD_CL_MINB 0
+#endif
+#ifndef AMPS_BWD_PREFETCH
+#define AMPS_BWD_PREFETCH 1
+#endif
 template <int DP, int NQ>
-__global__ void __launch_bounds__(3 * DP * NQ)
+#if AMPS_BWD_CL_MINB
+__global__ void __launch_bounds__(AMPS_BWD_CL_MAXT, 1)
+#else
+__global__ void __launch_bounds__(AMPS_BWD_CL_MAXT)
+#endif
     psi_bwd_cl_kernel(const float2* __restrict__ matN, const float2* __restrict__ matRH,
                       const float2* __restrict__ matS, const float2* __restrict__ qtab,
                       const float* __restrict__ ttab, const float* __restrict__ x, int T, AVal A_,
@@ -318,7 +359,7 @@ __global__ void __launch_bounds__(3 * DP * NQ)
                       const float* __restrict__ scales, int nchunks, float2* __restrict__ Gout,
                       float* __restrict__ gfout, float2* __restrict__ lam0out,
                       double* __restrict__ gAdir, const float2* __restrict__ sptraj,
-                      const float2* __restrict__ evin) {
+                      const float2* __restrict__ evin, SegBwd seg) {
   const float A = a_get(A_);
   using M = Map<DP, NQ>;
   constexpr int NTC = M::NT;
@@ -339,6 +380,22 @@ __global__ void __launch_bounds__(3 * DP * NQ)
   const int tr = t - grp * NTC;
   const int i = tr / NQ, jq = tr % NQ;
   auto chunk_len = [&](int c) { return min(CH, nsteps - c * CH); };
+  // n-th use (descending chunks) of the parity-p barriers by chunk c: phase parity of that use
+  auto use_parity = [&](int c) { return (unsigned)((((nchunks - 1 - c) >> 1)) & 1); };
+
+  if (t == 0) {
+    if (rank == 0) {
+      mbar_init(&cs.in_full[0], 1);
+      mbar_init(&cs.in_full[1], 1);
+    } else {
+      mbar_init(&sm.done_bar[0], 1);
+      mbar_init(&sm.done_bar[1], 1);
+    }
+    mbar_fence_init_cluster();
+  }
+  __syncthreads();
+  cluster_arrive_release();   // both CTAs' barriers are initialised before any remote arrive
+  cluster_wait_acquire();
 
   if (rank == 0) {
     // ===================================== CHAIN CTA ==========================================
@@ -348,11 +405,15 @@ __global__ void __launch_bounds__(3 * DP * NQ)
     if (grp == 0) {
       load_slice<DP, NQ>(Nr, matN, i, jq);
       load_slice<DP, NQ>(Hr, matRH, i, jq);
+      if (seg.lam_end) lam = seg.lam_end[(size_t)b * DP + i];
+      if (seg.accumulate) gf = gfout[(size_t)b * DP + i];
     }
     const bool mu_on = jq == 0;
-    for (int c = nchunks; c >= -1; --c) {
-      if (grp == 0 && c >= 0 && c < nchunks) {
+    const unsigned rdone = dsmem_addr(&sm.done_bar[0], 1);
+    if (grp == 0) for (int c = nchunks - 1; c >= 0; --c) {
+      {
         const int ca = c & 1, len = chunk_len(c);
+        mbar_wait(&cs.in_full[ca], use_parity(c));   // inputs of chunk c pushed, ring ca pulled
         // shared-window addresses of this chunk's chain inputs, computed once (generic pointers into
         // shared memory make the compiler re-read %cluster_ctaid inside the step loop)
         const unsigned mu_a = smem_addr_pinned(&cs.mus[ca][0][i]);
@@ -369,6 +430,13 @@ __global__ void __launch_bounds__(3 * DP * NQ)
         }
         bar_named(1, NTC);
         const unsigned mus_addr = smem_addr_pinned(&cs.mus[ca][0][2 * jq]);
+        // the filler's inputs of a step (s_k, {beta x_k, dt x_k}, {c q, alpha S x'}_{k-1}) are complete for the
+        // whole chunk before the chain enters it: they are fetched ONE STEP AHEAD, behind the mu loads, so
+        // that after the barrier only the mu ring itself is waited for and L_k = N + s_k R^dag can be formed
+        // while those loads are in flight
+        float s = lds32a(svc_a + (unsigned)(len - 1) * (unsigned)sizeof(float));
+        float4 b4 = lds128v(cinb_a + (unsigned)(len - 1) * ROW4);
+        float4 a4 = lds128v(cina_a + (unsigned)(len > 1 ? len - 2 : 0) * ROW4);
         auto step = [&](int kk) {
           float2 mv[CPT];
 #pragma unroll
@@ -378,9 +446,17 @@ __global__ void __launch_bounds__(3 * DP * NQ)
             mv[2 * m + 1] = make_float2(v.z, v.w);
           }
           const unsigned km = (unsigned)(kk > 0 ? kk - 1 : 0);
-          const float s = lds32a(svc_a + (unsigned)kk * (unsigned)sizeof(float));
-          const float4 b4 = lds128v(cinb_a + (unsigned)kk * ROW4);
-          const float4 a4 = lds128v(cina_a + km * ROW4);
+          const unsigned km2 = (unsigned)(kk > 1 ? kk - 2 : 0);
+#if AMPS_BWD_PREFETCH
+          const float s_n = lds32a(svc_a + km * (unsigned)sizeof(float));
+          const float4 b4_n = lds128v(cinb_a + km * ROW4);
+          const float4 a4_n = lds128v(cina_a + km2 * ROW4);
+#else
+          (void)km2;
+          s = lds32a(svc_a + (unsigned)kk * (unsigned)sizeof(float));
+          b4 = lds128v(cinb_a + (unsigned)kk * ROW4);
+          a4 = lds128v(cina_a + km * ROW4);
+#endif
           float2 a0 = make_float2(0.f, 0.f), a1 = a0;
 #pragma unroll
           for (int cc = 0; cc < CPT; cc += 2) {
@@ -399,6 +475,11 @@ __global__ void __launch_bounds__(3 * DP * NQ)
           mu.x += a4.z;
           mu.y += a4.w;
           sts64a_if(mu_on && kk > 0, mu_a + km * ROW2, mu);
+#if AMPS_BWD_PREFETCH
+          s = s_n;
+          b4 = b4_n;
+          a4 = a4_n;
+#endif
           bar_named(1, NTC);
         };
         if (len == CH) {
@@ -407,24 +488,26 @@ __global__ void __launch_bounds__(3 * DP * NQ)
         } else {
           for (int kk = len - 1; kk >= 0; --kk) step(kk);
         }
+        // every chain thread is past the last step's barrier: ring ca is complete, its inputs are dead
+        if (t == 0) mbar_arrive_remote(rdone + 8 * ca);
       }
-      __syncthreads();
-      cluster_arrive_release();
-      cluster_wait_acquire();
     }
     if (grp == 0 && jq == 0) {
       gfout[(size_t)b * DP + i] = gf;
       lam0out[(size_t)b * DP + i] = lam;
     }
+    cluster_arrive_release();   // do not exit while the filler may still read this CTA's rings
+    cluster_wait_acquire();
   } else {
     // ===================================== FILLER CTA =========================================
-    const float* xb = x + (size_t)b * T;
+    const float* xb = x + (size_t)b * seg.xstride;
     const float2* trb = traj + (size_t)b * T * DP;
     const float wb = w[b];
     float2 GR[CPT], GN[CPT], GE[CPT];
 #pragma unroll
     for (int c = 0; c < CPT; ++c) GR[c] = GN[c] = GE[c] = make_float2(0.f, 0.f);
     double gAacc = 0.0;
+    const bool tpv = seg.tprev_valid != 0;
 
     auto issue_loads = [&](int c) {          // prep group
       const int k0 = c * CH, len = chunk_len(c);
@@ -436,7 +519,7 @@ __global__ void __launch_bounds__(3 * DP * NQ)
       for (int idx = tr; idx < len * DP / 2; idx += NTC) cp_async16(qdst + 2 * idx, qsrc + 2 * idx);
       for (int idx = tr; idx <= len; idx += NTC) {
         cp_async4(&sm.wav[c & 1][idx], xb + k0 + idx);
-        cp_async4(&sm.tt[c & 1][idx], ttab + (k0 + idx > 0 ? k0 + idx - 1 : 0));
+        cp_async4(&sm.tt[c & 1][idx], ttab + ((k0 + idx > 0 || tpv) ? k0 + idx - 1 : 0));
       }
       if (tr == 0) cp_async4(&sm.scs[c & 1][0], scales + (size_t)b * nchunks + c);
       const float2* ssrc = sptraj + ((size_t)b * T + k0) * DP;
@@ -447,14 +530,14 @@ __global__ void __launch_bounds__(3 * DP * NQ)
         cp_async4(reinterpret_cast<float*>(&sm.evl[c & 1][0]) + idx, reinterpret_cast<const float*>(esrc) + idx);
     };
 
-    auto tiles_chunk = [&](int c) {          // tiles group
+    auto tiles_pull = [&](int c) {           // tiles group: the chunk's mu ring out of the chain CTA
       const int len = chunk_len(c);
-      {  // pull the chunk's mu ring out of the chain CTA
-        const unsigned rm = dsmem_addr(&cs.mus[c & 1][0][0], 0);
-        float4* lm = reinterpret_cast<float4*>(&sm.mul[0][0]);
-        for (int idx = t - NTC; idx < len * DP / 2; idx += 2 * NTC) lm[idx] = ld_dsmem_f4(rm + 16 * idx);
-      }
-      bar_named(3, 2 * NTC);
+      const unsigned rm = dsmem_addr(&cs.mus[c & 1][0][0], 0);
+      float4* lm = reinterpret_cast<float4*>(&sm.mul[0][0]);
+      for (int idx = t - NTC; idx < len * DP / 2; idx += 2 * NTC) lm[idx] = ld_dsmem_f4(rm + 16 * idx);
+    };
+    auto tiles_chunk = [&](int c) {          // tiles group (after the slot's __syncthreads: sm.mul is complete)
+      const int len = chunk_len(c);
       const float2(*xsb)[DP] = sm.xs[c & 3];
       const float2(*xpb)[DP] = sm.xps[c % 3];
 #ifdef AMPS_EXPERIMENT_NO_TILES
@@ -496,7 +579,7 @@ __global__ void __launch_bounds__(3 * DP * NQ)
         const float s = inc / A;
         sm.sv[lp3][tr] = s;
         st_dsmem_f1(rs + 4 * tr, s);
-        sm.dtm[tr] = (k0 + tr > 0) ? sm.tt[lq][tr + 1] - sm.tt[lq][tr] : 0.f;
+        sm.dtm[tr] = (k0 + tr > 0 || tpv) ? sm.tt[lq][tr + 1] - sm.tt[lq][tr] : 0.f;
         const float2 ev = sm.evl[lq][tr];          // (E_k, |x_k|^2) from the forward
         const float E = ev.x, nu2 = ev.y;
         const float arg = 1.0f + (E * inc) / A;
@@ -532,7 +615,11 @@ __global__ void __launch_bounds__(3 * DP * NQ)
       if (nchunks > 0) issue_loads(nchunks - 1);
       cp_async_commit();
     }
+    const unsigned rfull = dsmem_addr(&cs.in_full[0], 0);
     for (int c = nchunks; c >= -1; --c) {
+      const bool have_up = c + 1 >= 0 && c + 1 < nchunks;   // chunk c+1 exists: its ring is to be pulled
+      // the chain has finished chunk c+1: ring (c+1)&1 is complete and buffer (c-1)&1 == (c+1)&1 is free
+      if (have_up) mbar_wait(&sm.done_bar[(c + 1) & 1], use_parity(c + 1));
       if (grp == 0) {
         if (c - 2 >= 0) issue_loads(c - 2);
         cp_async_commit();
@@ -540,19 +627,22 @@ __global__ void __launch_bounds__(3 * DP * NQ)
         bar_named(2, NTC);
         if (c - 1 >= 0) prep_chunk(c - 1);
       } else {
-        if (c + 1 >= 0 && c + 1 < nchunks) tiles_chunk(c + 1);
+        if (have_up) tiles_pull(c + 1);
       }
-      __syncthreads();
-      cluster_arrive_release();
-      cluster_wait_acquire();
+      __syncthreads();          // inputs of chunk c-1 pushed, ring of chunk c+1 pulled
+      if (t == 0 && c - 1 >= 0) mbar_arrive_remote(rfull + 8 * ((c - 1) & 1));
+      if (grp != 0 && have_up) tiles_chunk(c + 1);
+      __syncthreads();          // tiles done with xps / xs / mul before the next slot's prep rewrites them
     }
+    cluster_arrive_release();
+    cluster_wait_acquire();
     if (grp == 0) {
       cp_async_wait<0>();
       gAacc = warp_sum_d(gAacc);
       if (lane == 0) sm.lred[tr >> 5] = gAacc;
       bar_named(2, NTC);
       if (tr == 0) {
-        double tot = 0.0;
+        double tot = seg.accumulate ? gAdir[b] : 0.0;
         for (int wv = 0; wv < NTC / 32; ++wv) tot += sm.lred[wv];
         gAdir[b] = tot;
       }
@@ -573,11 +663,21 @@ __global__ void __launch_bounds__(3 * DP * NQ)
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
           const int col = M::col(c, jq);
-          const float2 r = scratch[(0 * CPT + c) * NTC + tr], n = scratch[(1 * CPT + c) * NTC + tr],
-                       e = scratch[(2 * CPT + c) * NTC + tr];
-          Gb[0 * DP * DP + i * DP + col] = make_float2(GR[c].x + r.x, GR[c].y + r.y);
-          Gb[1 * DP * DP + i * DP + col] = make_float2(GN[c].x + n.x, GN[c].y + n.y);
-          Gb[2 * DP * DP + i * DP + col] = make_float2(GE[c].x + e.x, GE[c].y + e.y);
+          float2 r = scratch[(0 * CPT + c) * NTC + tr], n = scratch[(1 * CPT + c) * NTC + tr],
+                 e = scratch[(2 * CPT + c) * NTC + tr];
+          r = make_float2(GR[c].x + r.x, GR[c].y + r.y);
+          n = make_float2(GN[c].x + n.x, GN[c].y + n.y);
+          e = make_float2(GE[c].x + e.x, GE[c].y + e.y);
+          if (seg.accumulate) {   // continue the sums of the later time windows
+            const float2 r0 = Gb[0 * DP * DP + i * DP + col], n0 = Gb[1 * DP * DP + i * DP + col],
+                         e0 = Gb[2 * DP * DP + i * DP + col];
+            r = make_float2(r.x + r0.x, r.y + r0.y);
+            n = make_float2(n.x + n0.x, n.y + n0.y);
+            e = make_float2(e.x + e0.x, e.y + e0.y);
+          }
+          Gb[0 * DP * DP + i * DP + col] = r;
+          Gb[1 * DP * DP + i * DP + col] = n;
+          Gb[2 * DP * DP + i * DP + col] = e;
         }
       }
     }

@@ -8,6 +8,7 @@
 #pragma once
 #include "../../include/audiomps.h"
 #include "amps_common.cuh"
+#include "amps_prep.cuh"
 
 namespace amps {
 
@@ -50,26 +51,7 @@ __global__ void fill_kernel(float* __restrict__ p, int n, float v) {
   if (i < n) p[i] = v;
 }
 
-// Phase tables of a call: q_k = exp(i (fl32(f t_k) - fl32(f t_{k+1}))) and (optionally) p_{k+1} =
-// exp(i fl32(f t_{k+1})), from the float32 angles of the reference (model.py:178-179), evaluated in
-// double and rounded once.
-__global__ void rho_prep_phase_kernel(const float* __restrict__ freqs, const float* __restrict__ ttab,
-                                      int nsteps, int D, float2* __restrict__ qtab, float2* __restrict__ ptab) {
-  const size_t total = (size_t)nsteps * D;
-  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int k = (int)(idx / D), c = (int)(idx % D);
-    const float f = freqs[c];
-    const double th0 = (double)__fmul_rn(f, ttab[k]);
-    const double th1 = (double)__fmul_rn(f, ttab[k + 1]);
-    double sn, cs;
-    sincos(th0 - th1, &sn, &cs);
-    qtab[idx] = make_float2((float)cs, (float)sn);
-    if (ptab) {
-      sincos(th1, &sn, &cs);
-      ptab[idx] = make_float2((float)cs, (float)sn);
-    }
-  }
-}
+// Phase tables of a call (q_k, and p_{k+1} for lab-frame trajectories): prep_phase_tables_kernel, amps_prep.cuh.
 
 struct RhoArgs {
   const float2* R;      // [D][D]
@@ -553,8 +535,6 @@ inline int rho_launch_bwd(const amps_params* p, const float* ttab, const float2*
   g.lam0out = (float2*)(ws + L.lam0);
   g.gAdir = (double*)(ws + L.gAdir);
   const size_t smem = rho_bwd_smem_bytes(p->D);
-  if (cudaFuncSetAttribute(rho_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-    return AMPS_E_CUDA;
   rho_bwd_kernel<<<B, rho_block(p->D), smem, st>>>(g);
   if (cudaGetLastError() != cudaSuccess) return AMPS_E_CUDA;
   rho_grad_finalize_kernel<<<1, 256, 0, st>>>((const float2*)(ws + L.G), (const float*)(ws + L.acc),

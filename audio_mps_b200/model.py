@@ -82,24 +82,32 @@ class _PsiLossFn(torch.autograd.Function):
                             sigma=float(model.sigma), delta_t=float(model.delta_t),
                             A_dev=a_dev.data_ptr())
         # scan=True: the parallel-in-time tensor-core path (small batches, D <= 64)
-        ws_bytes = lib.amps_psi_scan_workspace_bytes if scan else lib.amps_psi_workspace_bytes
-        fwd = lib.amps_psi_loss_fwd_scan if scan else lib.amps_psi_loss_fwd
-        nbytes = ws_bytes(D, B, T, 1 if need_grad else 0)
+        # K > 1 (sequential kernels only): keep one state per K steps and recompute in the backward
+        K = 1 if (scan or not need_grad) else model._checkpoint_interval(D, B, T)
+        if K > 1:
+            nbytes = lib.amps_psi_workspace_bytes_k(D, B, T, K)
+        else:
+            ws_bytes = lib.amps_psi_scan_workspace_bytes if scan else lib.amps_psi_workspace_bytes
+            nbytes = ws_bytes(D, B, T, 1 if need_grad else 0)
         if nbytes == 0:
             raise _lib.AmpsError(-2, f"bond dimension {D} is not supported by the Psi "
                                      f"{'tensor-core scan' if scan else 'kernels'}")
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         loss = torch.empty(B, dtype=torch.float32, device=dev)
-        rc = fwd(h, C.byref(p), _ptr(x), B, T, _ptr(loss), _ptr(ws), nbytes,
-                 1 if need_grad else 0, _stream(dev))
+        if K > 1:
+            rc = lib.amps_psi_loss_fwd_k(h, C.byref(p), _ptr(x), B, T, K, _ptr(loss), _ptr(ws), nbytes, _stream(dev))
+        else:
+            fwd = lib.amps_psi_loss_fwd_scan if scan else lib.amps_psi_loss_fwd
+            rc = fwd(h, C.byref(p), _ptr(x), B, T, _ptr(loss), _ptr(ws), nbytes,
+                     1 if need_grad else 0, _stream(dev))
         _lib.check(h, rc)
         if need_grad:
-            ctx.keep = (R_ri, freqs, psi0_ri, x, ws, p, h, model, scan, a_dev)
+            ctx.keep = (R_ri, freqs, psi0_ri, x, ws, p, h, model, scan, a_dev, K)
         return loss
 
     @staticmethod
     def backward(ctx, gloss):
-        R_ri, freqs, psi0_ri, x, ws, p, h, model, scan, _a_dev = ctx.keep
+        R_ri, freqs, psi0_ri, x, ws, p, h, model, scan, _a_dev, K = ctx.keep
         lib = _lib.load()
         dev = x.device
         B, T = x.shape
@@ -107,8 +115,12 @@ class _PsiLossFn(torch.autograd.Function):
         w = gloss.detach().contiguous().float()
         ng = int(lib.amps_psi_grad_count(D))
         packed = torch.empty(ng, dtype=torch.float32, device=dev)
-        bwd = lib.amps_psi_loss_bwd_scan if scan else lib.amps_psi_loss_bwd
-        rc = bwd(h, C.byref(p), _ptr(x), B, T, _ptr(w), _ptr(ws), ws.numel(), _ptr(packed), _stream(dev))
+        if K > 1:
+            rc = lib.amps_psi_loss_bwd_k(h, C.byref(p), _ptr(x), B, T, K, _ptr(w), _ptr(ws), ws.numel(),
+                                         _ptr(packed), _stream(dev))
+        else:
+            bwd = lib.amps_psi_loss_bwd_scan if scan else lib.amps_psi_loss_bwd
+            rc = bwd(h, C.byref(p), _ptr(x), B, T, _ptr(w), _ptr(ws), ws.numel(), _ptr(packed), _stream(dev))
         _lib.check(h, rc)
         _allreduce_packed(model, packed, h, dev)
         model._last_packed = packed
@@ -384,6 +396,29 @@ class PsiCMPS(CMPS):
     #: instead of the one-chain-per-clip kernels.  Both meet the parity tolerances; "auto" picks the
     #: scan where it measured faster on B200 (profiles/r1_scan_timings.md): few long clips, D <= 64.
     time_parallel = "auto"
+
+    #: checkpoint interval K of the training path (amps_psi_loss_fwd_k / _bwd_k): 1 keeps the whole
+    #: state trajectory for the adjoint sweep (fastest, 12 + 16 D bytes per step and clip), an int K > 1
+    #: keeps one state per K steps and recomputes window by window in the backward, "auto" keeps the
+    #: trajectory while it fits in ``checkpoint_auto_fraction`` of the free device memory and switches
+    #: to K = 2048 beyond that (the reference's own O(T) activation stack: model.py:265-266).
+    checkpoint_every = "auto"
+    checkpoint_auto_fraction = 0.5
+
+    def _checkpoint_interval(self, D: int, B: int, T: int) -> int:
+        K = self.checkpoint_every
+        if K is None:
+            return 1
+        if K == "auto":
+            full = _lib.load().amps_psi_workspace_bytes(D, B, T, 1)
+            free, _total = torch.cuda.mem_get_info(self.device)
+            # memory the caching allocator holds but has not handed out is reusable too
+            free += torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+            return 1 if full <= self.checkpoint_auto_fraction * free else 2048
+        K = int(K)
+        if K < 1:
+            raise ValueError(f"checkpoint_every must be >= 1, 'auto' or None (got {K})")
+        return K
 
     def _use_scan(self, B: int, T: int, need_grad: bool) -> bool:
         if self.time_parallel == "always":

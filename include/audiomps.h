@@ -119,6 +119,28 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
                       void* stream);
 size_t amps_psi_grad_count(int D); /* = 2*D*D + 3*D + 2 */
 
+/* Checkpointed loss / gradient: the state is kept every K steps only (BASELINE north_star: "adjoint backward
+ * that recomputes from state checkpoints every K steps"; the reference's own memory wall is the O(T)
+ * activation stack of tf.foldl's reverse loop, model.py:265-266, train.py:91 "Unrolling in time?").
+ *   K == 1 : identical to amps_psi_loss_fwd(save_for_bwd = 1) / amps_psi_loss_bwd -- the whole trajectory
+ *            (12 + 16*DP bytes per step and clip) stays in the workspace; fastest when it fits.
+ *   K  > 1 : the forward stores ONE state (8*DP bytes) per K steps; the backward walks the windows from the
+ *            last to the first, re-running the forward kernel over window j-1 (on a second stream owned by
+ *            the context) while the adjoint kernel sweeps window j.  Workspace: checkpoints + two
+ *            window-sized trajectory buffers.  K is rounded up to a whole number of rescale chunks
+ *            (amps_psi_ckpt_interval: 32 steps, 16 above D = 64).  Every window costs two kernel launches,
+ *            so K of a few thousand steps is the useful range (K = 2048: 34 MB instead of 2.1 GB per 64
+ *            clips at D = 32).
+ * Same results as K == 1 (the replay is the same kernel from the same state: bit-identical trajectory);
+ * loss_dev, w_dev, grad_dev as above.  The backward must follow the forward on the same (params, x,
+ * workspace, K). */
+int amps_psi_ckpt_interval(int D, int K);
+size_t amps_psi_workspace_bytes_k(int D, int B, int T, int K);
+int amps_psi_loss_fwd_k(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T, int K,
+                        float* loss_dev, void* ws_dev, size_t ws_bytes, void* stream);
+int amps_psi_loss_bwd_k(amps_ctx* ctx, const amps_params* p, const float* x_dev, int B, int T, int K,
+                        const float* w_dev, void* ws_dev, size_t ws_bytes, float* grad_dev, void* stream);
+
 /* Parallel-in-time loss (and gradient) for SMALL batches (same results as amps_psi_loss_fwd / _bwd;
  * D <= 64, zero padded to 64): the clip is cut into ~#SMs/B time chunks whose step operators are
  * composed on the tcgen05 tensor cores (complex DxD as real 2Dx2D, kind::tf32 with a 3-pass hi/lo

@@ -188,7 +188,10 @@ def test_psi_random_shapes(cuda, lib):
         o = PsiCMPSOracle(ohp, raw, mode="f64")
         ref = o.loss_per_clip(data)
         got = model.loss_per_clip(data)
-        assert rel_clip(got.detach().cpu().numpy(), ref.detach().numpy()) <= LOSS_TOL, (D, B, T)
+        # floor 5 % of the largest clip: on these 2..130-sample clips a loss is a sum of a few dozen terms
+        # of either sign that can cancel to ~1 % of one term (D=2, T=32: 2.8e-5 against terms of 1e-4),
+        # where 1e-4 "relative" would ask for 3e-9 absolute -- below float32 rounding of the terms
+        assert rel_clip(got.detach().cpu().numpy(), ref.detach().numpy(), floor=0.05) <= LOSS_TOL, (D, B, T)
         gref = grads_of(o, ref.mean())
         names = ["A", "Rx", "Ry", "freqs_raw", "psi_x", "psi_y"]
         gs = torch.autograd.grad(got.mean(), [getattr(model, k) for k in names])
