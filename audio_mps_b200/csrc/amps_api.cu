@@ -18,6 +18,7 @@
 #include "amps_rho.cuh"
 #include "amps_psi_c4.cuh"
 #include "amps_scan_tc.cuh"
+#include "amps_tiles_tc.cuh"
 
 using namespace amps;
 
@@ -33,8 +34,8 @@ struct amps_ctx {
   cudaStream_t hstream = nullptr;
   // optional per-kernel timing (CUDA events on the launch stream)
   bool prof = false;
-  cudaEvent_t ev[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
-  bool ev_valid[3] = {false, false, false};
+  cudaEvent_t ev[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  bool ev_valid[4] = {false, false, false, false};
   // data-parallel communicator (NCCL, resolved at run time; see amps_comm_init)
   void* nccl_comm = nullptr;
   int comm_rank = 0, comm_size = 1;
@@ -42,6 +43,7 @@ struct amps_ctx {
   // second stream, next to the adjoint sweep of window j on the caller's stream
   cudaStream_t aux_stream = nullptr;
   bool ckpt_overlap = true;   // AMPS_CKPT_SERIAL=1: replay on the caller's stream (measurement aid)
+  bool tc_tiles = true;       // AMPS_NO_TC_TILES=1: D = 33..64 gradient tiles inside the sequential kernel (FFMA)
   cudaEvent_t ev_fork = nullptr, ev_replay[2] = {nullptr, nullptr}, ev_bwd[2] = {nullptr, nullptr};
 };
 
@@ -186,6 +188,20 @@ int dispatch_dp(int DP, F&& f) {
   }
 }
 
+// time splits of the tensor-core tile kernel (amps_tiles_tc.cuh): enough CTAs for two waves, at least
+// 1024 steps each; a function of the shape only (the workspace size must not depend on the context)
+int tiles_nsplit(int DP, int B, int nsteps) {
+  if (DP < 64 || B <= 0) return 1;
+  int n = (2 * 148 + B - 1) / B;
+  const int cap = nsteps / 1024;
+  if (n > cap) n = cap;
+  return n < 1 ? 1 : n;
+}
+int tiles_steps_per_split(int nsteps, int nsplit) {
+  const int s = (nsteps + nsplit - 1) / nsplit;
+  return ((s + TL_KS - 1) / TL_KS) * TL_KS;
+}
+
 struct PsiWs {
   size_t matN, matR, matRH, matS, psi0p, ttab, qtab, lossd;
   size_t traj, scales, G, gf, lam0, gAdir, Gtot, gftot, lam0tot, sptraj, ev;
@@ -215,7 +231,7 @@ PsiWs psi_ws_layout(int DP, int B, int nsteps_tab, int T, bool save) {
     const int nchunks = nsteps > 0 ? (nsteps + chl - 1) / chl : 0;
     w.traj = take((size_t)B * T * DP * sizeof(float2));
     w.scales = take((size_t)B * (nchunks > 0 ? nchunks : 1) * sizeof(float));
-    w.G = take((size_t)B * 3 * mat);
+    w.G = take((size_t)B * tiles_nsplit(DP, B, nsteps) * 3 * mat);
     w.gf = take((size_t)B * DP * sizeof(float));
     w.lam0 = take((size_t)B * DP * sizeof(float2));
     w.gAdir = take((size_t)B * sizeof(double));
@@ -325,6 +341,8 @@ int amps_create(int device, amps_ctx** out) {
   ctx->use_clusters = !(nc && nc[0] == '1');
   const char* cs = getenv("AMPS_CKPT_SERIAL");
   ctx->ckpt_overlap = !(cs && cs[0] == '1');
+  const char* nt = getenv("AMPS_NO_TC_TILES");
+  ctx->tc_tiles = !(nt && nt[0] == '1');
   // everything the device entry points need besides the caller's buffers is created HERE: kernel
   // attributes, the replay stream and its events (no allocation, no attribute call per launch)
   bool ok = amps_set_all_func_attrs() == cudaSuccess &&
@@ -353,7 +371,7 @@ int amps_destroy(amps_ctx* ctx) {
     if (ctx->ev_replay[i]) cudaEventDestroy(ctx->ev_replay[i]);
     if (ctx->ev_bwd[i]) cudaEventDestroy(ctx->ev_bwd[i]);
   }
-  for (int i = 0; i < 3; ++i)
+  for (int i = 0; i < 4; ++i)
     for (int j = 0; j < 2; ++j)
       if (ctx->ev[i][j]) cudaEventDestroy(ctx->ev[i][j]);
   delete ctx;
@@ -363,7 +381,7 @@ int amps_destroy(amps_ctx* ctx) {
 int amps_set_profiling(amps_ctx* ctx, int enable) {
   if (!ctx) return AMPS_E_INVALID;
   if (enable && !ctx->ev[0][0]) {
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < 4; ++i)
       for (int j = 0; j < 2; ++j) CUDA_TRY(ctx, cudaEventCreate(&ctx->ev[i][j]));
   }
   ctx->prof = enable != 0;
@@ -371,7 +389,7 @@ int amps_set_profiling(amps_ctx* ctx, int enable) {
 }
 
 int amps_get_kernel_ms(amps_ctx* ctx, int which, float* ms) {
-  if (!ctx || !ms || which < 0 || which > 2) return AMPS_E_INVALID;
+  if (!ctx || !ms || which < 0 || which > 3) return AMPS_E_INVALID;
   if (!ctx->ev_valid[which]) return fail(ctx, AMPS_E_STATE, "no timed launch of kernel %d yet", which);
   CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev[which][1]));
   CUDA_TRY(ctx, cudaEventElapsedTime(ms, ctx->ev[which][0], ctx->ev[which][1]));
@@ -463,6 +481,8 @@ struct BwdArgs {
   const float2* sptraj;
   const float2* ev;
   SegBwd seg;
+  int tiles_nsplit = 1;        // partial tile sets per clip in G (D = 33..64 tensor-core tile kernel)
+  int tiles_sps = 0;           // steps per split (multiple of 32)
 };
 
 // which kernel family serves (DP, B) on this context
@@ -502,6 +522,13 @@ cudaError_t amps_set_all_func_attrs() {
   if ((e = set_smem(psi_fwd_uni_kernel<64, 8>, sizeof(FwdSmemUni<64, 8>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_fwd_uni_kernel<64, 8, true>, sizeof(FwdSmemUni<64, 8>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_bwd_uni_kernel<64, 8>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_bwd_uni_kernel<64, 8, false, false>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_tiles_tc_kernel<64, 0>, sizeof(TilesSmem<64, 0>) + 1024)) != cudaSuccess) return e;
+  if ((e = set_smem(psi_tiles_tc_kernel<64, 1>, sizeof(TilesSmem<64, 1>) + 1024)) != cudaSuccess) return e;
+  if ((e = set_smem(psi_tiles_tc_kernel<128, 1>, sizeof(TilesSmem<128, 1>) + 1024)) != cudaSuccess) return e;
+  if ((e = set_smem(psi_tiles_tc_kernel<128, 2>, sizeof(TilesSmem<128, 2>) + 1024)) != cudaSuccess) return e;
+  if ((e = set_smem(psi_tiles_tc_kernel<128, 3>, sizeof(TilesSmem<128, 3>) + 1024)) != cudaSuccess) return e;
+  if ((e = set_smem(psi_bwd_c4_kernel<128, C4_CL, false, false>, sizeof(BwdC4Smem<128, C4_CL>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_bwd_uni_kernel<64, 8, true, false>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_bwd_uni_kernel<64, 8, true, true>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_sample_kernel<64, 8>, sizeof(SampleSmem<64>))) != cudaSuccess) return e;
@@ -560,10 +587,51 @@ int launch_psi_bwd(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t 
   const int chl = chunk_len_of(DP);
   const int nchunks = (nsteps + chl - 1) / chl;
   const Fam fam = family_of(ctx, DP, B);
+  // the gradient tiles as GEMMs over the time axis on the tensor cores (after a chain-only adjoint sweep that
+  // left mu_k in place of the consumed S x'_k)
+  auto tiles_args = [&]() {
+    TilesArgs g{};
+    g.mu = a.sptraj;
+    g.traj = a.traj;
+    g.qtab = a.qtab;
+    g.scales = a.scales;
+    g.ev = a.ev;
+    g.x = a.x;
+    g.w = a.w;
+    g.G = a.G;
+    g.T = a.T;
+    g.xstride = a.seg.xstride;
+    g.nchunks = nchunks;
+    g.chunk_len = chl;
+    g.nsplit = a.tiles_nsplit;
+    g.steps_per_split = a.tiles_sps;
+    g.accumulate = a.seg.accumulate;
+    g.A = a.A;
+    return g;
+  };
+  if (fam == Fam::C4 && ctx->tc_tiles) {
+    CUDA_TRY(ctx, launch_cluster(psi_bwd_c4_kernel<128, C4_CL, false, false>, B, C4_CL, 512, sizeof(BwdC4Smem<128, C4_CL>), st,
+                                 a.matN, a.matRH, a.matS, a.qtab, a.ttab, a.x, a.T, a.A, a.w, a.traj, a.scales, nchunks,
+                                 a.G, a.gf, a.lam0, a.gAdir, (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg,
+                                 const_cast<float2*>(a.sptraj)));
+    LAUNCH_CHECK(ctx, "psi_bwd_c4_kernel<chain>");
+    const TilesArgs g = tiles_args();
+    const dim3 grid(B * g.nsplit, 2);
+    PROF_BEGIN(ctx, 3, st);
+    psi_tiles_tc_kernel<128, 2><<<grid, TL_THREADS, sizeof(TilesSmem<128, 2>) + 1024, st>>>(g);
+    LAUNCH_CHECK(ctx, "psi_tiles_tc_kernel<128,2>");
+    psi_tiles_tc_kernel<128, 3><<<grid, TL_THREADS, sizeof(TilesSmem<128, 3>) + 1024, st>>>(g);
+    LAUNCH_CHECK(ctx, "psi_tiles_tc_kernel<128,3>");
+    psi_tiles_tc_kernel<128, 1><<<grid, TL_THREADS, sizeof(TilesSmem<128, 1>) + 1024, st>>>(g);
+    PROF_END(ctx, 3, st);
+    LAUNCH_CHECK(ctx, "psi_tiles_tc_kernel<128,1>");
+    return AMPS_OK;
+  }
   if (fam == Fam::C4) {
     CUDA_TRY(ctx, launch_cluster(psi_bwd_c4_kernel<128, C4_CL, false>, B, C4_CL, 512, sizeof(BwdC4Smem<128, C4_CL>), st,
                                  a.matN, a.matRH, a.matS, a.qtab, a.ttab, a.x, a.T, a.A, a.w, a.traj, a.scales, nchunks,
-                                 a.G, a.gf, a.lam0, a.gAdir, (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg));
+                                 a.G, a.gf, a.lam0, a.gAdir, (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg,
+                                 (float2*)nullptr));
     LAUNCH_CHECK(ctx, "psi_bwd_c4_kernel");
     return AMPS_OK;
   }
@@ -580,6 +648,21 @@ int launch_psi_bwd(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t 
       psi_bwd_kernel<DPc, NQc><<<B, 2 * DPc * NQc, sizeof(BwdSmem<DPc, NQc>), st>>>(
           a.matN, a.matRH, a.matS, a.qtab, a.ttab, a.x, a.T, a.A, a.w, a.traj, a.scales, nchunks, a.G, a.gf,
           a.lam0, a.gAdir, a.sptraj, a.ev, a.seg);
+    } else if (ctx->tc_tiles) {
+      // chain-only adjoint sweep (mu_k replaces the consumed S x'_k in place), then the gradient tiles as
+      // GEMMs over the time axis on the tensor cores
+      psi_bwd_uni_kernel<DPc, NQc, false, false><<<B, DPc * NQc, sizeof(BwdSmemUni<DPc>), st>>>(
+          a.matN, a.matRH, a.matS, a.qtab, a.ttab, a.x, a.T, a.A, a.w, a.traj, a.scales, nchunks, a.G, a.gf,
+          a.lam0, a.gAdir, (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg, const_cast<float2*>(a.sptraj));
+      LAUNCH_CHECK(ctx, "psi_bwd_uni_kernel<chain>");
+      const TilesArgs g = tiles_args();
+      PROF_BEGIN(ctx, 3, st);
+      psi_tiles_tc_kernel<DPc, 0><<<B * g.nsplit, TL_THREADS, sizeof(TilesSmem<DPc, 0>) + 1024, st>>>(g);
+      LAUNCH_CHECK(ctx, "psi_tiles_tc_kernel<0>");
+      psi_tiles_tc_kernel<DPc, 1><<<B * g.nsplit, TL_THREADS, sizeof(TilesSmem<DPc, 1>) + 1024, st>>>(g);
+      PROF_END(ctx, 3, st);
+      LAUNCH_CHECK(ctx, "psi_tiles_tc_kernel<1>");
+      return AMPS_OK;
     } else {
       psi_bwd_uni_kernel<DPc, NQc><<<B, DPc * NQc, sizeof(BwdSmemUni<DPc>), st>>>(
           a.matN, a.matRH, a.matS, a.qtab, a.ttab, a.x, a.T, a.A, a.w, a.traj, a.scales, nchunks, a.G, a.gf,
@@ -592,12 +675,12 @@ int launch_psi_bwd(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t 
 
 // clip reduction + finalize: packed effective-parameter gradient
 int psi_finalize(amps_ctx* ctx, const amps_params* p, int DP, int B, char* ws, const PsiWs& L, const float* w_dev,
-                 float* grad_dev, cudaStream_t st) {
+                 float* grad_dev, cudaStream_t st, int g_parts = 0) {
   const double cprime = -p->delta_t * (double)p->sigma * (double)p->sigma / 2.0;
   const int total = 3 * DP * DP + 2 * DP;
   psi_reduce_clips_kernel<<<(total + 127) / 128, 128, 0, st>>>(
       (const float2*)(ws + L.G), (const float*)(ws + L.gf), (const float2*)(ws + L.lam0), B, DP,
-      (float2*)(ws + L.Gtot), (float*)(ws + L.gftot), (float2*)(ws + L.lam0tot));
+      (float2*)(ws + L.Gtot), (float*)(ws + L.gftot), (float2*)(ws + L.lam0tot), 1, g_parts);
   LAUNCH_CHECK(ctx, "psi_reduce_clips_kernel");
   psi_grad_finalize_kernel<<<p->D, 128, 0, st>>>(
       (const float2*)(ws + L.Gtot), (const float*)(ws + L.gftot), (const float2*)(ws + L.lam0tot),
@@ -672,11 +755,14 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
             (const float2*)(ws + L.traj), (const float*)(ws + L.scales), (float2*)(ws + L.G), (float*)(ws + L.gf),
             (float2*)(ws + L.lam0), (double*)(ws + L.gAdir), (const float2*)(ws + L.sptraj),
             (const float2*)(ws + L.ev), seg_full_b(T)};
+  a.tiles_nsplit = tiles_nsplit(DP, B, T - 1);
+  a.tiles_sps = tiles_steps_per_split(T - 1, a.tiles_nsplit);
+  const bool tc = DP >= 64 && ctx->tc_tiles;
   PROF_BEGIN(ctx, 1, st);
   rc = launch_psi_bwd(ctx, DP, B, a, st);
   PROF_END(ctx, 1, st);
   if (rc) return rc;
-  return psi_finalize(ctx, p, DP, B, ws, L, w_dev, grad_dev, st);
+  return psi_finalize(ctx, p, DP, B, ws, L, w_dev, grad_dev, st, tc ? B * a.tiles_nsplit : 0);
 }
 
 }  // extern "C"
@@ -727,7 +813,7 @@ CkWs ck_ws_layout(int DP, int B, int T, int K) {
     w.ev[i] = take((size_t)B * Wt * sizeof(float2));
     w.scales[i] = take((size_t)B * wch * sizeof(float));
   }
-  w.base.G = take((size_t)B * 3 * mat);
+  w.base.G = take((size_t)B * tiles_nsplit(DP, B, w.W) * 3 * mat);
   w.base.gf = take((size_t)B * DP * sizeof(float));
   w.base.lam0 = take((size_t)B * DP * sizeof(float2));
   w.base.gAdir = take((size_t)B * sizeof(double));
@@ -805,13 +891,15 @@ int amps_psi_loss_bwd_k(amps_ctx* ctx, const amps_params* p, const float* x_dev,
   const int nsteps = T - 1;
   if (nsteps == 0) {   // nothing to sweep: Lam_0 = 0, all sums zero
     const size_t mat = (size_t)DP * DP * sizeof(float2);
-    CUDA_TRY(ctx, cudaMemsetAsync(ws + L.base.G, 0, (size_t)B * 3 * mat, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ws + L.base.G, 0, (size_t)B * tiles_nsplit(DP, B, L.W) * 3 * mat, st));
     CUDA_TRY(ctx, cudaMemsetAsync(ws + L.base.gf, 0, (size_t)B * DP * sizeof(float), st));
     CUDA_TRY(ctx, cudaMemsetAsync(ws + L.base.lam0, 0, (size_t)B * DP * sizeof(float2), st));
     CUDA_TRY(ctx, cudaMemsetAsync(ws + L.base.gAdir, 0, (size_t)B * sizeof(double), st));
     return psi_finalize(ctx, p, DP, B, ws, L.base, w_dev, grad_dev, st);
   }
   cudaStream_t s2 = ctx->ckpt_overlap ? ctx->aux_stream : st;
+  const int ck_nsplit = tiles_nsplit(DP, B, L.W), ck_sps = tiles_steps_per_split(L.W, ck_nsplit);
+  const bool tc = DP >= 64 && ctx->tc_tiles;
   const float2* qtab = (const float2*)(ws + L.base.qtab);
   const float* ttab = (const float*)(ws + L.base.ttab);
   auto wlen = [&](int j) { return (nsteps - j * L.W < L.W) ? nsteps - j * L.W : L.W; };
@@ -833,6 +921,8 @@ int amps_psi_loss_bwd_k(amps_ctx* ctx, const amps_params* p, const float* x_dev,
               (const float2*)(ws + L.traj[i]), (const float*)(ws + L.scales[i]), (float2*)(ws + L.base.G),
               (float*)(ws + L.base.gf), (float2*)(ws + L.base.lam0), (double*)(ws + L.base.gAdir),
               (const float2*)(ws + L.sptraj[i]), (const float2*)(ws + L.ev[i]), seg};
+    a.tiles_nsplit = ck_nsplit;     // fixed by the window length W: every window fills the same partial slots
+    a.tiles_sps = ck_sps;
     return launch_psi_bwd(ctx, DP, B, a, st);
   };
   PROF_BEGIN(ctx, 1, st);
@@ -852,7 +942,7 @@ int amps_psi_loss_bwd_k(amps_ctx* ctx, const amps_params* p, const float* x_dev,
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_bwd[j & 1], st));
   }
   PROF_END(ctx, 1, st);
-  return psi_finalize(ctx, p, DP, B, ws, L.base, w_dev, grad_dev, st);
+  return psi_finalize(ctx, p, DP, B, ws, L.base, w_dev, grad_dev, st, tc ? B * ck_nsplit : 0);
 }
 
 }  // extern "C"
@@ -1009,7 +1099,8 @@ int amps_psi_loss_bwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
                                    (const float2*)(ws + L.traj), (const float*)(ws + L.scales), 0,
                                    (float2*)(ws + L.G), (float*)(ws + L.gf), (float2*)(ws + L.lam0),
                                    (double*)(ws + L.gAdir), lam_end, L.nvc, L.m_steps,
-                                   (const float2*)(ws + L.sptraj), (const float2*)(ws + L.ev), seg_full_b(T));
+                                   (const float2*)(ws + L.sptraj), (const float2*)(ws + L.ev), seg_full_b(T),
+                                   (float2*)nullptr);   // (function pointers carry no default argument)
   };
   PROF_BEGIN(ctx, 1, st);
   adjoint_pass(nullptr);                                   // d_j: chunk adjoints with a zero end condition

@@ -218,13 +218,15 @@ __global__ void __launch_bounds__(256)
 __global__ void psi_reduce_clips_kernel(const float2* __restrict__ G, const float* __restrict__ gf,
                                         const float2* __restrict__ lam0, int B, int DP,
                                         float2* __restrict__ Gtot, float* __restrict__ gftot,
-                                        float2* __restrict__ lam0tot, int lam_step = 1) {
+                                        float2* __restrict__ lam0tot, int lam_step = 1, int g_parts = 0) {
+  // g_parts: number of partial tile sets in G when it differs from B (tensor-core tile kernel: B * nsplit)
   const int nG = 3 * DP * DP;
   const int total = nG + 2 * DP;
+  const int nparts = g_parts > 0 ? g_parts : B;
   for (int e = threadIdx.x + blockIdx.x * blockDim.x; e < total; e += blockDim.x * gridDim.x) {
     if (e < nG) {
       double sx = 0.0, sy = 0.0;
-      for (int b = 0; b < B; ++b) {
+      for (int b = 0; b < nparts; ++b) {
         const float2 v = G[(size_t)b * nG + e];
         sx += v.x;
         sy += v.y;

@@ -875,7 +875,10 @@ __global__ void __launch_bounds__(DP* NQ)
                    float* __restrict__ gfout, float2* __restrict__ lam0out,
                    double* __restrict__ gAdir, const float2* __restrict__ lam_end, int nvc,
                    int m_steps, const float2* __restrict__ sptraj, const float2* __restrict__ evin,
-                   SegBwd seg) {
+                   SegBwd seg, float2* __restrict__ mu_out = nullptr) {
+  // mu_out (chain-only instantiation): the adjoint mu_k of x'_k goes to row k of mu_out[b] for the
+  // tensor-core tile kernel (amps_tiles_tc.cuh).  It may alias sptraj: a chunk's S x' rows have been read
+  // into shared memory (cp.async, two chunks ahead) before its mu rows are written.
   const float A = a_get(A_);
   using M = Map<DP, NQ>;
   constexpr int NT = M::NT;
@@ -972,15 +975,17 @@ __global__ void __launch_bounds__(DP* NQ)
       sm.betas[ds][t] = -alpha * E;
       gAacc += (double)wb * (double)E * (double)inc / ((double)A * (double)A * (double)arg);
     }
-    const float inv_sc = 1.0f / sm.scs[lb][0];
-    for (int idx = t; idx < len * DP; idx += NT) {
-      const int kk = idx / DP, r = idx % DP;
-      float2 xp = cmul_ca(sm.qs[lb][kk][r], sm.xs[lb][kk + 1][r]);
-      if (kk == len - 1) {
-        xp.x *= inv_sc;
-        xp.y *= inv_sc;
+    if (TILES) {   // x'_k only feeds the G_E tile
+      const float inv_sc = 1.0f / sm.scs[lb][0];
+      for (int idx = t; idx < len * DP; idx += NT) {
+        const int kk = idx / DP, r = idx % DP;
+        float2 xp = cmul_ca(sm.qs[lb][kk][r], sm.xs[lb][kk + 1][r]);
+        if (kk == len - 1) {
+          xp.x *= inv_sc;
+          xp.y *= inv_sc;
+        }
+        sm.xps[ds][kk][r] = xp;
       }
-      sm.xps[ds][kk][r] = xp;
     }
   };
 
@@ -1102,6 +1107,11 @@ __global__ void __launch_bounds__(DP* NQ)
     };
 
     for (int kk = len - 1; kk >= 0; --kk) step(kk);
+    if (!TILES) if (mu_out) {   // flush the chunk's mu ring (complete after the last step's barrier)
+      const float4* src = reinterpret_cast<const float4*>(&sm.mus[0][0]);
+      float4* dst = reinterpret_cast<float4*>(mu_out + ((size_t)b * rows + (size_t)c * CH) * DP);
+      for (int idx = t; idx < len * DP / 2; idx += NT) dst[idx] = src[idx];
+    }
   }
   cp_async_wait<0>();
 

@@ -341,7 +341,10 @@ struct alignas(16) BwdC4Smem {
 };
 
 // Adjoint backward, same recursion and outputs as psi_bwd_uni_kernel; rows split over the cluster.
-template <int DP, int CL, bool VIRT>
+// TILES = false: chain only -- mu_k goes to row k of mu_out[b] (own rows of every CTA; may alias sptraj, whose
+// rows of a chunk are in shared memory two chunks before its mu rows are written) and the gradient tiles are
+// contracted afterwards on the tensor cores (amps_tiles_tc.cuh).
+template <int DP, int CL, bool VIRT, bool TILES = true>
 __global__ void __launch_bounds__(512)
     psi_bwd_c4_kernel(const float2* __restrict__ matN, const float2* __restrict__ matRH,
                       const float2* __restrict__ matS, const float2* __restrict__ qtab_,
@@ -351,7 +354,7 @@ __global__ void __launch_bounds__(512)
                       float* __restrict__ gfout, float2* __restrict__ lam0out,
                       double* __restrict__ gAdir, const float2* __restrict__ lam_end, int nvc,
                       int m_steps, const float2* __restrict__ sptraj, const float2* __restrict__ evin,
-                      SegBwd seg) {
+                      SegBwd seg, float2* __restrict__ mu_out = nullptr) {
   const float A = a_get(A_);
   using Cf = C4<DP, CL>;
   constexpr int NQ = Cf::NQ, CPT = Cf::CPT, NP = Cf::NP, RP = Cf::RP, NTL = Cf::NTL;
@@ -398,9 +401,9 @@ __global__ void __launch_bounds__(512)
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
       const int col = Map<DP, NQ>::col(c, jq);
-      GR[c] = accum ? Gb[0 * DP * DP + i * DP + col] : make_float2(0.f, 0.f);
-      GN[c] = accum ? Gb[1 * DP * DP + i * DP + col] : make_float2(0.f, 0.f);
-      GE[c] = accum ? Gb[2 * DP * DP + i * DP + col] : make_float2(0.f, 0.f);
+      GR[c] = (TILES && accum) ? Gb[0 * DP * DP + i * DP + col] : make_float2(0.f, 0.f);
+      GN[c] = (TILES && accum) ? Gb[1 * DP * DP + i * DP + col] : make_float2(0.f, 0.f);
+      GE[c] = (TILES && accum) ? Gb[2 * DP * DP + i * DP + col] : make_float2(0.f, 0.f);
     }
   }
 
@@ -448,15 +451,17 @@ __global__ void __launch_bounds__(512)
       sm.betas[ds][t] = -alpha * E;
       gAacc += (double)wb * (double)E * (double)inc / ((double)A * (double)A * (double)arg);
     }
-    const float inv_sc = 1.0f / sm.scs[lb][0];
-    for (int idx = t; idx < len * DP; idx += NTL) {
-      const int kk = idx / DP, r = idx % DP;
-      float2 xp = cmul_ca(sm.qs[lb][kk][r], sm.xs[lb][kk + 1][r]);
-      if (kk == len - 1) {
-        xp.x *= inv_sc;
-        xp.y *= inv_sc;
+    if (TILES) {   // x'_k only feeds the G_E tile
+      const float inv_sc = 1.0f / sm.scs[lb][0];
+      for (int idx = t; idx < len * DP; idx += NTL) {
+        const int kk = idx / DP, r = idx % DP;
+        float2 xp = cmul_ca(sm.qs[lb][kk][r], sm.xs[lb][kk + 1][r]);
+        if (kk == len - 1) {
+          xp.x *= inv_sc;
+          xp.y *= inv_sc;
+        }
+        sm.xps[ds][kk][r] = xp;
       }
-      sm.xps[ds][kk][r] = xp;
     }
   };
   float2 lam = make_float2(0.f, 0.f);  // adjoint of x_{k+1,i}, replicated over the NQ lanes
@@ -549,7 +554,7 @@ __global__ void __launch_bounds__(512)
       float ox = __shfl_xor_sync(0xffffffffu, lp.x, 1);
       float oy = __shfl_xor_sync(0xffffffffu, lp.y, 1);
       // ---- filler 1: rank-1 tiles of step kk (rows of this CTA) -------------------------
-      {
+      if (TILES) {
         const float2 xpi = sm.xps[ds][kk][i];
         const float al = sm.alphas[ds][kk];
         const float2 u1 = make_float2(s * mu.x, s * mu.y);
@@ -593,17 +598,28 @@ __global__ void __launch_bounds__(512)
     };
 
     for (int kk = len - 1; kk >= 0; --kk) step(kk);
+    if (!TILES) if (mu_out) {
+      // flush this CTA's rows of the chunk's mu ring (all of them have arrived: every step waited for its
+      // broadcast; a peer that is already one broadcast ahead only touches ITS rows of the ring)
+      float2* dst = mu_out + ((size_t)b * rows + (size_t)c * CH4) * DP + (int)rank * RP;
+      for (int idx = t; idx < len * RP; idx += NTL) {
+        const int kk = idx / RP, r = idx % RP;
+        dst[(size_t)kk * DP + r] = sm.mus[kk][(int)rank * RP + r];
+      }
+    }
   }
   cp_async_wait<0>();
 
   // ---- per-clip outputs (rows of this CTA) ---------------------------------------------------
-  float2* Gb = Gout + (size_t)b * 3 * DP * DP;
+  if (TILES) {
+    float2* Gb = Gout + (size_t)b * 3 * DP * DP;
 #pragma unroll
-  for (int c = 0; c < CPT; ++c) {
-    const int col = Map<DP, NQ>::col(c, jq);
-    Gb[0 * DP * DP + i * DP + col] = GR[c];
-    Gb[1 * DP * DP + i * DP + col] = GN[c];
-    Gb[2 * DP * DP + i * DP + col] = GE[c];
+    for (int c = 0; c < CPT; ++c) {
+      const int col = Map<DP, NQ>::col(c, jq);
+      Gb[0 * DP * DP + i * DP + col] = GR[c];
+      Gb[1 * DP * DP + i * DP + col] = GN[c];
+      Gb[2 * DP * DP + i * DP + col] = GE[c];
+    }
   }
   if (jq == 0) {
     gfout[(size_t)b * DP + i] = gf;

@@ -385,8 +385,8 @@ __global__ void __launch_bounds__(AMPS_BWD_CL_MAXT)
 
   if (t == 0) {
     if (rank == 0) {
-      mbar_init(&cs.in_full[0], 1);
-      mbar_init(&cs.in_full[1], 1);
+      mbar_init(&cs.in_full[0], 2);   // one arrival from the prep group (inputs pushed), one from the tiles
+      mbar_init(&cs.in_full[1], 2);   // groups (ring pulled)
     } else {
       mbar_init(&sm.done_bar[0], 1);
       mbar_init(&sm.done_bar[1], 1);
@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(AMPS_BWD_CL_MAXT)
       float4* lm = reinterpret_cast<float4*>(&sm.mul[0][0]);
       for (int idx = t - NTC; idx < len * DP / 2; idx += 2 * NTC) lm[idx] = ld_dsmem_f4(rm + 16 * idx);
     };
-    auto tiles_chunk = [&](int c) {          // tiles group (after the slot's __syncthreads: sm.mul is complete)
+    auto tiles_chunk = [&](int c) {          // tiles group (after the pull's barrier: sm.mul is complete)
       const int len = chunk_len(c);
       const float2(*xsb)[DP] = sm.xs[c & 3];
       const float2(*xpb)[DP] = sm.xps[c % 3];
@@ -625,13 +625,17 @@ __global__ void __launch_bounds__(AMPS_BWD_CL_MAXT)
         cp_async_commit();
         cp_async_wait<1>();
         bar_named(2, NTC);
-        if (c - 1 >= 0) prep_chunk(c - 1);
+        if (c - 1 >= 0) {
+          prep_chunk(c - 1);
+          bar_named(2, NTC);      // every prep thread's pushes are issued
+          if (tr == 0) mbar_arrive_remote(rfull + 8 * ((c - 1) & 1));
+        }
       } else {
         if (have_up) tiles_pull(c + 1);
+        bar_named(3, 2 * NTC);    // ring pulled (sm.mul complete)
+        if (t == NTC && c - 1 >= 0) mbar_arrive_remote(rfull + 8 * ((c - 1) & 1));
+        if (have_up) tiles_chunk(c + 1);
       }
-      __syncthreads();          // inputs of chunk c-1 pushed, ring of chunk c+1 pulled
-      if (t == 0 && c - 1 >= 0) mbar_arrive_remote(rfull + 8 * ((c - 1) & 1));
-      if (grp != 0 && have_up) tiles_chunk(c + 1);
       __syncthreads();          // tiles done with xps / xs / mul before the next slot's prep rewrites them
     }
     cluster_arrive_release();

@@ -12,7 +12,7 @@ from audio_mps_b200 import HParams, PsiCMPS, _lib, damped_sine  # noqa: E402
 dev = torch.device("cuda", 0)
 which = sys.argv[1:] or ["c1"]
 CFG = {"c1": (32, 64, 64000, (1, 512, 1024, 2048, 4096, 8192)), "c4": (64, 256, 64000, (1, 2048, 4096)),
-       "c3": (128, 128, 64000, (1, 2048)), "b2048": (64, 2048, 64000, (2048,)), "c0": (8, 8, 16000, (1, 1024, 2048)),
+       "c3": (128, 128, 64000, (1, 2048)), "c4k1": (64, 256, 64000, (1,)), "c3k1": (128, 128, 64000, (1,)), "b2048": (64, 2048, 64000, (2048,)), "c0": (8, 8, 16000, (1, 1024, 2048)),
        "b16": (32, 16, 64000, (1, 2048)), "b32": (32, 32, 64000, (1, 2048))}
 
 
@@ -53,6 +53,11 @@ for name in which:
         if g1 is None:
             g1 = g
         dg = float((g - g1).abs().max() / g1.abs().max())
-        print(f"{name} D={D} B={B} T={T} K={K}: step {ms:.2f} ms (fwd {_lib.kernel_ms(0,0):.2f}, bwd {_lib.kernel_ms(0,1):.2f}) "
+        tiles = ""
+        try:
+            tiles = f", tiles {_lib.kernel_ms(0,3):.2f}"
+        except Exception:
+            pass
+        print(f"{name} D={D} B={B} T={T} K={K}: step {ms:.2f} ms (fwd {_lib.kernel_ms(0,0):.2f}, bwd {_lib.kernel_ms(0,1):.2f}{tiles}) "
               f"-> {B*T/ms*1e3:.3e} samples/s; workspace {lib.amps_psi_workspace_bytes_k(D,B,T,K)/1e6:.1f} MB; "
               f"dRx vs first K {dg:.1e}", flush=True)
