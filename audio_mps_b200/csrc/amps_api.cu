@@ -618,11 +618,11 @@ int launch_psi_bwd(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t 
     const TilesArgs g = tiles_args();
     const dim3 grid(B * g.nsplit, 2);
     PROF_BEGIN(ctx, 3, st);
-    psi_tiles_tc_kernel<128, 2><<<grid, TL_THREADS, sizeof(TilesSmem<128, 2>) + 1024, st>>>(g);
+    psi_tiles_tc_kernel<128, 2><<<grid, TL_BLOCK, sizeof(TilesSmem<128, 2>) + 1024, st>>>(g);
     LAUNCH_CHECK(ctx, "psi_tiles_tc_kernel<128,2>");
-    psi_tiles_tc_kernel<128, 3><<<grid, TL_THREADS, sizeof(TilesSmem<128, 3>) + 1024, st>>>(g);
+    psi_tiles_tc_kernel<128, 3><<<grid, TL_BLOCK, sizeof(TilesSmem<128, 3>) + 1024, st>>>(g);
     LAUNCH_CHECK(ctx, "psi_tiles_tc_kernel<128,3>");
-    psi_tiles_tc_kernel<128, 1><<<grid, TL_THREADS, sizeof(TilesSmem<128, 1>) + 1024, st>>>(g);
+    psi_tiles_tc_kernel<128, 1><<<grid, TL_BLOCK, sizeof(TilesSmem<128, 1>) + 1024, st>>>(g);
     PROF_END(ctx, 3, st);
     LAUNCH_CHECK(ctx, "psi_tiles_tc_kernel<128,1>");
     return AMPS_OK;
@@ -657,9 +657,9 @@ int launch_psi_bwd(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t 
       LAUNCH_CHECK(ctx, "psi_bwd_uni_kernel<chain>");
       const TilesArgs g = tiles_args();
       PROF_BEGIN(ctx, 3, st);
-      psi_tiles_tc_kernel<DPc, 0><<<B * g.nsplit, TL_THREADS, sizeof(TilesSmem<DPc, 0>) + 1024, st>>>(g);
+      psi_tiles_tc_kernel<DPc, 0><<<B * g.nsplit, TL_BLOCK, sizeof(TilesSmem<DPc, 0>) + 1024, st>>>(g);
       LAUNCH_CHECK(ctx, "psi_tiles_tc_kernel<0>");
-      psi_tiles_tc_kernel<DPc, 1><<<B * g.nsplit, TL_THREADS, sizeof(TilesSmem<DPc, 1>) + 1024, st>>>(g);
+      psi_tiles_tc_kernel<DPc, 1><<<B * g.nsplit, TL_BLOCK, sizeof(TilesSmem<DPc, 1>) + 1024, st>>>(g);
       PROF_END(ctx, 3, st);
       LAUNCH_CHECK(ctx, "psi_tiles_tc_kernel<1>");
       return AMPS_OK;

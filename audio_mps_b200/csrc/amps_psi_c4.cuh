@@ -450,6 +450,9 @@ __global__ void __launch_bounds__(512)
       sm.alphas[ds][t] = alpha;
       sm.betas[ds][t] = -alpha * E;
       gAacc += (double)wb * (double)E * (double)inc / ((double)A * (double)A * (double)arg);
+      // chain-only sweep: (alpha_k, 1/c_k) replace the consumed (E_k, |x_k|^2) for the tile kernel
+      if (!TILES) if (mu_out && rank == 0)
+        const_cast<float2*>(evb)[(size_t)c * CH4 + t] = make_float2(alpha, t == len - 1 ? 1.0f / sm.scs[lb][0] : 1.0f);
     }
     if (TILES) {   // x'_k only feeds the G_E tile
       const float inv_sc = 1.0f / sm.scs[lb][0];

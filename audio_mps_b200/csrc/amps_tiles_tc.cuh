@@ -27,7 +27,9 @@ namespace amps {
 
 constexpr int TL_KS = 32;            // steps per stage = floats per 128-byte swizzle row
 constexpr int TL_STAGES = 2;
-constexpr int TL_THREADS = 512;      // warp 0: MMA issue + epilogue with warps 1-3; warps 1..15 (+ lanes of 0) produce
+constexpr int TL_THREADS = 512;      // producer threads (warps 0..15; warps 0..3 also run the epilogue)
+constexpr int TL_BLOCK = TL_THREADS + 32;   // + warp 16: issues the MMAs, nothing else (a tcgen05.mma can hold its
+                                            // thread while the pipe's queue is full: it must not gate the staging)
 constexpr int TL_ROWB = 128;         // bytes per operand row
 
 template <int DP, int TYPE>
@@ -38,8 +40,6 @@ struct alignas(1024) TilesSmem {
   uint8_t a_lo[TL_STAGES][MA * TL_ROWB];
   uint8_t b_hi[TL_STAGES][NB * TL_ROWB];
   uint8_t b_lo[TL_STAGES][NB * TL_ROWB];
-  float sk[TL_STAGES][TL_KS];        // type 0: s_k ; type 1: alpha_k
-  float ck[TL_STAGES][TL_KS];        // type 1: 1 / c_k (1 except at the last step of a rescale chunk)
   unsigned long long full_bar[TL_STAGES];
   unsigned long long empty_bar[TL_STAGES];
   unsigned long long done_bar;
@@ -69,7 +69,7 @@ struct TilesArgs {
   const float2* traj;     // [B][T][DP]  x_k (scaled), row k
   const float2* qtab;     // [nsteps][DP]                                     (type 1)
   const float* scales;    // [B][nchunks] c_k of each rescale chunk           (type 1)
-  const float2* ev;       // [B][T] (E_k, |x_k|^2)                            (type 1)
+  const float2* ev;       // [B][T] (alpha_k, 1/c_k), left by the chain-only adjoint sweep   (type 1)
   const float* x;         // waveform, clip stride xstride
   const float* w;         // [B] clip weights                                  (type 1)
   float2* G;              // [B * nsplit][3][DP][DP] partial tiles: [0] = G_R, [1] = G_N, [2] = G_E
@@ -79,9 +79,9 @@ struct TilesArgs {
   AVal A;
 };
 
-// grid = (B * nsplit, DP / 64), block = 512
+// grid = (B * nsplit, DP / 64), block = 544
 template <int DP, int TYPE>
-__global__ void __launch_bounds__(TL_THREADS, 1) psi_tiles_tc_kernel(TilesArgs g) {
+__global__ void __launch_bounds__(TL_BLOCK, 1) psi_tiles_tc_kernel(TilesArgs g) {
   using Sm = TilesSmem<DP, TYPE>;
   constexpr int MA = Sm::MA, NB = Sm::NB;
   static_assert(NB <= 256 && (DP == 64 || DP == 128), "UMMA N <= 256");
@@ -126,173 +126,174 @@ __global__ void __launch_bounds__(TL_THREADS, 1) psi_tiles_tc_kernel(TilesArgs g
   // left the kernel bound by one exposed HBM latency per block).
   constexpr int NBT = DP * (TL_KS / 4) / TL_THREADS;   // B tasks per thread: (component, group of 4 steps)
   static_assert(NBT * TL_THREADS == DP * (TL_KS / 4) && RA * (TL_KS / 4) == TL_THREADS, "static task map");
-  float2 pb[NBT][4];        // kind 0, 2, 3: x_k ; kind 1: x_{k+1}
-  float2 pq[NBT][4];        // kind 1: q_k
-  float2 pa[4];             // kind 0, 2, 3: mu_k of this CTA's component
-  float p_inc = 0.f, p_sc = 1.f;
-  float2 p_ev = make_float2(0.f, 1.f);
-  auto fetch = [&](int j) {
+  // Task map: a warp covers 16 components x 2 step groups -- lanes 4..7 of every eight take the SAME four
+  // components as lanes 0..3 but the neighbouring step group (kg ^ 1).  The Re rows (2r: rows 0,2,4,6 mod 8)
+  // of a quarter warp then land on eight different 16-byte bank groups of the swizzled tile (chunk kg or
+  // kg ^ 1, xor the row), and so do the Im rows: both operand stores are conflict free without any select.
+  const int l_r = (lane & 3) + 4 * (lane >> 3), l_kg = (lane >> 2) & 1;
+  auto task_of = [&](int wv, int ncomp, int& r, int& kg) {   // wv: warp index over the task set
+    const int per = ncomp / 16;
+    r = 16 * (wv % per) + l_r;
+    kg = 2 * (wv / per) + l_kg;
+  };
+  struct Pre {              // one block's global data, per thread
+    float2 pb[NBT][4];      // kind 0, 2, 3: x_k ; kind 1: x_{k+1}
+    float2 pq[TYPE == 1 ? NBT : 1][4];   // kind 1: q_k
+    float2 pa[4];           // kind 0, 2, 3: mu_k of this CTA's component
+    float xw[TYPE == 1 ? 1 : NBT][5];    // kind 0, 3: waveform samples of the task's four steps (s_k)
+    float2 ev[TYPE == 1 ? NBT : 1][4];   // kind 1: (alpha_k, 1 / c_k)
+  };
+  const float* xb = g.x + (size_t)b * g.xstride;
+  auto fetch = [&](Pre& P, int j) {
     const int k0 = k_begin + j * TL_KS;
     const int len = min(TL_KS, k_begin + nloc - k0);
-    if (tid < TL_KS && tid < len) {
-      const int k = k0 + tid;
-      const float* xb = g.x + (size_t)b * g.xstride;
-      p_inc = xb[k + 1] - xb[k];
-      if (TYPE == 1) {
-        p_ev = g.ev[rowbase + k];
-        const bool last = (k + 1) % g.chunk_len == 0 || k + 1 == nsteps;
-        p_sc = last ? g.scales[(size_t)b * g.nchunks + k / g.chunk_len] : 1.0f;
-      }
-    }
 #pragma unroll
     for (int n = 0; n < NBT; ++n) {
-      const int task = tid + n * TL_THREADS;
-      const int r = task % DP, kg = task / DP;
+      int r, kg;
+      task_of(warp + 16 * n, DP, r, kg);
+      if (TYPE == 0 || TYPE == 3) {
+#pragma unroll
+        for (int e = 0; e < 5; ++e) P.xw[n][e] = (4 * kg + e <= len) ? xb[k0 + 4 * kg + e] : 0.f;
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int kk = 4 * kg + e;
-        pb[n][e] = make_float2(0.f, 0.f);
-        pq[n][e] = make_float2(0.f, 0.f);
+        P.pb[n][e] = make_float2(0.f, 0.f);
+        if (TYPE == 1) {
+          P.pq[n][e] = make_float2(0.f, 0.f);
+          P.ev[n][e] = make_float2(0.f, 0.f);
+        }
         if (kk < len) {
           const int k = k0 + kk;
           if (TYPE != 1) {
-            pb[n][e] = g.traj[(rowbase + k) * DP + r];
+            P.pb[n][e] = g.traj[(rowbase + k) * DP + r];
           } else {
-            pq[n][e] = g.qtab[(size_t)k * DP + r];
-            pb[n][e] = g.traj[(rowbase + k + 1) * DP + r];
+            P.pq[n][e] = g.qtab[(size_t)k * DP + r];
+            P.pb[n][e] = g.traj[(rowbase + k + 1) * DP + r];
+            P.ev[n][e] = g.ev[rowbase + k];
           }
         }
       }
     }
     if (TYPE != 1) {
-      const int rl = tid % RA, kg = tid / RA;
+      int rl, kg;
+      task_of(warp, RA, rl, kg);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int kk = 4 * kg + e;
-        pa[e] = (kk < len) ? g.mu[(rowbase + k0 + kk) * DP + ra0 + rl] : make_float2(0.f, 0.f);
+        P.pa[e] = (kk < len) ? g.mu[(rowbase + k0 + kk) * DP + ra0 + rl] : make_float2(0.f, 0.f);
       }
     }
   };
-  auto stage = [&](int j, int s) {
-    const int k0 = k_begin + j * TL_KS;
-    const int len = min(TL_KS, k_begin + nloc - k0);
-    // per-step scalars
-    if (tid < TL_KS) {
-      float sv = 0.f, cv = 1.f;
-      if (tid < len) {
-        const float s_k = p_inc / A;
-        if (TYPE != 1) {
-          sv = s_k;
-        } else {
-          const float arg = 1.0f + (p_ev.x * p_inc) / A;
-          const float gE = g.w[b] * (-s_k / arg);
-          sv = 2.0f * gE / fmaxf(p_ev.y, 1e-12f);      // alpha_k
-          cv = 1.0f / p_sc;                             // 1 / c_k: the rescale sits on a chunk's last step
-        }
-      }
-      sm.sk[s][tid] = sv;
-      sm.ck[s][tid] = cv;
-    }
-    bar_named(4, TL_THREADS);
-    // (component r, group of 4 steps) -> one 16-byte chunk of rows 2r (Re) and 2r+1 (Im)
-    auto put = [&](uint8_t* hi, uint8_t* lo, int row, const float (&v)[4], int kg) {
-      float4 h, l;
-      h.x = tc_trunc_tf32(v[0]);
-      h.y = tc_trunc_tf32(v[1]);
-      h.z = tc_trunc_tf32(v[2]);
-      h.w = tc_trunc_tf32(v[3]);
-      l = make_float4(v[0] - h.x, v[1] - h.y, v[2] - h.z, v[3] - h.w);
-      const int o = tl_off(row, kg);
-      *reinterpret_cast<float4*>(hi + o) = h;
-      *reinterpret_cast<float4*>(lo + o) = l;
-    };
+  auto put2 = [&](uint8_t* hi, uint8_t* lo, int r, const float (&re)[4], const float (&im)[4], int kg) {
+    const float4 rh = make_float4(tc_trunc_tf32(re[0]), tc_trunc_tf32(re[1]), tc_trunc_tf32(re[2]), tc_trunc_tf32(re[3]));
+    const float4 ih = make_float4(tc_trunc_tf32(im[0]), tc_trunc_tf32(im[1]), tc_trunc_tf32(im[2]), tc_trunc_tf32(im[3]));
+    const int o0 = tl_off(2 * r, kg), o1 = tl_off(2 * r + 1, kg);
+    *reinterpret_cast<float4*>(hi + o0) = rh;
+    *reinterpret_cast<float4*>(lo + o0) = make_float4(re[0] - rh.x, re[1] - rh.y, re[2] - rh.z, re[3] - rh.w);
+    *reinterpret_cast<float4*>(hi + o1) = ih;
+    *reinterpret_cast<float4*>(lo + o1) = make_float4(im[0] - ih.x, im[1] - ih.y, im[2] - ih.z, im[3] - ih.w);
+  };
+  const float rcpA = 1.0f / A;
+  auto stage = [&](const Pre& P, int j, int s) {
     // B operand (all DP components); kind 1 also fills the A rows of this CTA's components from the same x'
 #pragma unroll
     for (int n = 0; n < NBT; ++n) {
-      const int task = tid + n * TL_THREADS;
-      const int r = task % DP, kg = task / DP;
+      int r, kg;
+      task_of(warp + 16 * n, DP, r, kg);
+      float sk[4];          // kind 0, 3: s_k ; kind 1: alpha_k
       float bre[4], bim[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         if (TYPE != 1) {
-          bre[e] = pb[n][e].x;
-          bim[e] = pb[n][e].y;
+          if (TYPE != 2) sk[e] = (P.xw[n][e + 1] - P.xw[n][e]) * rcpA;   // s_k = inc_k / A
+          bre[e] = P.pb[n][e].x;
+          bim[e] = P.pb[n][e].y;
         } else {
-          const float2 xp = cmul_ca(pq[n][e], pb[n][e]);     // x'_k = conj(q_k) x_{k+1} / c_k
-          const float ic = sm.ck[s][4 * kg + e];
-          bre[e] = xp.x * ic;
-          bim[e] = xp.y * ic;
+          sk[e] = P.ev[n][e].x;                                            // alpha_k
+          const float2 xp = cmul_ca(P.pq[n][e], P.pb[n][e]);               // x'_k = conj(q_k) x_{k+1} / c_k
+          bre[e] = xp.x * P.ev[n][e].y;
+          bim[e] = xp.y * P.ev[n][e].y;
         }
       }
       if (TYPE == 0 || TYPE == 3) {   // s_k x_k
         float sre[4], sim[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float s_k = sm.sk[s][4 * kg + e];
-          sre[e] = s_k * bre[e];
-          sim[e] = s_k * bim[e];
+          sre[e] = sk[e] * bre[e];
+          sim[e] = sk[e] * bim[e];
         }
-        const int row0 = TYPE == 0 ? 2 * DP : 0;   // kind 0: stacked under x ; kind 3: the only B rows
-        put(sm.b_hi[s], sm.b_lo[s], row0 + 2 * r, sre, kg);
-        put(sm.b_hi[s], sm.b_lo[s], row0 + 2 * r + 1, sim, kg);
+        // kind 0: stacked under x (rows 2 DP ..) ; kind 3: the only B rows
+        put2(sm.b_hi[s] + (TYPE == 0 ? 2 * DP * TL_ROWB : 0), sm.b_lo[s] + (TYPE == 0 ? 2 * DP * TL_ROWB : 0), r, sre, sim, kg);
       }
-      if (TYPE != 3) {
-        put(sm.b_hi[s], sm.b_lo[s], 2 * r, bre, kg);
-        put(sm.b_hi[s], sm.b_lo[s], 2 * r + 1, bim, kg);
-      }
-      if (TYPE == 1 && r >= ra0 && r < ra0 + RA) {   // A = alpha_k x'_k
+      if (TYPE != 3) put2(sm.b_hi[s], sm.b_lo[s], r, bre, bim, kg);
+      if (TYPE == 1 && r >= ra0 && r < ra0 + RA) {   // A = alpha_k x'_k  (warp-uniform: 16 components per warp)
         float are[4], aim[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float al = sm.sk[s][4 * kg + e];
-          are[e] = al * bre[e];
-          aim[e] = al * bim[e];
+          are[e] = sk[e] * bre[e];
+          aim[e] = sk[e] * bim[e];
         }
-        put(sm.a_hi[s], sm.a_lo[s], 2 * (r - ra0), are, kg);
-        put(sm.a_hi[s], sm.a_lo[s], 2 * (r - ra0) + 1, aim, kg);
+        put2(sm.a_hi[s], sm.a_lo[s], r - ra0, are, aim, kg);
       }
     }
     if (TYPE != 1) {   // A = mu_k, this CTA's 64 components
-      const int rl = tid % RA, kg = tid / RA;
+      int rl, kg;
+      task_of(warp, RA, rl, kg);
       float are[4], aim[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        are[e] = pa[e].x;
-        aim[e] = pa[e].y;
+        are[e] = P.pa[e].x;
+        aim[e] = P.pa[e].y;
       }
-      put(sm.a_hi[s], sm.a_lo[s], 2 * rl, are, kg);
-      put(sm.a_hi[s], sm.a_lo[s], 2 * rl + 1, aim, kg);
+      put2(sm.a_hi[s], sm.a_lo[s], rl, are, aim, kg);
     }
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> visible to the MMA
     tl_mbar_arrive(&sm.full_bar[s]);
   };
 
-  // ---- main loop.  Iteration j: thread 0 first issues the MMAs of block j-1 (they then run on the tensor
-  // pipe while everybody stages block j into the other stage); staging block j only has to wait for the
-  // MMAs of block j-2, issued one iteration earlier.
-  if (nblk > 0) fetch(0);
-  for (int j = 0; j <= nblk; ++j) {
-    if (tid == 0 && j > 0) {
-      const int jm = j - 1, s = jm % TL_STAGES;
-      mbar_wait_cta(&sm.full_bar[s], (jm / TL_STAGES) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  // MMA thread: MMAs of block jm out of stage jm % 2
+  auto issue_mma = [&](int jm) {
+    const int s = jm % TL_STAGES;
+    mbar_wait_cta(&sm.full_bar[s], (jm / TL_STAGES) & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll 1
-      for (int pass = 0; pass < 3; ++pass) {
-        const uint64_t da0 = tc_make_desc(tc_smem_u32(pass == 1 ? sm.a_lo[s] : sm.a_hi[s]));
-        const uint64_t db0 = tc_make_desc(tc_smem_u32(pass == 2 ? sm.b_lo[s] : sm.b_hi[s]));
+    for (int pass = 0; pass < 3; ++pass) {
+      const uint64_t da0 = tc_make_desc(tc_smem_u32(pass == 1 ? sm.a_lo[s] : sm.a_hi[s]));
+      const uint64_t db0 = tc_make_desc(tc_smem_u32(pass == 2 ? sm.b_lo[s] : sm.b_hi[s]));
 #pragma unroll
-        for (int ks = 0; ks < TL_KS / 8; ++ks)      // UMMA_K = 8 tf32 = 32 bytes along the swizzled row
-          tl_mma_ss(tmem, da0 + 2 * ks, db0 + 2 * ks, idesc, (jm > 0 || pass > 0 || ks > 0) ? 1u : 0u);
-      }
-      tl_commit(&sm.empty_bar[s]);
-      if (jm == nblk - 1) tl_commit(&sm.done_bar);
+      for (int ks = 0; ks < TL_KS / 8; ++ks)      // UMMA_K = 8 tf32 = 32 bytes along the swizzled row
+        tl_mma_ss(tmem, da0 + 2 * ks, db0 + 2 * ks, idesc, (jm > 0 || pass > 0 || ks > 0) ? 1u : 0u);
     }
-    __syncwarp();
-    if (j < nblk) {
+    tl_commit(&sm.empty_bar[s]);
+    if (jm == nblk - 1) tl_commit(&sm.done_bar);
+  };
+  // ---- main loop: warp 16 issues, warps 0..15 stage (register sets ping-pong) -------------------------
+  if (warp == TL_THREADS / 32) {
+    if (lane == 0)
+      for (int jm = 0; jm < nblk; ++jm) issue_mma(jm);
+  } else {
+    // fetch block j+1 into `nxt` -- its loads fly while block j is staged out of `cur`.  (Where two register
+    // sets do not fit, block j+1 is fetched into the same set right after block j has been staged: the other
+    // three warps of the scheduler cover the load latency.)
+    constexpr bool TWO_SETS = !(DP == 128 && TYPE == 1);
+    auto iterate = [&](Pre& cur, Pre& nxt, int j) {
+      if (TWO_SETS && j + 1 < nblk) fetch(nxt, j + 1);
       const int s = j % TL_STAGES;
       if (j >= TL_STAGES) mbar_wait_cta(&sm.empty_bar[s], ((j / TL_STAGES) - 1) & 1);   // MMAs of block j-2 done
-      stage(j, s);
-      if (j + 1 < nblk) fetch(j + 1);
+      stage(cur, j, s);
+      if (!TWO_SETS && j + 1 < nblk) fetch(cur, j + 1);
+    };
+    Pre P0;
+    if (nblk > 0) fetch(P0, 0);
+    if (TWO_SETS) {
+      Pre P1;
+      for (int j = 0; j < nblk; j += 2) {
+        iterate(P0, P1, j);
+        if (j + 1 < nblk) iterate(P1, P0, j + 1);
+      }
+    } else {
+      for (int j = 0; j < nblk; ++j) iterate(P0, P0, j);
     }
   }
 
