@@ -35,7 +35,7 @@ if ROOT not in sys.path:
 
 UNIT = "samples/s"
 T_FULL = 64000
-# name -> (kind, D, batch per GPU, T, tag, golden fixture)
+# name -> (kind, D, batch per GPU, T, tag, golden fixture[, checkpoint interval K])
 CONFIGS = {
     "c0": ("train", 8, 8, 16000, "C0: reference CPU-runnable case", "psi_c0_d8_t16000"),
     "c1": ("train", 32, 64, T_FULL, "C1", "psi_c1_full"),
@@ -44,13 +44,19 @@ CONFIGS = {
            "psi_c3_batch_t2000"),
     "c4": ("train", 64, 256, T_FULL, "C4 (per-GPU share of the global batch 2048 at 8 GPUs)",
            "psi_c4_batch_t4000"),
+    # checkpointed backward (one state per K steps, windowed recompute): C1 at K = 2048, and C4's WHOLE global
+    # batch on one GPU (136 GB of trajectory at K = 1)
+    "c1_k2048": ("train", 32, 64, T_FULL, "C1 with checkpoint interval K = 2048", None, 2048),
+    "c4_b2048_k2048": ("train", 64, 2048, T_FULL, "C4's global batch 2048 on ONE GPU, checkpoint interval K = 2048",
+                       None, 2048),
 }
 
 
 class Cfg:
     def __init__(self, name):
         self.name = name
-        self.kind, self.D, self.B, self.T, self.tag, self.golden = CONFIGS[name]
+        self.kind, self.D, self.B, self.T, self.tag, self.golden = CONFIGS[name][:6]
+        self.K = CONFIGS[name][6] if len(CONFIGS[name]) > 6 else None
         if self.kind == "sample":
             self.metric = f"AudioMPS sampling audio samples/s (D={self.D}, 4 s 16 kHz clips)"
             self.workload = (f"{self.tag}: PsiCMPS.sample D={self.D}, {self.B} waveforms/GPU x {self.T} steps, "
@@ -77,7 +83,12 @@ class Cfg:
         clustered = D <= 32 and 2 * B <= n_sms and os.environ.get("AMPS_NO_CLUSTER") != "1"
         kn = (f"cl_kernel<{_dp(D)}>" if clustered else f"kernel<{_dp(D)}>") if D <= 32 else \
             "uni_kernel<64,8>" if D <= 64 else "c4_kernel<128,4>"
-        return {"fwd": f"psi_fwd_{kn}", "bwd": f"psi_bwd_{kn}"}
+        names = {"fwd": f"psi_fwd_{kn}", "bwd": f"psi_bwd_{kn}"}
+        if D > 32 and os.environ.get("AMPS_NO_TC_TILES") != "1":
+            # chain-only adjoint sweep + the gradient tiles as tcgen05 GEMMs over the time axis (both inside "bwd")
+            names["bwd"] += " (chain only) + psi_tiles_tc_kernel"
+            names["tiles"] = f"psi_tiles_tc_kernel<{_dp(D)}>"
+        return names
 
 
 def _dp(D):
@@ -378,6 +389,8 @@ def measure_train(h, cfg, steps, warmup, full_detail):
     D, B, T = cfg.D, cfg.B, cfg.T
     hp = HParams(**cfg.hparams_kw())
     model = PsiCMPS(hp, device=h.dev, seed=0)            # same seed on every rank: replicated params
+    if cfg.K is not None:
+        model.checkpoint_every = cfg.K
     trainer = Trainer(model, group=None)
     gb = B * h.world
     x_host = torch.from_numpy(damped_sine(B, T, hp.delta_t, np.random.default_rng(1 + h.rank))).pin_memory()
@@ -391,8 +404,13 @@ def measure_train(h, cfg, steps, warmup, full_detail):
     if sampler:
         sampler.start()
     step_ms, launches = h.timed(step, steps, warmup)
-    kms = h.kernel_ms(step, (0, 1), min(steps, 3))
+    has_tiles = "tiles" in cfg.kernel_names()
+    kms = h.kernel_ms(step, (0, 1, 3) if has_tiles else (0, 1), min(steps, 3))
     res = {"step_ms": step_ms, "launches": launches, "fwd_ms": kms[0], "bwd_ms": kms[1], "gb": gb}
+    if has_tiles:
+        res["tiles_ms"] = kms[3]
+    res["checkpoint_interval"] = model._checkpoint_interval(D, B, T)
+    res["workspace_bytes"] = int(h.lib.load().amps_psi_workspace_bytes_k(D, B, T, res["checkpoint_interval"]))
 
     if full_detail:
         # ---- end to end: every step's batch comes from pinned host memory (double-buffered prefetch on
@@ -498,6 +516,8 @@ def kernel_entries(h, cfg, res):
     design_b = {"fwd": 12 + 16 * _dp(D), "bwd": 12 + 16 * _dp(D), "sample": 8}
     out = {}
     for which, name in names.items():
+        if which == "tiles":
+            continue
         ms = res[f"{which}_ms"]
         t = ms * 1e-3
         fl = units * cfg.flops(which)
@@ -508,6 +528,19 @@ def kernel_entries(h, cfg, res):
                       "hbm_frac_design": units * design_b[which] / t / 1e9 / peaks["hbm_gbs"],
                       "bytes_per_unit_survey": survey_b[which], "bytes_per_unit_design": design_b[which],
                       "cycles_per_step_at_1965MHz": t / max(cfg.T - 1, 1) * 1.965e9}
+    if "tiles" in names and res.get("tiles_ms"):
+        # G_N, G_R, G_E = 3 complex outer products per (clip, sample): 24 D^2 real flops; executed on the tensor
+        # pipe as 3 tf32 passes (hi*hi + lo*hi + hi*lo) of the real 2D x 2D (x 4D for the stacked pair) form
+        t = res["tiles_ms"] * 1e-3
+        Dp = _dp(D)
+        out["bwd"]["of_which_tiles_ms"] = res["tiles_ms"]
+        out["bwd"]["tiles"] = {"kernel": names["tiles"], "kernel_ms": res["tiles_ms"], "pipe": "tcgen05 kind::tf32, 3-pass split",
+                               "algorithmic_tflops": units * 24 * D * D / t / 1e12,
+                               "executed_tf32_tflops": units * 3 * 2 * (2 * Dp) * (6 * Dp) / t / 1e12,
+                               "hbm_gbs": units * (3 * 8 * Dp + 8) / t / 1e9,
+                               "hbm_frac": units * (3 * 8 * Dp + 8) / t / 1e9 / peaks["hbm_gbs"],
+                               "bytes_per_unit": 3 * 8 * Dp + 8,
+                               "ncu": "profiles/r2_ncu_tiles.md"}
     return out, fma, peaks, peak_src
 
 
@@ -569,10 +602,11 @@ def run_ours(args, cfg):
                 cpu = {"error": str(e)[:200]}
         if h.world == 1 and cfg.name == "c1" and not args.no_other_configs:
             other = {"c1": {"parity_err_vs_golden": golden_parity(h, cfg)}}
-            for name in ("c0", "c2", "c3", "c4"):
+            for name in ("c0", "c2", "c3", "c4", "c1_k2048", "c4_b2048_k2048"):
                 oc = Cfg(name)
                 try:
-                    m2 = (measure_sample if oc.kind == "sample" else measure_train)(h, oc, 3, 3, False)
+                    nst = 1 if oc.B > 1024 else 3          # (the 2048-clip step takes ~1.5 s)
+                    m2 = (measure_sample if oc.kind == "sample" else measure_train)(h, oc, nst, 3, False)
                     e2, _, _, _ = kernel_entries(h, oc, m2)
                     dk = max(e2, key=lambda k: e2[k]["kernel_ms"])
                     ms = float(np.mean(m2["step_ms"]))
@@ -583,7 +617,12 @@ def run_ours(args, cfg):
                                    "cycles_per_step": e2[dk]["cycles_per_step_at_1965MHz"],
                                    "kernels_ms": {k: v["kernel_ms"] for k, v in e2.items()},
                                    "gpu_launches": int(m2["launches"]),
-                                   "parity_err_vs_golden": golden_parity(h, oc)}
+                                   "parity_err_vs_golden": golden_parity(h, oc) if oc.golden else None}
+                    if "checkpoint_interval" in m2:
+                        other[name]["checkpoint_interval"] = m2["checkpoint_interval"]
+                        other[name]["workspace_mb"] = m2["workspace_bytes"] / 1e6
+                    if "tiles" in e2.get("bwd", {}):
+                        other[name]["tiles"] = e2["bwd"]["tiles"]
                 except Exception as e:
                     other[name] = {"error": str(e)[:300]}
         line = {"metric": cfg.metric, "value": value, "unit": UNIT, "n_gpus": h.world, "steps": K,

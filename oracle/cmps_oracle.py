@@ -248,6 +248,26 @@ class PsiCMPSOracle(CMPSOracle):
             t = np.float32(t + self.dt32)                             # :281
         return loss
 
+    def loss_and_abs_terms(self, data):
+        """(loss_b, sum_k |term_{k,b}|): the second is the condition of the sum -- a clip whose terms
+        cancel (loss_b << sum |terms|) cannot be held to a relative tolerance on loss_b alone."""
+        incs = self._incs(data)
+        B = incs.shape[1]
+        psi = self.psi_0.unsqueeze(0).repeat(B, 1)
+        loss = torch.zeros(B, dtype=self.rdt)
+        absum = torch.zeros(B, dtype=self.rdt)
+        t = np.float32(0.0)
+        with torch.no_grad():
+            for k in range(incs.shape[0]):
+                sig = incs[k]
+                psi = self._update_ancilla_psi(psi, sig, t)
+                term = self._inc_loss_psi(psi, sig, t)
+                loss = loss + term
+                absum = absum + term.abs()
+                psi = self._normalize_psi(psi, axis=1)
+                t = np.float32(t + self.dt32)
+        return loss, absum
+
     def loss(self, data):
         return self.loss_per_clip(data).mean()                        # :267
 

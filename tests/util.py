@@ -66,3 +66,15 @@ def worst_clip(a, b, floor=1e-2):
     e = np.abs(a - b) / den
     i = int(e.argmax())
     return i, float(e[i]), float(a[i]), float(b[i])
+
+
+def rel_clip_cond(a, b, abs_terms, kappa=0.1, floor=1e-2):
+    """Per-clip error with a condition-aware denominator: max(|r_b|, floor * max|r|, kappa * sum_k |term_kb|).
+    Used for the parallel-in-time scan, whose chunk start states carry ~1e-6 of float32 / tf32-split rounding:
+    on a clip whose log-terms cancel to a few percent of their absolute sum that is 1e-4 of the (small) loss
+    although every term is accurate to 1e-6 (profiles/diag_scan_err.py)."""
+    a = np.asarray(a, dtype=np.float64).reshape(-1)
+    b = np.asarray(b, dtype=np.float64).reshape(-1)
+    s = np.asarray(abs_terms, dtype=np.float64).reshape(-1)
+    den = np.maximum(np.maximum(np.abs(b), floor * max(float(np.abs(b).max()), 1e-300)), kappa * s)
+    return float((np.abs(a - b) / den).max())
