@@ -19,6 +19,7 @@
 #include "amps_psi_c4.cuh"
 #include "amps_scan_tc.cuh"
 #include "amps_tiles_tc.cuh"
+#include "amps_sx_tc.cuh"
 
 using namespace amps;
 
@@ -204,7 +205,7 @@ int tiles_steps_per_split(int nsteps, int nsplit) {
 
 struct PsiWs {
   size_t matN, matR, matRH, matS, psi0p, ttab, qtab, lossd;
-  size_t traj, scales, G, gf, lam0, gAdir, Gtot, gftot, lam0tot, sptraj, ev;
+  size_t traj, scales, G, gf, lam0, gAdir, Gtot, gftot, lam0tot, sptraj, ev, lossp;
   size_t total;
 };
 
@@ -241,6 +242,7 @@ PsiWs psi_ws_layout(int DP, int B, int nsteps_tab, int T, bool save) {
     {   // S x'_k and (E_k, |x_k|^2) from the forward
       w.sptraj = take((size_t)B * T * DP * sizeof(float2));   // S x'_k
       w.ev = take((size_t)B * T * sizeof(float2));            // (E_k, |x_k|^2)
+      w.lossp = take((size_t)B * tiles_nsplit(DP, B, nsteps) * sizeof(double));   // per-split loss sums (D = 33..64)
     }
   }
   w.total = off;
@@ -464,6 +466,8 @@ struct FwdArgs {
   float2* sptraj;
   float2* ev;
   SegFwd seg;
+  double* loss_part = nullptr;   // D = 33..64 saving forward: per-split loss sums of psi_sx_tc_kernel
+  int sx_nsplit = 1, sx_sps = 0;
 };
 struct BwdArgs {
   const float2 *matN, *matRH, *matS, *qtab;
@@ -525,6 +529,8 @@ cudaError_t amps_set_all_func_attrs() {
   if ((e = set_smem(psi_bwd_uni_kernel<64, 8, false, false>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_tiles_tc_kernel<64, 0>, sizeof(TilesSmem<64, 0>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_tiles_tc_kernel<64, 1>, sizeof(TilesSmem<64, 1>) + 1024)) != cudaSuccess) return e;
+  if ((e = set_smem(psi_fwd_uni_kernel<64, 8, false, true>, sizeof(FwdSmemUni<64, 8>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_sx_tc_kernel<64>, sizeof(SxSmem<64>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_tiles_tc_kernel<128, 1>, sizeof(TilesSmem<128, 1>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_tiles_tc_kernel<128, 2>, sizeof(TilesSmem<128, 2>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_tiles_tc_kernel<128, 3>, sizeof(TilesSmem<128, 3>) + 1024)) != cudaSuccess) return e;
@@ -572,6 +578,31 @@ int launch_psi_fwd(amps_ctx* ctx, int DP, int B, const FwdArgs& a, cudaStream_t 
       psi_fwd_kernel<DPc, NQc><<<B, 2 * DPc * NQc, sizeof(FwdSmem<DPc, NQc>), st>>>(
           a.matN, a.matR, a.matS, a.qtab, a.psi0p, a.x, a.T, a.A, a.loss, a.lossd, a.traj, a.scales, nchunks,
           a.sptraj, a.ev, a.seg);
+    } else if (ctx->tc_tiles && a.traj && a.sptraj && a.loss_part) {
+      // chain-only forward (x'_k and |x_k|^2 stored), then S x'_k, E_k and the loss as ONE GEMM over the time
+      // axis on the tensor cores, in place
+      psi_fwd_uni_kernel<DPc, NQc, false, true><<<B, DPc * NQc, sizeof(FwdSmemUni<DPc, NQc>), st>>>(
+          a.matN, a.matR, a.matS, a.qtab, a.psi0p, a.x, a.T, a.A, a.loss, a.lossd, a.traj, a.scales, nchunks,
+          (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg);
+      LAUNCH_CHECK(ctx, "psi_fwd_uni_kernel<chain>");
+      SxArgs g{};
+      g.matS = a.matS;
+      g.sptraj = a.sptraj;
+      g.ev = a.ev;
+      g.x = a.x;
+      g.loss_part = a.loss_part;
+      g.T = a.T;
+      g.xstride = a.seg.xstride;
+      g.nsplit = a.sx_nsplit;
+      g.steps_per_split = a.sx_sps;
+      g.A = a.A;
+      PROF_BEGIN(ctx, 2, st);
+      psi_sx_tc_kernel<DPc><<<B * g.nsplit, SX_BLOCK, sizeof(SxSmem<DPc>) + 1024, st>>>(g);
+      PROF_END(ctx, 2, st);
+      LAUNCH_CHECK(ctx, "psi_sx_tc_kernel");
+      psi_scan_sum_kernel<<<(B + 127) / 128, 128, 0, st>>>(a.loss_part, B, g.nsplit, a.loss, a.lossd);
+      LAUNCH_CHECK(ctx, "psi_scan_sum_kernel");
+      return AMPS_OK;
     } else {
       psi_fwd_uni_kernel<DPc, NQc><<<B, DPc * NQc, sizeof(FwdSmemUni<DPc, NQc>), st>>>(
           a.matN, a.matR, a.matS, a.qtab, a.psi0p, a.x, a.T, a.A, a.loss, a.lossd, a.traj, a.scales, nchunks,
@@ -724,6 +755,11 @@ int amps_psi_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
             (double*)(ws + L.lossd), save ? (float2*)(ws + L.traj) : nullptr,
             save ? (float*)(ws + L.scales) : nullptr, save ? (float2*)(ws + L.sptraj) : nullptr,
             save ? (float2*)(ws + L.ev) : nullptr, seg_full_f(T)};
+  if (save) {
+    a.loss_part = (double*)(ws + L.lossp);
+    a.sx_nsplit = tiles_nsplit(DP, B, T - 1);
+    a.sx_sps = tiles_steps_per_split(T - 1, a.sx_nsplit);
+  }
   PROF_BEGIN(ctx, 0, st);
   rc = launch_psi_fwd(ctx, DP, B, a, st);
   PROF_END(ctx, 0, st);
@@ -807,6 +843,7 @@ CkWs ck_ws_layout(int DP, int B, int T, int K) {
   w.ckpt = take((size_t)B * w.nwin * DP * sizeof(float2));
   w.loss_scr = take((size_t)B * sizeof(float));
   w.lossd_scr = take((size_t)B * sizeof(double));
+  w.base.lossp = take((size_t)B * tiles_nsplit(DP, B, w.W) * sizeof(double));
   for (int i = 0; i < 2; ++i) {
     w.traj[i] = take((size_t)B * Wt * DP * sizeof(float2));
     w.sptraj[i] = take((size_t)B * Wt * DP * sizeof(float2));
@@ -910,6 +947,9 @@ int amps_psi_loss_bwd_k(amps_ctx* ctx, const amps_params* p, const float* x_dev,
               qtab + (size_t)j * L.W * DP, (const float2*)(ws + L.base.psi0p), x_dev + (size_t)j * L.W, wlen(j) + 1,
               aval(p), (float*)(ws + L.loss_scr), (double*)(ws + L.lossd_scr), (float2*)(ws + L.traj[i]),
               (float*)(ws + L.scales[i]), (float2*)(ws + L.sptraj[i]), (float2*)(ws + L.ev[i]), seg};
+    a.loss_part = (double*)(ws + L.base.lossp);
+    a.sx_nsplit = ck_nsplit;
+    a.sx_sps = ck_sps;
     return launch_psi_fwd(ctx, DP, B, a, s2);
   };
   auto adjoint = [&](int j) -> int {

@@ -593,7 +593,10 @@ struct alignas(16) BwdSmemUni {
 // VIRT: "virtual clip" mode of the parallel-in-time scan (amps_scan_tc.cuh): block b replays time
 // chunk (b % nvc) of clip (b / nvc) -- m_steps steps from global step (b % nvc) * m_steps -- starting
 // from its own state psi0v[b]; the per-chunk loss goes to lossd[b].
-template <int DP, int NQ, bool VIRT = false>
+// SXO ("S x' offloaded"): chain only -- x'_k goes where S x'_k would (sptraj rows) and |x_k|^2 into ev[k].y;
+// S x'_k, E_k and the loss are produced afterwards, in place, by psi_sx_tc_kernel (amps_sx_tc.cuh) on the
+// tensor cores.  Needs the trajectory buffers (a saving forward).
+template <int DP, int NQ, bool VIRT = false, bool SXO = false>
 __global__ void __launch_bounds__(DP* NQ)
     psi_fwd_uni_kernel(const float2* __restrict__ matN, const float2* __restrict__ matR,
                    const float2* __restrict__ matS, const float2* __restrict__ qtab_,
@@ -772,19 +775,29 @@ __global__ void __launch_bounds__(DP* NQ)
       __syncthreads();
     };
 
-    step(IC0{}, 0);
-    if (len > 1) step(IC1{}, 1);
-    if (len == CH) {
+    if (SXO) {
+      if (len == CH) {
 #pragma unroll 2
-      for (int kk = 2; kk < CH; ++kk) step(IC2{}, kk);
+        for (int kk = 0; kk < CH; ++kk) step(IC0{}, kk);
+      } else {
+        for (int kk = 0; kk < len; ++kk) step(IC0{}, kk);
+      }
+      cp_async_wait<0>();
     } else {
-      for (int kk = 2; kk < len; ++kk) step(IC2{}, kk);
+      step(IC0{}, 0);
+      if (len > 1) step(IC1{}, 1);
+      if (len == CH) {
+#pragma unroll 2
+        for (int kk = 2; kk < CH; ++kk) step(IC2{}, kk);
+      } else {
+        for (int kk = 2; kk < len; ++kk) step(IC2{}, kk);
+      }
+      cp_async_wait<0>();
+      // drain the expectation pipeline: step len-2's partial is in part_pp, step len-1 has none yet
+      if (len >= 2) finish_expect(part_pp, len - 2);
+      finish_expect(matvec1<DP, NQ>(Sr, sm.xps[len - 1], jq), len - 1);
+      __syncthreads();  // (A)
     }
-    cp_async_wait<0>();
-    // drain the expectation pipeline: step len-2's partial is in part_pp, step len-1 has none yet
-    if (len >= 2) finish_expect(part_pp, len - 2);
-    finish_expect(matvec1<DP, NQ>(Sr, sm.xps[len - 1], jq), len - 1);
-    __syncthreads();  // (A)
 
     {  // per-step scalars, lane-parallel over the chunk: G threads per step
       const int kk = t / G, g = t % G;
@@ -792,20 +805,24 @@ __global__ void __launch_bounds__(DP* NQ)
       if (kk < len) {
 #pragma unroll
         for (int r = 0; r < PER; ++r) {
-          en += sm.esr[kk][2 * (g * PER + r)] + sm.esr[kk][2 * (g * PER + r) + 1];
+          if (!SXO) en += sm.esr[kk][2 * (g * PER + r)] + sm.esr[kk][2 * (g * PER + r) + 1];
           nu2 += sm.ns[buf][kk][g * PER + r];
         }
       }
 #pragma unroll
       for (int m = 1; m < G; m <<= 1) {
-        en += __shfl_xor_sync(0xffffffffu, en, m);
+        if (!SXO) en += __shfl_xor_sync(0xffffffffu, en, m);
         nu2 += __shfl_xor_sync(0xffffffffu, nu2, m);
       }
       if (g == 0 && kk < len) {
-        const float E = en / fmaxf(nu2, 1e-12f);                                  // model.py:324-325 on x'
-        const float z = (E * sm.incv[buf][kk]) / A;                // model.py:294
-        lossacc -= (double)log1pf(z);
-        sm.evs[kk] = make_float2(E, nu2);
+        if (SXO) {
+          sm.evs[kk] = make_float2(0.f, nu2);                        // E_k: psi_sx_tc_kernel
+        } else {
+          const float E = en / fmaxf(nu2, 1e-12f);                                  // model.py:324-325 on x'
+          const float z = (E * sm.incv[buf][kk]) / A;                // model.py:294
+          lossacc -= (double)log1pf(z);
+          sm.evs[kk] = make_float2(E, nu2);
+        }
       }
     }
     if (c + 1 < nchunks) compute_s(buf ^ 1, min(CH, nsteps - (k0 + CH)));
@@ -828,8 +845,8 @@ __global__ void __launch_bounds__(DP* NQ)
       const float4* src = reinterpret_cast<const float4*>(&sm.xs[1][0]);
       float4* dst = reinterpret_cast<float4*>(traj + ((size_t)b * tstride + k0 + 1) * DP);
       for (int idx = t; idx < len * DP / 2; idx += NT) dst[idx] = src[idx];
-      if (sptraj) {   // S x'_k and (E_k, |x_k|^2) for the adjoint: row k of the (virtual) clip
-        const float4* ssrc = reinterpret_cast<const float4*>(&sm.sps[0][0]);
+      if (sptraj) {   // S x'_k (SXO: x'_k) and (E_k, |x_k|^2) for the adjoint: row k of the (virtual) clip
+        const float4* ssrc = reinterpret_cast<const float4*>(SXO ? &sm.xps[0][0] : &sm.sps[0][0]);
         float4* sdst = reinterpret_cast<float4*>(sptraj + ((size_t)b * tstride + k0) * DP);
         for (int idx = t; idx < len * DP / 2; idx += NT) sdst[idx] = ssrc[idx];
         if (t < len) evout[(size_t)b * tstride + k0 + t] = sm.evs[t];
@@ -841,7 +858,7 @@ __global__ void __launch_bounds__(DP* NQ)
   lossacc = warp_sum_d(lossacc);
   if (lane == 0) sm.lred[warp] = lossacc;
   __syncthreads();
-  if (t == 0) {
+  if (t == 0 && !SXO) {
     double tot = 0.0;
     for (int wv = 0; wv < NT / 32; ++wv) tot += sm.lred[wv];
     if (loss) loss[b] = (float)tot;

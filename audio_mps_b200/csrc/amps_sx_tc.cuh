@@ -1,0 +1,241 @@
+// Expectation pass of the forward on the tensor cores (D = 33..64).
+//
+// Per step the forward needs, besides the chain x_{k+1} = c_k q_k (N + s_k R) x_k, the vector S x'_k
+// (S = R + R^dag; kept for the adjoint sweep), E_k = x'_k^dag S x'_k / |x_k|^2 and the loss term
+// -log1p(E_k inc_k / A) (model.py:293-294, 319-325).  None of that feeds the next state.  Inside the
+// sequential kernel it was a second mat-vec per step (32 FFMA + 4 LDS.128 per thread in the chain's
+// shuffle shadows); over the time axis it is ONE GEMM,  [S x'_k]_k = S_real X'^T  (2D x 2D times 2D x T),
+// fully parallel.  The sequential kernel now stores x'_k (where S x'_k used to go) and |x_k|^2, and this
+// kernel transforms the trajectory IN PLACE:
+//     rows of sptraj:  x'_k  ->  S x'_k            ev[k] = (E_k, |x_k|^2)            loss_part[b][split]
+// A = S in real form (row 2i+c, column 2j+c'; [[Sr, -Si], [Si, Sr]]), tf32 hi + lo, staged ONCE per CTA
+// (128 KB); B = 32 steps of x' per stage (row = step: the trajectory's own layout IS K-major), tf32 hi + lo;
+// three passes S_hi X_hi + S_lo X_hi + S_hi X_lo (2^-21 per product: E_k is a small residual of large terms,
+// a single rounded x' operand was worth 1e-4 of a 32-step loss).  Accumulators: two 32-column buffers in
+// tensor memory; warp 16 issues the MMAs; the 16 worker warps stage tile j+1, then drain tile j:
+// tcgen05.ld -> shared transpose -> coalesced read-modify-write of the trajectory rows with the E_k dot
+// products folded in.
+#pragma once
+#include "amps_common.cuh"
+#include "amps_scan_tc.cuh"
+#include "amps_tiles_tc.cuh"
+
+namespace amps {
+
+constexpr int SX_NS = 32;             // steps per tile = UMMA N
+constexpr int SX_THREADS = 512;       // worker threads (warps 0..15)
+constexpr int SX_BLOCK = SX_THREADS + 32;
+
+template <int DP>
+struct alignas(1024) SxSmem {
+  static constexpr int KR = 2 * DP;                 // real contraction length
+  static constexpr int NKB = KR / 32;               // 128-byte K blocks
+  uint8_t a_hi[NKB][128 * TL_ROWB];                 // S real form, rows 2i+c, K block kb
+  uint8_t a_lo[NKB][128 * TL_ROWB];
+  uint8_t b[2][NKB][SX_NS * TL_ROWB];               // x' tile truncated to tf32, row = step
+  uint8_t b_lo[2][NKB][SX_NS * TL_ROWB];            // x' - trunc(x')
+  float outs[SX_NS][KR + 4];                        // (S x')[step][2i+c], epilogue transpose
+  float red[SX_NS][8];                              // E_k partial sums
+  double lred[16];
+  unsigned long long full_bar[2], empty_bar[2], acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+struct SxArgs {
+  const float2* matS;      // [DP][DP]
+  float2* sptraj;          // [B][T][DP]  in: x'_k (row k), out: S x'_k
+  float2* ev;              // [B][T]      in: (., |x_k|^2), out: (E_k, |x_k|^2)
+  const float* x;          // waveform, clip stride xstride
+  double* loss_part;       // [B][nsplit]
+  int T, xstride, nsplit, steps_per_split;   // steps_per_split: multiple of SX_NS
+  AVal A;
+};
+
+// grid = B * nsplit, block = 544
+template <int DP>
+__global__ void __launch_bounds__(SX_BLOCK, 1) psi_sx_tc_kernel(SxArgs g) {
+  using Sm = SxSmem<DP>;
+  constexpr int KR = Sm::KR, NKB = Sm::NKB;
+  static_assert(DP == 64, "one UMMA M = 128 tile of output rows");
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem_al = smem_raw + ((1024u - (tc_smem_u32(smem_raw) & 1023u)) & 1023u);
+  Sm& sm = *reinterpret_cast<Sm*>(smem_al);
+  const float A = a_get(g.A);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x / g.nsplit, sp = blockIdx.x % g.nsplit;
+  const int nsteps = g.T - 1;
+  const int k_begin = sp * g.steps_per_split;
+  const int nloc = max(0, min(g.steps_per_split, nsteps - k_begin));
+  const int ntile = (nloc + SX_NS - 1) / SX_NS;
+  float* rows = reinterpret_cast<float*>(g.sptraj + ((size_t)b * g.T + k_begin) * DP);   // [step][KR] floats
+  float2* evb = g.ev + (size_t)b * g.T + k_begin;
+  const float* xb = g.x + (size_t)b * g.xstride + k_begin;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sm.full_bar[s], SX_THREADS);
+      mbar_init(&sm.empty_bar[s], 1);
+      mbar_init(&sm.acc_full[s], 1);
+      mbar_init(&sm.acc_empty[s], SX_THREADS);
+    }
+    mbar_fence_init_cluster();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;\n" ::"r"(tc_smem_u32(&sm.tmem_base)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  // A = S real form, hi / lo, once
+  if (tid < SX_THREADS) {
+    for (int idx = tid; idx < DP * (DP / 2); idx += SX_THREADS) {   // (row i, pair of columns j, j+1)
+      const int i = idx / (DP / 2), j = 2 * (idx % (DP / 2));
+      const float2 s0 = g.matS[i * DP + j], s1 = g.matS[i * DP + j + 1];
+      // real columns 2j .. 2j+3 of rows 2i (Re out) and 2i+1 (Im out): one 16-byte chunk each
+      const float r0[4] = {s0.x, -s0.y, s1.x, -s1.y};
+      const float r1[4] = {s0.y, s0.x, s1.y, s1.x};
+      const int kb = (2 * j) / 32, ch = ((2 * j) % 32) / 4;
+      auto put = [&](int row, const float (&v)[4]) {
+        const float4 h = make_float4(tc_trunc_tf32(v[0]), tc_trunc_tf32(v[1]), tc_trunc_tf32(v[2]), tc_trunc_tf32(v[3]));
+        const int o = tl_off(row, ch);
+        *reinterpret_cast<float4*>(sm.a_hi[kb] + o) = h;
+        *reinterpret_cast<float4*>(sm.a_lo[kb] + o) = make_float4(v[0] - h.x, v[1] - h.y, v[2] - h.z, v[3] - h.w);
+      };
+      put(2 * i, r0);
+      put(2 * i + 1, r1);
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = sm.tmem_base;
+  // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 32, M = 128
+  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(SX_NS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+  if (warp == SX_THREADS / 32) {
+    // ---- MMA warp -----------------------------------------------------------------------------
+    if (lane == 0) {
+      for (int j = 0; j < ntile; ++j) {
+        const int s = j & 1;
+        mbar_wait_cta(&sm.full_bar[s], (j >> 1) & 1);
+        if (j >= 2) mbar_wait_cta(&sm.acc_empty[s], ((j >> 1) - 1) & 1);   // tile j-2 drained out of accumulator s
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        bool first = true;
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll 1
+          for (int kb = 0; kb < NKB; ++kb) {
+            const uint64_t da0 = tc_make_desc(tc_smem_u32(pass == 1 ? sm.a_lo[kb] : sm.a_hi[kb]));
+            const uint64_t db0 = tc_make_desc(tc_smem_u32(pass == 2 ? sm.b_lo[s][kb] : sm.b[s][kb]));
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              tl_mma_ss(tmem + SX_NS * s, da0 + 2 * ks, db0 + 2 * ks, idesc, first ? 0u : 1u);
+              first = false;
+            }
+          }
+        }
+        tl_commit(&sm.empty_bar[s]);
+        tl_commit(&sm.acc_full[s]);
+      }
+    }
+  } else {
+    // ---- worker warps ---------------------------------------------------------------------------
+    double lossacc = 0.0;
+    // stage tile j: 32 rows x KR floats, as 16-byte chunks (row n, K block kb, chunk c)
+    constexpr int NCH = SX_NS * KR / 4 / SX_THREADS;   // chunks per thread
+    float4 pre[NCH];
+    auto fetch = [&](int j) {
+      const int n0 = j * SX_NS, len = min(SX_NS, nloc - n0);
+#pragma unroll
+      for (int q = 0; q < NCH; ++q) {
+        const int idx = tid + q * SX_THREADS;
+        const int n = idx / (KR / 4), c4 = idx % (KR / 4);
+        pre[q] = (n < len) ? *reinterpret_cast<const float4*>(rows + (size_t)(n0 + n) * KR + 4 * c4)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto stage = [&](int j) {
+      const int s = j & 1;
+      if (j >= 2) mbar_wait_cta(&sm.empty_bar[s], ((j >> 1) - 1) & 1);
+#pragma unroll
+      for (int q = 0; q < NCH; ++q) {
+        const int idx = tid + q * SX_THREADS;
+        const int n = idx / (KR / 4), c4 = idx % (KR / 4);
+        const int kb = c4 / 8, ch = c4 % 8;
+        const float4 v = pre[q];
+        const float4 h = make_float4(tc_trunc_tf32(v.x), tc_trunc_tf32(v.y), tc_trunc_tf32(v.z), tc_trunc_tf32(v.w));
+        *reinterpret_cast<float4*>(sm.b[s][kb] + tl_off(n, ch)) = h;
+        *reinterpret_cast<float4*>(sm.b_lo[s][kb] + tl_off(n, ch)) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+      }
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      tl_mbar_arrive(&sm.full_bar[s]);
+    };
+    // drain tile j: accumulator -> outs (transposed) -> rows (in place), E_k, loss
+    const int q4 = warp & 3, cg = warp >> 2;          // TMEM lane quarter, column group (8 steps)
+    auto drain = [&](int j) {
+      const int s = j & 1;
+      const int n0 = j * SX_NS, len = min(SX_NS, nloc - n0);
+      mbar_wait_cta(&sm.acc_full[s], (j >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      {
+        uint32_t r[8];
+        const uint32_t taddr = tmem + ((uint32_t)(32 * q4) << 16) + SX_NS * s + 8 * cg;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        const int m = 32 * q4 + lane;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sm.outs[8 * cg + e][m] = __uint_as_float(r[e]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      tl_mbar_arrive(&sm.acc_empty[s]);
+      bar_named(5, SX_THREADS);
+      // 16 threads per step: each owns 8 consecutive floats of the row
+      {
+        const int n = tid >> 4, part = tid & 15;
+        float e = 0.f;
+        if (n < len) {
+          float* gp = rows + (size_t)(n0 + n) * KR + 8 * part;
+          const float4 x0 = *reinterpret_cast<const float4*>(gp), x1 = *reinterpret_cast<const float4*>(gp + 4);
+          const float4 o0 = *reinterpret_cast<const float4*>(&sm.outs[n][8 * part]);
+          const float4 o1 = *reinterpret_cast<const float4*>(&sm.outs[n][8 * part + 4]);
+          e = x0.x * o0.x + x0.y * o0.y + x0.z * o0.z + x0.w * o0.w + x1.x * o1.x + x1.y * o1.y + x1.z * o1.z + x1.w * o1.w;
+          *reinterpret_cast<float4*>(gp) = o0;
+          *reinterpret_cast<float4*>(gp + 4) = o1;
+        }
+        e += __shfl_xor_sync(0xffffffffu, e, 1);
+        e += __shfl_xor_sync(0xffffffffu, e, 2);
+        e += __shfl_xor_sync(0xffffffffu, e, 4);
+        e += __shfl_xor_sync(0xffffffffu, e, 8);
+        if (part == 0 && n < len) {
+          const float nu2 = evb[n0 + n].y;
+          const float E = e / fmaxf(nu2, 1e-12f);                       // model.py:324-325 on x'
+          const float inc = xb[n0 + n + 1] - xb[n0 + n];
+          lossacc -= (double)log1pf((E * inc) / A);                     // model.py:294
+          evb[n0 + n] = make_float2(E, nu2);
+        }
+      }
+      bar_named(5, SX_THREADS);   // outs free for the next tile
+    };
+    if (ntile > 0) fetch(0);
+    for (int j = 0; j < ntile; ++j) {
+      stage(j);
+      if (j + 1 < ntile) fetch(j + 1);
+      if (j > 0) drain(j - 1);
+    }
+    if (ntile > 0) drain(ntile - 1);
+    lossacc = warp_sum_d(lossacc);
+    if (lane == 0) sm.lred[warp] = lossacc;
+    bar_named(5, SX_THREADS);
+    if (tid == 0) {
+      double tot = 0.0;
+      for (int wv = 0; wv < SX_THREADS / 32; ++wv) tot += sm.lred[wv];
+      g.loss_part[blockIdx.x] = tot;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;\n" ::"r"(tmem));
+}
+
+}  // namespace amps

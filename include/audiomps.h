@@ -79,7 +79,8 @@ int amps_time_table_host(double delta_t, int n, float* out);
 /* ---- measurement helpers (bench.py) ------------------------------------------------------ */
 /* When enabled, the context brackets the dominant kernel of each entry point with CUDA events on
  * the launch stream; amps_get_kernel_ms(which: 0 = psi forward, 1 = psi backward (all of its kernels),
- * 2 = psi sampler / operator composition, 3 = the tensor-core gradient-tile kernels inside 1)
+ * 2 = psi sampler / operator composition / the tensor-core expectation pass inside 0,
+ * 3 = the tensor-core gradient-tile kernels inside 1)
  * synchronises on the stop event and returns the last launch's duration. */
 int amps_set_profiling(amps_ctx* ctx, int enable);
 int amps_get_kernel_ms(amps_ctx* ctx, int which, float* ms);

@@ -55,7 +55,7 @@ for name in which:
         dg = float((g - g1).abs().max() / g1.abs().max())
         tiles = ""
         try:
-            tiles = f", tiles {_lib.kernel_ms(0,3):.2f}"
+            tiles = f", tiles {_lib.kernel_ms(0,3):.2f}, sx {_lib.kernel_ms(0,2):.2f}"
         except Exception:
             pass
         print(f"{name} D={D} B={B} T={T} K={K}: step {ms:.2f} ms (fwd {_lib.kernel_ms(0,0):.2f}, bwd {_lib.kernel_ms(0,1):.2f}{tiles}) "
