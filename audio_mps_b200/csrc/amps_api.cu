@@ -534,6 +534,7 @@ cudaError_t amps_set_all_func_attrs() {
   if ((e = set_smem(psi_tiles_tc_kernel<128, 1>, sizeof(TilesSmem<128, 1>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_tiles_tc_kernel<128, 2>, sizeof(TilesSmem<128, 2>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_tiles_tc_kernel<128, 3>, sizeof(TilesSmem<128, 3>) + 1024)) != cudaSuccess) return e;
+  if ((e = set_smem(psi_sample_c4_kernel<128, C4_CL>, sizeof(SampleC4Smem<128, C4_CL>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_bwd_c4_kernel<128, C4_CL, false, false>, sizeof(BwdC4Smem<128, C4_CL>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_bwd_uni_kernel<64, 8, true, false>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_bwd_uni_kernel<64, 8, true, true>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
@@ -1173,7 +1174,8 @@ int amps_psi_loss_bwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
 size_t amps_psi_sample_workspace_bytes(int D, int L, int n) {
   const int DP = padded_dim(D);
   if (DP < 0 || L < 0 || n < 0) return 0;
-  return psi_ws_layout(DP, 0, L, 0, false).total;
+  // step operators, t_k / q_k tables + the noise tensor transposed to [n][L]
+  return psi_ws_layout(DP, 0, L, 0, false).total + align_up((size_t)n * L * sizeof(float));
 }
 
 int amps_psi_sample(amps_ctx* ctx, const amps_params* p, const float* noise_dev, int L_, int n,
@@ -1185,14 +1187,28 @@ int amps_psi_sample(amps_ctx* ctx, const amps_params* p, const float* noise_dev,
   if (L_ == 0 || n == 0) return AMPS_OK;
   if (!noise_dev || !out_dev) return fail(ctx, AMPS_E_INVALID, "NULL buffer");
   const int DP = padded_dim(p->D);
-  if (DP < 0 || DP > 64) return fail(ctx, AMPS_E_UNSUPPORTED, "bond dimension %d > 64 not supported by the sampler", p->D);
+  if (DP < 0) return fail(ctx, AMPS_E_UNSUPPORTED, "bond dimension %d > 128 not supported", p->D);
   const PsiWs L = psi_ws_layout(DP, 0, L_, 0, false);
-  if (!ws_dev || ws_bytes < L.total)
-    return fail(ctx, AMPS_E_WORKSPACE, "workspace %zu < required %zu bytes", ws_bytes, L.total);
+  const size_t need = L.total + align_up((size_t)n * L_ * sizeof(float));
+  if (!ws_dev || ws_bytes < need)
+    return fail(ctx, AMPS_E_WORKSPACE, "workspace %zu < required %zu bytes", ws_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)ws_dev;
   rc = psi_prepare(ctx, p, DP, ws, L, L_, st);
   if (rc) return rc;
+  float* noiseT = (float*)(ws + L.total);
+  prep_transpose_kernel<<<dim3((n + 31) / 32, (L_ + 31) / 32), dim3(32, 8), 0, st>>>(noise_dev, L_, n, noiseT);
+  LAUNCH_CHECK(ctx, "prep_transpose_kernel");
+  noise_dev = noiseT;
+  if (DP == 128) {   // rows of N and R split over a 4-CTA cluster per waveform
+    PROF_BEGIN(ctx, 2, st);
+    CUDA_TRY(ctx, launch_cluster(psi_sample_c4_kernel<128, C4_CL>, n, C4_CL, 512, sizeof(SampleC4Smem<128, C4_CL>), st,
+                                 (const float2*)(ws + L.matN), (const float2*)(ws + L.matR), (const float2*)(ws + L.qtab),
+                                 (const float2*)(ws + L.psi0p), noise_dev, L_, n, p->A, (float)p->delta_t, out_dev));
+    PROF_END(ctx, 2, st);
+    LAUNCH_CHECK(ctx, "psi_sample_c4_kernel");
+    return AMPS_OK;
+  }
   return dispatch_dp(DP, [&](auto dp, auto nq) -> int {
     constexpr int DPc = decltype(dp)::value, NQc = decltype(nq)::value;
     auto kern = psi_sample_kernel<DPc, NQc>;

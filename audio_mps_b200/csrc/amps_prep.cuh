@@ -122,6 +122,23 @@ __global__ void prep_mats_kernel(const float2* __restrict__ R, int D, int DP, do
   }
 }
 
+// noise [L][n] (time-major, as tf.random_normal([length, num_samples]), model.py:246) -> [n][L]: the sampler
+// kernels read one waveform's noise as a contiguous stream instead of one 4-byte element per 32-byte sector.
+// 32 x 32 tiles through shared memory, coalesced on both sides.  grid = (ceil(n/32), ceil(L/32)), block = (32, 8).
+__global__ void prep_transpose_kernel(const float* __restrict__ in, int L, int n, float* __restrict__ outT) {
+  __shared__ float tile[32][33];
+  const int n0 = blockIdx.x * 32, l0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int l = l0 + r, c = n0 + threadIdx.x;
+    if (l < L && c < n) tile[r][threadIdx.x] = in[(size_t)l * n + c];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int c = n0 + r, l = l0 + threadIdx.x;
+    if (c < n && l < L) outT[(size_t)c * L + l] = tile[threadIdx.x][r];
+  }
+}
+
 __global__ void prep_pad_vec_kernel(const float2* __restrict__ v, int D, int DP,
                                     float2* __restrict__ vp) {
   const int i = threadIdx.x + blockIdx.x * blockDim.x;

@@ -1192,7 +1192,7 @@ __global__ void __launch_bounds__(DP* NQ)
     float2* qdst = &sm.qs[buf][0][0];
     for (int idx = t; idx < len * DP / 2; idx += NT) cp_async16(qdst + 2 * idx, qsrc + 2 * idx);
     for (int idx = t; idx < len; idx += NT)
-      cp_async4(&sm.nz[buf][idx], noise + (size_t)(k0 + idx) * n + b);
+      cp_async4(&sm.nz[buf][idx], noise + (size_t)b * L + k0 + idx);   // noise: [n][L] (transposed copy)
   };
 
   // shared-window addresses of the step loop's arrays, computed once (see lds64a)

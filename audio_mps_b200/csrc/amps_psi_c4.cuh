@@ -639,4 +639,176 @@ __global__ void __launch_bounds__(512)
   cluster_sync_all();
 }
 
+// -------------------------------------------------------------------------------------------
+// Sampler for bond dimensions 65..128 (model.py:242-251, 284-291): one waveform per 4-CTA cluster,
+// rows of N and R split as above.  The sampler feeds E(psi_k) back into the increment, so a step needs
+// every row's <x, R x> and |x|^2 BEFORE the new state exists -- two all-to-all exchanges per step if the
+// owners formed x_{k+1} themselves.  Here the owners broadcast the two mat-vec results a_i = (N x_k)_i,
+// y_i = (R x_k)_i (one 16-byte st.async per row and target CTA) and every CTA its partial
+// (sum conj(x_i) y_i, sum |x_i|^2) into the SAME mbarrier phase; after that single wait every thread has
+// s_k and the norm and forms the eight entries  x_{k+1,j} = c q_{k,j} (a_j + s_k y_j)  its next mat-vec
+// reads straight into registers (the state itself is never stored).  One intra-CTA barrier (partial
+// sums) and one cluster exchange per step.
+// -------------------------------------------------------------------------------------------
+template <int DP, int CL>
+struct alignas(16) SampleC4Smem {
+  float4 ay[2][DP];              // (a_j, y_j) of every row, by step parity
+  float2 part[2][CL];            // per-CTA (sum conj(x_i) y_i, sum |x_i|^2), by step parity
+  float2 qs[2][CH4][DP];         // q_k, double buffered by chunk
+  float nz[2][CH4];
+  float outs[CH4];
+  float2 wred[2][16];
+  unsigned long long xbar[2];
+};
+
+// grid = CL * n, cluster = CL, block = 512
+template <int DP, int CL>
+__global__ void __launch_bounds__(512)
+    psi_sample_c4_kernel(const float2* __restrict__ matN, const float2* __restrict__ matR,
+                         const float2* __restrict__ qtab, const float2* __restrict__ psi0p,
+                         const float* __restrict__ noise, int L, int n, float A, float dtf,
+                         float* __restrict__ out) {
+  using Cf = C4<DP, CL>;
+  constexpr int NQ = Cf::NQ, CPT = Cf::CPT, RP = Cf::RP, NTL = Cf::NTL;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SampleC4Smem<DP, CL>& sm = *reinterpret_cast<SampleC4Smem<DP, CL>*>(smem_raw);
+  const int t = threadIdx.x, il = t / NQ, jq = t % NQ, lane = t & 31, warp = t >> 5;
+  const unsigned rank = cluster_ctarank();
+  const int b = blockIdx.x / CL;
+  const int i = (int)rank * RP + il;
+  const int nchunks = (L + CH4 - 1) / CH4;
+
+  float2 Nr[CPT], Rr[CPT];
+  load_slice<DP, NQ>(Nr, matN, i, jq);
+  load_slice<DP, NQ>(Rr, matR, i, jq);
+
+  auto issue_loads = [&](int c, int buf) {
+    const int k0 = c * CH4, len = min(CH4, L - k0);
+    const float2* qsrc = qtab + (size_t)k0 * DP;
+    float2* qdst = &sm.qs[buf][0][0];
+    for (int idx = t; idx < len * DP / 2; idx += NTL) cp_async16(qdst + 2 * idx, qsrc + 2 * idx);
+    for (int idx = t; idx < len; idx += NTL) cp_async4(&sm.nz[buf][idx], noise + (size_t)b * L + k0 + idx);   // [n][L]
+  };
+  if (t == 0) {
+    mbar_init(&sm.xbar[0], 1);
+    mbar_init(&sm.xbar[1], 1);
+    mbar_fence_init_cluster();
+  }
+  if (nchunks > 0) issue_loads(0, 0);
+  cp_async_commit();
+  __syncthreads();
+  cluster_sync_all();   // every CTA's barriers are initialised before any remote st.async
+
+  constexpr unsigned STEP_TX = DP * sizeof(float4) + CL * sizeof(float2);
+  const bool bc_on = jq < CL;                              // lane jq < CL sends (a_i, y_i) to CTA jq
+  const unsigned ay_addr0 = dsmem_addr(&sm.ay[0][i], (unsigned)(jq & (CL - 1)));
+  const unsigned bar_addr0 = dsmem_addr(&sm.xbar[0], (unsigned)(jq & (CL - 1)));
+  const unsigned pt_addr0 = dsmem_addr(&sm.part[0][rank], (unsigned)(t & (CL - 1)));   // (threads t < CL)
+  const unsigned pb_addr0 = dsmem_addr(&sm.xbar[0], (unsigned)(t & (CL - 1)));
+
+  // mat-vec of the state held in registers (this thread's 8 columns) + exchange of step `sg`
+  float2 a_own = make_float2(0.f, 0.f), y_own = a_own, x_own = a_own;
+  int sg = 0;
+  auto matvec_and_send = [&](const float2 (&xv)[CPT]) {
+    const int p = sg & 1;
+    if (t == 0) mbar_arrive_expect_tx(&sm.xbar[p], STEP_TX);
+    float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+#pragma unroll
+    for (int cc = 0; cc < CPT; cc += 2) {
+      cmac(a0, Nr[cc], xv[cc]);
+      cmac(a1, Nr[cc + 1], xv[cc + 1]);
+      cmac(b0, Rr[cc], xv[cc]);
+      cmac(b1, Rr[cc + 1], xv[cc + 1]);
+    }
+    float4 ayv = make_float4(a0.x + a1.x, a0.y + a1.y, b0.x + b1.x, b0.y + b1.y);
+#pragma unroll
+    for (int m = 1; m < NQ; m <<= 1) {
+      ayv.x += __shfl_xor_sync(0xffffffffu, ayv.x, m);
+      ayv.y += __shfl_xor_sync(0xffffffffu, ayv.y, m);
+      ayv.z += __shfl_xor_sync(0xffffffffu, ayv.z, m);
+      ayv.w += __shfl_xor_sync(0xffffffffu, ayv.w, m);
+    }
+    a_own = make_float2(ayv.x, ayv.y);
+    y_own = make_float2(ayv.z, ayv.w);
+    if (bc_on) {
+      asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];\n" ::"r"(
+                       ay_addr0 + (unsigned)(p * DP * sizeof(float4))),
+                   "f"(ayv.x), "f"(ayv.y), "f"(ayv.z), "f"(ayv.w), "r"(bar_addr0 + (unsigned)(p * sizeof(unsigned long long)))
+                   : "memory");
+    }
+    // this CTA's partial of <x, R x> and |x|^2 (values replicated over a row's 16 lanes: two rows per warp)
+    float e = fmaf(x_own.x, y_own.x, x_own.y * y_own.y), nn = cabs2(x_own);
+    e += __shfl_xor_sync(0xffffffffu, e, 16);
+    nn += __shfl_xor_sync(0xffffffffu, nn, 16);
+    if (lane == 0) sm.wred[p][warp] = make_float2(e, nn);
+    __syncthreads();
+    if (t < CL) {
+      float es = 0.f, ns = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < NTL / 32; ++wv) {
+        es += sm.wred[p][wv].x;
+        ns += sm.wred[p][wv].y;
+      }
+      st_async_f2_if(true, pt_addr0 + (unsigned)(p * CL * sizeof(float2)), make_float2(es, ns),
+                     pb_addr0 + (unsigned)(p * sizeof(unsigned long long)));
+    }
+    ++sg;
+  };
+
+  // step 0's mat-vec: x_0 = psi_0
+  {
+    float2 xv[CPT];
+#pragma unroll
+    for (int cc = 0; cc < CPT; ++cc) xv[cc] = psi0p[Map<DP, NQ>::col(cc, jq)];
+    x_own = psi0p[i];
+    if (L > 0) matvec_and_send(xv);
+  }
+  float X = 0.f;
+  for (int c = 0; c < nchunks; ++c) {
+    const int buf = c & 1, k0 = c * CH4, len = min(CH4, L - k0);
+    if (c + 1 < nchunks) issue_loads(c + 1, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();   // q_k / noise of this chunk visible; outs flushed
+    for (int kk = 0; kk < len; ++kk) {
+      const int p = (sg - 1) & 1;
+      mbar_wait_cta(&sm.xbar[p], ((sg - 1) >> 1) & 1);     // (a, y) of every row and the four partials are in
+      float es = 0.f, nsum = 0.f;
+#pragma unroll
+      for (int r = 0; r < CL; ++r) {
+        const float2 pr = sm.part[p][r];
+        es += pr.x;
+        nsum += pr.y;
+      }
+      const float E = 2.0f * es / fmaxf(nsum, 1e-12f);                         // model.py:319-325
+      const float inc = __fadd_rn(__fmul_rn(E, dtf), sm.nz[buf][kk]);           // model.py:286
+      X = __fadd_rn(X, inc);                                                    // model.py:287
+      const float s = inc / A;                                                  // model.py:303
+      const float rn = rsqrtf(fmaxf(nsum, 1e-12f));   // lagged normalisation keeps |x| ~ 1
+      if (t == 0 && rank == 0) sm.outs[kk] = A * X;                             // model.py:251
+      const bool more = k0 + kk + 1 < L;
+      // x_{k+1}: own row from registers, the eight mat-vec columns from the broadcast vectors
+      {
+        const float2 xp = make_float2(fmaf(s, y_own.x, a_own.x) * rn, fmaf(s, y_own.y, a_own.y) * rn);
+        x_own = cmul(sm.qs[buf][kk][i], xp);
+      }
+      if (more) {
+        float2 xv[CPT];
+#pragma unroll
+        for (int cc = 0; cc < CPT; ++cc) {
+          const int col = Map<DP, NQ>::col(cc, jq);
+          const float4 v = sm.ay[p][col];
+          const float2 xp = make_float2(fmaf(s, v.z, v.x) * rn, fmaf(s, v.w, v.y) * rn);
+          xv[cc] = cmul(sm.qs[buf][kk][col], xp);
+        }
+        matvec_and_send(xv);
+      }
+    }
+    __syncthreads();
+    if (rank == 0 && t < len) out[(size_t)b * L + k0 + t] = sm.outs[t];
+  }
+  cp_async_wait<0>();
+  cluster_sync_all();   // no CTA leaves while a peer could still address its shared memory
+}
+
 }  // namespace amps

@@ -92,7 +92,7 @@ double amps_fma_peak_tflops2(amps_ctx* ctx, int packed);
 /* ---- PsiCMPS --------------------------------------------------------------------------- */
 
 /* Bond dimensions: loss, gradient and trajectory 1 <= D <= 128 (zero-padded to 8/16/32/64/128; above
- * 64 the matrices are row-split over a 4-CTA cluster); sampler and tensor-core scan D <= 64; Rho
+ * 64 the matrices are row-split over a 4-CTA cluster), sampler likewise; tensor-core scan D <= 64; Rho
  * D <= 32.  Anything else returns AMPS_E_UNSUPPORTED (and a workspace size of 0).
  *
  * bytes of caller-owned workspace for the Psi loss forward/backward at (D, B clips, T samples).

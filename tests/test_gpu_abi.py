@@ -47,12 +47,13 @@ def test_error_codes(cuda, lib):
     with pytest.raises(_lib.AmpsError) as e:
         m.loss_per_clip(np.zeros((2, 16), np.float32))
     assert e.value.code == -2                                       # AMPS_E_UNSUPPORTED
-    _, php = hp_pair(bond_dim=100)                                  # the sampler stops at D = 64
-    m = PsiCMPS(php, device=cuda)
-    with pytest.raises(_lib.AmpsError) as e:
+    with pytest.raises(_lib.AmpsError) as e:                        # ... and so does the sampler
         m.sample(2, 16)
     assert e.value.code == -2
-    with pytest.raises(_lib.AmpsError) as e:                        # ... and so does the tensor-core scan
+    _, php = hp_pair(bond_dim=100)
+    m = PsiCMPS(php, device=cuda)
+    assert m.sample(2, 16).shape == (2, 16)
+    with pytest.raises(_lib.AmpsError) as e:                        # the tensor-core scan stops at D = 64
         m.loss_per_clip_scan(np.zeros((2, 16), np.float32))
     assert e.value.code == -2
     h = _lib.context(0)

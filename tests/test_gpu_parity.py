@@ -85,7 +85,9 @@ def test_psi_weighted_grads_effective(cuda, lib):
 
 
 @pytest.mark.parametrize("D,n,L,over", [(2, 2, 512, dict(sigma=1.0, A=1.0)), (7, 5, 256, dict()),
-                                        (32, 3, 400, dict(sigma=0.01)), (64, 2, 100, dict())])
+                                        (32, 3, 400, dict(sigma=0.01)), (64, 2, 100, dict()),
+                                        # D > 64: one waveform per 4-CTA cluster (psi_sample_c4_kernel); ragged chunk
+                                        (100, 3, 131, dict()), (128, 5, 64, dict(sigma=0.01)), (65, 1, 17, dict())])
 def test_psi_sample_from_noise(cuda, lib, D, n, L, over):
     ohp, php = hp_pair(bond_dim=D, **over)
     if D == 2:  # the reference's two-level system (tests/test_model.py:145-152)
