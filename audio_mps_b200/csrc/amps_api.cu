@@ -242,7 +242,7 @@ PsiWs psi_ws_layout(int DP, int B, int nsteps_tab, int T, bool save) {
     {   // S x'_k and (E_k, |x_k|^2) from the forward
       w.sptraj = take((size_t)B * T * DP * sizeof(float2));   // S x'_k
       w.ev = take((size_t)B * T * sizeof(float2));            // (E_k, |x_k|^2)
-      w.lossp = take((size_t)B * tiles_nsplit(DP, B, nsteps) * sizeof(double));   // per-split loss sums (D = 33..64)
+      w.lossp = take((size_t)B * tiles_nsplit(DP, B, nsteps) * sizeof(double));   // per-split loss sums (D > 32)
     }
   }
   w.total = off;
@@ -531,6 +531,8 @@ cudaError_t amps_set_all_func_attrs() {
   if ((e = set_smem(psi_tiles_tc_kernel<64, 1>, sizeof(TilesSmem<64, 1>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_fwd_uni_kernel<64, 8, false, true>, sizeof(FwdSmemUni<64, 8>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_sx_tc_kernel<64>, sizeof(SxSmem<64>) + 1024)) != cudaSuccess) return e;
+  if ((e = set_smem(psi_sx2_tc_kernel, sizeof(Sx2Smem) + 1024)) != cudaSuccess) return e;
+  if ((e = set_smem(psi_fwd_c4_kernel<128, C4_CL, false, true>, sizeof(FwdC4Smem<128, C4_CL>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_tiles_tc_kernel<128, 1>, sizeof(TilesSmem<128, 1>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_tiles_tc_kernel<128, 2>, sizeof(TilesSmem<128, 2>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_tiles_tc_kernel<128, 3>, sizeof(TilesSmem<128, 3>) + 1024)) != cudaSuccess) return e;
@@ -558,6 +560,35 @@ int launch_psi_fwd(amps_ctx* ctx, int DP, int B, const FwdArgs& a, cudaStream_t 
   const int chl = chunk_len_of(DP);
   const int nchunks = (nsteps + chl - 1) / chl;
   const Fam fam = family_of(ctx, DP, B);
+  auto sx_args = [&]() {
+    SxArgs g{};
+    g.matS = a.matS;
+    g.sptraj = a.sptraj;
+    g.ev = a.ev;
+    g.x = a.x;
+    g.loss_part = a.loss_part;
+    g.T = a.T;
+    g.xstride = a.seg.xstride;
+    g.nsplit = a.sx_nsplit;
+    g.steps_per_split = a.sx_sps;
+    g.A = a.A;
+    return g;
+  };
+  const bool sxo = ctx->tc_tiles && a.traj && a.sptraj && a.loss_part;   // chain-only forward + tensor-core expectation pass
+  if (fam == Fam::C4 && sxo) {
+    CUDA_TRY(ctx, launch_cluster(psi_fwd_c4_kernel<128, C4_CL, false, true>, B, C4_CL, 512, sizeof(FwdC4Smem<128, C4_CL>), st,
+                                 a.matN, a.matR, a.matS, a.qtab, a.psi0p, a.x, a.T, a.A, a.loss, a.lossd, a.traj,
+                                 a.scales, nchunks, (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg));
+    LAUNCH_CHECK(ctx, "psi_fwd_c4_kernel<chain>");
+    const SxArgs g = sx_args();
+    PROF_BEGIN(ctx, 2, st);
+    psi_sx2_tc_kernel<<<B * g.nsplit, SX_BLOCK, sizeof(Sx2Smem) + 1024, st>>>(g);
+    PROF_END(ctx, 2, st);
+    LAUNCH_CHECK(ctx, "psi_sx2_tc_kernel");
+    psi_scan_sum_kernel<<<(B + 127) / 128, 128, 0, st>>>(a.loss_part, B, g.nsplit, a.loss, a.lossd);
+    LAUNCH_CHECK(ctx, "psi_scan_sum_kernel");
+    return AMPS_OK;
+  }
   if (fam == Fam::C4) {   // rows of N, R, S split over a 4-CTA cluster per clip
     CUDA_TRY(ctx, launch_cluster(psi_fwd_c4_kernel<128, C4_CL, false>, B, C4_CL, 512, sizeof(FwdC4Smem<128, C4_CL>), st,
                                  a.matN, a.matR, a.matS, a.qtab, a.psi0p, a.x, a.T, a.A, a.loss, a.lossd, a.traj,
@@ -579,24 +610,14 @@ int launch_psi_fwd(amps_ctx* ctx, int DP, int B, const FwdArgs& a, cudaStream_t 
       psi_fwd_kernel<DPc, NQc><<<B, 2 * DPc * NQc, sizeof(FwdSmem<DPc, NQc>), st>>>(
           a.matN, a.matR, a.matS, a.qtab, a.psi0p, a.x, a.T, a.A, a.loss, a.lossd, a.traj, a.scales, nchunks,
           a.sptraj, a.ev, a.seg);
-    } else if (ctx->tc_tiles && a.traj && a.sptraj && a.loss_part) {
+    } else if (sxo) {
       // chain-only forward (x'_k and |x_k|^2 stored), then S x'_k, E_k and the loss as ONE GEMM over the time
       // axis on the tensor cores, in place
       psi_fwd_uni_kernel<DPc, NQc, false, true><<<B, DPc * NQc, sizeof(FwdSmemUni<DPc, NQc>), st>>>(
           a.matN, a.matR, a.matS, a.qtab, a.psi0p, a.x, a.T, a.A, a.loss, a.lossd, a.traj, a.scales, nchunks,
           (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg);
       LAUNCH_CHECK(ctx, "psi_fwd_uni_kernel<chain>");
-      SxArgs g{};
-      g.matS = a.matS;
-      g.sptraj = a.sptraj;
-      g.ev = a.ev;
-      g.x = a.x;
-      g.loss_part = a.loss_part;
-      g.T = a.T;
-      g.xstride = a.seg.xstride;
-      g.nsplit = a.sx_nsplit;
-      g.steps_per_split = a.sx_sps;
-      g.A = a.A;
+      const SxArgs g = sx_args();
       PROF_BEGIN(ctx, 2, st);
       psi_sx_tc_kernel<DPc><<<B * g.nsplit, SX_BLOCK, sizeof(SxSmem<DPc>) + 1024, st>>>(g);
       PROF_END(ctx, 2, st);

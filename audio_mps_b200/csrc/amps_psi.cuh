@@ -553,6 +553,7 @@ using FalseT = std::false_type;
 using IC0 = std::integral_constant<int, 0>;
 using IC1 = std::integral_constant<int, 1>;
 using IC2 = std::integral_constant<int, 2>;
+using IC3 = std::integral_constant<int, 3>;
 
 template <int DP, int NQ>
 struct alignas(16) FwdSmemUni {

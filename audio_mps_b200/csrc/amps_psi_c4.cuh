@@ -51,7 +51,9 @@ struct alignas(16) FwdC4Smem {
 
 // grid = CL * (number of clips or virtual clips), cluster = CL, block = 512.
 // VIRT: virtual-clip mode of the parallel-in-time scan, as in psi_fwd_uni_kernel.
-template <int DP, int CL, bool VIRT>
+// SXO: chain only -- x'_k goes where S x'_k would and |x_k|^2 into ev[k].y; S x'_k, E_k and the loss come from
+// psi_sx_tc_kernel afterwards (no S mat-vec, no per-chunk exchange of partial sums between the CTAs).
+template <int DP, int CL, bool VIRT, bool SXO = false>
 __global__ void __launch_bounds__(512)
     psi_fwd_c4_kernel(const float2* __restrict__ matN, const float2* __restrict__ matR,
                       const float2* __restrict__ matS, const float2* __restrict__ qtab_,
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(512)
   float2 Nr[CPT], Rr[CPT], Sr[CPT];
   load_slice<DP, NQ>(Nr, matN, i, jq);
   load_slice<DP, NQ>(Rr, matR, i, jq);
-  load_slice<DP, NQ>(Sr, matS, i, jq);
+  if (!SXO) load_slice<DP, NQ>(Sr, matS, i, jq);
 
   if (t < DP) {
     const float2 p = psi0p[t];
@@ -162,6 +164,7 @@ __global__ void __launch_bounds__(512)
     auto step = [&](auto stage_tag, int kk) {
       constexpr int STAGE = decltype(stage_tag)::value;
       constexpr bool FIRST = STAGE == 0;
+      constexpr bool EXPC = STAGE == 1 || STAGE == 2;   // expectation pipeline (stage 3: chain only, not first)
       if (t == 0) mbar_arrive_expect_tx(&sm.xbar[sg & 1], STEP_TX);          // arm this step's phase
       if (!FIRST) mbar_wait_cta(&sm.xbar[(sg - 1) & 1], ((sg - 1) >> 1) & 1);    // previous step's rows are in
       float2 xv[CPT], pv[CPT];
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(512)
         xv[2 * m] = make_float2(v.x, v.y);
         xv[2 * m + 1] = make_float2(v.z, v.w);
       }
-      if (!FIRST) {
+      if (EXPC) {
 #pragma unroll
         for (int m = 0; m < CPT / 2; ++m) {
           const float4 v = *reinterpret_cast<const float4*>(&sm.xps[kk - 1][2 * NQ * m + 2 * jq]);
@@ -182,7 +185,7 @@ __global__ void __launch_bounds__(512)
       const float2 q = sm.qs[buf][kk][i];
       const float s_next = sm.sv[buf][kk + 1];
       float red = 0.f;
-      if (STAGE >= 2) {   // row reduction of step kk-2's partial, level 1
+      if (STAGE == 2) {   // row reduction of step kk-2's partial, level 1
         const bool odd = jq & 1;
         red = (odd ? part_pp.y : part_pp.x) + __shfl_xor_sync(0xffffffffu, odd ? part_pp.x : part_pp.y, 1);
       }
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(512)
         cmac(a1, L[cc + 1], xv[cc + 1]);
       }
       float2 xp = make_float2(a0.x + a1.x, a0.y + a1.y);
-      if (STAGE >= 2) {
+      if (STAGE == 2) {
         red += __shfl_xor_sync(0xffffffffu, red, 2);
         red += __shfl_xor_sync(0xffffffffu, red, 4);
       }
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(512)
       for (int lv = 0; lv < LV; ++lv) {
         const float ox = __shfl_xor_sync(0xffffffffu, xp.x, 1 << lv);
         const float oy = __shfl_xor_sync(0xffffffffu, xp.y, 1 << lv);
-        if (!FIRST) {
+        if (EXPC) {
 #pragma unroll
           for (int cc = lv * CPL; cc < (lv + 1) * CPL && cc < CPT; ++cc) {
             if (cc & 1) cmac(p1, Sr[cc], pv[cc]);
@@ -222,27 +225,31 @@ __global__ void __launch_bounds__(512)
       const float2 xn = cmul(q, xp);
       st_async_f2_if(st_on, st_addr0 + (unsigned)(kk * DP * (int)sizeof(float2)), st_x ? xn : xp,
                      st_bar0 + (unsigned)((sg & 1) * sizeof(unsigned long long)));
-      if (!FIRST) sm.es[kk - 1][t] = fmaf(xp_prev.x, p0.x + p1.x, xp_prev.y * (p0.y + p1.y));
-      if (STAGE >= 2) {
+      if (EXPC) sm.es[kk - 1][t] = fmaf(xp_prev.x, p0.x + p1.x, xp_prev.y * (p0.y + p1.y));
+      if (STAGE == 2) {
         red += __shfl_xor_sync(0xffffffffu, red, 8);
         sts_if(ex_on, spf_st + (kk - 2) * (2 * RP), red);
       }
-      if (!FIRST) part_pp = make_float2(p0.x + p1.x, p0.y + p1.y);
+      if (EXPC) part_pp = make_float2(p0.x + p1.x, p0.y + p1.y);
       xp_prev = xp;
       s_cur = s_next;
       ++sg;
     };
 
     step(IC0{}, 0);
-    if (len > 1) step(IC1{}, 1);
-    if (len == CH4) {
-#pragma unroll 2
-      for (int kk = 2; kk < CH4; ++kk) step(IC2{}, kk);
+    if (SXO) {
+      for (int kk = 1; kk < len; ++kk) step(IC3{}, kk);
     } else {
-      for (int kk = 2; kk < len; ++kk) step(IC2{}, kk);
+      if (len > 1) step(IC1{}, 1);
+      if (len == CH4) {
+#pragma unroll 2
+        for (int kk = 2; kk < CH4; ++kk) step(IC2{}, kk);
+      } else {
+        for (int kk = 2; kk < len; ++kk) step(IC2{}, kk);
+      }
     }
     mbar_wait_cta(&sm.xbar[(sg - 1) & 1], ((sg - 1) >> 1) & 1);   // the chunk's last broadcast has landed
-    {  // drain: step len-2's partial is in part_pp; the chunk's last step has none yet
+    if (!SXO) {  // drain: step len-2's partial is in part_pp; the chunk's last step has none yet
       if (len >= 2) sts_if(ex_on, spf_st + (len - 2) * (2 * RP), pair_reduce<NQ>(part_pp, jq));
       const float2 part = matvec1<DP, NQ>(Sr, sm.xps[len - 1], jq);
       sm.es[len - 1][t] = fmaf(xp_prev.x, part.x, xp_prev.y * part.y);
@@ -251,18 +258,37 @@ __global__ void __launch_bounds__(512)
     cp_async_wait<0>();
     __syncthreads();  // (A)
 
+    if (!SXO) {
     {  // this CTA's partial of Re(x'^dag S x') for step `warp`, handed to every CTA of the cluster
-      const int kk = warp;
-      float en = 0.f;
-      if (kk < len) {
+        const int kk = warp;
+        float en = 0.f;
+        if (kk < len) {
 #pragma unroll
-        for (int r = 0; r < NTL / 32; ++r) en += sm.es[kk][lane + 32 * r];
+          for (int r = 0; r < NTL / 32; ++r) en += sm.es[kk][lane + 32 * r];
+        }
+        en = warp_sum_f(en);
+        if (lane < CL && kk < len) st_dsmem_f1(dsmem_addr(&sm.enx[rank][kk], (unsigned)lane), en);
       }
-      en = warp_sum_f(en);
-      if (lane < CL && kk < len) st_dsmem_f1(dsmem_addr(&sm.enx[rank][kk], (unsigned)lane), en);
-    }
-    cluster_sync_all();  // (X1)
-    {  // per-step scalars, identical on every CTA (same operands, same order)
+      cluster_sync_all();  // (X1)
+      {  // per-step scalars, identical on every CTA (same operands, same order)
+        const int kk = warp;
+        float nu2 = 0.f;
+        if (kk < len) {
+#pragma unroll
+          for (int r = 0; r < DP / 32; ++r) nu2 += cabs2(sm.xs[kk][lane + 32 * r]);
+        }
+        nu2 = warp_sum_f(nu2);
+        if (lane == 0 && kk < len) {
+          float en = 0.f;
+#pragma unroll
+          for (int r = 0; r < CL; ++r) en += sm.enx[r][kk];
+          const float E = en / fmaxf(nu2, 1e-12f);                                  // model.py:324-325 on x'
+          const float z = (E * sm.incv[buf][kk]) / A;                // model.py:294
+          lossacc -= (double)log1pf(z);
+          sm.evs[kk] = make_float2(E, nu2);
+        }
+      }
+    } else {   // |x_k|^2 per step (E_k: psi_sx_tc_kernel)
       const int kk = warp;
       float nu2 = 0.f;
       if (kk < len) {
@@ -270,15 +296,7 @@ __global__ void __launch_bounds__(512)
         for (int r = 0; r < DP / 32; ++r) nu2 += cabs2(sm.xs[kk][lane + 32 * r]);
       }
       nu2 = warp_sum_f(nu2);
-      if (lane == 0 && kk < len) {
-        float en = 0.f;
-#pragma unroll
-        for (int r = 0; r < CL; ++r) en += sm.enx[r][kk];
-        const float E = en / fmaxf(nu2, 1e-12f);                                  // model.py:324-325 on x'
-        const float z = (E * sm.incv[buf][kk]) / A;                // model.py:294
-        lossacc -= (double)log1pf(z);
-        sm.evs[kk] = make_float2(E, nu2);
-      }
+      if (lane == 0 && kk < len) sm.evs[kk] = make_float2(0.f, nu2);
     }
     if (c + 1 < nchunks) compute_s(buf ^ 1, min(CH4, nsteps - (k0 + CH4)));
     // rescale by 1/|x_{k0+len}| (every warp of every CTA computes the same norm)
@@ -304,7 +322,8 @@ __global__ void __launch_bounds__(512)
         for (int idx = t; idx < len * RP / 2; idx += NTL) {
           const int kk = idx / (RP / 2), r2 = idx % (RP / 2);
           *reinterpret_cast<float4*>(sptraj + ((size_t)b * tstride + k0 + kk) * DP + (int)rank * RP + 2 * r2) =
-              *reinterpret_cast<const float4*>(&sm.sps[kk][2 * r2]);
+              SXO ? *reinterpret_cast<const float4*>(&sm.xps[kk][(int)rank * RP + 2 * r2])
+                  : *reinterpret_cast<const float4*>(&sm.sps[kk][2 * r2]);
         }
         if (rank == 0 && t < len) evout[(size_t)b * tstride + k0 + t] = sm.evs[t];
       }
@@ -314,7 +333,7 @@ __global__ void __launch_bounds__(512)
   lossacc = warp_sum_d(lossacc);
   if (lane == 0) sm.lred[warp] = lossacc;
   __syncthreads();
-  if (t == 0 && rank == 0) {
+  if (t == 0 && rank == 0 && !SXO) {
     double tot = 0.0;
     for (int wv = 0; wv < NTL / 32; ++wv) tot += sm.lred[wv];
     if (loss) loss[b] = (float)tot;

@@ -238,4 +238,223 @@ __global__ void __launch_bounds__(SX_BLOCK, 1) psi_sx_tc_kernel(SxArgs g) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;\n" ::"r"(tmem));
 }
 
+
+// -------------------------------------------------------------------------------------------
+// D = 65..128: S in real form is 256 x 256 (512 KB with its lo part) -- it cannot stay in shared memory.
+// The CTA walks its steps in BLOCKS of 256 (8 tiles of 32 steps) and, per block, through four phases
+// (output-row half mh, contraction half kh): a phase stages the 128 x 128 quadrant S[mh][kh] (hi + lo,
+// 128 KB) once and runs the block's 8 tiles against it, accumulating into 16 accumulators of 32 columns
+// (2 halves x 8 tiles = all 512 columns of tensor memory).  Only after the fourth phase are the rows
+// rewritten (x' -> S x', both halves), so the in-place update never overtakes a read.  Re-staging S costs
+// 2 KB of shared-memory stores per step against 30 KB of operand reads by the MMAs.
+// -------------------------------------------------------------------------------------------
+constexpr int SX2_TPB = 8;             // tiles per block
+struct alignas(1024) Sx2Smem {
+  uint8_t a_hi[4][128 * TL_ROWB];      // S[mh][kh] quadrant, K blocks of 32
+  uint8_t a_lo[4][128 * TL_ROWB];
+  uint8_t b[2][4][SX_NS * TL_ROWB];    // x' tile, one contraction half, hi
+  uint8_t b_lo[2][4][SX_NS * TL_ROWB];
+  float outs[SX_NS][128 + 4];
+  float esum[SX2_TPB * SX_NS];         // sum_i Re(conj(x'_i) (S x')_i) per step of the block
+  double lred[16];
+  unsigned long long a_full, a_empty, b_full[2], b_empty[2], acc_full, acc_empty;
+  uint32_t tmem_base;
+};
+
+// grid = B * nsplit, block = 544; steps_per_split: multiple of 256
+__global__ void __launch_bounds__(SX_BLOCK, 1) psi_sx2_tc_kernel(SxArgs g) {
+  constexpr int DP = 128, KR = 256, BLK = SX2_TPB * SX_NS;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem_al = smem_raw + ((1024u - (tc_smem_u32(smem_raw) & 1023u)) & 1023u);
+  Sx2Smem& sm = *reinterpret_cast<Sx2Smem*>(smem_al);
+  const float A = a_get(g.A);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x / g.nsplit, sp = blockIdx.x % g.nsplit;
+  const int nsteps = g.T - 1;
+  const int k_begin = sp * g.steps_per_split;
+  const int nloc = max(0, min(g.steps_per_split, nsteps - k_begin));
+  const int nblk = (nloc + BLK - 1) / BLK;
+  float* rows = reinterpret_cast<float*>(g.sptraj + ((size_t)b * g.T + k_begin) * DP);
+  float2* evb = g.ev + (size_t)b * g.T + k_begin;
+  const float* xb = g.x + (size_t)b * g.xstride + k_begin;
+
+  if (tid == 0) {
+    mbar_init(&sm.a_full, SX_THREADS);
+    mbar_init(&sm.a_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sm.b_full[s], SX_THREADS);
+      mbar_init(&sm.b_empty[s], 1);
+    }
+    mbar_init(&sm.acc_full, 1);
+    mbar_init(&sm.acc_empty, SX_THREADS);
+    mbar_fence_init_cluster();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(tc_smem_u32(&sm.tmem_base)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = sm.tmem_base;
+  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(SX_NS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  auto ntile_of = [&](int blk) { return (min(BLK, nloc - blk * BLK) + SX_NS - 1) / SX_NS; };
+
+  if (warp == SX_THREADS / 32) {
+    // ---- MMA warp -----------------------------------------------------------------------------
+    if (lane == 0) {
+      int gp = 0, jb = 0;      // phases and B tiles so far (barrier parities)
+      for (int blk = 0; blk < nblk; ++blk) {
+        const int nt = ntile_of(blk);
+        if (blk > 0) mbar_wait_cta(&sm.acc_empty, (blk - 1) & 1);     // the previous block is drained
+        for (int mh = 0; mh < 2; ++mh)
+          for (int kh = 0; kh < 2; ++kh, ++gp) {
+            mbar_wait_cta(&sm.a_full, gp & 1);
+            for (int tl = 0; tl < nt; ++tl, ++jb) {
+              const int s = jb & 1;
+              mbar_wait_cta(&sm.b_full[s], (jb >> 1) & 1);
+              asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+              bool first = kh == 0;
+#pragma unroll 1
+              for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll 1
+                for (int kb = 0; kb < 4; ++kb) {
+                  const uint64_t da0 = tc_make_desc(tc_smem_u32(pass == 1 ? sm.a_lo[kb] : sm.a_hi[kb]));
+                  const uint64_t db0 = tc_make_desc(tc_smem_u32(pass == 2 ? sm.b_lo[s][kb] : sm.b[s][kb]));
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks) {
+                    tl_mma_ss(tmem + (uint32_t)((mh * SX2_TPB + tl) * SX_NS), da0 + 2 * ks, db0 + 2 * ks, idesc, first ? 0u : 1u);
+                    first = false;
+                  }
+                }
+              }
+              tl_commit(&sm.b_empty[s]);
+            }
+            tl_commit(&sm.a_empty);
+          }
+        tl_commit(&sm.acc_full);
+      }
+    }
+  } else {
+    // ---- worker warps ---------------------------------------------------------------------------
+    double lossacc = 0.0;
+    const int q4 = warp & 3, cg = warp >> 2;
+    int gp = 0, jb = 0;
+    for (int blk = 0; blk < nblk; ++blk) {
+      const int n0b = blk * BLK, nt = ntile_of(blk);
+      for (int mh = 0; mh < 2; ++mh)
+        for (int kh = 0; kh < 2; ++kh, ++gp) {
+          // S[mh][kh]: rows 2i+c of the half (i = 64 mh ..), contraction columns 2j+c' (j = 64 kh ..)
+          if (gp > 0) mbar_wait_cta(&sm.a_empty, (gp - 1) & 1);
+          for (int idx = tid; idx < 64 * 32; idx += SX_THREADS) {   // (row i of 64, pair of columns j, j+1 of 64)
+            const int il = idx / 32, jl = 2 * (idx % 32);
+            const float2* srow = g.matS + (size_t)(64 * mh + il) * DP + 64 * kh + jl;
+            const float2 s0 = srow[0], s1 = srow[1];
+            const float r0[4] = {s0.x, -s0.y, s1.x, -s1.y};
+            const float r1[4] = {s0.y, s0.x, s1.y, s1.x};
+            const int kb = (2 * jl) / 32, ch = ((2 * jl) % 32) / 4;
+            auto put = [&](int row, const float (&v)[4]) {
+              const float4 h = make_float4(tc_trunc_tf32(v[0]), tc_trunc_tf32(v[1]), tc_trunc_tf32(v[2]), tc_trunc_tf32(v[3]));
+              const int o = tl_off(row, ch);
+              *reinterpret_cast<float4*>(sm.a_hi[kb] + o) = h;
+              *reinterpret_cast<float4*>(sm.a_lo[kb] + o) = make_float4(v[0] - h.x, v[1] - h.y, v[2] - h.z, v[3] - h.w);
+            };
+            put(2 * il, r0);
+            put(2 * il + 1, r1);
+          }
+          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+          tl_mbar_arrive(&sm.a_full);
+          // the block's tiles, contraction half kh: 32 rows x 128 floats = 1024 16-byte chunks, 2 per thread
+          for (int tl = 0; tl < nt; ++tl, ++jb) {
+            const int s = jb & 1;
+            const int n0 = n0b + tl * SX_NS, len = min(SX_NS, nloc - n0);
+            float4 pre[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int idx = tid + q * SX_THREADS;
+              const int n = idx / 32, c4 = idx % 32;
+              pre[q] = (n < len) ? *reinterpret_cast<const float4*>(rows + (size_t)(n0 + n) * KR + 128 * kh + 4 * c4)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (jb >= 2) mbar_wait_cta(&sm.b_empty[s], ((jb >> 1) - 1) & 1);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int idx = tid + q * SX_THREADS;
+              const int n = idx / 32, c4 = idx % 32;
+              const int kb = c4 / 8, ch = c4 % 8;
+              const float4 v = pre[q];
+              const float4 h = make_float4(tc_trunc_tf32(v.x), tc_trunc_tf32(v.y), tc_trunc_tf32(v.z), tc_trunc_tf32(v.w));
+              *reinterpret_cast<float4*>(sm.b[s][kb] + tl_off(n, ch)) = h;
+              *reinterpret_cast<float4*>(sm.b_lo[s][kb] + tl_off(n, ch)) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+            }
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            tl_mbar_arrive(&sm.b_full[s]);
+          }
+        }
+      // ---- drain the block: 2 halves x nt tiles ---------------------------------------------------
+      mbar_wait_cta(&sm.acc_full, blk & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      for (int mh = 0; mh < 2; ++mh)
+        for (int tl = 0; tl < nt; ++tl) {
+          const int n0 = n0b + tl * SX_NS, len = min(SX_NS, nloc - n0);
+          {
+            uint32_t r[8];
+            const uint32_t taddr = tmem + ((uint32_t)(32 * q4) << 16) + (uint32_t)((mh * SX2_TPB + tl) * SX_NS + 8 * cg);
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                         : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            const int m = 32 * q4 + lane;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sm.outs[8 * cg + e][m] = __uint_as_float(r[e]);
+          }
+          bar_named(5, SX_THREADS);
+          {
+            const int n = tid >> 4, part = tid & 15;
+            float e = 0.f;
+            if (n < len) {
+              float* gp_ = rows + (size_t)(n0 + n) * KR + 128 * mh + 8 * part;
+              const float4 x0 = *reinterpret_cast<const float4*>(gp_), x1 = *reinterpret_cast<const float4*>(gp_ + 4);
+              const float4 o0 = *reinterpret_cast<const float4*>(&sm.outs[n][8 * part]);
+              const float4 o1 = *reinterpret_cast<const float4*>(&sm.outs[n][8 * part + 4]);
+              e = x0.x * o0.x + x0.y * o0.y + x0.z * o0.z + x0.w * o0.w + x1.x * o1.x + x1.y * o1.y + x1.z * o1.z + x1.w * o1.w;
+              *reinterpret_cast<float4*>(gp_) = o0;
+              *reinterpret_cast<float4*>(gp_ + 4) = o1;
+            }
+            e += __shfl_xor_sync(0xffffffffu, e, 1);
+            e += __shfl_xor_sync(0xffffffffu, e, 2);
+            e += __shfl_xor_sync(0xffffffffu, e, 4);
+            e += __shfl_xor_sync(0xffffffffu, e, 8);
+            if (part == 0 && n < len) sm.esum[tl * SX_NS + n] = (mh == 0 ? 0.f : sm.esum[tl * SX_NS + n]) + e;
+          }
+          bar_named(5, SX_THREADS);
+        }
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      tl_mbar_arrive(&sm.acc_empty);      // every accumulator of the block has been read
+      {
+        const int nb = min(BLK, nloc - n0b);
+        if (tid < nb) {
+          const float nu2 = evb[n0b + tid].y;
+          const float E = sm.esum[tid] / fmaxf(nu2, 1e-12f);                // model.py:324-325 on x'
+          const float inc = xb[n0b + tid + 1] - xb[n0b + tid];
+          lossacc -= (double)log1pf((E * inc) / A);                         // model.py:294
+          evb[n0b + tid] = make_float2(E, nu2);
+        }
+      }
+      bar_named(5, SX_THREADS);
+    }
+    lossacc = warp_sum_d(lossacc);
+    if (lane == 0) sm.lred[warp] = lossacc;
+    bar_named(5, SX_THREADS);
+    if (tid == 0) {
+      double tot = 0.0;
+      for (int wv = 0; wv < SX_THREADS / 32; ++wv) tot += sm.lred[wv];
+      g.loss_part[blockIdx.x] = tot;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem));
+}
+
 }  // namespace amps
