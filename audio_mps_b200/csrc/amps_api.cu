@@ -320,6 +320,14 @@ int rho_tables(amps_ctx* ctx, const amps_params* p, int nsteps, bool need_p, cha
 }  // namespace
 
 cudaError_t amps_set_all_func_attrs();   // defined with the launch helpers below
+// second stream of a context (forward replay of the checkpointed backward, tensor-core pass of finished
+// waves): lowest priority, so that the latency-bound chain kernels on the caller's stream get their SMs first
+static cudaError_t create_aux_stream(cudaStream_t* s) {
+  int least = 0, greatest = 0;
+  cudaError_t e = cudaDeviceGetStreamPriorityRange(&least, &greatest);
+  if (e != cudaSuccess) return e;
+  return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, least);
+}
 
 // ------------------------------------------------------------------------------------------
 extern "C" {
@@ -348,7 +356,7 @@ int amps_create(int device, amps_ctx** out) {
   // everything the device entry points need besides the caller's buffers is created HERE: kernel
   // attributes, the replay stream and its events (no allocation, no attribute call per launch)
   bool ok = amps_set_all_func_attrs() == cudaSuccess &&
-            cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            create_aux_stream(&ctx->aux_stream) == cudaSuccess &&
             cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; i < 2 && ok; ++i)
     ok = cudaEventCreateWithFlags(&ctx->ev_replay[i], cudaEventDisableTiming) == cudaSuccess &&
@@ -466,8 +474,9 @@ struct FwdArgs {
   float2* sptraj;
   float2* ev;
   SegFwd seg;
-  double* loss_part = nullptr;   // D = 33..64 saving forward: per-split loss sums of psi_sx_tc_kernel
+  double* loss_part = nullptr;   // D > 32 saving forward: per-split loss sums of the expectation pass
   int sx_nsplit = 1, sx_sps = 0;
+  bool allow_split = false;      // whole-batch call on the caller's stream: partial waves may be pipelined
 };
 struct BwdArgs {
   const float2 *matN, *matRH, *matS, *qtab;
@@ -485,8 +494,9 @@ struct BwdArgs {
   const float2* sptraj;
   const float2* ev;
   SegBwd seg;
-  int tiles_nsplit = 1;        // partial tile sets per clip in G (D = 33..64 tensor-core tile kernel)
+  int tiles_nsplit = 1;        // partial tile sets per clip in G (D > 32: tensor-core tile kernel)
   int tiles_sps = 0;           // steps per split (multiple of 32)
+  bool allow_split = false;
 };
 
 // which kernel family serves (DP, B) on this context
@@ -555,7 +565,8 @@ cudaError_t amps_set_all_func_attrs() {
 }
 namespace {
 
-int launch_psi_fwd(amps_ctx* ctx, int DP, int B, const FwdArgs& a, cudaStream_t st) {
+// phase (tensor-core paths only): 0 = everything, 1 = the sequential chain kernel, 2 = the GEMM pass after it
+int launch_psi_fwd(amps_ctx* ctx, int DP, int B, const FwdArgs& a, cudaStream_t st, int phase = 0) {
   const int nsteps = a.T - 1;
   const int chl = chunk_len_of(DP);
   const int nchunks = (nsteps + chl - 1) / chl;
@@ -576,10 +587,13 @@ int launch_psi_fwd(amps_ctx* ctx, int DP, int B, const FwdArgs& a, cudaStream_t 
   };
   const bool sxo = ctx->tc_tiles && a.traj && a.sptraj && a.loss_part;   // chain-only forward + tensor-core expectation pass
   if (fam == Fam::C4 && sxo) {
-    CUDA_TRY(ctx, launch_cluster(psi_fwd_c4_kernel<128, C4_CL, false, true>, B, C4_CL, 512, sizeof(FwdC4Smem<128, C4_CL>), st,
-                                 a.matN, a.matR, a.matS, a.qtab, a.psi0p, a.x, a.T, a.A, a.loss, a.lossd, a.traj,
-                                 a.scales, nchunks, (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg));
-    LAUNCH_CHECK(ctx, "psi_fwd_c4_kernel<chain>");
+    if (phase != 2) {
+      CUDA_TRY(ctx, launch_cluster(psi_fwd_c4_kernel<128, C4_CL, false, true>, B, C4_CL, 512, sizeof(FwdC4Smem<128, C4_CL>), st,
+                                   a.matN, a.matR, a.matS, a.qtab, a.psi0p, a.x, a.T, a.A, a.loss, a.lossd, a.traj,
+                                   a.scales, nchunks, (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg));
+      LAUNCH_CHECK(ctx, "psi_fwd_c4_kernel<chain>");
+    }
+    if (phase == 1) return AMPS_OK;
     const SxArgs g = sx_args();
     PROF_BEGIN(ctx, 2, st);
     psi_sx2_tc_kernel<<<B * g.nsplit, SX_BLOCK, sizeof(Sx2Smem) + 1024, st>>>(g);
@@ -613,10 +627,13 @@ int launch_psi_fwd(amps_ctx* ctx, int DP, int B, const FwdArgs& a, cudaStream_t 
     } else if (sxo) {
       // chain-only forward (x'_k and |x_k|^2 stored), then S x'_k, E_k and the loss as ONE GEMM over the time
       // axis on the tensor cores, in place
-      psi_fwd_uni_kernel<DPc, NQc, false, true><<<B, DPc * NQc, sizeof(FwdSmemUni<DPc, NQc>), st>>>(
-          a.matN, a.matR, a.matS, a.qtab, a.psi0p, a.x, a.T, a.A, a.loss, a.lossd, a.traj, a.scales, nchunks,
-          (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg);
-      LAUNCH_CHECK(ctx, "psi_fwd_uni_kernel<chain>");
+      if (phase != 2) {
+        psi_fwd_uni_kernel<DPc, NQc, false, true><<<B, DPc * NQc, sizeof(FwdSmemUni<DPc, NQc>), st>>>(
+            a.matN, a.matR, a.matS, a.qtab, a.psi0p, a.x, a.T, a.A, a.loss, a.lossd, a.traj, a.scales, nchunks,
+            (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg);
+        LAUNCH_CHECK(ctx, "psi_fwd_uni_kernel<chain>");
+      }
+      if (phase == 1) return AMPS_OK;
       const SxArgs g = sx_args();
       PROF_BEGIN(ctx, 2, st);
       psi_sx_tc_kernel<DPc><<<B * g.nsplit, SX_BLOCK, sizeof(SxSmem<DPc>) + 1024, st>>>(g);
@@ -635,7 +652,7 @@ int launch_psi_fwd(amps_ctx* ctx, int DP, int B, const FwdArgs& a, cudaStream_t 
   });
 }
 
-int launch_psi_bwd(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t st) {
+int launch_psi_bwd(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t st, int phase = 0) {
   const int nsteps = a.T - 1;
   const int chl = chunk_len_of(DP);
   const int nchunks = (nsteps + chl - 1) / chl;
@@ -663,11 +680,14 @@ int launch_psi_bwd(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t 
     return g;
   };
   if (fam == Fam::C4 && ctx->tc_tiles) {
-    CUDA_TRY(ctx, launch_cluster(psi_bwd_c4_kernel<128, C4_CL, false, false>, B, C4_CL, 512, sizeof(BwdC4Smem<128, C4_CL>), st,
-                                 a.matN, a.matRH, a.matS, a.qtab, a.ttab, a.x, a.T, a.A, a.w, a.traj, a.scales, nchunks,
-                                 a.G, a.gf, a.lam0, a.gAdir, (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg,
-                                 const_cast<float2*>(a.sptraj)));
-    LAUNCH_CHECK(ctx, "psi_bwd_c4_kernel<chain>");
+    if (phase != 2) {
+      CUDA_TRY(ctx, launch_cluster(psi_bwd_c4_kernel<128, C4_CL, false, false>, B, C4_CL, 512, sizeof(BwdC4Smem<128, C4_CL>), st,
+                                   a.matN, a.matRH, a.matS, a.qtab, a.ttab, a.x, a.T, a.A, a.w, a.traj, a.scales, nchunks,
+                                   a.G, a.gf, a.lam0, a.gAdir, (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg,
+                                   const_cast<float2*>(a.sptraj)));
+      LAUNCH_CHECK(ctx, "psi_bwd_c4_kernel<chain>");
+    }
+    if (phase == 1) return AMPS_OK;
     const TilesArgs g = tiles_args();
     const dim3 grid(B * g.nsplit, 2);
     PROF_BEGIN(ctx, 3, st);
@@ -704,10 +724,13 @@ int launch_psi_bwd(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t 
     } else if (ctx->tc_tiles) {
       // chain-only adjoint sweep (mu_k replaces the consumed S x'_k in place), then the gradient tiles as
       // GEMMs over the time axis on the tensor cores
-      psi_bwd_uni_kernel<DPc, NQc, false, false><<<B, DPc * NQc, sizeof(BwdSmemUni<DPc>), st>>>(
-          a.matN, a.matRH, a.matS, a.qtab, a.ttab, a.x, a.T, a.A, a.w, a.traj, a.scales, nchunks, a.G, a.gf,
-          a.lam0, a.gAdir, (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg, const_cast<float2*>(a.sptraj));
-      LAUNCH_CHECK(ctx, "psi_bwd_uni_kernel<chain>");
+      if (phase != 2) {
+        psi_bwd_uni_kernel<DPc, NQc, false, false><<<B, DPc * NQc, sizeof(BwdSmemUni<DPc>), st>>>(
+            a.matN, a.matRH, a.matS, a.qtab, a.ttab, a.x, a.T, a.A, a.w, a.traj, a.scales, nchunks, a.G, a.gf,
+            a.lam0, a.gAdir, (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg, const_cast<float2*>(a.sptraj));
+        LAUNCH_CHECK(ctx, "psi_bwd_uni_kernel<chain>");
+      }
+      if (phase == 1) return AMPS_OK;
       const TilesArgs g = tiles_args();
       PROF_BEGIN(ctx, 3, st);
       psi_tiles_tc_kernel<DPc, 0><<<B * g.nsplit, TL_BLOCK, sizeof(TilesSmem<DPc, 0>) + 1024, st>>>(g);
@@ -724,6 +747,74 @@ int launch_psi_bwd(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t 
     LAUNCH_CHECK(ctx, "psi_bwd_kernel");
     return AMPS_OK;
   });
+}
+
+// Batches beyond one wave of chain CTAs (D > 32: one CTA, or one 4-CTA cluster, per SM resp. 4 SMs): the last,
+// partial wave leaves SMs idle (C4: 256 clips = 148 + 108; C3: 128 clusters = 3 x 37 + 17).  The batch is cut
+// into the full waves (A) and the remainder (R): chain(A); then chain(R) next to gemm(A) -- the tensor-core
+// pass of the clips already done, on the context's second (low-priority) stream, in the SMs chain(R) leaves
+// free; then gemm(R).  Results are identical (every kernel works per clip).  Measured: C4 112.0 -> 108.5 ms;
+// at D = 128 it LOSES (C3 338 -> 390 ms: the 4-CTA chain clusters of the remainder wait for SM quadruples
+// behind the single-SM GEMM CTAs), so only the single-CTA family (D = 33..64) is pipelined.
+int wave_capacity(const amps_ctx* ctx, int DP) { return DP == 128 ? ctx->num_sms / C4_CL : ctx->num_sms; }
+template <class Args, class Shift, class Launch>
+int launch_waves(amps_ctx* ctx, int DP, int B, const Args& a, cudaStream_t st, bool tensor_path, Shift shift,
+                 Launch launch) {
+  const int cap = wave_capacity(ctx, DP);
+  const int R = (DP == 64 && cap > 0) ? B % cap : 0;
+  if (!tensor_path || !a.allow_split || ctx->prof || !ctx->ckpt_overlap || B <= cap || R == 0 || st == ctx->aux_stream)
+    return launch(B, a, st, 0);
+  const int Afull = B - R;
+  const Args aR = shift(a, Afull);
+  cudaStream_t s2 = ctx->aux_stream;
+  int rc;
+  if ((rc = launch(Afull, a, st, 1))) return rc;
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
+  if ((rc = launch(R, aR, st, 1))) return rc;
+  CUDA_TRY(ctx, cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
+  if ((rc = launch(Afull, a, s2, 2))) return rc;
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_replay[0], s2));
+  if ((rc = launch(R, aR, st, 2))) return rc;
+  CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_replay[0], 0));
+  return AMPS_OK;
+}
+int launch_psi_fwd_waves(amps_ctx* ctx, int DP, int B, const FwdArgs& a, cudaStream_t st) {
+  const bool tensor_path = ctx->tc_tiles && a.traj && a.sptraj && a.loss_part && !a.seg.x0 && !a.seg.ckpt;
+  const int chl = chunk_len_of(DP), nchunks = (a.T - 1 + chl - 1) / chl;
+  auto shift = [&](const FwdArgs& f, int b0) {
+    FwdArgs r = f;
+    r.x += (size_t)b0 * f.seg.xstride;
+    r.loss += b0;
+    if (r.lossd) r.lossd += b0;
+    r.traj += (size_t)b0 * f.T * DP;
+    r.scales += (size_t)b0 * nchunks;
+    r.sptraj += (size_t)b0 * f.T * DP;
+    r.ev += (size_t)b0 * f.T;
+    r.loss_part += (size_t)b0 * f.sx_nsplit;
+    return r;
+  };
+  return launch_waves(ctx, DP, B, a, st, tensor_path, shift,
+                      [&](int Bp, const FwdArgs& ap, cudaStream_t s, int ph) { return launch_psi_fwd(ctx, DP, Bp, ap, s, ph); });
+}
+int launch_psi_bwd_waves(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t st) {
+  const bool tensor_path = ctx->tc_tiles && !a.seg.lam_end && !a.seg.accumulate;
+  const int chl = chunk_len_of(DP), nchunks = (a.T - 1 + chl - 1) / chl;
+  auto shift = [&](const BwdArgs& f, int b0) {
+    BwdArgs r = f;
+    r.x += (size_t)b0 * f.seg.xstride;
+    r.w += b0;
+    r.traj += (size_t)b0 * f.T * DP;
+    r.scales += (size_t)b0 * nchunks;
+    r.G += (size_t)b0 * f.tiles_nsplit * 3 * DP * DP;
+    r.gf += (size_t)b0 * DP;
+    r.lam0 += (size_t)b0 * DP;
+    r.gAdir += b0;
+    r.sptraj += (size_t)b0 * f.T * DP;
+    r.ev += (size_t)b0 * f.T;
+    return r;
+  };
+  return launch_waves(ctx, DP, B, a, st, tensor_path, shift,
+                      [&](int Bp, const BwdArgs& ap, cudaStream_t s, int ph) { return launch_psi_bwd(ctx, DP, Bp, ap, s, ph); });
 }
 
 // clip reduction + finalize: packed effective-parameter gradient
@@ -781,9 +872,10 @@ int amps_psi_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
     a.loss_part = (double*)(ws + L.lossp);
     a.sx_nsplit = tiles_nsplit(DP, B, T - 1);
     a.sx_sps = tiles_steps_per_split(T - 1, a.sx_nsplit);
+    a.allow_split = true;
   }
   PROF_BEGIN(ctx, 0, st);
-  rc = launch_psi_fwd(ctx, DP, B, a, st);
+  rc = launch_psi_fwd_waves(ctx, DP, B, a, st);
   PROF_END(ctx, 0, st);
   return rc;
 }
@@ -815,9 +907,10 @@ int amps_psi_loss_bwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
             (const float2*)(ws + L.ev), seg_full_b(T)};
   a.tiles_nsplit = tiles_nsplit(DP, B, T - 1);
   a.tiles_sps = tiles_steps_per_split(T - 1, a.tiles_nsplit);
+  a.allow_split = true;
   const bool tc = DP >= 64 && ctx->tc_tiles;
   PROF_BEGIN(ctx, 1, st);
-  rc = launch_psi_bwd(ctx, DP, B, a, st);
+  rc = launch_psi_bwd_waves(ctx, DP, B, a, st);
   PROF_END(ctx, 1, st);
   if (rc) return rc;
   return psi_finalize(ctx, p, DP, B, ws, L, w_dev, grad_dev, st, tc ? B * a.tiles_nsplit : 0);

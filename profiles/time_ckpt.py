@@ -49,6 +49,9 @@ for name in which:
             m.zero_grad()
             m.loss_fn(x).backward()
         ms = timed(step, reps=2 if B * D >= 8192 else 3)
+        _lib.set_profiling(0, False)      # without the per-kernel events partial waves are pipelined (launch_waves)
+        ms_pipe = timed(step, reps=2 if B * D >= 8192 else 3)
+        _lib.set_profiling(0, True)
         g = m.Rx.grad.detach().clone()
         if g1 is None:
             g1 = g
@@ -59,5 +62,5 @@ for name in which:
         except Exception:
             pass
         print(f"{name} D={D} B={B} T={T} K={K}: step {ms:.2f} ms (fwd {_lib.kernel_ms(0,0):.2f}, bwd {_lib.kernel_ms(0,1):.2f}{tiles}) "
-              f"-> {B*T/ms*1e3:.3e} samples/s; workspace {lib.amps_psi_workspace_bytes_k(D,B,T,K)/1e6:.1f} MB; "
+              f"; step without kernel events {ms_pipe:.2f} ms -> {B*T/ms_pipe*1e3:.3e} samples/s; workspace {lib.amps_psi_workspace_bytes_k(D,B,T,K)/1e6:.1f} MB; "
               f"dRx vs first K {dg:.1e}", flush=True)
