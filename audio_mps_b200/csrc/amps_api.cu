@@ -539,7 +539,7 @@ cudaError_t amps_set_all_func_attrs() {
   if ((e = set_smem(psi_bwd_uni_kernel<64, 8, false, false>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_tiles_tc_kernel<64, 0>, sizeof(TilesSmem<64, 0>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_tiles_tc_kernel<64, 1>, sizeof(TilesSmem<64, 1>) + 1024)) != cudaSuccess) return e;
-  if ((e = set_smem(psi_fwd_uni_kernel<64, 8, false, true>, sizeof(FwdSmemUni<64, 8>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_fwd_uni_kernel<64, 8, false, true>, sizeof(FwdSmemUni<64, 8, true>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_sx_tc_kernel<64>, sizeof(SxSmem<64>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_sx2_tc_kernel, sizeof(Sx2Smem) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_fwd_c4_kernel<128, C4_CL, false, true>, sizeof(FwdC4Smem<128, C4_CL>))) != cudaSuccess) return e;
@@ -628,7 +628,7 @@ int launch_psi_fwd(amps_ctx* ctx, int DP, int B, const FwdArgs& a, cudaStream_t 
       // chain-only forward (x'_k and |x_k|^2 stored), then S x'_k, E_k and the loss as ONE GEMM over the time
       // axis on the tensor cores, in place
       if (phase != 2) {
-        psi_fwd_uni_kernel<DPc, NQc, false, true><<<B, DPc * NQc, sizeof(FwdSmemUni<DPc, NQc>), st>>>(
+        psi_fwd_uni_kernel<DPc, NQc, false, true><<<B, DPc * NQc, sizeof(FwdSmemUni<DPc, NQc, true>), st>>>(
             a.matN, a.matR, a.matS, a.qtab, a.psi0p, a.x, a.T, a.A, a.loss, a.lossd, a.traj, a.scales, nchunks,
             (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg);
         LAUNCH_CHECK(ctx, "psi_fwd_uni_kernel<chain>");
@@ -756,11 +756,9 @@ int launch_psi_bwd(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t 
 // free; then gemm(R).  Results are identical (every kernel works per clip).  Measured: C4 112.0 -> 108.5 ms;
 // at D = 128 it LOSES (C3 338 -> 390 ms: the 4-CTA chain clusters of the remainder wait for SM quadruples
 // behind the single-SM GEMM CTAs), so only the single-CTA family (D = 33..64) is pipelined.
-int wave_capacity(const amps_ctx* ctx, int DP) { return DP == 128 ? ctx->num_sms / C4_CL : ctx->num_sms; }
 template <class Args, class Shift, class Launch>
-int launch_waves(amps_ctx* ctx, int DP, int B, const Args& a, cudaStream_t st, bool tensor_path, Shift shift,
+int launch_waves(amps_ctx* ctx, int DP, int B, const Args& a, cudaStream_t st, bool tensor_path, int cap, Shift shift,
                  Launch launch) {
-  const int cap = wave_capacity(ctx, DP);
   const int R = (DP == 64 && cap > 0) ? B % cap : 0;
   if (!tensor_path || !a.allow_split || ctx->prof || !ctx->ckpt_overlap || B <= cap || R == 0 || st == ctx->aux_stream)
     return launch(B, a, st, 0);
@@ -793,7 +791,8 @@ int launch_psi_fwd_waves(amps_ctx* ctx, int DP, int B, const FwdArgs& a, cudaStr
     r.loss_part += (size_t)b0 * f.sx_nsplit;
     return r;
   };
-  return launch_waves(ctx, DP, B, a, st, tensor_path, shift,
+  // the chain-only D = 64 forward fits two CTAs per SM (64 registers, 85 KB)
+  return launch_waves(ctx, DP, B, a, st, tensor_path, 2 * ctx->num_sms, shift,
                       [&](int Bp, const FwdArgs& ap, cudaStream_t s, int ph) { return launch_psi_fwd(ctx, DP, Bp, ap, s, ph); });
 }
 int launch_psi_bwd_waves(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t st) {
@@ -813,7 +812,7 @@ int launch_psi_bwd_waves(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStr
     r.ev += (size_t)b0 * f.T;
     return r;
   };
-  return launch_waves(ctx, DP, B, a, st, tensor_path, shift,
+  return launch_waves(ctx, DP, B, a, st, tensor_path, ctx->num_sms, shift,
                       [&](int Bp, const BwdArgs& ap, cudaStream_t s, int ph) { return launch_psi_bwd(ctx, DP, Bp, ap, s, ph); });
 }
 

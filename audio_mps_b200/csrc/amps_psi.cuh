@@ -555,14 +555,16 @@ using IC1 = std::integral_constant<int, 1>;
 using IC2 = std::integral_constant<int, 2>;
 using IC3 = std::integral_constant<int, 3>;
 
-template <int DP, int NQ>
+// SXO (chain-only forward): the S x' / E_k staging arrays shrink to nothing -- 85 KB instead of 118 KB, so TWO
+// of these 64-register CTAs share an SM (a batch of 256 clips runs as one wave on 148 SMs instead of two)
+template <int DP, int NQ, bool SXO = false>
 struct alignas(16) FwdSmemUni {
   static constexpr int NT = DP * NQ, G = NT / 32;
   float2 xs[CH + 1][DP];        // x_{k0+kk}
   float2 xps[CH][DP];           // x'_{k0+kk}
   float2 qs[2][CH][DP];         // q_k, double buffered
-  float2 sps[CH][DP];           // S x'_{k0+kk} (chunk-end pass; kept for the backward)
-  float esr[CH][2 * DP + 2];    // Re x'_i Re(S x')_i and Im x'_i Im(S x')_i (even / odd lane of the row)
+  float2 sps[SXO ? 1 : CH][DP];           // S x'_{k0+kk} (chunk-end pass; kept for the backward)
+  float esr[SXO ? 1 : CH][2 * DP + 2];    // Re x'_i Re(S x')_i and Im x'_i Im(S x')_i (even / odd lane of the row)
   float ns[2][CH + 1][DP + 1];  // |x_{k,i}|^2, by chunk parity
   float2 evs[CH];               // (E_k, |x_k|^2)
   float wav[2][CH + 4];         // waveform samples k0..k0+len, double buffered
@@ -608,7 +610,7 @@ __global__ void __launch_bounds__(DP* NQ)
                    float2* __restrict__ sptraj, float2* __restrict__ evout, SegFwd seg) {
   const float A = a_get(A_);
   using M = Map<DP, NQ>;
-  using Sm = FwdSmemUni<DP, NQ>;
+  using Sm = FwdSmemUni<DP, NQ, SXO>;
   constexpr int NT = M::NT;
   constexpr int CPT = M::CPT;
   constexpr int G = Sm::G, PER = DP / G;

@@ -1,5 +1,5 @@
 """One PsiCMPS training step (fwd scan + adjoint bwd) for ncu captures.
-usage: python profiles/prof_step.py [D] [B] [T] [reps]"""
+usage: python profiles/prof_step.py [D] [B] [T] [reps] [K]"""
 import os
 import sys
 
@@ -13,10 +13,13 @@ D = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 T = int(sys.argv[3]) if len(sys.argv) > 3 else 64000
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 2
+K = int(sys.argv[5]) if len(sys.argv) > 5 else None
 dev = torch.device("cuda", 0)
 hp = HParams(minibatch_size=B, bond_dim=D, delta_t=1 / 16000, sigma=0.0001,
              h_reg=200 / (np.pi * 16000) ** 2, r_reg=0.1, initial_rank=None, A=100., learning_rate=0.001)
 model = PsiCMPS(hp, device=dev, seed=0)
+if K is not None:
+    model.checkpoint_every = K
 x = torch.from_numpy(damped_sine(B, T, hp.delta_t, np.random.default_rng(1))).to(dev)
 for _ in range(reps):
     model.zero_grad()
