@@ -174,6 +174,20 @@ __global__ void __launch_bounds__(SX_BLOCK, 1) psi_sx_tc_kernel(SxArgs g) {
     auto drain = [&](int j) {
       const int s = j & 1;
       const int n0 = j * SX_NS, len = min(SX_NS, nloc - n0);
+      // this thread's 8 floats of its step's x' row (16 threads per step): requested BEFORE the accumulator is
+      // awaited, so the (L2) read latency hides behind the MMAs and the transpose
+      const int n = tid >> 4, part = tid & 15;
+      float* gp = rows + (size_t)(n0 + n) * KR + 8 * part;
+      float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+      float nu2 = 1.f, inc = 0.f;
+      if (n < len) {
+        x0 = *reinterpret_cast<const float4*>(gp);
+        x1 = *reinterpret_cast<const float4*>(gp + 4);
+        if (part == 0) {
+          nu2 = evb[n0 + n].y;
+          inc = xb[n0 + n + 1] - xb[n0 + n];
+        }
+      }
       mbar_wait_cta(&sm.acc_full[s], (j >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       {
@@ -190,13 +204,9 @@ __global__ void __launch_bounds__(SX_BLOCK, 1) psi_sx_tc_kernel(SxArgs g) {
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       tl_mbar_arrive(&sm.acc_empty[s]);
       bar_named(5, SX_THREADS);
-      // 16 threads per step: each owns 8 consecutive floats of the row
       {
-        const int n = tid >> 4, part = tid & 15;
         float e = 0.f;
         if (n < len) {
-          float* gp = rows + (size_t)(n0 + n) * KR + 8 * part;
-          const float4 x0 = *reinterpret_cast<const float4*>(gp), x1 = *reinterpret_cast<const float4*>(gp + 4);
           const float4 o0 = *reinterpret_cast<const float4*>(&sm.outs[n][8 * part]);
           const float4 o1 = *reinterpret_cast<const float4*>(&sm.outs[n][8 * part + 4]);
           e = x0.x * o0.x + x0.y * o0.y + x0.z * o0.z + x0.w * o0.w + x1.x * o1.x + x1.y * o1.y + x1.z * o1.z + x1.w * o1.w;
@@ -208,9 +218,7 @@ __global__ void __launch_bounds__(SX_BLOCK, 1) psi_sx_tc_kernel(SxArgs g) {
         e += __shfl_xor_sync(0xffffffffu, e, 4);
         e += __shfl_xor_sync(0xffffffffu, e, 8);
         if (part == 0 && n < len) {
-          const float nu2 = evb[n0 + n].y;
           const float E = e / fmaxf(nu2, 1e-12f);                       // model.py:324-325 on x'
-          const float inc = xb[n0 + n + 1] - xb[n0 + n];
           lossacc -= (double)log1pf((E * inc) / A);                     // model.py:294
           evb[n0 + n] = make_float2(E, nu2);
         }
