@@ -410,15 +410,23 @@ class PsiCMPS(CMPS):
         if K is None:
             return 1
         if K == "auto":
-            full = _lib.load().amps_psi_workspace_bytes(D, B, T, 1)
-            free, _total = torch.cuda.mem_get_info(self.device)
-            # memory the caching allocator holds but has not handed out is reusable too
-            free += torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
-            return 1 if full <= self.checkpoint_auto_fraction * free else 2048
+            # decided once per shape: querying the free memory every step costs a driver call per forward
+            key = (D, B, T, self.checkpoint_auto_fraction)
+            cache = self.__dict__.setdefault("_ckpt_auto_cache", {})
+            if key not in cache:
+                cache[key] = self._checkpoint_auto(D, B, T)
+            return cache[key]
         K = int(K)
         if K < 1:
             raise ValueError(f"checkpoint_every must be >= 1, 'auto' or None (got {K})")
         return K
+
+    def _checkpoint_auto(self, D: int, B: int, T: int) -> int:
+        full = _lib.load().amps_psi_workspace_bytes(D, B, T, 1)
+        free, _total = torch.cuda.mem_get_info(self.device)
+        # memory the caching allocator holds but has not handed out is reusable too
+        free += torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+        return 1 if full <= self.checkpoint_auto_fraction * free else 2048
 
     def _use_scan(self, B: int, T: int, need_grad: bool) -> bool:
         if self.time_parallel == "always":

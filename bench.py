@@ -391,7 +391,7 @@ def measure_train(h, cfg, steps, warmup, full_detail):
     model = PsiCMPS(hp, device=h.dev, seed=0)            # same seed on every rank: replicated params
     if cfg.K is not None:
         model.checkpoint_every = cfg.K
-    trainer = Trainer(model, group=None)
+    trainer = Trainer(model, group=None, cuda_graph=os.environ.get("AMPS_BENCH_NO_GRAPH") != "1")
     gb = B * h.world
     x_host = torch.from_numpy(damped_sine(B, T, hp.delta_t, np.random.default_rng(1 + h.rank))).pin_memory()
     x_dev = x_host.to(h.dev)
@@ -404,8 +404,13 @@ def measure_train(h, cfg, steps, warmup, full_detail):
     if sampler:
         sampler.start()
     step_ms, launches = h.timed(step, steps, warmup)
+    if trainer.cuda_graph:   # replays launch without passing through the library's host-side counter
+        launches = max(launches, steps * trainer.graph_launches_per_step)
     has_tiles = "tiles" in cfg.kernel_names()
-    kms = h.kernel_ms(step, (0, 1, 3) if has_tiles else (0, 1), min(steps, 3))
+
+    def step_eager():        # per-kernel CUDA events cannot be read out of a captured graph
+        return trainer._step_eager(x_dev, global_batch=gb)
+    kms = h.kernel_ms(step_eager, (0, 1, 3) if has_tiles else (0, 1), min(steps, 3))
     res = {"step_ms": step_ms, "launches": launches, "fwd_ms": kms[0], "bwd_ms": kms[1], "gb": gb}
     if has_tiles:
         res["tiles_ms"] = kms[3]
