@@ -551,7 +551,7 @@ def kernel_entries(h, cfg, res):
 
 # dram__bytes_read + dram__bytes_write per launch at the exact bench workload, from the committed
 # ncu --set full captures (profiles/): (fwd, bwd) or sampler
-NCU_TRAFFIC = {"c1": {"fwd": 2.106e9, "bwd": 2.172e9, "source": "profiles/r1_ncu_cluster.md"}}
+NCU_TRAFFIC = {"c1": {"fwd": 2.105e9, "bwd": 2.164e9, "source": "profiles/r2_ncu_summary.md"}}
 
 
 def run_ours(args, cfg):
