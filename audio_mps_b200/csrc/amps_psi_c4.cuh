@@ -120,11 +120,13 @@ __global__ void __launch_bounds__(512)
   // x'_{k,i} into CTA jq - CL (own CTA included: one code path, no local store).
   // Data and completion travel together: st.async ... mbarrier::complete_tx on the TARGET's xbar[s & 1];
   // the consumer waits on its own mbarrier, so no barrier.cluster sits on the per-step critical path.
-  const bool st_on = jq < 2 * CL, st_x = jq < CL;
+  // (SXO: x'_k is needed by nobody but the store to global memory -- the owner keeps it locally, only x_{k+1}
+  // is broadcast: half the DSMEM traffic per step)
+  const bool st_on = jq < (SXO ? CL : 2 * CL), st_x = jq < CL;
   const unsigned st_addr0 = dsmem_addr(st_x ? (const void*)&sm.xs[1][i] : (const void*)&sm.xps[0][i],
                                        (unsigned)(jq & (CL - 1)));
   const unsigned st_bar0 = dsmem_addr(&sm.xbar[0], (unsigned)(jq & (CL - 1)));
-  constexpr unsigned STEP_TX = 2 * DP * sizeof(float2);   // x_{k+1} and x'_k, all rows
+  constexpr unsigned STEP_TX = (SXO ? 1 : 2) * DP * sizeof(float2);   // x_{k+1} (and x'_k), all rows
   if (t == 0) {
     mbar_init(&sm.xbar[0], 1);
     mbar_init(&sm.xbar[1], 1);
@@ -225,6 +227,7 @@ __global__ void __launch_bounds__(512)
       const float2 xn = cmul(q, xp);
       st_async_f2_if(st_on, st_addr0 + (unsigned)(kk * DP * (int)sizeof(float2)), st_x ? xn : xp,
                      st_bar0 + (unsigned)((sg & 1) * sizeof(unsigned long long)));
+      if (SXO) if (jq == CL) sm.xps[kk][i] = xp;   // own row of x'_k, local (flushed by this CTA after the chunk)
       if (EXPC) sm.es[kk - 1][t] = fmaf(xp_prev.x, p0.x + p1.x, xp_prev.y * (p0.y + p1.y));
       if (STAGE == 2) {
         red += __shfl_xor_sync(0xffffffffu, red, 8);
