@@ -139,29 +139,33 @@ __global__ void __launch_bounds__(SX_BLOCK, 1) psi_sx_tc_kernel(SxArgs g) {
     }
   } else {
     // ---- worker warps ---------------------------------------------------------------------------
+    // A tile is 32 rows (steps) x KR floats; warp w owns rows w and w + 16, lane l the 16-byte chunk l of the
+    // row (one coalesced 512-byte row per warp instruction).  The same map serves the staging AND the drain,
+    // so the x' values a thread staged are the ones it needs for the E_k dot product two iterations later:
+    // three register sets roll through fetch(j+1) / stage(j) / drain(j-1) and nothing is read twice.
     double lossacc = 0.0;
-    // stage tile j: 32 rows x KR floats, as 16-byte chunks (row n, K block kb, chunk c)
-    constexpr int NCH = SX_NS * KR / 4 / SX_THREADS;   // chunks per thread
-    float4 pre[NCH];
-    auto fetch = [&](int j) {
+    constexpr int NCH = 2;                 // rows per warp
+    static_assert(SX_NS == 32 && KR / 4 == 32, "one lane per 16-byte chunk of a 128-float row");
+    struct Pre {
+      float4 v[NCH];
+    };
+    auto fetch = [&](Pre& P, int j) {
       const int n0 = j * SX_NS, len = min(SX_NS, nloc - n0);
 #pragma unroll
       for (int q = 0; q < NCH; ++q) {
-        const int idx = tid + q * SX_THREADS;
-        const int n = idx / (KR / 4), c4 = idx % (KR / 4);
-        pre[q] = (n < len) ? *reinterpret_cast<const float4*>(rows + (size_t)(n0 + n) * KR + 4 * c4)
+        const int n = warp + 16 * q;
+        P.v[q] = (n < len) ? *reinterpret_cast<const float4*>(rows + (size_t)(n0 + n) * KR + 4 * lane)
                            : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    auto stage = [&](int j) {
+    auto stage = [&](const Pre& P, int j) {
       const int s = j & 1;
       if (j >= 2) mbar_wait_cta(&sm.empty_bar[s], ((j >> 1) - 1) & 1);
 #pragma unroll
       for (int q = 0; q < NCH; ++q) {
-        const int idx = tid + q * SX_THREADS;
-        const int n = idx / (KR / 4), c4 = idx % (KR / 4);
-        const int kb = c4 / 8, ch = c4 % 8;
-        const float4 v = pre[q];
+        const int n = warp + 16 * q;
+        const int kb = lane / 8, ch = lane % 8;
+        const float4 v = P.v[q];
         const float4 h = make_float4(tc_trunc_tf32(v.x), tc_trunc_tf32(v.y), tc_trunc_tf32(v.z), tc_trunc_tf32(v.w));
         *reinterpret_cast<float4*>(sm.b[s][kb] + tl_off(n, ch)) = h;
         *reinterpret_cast<float4*>(sm.b_lo[s][kb] + tl_off(n, ch)) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
@@ -171,21 +175,18 @@ __global__ void __launch_bounds__(SX_BLOCK, 1) psi_sx_tc_kernel(SxArgs g) {
     };
     // drain tile j: accumulator -> outs (transposed) -> rows (in place), E_k, loss
     const int q4 = warp & 3, cg = warp >> 2;          // TMEM lane quarter, column group (8 steps)
-    auto drain = [&](int j) {
+    auto drain = [&](const Pre& P, int j) {
       const int s = j & 1;
       const int n0 = j * SX_NS, len = min(SX_NS, nloc - n0);
-      // this thread's 8 floats of its step's x' row (16 threads per step): requested BEFORE the accumulator is
-      // awaited, so the (L2) read latency hides behind the MMAs and the transpose
-      const int n = tid >> 4, part = tid & 15;
-      float* gp = rows + (size_t)(n0 + n) * KR + 8 * part;
-      float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-      float nu2 = 1.f, inc = 0.f;
-      if (n < len) {
-        x0 = *reinterpret_cast<const float4*>(gp);
-        x1 = *reinterpret_cast<const float4*>(gp + 4);
-        if (part == 0) {
-          nu2 = evb[n0 + n].y;
-          inc = xb[n0 + n + 1] - xb[n0 + n];
+      float nu2[NCH], inc[NCH];
+#pragma unroll
+      for (int q = 0; q < NCH; ++q) {       // the step's scalars, requested before the accumulator is awaited
+        const int n = warp + 16 * q;
+        nu2[q] = 1.f;
+        inc[q] = 0.f;
+        if (lane == 0 && n < len) {
+          nu2[q] = evb[n0 + n].y;
+          inc[q] = xb[n0 + n + 1] - xb[n0 + n];
         }
       }
       mbar_wait_cta(&sm.acc_full[s], (j >> 1) & 1);
@@ -204,34 +205,45 @@ __global__ void __launch_bounds__(SX_BLOCK, 1) psi_sx_tc_kernel(SxArgs g) {
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       tl_mbar_arrive(&sm.acc_empty[s]);
       bar_named(5, SX_THREADS);
-      {
+#pragma unroll
+      for (int q = 0; q < NCH; ++q) {
+        const int n = warp + 16 * q;
         float e = 0.f;
         if (n < len) {
-          const float4 o0 = *reinterpret_cast<const float4*>(&sm.outs[n][8 * part]);
-          const float4 o1 = *reinterpret_cast<const float4*>(&sm.outs[n][8 * part + 4]);
-          e = x0.x * o0.x + x0.y * o0.y + x0.z * o0.z + x0.w * o0.w + x1.x * o1.x + x1.y * o1.y + x1.z * o1.z + x1.w * o1.w;
-          *reinterpret_cast<float4*>(gp) = o0;
-          *reinterpret_cast<float4*>(gp + 4) = o1;
+          const float4 o = *reinterpret_cast<const float4*>(&sm.outs[n][4 * lane]);
+          const float4 x = P.v[q];
+          e = x.x * o.x + x.y * o.y + x.z * o.z + x.w * o.w;
+          *reinterpret_cast<float4*>(rows + (size_t)(n0 + n) * KR + 4 * lane) = o;
         }
-        e += __shfl_xor_sync(0xffffffffu, e, 1);
-        e += __shfl_xor_sync(0xffffffffu, e, 2);
-        e += __shfl_xor_sync(0xffffffffu, e, 4);
-        e += __shfl_xor_sync(0xffffffffu, e, 8);
-        if (part == 0 && n < len) {
-          const float E = e / fmaxf(nu2, 1e-12f);                       // model.py:324-325 on x'
-          lossacc -= (double)log1pf((E * inc) / A);                     // model.py:294
-          evb[n0 + n] = make_float2(E, nu2);
+        e = warp_sum_f(e);
+        if (lane == 0 && n < len) {
+          const float E = e / fmaxf(nu2[q], 1e-12f);                    // model.py:324-325 on x'
+          lossacc -= (double)log1pf((E * inc[q]) / A);                  // model.py:294
+          evb[n0 + n] = make_float2(E, nu2[q]);
         }
       }
       bar_named(5, SX_THREADS);   // outs free for the next tile
     };
-    if (ntile > 0) fetch(0);
-    for (int j = 0; j < ntile; ++j) {
-      stage(j);
-      if (j + 1 < ntile) fetch(j + 1);
-      if (j > 0) drain(j - 1);
+    {
+      Pre P0, P1, P2;
+      auto iter = [&](Pre& cur, Pre& nxt, Pre& prv, int j) {   // j < ntile
+        if (j + 1 < ntile) fetch(nxt, j + 1);
+        stage(cur, j);
+        if (j > 0) drain(prv, j - 1);
+      };
+      if (ntile > 0) fetch(P0, 0);
+      for (int j = 0; j < ntile; j += 3) {
+        iter(P0, P1, P2, j);
+        if (j + 1 < ntile) iter(P1, P2, P0, j + 1);
+        if (j + 2 < ntile) iter(P2, P0, P1, j + 2);
+      }
+      if (ntile > 0) {
+        const int last = ntile - 1;
+        if (last % 3 == 0) drain(P0, last);
+        else if (last % 3 == 1) drain(P1, last);
+        else drain(P2, last);
+      }
     }
-    if (ntile > 0) drain(ntile - 1);
     lossacc = warp_sum_d(lossacc);
     if (lane == 0) sm.lred[warp] = lossacc;
     bar_named(5, SX_THREADS);
