@@ -512,9 +512,9 @@ Fam family_of(const amps_ctx* ctx, int DP, int B) {
 // backward runs the replay next to the adjoint) if it does not have to be drained to change its
 // L1/shared split.
 template <class Kern>
-cudaError_t set_smem(Kern k, size_t bytes) {
+cudaError_t set_smem(Kern k, size_t bytes, bool max_carveout = true) {
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  if (e != cudaSuccess) return e;
+  if (e != cudaSuccess || !max_carveout || getenv("AMPS_DEFAULT_CARVEOUT")) return e;
   return cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
 }
 template <int DPc, int NQc>

@@ -599,8 +599,15 @@ struct alignas(16) BwdSmemUni {
 // SXO ("S x' offloaded"): chain only -- x'_k goes where S x'_k would (sptraj rows) and |x_k|^2 into ev[k].y;
 // S x'_k, E_k and the loss are produced afterwards, in place, by psi_sx_tc_kernel (amps_sx_tc.cuh) on the
 // tensor cores.  Needs the trajectory buffers (a saving forward).
+#ifndef AMPS_UNI_FWD_MINB
+#define AMPS_UNI_FWD_MINB 0
+#endif
 template <int DP, int NQ, bool VIRT = false, bool SXO = false>
+#if AMPS_UNI_FWD_MINB
+__global__ void __launch_bounds__(DP* NQ, AMPS_UNI_FWD_MINB)
+#else
 __global__ void __launch_bounds__(DP* NQ)
+#endif
     psi_fwd_uni_kernel(const float2* __restrict__ matN, const float2* __restrict__ matR,
                    const float2* __restrict__ matS, const float2* __restrict__ qtab_,
                    const float2* __restrict__ psi0p_, const float* __restrict__ x, int T, AVal A_,
@@ -1166,8 +1173,10 @@ __global__ void __launch_bounds__(DP* NQ)
 // -------------------------------------------------------------------------------------------
 // K3: sampler (model.py:242-251, 284-291) from a supplied noise tensor [L][n]
 // -------------------------------------------------------------------------------------------
+// (the occupancy hint matters: without it ptxas keeps the kernel at 64 registers and serialises the state loads
+// behind the FFMAs that free their registers -- C2 28.0 ms; with it 93 registers, 24.0 ms)
 template <int DP, int NQ>
-__global__ void __launch_bounds__(DP* NQ)
+__global__ void __launch_bounds__(DP* NQ, (DP * NQ <= 256 ? 2 : 1))
     psi_sample_kernel(const float2* __restrict__ matN, const float2* __restrict__ matR,
                       const float2* __restrict__ qtab, const float2* __restrict__ psi0p,
                       const float* __restrict__ noise, int L, int n, float A, float dtf,

@@ -53,8 +53,15 @@ struct alignas(16) FwdC4Smem {
 // VIRT: virtual-clip mode of the parallel-in-time scan, as in psi_fwd_uni_kernel.
 // SXO: chain only -- x'_k goes where S x'_k would and |x_k|^2 into ev[k].y; S x'_k, E_k and the loss come from
 // psi_sx_tc_kernel afterwards (no S mat-vec, no per-chunk exchange of partial sums between the CTAs).
+#ifndef AMPS_C4_MINB
+#define AMPS_C4_MINB 1
+#endif
 template <int DP, int CL, bool VIRT, bool SXO = false>
+#if AMPS_C4_MINB
+__global__ void __launch_bounds__(512, 1)
+#else
 __global__ void __launch_bounds__(512)
+#endif
     psi_fwd_c4_kernel(const float2* __restrict__ matN, const float2* __restrict__ matR,
                       const float2* __restrict__ matS, const float2* __restrict__ qtab_,
                       const float2* __restrict__ psi0p_, const float* __restrict__ x, int T, AVal A_,
@@ -367,7 +374,11 @@ struct alignas(16) BwdC4Smem {
 // rows of a chunk are in shared memory two chunks before its mu rows are written) and the gradient tiles are
 // contracted afterwards on the tensor cores (amps_tiles_tc.cuh).
 template <int DP, int CL, bool VIRT, bool TILES = true>
+#if AMPS_C4_MINB
+__global__ void __launch_bounds__(512, 1)
+#else
 __global__ void __launch_bounds__(512)
+#endif
     psi_bwd_c4_kernel(const float2* __restrict__ matN, const float2* __restrict__ matRH,
                       const float2* __restrict__ matS, const float2* __restrict__ qtab_,
                       const float* __restrict__ ttab_, const float* __restrict__ x, int T, AVal A_,
