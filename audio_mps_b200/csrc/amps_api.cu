@@ -43,6 +43,7 @@ struct amps_ctx {
   // checkpointed backward (amps_psi_loss_bwd_k): the forward replay of time window j-1 runs on this
   // second stream, next to the adjoint sweep of window j on the caller's stream
   cudaStream_t aux_stream = nullptr;
+  cudaStream_t hi_stream = nullptr;   // highest priority: the latency-bound chain kernels of a partial wave (launch_waves)
   bool ckpt_overlap = true;   // AMPS_CKPT_SERIAL=1: replay on the caller's stream (measurement aid)
   bool tc_tiles = true;       // AMPS_NO_TC_TILES=1: D = 33..64 gradient tiles inside the sequential kernel (FFMA)
   cudaEvent_t ev_fork = nullptr, ev_replay[2] = {nullptr, nullptr}, ev_bwd[2] = {nullptr, nullptr};
@@ -322,11 +323,11 @@ int rho_tables(amps_ctx* ctx, const amps_params* p, int nsteps, bool need_p, cha
 cudaError_t amps_set_all_func_attrs();   // defined with the launch helpers below
 // second stream of a context (forward replay of the checkpointed backward, tensor-core pass of finished
 // waves): lowest priority, so that the latency-bound chain kernels on the caller's stream get their SMs first
-static cudaError_t create_aux_stream(cudaStream_t* s) {
+static cudaError_t create_aux_stream(cudaStream_t* s, bool highest = false) {
   int least = 0, greatest = 0;
   cudaError_t e = cudaDeviceGetStreamPriorityRange(&least, &greatest);
   if (e != cudaSuccess) return e;
-  return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, least);
+  return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, highest ? greatest : least);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -357,6 +358,7 @@ int amps_create(int device, amps_ctx** out) {
   // attributes, the replay stream and its events (no allocation, no attribute call per launch)
   bool ok = amps_set_all_func_attrs() == cudaSuccess &&
             create_aux_stream(&ctx->aux_stream) == cudaSuccess &&
+            create_aux_stream(&ctx->hi_stream, true) == cudaSuccess &&
             cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; i < 2 && ok; ++i)
     ok = cudaEventCreateWithFlags(&ctx->ev_replay[i], cudaEventDisableTiming) == cudaSuccess &&
@@ -376,6 +378,7 @@ int amps_destroy(amps_ctx* ctx) {
   if (ctx->hbuf) cudaFree(ctx->hbuf);
   if (ctx->hstream) cudaStreamDestroy(ctx->hstream);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+  if (ctx->hi_stream) cudaStreamDestroy(ctx->hi_stream);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   for (int i = 0; i < 2; ++i) {
     if (ctx->ev_replay[i]) cudaEventDestroy(ctx->ev_replay[i]);
@@ -752,10 +755,10 @@ int launch_psi_bwd(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t 
 // Batches beyond one wave of chain CTAs (D > 32: one CTA, or one 4-CTA cluster, per SM resp. 4 SMs): the last,
 // partial wave leaves SMs idle (C4: 256 clips = 148 + 108; C3: 128 clusters = 3 x 37 + 17).  The batch is cut
 // into the full waves (A) and the remainder (R): chain(A); then chain(R) next to gemm(A) -- the tensor-core
-// pass of the clips already done, on the context's second (low-priority) stream, in the SMs chain(R) leaves
-// free; then gemm(R).  Results are identical (every kernel works per clip).  Measured: C4 112.0 -> 108.5 ms;
-// at D = 128 it LOSES (C3 338 -> 390 ms: the 4-CTA chain clusters of the remainder wait for SM quadruples
-// behind the single-SM GEMM CTAs), so only the single-CTA family (D = 33..64) is pipelined.
+// pass of the clips already done, on the caller's stream, in the SMs chain(R) (highest-priority stream) leaves
+// free; then gemm(R).  Results are identical (every kernel works per clip).  Measured: C4's backward -3.5 ms;
+// at D = 128 it LOSES (C3 313 -> 352 ms even with the remainder's clusters on the highest-priority stream,
+// 390 ms without), so only the single-CTA family (D = 33..64) is pipelined.
 template <class Args, class Shift, class Launch>
 int launch_waves(amps_ctx* ctx, int DP, int B, const Args& a, cudaStream_t st, bool tensor_path, int cap, Shift shift,
                  Launch launch) {
@@ -764,16 +767,18 @@ int launch_waves(amps_ctx* ctx, int DP, int B, const Args& a, cudaStream_t st, b
     return launch(B, a, st, 0);
   const int Afull = B - R;
   const Args aR = shift(a, Afull);
-  cudaStream_t s2 = ctx->aux_stream;
+  // (the default priority of a stream is the LOWEST: the remainder's chain kernel gets the context's
+  // highest-priority stream so that its CTAs / clusters are placed before the GEMM CTAs of the finished waves)
+  cudaStream_t sh = ctx->hi_stream;
   int rc;
   if ((rc = launch(Afull, a, st, 1))) return rc;
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
-  if ((rc = launch(R, aR, st, 1))) return rc;
-  CUDA_TRY(ctx, cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
-  if ((rc = launch(Afull, a, s2, 2))) return rc;
-  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_replay[0], s2));
-  if ((rc = launch(R, aR, st, 2))) return rc;
+  CUDA_TRY(ctx, cudaStreamWaitEvent(sh, ctx->ev_fork, 0));
+  if ((rc = launch(R, aR, sh, 1))) return rc;
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_replay[0], sh));
+  if ((rc = launch(Afull, a, st, 2))) return rc;
   CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_replay[0], 0));
+  if ((rc = launch(R, aR, st, 2))) return rc;
   return AMPS_OK;
 }
 int launch_psi_fwd_waves(amps_ctx* ctx, int DP, int B, const FwdArgs& a, cudaStream_t st) {
@@ -792,7 +797,7 @@ int launch_psi_fwd_waves(amps_ctx* ctx, int DP, int B, const FwdArgs& a, cudaStr
     return r;
   };
   // the chain-only D = 64 forward fits two CTAs per SM (64 registers, 85 KB)
-  return launch_waves(ctx, DP, B, a, st, tensor_path, 2 * ctx->num_sms, shift,
+  return launch_waves(ctx, DP, B, a, st, tensor_path, DP == 128 ? ctx->num_sms / C4_CL : 2 * ctx->num_sms, shift,
                       [&](int Bp, const FwdArgs& ap, cudaStream_t s, int ph) { return launch_psi_fwd(ctx, DP, Bp, ap, s, ph); });
 }
 int launch_psi_bwd_waves(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t st) {
@@ -812,7 +817,7 @@ int launch_psi_bwd_waves(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStr
     r.ev += (size_t)b0 * f.T;
     return r;
   };
-  return launch_waves(ctx, DP, B, a, st, tensor_path, ctx->num_sms, shift,
+  return launch_waves(ctx, DP, B, a, st, tensor_path, DP == 128 ? ctx->num_sms / C4_CL : ctx->num_sms, shift,
                       [&](int Bp, const BwdArgs& ap, cudaStream_t s, int ph) { return launch_psi_bwd(ctx, DP, Bp, ap, s, ph); });
 }
 
