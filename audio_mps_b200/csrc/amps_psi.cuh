@@ -35,6 +35,13 @@ __host__ __device__ constexpr int chunk_steps(int) { return CH; }
 __device__ __forceinline__ void bar_named(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
+// chain barrier of NT threads: a chain of ONE warp (DP = 8: 32 chain threads) only needs warp-level
+// ordering of its shared-memory traffic, not a bar.sync round trip
+template <int NT>
+__device__ __forceinline__ void chain_bar() {
+  if (NT == 32) __syncwarp();
+  else bar_named(1, NT);
+}
 
 // -------------------------------------------------------------------------------------------
 // shared-memory layouts

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(2 * DP * NQ + 32, 1)
             const float2 xn = cmul(q, xp);
             sts_if(st2_on, st2 + kk * DP, (jq == 0) ? xn : xp);
             s_cur = s_next;
-            bar_named(1, NTC);
+            chain_bar<NTC>();
           };
           if (len == CH) {
 #pragma unroll 2
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(AMPS_BWD_CL_MAXT)
           mu.y += a4.w;
           sts64a_if(mu_on, mu_a + (unsigned)(len - 1) * ROW2, mu);
         }
-        bar_named(1, NTC);
+        chain_bar<NTC>();
         const unsigned mus_addr = smem_addr_pinned(&cs.mus[ca][0][2 * jq]);
         // the filler's inputs of a step (s_k, {beta x_k, dt x_k}, {c q, alpha S x'}_{k-1}) are complete for the
         // whole chunk before the chain enters it: they are fetched ONE STEP AHEAD, behind the mu loads, so
@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(AMPS_BWD_CL_MAXT)
           b4 = b4_n;
           a4 = a4_n;
 #endif
-          bar_named(1, NTC);
+          chain_bar<NTC>();
         };
         if (len == CH) {
 #pragma unroll 2
