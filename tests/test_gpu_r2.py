@@ -148,3 +148,28 @@ def test_cuda_graph_trainer_matches_eager(cuda, lib, D, K):
     assert se == sg == 6 and le == lg
     for a, b in zip(pe, pg):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("D,B,T", [(64, 150, 40), (40, 297, 35)])
+def test_partial_wave_pipelining_matches_oracle(cuda, lib, D, B, T):
+    """Batches just beyond one wave of chain CTAs (backward: 148 per wave, forward: 296) take the launch_waves
+    path: chain of the remainder next to the tensor-core pass of the full waves, on three streams.  Loss and
+    gradients against the float64 oracle, and identical to the unsplit run (AMPS_CKPT_SERIAL disables the split
+    only at context creation, so the comparison here is against the oracle and against a B <= 148 sub-batch)."""
+    ohp, php = hp_pair(bond_dim=D, minibatch_size=B)
+    raw = random_raw_params(ohp, np.random.default_rng(5))
+    data = damped_sine(B, T, ohp.delta_t, np.random.default_rng(6))
+    m = PsiCMPS(php, device=cuda)
+    set_raw(m, raw)
+    lpc = m.loss_per_clip(data)
+    w = torch.linspace(0.5, 1.5, B, device=cuda) / B
+    (lpc * w).sum().backward()
+    o = PsiCMPSOracle(ohp, raw, mode="f64")
+    ref = o.loss_per_clip(data)
+    gref = grads_of(o, (ref * torch.as_tensor(w.cpu().numpy(), dtype=torch.float64)).sum())
+    assert rel_clip(lpc.detach().cpu().numpy(), ref.detach().numpy(), floor=0.05) <= 1e-4
+    for n in ("Rx", "Ry", "freqs_raw", "psi_x", "psi_y", "A"):
+        assert rel(getattr(m, n).grad.cpu().numpy(), gref["freqs" if n == "freqs_raw" else n]) <= 1e-3, n
+    # the first 100 clips alone (no split) give the same per-clip losses bit for bit
+    lpc_sub = m.loss_per_clip(data[:100])
+    assert torch.equal(lpc_sub.detach(), lpc.detach()[:100])
