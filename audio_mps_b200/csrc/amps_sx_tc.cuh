@@ -22,24 +22,10 @@
 
 namespace amps {
 
-constexpr int SX_NS = 32;             // steps per tile = UMMA N
+constexpr int SX_NS = 32;             // steps per tile = UMMA N (D = 128 kernel)
 constexpr int SX_THREADS = 512;       // worker threads (warps 0..15)
 constexpr int SX_BLOCK = SX_THREADS + 32;
-
-template <int DP>
-struct alignas(1024) SxSmem {
-  static constexpr int KR = 2 * DP;                 // real contraction length
-  static constexpr int NKB = KR / 32;               // 128-byte K blocks
-  uint8_t a_hi[NKB][128 * TL_ROWB];                 // S real form, rows 2i+c, K block kb
-  uint8_t a_lo[NKB][128 * TL_ROWB];
-  uint8_t b[2][NKB][SX_NS * TL_ROWB];               // x' tile truncated to tf32, row = step
-  uint8_t b_lo[2][NKB][SX_NS * TL_ROWB];            // x' - trunc(x')
-  float outs[SX_NS][KR + 4];                        // (S x')[step][2i+c], epilogue transpose
-  float red[SX_NS][8];                              // E_k partial sums
-  double lred[16];
-  unsigned long long full_bar[2], empty_bar[2], acc_full[2], acc_empty[2];
-  uint32_t tmem_base;
-};
+constexpr int SX1_NS = 64;            // steps per tile of the D = 64 kernel
 
 struct SxArgs {
   const float2* matS;      // [DP][DP]
@@ -47,16 +33,34 @@ struct SxArgs {
   float2* ev;              // [B][T]      in: (., |x_k|^2), out: (E_k, |x_k|^2)
   const float* x;          // waveform, clip stride xstride
   double* loss_part;       // [B][nsplit]
-  int T, xstride, nsplit, steps_per_split;   // steps_per_split: multiple of SX_NS
+  int T, xstride, nsplit, steps_per_split;   // steps_per_split: multiple of 32
   AVal A;
+};
+
+// D = 64.  A = S (real form, tf32 hi and lo) lives in TENSOR MEMORY for the whole kernel (TS-mode MMA: columns
+// [0,128) = S_hi, [128,256) = S_lo, written once with tcgen05.st), so an MMA reads only the 64-row x' tile from
+// shared memory: with both operands in shared memory every K = 8 instruction re-read a 128 x 8 slice of S (32
+// wavefronts) for 17 cycles of math, and the kernel sat at 15-20 % tensor activity.  Two 64-column
+// accumulators ([256,320), [320,384)); two 64 KB stages of x' (hi, lo).
+template <int DP>
+struct alignas(1024) SxSmem {
+  static constexpr int KR = 2 * DP;                 // real contraction length
+  static constexpr int NKB = KR / 32;               // 128-byte K blocks
+  uint8_t b[2][NKB][SX1_NS * TL_ROWB];              // x' tile truncated to tf32, row = step
+  uint8_t b_lo[2][NKB][SX1_NS * TL_ROWB];           // x' - trunc(x')
+  float outs[SX1_NS][KR + 4];                       // (S x')[step][2i+c], epilogue transpose
+  double lred[16];
+  unsigned long long full_bar[2], empty_bar[2], acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
 };
 
 // grid = B * nsplit, block = 544
 template <int DP>
 __global__ void __launch_bounds__(SX_BLOCK, 1) psi_sx_tc_kernel(SxArgs g) {
   using Sm = SxSmem<DP>;
-  constexpr int KR = Sm::KR, NKB = Sm::NKB;
+  constexpr int KR = Sm::KR, NKB = Sm::NKB, NS = SX1_NS;
   static_assert(DP == 64, "one UMMA M = 128 tile of output rows");
+  constexpr uint32_t COL_AH = 0, COL_AL = 128, COL_ACC = 256;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem_al = smem_raw + ((1024u - (tc_smem_u32(smem_raw) & 1023u)) & 1023u);
   Sm& sm = *reinterpret_cast<Sm*>(smem_al);
@@ -66,7 +70,7 @@ __global__ void __launch_bounds__(SX_BLOCK, 1) psi_sx_tc_kernel(SxArgs g) {
   const int nsteps = g.T - 1;
   const int k_begin = sp * g.steps_per_split;
   const int nloc = max(0, min(g.steps_per_split, nsteps - k_begin));
-  const int ntile = (nloc + SX_NS - 1) / SX_NS;
+  const int ntile = (nloc + NS - 1) / NS;
   float* rows = reinterpret_cast<float*>(g.sptraj + ((size_t)b * g.T + k_begin) * DP);   // [step][KR] floats
   float2* evb = g.ev + (size_t)b * g.T + k_begin;
   const float* xb = g.x + (size_t)b * g.xstride + k_begin;
@@ -81,35 +85,38 @@ __global__ void __launch_bounds__(SX_BLOCK, 1) psi_sx_tc_kernel(SxArgs g) {
     mbar_fence_init_cluster();
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;\n" ::"r"(tc_smem_u32(&sm.tmem_base)));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(tc_smem_u32(&sm.tmem_base)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
-  }
-  // A = S real form, hi / lo, once
-  if (tid < SX_THREADS) {
-    for (int idx = tid; idx < DP * (DP / 2); idx += SX_THREADS) {   // (row i, pair of columns j, j+1)
-      const int i = idx / (DP / 2), j = 2 * (idx % (DP / 2));
-      const float2 s0 = g.matS[i * DP + j], s1 = g.matS[i * DP + j + 1];
-      // real columns 2j .. 2j+3 of rows 2i (Re out) and 2i+1 (Im out): one 16-byte chunk each
-      const float r0[4] = {s0.x, -s0.y, s1.x, -s1.y};
-      const float r1[4] = {s0.y, s0.x, s1.y, s1.x};
-      const int kb = (2 * j) / 32, ch = ((2 * j) % 32) / 4;
-      auto put = [&](int row, const float (&v)[4]) {
-        const float4 h = make_float4(tc_trunc_tf32(v[0]), tc_trunc_tf32(v[1]), tc_trunc_tf32(v[2]), tc_trunc_tf32(v[3]));
-        const int o = tl_off(row, ch);
-        *reinterpret_cast<float4*>(sm.a_hi[kb] + o) = h;
-        *reinterpret_cast<float4*>(sm.a_lo[kb] + o) = make_float4(v[0] - h.x, v[1] - h.y, v[2] - h.z, v[3] - h.w);
-      };
-      put(2 * i, r0);
-      put(2 * i + 1, r1);
-    }
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = sm.tmem_base;
-  // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 32, M = 128
-  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(SX_NS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const int q4 = warp & 3, cg = warp >> 2;          // (worker warps) TMEM lane quarter, column group
+  // A = S real form: lane m = 2i + c holds row m; warp (q4, cg) writes contraction columns [32 cg, 32 cg + 32),
+  // i.e. complex columns j = 16 cg .. 16 cg + 15 of row i:  Re-out row: (Sr, -Si) pairs, Im-out row: (Si, Sr)
+  if (warp < SX_THREADS / 32) {
+    const int m = 32 * q4 + lane, i = m >> 1, c = m & 1;
+    float hi[32], lo[32];
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) {
+      const float2 sv = g.matS[i * DP + 16 * cg + jj];
+      const float v0 = c ? sv.y : sv.x, v1 = c ? sv.x : -sv.y;
+      hi[2 * jj] = tc_trunc_tf32(v0);
+      hi[2 * jj + 1] = tc_trunc_tf32(v1);
+      lo[2 * jj] = v0 - hi[2 * jj];
+      lo[2 * jj + 1] = v1 - hi[2 * jj + 1];
+    }
+    const uint32_t lane_base = tmem + ((uint32_t)(32 * q4) << 16);
+    tc_st32(lane_base + COL_AH + 32 * cg, hi);
+    tc_st32(lane_base + COL_AL + 32 * cg, lo);
+    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 64, M = 128
+  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
   if (warp == SX_THREADS / 32) {
     // ---- MMA warp -----------------------------------------------------------------------------
@@ -121,14 +128,14 @@ __global__ void __launch_bounds__(SX_BLOCK, 1) psi_sx_tc_kernel(SxArgs g) {
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         bool first = true;
 #pragma unroll 1
-        for (int pass = 0; pass < 3; ++pass) {
+        for (int pass = 0; pass < 3; ++pass) {      // S_hi X_hi + S_lo X_hi + S_hi X_lo
+          const uint32_t acol = tmem + (pass == 1 ? COL_AL : COL_AH);
 #pragma unroll 1
           for (int kb = 0; kb < NKB; ++kb) {
-            const uint64_t da0 = tc_make_desc(tc_smem_u32(pass == 1 ? sm.a_lo[kb] : sm.a_hi[kb]));
             const uint64_t db0 = tc_make_desc(tc_smem_u32(pass == 2 ? sm.b_lo[s][kb] : sm.b[s][kb]));
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              tl_mma_ss(tmem + SX_NS * s, da0 + 2 * ks, db0 + 2 * ks, idesc, first ? 0u : 1u);
+              tc_mma_ts(tmem + COL_ACC + NS * s, acol + kb * 32 + ks * 8, db0 + 2 * ks, idesc, first ? 0u : 1u);
               first = false;
             }
           }
@@ -139,18 +146,18 @@ __global__ void __launch_bounds__(SX_BLOCK, 1) psi_sx_tc_kernel(SxArgs g) {
     }
   } else {
     // ---- worker warps ---------------------------------------------------------------------------
-    // A tile is 32 rows (steps) x KR floats; warp w owns rows w and w + 16, lane l the 16-byte chunk l of the
-    // row (one coalesced 512-byte row per warp instruction).  The same map serves the staging AND the drain,
-    // so the x' values a thread staged are the ones it needs for the E_k dot product two iterations later:
+    // A tile is 64 rows (steps) x KR floats; warp w owns rows w + 16 q, lane l the 16-byte chunk l of the row
+    // (one coalesced 512-byte row per warp instruction).  The same map serves the staging AND the drain, so
+    // the x' values a thread staged are the ones it needs for the E_k dot product two iterations later:
     // three register sets roll through fetch(j+1) / stage(j) / drain(j-1) and nothing is read twice.
     double lossacc = 0.0;
-    constexpr int NCH = 2;                 // rows per warp
-    static_assert(SX_NS == 32 && KR / 4 == 32, "one lane per 16-byte chunk of a 128-float row");
+    constexpr int NCH = NS / 16;           // rows per warp
+    static_assert(KR / 4 == 32, "one lane per 16-byte chunk of a 128-float row");
     struct Pre {
       float4 v[NCH];
     };
     auto fetch = [&](Pre& P, int j) {
-      const int n0 = j * SX_NS, len = min(SX_NS, nloc - n0);
+      const int n0 = j * NS, len = min(NS, nloc - n0);
 #pragma unroll
       for (int q = 0; q < NCH; ++q) {
         const int n = warp + 16 * q;
@@ -174,10 +181,9 @@ __global__ void __launch_bounds__(SX_BLOCK, 1) psi_sx_tc_kernel(SxArgs g) {
       tl_mbar_arrive(&sm.full_bar[s]);
     };
     // drain tile j: accumulator -> outs (transposed) -> rows (in place), E_k, loss
-    const int q4 = warp & 3, cg = warp >> 2;          // TMEM lane quarter, column group (8 steps)
     auto drain = [&](const Pre& P, int j) {
       const int s = j & 1;
-      const int n0 = j * SX_NS, len = min(SX_NS, nloc - n0);
+      const int n0 = j * NS, len = min(NS, nloc - n0);
       float nu2[NCH], inc[NCH];
 #pragma unroll
       for (int q = 0; q < NCH; ++q) {       // the step's scalars, requested before the accumulator is awaited
@@ -192,15 +198,18 @@ __global__ void __launch_bounds__(SX_BLOCK, 1) psi_sx_tc_kernel(SxArgs g) {
       mbar_wait_cta(&sm.acc_full[s], (j >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       {
-        uint32_t r[8];
-        const uint32_t taddr = tmem + ((uint32_t)(32 * q4) << 16) + SX_NS * s + 8 * cg;
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
-                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                     : "r"(taddr));
+        // warp (q4, cg): lanes 32 q4 .. (output rows m), steps 16 cg .. 16 cg + 15 of the tile
+        uint32_t r[16];
+        const uint32_t taddr = tmem + ((uint32_t)(32 * q4) << 16) + COL_ACC + NS * s + 16 * cg;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
         const int m = 32 * q4 + lane;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) sm.outs[8 * cg + e][m] = __uint_as_float(r[e]);
+        for (int e = 0; e < 16; ++e) sm.outs[16 * cg + e][m] = __uint_as_float(r[e]);
       }
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       tl_mbar_arrive(&sm.acc_empty[s]);
@@ -255,9 +264,8 @@ __global__ void __launch_bounds__(SX_BLOCK, 1) psi_sx_tc_kernel(SxArgs g) {
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;\n" ::"r"(tmem));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem));
 }
-
 
 // -------------------------------------------------------------------------------------------
 // D = 65..128: S in real form is 256 x 256 (512 KB with its lo part) -- it cannot stay in shared memory.
