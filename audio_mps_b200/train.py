@@ -59,7 +59,15 @@ class Trainer:
 
     def step(self, x_local, global_batch: Optional[int] = None, regularise: bool = True):
         if self.cuda_graph and isinstance(x_local, torch.Tensor) and x_local.is_cuda:
-            return self._step_graphed(x_local, global_batch, regularise)
+            try:
+                return self._step_graphed(x_local, global_batch, regularise)
+            except RuntimeError as e:          # capture refused (driver / allocator state): train eagerly instead
+                if self._graphs:
+                    raise
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the training step failed ({e}); continuing eagerly")
+                self.cuda_graph = False
+                torch.cuda.synchronize(x_local.device)
         return self._step_eager(x_local, global_batch, regularise)
 
     def _step_graphed(self, x_local, global_batch, regularise):
