@@ -26,6 +26,7 @@ using namespace amps;
 struct amps_ctx {
   int device = 0;
   int num_sms = 0;
+  int c4_cap = 0;                     // 4-CTA clusters of the D = 128 chain kernels resident at once (GPC granularity)
   bool use_clusters = true;   // AMPS_NO_CLUSTER=1 disables the 2-CTA cluster kernels
   char err[512] = {0};
   int64_t launches = 0;
@@ -204,8 +205,22 @@ int tiles_steps_per_split(int nsteps, int nsplit) {
   return ((s + TL_KS - 1) / TL_KS) * TL_KS;
 }
 
+// time splits of the expectation pass (amps_sx_tc.cuh): it keeps no per-split matrices, so it can use many more
+// CTAs than the tile kernel -- about eight waves of one CTA per SM keep the tail wave under a tenth of the run
+int sx_nsplit_of(int DP, int B, int nsteps) {
+  if (DP < 64 || B <= 0) return 1;
+  int n = (8 * 148 + B - 1) / B;
+  const int cap = nsteps / 1024;
+  if (n > cap) n = cap;
+  return n < 1 ? 1 : n;
+}
+int sx_steps_per_split(int nsteps, int nsplit) {
+  const int s = (nsteps + nsplit - 1) / nsplit;
+  return ((s + 127) / 128) * 128;
+}
+
 struct PsiWs {
-  size_t matN, matR, matRH, matS, psi0p, ttab, qtab, lossd;
+  size_t matN, matR, matRH, matS, spanel, psi0p, ttab, qtab, lossd;
   size_t traj, scales, G, gf, lam0, gAdir, Gtot, gftot, lam0tot, sptraj, ev, lossp;
   size_t total;
 };
@@ -223,6 +238,7 @@ PsiWs psi_ws_layout(int DP, int B, int nsteps_tab, int T, bool save) {
   w.matR = take(mat);
   w.matRH = take(mat);
   w.matS = take(mat);
+  w.spanel = take(DP == 128 ? 4 * mat : 0);   // S in real form, tf32 hi + lo, in the panel order of psi_sx2_tc_kernel
   w.psi0p = take((size_t)DP * sizeof(float2));
   w.ttab = take((size_t)(nsteps_tab > 0 ? nsteps_tab + 2 : 2) * sizeof(float));   // t_k, k = 0..nsteps_tab
   w.qtab = take((size_t)(nsteps_tab > 0 ? nsteps_tab : 1) * DP * sizeof(float2));
@@ -243,7 +259,7 @@ PsiWs psi_ws_layout(int DP, int B, int nsteps_tab, int T, bool save) {
     {   // S x'_k and (E_k, |x_k|^2) from the forward
       w.sptraj = take((size_t)B * T * DP * sizeof(float2));   // S x'_k
       w.ev = take((size_t)B * T * sizeof(float2));            // (E_k, |x_k|^2)
-      w.lossp = take((size_t)B * tiles_nsplit(DP, B, nsteps) * sizeof(double));   // per-split loss sums (D > 32)
+      w.lossp = take((size_t)B * sx_nsplit_of(DP, B, nsteps) * sizeof(double));   // per-split loss sums (D > 32)
     }
   }
   w.total = off;
@@ -302,6 +318,24 @@ cudaError_t launch_cluster(K kern, int nclusters, int CL, int threads, size_t sm
 }
 constexpr int C4_CL = 4;
 
+// plain launch, optionally with programmatic stream serialisation: the kernel may start once every CTA of the
+// kernel queued before it in the stream has executed griddepcontrol.launch_dependents (or exited) -- it does NOT
+// wait for that kernel, or the ones before it, to finish
+template <class K, class... Args>
+cudaError_t launch_pdl(K kern, dim3 grid, int threads, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 // Rho tables of one call -- float32 t_k, q_k, and p_{k+1} when a lab-frame trajectory is wanted -- into
 // the caller's workspace
 int rho_tables(amps_ctx* ctx, const amps_params* p, int nsteps, bool need_p, char* ws, const RhoWs& L,
@@ -321,6 +355,7 @@ int rho_tables(amps_ctx* ctx, const amps_params* p, int nsteps, bool need_p, cha
 }  // namespace
 
 cudaError_t amps_set_all_func_attrs();   // defined with the launch helpers below
+int amps_c4_cluster_capacity();          // idem
 // second stream of a context (forward replay of the checkpointed backward, tensor-core pass of finished
 // waves): lowest priority, so that the latency-bound chain kernels on the caller's stream get their SMs first
 static cudaError_t create_aux_stream(cudaStream_t* s, bool highest = false) {
@@ -367,6 +402,8 @@ int amps_create(int device, amps_ctx** out) {
     amps_destroy(ctx);
     return AMPS_E_CUDA;
   }
+  ctx->c4_cap = amps_c4_cluster_capacity();
+  if (ctx->c4_cap <= 0) ctx->c4_cap = ctx->num_sms / 4;
   *out = ctx;
   return AMPS_OK;
 }
@@ -477,6 +514,8 @@ struct FwdArgs {
   float2* sptraj;
   float2* ev;
   SegFwd seg;
+  float4* spanel = nullptr;      // D = 128: panel-ordered tf32 split of S for the expectation pass
+  bool build_panel = true;       // (built by the first wave only: later waves run next to a reader of it)
   double* loss_part = nullptr;   // D > 32 saving forward: per-split loss sums of the expectation pass
   int sx_nsplit = 1, sx_sps = 0;
   bool allow_split = false;      // whole-batch call on the caller's stream: partial waves may be pipelined
@@ -530,6 +569,34 @@ cudaError_t set_attrs_ws() {
   return set_smem(psi_sample_kernel<DPc, NQc>, sizeof(SampleSmem<DPc>));
 }
 }  // namespace
+// how many 4-CTA clusters of the D = 128 chain kernels the device holds at once: clusters do not span GPCs, so this
+// is below num_sms / 4 (B200: 148 SMs, 32 clusters)
+int amps_c4_cluster_capacity() {
+  using namespace amps;
+  int best = 1 << 30;
+  auto query = [&](auto kern, size_t smem) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(C4_CL * 64);
+    cfg.blockDim = dim3(512);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C4_CL;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      n = 0;
+    }
+    if (n < best) best = n;
+  };
+  query(psi_fwd_c4_kernel<128, C4_CL, false, true>, sizeof(FwdC4Smem<128, C4_CL>));
+  query(psi_bwd_c4_kernel<128, C4_CL, false, false>, sizeof(BwdC4Smem<128, C4_CL>));
+  return best == (1 << 30) ? 0 : best;
+}
 cudaError_t amps_set_all_func_attrs() {
   using namespace amps;
   cudaError_t e;
@@ -581,6 +648,7 @@ int launch_psi_fwd(amps_ctx* ctx, int DP, int B, const FwdArgs& a, cudaStream_t 
     g.ev = a.ev;
     g.x = a.x;
     g.loss_part = a.loss_part;
+    g.spanel = a.spanel;
     g.T = a.T;
     g.xstride = a.seg.xstride;
     g.nsplit = a.sx_nsplit;
@@ -588,9 +656,13 @@ int launch_psi_fwd(amps_ctx* ctx, int DP, int B, const FwdArgs& a, cudaStream_t 
     g.A = a.A;
     return g;
   };
-  const bool sxo = ctx->tc_tiles && a.traj && a.sptraj && a.loss_part;   // chain-only forward + tensor-core expectation pass
+  const bool sxo = ctx->tc_tiles && a.traj && a.sptraj && a.loss_part && (DP != 128 || a.spanel);   // chain-only forward + tensor-core expectation pass
   if (fam == Fam::C4 && sxo) {
-    if (phase != 2) {
+    if (phase < 2) {
+      if (a.build_panel) {
+        psi_sx2_panel_kernel<<<8, SX_THREADS, 0, st>>>(a.matS, a.spanel);
+        LAUNCH_CHECK(ctx, "psi_sx2_panel_kernel");
+      }
       CUDA_TRY(ctx, launch_cluster(psi_fwd_c4_kernel<128, C4_CL, false, true>, B, C4_CL, 512, sizeof(FwdC4Smem<128, C4_CL>), st,
                                    a.matN, a.matR, a.matS, a.qtab, a.psi0p, a.x, a.T, a.A, a.loss, a.lossd, a.traj,
                                    a.scales, nchunks, (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg));
@@ -598,10 +670,13 @@ int launch_psi_fwd(amps_ctx* ctx, int DP, int B, const FwdArgs& a, cudaStream_t 
     }
     if (phase == 1) return AMPS_OK;
     const SxArgs g = sx_args();
-    PROF_BEGIN(ctx, 2, st);
-    psi_sx2_tc_kernel<<<B * g.nsplit, SX_BLOCK, sizeof(Sx2Smem) + 1024, st>>>(g);
-    PROF_END(ctx, 2, st);
-    LAUNCH_CHECK(ctx, "psi_sx2_tc_kernel");
+    if (phase != 4) {
+      PROF_BEGIN(ctx, 2, st);
+      CUDA_TRY(ctx, launch_pdl(psi_sx2_tc_kernel, dim3(B * g.nsplit), SX_BLOCK, sizeof(Sx2Smem) + 1024, st, phase == 3, g));
+      PROF_END(ctx, 2, st);
+      LAUNCH_CHECK(ctx, "psi_sx2_tc_kernel");
+    }
+    if (phase == 3) return AMPS_OK;
     psi_scan_sum_kernel<<<(B + 127) / 128, 128, 0, st>>>(a.loss_part, B, g.nsplit, a.loss, a.lossd);
     LAUNCH_CHECK(ctx, "psi_scan_sum_kernel");
     return AMPS_OK;
@@ -683,7 +758,7 @@ int launch_psi_bwd(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t 
     return g;
   };
   if (fam == Fam::C4 && ctx->tc_tiles) {
-    if (phase != 2) {
+    if (phase < 2) {
       CUDA_TRY(ctx, launch_cluster(psi_bwd_c4_kernel<128, C4_CL, false, false>, B, C4_CL, 512, sizeof(BwdC4Smem<128, C4_CL>), st,
                                    a.matN, a.matRH, a.matS, a.qtab, a.ttab, a.x, a.T, a.A, a.w, a.traj, a.scales, nchunks,
                                    a.G, a.gf, a.lam0, a.gAdir, (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg,
@@ -694,11 +769,12 @@ int launch_psi_bwd(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t 
     const TilesArgs g = tiles_args();
     const dim3 grid(B * g.nsplit, 2);
     PROF_BEGIN(ctx, 3, st);
-    psi_tiles_tc_kernel<128, 2><<<grid, TL_BLOCK, sizeof(TilesSmem<128, 2>) + 1024, st>>>(g);
-    LAUNCH_CHECK(ctx, "psi_tiles_tc_kernel<128,2>");
-    psi_tiles_tc_kernel<128, 3><<<grid, TL_BLOCK, sizeof(TilesSmem<128, 3>) + 1024, st>>>(g);
-    LAUNCH_CHECK(ctx, "psi_tiles_tc_kernel<128,3>");
-    psi_tiles_tc_kernel<128, 1><<<grid, TL_BLOCK, sizeof(TilesSmem<128, 1>) + 1024, st>>>(g);
+    if (phase != 4) {   // phase 3: G_N and G_R with programmatic serialisation (launch_waves); phase 4: G_E after them
+      CUDA_TRY(ctx, launch_pdl(psi_tiles_tc_kernel<128, 2>, grid, TL_BLOCK, sizeof(TilesSmem<128, 2>) + 1024, st, phase == 3, g));
+      CUDA_TRY(ctx, launch_pdl(psi_tiles_tc_kernel<128, 3>, grid, TL_BLOCK, sizeof(TilesSmem<128, 3>) + 1024, st, phase == 3, g));
+    }
+    if (phase != 3)
+      CUDA_TRY(ctx, launch_pdl(psi_tiles_tc_kernel<128, 1>, grid, TL_BLOCK, sizeof(TilesSmem<128, 1>) + 1024, st, false, g));
     PROF_END(ctx, 3, st);
     LAUNCH_CHECK(ctx, "psi_tiles_tc_kernel<128,1>");
     return AMPS_OK;
@@ -752,25 +828,45 @@ int launch_psi_bwd(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t 
   });
 }
 
-// Batches beyond one wave of chain CTAs (D > 32: one CTA, or one 4-CTA cluster, per SM resp. 4 SMs): the last,
-// partial wave leaves SMs idle (C4: 256 clips = 148 + 108; C3: 128 clusters = 3 x 37 + 17).  The batch is cut
-// into the full waves (A) and the remainder (R): chain(A); then chain(R) next to gemm(A) -- the tensor-core
-// pass of the clips already done, on the caller's stream, in the SMs chain(R) (highest-priority stream) leaves
-// free; then gemm(R).  Results are identical (every kernel works per clip).  Measured: C4's backward -3.5 ms;
-// at D = 128 it LOSES (C3 313 -> 352 ms even with the remainder's clusters on the highest-priority stream,
-// 390 ms without), so only the single-CTA family (D = 33..64) is pipelined.
+// Batches beyond one wave of chain CTAs (D = 64: one CTA per SM in the backward, two in the forward; C4: 256 clips =
+// 148 + 108): the last, partial wave leaves SMs idle.  The batch is cut into the full waves (A) and the remainder
+// (R): chain(A); then chain(R) next to gemm(A) -- the tensor-core pass of the clips already done, on the caller's
+// stream, in the SMs chain(R) (highest-priority stream) leaves free; then gemm(R).  Results are identical (every
+// kernel works per clip).  Measured: C4's backward -3.5 ms.  D = 128: see inside.
 template <class Args, class Shift, class Launch>
 int launch_waves(amps_ctx* ctx, int DP, int B, const Args& a, cudaStream_t st, bool tensor_path, int cap, Shift shift,
                  Launch launch) {
-  const int R = (DP == 64 && cap > 0) ? B % cap : 0;
-  if (!tensor_path || !a.allow_split || ctx->prof || !ctx->ckpt_overlap || B <= cap || R == 0 || st == ctx->aux_stream)
+  if (!tensor_path || !a.allow_split || ctx->prof || !ctx->ckpt_overlap || DP < 64 || cap <= 0 || B <= cap ||
+      st == ctx->aux_stream)
     return launch(B, a, st, 0);
+  int rc;
+  if (DP == 128) {
+    // D = 128: the device holds `cap` 4-CTA clusters (B200: 32 = 128 SMs; clusters do not span GPCs), so EVERY wave
+    // leaves SMs idle.  All in the caller's stream: chain(wave w), then the GEMM pass of wave w-1 launched with
+    // programmatic stream serialisation -- it starts when every CTA of chain(w) has executed
+    // griddepcontrol.launch_dependents (its first instruction), i.e. once the clusters are placed, and works in the
+    // SMs they leave free.  (Two streams lose here: the GEMM CTAs win the race for the SMs and the clusters of
+    // the next wave then wait for four free SMs of one GPC -- C3 313 -> 352 ms.)  The backward overlaps only
+    // G_N and G_R (two thirds of the tile work: all three would outlast a wave on the spare SMs); G_E follows.
+    const int nw = (B + cap - 1) / cap;
+    for (int w = 0; w < nw; ++w) {
+      const int b0 = w * cap, n = B - b0 < cap ? B - b0 : cap;
+      if ((rc = launch(n, shift(a, b0), st, 1))) return rc;
+      if (w > 0 && (rc = launch(cap, shift(a, b0 - cap), st, 3))) return rc;
+    }
+    const int bl = (nw - 1) * cap;
+    if ((rc = launch(B - bl, shift(a, bl), st, 2))) return rc;
+    for (int w = 0; w + 1 < nw; ++w)
+      if ((rc = launch(cap, shift(a, w * cap), st, 4))) return rc;
+    return AMPS_OK;
+  }
+  const int R = B % cap;
+  if (R == 0) return launch(B, a, st, 0);
   const int Afull = B - R;
   const Args aR = shift(a, Afull);
   // (the default priority of a stream is the LOWEST: the remainder's chain kernel gets the context's
   // highest-priority stream so that its CTAs / clusters are placed before the GEMM CTAs of the finished waves)
   cudaStream_t sh = ctx->hi_stream;
-  int rc;
   if ((rc = launch(Afull, a, st, 1))) return rc;
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
   CUDA_TRY(ctx, cudaStreamWaitEvent(sh, ctx->ev_fork, 0));
@@ -794,10 +890,11 @@ int launch_psi_fwd_waves(amps_ctx* ctx, int DP, int B, const FwdArgs& a, cudaStr
     r.sptraj += (size_t)b0 * f.T * DP;
     r.ev += (size_t)b0 * f.T;
     r.loss_part += (size_t)b0 * f.sx_nsplit;
+    r.build_panel = b0 == 0;
     return r;
   };
   // the chain-only D = 64 forward fits two CTAs per SM (64 registers, 85 KB)
-  return launch_waves(ctx, DP, B, a, st, tensor_path, DP == 128 ? ctx->num_sms / C4_CL : 2 * ctx->num_sms, shift,
+  return launch_waves(ctx, DP, B, a, st, tensor_path, DP == 128 ? ctx->c4_cap : 2 * ctx->num_sms, shift,
                       [&](int Bp, const FwdArgs& ap, cudaStream_t s, int ph) { return launch_psi_fwd(ctx, DP, Bp, ap, s, ph); });
 }
 int launch_psi_bwd_waves(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t st) {
@@ -817,7 +914,7 @@ int launch_psi_bwd_waves(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStr
     r.ev += (size_t)b0 * f.T;
     return r;
   };
-  return launch_waves(ctx, DP, B, a, st, tensor_path, DP == 128 ? ctx->num_sms / C4_CL : ctx->num_sms, shift,
+  return launch_waves(ctx, DP, B, a, st, tensor_path, DP == 128 ? ctx->c4_cap : ctx->num_sms, shift,
                       [&](int Bp, const BwdArgs& ap, cudaStream_t s, int ph) { return launch_psi_bwd(ctx, DP, Bp, ap, s, ph); });
 }
 
@@ -874,8 +971,9 @@ int amps_psi_loss_fwd(amps_ctx* ctx, const amps_params* p, const float* x_dev, i
             save ? (float2*)(ws + L.ev) : nullptr, seg_full_f(T)};
   if (save) {
     a.loss_part = (double*)(ws + L.lossp);
-    a.sx_nsplit = tiles_nsplit(DP, B, T - 1);
-    a.sx_sps = tiles_steps_per_split(T - 1, a.sx_nsplit);
+    a.spanel = (float4*)(ws + L.spanel);
+    a.sx_nsplit = sx_nsplit_of(DP, B, T - 1);
+    a.sx_sps = sx_steps_per_split(T - 1, a.sx_nsplit);
     a.allow_split = true;
   }
   PROF_BEGIN(ctx, 0, st);
@@ -962,7 +1060,7 @@ CkWs ck_ws_layout(int DP, int B, int T, int K) {
   w.ckpt = take((size_t)B * w.nwin * DP * sizeof(float2));
   w.loss_scr = take((size_t)B * sizeof(float));
   w.lossd_scr = take((size_t)B * sizeof(double));
-  w.base.lossp = take((size_t)B * tiles_nsplit(DP, B, w.W) * sizeof(double));
+  w.base.lossp = take((size_t)B * sx_nsplit_of(DP, B, w.W) * sizeof(double));
   for (int i = 0; i < 2; ++i) {
     w.traj[i] = take((size_t)B * Wt * DP * sizeof(float2));
     w.sptraj[i] = take((size_t)B * Wt * DP * sizeof(float2));
@@ -1067,8 +1165,9 @@ int amps_psi_loss_bwd_k(amps_ctx* ctx, const amps_params* p, const float* x_dev,
               aval(p), (float*)(ws + L.loss_scr), (double*)(ws + L.lossd_scr), (float2*)(ws + L.traj[i]),
               (float*)(ws + L.scales[i]), (float2*)(ws + L.sptraj[i]), (float2*)(ws + L.ev[i]), seg};
     a.loss_part = (double*)(ws + L.base.lossp);
-    a.sx_nsplit = ck_nsplit;
-    a.sx_sps = ck_sps;
+    a.spanel = (float4*)(ws + L.base.spanel);
+    a.sx_nsplit = sx_nsplit_of(DP, B, L.W);
+    a.sx_sps = sx_steps_per_split(L.W, a.sx_nsplit);
     return launch_psi_fwd(ctx, DP, B, a, s2);
   };
   auto adjoint = [&](int j) -> int {

@@ -69,6 +69,9 @@ __global__ void __launch_bounds__(512)
                       float2* __restrict__ traj, float* __restrict__ scales, int nchunks,
                       const float2* __restrict__ psi0v, int nvc, int m_steps,
                       float2* __restrict__ sptraj, float2* __restrict__ evout, SegFwd seg) {
+  // a kernel queued behind this one with the programmatic-serialisation attribute (launch_waves: the GEMM pass of
+  // the clips already done) may start as soon as every CTA of this grid is resident
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const float A = a_get(A_);
   using Cf = C4<DP, CL>;
   constexpr int NQ = Cf::NQ, CPT = Cf::CPT, RP = Cf::RP, NTL = Cf::NTL;
@@ -388,6 +391,7 @@ __global__ void __launch_bounds__(512)
                       double* __restrict__ gAdir, const float2* __restrict__ lam_end, int nvc,
                       int m_steps, const float2* __restrict__ sptraj, const float2* __restrict__ evin,
                       SegBwd seg, float2* __restrict__ mu_out = nullptr) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see psi_fwd_c4_kernel
   const float A = a_get(A_);
   using Cf = C4<DP, CL>;
   constexpr int NQ = Cf::NQ, CPT = Cf::CPT, NP = Cf::NP, RP = Cf::RP, NTL = Cf::NTL;

@@ -33,6 +33,7 @@ struct SxArgs {
   float2* ev;              // [B][T]      in: (., |x_k|^2), out: (E_k, |x_k|^2)
   const float* x;          // waveform, clip stride xstride
   double* loss_part;       // [B][nsplit]
+  const float4* spanel;    // D = 128: [8 phases][8][512] panel-ordered tf32 hi/lo of S (psi_sx2_panel_kernel)
   int T, xstride, nsplit, steps_per_split;   // steps_per_split: multiple of 32
   AVal A;
 };
@@ -268,30 +269,74 @@ __global__ void __launch_bounds__(SX_BLOCK, 1) psi_sx_tc_kernel(SxArgs g) {
 }
 
 // -------------------------------------------------------------------------------------------
-// D = 65..128: S in real form is 256 x 256 (512 KB with its lo part) -- it cannot stay in shared memory.
-// The CTA walks its steps in BLOCKS of 256 (8 tiles of 32 steps) and, per block, through four phases
-// (output-row half mh, contraction half kh): a phase stages the 128 x 128 quadrant S[mh][kh] (hi + lo,
-// 128 KB) once and runs the block's 8 tiles against it, accumulating into 16 accumulators of 32 columns
-// (2 halves x 8 tiles = all 512 columns of tensor memory).  Only after the fourth phase are the rows
-// rewritten (x' -> S x', both halves), so the in-place update never overtakes a read.  Re-staging S costs
-// 2 KB of shared-memory stores per step against 30 KB of operand reads by the MMAs.
+// D = 65..128: S in real form is 256 x 256 (512 KB with its lo part) -- it fits neither tensor nor shared memory.
+// The CTA walks its steps in BLOCKS of 128 (2 tiles of 64 steps) and, per block, through eight phases
+// (contraction quarter kq, output-row half mh): a phase writes the 128 x 64 panel S[mh][kq] (hi + lo, 128 columns)
+// into one of TWO tensor-memory buffers (columns [0,256); TS-mode MMA as in the D = 64 kernel), so the panel of
+// phase p+1 is written while the MMAs of phase p run.  The x' tiles of a quarter (64 steps x 64 floats, hi + lo) are
+// staged once and used by both halves.  The 4 accumulators (2 halves x 2 tiles x 64 columns) live in columns
+// [256,512); only after the eighth phase are the rows rewritten (x' -> S x'), so the in-place update never
+// overtakes a read.
 // -------------------------------------------------------------------------------------------
-constexpr int SX2_TPB = 8;             // tiles per block
+constexpr int SX2_TPB = 2;             // tiles per block
+constexpr int SX2_NS = 64;             // steps per tile
+constexpr int SX2_SLOTS = 4;
 struct alignas(1024) Sx2Smem {
-  uint8_t a_hi[4][128 * TL_ROWB];      // S[mh][kh] quadrant, K blocks of 32
-  uint8_t a_lo[4][128 * TL_ROWB];
-  uint8_t b[2][4][SX_NS * TL_ROWB];    // x' tile, one contraction half, hi
-  uint8_t b_lo[2][4][SX_NS * TL_ROWB];
-  float outs[SX_NS][128 + 4];
-  float esum[SX2_TPB * SX_NS];         // sum_i Re(conj(x'_i) (S x')_i) per step of the block
+  uint8_t b[SX2_SLOTS][2][SX2_NS * TL_ROWB];   // x' tile, one contraction quarter (2 K blocks of 32), hi
+  uint8_t b_lo[SX2_SLOTS][2][SX2_NS * TL_ROWB];
+  float outs[SX2_NS][128 + 4];
+  float esum[SX2_TPB * SX2_NS];        // sum_i Re(conj(x'_i) (S x')_i) per step of the block
   double lred[16];
-  unsigned long long a_full, a_empty, b_full[2], b_empty[2], acc_full, acc_empty;
+  unsigned long long a_full[2], a_empty[2], b_full[SX2_SLOTS], b_empty[SX2_SLOTS], acc_full, acc_empty;
   uint32_t tmem_base;
 };
 
-// grid = B * nsplit, block = 544; steps_per_split: multiple of 256
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+
+// Panel table of S for psi_sx2_tc_kernel: phase p = 2 kq + mh, worker thread t = 32 warp + lane with (q4, cg) =
+// (warp & 3, warp >> 2).  TMEM lane m = 32 q4 + lane = 2 il + c holds real row c of complex output row
+// i = 64 mh + il; the thread owns panel columns [16 cg, 16 cg + 16) = complex columns j = 32 kq + 8 cg + (0..7)
+// (real form: row Re = (Re S, -Im S), row Im = (Im S, Re S)).  Stored as float4 e (0..3 = hi, 4..7 = lo) at
+// [(8 p + e) * 512 + t], so a warp's load is one contiguous 512 bytes (reading S itself here would be 32
+// different rows per instruction -- that serialised the L1 tag stage and was 60 % of the kernel's time).
+// grid = 8, block = 512
+__global__ void __launch_bounds__(SX_THREADS) psi_sx2_panel_kernel(const float2* __restrict__ matS, float4* __restrict__ spanel) {
+  constexpr int DP = 128;
+  const int p = blockIdx.x, kq = p >> 1, mh = p & 1;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int q4 = warp & 3, cg = warp >> 2;
+  const int m = 32 * q4 + lane, c = m & 1;
+  const float2* src = matS + (size_t)(64 * mh + (m >> 1)) * DP + 32 * kq + 8 * cg;
+  float hi[16], lo[16];
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    const float2 sv = src[jj];
+    const float v0 = c ? sv.y : sv.x, v1 = c ? sv.x : -sv.y;
+    hi[2 * jj] = tc_trunc_tf32(v0);
+    hi[2 * jj + 1] = tc_trunc_tf32(v1);
+    lo[2 * jj] = v0 - hi[2 * jj];
+    lo[2 * jj + 1] = v1 - hi[2 * jj + 1];
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    spanel[(size_t)(8 * p + e) * SX_THREADS + t] = make_float4(hi[4 * e], hi[4 * e + 1], hi[4 * e + 2], hi[4 * e + 3]);
+    spanel[(size_t)(8 * p + 4 + e) * SX_THREADS + t] = make_float4(lo[4 * e], lo[4 * e + 1], lo[4 * e + 2], lo[4 * e + 3]);
+  }
+}
+
+// grid = B * nsplit, block = 544
 __global__ void __launch_bounds__(SX_BLOCK, 1) psi_sx2_tc_kernel(SxArgs g) {
-  constexpr int DP = 128, KR = 256, BLK = SX2_TPB * SX_NS;
+  constexpr int DP = 128, KR = 256, NS = SX2_NS, BLK = SX2_TPB * NS;
+  constexpr uint32_t COL_ACC = 256;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem_al = smem_raw + ((1024u - (tc_smem_u32(smem_raw) & 1023u)) & 1023u);
   Sx2Smem& sm = *reinterpret_cast<Sx2Smem*>(smem_al);
@@ -307,9 +352,11 @@ __global__ void __launch_bounds__(SX_BLOCK, 1) psi_sx2_tc_kernel(SxArgs g) {
   const float* xb = g.x + (size_t)b * g.xstride + k_begin;
 
   if (tid == 0) {
-    mbar_init(&sm.a_full, SX_THREADS);
-    mbar_init(&sm.a_empty, 1);
     for (int s = 0; s < 2; ++s) {
+      mbar_init(&sm.a_full[s], SX_THREADS);
+      mbar_init(&sm.a_empty[s], 1);
+    }
+    for (int s = 0; s < SX2_SLOTS; ++s) {
       mbar_init(&sm.b_full[s], SX_THREADS);
       mbar_init(&sm.b_empty[s], 1);
     }
@@ -325,40 +372,42 @@ __global__ void __launch_bounds__(SX_BLOCK, 1) psi_sx2_tc_kernel(SxArgs g) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = sm.tmem_base;
-  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(SX_NS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  auto ntile_of = [&](int blk) { return (min(BLK, nloc - blk * BLK) + SX_NS - 1) / SX_NS; };
+  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  auto ntile_of = [&](int blk) { return (min(BLK, nloc - blk * BLK) + NS - 1) / NS; };
 
   if (warp == SX_THREADS / 32) {
     // ---- MMA warp -----------------------------------------------------------------------------
     if (lane == 0) {
-      int gp = 0, jb = 0;      // phases and B tiles so far (barrier parities)
+      int gp = 0, jb = 0;      // phases and staged tiles so far (barrier parities)
       for (int blk = 0; blk < nblk; ++blk) {
         const int nt = ntile_of(blk);
         if (blk > 0) mbar_wait_cta(&sm.acc_empty, (blk - 1) & 1);     // the previous block is drained
-        for (int mh = 0; mh < 2; ++mh)
-          for (int kh = 0; kh < 2; ++kh, ++gp) {
-            mbar_wait_cta(&sm.a_full, gp & 1);
-            for (int tl = 0; tl < nt; ++tl, ++jb) {
-              const int s = jb & 1;
-              mbar_wait_cta(&sm.b_full[s], (jb >> 1) & 1);
+        for (int kq = 0; kq < 4; ++kq, jb += nt)
+          for (int mh = 0; mh < 2; ++mh, ++gp) {
+            const int ab = gp & 1;
+            mbar_wait_cta(&sm.a_full[ab], (gp >> 1) & 1);
+            for (int tl = 0; tl < nt; ++tl) {
+              const int j = jb + tl, s = j % SX2_SLOTS;
+              if (mh == 0) mbar_wait_cta(&sm.b_full[s], (j / SX2_SLOTS) & 1);
               asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-              bool first = kh == 0;
+              bool first = kq == 0;
 #pragma unroll 1
-              for (int pass = 0; pass < 3; ++pass) {
-#pragma unroll 1
-                for (int kb = 0; kb < 4; ++kb) {
-                  const uint64_t da0 = tc_make_desc(tc_smem_u32(pass == 1 ? sm.a_lo[kb] : sm.a_hi[kb]));
+              for (int pass = 0; pass < 3; ++pass) {      // S_hi X_hi + S_lo X_hi + S_hi X_lo
+                const uint32_t acol = tmem + 128 * ab + (pass == 1 ? 64 : 0);
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb) {
                   const uint64_t db0 = tc_make_desc(tc_smem_u32(pass == 2 ? sm.b_lo[s][kb] : sm.b[s][kb]));
 #pragma unroll
                   for (int ks = 0; ks < 4; ++ks) {
-                    tl_mma_ss(tmem + (uint32_t)((mh * SX2_TPB + tl) * SX_NS), da0 + 2 * ks, db0 + 2 * ks, idesc, first ? 0u : 1u);
+                    tc_mma_ts(tmem + COL_ACC + (uint32_t)((mh * SX2_TPB + tl) * NS), acol + kb * 32 + ks * 8, db0 + 2 * ks,
+                              idesc, first ? 0u : 1u);
                     first = false;
                   }
                 }
               }
-              tl_commit(&sm.b_empty[s]);
+              if (mh == 1) tl_commit(&sm.b_empty[s]);
             }
-            tl_commit(&sm.a_empty);
+            tl_commit(&sm.a_empty[ab]);
           }
         tl_commit(&sm.acc_full);
       }
@@ -366,51 +415,47 @@ __global__ void __launch_bounds__(SX_BLOCK, 1) psi_sx2_tc_kernel(SxArgs g) {
   } else {
     // ---- worker warps ---------------------------------------------------------------------------
     double lossacc = 0.0;
-    const int q4 = warp & 3, cg = warp >> 2;
+    const int q4 = warp & 3, cg = warp >> 2;          // TMEM lane quarter, column group
+    const uint32_t lane_base = tmem + ((uint32_t)(32 * q4) << 16);
+    const int srow = tid >> 4, sc = tid & 15;         // staging map: rows srow, srow + 32; 16-byte chunk sc of the quarter
+    // panel S[mh][kq] comes pre-split and in thread order from psi_sx2_panel_kernel: 8 coalesced float4 per phase
+    float4 apre[8];
+    auto fetch_a = [&](int kq, int mh) {
+      const float4* src = g.spanel + (size_t)(8 * (2 * kq + mh)) * SX_THREADS + tid;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) apre[e] = __ldg(src + (size_t)e * SX_THREADS);
+    };
+    float4 pre[SX2_TPB][2];
+    auto fetch_b = [&](int n0b, int kq) {
+#pragma unroll
+      for (int tl = 0; tl < SX2_TPB; ++tl) {
+        const int n0 = n0b + tl * NS, len = min(NS, nloc - n0);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int n = srow + 32 * q;
+          pre[tl][q] = (n < len) ? *reinterpret_cast<const float4*>(rows + (size_t)(n0 + n) * KR + 64 * kq + 4 * sc)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    };
     int gp = 0, jb = 0;
+    if (nblk > 0) {
+      fetch_b(0, 0);
+      fetch_a(0, 0);
+    }
     for (int blk = 0; blk < nblk; ++blk) {
       const int n0b = blk * BLK, nt = ntile_of(blk);
-      for (int mh = 0; mh < 2; ++mh)
-        for (int kh = 0; kh < 2; ++kh, ++gp) {
-          // S[mh][kh]: rows 2i+c of the half (i = 64 mh ..), contraction columns 2j+c' (j = 64 kh ..)
-          if (gp > 0) mbar_wait_cta(&sm.a_empty, (gp - 1) & 1);
-          for (int idx = tid; idx < 64 * 32; idx += SX_THREADS) {   // (row i of 64, pair of columns j, j+1 of 64)
-            const int il = idx / 32, jl = 2 * (idx % 32);
-            const float2* srow = g.matS + (size_t)(64 * mh + il) * DP + 64 * kh + jl;
-            const float2 s0 = srow[0], s1 = srow[1];
-            const float r0[4] = {s0.x, -s0.y, s1.x, -s1.y};
-            const float r1[4] = {s0.y, s0.x, s1.y, s1.x};
-            const int kb = (2 * jl) / 32, ch = ((2 * jl) % 32) / 4;
-            auto put = [&](int row, const float (&v)[4]) {
-              const float4 h = make_float4(tc_trunc_tf32(v[0]), tc_trunc_tf32(v[1]), tc_trunc_tf32(v[2]), tc_trunc_tf32(v[3]));
-              const int o = tl_off(row, ch);
-              *reinterpret_cast<float4*>(sm.a_hi[kb] + o) = h;
-              *reinterpret_cast<float4*>(sm.a_lo[kb] + o) = make_float4(v[0] - h.x, v[1] - h.y, v[2] - h.z, v[3] - h.w);
-            };
-            put(2 * il, r0);
-            put(2 * il + 1, r1);
-          }
-          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-          tl_mbar_arrive(&sm.a_full);
-          // the block's tiles, contraction half kh: 32 rows x 128 floats = 1024 16-byte chunks, 2 per thread
-          for (int tl = 0; tl < nt; ++tl, ++jb) {
-            const int s = jb & 1;
-            const int n0 = n0b + tl * SX_NS, len = min(SX_NS, nloc - n0);
-            float4 pre[2];
+      for (int kq = 0; kq < 4; ++kq) {
+        // x' tiles of this quarter -> shared memory (rows fetched one quarter ahead)
+#pragma unroll
+        for (int tl = 0; tl < SX2_TPB; ++tl) {
+          if (tl < nt) {
+            const int j = jb + tl, s = j % SX2_SLOTS;
+            if (j >= SX2_SLOTS) mbar_wait_cta(&sm.b_empty[s], ((j / SX2_SLOTS) - 1) & 1);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-              const int idx = tid + q * SX_THREADS;
-              const int n = idx / 32, c4 = idx % 32;
-              pre[q] = (n < len) ? *reinterpret_cast<const float4*>(rows + (size_t)(n0 + n) * KR + 128 * kh + 4 * c4)
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            if (jb >= 2) mbar_wait_cta(&sm.b_empty[s], ((jb >> 1) - 1) & 1);
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const int idx = tid + q * SX_THREADS;
-              const int n = idx / 32, c4 = idx % 32;
-              const int kb = c4 / 8, ch = c4 % 8;
-              const float4 v = pre[q];
+              const int n = srow + 32 * q, kb = sc >> 3, ch = sc & 7;
+              const float4 v = pre[tl][q];
               const float4 h = make_float4(tc_trunc_tf32(v.x), tc_trunc_tf32(v.y), tc_trunc_tf32(v.z), tc_trunc_tf32(v.w));
               *reinterpret_cast<float4*>(sm.b[s][kb] + tl_off(n, ch)) = h;
               *reinterpret_cast<float4*>(sm.b_lo[s][kb] + tl_off(n, ch)) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
@@ -419,41 +464,68 @@ __global__ void __launch_bounds__(SX_BLOCK, 1) psi_sx2_tc_kernel(SxArgs g) {
             tl_mbar_arrive(&sm.b_full[s]);
           }
         }
-      // ---- drain the block: 2 halves x nt tiles ---------------------------------------------------
+        jb += nt;
+        if (kq < 3) fetch_b(n0b, kq + 1);
+        else if (blk + 1 < nblk) fetch_b(n0b + BLK, 0);
+        // the two panels of this quarter
+#pragma unroll
+        for (int mh = 0; mh < 2; ++mh, ++gp) {
+          float hi[16], lo[16];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            hi[4 * e] = apre[e].x, hi[4 * e + 1] = apre[e].y, hi[4 * e + 2] = apre[e].z, hi[4 * e + 3] = apre[e].w;
+            lo[4 * e] = apre[4 + e].x, lo[4 * e + 1] = apre[4 + e].y, lo[4 * e + 2] = apre[4 + e].z, lo[4 * e + 3] = apre[4 + e].w;
+          }
+          if (mh == 0) fetch_a(kq, 1);
+          else fetch_a((kq + 1) & 3, 0);
+          const int ab = gp & 1;
+          if (gp >= 2) mbar_wait_cta(&sm.a_empty[ab], ((gp >> 1) - 1) & 1);   // the MMAs of phase gp - 2 have read it
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          tc_st16(lane_base + 128 * ab + 16 * cg, hi);
+          tc_st16(lane_base + 128 * ab + 64 + 16 * cg, lo);
+          asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+          tl_mbar_arrive(&sm.a_full[ab]);
+        }
+      }
+      // ---- drain the block: 2 halves x nt tiles; warp w owns rows w + 16 q, lane l the 16-byte chunk l ----
       mbar_wait_cta(&sm.acc_full, blk & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       for (int mh = 0; mh < 2; ++mh)
         for (int tl = 0; tl < nt; ++tl) {
-          const int n0 = n0b + tl * SX_NS, len = min(SX_NS, nloc - n0);
+          const int n0 = n0b + tl * NS, len = min(NS, nloc - n0);
+          float4 xr[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {      // x' of this half, before it is overwritten (L2)
+            const int n = warp + 16 * q;
+            xr[q] = (n < len) ? *reinterpret_cast<const float4*>(rows + (size_t)(n0 + n) * KR + 128 * mh + 4 * lane)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
           {
-            uint32_t r[8];
-            const uint32_t taddr = tmem + ((uint32_t)(32 * q4) << 16) + (uint32_t)((mh * SX2_TPB + tl) * SX_NS + 8 * cg);
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
-                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                         : "r"(taddr));
+            uint32_t r[16];
+            const uint32_t taddr = lane_base + COL_ACC + (uint32_t)((mh * SX2_TPB + tl) * NS + 16 * cg);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
             const int m = 32 * q4 + lane;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) sm.outs[8 * cg + e][m] = __uint_as_float(r[e]);
+            for (int e = 0; e < 16; ++e) sm.outs[16 * cg + e][m] = __uint_as_float(r[e]);
           }
           bar_named(5, SX_THREADS);
-          {
-            const int n = tid >> 4, part = tid & 15;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int n = warp + 16 * q;
             float e = 0.f;
             if (n < len) {
-              float* gp_ = rows + (size_t)(n0 + n) * KR + 128 * mh + 8 * part;
-              const float4 x0 = *reinterpret_cast<const float4*>(gp_), x1 = *reinterpret_cast<const float4*>(gp_ + 4);
-              const float4 o0 = *reinterpret_cast<const float4*>(&sm.outs[n][8 * part]);
-              const float4 o1 = *reinterpret_cast<const float4*>(&sm.outs[n][8 * part + 4]);
-              e = x0.x * o0.x + x0.y * o0.y + x0.z * o0.z + x0.w * o0.w + x1.x * o1.x + x1.y * o1.y + x1.z * o1.z + x1.w * o1.w;
-              *reinterpret_cast<float4*>(gp_) = o0;
-              *reinterpret_cast<float4*>(gp_ + 4) = o1;
+              const float4 o = *reinterpret_cast<const float4*>(&sm.outs[n][4 * lane]);
+              e = xr[q].x * o.x + xr[q].y * o.y + xr[q].z * o.z + xr[q].w * o.w;
+              *reinterpret_cast<float4*>(rows + (size_t)(n0 + n) * KR + 128 * mh + 4 * lane) = o;
             }
-            e += __shfl_xor_sync(0xffffffffu, e, 1);
-            e += __shfl_xor_sync(0xffffffffu, e, 2);
-            e += __shfl_xor_sync(0xffffffffu, e, 4);
-            e += __shfl_xor_sync(0xffffffffu, e, 8);
-            if (part == 0 && n < len) sm.esum[tl * SX_NS + n] = (mh == 0 ? 0.f : sm.esum[tl * SX_NS + n]) + e;
+            e = warp_sum_f(e);
+            if (lane == 0 && n < len) sm.esum[tl * NS + n] = (mh == 0 ? 0.f : sm.esum[tl * NS + n]) + e;
           }
           bar_named(5, SX_THREADS);
         }
