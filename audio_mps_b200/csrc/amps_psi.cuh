@@ -1219,6 +1219,7 @@ __global__ void __launch_bounds__(DP* NQ, (DP * NQ <= 256 ? 2 : 1))
   const unsigned qs_a = smem_addr_pinned(&sm.qs[0][0][0]), nz_a = smem_addr_pinned(&sm.nz[0][0]);
   const unsigned outs_a = smem_addr_pinned(&sm.outs[0]);
   float X = 0.f;  // cumulative sample, replicated in every thread (identical arithmetic)
+  const float invA = 1.0f / A;
   if (nchunks > 0) issue_loads(0, 0);
   cp_async_commit();
 
@@ -1274,11 +1275,13 @@ __global__ void __launch_bounds__(DP* NQ, (DP * NQ <= 256 ? 2 : 1))
         es += w2.x;
         nsum += w2.y;
       }
-      const float E = 2.0f * es / fmaxf(nsum, 1e-12f);                                  // model.py:319-325
+      // (both divisions sit on the step's dependency chain: reciprocal + multiply, 1-2 ulp from the IEEE quotient)
+      const float nsc = fmaxf(nsum, 1e-12f);
+      const float E = 2.0f * es * __frcp_rn(nsc);                                       // model.py:319-325
       const float inc = __fadd_rn(__fmul_rn(E, dtf), lds32a(nz_b + (unsigned)(kk * sizeof(float))));   // model.py:286
       X = __fadd_rn(X, inc);                                             // model.py:287
-      const float s = inc / A;                                           // model.py:303
-      const float rn = rsqrtf(fmaxf(nsum, 1e-12f));   // lagged normalisation keeps |x| ~ 1
+      const float s = inc * invA;                                        // model.py:303
+      const float rn = rsqrtf(nsc);   // lagged normalisation keeps |x| ~ 1
       float2 xp = make_float2(fmaf(s, y.x, a.x) * rn, fmaf(s, y.y, a.y) * rn);
       const float2 xn = cmul(lds64a(qs_b + (unsigned)((kk * DP + i) * sizeof(float2))), xp);
       sts64a_if(jq == 0, xs_a + XN + (unsigned)(i * sizeof(float2)), xn);
