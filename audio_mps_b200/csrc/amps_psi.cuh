@@ -1275,13 +1275,14 @@ __global__ void __launch_bounds__(DP* NQ, (DP * NQ <= 256 ? 2 : 1))
         es += w2.x;
         nsum += w2.y;
       }
-      // (both divisions sit on the step's dependency chain: reciprocal + multiply, 1-2 ulp from the IEEE quotient)
+      // (both divisions sit on the step's dependency chain: MUFU reciprocal + multiply, 1-2 ulp from the IEEE quotient)
       const float nsc = fmaxf(nsum, 1e-12f);
-      const float E = 2.0f * es * __frcp_rn(nsc);                                       // model.py:319-325
+      const float E = __fdividef(2.0f * es, nsc);                                       // model.py:319-325
       const float inc = __fadd_rn(__fmul_rn(E, dtf), lds32a(nz_b + (unsigned)(kk * sizeof(float))));   // model.py:286
       X = __fadd_rn(X, inc);                                             // model.py:287
       const float s = inc * invA;                                        // model.py:303
-      const float rn = rsqrtf(nsc);   // lagged normalisation keeps |x| ~ 1
+      float rn;   // lagged normalisation keeps |x| ~ 1 (nsc >= 1e-12 is a normal number: no denormal scaling path)
+      asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rn) : "f"(nsc));
       float2 xp = make_float2(fmaf(s, y.x, a.x) * rn, fmaf(s, y.y, a.y) * rn);
       const float2 xn = cmul(lds64a(qs_b + (unsigned)((kk * DP + i) * sizeof(float2))), xp);
       sts64a_if(jq == 0, xs_a + XN + (unsigned)(i * sizeof(float2)), xn);
