@@ -26,7 +26,7 @@ using namespace amps;
 struct amps_ctx {
   int device = 0;
   int num_sms = 0;
-  int c4_cap = 0;                     // 4-CTA clusters of the D = 128 chain kernels resident at once (GPC granularity)
+  int c4_cap_fwd = 0, c4_cap_bwd = 0; // 4-CTA clusters of the D = 128 chain kernels resident at once (GPC granularity)
   bool use_clusters = true;   // AMPS_NO_CLUSTER=1 disables the 2-CTA cluster kernels
   char err[512] = {0};
   int64_t launches = 0;
@@ -46,6 +46,7 @@ struct amps_ctx {
   cudaStream_t aux_stream = nullptr;
   cudaStream_t hi_stream = nullptr;   // highest priority: the latency-bound chain kernels of a partial wave (launch_waves)
   bool ckpt_overlap = true;   // AMPS_CKPT_SERIAL=1: replay on the caller's stream (measurement aid)
+  int waves_mask = 3;         // AMPS_WAVES: bit 0 = forward, bit 1 = backward, bit 2 = D = 128 forward wave pipelining
   bool tc_tiles = true;       // AMPS_NO_TC_TILES=1: D = 33..64 gradient tiles inside the sequential kernel (FFMA)
   cudaEvent_t ev_fork = nullptr, ev_replay[2] = {nullptr, nullptr}, ev_bwd[2] = {nullptr, nullptr};
 };
@@ -355,7 +356,7 @@ int rho_tables(amps_ctx* ctx, const amps_params* p, int nsteps, bool need_p, cha
 }  // namespace
 
 cudaError_t amps_set_all_func_attrs();   // defined with the launch helpers below
-int amps_c4_cluster_capacity();          // idem
+int amps_c4_cluster_capacity(bool bwd);  // idem
 // second stream of a context (forward replay of the checkpointed backward, tensor-core pass of finished
 // waves): lowest priority, so that the latency-bound chain kernels on the caller's stream get their SMs first
 static cudaError_t create_aux_stream(cudaStream_t* s, bool highest = false) {
@@ -387,6 +388,7 @@ int amps_create(int device, amps_ctx** out) {
   ctx->use_clusters = !(nc && nc[0] == '1');
   const char* cs = getenv("AMPS_CKPT_SERIAL");
   ctx->ckpt_overlap = !(cs && cs[0] == '1');
+  if (const char* wm = getenv("AMPS_WAVES")) ctx->waves_mask = atoi(wm);
   const char* nt = getenv("AMPS_NO_TC_TILES");
   ctx->tc_tiles = !(nt && nt[0] == '1');
   // everything the device entry points need besides the caller's buffers is created HERE: kernel
@@ -402,8 +404,10 @@ int amps_create(int device, amps_ctx** out) {
     amps_destroy(ctx);
     return AMPS_E_CUDA;
   }
-  ctx->c4_cap = amps_c4_cluster_capacity();
-  if (ctx->c4_cap <= 0) ctx->c4_cap = ctx->num_sms / 4;
+  ctx->c4_cap_fwd = amps_c4_cluster_capacity(false);
+  ctx->c4_cap_bwd = amps_c4_cluster_capacity(true);
+  if (ctx->c4_cap_fwd <= 0) ctx->c4_cap_fwd = ctx->num_sms / 4;
+  if (ctx->c4_cap_bwd <= 0) ctx->c4_cap_bwd = ctx->num_sms / 4;
   *out = ctx;
   return AMPS_OK;
 }
@@ -570,10 +574,10 @@ cudaError_t set_attrs_ws() {
 }
 }  // namespace
 // how many 4-CTA clusters of the D = 128 chain kernels the device holds at once: clusters do not span GPCs, so this
-// is below num_sms / 4 (B200: 148 SMs, 32 clusters)
-int amps_c4_cluster_capacity() {
+// is below num_sms / 4 per resident CTA (B200, 148 SMs: 32 clusters of the backward, one CTA per SM; 64 of the
+// chain-only forward, two CTAs per SM)
+int amps_c4_cluster_capacity(bool bwd) {
   using namespace amps;
-  int best = 1 << 30;
   auto query = [&](auto kern, size_t smem) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(C4_CL * 64);
@@ -591,11 +595,10 @@ int amps_c4_cluster_capacity() {
       cudaGetLastError();
       n = 0;
     }
-    if (n < best) best = n;
+    return n;
   };
-  query(psi_fwd_c4_kernel<128, C4_CL, false, true>, sizeof(FwdC4Smem<128, C4_CL>));
-  query(psi_bwd_c4_kernel<128, C4_CL, false, false>, sizeof(BwdC4Smem<128, C4_CL>));
-  return best == (1 << 30) ? 0 : best;
+  return bwd ? query(psi_bwd_c4_kernel<128, C4_CL, false, false>, sizeof(BwdC4Smem<128, C4_CL>))
+             : query(psi_fwd_c4_kernel<128, C4_CL, false, true>, sizeof(FwdC4Smem<128, C4_CL>));
 }
 cudaError_t amps_set_all_func_attrs() {
   using namespace amps;
@@ -894,7 +897,10 @@ int launch_psi_fwd_waves(amps_ctx* ctx, int DP, int B, const FwdArgs& a, cudaStr
     return r;
   };
   // the chain-only D = 64 forward fits two CTAs per SM (64 registers, 85 KB)
-  return launch_waves(ctx, DP, B, a, st, tensor_path, DP == 128 ? ctx->c4_cap : 2 * ctx->num_sms, shift,
+  // (D = 128: the chain-only forward runs two CTAs per SM, its clusters cover every SM and the GEMM CTAs -- one per
+  // SM, 165 KB -- find no room next to them: pipelined 134 ms, plain 129 ms.  AMPS_WAVES=7 forces it.)
+  const bool pipe = DP == 128 ? (ctx->waves_mask & 4) != 0 : (ctx->waves_mask & 1) != 0;
+  return launch_waves(ctx, DP, B, a, st, tensor_path && pipe, DP == 128 ? ctx->c4_cap_fwd : 2 * ctx->num_sms, shift,
                       [&](int Bp, const FwdArgs& ap, cudaStream_t s, int ph) { return launch_psi_fwd(ctx, DP, Bp, ap, s, ph); });
 }
 int launch_psi_bwd_waves(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t st) {
@@ -914,7 +920,7 @@ int launch_psi_bwd_waves(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStr
     r.ev += (size_t)b0 * f.T;
     return r;
   };
-  return launch_waves(ctx, DP, B, a, st, tensor_path, DP == 128 ? ctx->c4_cap : ctx->num_sms, shift,
+  return launch_waves(ctx, DP, B, a, st, tensor_path && (ctx->waves_mask & 2), DP == 128 ? ctx->c4_cap_bwd : ctx->num_sms, shift,
                       [&](int Bp, const BwdArgs& ap, cudaStream_t s, int ph) { return launch_psi_bwd(ctx, DP, Bp, ap, s, ph); });
 }
 

@@ -56,9 +56,12 @@ struct alignas(16) FwdC4Smem {
 #ifndef AMPS_C4_MINB
 #define AMPS_C4_MINB 1
 #endif
+#ifndef AMPS_C4_SXO_MINB
+#define AMPS_C4_SXO_MINB 2
+#endif
 template <int DP, int CL, bool VIRT, bool SXO = false>
 #if AMPS_C4_MINB
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(512, SXO ? AMPS_C4_SXO_MINB : 1)
 #else
 __global__ void __launch_bounds__(512)
 #endif
