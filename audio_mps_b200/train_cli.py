@@ -4,8 +4,10 @@
         --sample_duration=65536 --hparams=bond_dim=32,minibatch_size=64 --logdir=/tmp/amps --steps=100
 
 Launch under ``torchrun`` for batch data parallelism (one process per GPU; the batch is sharded and the
-packed kernel gradient is all-reduced once per step).  Scalars that the reference sends to TensorBoard
-(train.py:62-72) are written as JSON lines to ``{logdir}/scalars.jsonl``; a checkpoint
+packed kernel gradient is all-reduced once per step).  The summaries of train.py:62-85 go to TensorBoard event
+files in ``{logdir}`` -- scalars every step (also as JSON lines in ``{logdir}/scalars.jsonl``); every
+``--save_summaries_steps`` steps the ``data`` audio clips (5 at most), the ``frequencies`` histogram and, with
+``--visualize``, the ``data_waveform`` / ``sample_waveform`` images (train.py:74-85).  A checkpoint
 (``model.pt``: raw variables under the reference's names, Adam state, global_step) is written every
 ``--save_checkpoint_secs`` (60 s in the reference, train.py:93) and restored on restart.
 """
@@ -25,6 +27,47 @@ from . import HParams, PsiCMPS, RhoCMPS, default_hparams, get_audio
 from .train import Trainer, regulariser, shard_bounds
 
 
+def waveform_image(waveform, width=300, height=300):
+    """The picture of ``utils.waveform_plot`` (utils.py:10-17: signal against time, 3 x 3 inch figure) without
+    matplotlib: a [3, H, W] uint8 raster, white background, axes box, the waveform as a polyline."""
+    w = np.asarray(waveform, np.float64).ravel()
+    img = np.full((height, width), 255, np.uint8)
+    m = 12                                                           # margin of the axes box
+    img[m, m:width - m] = img[height - m - 1, m:width - m] = 0
+    img[m:height - m, m] = img[m:height - m, width - m - 1] = 0
+    if w.size:
+        lo, hi = float(w.min()), float(w.max())
+        if hi - lo < 1e-30:
+            lo, hi = lo - 1.0, hi + 1.0
+        nx = width - 2 * m - 2
+        # min / max of the samples that fall into each pixel column (a polyline through every sample)
+        edges = np.linspace(0, w.size, nx + 1).astype(np.int64)
+        for c in range(nx):
+            seg = w[edges[c]:max(edges[c + 1], edges[c] + 1)]
+            if seg.size == 0:
+                continue
+            y0 = (hi - float(seg.max())) / (hi - lo) * (height - 2 * m - 3)
+            y1 = (hi - float(seg.min())) / (hi - lo) * (height - 2 * m - 3)
+            img[m + 1 + int(y0):m + 2 + int(y1), m + 1 + c] = 40
+    return np.stack([img, img, img])
+
+
+def write_summaries(tb, step, batch, model, sample_rate, visualize=False, samples=None):
+    """train.py:74-85: audio summary of the batch (max_outputs = 5), histogram of the frequencies in Hz, and (with
+    --visualize) waveform images of the batch and of samples drawn from the model."""
+    batch = np.asarray(batch, np.float32)
+    for i in range(min(5, batch.shape[0])):
+        tb.add_audio(f"data/{i}", torch.from_numpy(batch[i:i + 1]), step, sample_rate=sample_rate)
+    with torch.no_grad():
+        tb.add_histogram("frequencies", (model.freqs / (2 * math.pi)).detach().float().cpu(), step)
+    if visualize:
+        for i in range(batch.shape[0]):
+            tb.add_image(f"data_waveform/{i}", waveform_image(batch[i]), step)
+        if samples is not None:
+            for i, w in enumerate(np.asarray(samples)):
+                tb.add_image(f"sample_waveform/{i}", waveform_image(w), step)
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--mps_model", default="psi_mps", choices=["rho_mps", "psi_mps"])                # train.py:18
@@ -37,6 +80,9 @@ def main(argv=None):
     ap.add_argument("--logdir", default="../logging/audio_mps")
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--save_checkpoint_secs", type=float, default=60.0)
+    ap.add_argument("--save_summaries_steps", type=int, default=100,
+                    help="cadence of the audio / histogram / image summaries (tf.contrib.training.train default)")
+    ap.add_argument("--visualize", action="store_true", help="waveform images of data and samples (train.py:24, 77-85)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--init_tf_checkpoint", default="",
                     help="TensorFlow V2 checkpoint prefix or directory (the reference's logdir) to start from")
@@ -109,6 +155,11 @@ def main(argv=None):
                 for k, v in rec.items():
                     if k != "step":
                         tb.add_scalar(k, v, trainer.global_step)
+                if args.save_summaries_steps > 0 and (trainer.global_step - 1) % args.save_summaries_steps == 0:
+                    smp = None
+                    if args.visualize and args.num_samples:
+                        smp = model.sample(args.num_samples, args.sample_duration).cpu().numpy()
+                    write_summaries(tb, trainer.global_step, batch, model, args.sample_rate, args.visualize, smp)
             if time.time() - last_save >= args.save_checkpoint_secs:
                 save()
                 last_save = time.time()

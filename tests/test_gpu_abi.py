@@ -135,10 +135,19 @@ def test_train_cli_trains_and_resumes(cuda, lib, tmp_path):
     from audio_mps_b200 import train_cli
     argv = ["--dataset=damped_sine", "--sample_duration=512", "--hparams=bond_dim=8,minibatch_size=4",
             f"--logdir={tmp_path}", "--steps=6", "--num_samples=2", "--save_checkpoint_secs=0"]
-    train_cli.main(argv)
+    train_cli.main(argv + ["--visualize", "--save_summaries_steps=4"])
     logdir = tmp_path / "damped_sine" / f"8_{1/16000}_4"
     recs = [json.loads(l) for l in open(logdir / "scalars.jsonl")]
     assert [r["step"] for r in recs] == [1, 2, 3, 4, 5, 6]
+    # the summaries of train.py:62-85 as TensorBoard events: scalars, data audio, frequency histogram, waveform images
+    from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+    ea = EventAccumulator(str(logdir), size_guidance={"audio": 0, "images": 0, "histograms": 0, "scalars": 0})
+    ea.Reload()
+    tags = ea.Tags()
+    assert {"model_loss", "total_loss", "A", "sigma", "h_l2norm", "r_l2norm", "gr_decay_time"} <= set(tags["scalars"])
+    assert "data/0" in tags["audio"] and "data/3" in tags["audio"] and "frequencies" in tags["histograms"]
+    assert "data_waveform/0" in tags["images"] and "sample_waveform/1" in tags["images"]
+    assert [e.step for e in ea.Audio("data/0")] == [1, 5]
     assert all(np.isfinite(r["total_loss"]) for r in recs)
     assert np.load(logdir / "samples.npy").shape == (2, 512)
     train_cli.main(argv[:4] + ["--steps=2", "--num_samples=0"])          # resumes from model.pt

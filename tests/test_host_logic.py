@@ -292,3 +292,34 @@ def test_host_generators_match_the_oracle_generators():
     a, b = prp(16, hp.A, np.random.default_rng(3)), random_raw_params(hp, np.random.default_rng(3))
     assert set(a) == set(b) and all(np.array_equal(a[k], b[k]) for k in b)
     assert np.array_equal(psn(hp.sigma, hp.delta_t, 100, 3, 5), osn(hp, 100, 3, 5))
+
+
+def test_waveform_image_and_summaries(tmp_path):
+    """utils.waveform_plot / the summaries block of train.py:62-85 without TF, tfplot or matplotlib."""
+    import types
+
+    import torch
+    from audio_mps_b200.train_cli import waveform_image, write_summaries
+    from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+    from torch.utils.tensorboard import SummaryWriter
+    x = np.sin(np.linspace(0, 20, 4000)).astype(np.float32)
+    img = waveform_image(x)
+    assert img.shape == (3, 300, 300) and img.dtype == np.uint8
+    inner = img[0, 13:-13, 13:-13]
+    assert (inner == 40).any(axis=0).all()                     # every pixel column carries part of the curve
+    assert (img[0, 12, 12:-12] == 0).all() and (img[0, 0] == 255).all()      # axes box, white margin
+    assert waveform_image(np.zeros(10)).shape == (3, 300, 300)  # constant signal: no division by zero
+    assert waveform_image(np.zeros(0)).shape == (3, 300, 300)
+    tb = SummaryWriter(str(tmp_path))
+    model = types.SimpleNamespace(freqs=torch.linspace(-3000.0, 3000.0, 8))
+    batch = np.stack([x, -x, 0.5 * x, x, x, x, x])
+    write_summaries(tb, 7, batch, model, 16000, visualize=True, samples=batch[:2])
+    tb.close()
+    ea = EventAccumulator(str(tmp_path), size_guidance={"audio": 0, "images": 0, "histograms": 0})
+    ea.Reload()
+    tags = ea.Tags()
+    assert sorted(tags["audio"]) == [f"data/{i}" for i in range(5)]          # max_outputs = 5
+    assert tags["histograms"] == ["frequencies"]
+    assert len([t for t in tags["images"] if t.startswith("data_waveform/")]) == 7
+    assert len([t for t in tags["images"] if t.startswith("sample_waveform/")]) == 2
+    assert ea.Audio("data/0")[0].sample_rate == 16000 and ea.Audio("data/0")[0].step == 7
