@@ -71,11 +71,52 @@ def one_case(case, seed, rng, dev, tmax_big, verbose):
         return None if ok else (case, D, B, T, K, el, eg)
 
 
+def run_samplers(n_cases=20, seed=0, verbose=True):
+    """PsiCMPS.sample_from_noise / RhoCMPS.sample_from_noise, trajectories and the Rho loss + gradient against the
+    oracle over random shapes (samples 1e-3 per waveform given the same noise; Rho gradients 1e-3)."""
+    from audio_mps_b200 import RhoCMPS
+    from oracle.cmps_oracle import RhoCMPSOracle
+    rng = np.random.default_rng(seed)
+    dev = torch.device("cuda", 0)
+    failures = []
+    for case in range(n_cases):
+        rho = case % 3 == 2
+        D = int(rng.integers(1, 33)) if rho else int(rng.choice([rng.integers(1, 33), rng.integers(33, 65), rng.integers(65, 129)]))
+        n = int(rng.integers(1, 7)) if (rho or D > 64) else int(rng.choice([1, 3, 9, 150, 300]))
+        L = int(rng.integers(1, 300 if n < 20 else 40))
+        ohp, php = hp_pair(bond_dim=D, minibatch_size=max(n, 1))
+        raw = random_raw_params(ohp, np.random.default_rng(7000 * (seed + 1) + case), rho=rho) if rho else \
+            random_raw_params(ohp, np.random.default_rng(7000 * (seed + 1) + case))
+        noise = (np.random.default_rng(9000 + case).standard_normal((L, n)) * ohp.sigma * np.sqrt(ohp.delta_t)).astype(np.float32)
+        if rho:
+            o, m = RhoCMPSOracle(ohp, raw, mode="f64"), RhoCMPS(php, device=dev)
+        else:
+            o, m = PsiCMPSOracle(ohp, raw, mode="f64"), PsiCMPS(php, device=dev)
+        set_raw(m, raw)
+        es = rel(m.sample_from_noise(noise).cpu().numpy(), o.sample_from_noise(noise).detach().numpy())
+        eg = 0.0
+        if rho and L >= 2:
+            data = damped_sine(n, L + 1, ohp.delta_t, np.random.default_rng(case))
+            ref = o.loss_per_clip(data)
+            gref = grads_of(o, ref.mean())
+            m.loss_per_clip(data).mean().backward()
+            eg = max(rel(getattr(m, k).grad.cpu().numpy(), gref["freqs" if k == "freqs_raw" else k])
+                     for k in ("Rx", "Ry", "freqs_raw", "Wx", "Wy", "A"))
+        ok = es <= 1e-3 and eg <= 1e-3 and np.isfinite(es) and np.isfinite(eg)
+        if verbose:
+            print(f"sampler case {case:3d} {'rho' if rho else 'psi'} D={D:3d} n={n:3d} L={L:3d}: samples {es:.2e} "
+                  f"rho-grad {eg:.2e} {'ok' if ok else 'FAIL'}", flush=True)
+        if not ok:
+            failures.append((case, rho, D, n, L, es, eg))
+    return failures
+
+
 if __name__ == "__main__":
     n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 40
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     tmax_big = int(sys.argv[3]) if len(sys.argv) > 3 else 60
     t0 = time.time()
     failures = run(n_cases, seed, tmax_big)
+    failures += run_samplers(max(n_cases // 2, 1), seed)
     print(f"{n_cases - len(failures)}/{n_cases} ok in {time.time() - t0:.0f} s")
     sys.exit(1 if failures else 0)
