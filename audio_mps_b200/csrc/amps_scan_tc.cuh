@@ -33,7 +33,8 @@ struct alignas(1024) ScanTcSmem {
   float2 cM[TC_D][TC_D];           // c' R^dag R  ( = N - I )
   float2 Rm[TC_D][TC_D];
   float2 qv[2][TC_D];              // q_k, by step parity
-  unsigned long long mbar;
+  unsigned long long mbar;         // all MMAs of a step are complete
+  unsigned long long mbar_lo;      // the E_lo pass of a step is complete (blo may be rewritten)
   uint32_t tmem_base;
 };
 
@@ -97,9 +98,10 @@ __device__ __forceinline__ float tc_trunc_tf32(float x) {
 // Dacc = exact fp32 copy of P^T that the MMAs accumulate P^T E^T onto.
 constexpr uint32_t TC_COL_X = 0, TC_COL_Z = 128, TC_COL_D = 256;
 
-// grid = B * nvc CTAs, block = 512 threads: warps 0-3 own the 128 TMEM lanes (epilogue),
-// warps 4-15 form E_k in shared memory; thread 0 issues the MMAs.
+// grid = B * nvc CTAs, block = 512 threads: warps 0-7 run the per-step epilogue (warp w: TMEM lanes 32 (w & 3) ..,
+// column-pair half w >> 2), warps 8-15 form E_k in shared memory; thread 0 issues the MMAs.
 constexpr int TC_THREADS = 512;
+constexpr int TC_EPI = 256;      // threads of the per-step epilogue (warps 0-7); the rest form E_k
 // HALF (bond dimension <= 32): E_k is zero outside rows/columns [0,32) of each real-form quadrant, i.e.
 // K blocks 1 and 3 of the B operand never change from zero -- they are neither re-formed nor multiplied.
 template <bool HALF>
@@ -136,6 +138,7 @@ __global__ void __launch_bounds__(TC_THREADS)
   }
   if (tid == 0) {
     mbar_init(&sm.mbar, 1);
+    mbar_init(&sm.mbar_lo, 1);
     mbar_fence_init_cluster();
   }
   if (warp == 0) {
@@ -165,58 +168,79 @@ __global__ void __launch_bounds__(TC_THREADS)
   // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_N >> 4) << 24);
 
+  // ---- producers: E_k = c' R^dag R + s_k R in real form [[Er,-Ei],[Ei,Er]], tf32 hi / lo, swizzled --------------
+  // One thread per (row a, 4 consecutive columns b): the complex element is computed once and written to its
+  // four real-form positions, hi and lo.  The MMAs of a step run the E_lo pass FIRST, so blo is free after a third
+  // of the step's tensor work: E_{k+1} is computed and its lo half written while the rest of step k's MMAs run;
+  // only the hi half (kept in registers meanwhile) is written between the steps.  (Rewriting the whole 128 KB
+  // operand between two steps was ~2 k of the 7.9 k cycles per step.)
+  constexpr int NPROD = TC_THREADS - TC_EPI;
+  constexpr int cq = Dq / 4;
+  constexpr int NITEM = (Dq * cq + NPROD - 1) / NPROD;
+  const int pt = tid - TC_EPI;
+  float4 keep_er[NITEM], keep_ei[NITEM];     // hi parts of the step being prepared
+  auto boff = [](int n, int cch) { return (cch / 8) * TC_TILE + n * 128 + (((cch % 8) ^ (n & 7)) * 16); };
+  auto produce_lo = [&](int k) {             // E_k: lo half -> blo, hi half -> registers
+    const float s = (xb[k + 1] - xb[k]) / A;                           // model.py:263, 303
+#pragma unroll
+    for (int it = 0; it < NITEM; ++it) {
+      const int idx = pt + it * NPROD;
+      if (idx < Dq * cq) {
+        const int a = idx / cq, c = idx % cq;                           // c: 16-byte chunk within [0, D)
+        float er[4], ei[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 m = sm.cM[a][4 * c + e], r = sm.Rm[a][4 * c + e];
+          er[e] = fmaf(s, r.x, m.x);
+          ei[e] = fmaf(s, r.y, m.y);
+        }
+        const float4 erh = make_float4(tc_trunc_tf32(er[0]), tc_trunc_tf32(er[1]), tc_trunc_tf32(er[2]), tc_trunc_tf32(er[3]));
+        const float4 eih = make_float4(tc_trunc_tf32(ei[0]), tc_trunc_tf32(ei[1]), tc_trunc_tf32(ei[2]), tc_trunc_tf32(ei[3]));
+        const float4 erl = make_float4(er[0] - erh.x, er[1] - erh.y, er[2] - erh.z, er[3] - erh.w);
+        const float4 eil = make_float4(ei[0] - eih.x, ei[1] - eih.y, ei[2] - eih.z, ei[3] - eih.w);
+        keep_er[it] = erh;
+        keep_ei[it] = eih;
+        const int cl = c, cr = c + TC_D / 4, rt = a, rb = a + TC_D;   // chunk within a 128-column row: left c, right c + 16
+        *reinterpret_cast<float4*>(sm.blo + boff(rt, cl)) = erl;                                        // top-left      Er
+        *reinterpret_cast<float4*>(sm.blo + boff(rt, cr)) = make_float4(-eil.x, -eil.y, -eil.z, -eil.w);  // top-right    -Ei
+        *reinterpret_cast<float4*>(sm.blo + boff(rb, cl)) = eil;                                        // bottom-left   Ei
+        *reinterpret_cast<float4*>(sm.blo + boff(rb, cr)) = erl;                                        // bottom-right  Er
+      }
+    }
+  };
+  auto produce_hi = [&]() {
+#pragma unroll
+    for (int it = 0; it < NITEM; ++it) {
+      const int idx = pt + it * NPROD;
+      if (idx < Dq * cq) {
+        const int a = idx / cq, c = idx % cq;
+        const float4 erh = keep_er[it], eih = keep_ei[it];
+        const int cl = c, cr = c + TC_D / 4, rt = a, rb = a + TC_D;
+        *reinterpret_cast<float4*>(sm.bhi + boff(rt, cl)) = erh;
+        *reinterpret_cast<float4*>(sm.bhi + boff(rt, cr)) = make_float4(-eih.x, -eih.y, -eih.z, -eih.w);
+        *reinterpret_cast<float4*>(sm.bhi + boff(rb, cl)) = eih;
+        *reinterpret_cast<float4*>(sm.bhi + boff(rb, cr)) = erh;
+      }
+    }
+  };
+  if (tid >= TC_EPI && nloc > 0) produce_lo(0);
+
   for (int kk = 0; kk <= nloc; ++kk) {
     if (kk > 0) mbar_wait_cta(&sm.mbar, (kk - 1) & 1); // the MMAs of step kk-1 are complete (tcgen05.commit)
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    if (tid >= 128) {
+    if (tid >= TC_EPI) {
       if (kk < nloc) {
-        // ---- producers: E_k = c' R^dag R + s_k R in real form [[Er,-Ei],[Ei,Er]], hi/lo, swizzled ----
-        const int pt = tid - 128;
-        const float s = (xb[kk + 1] - xb[kk]) / A;                       // model.py:263, 303
         if (pt < TC_D) sm.qv[kk & 1][pt] = qb[(size_t)kk * TC_D + pt];
-        // one thread per (row a, 4 consecutive columns b): the complex element is computed once and
-        // written to its four real-form positions  [ Er -Ei ; Ei Er ], hi and lo
-        constexpr int cq = Dq / 4;
-        for (int idx = pt; idx < Dq * cq; idx += TC_THREADS - 128) {
-          const int a = idx / cq, c = idx % cq;                           // c: 16-byte chunk within [0, D)
-          float er[4], ei[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 m = sm.cM[a][4 * c + e], r = sm.Rm[a][4 * c + e];
-            er[e] = fmaf(s, r.x, m.x);
-            ei[e] = fmaf(s, r.y, m.y);
-          }
-          float4 erh, erl, eih, eil, nih, nil_;
-          float* ph[6] = {&erh.x, &erl.x, &eih.x, &eil.x, &nih.x, &nil_.x};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float h1 = tc_trunc_tf32(er[e]), h2 = tc_trunc_tf32(ei[e]);
-            ph[0][e] = h1;
-            ph[1][e] = er[e] - h1;
-            ph[2][e] = h2;
-            ph[3][e] = ei[e] - h2;
-            ph[4][e] = -h2;
-            ph[5][e] = -(ei[e] - h2);
-          }
-          // chunk index within a 128-column row: left half c, right half c + 16
-          const int cl = c, cr = c + TC_D / 4;
-          const int rt = a, rb = a + TC_D;
-          auto off = [](int n, int cch) { return (cch / 8) * TC_TILE + n * 128 + (((cch % 8) ^ (n & 7)) * 16); };
-          *reinterpret_cast<float4*>(sm.bhi + off(rt, cl)) = erh;    // top-left      Er
-          *reinterpret_cast<float4*>(sm.blo + off(rt, cl)) = erl;
-          *reinterpret_cast<float4*>(sm.bhi + off(rt, cr)) = nih;    // top-right    -Ei
-          *reinterpret_cast<float4*>(sm.blo + off(rt, cr)) = nil_;
-          *reinterpret_cast<float4*>(sm.bhi + off(rb, cl)) = eih;    // bottom-left   Ei
-          *reinterpret_cast<float4*>(sm.blo + off(rb, cl)) = eil;
-          *reinterpret_cast<float4*>(sm.bhi + off(rb, cr)) = erh;    // bottom-right  Er
-          *reinterpret_cast<float4*>(sm.blo + off(rb, cr)) = erl;
-        }
+        produce_hi();                                   // E_kk, hi half (lo half is in place already)
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
       }
     } else if (kk > 0) {
       // ---- epilogue of step kk-1: Dacc = (P + E P)^T ; rotate column pairs (a, a+D) by q_a ----
+      // (eight warps: warp w owns TMEM lanes 32 (w & 3) .. and the column-pair half h = w >> 2)
       const float2* q = sm.qv[(kk - 1) & 1];
-      for (int h = 0; h < 2; ++h) {
+      const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+      {
+        const int h = warp >> 2;
         float ya[32], yb[32];
         tc_ld32(lane_base + TC_COL_D + 32 * h, ya);
         tc_ld32(lane_base + TC_COL_D + TC_D + 32 * h, yb);
@@ -246,11 +270,11 @@ __global__ void __launch_bounds__(TC_THREADS)
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     if (tid == 0 && kk < nloc) {
-      // Dacc += P_hi^T E_hi^T + P_lo^T E_hi^T + P_hi^T E_lo^T   (A from tensor memory, B from smem)
+      // Dacc += P_hi^T E_lo^T (first: frees blo) + P_hi^T E_hi^T + P_lo^T E_hi^T   (A from tensor memory, B from smem)
 #pragma unroll 1
       for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t acol = tmem + ((pass == 1) ? TC_COL_Z : TC_COL_X);
-        const uint8_t* bsm = (pass == 2) ? sm.blo : sm.bhi;
+        const uint32_t acol = tmem + ((pass == 2) ? TC_COL_Z : TC_COL_X);
+        const uint8_t* bsm = (pass == 0) ? sm.blo : sm.bhi;
 #pragma unroll 1
         for (int kb = 0; kb < TC_NKB; ++kb) {
           if (Dq < TC_D && (kb & 1)) continue;          // all-zero K block of E_k^T
@@ -259,10 +283,20 @@ __global__ void __launch_bounds__(TC_THREADS)
           for (int ks = 0; ks < TC_KB / 8; ++ks)      // UMMA_K = 8 tf32: 8 TMEM columns / 32 smem bytes
             tc_mma_ts(tmem + TC_COL_D, acol + kb * TC_KB + ks * 8, db0 + 2 * ks, idesc, 1u);
         }
+        if (pass == 0)
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
+                           tc_smem_u32(&sm.mbar_lo))
+                       : "memory");
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
                        tc_smem_u32(&sm.mbar))
                    : "memory");
+    }
+    if (tid >= TC_EPI && kk + 1 < nloc) {
+      // E_{kk+1}: computed now, its lo half written as soon as step kk's E_lo pass has been read
+      mbar_wait_cta(&sm.mbar_lo, kk & 1);
+      produce_lo(kk + 1);
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     }
   }
 
