@@ -598,7 +598,7 @@ int amps_c4_cluster_capacity(bool bwd) {
     return n;
   };
   return bwd ? query(psi_bwd_c4_kernel<128, C4_CL, false, false>, sizeof(BwdC4Smem<128, C4_CL>))
-             : query(psi_fwd_c4_kernel<128, C4_CL, false, true>, sizeof(FwdC4Smem<128, C4_CL>));
+             : query(psi_fwd_c4_kernel<128, C4_CL, false, true, true>, sizeof(FwdC4Smem<128, C4_CL>));
 }
 cudaError_t amps_set_all_func_attrs() {
   using namespace amps;
@@ -616,6 +616,7 @@ cudaError_t amps_set_all_func_attrs() {
   if ((e = set_smem(psi_sx_tc_kernel<64>, sizeof(SxSmem<64>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_sx2_tc_kernel, sizeof(Sx2Smem) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_fwd_c4_kernel<128, C4_CL, false, true>, sizeof(FwdC4Smem<128, C4_CL>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_fwd_c4_kernel<128, C4_CL, false, true, true>, sizeof(FwdC4Smem<128, C4_CL>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_tiles_tc_kernel<128, 1>, sizeof(TilesSmem<128, 1>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_tiles_tc_kernel<128, 2>, sizeof(TilesSmem<128, 2>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_tiles_tc_kernel<128, 3>, sizeof(TilesSmem<128, 3>) + 1024)) != cudaSuccess) return e;
@@ -666,7 +667,9 @@ int launch_psi_fwd(amps_ctx* ctx, int DP, int B, const FwdArgs& a, cudaStream_t 
         psi_sx2_panel_kernel<<<8, SX_THREADS, 0, st>>>(a.matS, a.spanel);
         LAUNCH_CHECK(ctx, "psi_sx2_panel_kernel");
       }
-      CUDA_TRY(ctx, launch_cluster(psi_fwd_c4_kernel<128, C4_CL, false, true>, B, C4_CL, 512, sizeof(FwdC4Smem<128, C4_CL>), st,
+      // more clips than one-CTA-per-SM clusters fit: the 64-register build, two clusters per SM quadruple
+      auto kern = B > ctx->c4_cap_bwd ? psi_fwd_c4_kernel<128, C4_CL, false, true, true> : psi_fwd_c4_kernel<128, C4_CL, false, true>;
+      CUDA_TRY(ctx, launch_cluster(kern, B, C4_CL, 512, sizeof(FwdC4Smem<128, C4_CL>), st,
                                    a.matN, a.matR, a.matS, a.qtab, a.psi0p, a.x, a.T, a.A, a.loss, a.lossd, a.traj,
                                    a.scales, nchunks, (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg));
       LAUNCH_CHECK(ctx, "psi_fwd_c4_kernel<chain>");

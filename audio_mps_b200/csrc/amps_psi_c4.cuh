@@ -56,12 +56,12 @@ struct alignas(16) FwdC4Smem {
 #ifndef AMPS_C4_MINB
 #define AMPS_C4_MINB 1
 #endif
-#ifndef AMPS_C4_SXO_MINB
-#define AMPS_C4_SXO_MINB 2
-#endif
-template <int DP, int CL, bool VIRT, bool SXO = false>
+// OCC2: compiled for two CTAs per SM (64 registers; the chain-only forward needs no more and 103 KB of shared
+// memory): with more clips than one-CTA-per-SM clusters fit, two clusters share every SM quadruple and all 148 SMs
+// are used (C3: forward chain 134.8 -> 117.7 ms).  Up to that many clips the 99-register build is 5-7 % faster.
+template <int DP, int CL, bool VIRT, bool SXO = false, bool OCC2 = false>
 #if AMPS_C4_MINB
-__global__ void __launch_bounds__(512, SXO ? AMPS_C4_SXO_MINB : 1)
+__global__ void __launch_bounds__(512, OCC2 ? 2 : 1)
 #else
 __global__ void __launch_bounds__(512)
 #endif
