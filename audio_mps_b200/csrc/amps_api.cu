@@ -520,6 +520,7 @@ struct FwdArgs {
   SegFwd seg;
   float4* spanel = nullptr;      // D = 128: panel-ordered tf32 split of S for the expectation pass
   bool build_panel = true;       // (built by the first wave only: later waves run next to a reader of it)
+  bool paired = false;           // replay of the checkpointed backward (family_of)
   double* loss_part = nullptr;   // D > 32 saving forward: per-split loss sums of the expectation pass
   int sx_nsplit = 1, sx_sps = 0;
   bool allow_split = false;      // whole-batch call on the caller's stream: partial waves may be pipelined
@@ -543,13 +544,19 @@ struct BwdArgs {
   int tiles_nsplit = 1;        // partial tile sets per clip in G (D > 32: tensor-core tile kernel)
   int tiles_sps = 0;           // steps per split (multiple of 32)
   bool allow_split = false;
+  bool paired = false;         // adjoint of the checkpointed backward, next to a replay (family_of)
 };
 
 // which kernel family serves (DP, B) on this context
 enum class Fam { C4, CL, WS, UNI };
-Fam family_of(const amps_ctx* ctx, int DP, int B) {
+// paired: the launch is one of the two concurrent kernels of the checkpointed backward (replay of window j-1 next
+// to the adjoint of window j).  Two 2-CTA-per-clip cluster kernels only run side by side while 4 B <= #SMs; above
+// that (C1: 64 clips) the single-CTA family lets both fit (2 B <= #SMs) -- C1 at K = 2048: replay + adjoint
+// 18.1 ms serialised on the cluster kernels, 13.9 ms overlapped on the single-CTA ones.
+Fam family_of(const amps_ctx* ctx, int DP, int B, bool paired = false) {
   if (DP == 128) return Fam::C4;
   if (DP == 64) return Fam::UNI;
+  if (paired && ctx->ckpt_overlap && 4 * B > ctx->num_sms) return Fam::WS;
   return (ctx->use_clusters && 2 * B <= ctx->num_sms) ? Fam::CL : Fam::WS;
 }
 
@@ -644,7 +651,7 @@ int launch_psi_fwd(amps_ctx* ctx, int DP, int B, const FwdArgs& a, cudaStream_t 
   const int nsteps = a.T - 1;
   const int chl = chunk_len_of(DP);
   const int nchunks = (nsteps + chl - 1) / chl;
-  const Fam fam = family_of(ctx, DP, B);
+  const Fam fam = family_of(ctx, DP, B, a.paired);
   auto sx_args = [&]() {
     SxArgs g{};
     g.matS = a.matS;
@@ -740,7 +747,7 @@ int launch_psi_bwd(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t 
   const int nsteps = a.T - 1;
   const int chl = chunk_len_of(DP);
   const int nchunks = (nsteps + chl - 1) / chl;
-  const Fam fam = family_of(ctx, DP, B);
+  const Fam fam = family_of(ctx, DP, B, a.paired);
   // the gradient tiles as GEMMs over the time axis on the tensor cores (after a chain-only adjoint sweep that
   // left mu_k in place of the consumed S x'_k)
   auto tiles_args = [&]() {
@@ -1177,6 +1184,7 @@ int amps_psi_loss_bwd_k(amps_ctx* ctx, const amps_params* p, const float* x_dev,
     a.spanel = (float4*)(ws + L.base.spanel);
     a.sx_nsplit = sx_nsplit_of(DP, B, L.W);
     a.sx_sps = sx_steps_per_split(L.W, a.sx_nsplit);
+    a.paired = true;
     return launch_psi_fwd(ctx, DP, B, a, s2);
   };
   auto adjoint = [&](int j) -> int {
@@ -1190,6 +1198,7 @@ int amps_psi_loss_bwd_k(amps_ctx* ctx, const amps_params* p, const float* x_dev,
               (const float2*)(ws + L.sptraj[i]), (const float2*)(ws + L.ev[i]), seg};
     a.tiles_nsplit = ck_nsplit;     // fixed by the window length W: every window fills the same partial slots
     a.tiles_sps = ck_sps;
+    a.paired = true;
     return launch_psi_bwd(ctx, DP, B, a, st);
   };
   PROF_BEGIN(ctx, 1, st);
