@@ -620,6 +620,8 @@ cudaError_t amps_set_all_func_attrs() {
   if ((e = set_smem(psi_tiles_tc_kernel<64, 0>, sizeof(TilesSmem<64, 0>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_tiles_tc_kernel<64, 1>, sizeof(TilesSmem<64, 1>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_fwd_uni_kernel<64, 8, false, true>, sizeof(FwdSmemUni<64, 8, true>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_fwd_uni_kernel<64, 4, false, true>, sizeof(FwdSmemUni<64, 4, true>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_bwd_uni_kernel<64, 4, false, false>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_sx_tc_kernel<64>, sizeof(SxSmem<64>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_sx2_tc_kernel, sizeof(Sx2Smem) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_fwd_c4_kernel<128, C4_CL, false, true>, sizeof(FwdC4Smem<128, C4_CL>))) != cudaSuccess) return e;
@@ -719,7 +721,10 @@ int launch_psi_fwd(amps_ctx* ctx, int DP, int B, const FwdArgs& a, cudaStream_t 
       // chain-only forward (x'_k and |x_k|^2 stored), then S x'_k, E_k and the loss as ONE GEMM over the time
       // axis on the tensor cores, in place
       if (phase != 2) {
-        psi_fwd_uni_kernel<DPc, NQc, false, true><<<B, DPc * NQc, sizeof(FwdSmemUni<DPc, NQc, true>), st>>>(
+        // FOUR lanes per row (256 threads, 16 columns of N and R per thread, 104 registers, still two CTAs per SM):
+        // one shuffle level less and an 8-warp instead of a 16-warp barrier on every step -- C4's chain
+        // 39.6 -> 30.0 ms.  (The full kernel keeps 8 lanes per row: with the S slices it would need > 128 registers.)
+        psi_fwd_uni_kernel<DPc, 4, false, true><<<B, DPc * 4, sizeof(FwdSmemUni<DPc, 4, true>), st>>>(
             a.matN, a.matR, a.matS, a.qtab, a.psi0p, a.x, a.T, a.A, a.loss, a.lossd, a.traj, a.scales, nchunks,
             (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg);
         LAUNCH_CHECK(ctx, "psi_fwd_uni_kernel<chain>");
@@ -817,7 +822,8 @@ int launch_psi_bwd(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t 
       // chain-only adjoint sweep (mu_k replaces the consumed S x'_k in place), then the gradient tiles as
       // GEMMs over the time axis on the tensor cores
       if (phase != 2) {
-        psi_bwd_uni_kernel<DPc, NQc, false, false><<<B, DPc * NQc, sizeof(BwdSmemUni<DPc>), st>>>(
+        // (four lanes per row, 256 threads, 118 registers -- as the chain-only forward: C4's chain 46.5 -> 40.5 ms)
+        psi_bwd_uni_kernel<DPc, 4, false, false><<<B, DPc * 4, sizeof(BwdSmemUni<DPc>), st>>>(
             a.matN, a.matRH, a.matS, a.qtab, a.ttab, a.x, a.T, a.A, a.w, a.traj, a.scales, nchunks, a.G, a.gf,
             a.lam0, a.gAdir, (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg, const_cast<float2*>(a.sptraj));
         LAUNCH_CHECK(ctx, "psi_bwd_uni_kernel<chain>");
