@@ -588,7 +588,7 @@ int amps_c4_cluster_capacity(bool bwd) {
   auto query = [&](auto kern, size_t smem) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(C4_CL * 64);
-    cfg.blockDim = dim3(512);
+    cfg.blockDim = dim3(256);
     cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -604,8 +604,8 @@ int amps_c4_cluster_capacity(bool bwd) {
     }
     return n;
   };
-  return bwd ? query(psi_bwd_c4_kernel<128, C4_CL, false, false>, sizeof(BwdC4Smem<128, C4_CL>))
-             : query(psi_fwd_c4_kernel<128, C4_CL, false, true, true>, sizeof(FwdC4Smem<128, C4_CL>));
+  return bwd ? query(psi_bwd_c4_kernel<128, C4_CL, false, false, 256>, sizeof(BwdC4Smem<128, C4_CL>))
+             : query(psi_fwd_c4_kernel<128, C4_CL, false, true, true, 256>, sizeof(FwdC4Smem<128, C4_CL>));
 }
 cudaError_t amps_set_all_func_attrs() {
   using namespace amps;
@@ -624,13 +624,12 @@ cudaError_t amps_set_all_func_attrs() {
   if ((e = set_smem(psi_bwd_uni_kernel<64, 4, false, false>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_sx_tc_kernel<64>, sizeof(SxSmem<64>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_sx2_tc_kernel, sizeof(Sx2Smem) + 1024)) != cudaSuccess) return e;
-  if ((e = set_smem(psi_fwd_c4_kernel<128, C4_CL, false, true>, sizeof(FwdC4Smem<128, C4_CL>))) != cudaSuccess) return e;
-  if ((e = set_smem(psi_fwd_c4_kernel<128, C4_CL, false, true, true>, sizeof(FwdC4Smem<128, C4_CL>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_tiles_tc_kernel<128, 1>, sizeof(TilesSmem<128, 1>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_tiles_tc_kernel<128, 2>, sizeof(TilesSmem<128, 2>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_tiles_tc_kernel<128, 3>, sizeof(TilesSmem<128, 3>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_sample_c4_kernel<128, C4_CL>, sizeof(SampleC4Smem<128, C4_CL>))) != cudaSuccess) return e;
-  if ((e = set_smem(psi_bwd_c4_kernel<128, C4_CL, false, false>, sizeof(BwdC4Smem<128, C4_CL>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_bwd_c4_kernel<128, C4_CL, false, false, 256>, sizeof(BwdC4Smem<128, C4_CL>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_fwd_c4_kernel<128, C4_CL, false, true, true, 256>, sizeof(FwdC4Smem<128, C4_CL>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_bwd_uni_kernel<64, 8, true, false>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_bwd_uni_kernel<64, 8, true, true>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_sample_kernel<64, 8>, sizeof(SampleSmem<64>))) != cudaSuccess) return e;
@@ -676,9 +675,10 @@ int launch_psi_fwd(amps_ctx* ctx, int DP, int B, const FwdArgs& a, cudaStream_t 
         psi_sx2_panel_kernel<<<8, SX_THREADS, 0, st>>>(a.matS, a.spanel);
         LAUNCH_CHECK(ctx, "psi_sx2_panel_kernel");
       }
-      // more clips than one-CTA-per-SM clusters fit: the 64-register build, two clusters per SM quadruple
-      auto kern = B > ctx->c4_cap_bwd ? psi_fwd_c4_kernel<128, C4_CL, false, true, true> : psi_fwd_c4_kernel<128, C4_CL, false, true>;
-      CUDA_TRY(ctx, launch_cluster(kern, B, C4_CL, 512, sizeof(FwdC4Smem<128, C4_CL>), st,
+      // 256 threads: 8 lanes per row, 16 columns of N and R per thread (one shuffle level less and half the warps
+      // at every exchange than the 512-thread build; 113 registers, 103 KB: two clusters per SM quadruple)
+      CUDA_TRY(ctx, launch_cluster(psi_fwd_c4_kernel<128, C4_CL, false, true, true, 256>, B, C4_CL, 256,
+                                   sizeof(FwdC4Smem<128, C4_CL>), st,
                                    a.matN, a.matR, a.matS, a.qtab, a.psi0p, a.x, a.T, a.A, a.loss, a.lossd, a.traj,
                                    a.scales, nchunks, (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg));
       LAUNCH_CHECK(ctx, "psi_fwd_c4_kernel<chain>");
@@ -777,7 +777,8 @@ int launch_psi_bwd(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t 
   };
   if (fam == Fam::C4 && ctx->tc_tiles) {
     if (phase < 2) {
-      CUDA_TRY(ctx, launch_cluster(psi_bwd_c4_kernel<128, C4_CL, false, false>, B, C4_CL, 512, sizeof(BwdC4Smem<128, C4_CL>), st,
+      CUDA_TRY(ctx, launch_cluster(psi_bwd_c4_kernel<128, C4_CL, false, false, 256>, B, C4_CL, 256,
+                                   sizeof(BwdC4Smem<128, C4_CL>), st,
                                    a.matN, a.matRH, a.matS, a.qtab, a.ttab, a.x, a.T, a.A, a.w, a.traj, a.scales, nchunks,
                                    a.G, a.gf, a.lam0, a.gAdir, (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg,
                                    const_cast<float2*>(a.sptraj)));

@@ -21,14 +21,14 @@ namespace amps {
 
 constexpr int CH4 = 16;
 
-template <int DP, int CL>
+template <int DP, int CL, int NTHREADS = 512>
 struct C4 {
   static constexpr int RP = DP / CL;      // rows per CTA
-  static constexpr int NTL = 512;         // threads per CTA
+  static constexpr int NTL = NTHREADS;    // threads per CTA (512: 16 lanes per row; 256: 8 lanes, 16 columns each)
   static constexpr int NQ = NTL / RP;     // lanes per row
   static constexpr int CPT = DP / NQ;     // complex columns per thread
   static constexpr int NP = CPT / 2;
-  static_assert(NTL / 32 == CH4, "one warp per step in the chunk-end scalar passes");
+  static_assert(CH4 % (NTL / 32) == 0, "whole steps per warp in the chunk-end scalar passes");
   static_assert(RP == 32, "own-row partial sums are one warp wide");
   static_assert(2 * CL <= NQ, "broadcast lanes");
 };
@@ -59,11 +59,11 @@ struct alignas(16) FwdC4Smem {
 // OCC2: compiled for two CTAs per SM (64 registers; the chain-only forward needs no more and 103 KB of shared
 // memory): with more clips than one-CTA-per-SM clusters fit, two clusters share every SM quadruple and all 148 SMs
 // are used (C3: forward chain 134.8 -> 117.7 ms).  Up to that many clips the 99-register build is 5-7 % faster.
-template <int DP, int CL, bool VIRT, bool SXO = false, bool OCC2 = false>
+template <int DP, int CL, bool VIRT, bool SXO = false, bool OCC2 = false, int NTHREADS = 512>
 #if AMPS_C4_MINB
-__global__ void __launch_bounds__(512, OCC2 ? 2 : 1)
+__global__ void __launch_bounds__(NTHREADS, OCC2 ? 2 : 1)
 #else
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(NTHREADS)
 #endif
     psi_fwd_c4_kernel(const float2* __restrict__ matN, const float2* __restrict__ matR,
                       const float2* __restrict__ matS, const float2* __restrict__ qtab_,
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(512)
   // the clips already done) may start as soon as every CTA of this grid is resident
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const float A = a_get(A_);
-  using Cf = C4<DP, CL>;
+  using Cf = C4<DP, CL, NTHREADS>;
   constexpr int NQ = Cf::NQ, CPT = Cf::CPT, RP = Cf::RP, NTL = Cf::NTL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FwdC4Smem<DP, CL>& sm = *reinterpret_cast<FwdC4Smem<DP, CL>*>(smem_raw);
@@ -219,9 +219,10 @@ __global__ void __launch_bounds__(512)
         red += __shfl_xor_sync(0xffffffffu, red, 2);
         red += __shfl_xor_sync(0xffffffffu, red, 4);
       }
-      // 16-lane row reduction, the previous step's S x' FMAs in the shuffle shadows
+      // row reduction over the NQ lanes of a row, the previous step's S x' FMAs in the shuffle shadows
       float2 p0 = make_float2(0.f, 0.f), p1 = p0;
-      constexpr int LV = 4;
+      static_assert(NQ == 16 || (NQ == 8 && SXO), "the expectation pipeline's pair reduction is written for 16 lanes");
+      constexpr int LV = NQ == 16 ? 4 : 3;
       constexpr int CPL = (CPT + LV - 1) / LV;
 #pragma unroll
       for (int lv = 0; lv < LV; ++lv) {
@@ -275,8 +276,7 @@ __global__ void __launch_bounds__(512)
     __syncthreads();  // (A)
 
     if (!SXO) {
-    {  // this CTA's partial of Re(x'^dag S x') for step `warp`, handed to every CTA of the cluster
-        const int kk = warp;
+    for (int kk = warp; kk < CH4; kk += NTL / 32) {  // this CTA's partial of Re(x'^dag S x') per step, to every CTA of the cluster
         float en = 0.f;
         if (kk < len) {
 #pragma unroll
@@ -286,8 +286,7 @@ __global__ void __launch_bounds__(512)
         if (lane < CL && kk < len) st_dsmem_f1(dsmem_addr(&sm.enx[rank][kk], (unsigned)lane), en);
       }
       cluster_sync_all();  // (X1)
-      {  // per-step scalars, identical on every CTA (same operands, same order)
-        const int kk = warp;
+      for (int kk = warp; kk < CH4; kk += NTL / 32) {  // per-step scalars, identical on every CTA (same operands, same order)
         float nu2 = 0.f;
         if (kk < len) {
 #pragma unroll
@@ -305,14 +304,15 @@ __global__ void __launch_bounds__(512)
         }
       }
     } else {   // |x_k|^2 per step (E_k: psi_sx_tc_kernel)
-      const int kk = warp;
-      float nu2 = 0.f;
-      if (kk < len) {
+      for (int kk = warp; kk < CH4; kk += NTL / 32) {
+        float nu2 = 0.f;
+        if (kk < len) {
 #pragma unroll
-        for (int r = 0; r < DP / 32; ++r) nu2 += cabs2(sm.xs[kk][lane + 32 * r]);
+          for (int r = 0; r < DP / 32; ++r) nu2 += cabs2(sm.xs[kk][lane + 32 * r]);
+        }
+        nu2 = warp_sum_f(nu2);
+        if (lane == 0 && kk < len) sm.evs[kk] = make_float2(0.f, nu2);
       }
-      nu2 = warp_sum_f(nu2);
-      if (lane == 0 && kk < len) sm.evs[kk] = make_float2(0.f, nu2);
     }
     if (c + 1 < nchunks) compute_s(buf ^ 1, min(CH4, nsteps - (k0 + CH4)));
     // rescale by 1/|x_{k0+len}| (every warp of every CTA computes the same norm)
@@ -379,11 +379,11 @@ struct alignas(16) BwdC4Smem {
 // TILES = false: chain only -- mu_k goes to row k of mu_out[b] (own rows of every CTA; may alias sptraj, whose
 // rows of a chunk are in shared memory two chunks before its mu rows are written) and the gradient tiles are
 // contracted afterwards on the tensor cores (amps_tiles_tc.cuh).
-template <int DP, int CL, bool VIRT, bool TILES = true>
+template <int DP, int CL, bool VIRT, bool TILES = true, int NTHREADS = 512>
 #if AMPS_C4_MINB
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 #else
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(NTHREADS)
 #endif
     psi_bwd_c4_kernel(const float2* __restrict__ matN, const float2* __restrict__ matRH,
                       const float2* __restrict__ matS, const float2* __restrict__ qtab_,
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(512)
                       SegBwd seg, float2* __restrict__ mu_out = nullptr) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see psi_fwd_c4_kernel
   const float A = a_get(A_);
-  using Cf = C4<DP, CL>;
+  using Cf = C4<DP, CL, NTHREADS>;
   constexpr int NQ = Cf::NQ, CPT = Cf::CPT, NP = Cf::NP, RP = Cf::RP, NTL = Cf::NTL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdC4Smem<DP, CL>& sm = *reinterpret_cast<BwdC4Smem<DP, CL>*>(smem_raw);
@@ -624,8 +624,11 @@ __global__ void __launch_bounds__(512)
       lp.y += oy;
       lp.x += __shfl_xor_sync(0xffffffffu, lp.x, 4);
       lp.y += __shfl_xor_sync(0xffffffffu, lp.y, 4);
-      lp.x += __shfl_xor_sync(0xffffffffu, lp.x, 8);
-      lp.y += __shfl_xor_sync(0xffffffffu, lp.y, 8);
+      if (NQ == 16) {
+        lp.x += __shfl_xor_sync(0xffffffffu, lp.x, 8);
+        lp.y += __shfl_xor_sync(0xffffffffu, lp.y, 8);
+      }
+      static_assert(NQ == 16 || NQ == 8, "row reduction levels");
       lam.x = fmaf(be, xk.x, lp.x);
       lam.y = fmaf(be, xk.y, lp.y);
       // ---- adjoint of x' for step kk-1 --------------------------------------------------
