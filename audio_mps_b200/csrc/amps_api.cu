@@ -318,6 +318,7 @@ cudaError_t launch_cluster(K kern, int nclusters, int CL, int threads, size_t sm
   return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 constexpr int C4_CL = 4;
+constexpr int C4_CHAIN_THREADS = 128;   // threads per CTA of the chain-only D = 128 kernels (launch_psi_fwd)
 
 // plain launch, optionally with programmatic stream serialisation: the kernel may start once every CTA of the
 // kernel queued before it in the stream has executed griddepcontrol.launch_dependents (or exited) -- it does NOT
@@ -588,7 +589,7 @@ int amps_c4_cluster_capacity(bool bwd) {
   auto query = [&](auto kern, size_t smem) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(C4_CL * 64);
-    cfg.blockDim = dim3(256);
+    cfg.blockDim = dim3(C4_CHAIN_THREADS);
     cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -604,8 +605,8 @@ int amps_c4_cluster_capacity(bool bwd) {
     }
     return n;
   };
-  return bwd ? query(psi_bwd_c4_kernel<128, C4_CL, false, false, 256>, sizeof(BwdC4Smem<128, C4_CL>))
-             : query(psi_fwd_c4_kernel<128, C4_CL, false, true, true, 256>, sizeof(FwdC4Smem<128, C4_CL>));
+  return bwd ? query(psi_bwd_c4_kernel<128, C4_CL, false, false, C4_CHAIN_THREADS>, sizeof(BwdC4Smem<128, C4_CL>))
+             : query(psi_fwd_c4_kernel<128, C4_CL, false, true, true, C4_CHAIN_THREADS>, sizeof(FwdC4Smem<128, C4_CL>));
 }
 cudaError_t amps_set_all_func_attrs() {
   using namespace amps;
@@ -628,8 +629,8 @@ cudaError_t amps_set_all_func_attrs() {
   if ((e = set_smem(psi_tiles_tc_kernel<128, 2>, sizeof(TilesSmem<128, 2>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_tiles_tc_kernel<128, 3>, sizeof(TilesSmem<128, 3>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_sample_c4_kernel<128, C4_CL>, sizeof(SampleC4Smem<128, C4_CL>))) != cudaSuccess) return e;
-  if ((e = set_smem(psi_bwd_c4_kernel<128, C4_CL, false, false, 256>, sizeof(BwdC4Smem<128, C4_CL>))) != cudaSuccess) return e;
-  if ((e = set_smem(psi_fwd_c4_kernel<128, C4_CL, false, true, true, 256>, sizeof(FwdC4Smem<128, C4_CL>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_bwd_c4_kernel<128, C4_CL, false, false, C4_CHAIN_THREADS>, sizeof(BwdC4Smem<128, C4_CL>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_fwd_c4_kernel<128, C4_CL, false, true, true, C4_CHAIN_THREADS>, sizeof(FwdC4Smem<128, C4_CL>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_bwd_uni_kernel<64, 8, true, false>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_bwd_uni_kernel<64, 8, true, true>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_sample_kernel<64, 8>, sizeof(SampleSmem<64>))) != cudaSuccess) return e;
@@ -675,10 +676,12 @@ int launch_psi_fwd(amps_ctx* ctx, int DP, int B, const FwdArgs& a, cudaStream_t 
         psi_sx2_panel_kernel<<<8, SX_THREADS, 0, st>>>(a.matS, a.spanel);
         LAUNCH_CHECK(ctx, "psi_sx2_panel_kernel");
       }
-      // 256 threads: 8 lanes per row, 16 columns of N and R per thread (one shuffle level less and half the warps
-      // at every exchange than the 512-thread build; 113 registers, 103 KB: two clusters per SM quadruple)
-      CUDA_TRY(ctx, launch_cluster(psi_fwd_c4_kernel<128, C4_CL, false, true, true, 256>, B, C4_CL, 256,
-                                   sizeof(FwdC4Smem<128, C4_CL>), st,
+      // chain-only kernels run 128 threads per CTA: FOUR lanes per row, 32 columns of N and R per thread (178 / 200
+      // registers).  The step is a latency chain -- row-sum shuffles, the exchange between the CTAs, the waits of
+      // every warp on it -- not a throughput problem: 512 threads (16 lanes, 4 shuffle levels, 16 warps per CTA)
+      // 117.7 / 135.5 ms forward / backward chain at C3, 256 threads 95 / 121.6, 128 threads 87.3 / 111.5.
+      CUDA_TRY(ctx, launch_cluster(psi_fwd_c4_kernel<128, C4_CL, false, true, true, C4_CHAIN_THREADS>, B, C4_CL,
+                                   C4_CHAIN_THREADS, sizeof(FwdC4Smem<128, C4_CL>), st,
                                    a.matN, a.matR, a.matS, a.qtab, a.psi0p, a.x, a.T, a.A, a.loss, a.lossd, a.traj,
                                    a.scales, nchunks, (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg));
       LAUNCH_CHECK(ctx, "psi_fwd_c4_kernel<chain>");
@@ -777,8 +780,8 @@ int launch_psi_bwd(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t 
   };
   if (fam == Fam::C4 && ctx->tc_tiles) {
     if (phase < 2) {
-      CUDA_TRY(ctx, launch_cluster(psi_bwd_c4_kernel<128, C4_CL, false, false, 256>, B, C4_CL, 256,
-                                   sizeof(BwdC4Smem<128, C4_CL>), st,
+      CUDA_TRY(ctx, launch_cluster(psi_bwd_c4_kernel<128, C4_CL, false, false, C4_CHAIN_THREADS>, B, C4_CL,
+                                   C4_CHAIN_THREADS, sizeof(BwdC4Smem<128, C4_CL>), st,
                                    a.matN, a.matRH, a.matS, a.qtab, a.ttab, a.x, a.T, a.A, a.w, a.traj, a.scales, nchunks,
                                    a.G, a.gf, a.lam0, a.gAdir, (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg,
                                    const_cast<float2*>(a.sptraj)));

@@ -30,7 +30,7 @@ struct C4 {
   static constexpr int NP = CPT / 2;
   static_assert(CH4 % (NTL / 32) == 0, "whole steps per warp in the chunk-end scalar passes");
   static_assert(RP == 32, "own-row partial sums are one warp wide");
-  static_assert(2 * CL <= NQ, "broadcast lanes");
+  static_assert(CL <= NQ, "broadcast lanes (the full forward needs 2 CL: checked there)");
 };
 
 template <int DP, int CL>
@@ -221,8 +221,8 @@ __global__ void __launch_bounds__(NTHREADS)
       }
       // row reduction over the NQ lanes of a row, the previous step's S x' FMAs in the shuffle shadows
       float2 p0 = make_float2(0.f, 0.f), p1 = p0;
-      static_assert(NQ == 16 || (NQ == 8 && SXO), "the expectation pipeline's pair reduction is written for 16 lanes");
-      constexpr int LV = NQ == 16 ? 4 : 3;
+      static_assert(NQ == 16 || SXO, "the expectation pipeline's pair reduction is written for 16 lanes");
+      constexpr int LV = NQ == 16 ? 4 : NQ == 8 ? 3 : 2;
       constexpr int CPL = (CPT + LV - 1) / LV;
 #pragma unroll
       for (int lv = 0; lv < LV; ++lv) {
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(NTHREADS)
       const float2 xn = cmul(q, xp);
       st_async_f2_if(st_on, st_addr0 + (unsigned)(kk * DP * (int)sizeof(float2)), st_x ? xn : xp,
                      st_bar0 + (unsigned)((sg & 1) * sizeof(unsigned long long)));
-      if (SXO) if (jq == CL) sm.xps[kk][i] = xp;   // own row of x'_k, local (flushed by this CTA after the chunk)
+      if (SXO) if (jq == (NQ > CL ? CL : 0)) sm.xps[kk][i] = xp;   // own row of x'_k, local (flushed by this CTA after the chunk)
       if (EXPC) sm.es[kk - 1][t] = fmaf(xp_prev.x, p0.x + p1.x, xp_prev.y * (p0.y + p1.y));
       if (STAGE == 2) {
         red += __shfl_xor_sync(0xffffffffu, red, 8);
@@ -622,13 +622,15 @@ __global__ void __launch_bounds__(NTHREADS)
       oy = __shfl_xor_sync(0xffffffffu, lp.y, 2);
       lp.x += ox;
       lp.y += oy;
-      lp.x += __shfl_xor_sync(0xffffffffu, lp.x, 4);
-      lp.y += __shfl_xor_sync(0xffffffffu, lp.y, 4);
+      if (NQ >= 8) {
+        lp.x += __shfl_xor_sync(0xffffffffu, lp.x, 4);
+        lp.y += __shfl_xor_sync(0xffffffffu, lp.y, 4);
+      }
       if (NQ == 16) {
         lp.x += __shfl_xor_sync(0xffffffffu, lp.x, 8);
         lp.y += __shfl_xor_sync(0xffffffffu, lp.y, 8);
       }
-      static_assert(NQ == 16 || NQ == 8, "row reduction levels");
+      static_assert(NQ == 16 || NQ == 8 || NQ == 4, "row reduction levels");
       lam.x = fmaf(be, xk.x, lp.x);
       lam.y = fmaf(be, xk.y, lp.y);
       // ---- adjoint of x' for step kk-1 --------------------------------------------------
