@@ -82,7 +82,7 @@ class Cfg:
             return {"sample": f"psi_sample_kernel<{_dp(D)}>"}
         clustered = D <= 32 and 2 * B <= n_sms and os.environ.get("AMPS_NO_CLUSTER") != "1"
         kn = (f"cl_kernel<{_dp(D)}>" if clustered else f"kernel<{_dp(D)}>") if D <= 32 else \
-            "uni_kernel<64,8>" if D <= 64 else "c4_kernel<128,4>"
+            "uni_kernel<64,4>" if D <= 64 else "c4_kernel<128,4,...,128 threads>"
         names = {"fwd": f"psi_fwd_{kn}", "bwd": f"psi_bwd_{kn}"}
         if D > 32 and os.environ.get("AMPS_NO_TC_TILES") != "1":
             # chain-only adjoint sweep + the gradient tiles as tcgen05 GEMMs over the time axis (both inside "bwd")
