@@ -605,7 +605,7 @@ int amps_c4_cluster_capacity(bool bwd) {
     }
     return n;
   };
-  return bwd ? query(psi_bwd_c4_kernel<128, C4_CL, false, false, C4_CHAIN_THREADS>, sizeof(BwdC4Smem<128, C4_CL>))
+  return bwd ? query(psi_bwd_c4_kernel<128, C4_CL, false, false, C4_CHAIN_THREADS>, sizeof(BwdC4Smem<128, C4_CL, true>))
              : query(psi_fwd_c4_kernel<128, C4_CL, false, true, true, C4_CHAIN_THREADS>, sizeof(FwdC4Smem<128, C4_CL>));
 }
 cudaError_t amps_set_all_func_attrs() {
@@ -630,7 +630,7 @@ cudaError_t amps_set_all_func_attrs() {
   if ((e = set_smem(psi_tiles_tc_kernel<128, 2>, sizeof(TilesSmem<128, 2>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_tiles_tc_kernel<128, 3>, sizeof(TilesSmem<128, 3>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_sample_c4_kernel<128, C4_CL>, sizeof(SampleC4Smem<128, C4_CL>))) != cudaSuccess) return e;
-  if ((e = set_smem(psi_bwd_c4_kernel<128, C4_CL, false, false, C4_CHAIN_THREADS>, sizeof(BwdC4Smem<128, C4_CL>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_bwd_c4_kernel<128, C4_CL, false, false, C4_CHAIN_THREADS>, sizeof(BwdC4Smem<128, C4_CL, true>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_fwd_c4_kernel<128, C4_CL, false, true, true, C4_CHAIN_THREADS>, sizeof(FwdC4Smem<128, C4_CL>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_bwd_uni_kernel<64, 8, true, false>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_bwd_uni_kernel<64, 8, true, true>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
@@ -784,7 +784,7 @@ int launch_psi_bwd(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t 
   if (fam == Fam::C4 && ctx->tc_tiles) {
     if (phase < 2) {
       CUDA_TRY(ctx, launch_cluster(psi_bwd_c4_kernel<128, C4_CL, false, false, C4_CHAIN_THREADS>, B, C4_CL,
-                                   C4_CHAIN_THREADS, sizeof(BwdC4Smem<128, C4_CL>), st,
+                                   C4_CHAIN_THREADS, sizeof(BwdC4Smem<128, C4_CL, true>), st,
                                    a.matN, a.matRH, a.matS, a.qtab, a.ttab, a.x, a.T, a.A, a.w, a.traj, a.scales, nchunks,
                                    a.G, a.gf, a.lam0, a.gAdir, (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg,
                                    const_cast<float2*>(a.sptraj)));

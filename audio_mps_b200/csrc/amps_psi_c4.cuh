@@ -358,18 +358,21 @@ __global__ void __launch_bounds__(NTHREADS)
   cluster_sync_all();  // no CTA leaves while a peer could still address its shared memory
 }
 
-template <int DP, int CL>
+// CHAIN (the chain-only sweep, TILES = false): no x'_k reconstruction and the inputs double- instead of triple-
+// buffered -- 93 KB instead of 163 KB, so that two clusters share every SM quadruple (as in the forward).
+template <int DP, int CL, bool CHAIN = false>
 struct alignas(16) BwdC4Smem {
   static constexpr int RP = C4<DP, CL>::RP;
-  float2 xs[3][CH4 + 1][DP];   // trajectory chunk, triple buffered (chunk c, c-1 in use, c-2 landing)
-  float2 qs[3][CH4][DP];
-  float2 spl[3][CH4][RP];      // (S x'_k)_i stored by the forward, own rows
-  float2 evl[3][CH4];          // (E_k, |x_k|^2) stored by the forward
-  float2 xps[2][CH4][DP];      // reconstructed x'_k, full vector
+  static constexpr int NB = CHAIN ? 2 : 3;
+  float2 xs[NB][CH4 + 1][DP];  // trajectory chunk, NB-buffered (3: chunk c, c-1 in use, c-2 landing; 2: c in use, c-1 landing)
+  float2 qs[NB][CH4][DP];
+  float2 spl[NB][CH4][RP];     // (S x'_k)_i stored by the forward, own rows
+  float2 evl[NB][CH4];         // (E_k, |x_k|^2) stored by the forward
+  float2 xps[CHAIN ? 1 : 2][CHAIN ? 1 : CH4][DP];   // reconstructed x'_k, full vector (tile fillers only)
   float2 mus[CH4][DP];         // adjoint of x'_k, full vector (own rows local, the rest from peers)
-  float wav[3][CH4 + 4];
-  float tt[3][CH4 + 4];
-  float scs[3][4];
+  float wav[NB][CH4 + 4];
+  float tt[NB][CH4 + 4];
+  float scs[NB][4];
   float sv[2][CH4], incv[2][CH4], dtk[2][CH4], alphas[2][CH4], betas[2][CH4];
   double lred[16];
   unsigned long long mbar[2];  // "mu broadcast number p has fully arrived", by parity of p
@@ -399,7 +402,9 @@ __global__ void __launch_bounds__(NTHREADS)
   using Cf = C4<DP, CL, NTHREADS>;
   constexpr int NQ = Cf::NQ, CPT = Cf::CPT, NP = Cf::NP, RP = Cf::RP, NTL = Cf::NTL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  BwdC4Smem<DP, CL>& sm = *reinterpret_cast<BwdC4Smem<DP, CL>*>(smem_raw);
+  using Sm = BwdC4Smem<DP, CL, !TILES>;
+  constexpr int NB = Sm::NB;
+  Sm& sm = *reinterpret_cast<Sm*>(smem_raw);
 
   const int t = threadIdx.x, il = t / NQ, jq = t % NQ, lane = t & 31, warp = t >> 5;
   const unsigned rank = cluster_ctarank();
@@ -450,7 +455,7 @@ __global__ void __launch_bounds__(NTHREADS)
   auto chunk_len = [&](int c) { return min(CH4, nsteps - c * CH4); };
 
   auto issue_loads = [&](int c) {
-    const int lb = c % 3;
+    const int lb = c % NB;
     const int k0 = c * CH4;
     const int len = chunk_len(c);
     const float2* xsrc = trb + (size_t)k0 * DP;
@@ -475,7 +480,7 @@ __global__ void __launch_bounds__(NTHREADS)
   // s, inc, dt, alpha_k, beta_k, the direct dL/dA term (from the forward's (E_k, |x_k|^2));
   // x'_k = conj(q_k) x_{k+1} / c_k (full vector, every CTA)
   auto prep_elementwise = [&](int c) {
-    const int lb = c % 3, ds = c & 1, len = chunk_len(c);
+    const int lb = c % NB, ds = c & 1, len = chunk_len(c);
     if (t < len) {
       const float inc = sm.wav[lb][t + 1] - sm.wav[lb][t];
       const float s = inc / A;
@@ -524,11 +529,13 @@ __global__ void __launch_bounds__(NTHREADS)
     const int cl = nchunks - 1;
     issue_loads(cl);
     cp_async_commit();
-    if (cl >= 1) issue_loads(cl - 1);
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-    prep_elementwise(cl);
+    if (NB == 3) {
+      if (cl >= 1) issue_loads(cl - 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncthreads();
+      prep_elementwise(cl);
+    }
     cluster_sync_all();   // every CTA of the cluster has started: remote shared memory is addressable
   }
 
@@ -540,13 +547,22 @@ __global__ void __launch_bounds__(NTHREADS)
   int pg = 0;   // mu broadcasts so far: barrier index pg & 1, phase (pg >> 1) & 1
 
   for (int c = nchunks - 1; c >= 0; --c) {
-    const int lb = c % 3, ds = c & 1;
+    const int lb = c % NB, ds = c & 1;
     const int len = chunk_len(c);
-    if (c >= 2) issue_loads(c - 2);
-    cp_async_commit();
-    cp_async_wait<1>();   // chunk c-1 has landed
-    __syncthreads();      // (T1) alphas/betas of chunk c visible
-    if (c >= 1) prep_elementwise(c - 1);
+    if (NB == 3) {
+      if (c >= 2) issue_loads(c - 2);
+      cp_async_commit();
+      cp_async_wait<1>();   // chunk c-1 has landed
+      __syncthreads();      // (T1) alphas/betas of chunk c visible
+      if (c >= 1) prep_elementwise(c - 1);
+    } else {
+      cp_async_wait<0>();   // chunk c has landed (issued one chunk = ~15 k cycles ago)
+      __syncthreads();      // ... for every thread, and everybody is done with chunk c+1's buffer
+      prep_elementwise(c);
+      if (c >= 1) issue_loads(c - 1);   // into the buffer chunk c+1 has just left
+      cp_async_commit();
+      __syncthreads();      // (T1) alphas/betas of chunk c visible
+    }
     const float sc = sm.scs[lb][0];
 
     float2 mu;
