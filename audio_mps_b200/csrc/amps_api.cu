@@ -618,12 +618,12 @@ cudaError_t amps_set_all_func_attrs() {
   if ((e = set_smem(psi_fwd_uni_kernel<64, 4>, sizeof(FwdSmemUni<64, 4>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_fwd_uni_kernel<64, 8, true>, sizeof(FwdSmemUni<64, 8>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_bwd_uni_kernel<64, 8>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
-  if ((e = set_smem(psi_bwd_uni_kernel<64, 8, false, false>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_bwd_uni_kernel<64, 8, false, false>, sizeof(BwdSmemUni<64, true>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_tiles_tc_kernel<64, 0>, sizeof(TilesSmem<64, 0>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_tiles_tc_kernel<64, 1>, sizeof(TilesSmem<64, 1>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_fwd_uni_kernel<64, 8, false, true>, sizeof(FwdSmemUni<64, 8, true>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_fwd_uni_kernel<64, 4, false, true>, sizeof(FwdSmemUni<64, 4, true>))) != cudaSuccess) return e;
-  if ((e = set_smem(psi_bwd_uni_kernel<64, 4, false, false>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_bwd_uni_kernel<64, 4, false, false>, sizeof(BwdSmemUni<64, true>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_sx_tc_kernel<64>, sizeof(SxSmem<64>) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_sx2_tc_kernel, sizeof(Sx2Smem) + 1024)) != cudaSuccess) return e;
   if ((e = set_smem(psi_tiles_tc_kernel<128, 1>, sizeof(TilesSmem<128, 1>) + 1024)) != cudaSuccess) return e;
@@ -830,7 +830,7 @@ int launch_psi_bwd(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStream_t 
       // GEMMs over the time axis on the tensor cores
       if (phase != 2) {
         // (four lanes per row, 256 threads, 118 registers -- as the chain-only forward: C4's chain 46.5 -> 40.5 ms)
-        psi_bwd_uni_kernel<DPc, 4, false, false><<<B, DPc * 4, sizeof(BwdSmemUni<DPc>), st>>>(
+        psi_bwd_uni_kernel<DPc, 4, false, false><<<B, DPc * 4, sizeof(BwdSmemUni<DPc, true>), st>>>(
             a.matN, a.matRH, a.matS, a.qtab, a.ttab, a.x, a.T, a.A, a.w, a.traj, a.scales, nchunks, a.G, a.gf,
             a.lam0, a.gAdir, (const float2*)nullptr, 0, 0, a.sptraj, a.ev, a.seg, const_cast<float2*>(a.sptraj));
         LAUNCH_CHECK(ctx, "psi_bwd_uni_kernel<chain>");
@@ -943,7 +943,8 @@ int launch_psi_bwd_waves(amps_ctx* ctx, int DP, int B, const BwdArgs& a, cudaStr
     r.ev += (size_t)b0 * f.T;
     return r;
   };
-  return launch_waves(ctx, DP, B, a, st, tensor_path && (ctx->waves_mask & 2), DP == 128 ? ctx->c4_cap_bwd : ctx->num_sms, shift,
+  // (D = 64: the chain-only backward fits two CTAs per SM, like the forward)
+  return launch_waves(ctx, DP, B, a, st, tensor_path && (ctx->waves_mask & 2), DP == 128 ? ctx->c4_cap_bwd : 2 * ctx->num_sms, shift,
                       [&](int Bp, const BwdArgs& ap, cudaStream_t s, int ph) { return launch_psi_bwd(ctx, DP, Bp, ap, s, ph); });
 }
 

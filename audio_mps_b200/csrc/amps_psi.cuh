@@ -580,17 +580,22 @@ struct alignas(16) FwdSmemUni {
   double lred[32];
 };
 
-template <int DP>
+// CHAIN (the chain-only sweep of the tensor-core path, TILES = false and not VIRT): inputs double- instead of triple-
+// buffered, no x' reconstruction, and a two-row mu ring (mu_k goes to global memory as it is formed) -- 103 KB
+// instead of 195 KB, so that two CTAs share an SM and C4's 256 clips run as ONE wave.
+template <int DP, bool CHAIN = false>
 struct alignas(16) BwdSmemUni {
-  float2 xs[3][CH + 1][DP];  // trajectory chunk, triple buffered (chunk c, c-1 in use, c-2 landing)
-  float2 qs[3][CH][DP];
-  float2 spl[3][CH][DP];     // S x'_k stored by the forward
-  float2 evl[3][CH];         // (E_k, |x_k|^2) stored by the forward
-  float2 xps[2][CH][DP];     // reconstructed x'_k      (chunk c and, being prepared, c-1)
-  float2 mus[CH][DP];        // adjoint of x'_k
-  float wav[3][CH + 4];
-  float tt[3][CH + 4];
-  float scs[3][4];
+  static constexpr int NB = CHAIN ? 2 : 3;
+  static constexpr int NMU = CHAIN ? 2 : CH;
+  float2 xs[NB][CH + 1][DP];  // trajectory chunk, NB-buffered (3: chunk c, c-1 in use, c-2 landing; 2: c in use, c-1 landing)
+  float2 qs[NB][CH][DP];
+  float2 spl[NB][CH][DP];     // S x'_k stored by the forward
+  float2 evl[NB][CH];         // (E_k, |x_k|^2) stored by the forward
+  float2 xps[CHAIN ? 1 : 2][CHAIN ? 1 : CH][DP];   // reconstructed x'_k (tile fillers only)
+  float2 mus[NMU][DP];        // adjoint of x'_k
+  float wav[NB][CH + 4];
+  float tt[NB][CH + 4];
+  float scs[NB][4];
   float sv[2][CH], incv[2][CH], dtk[2][CH], alphas[2][CH], betas[2][CH];
   double lred[32];
 };
@@ -919,7 +924,10 @@ __global__ void __launch_bounds__(DP* NQ)
   constexpr int CPT = M::CPT;
   constexpr int NP = M::NP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  BwdSmemUni<DP>& sm = *reinterpret_cast<BwdSmemUni<DP>*>(smem_raw);
+  constexpr bool CHAINM = !TILES && !VIRT;   // chain-only sweep: compact shared memory (BwdSmemUni)
+  using Sm = BwdSmemUni<DP, CHAINM>;
+  constexpr int NB = Sm::NB;
+  Sm& sm = *reinterpret_cast<Sm*>(smem_raw);
 
   const int t = threadIdx.x, i = t / NQ, jq = t % NQ, lane = t & 31, warp = t >> 5;
   const int b = blockIdx.x;
@@ -967,7 +975,7 @@ __global__ void __launch_bounds__(DP* NQ)
   auto chunk_len = [&](int c) { return min(CH, nsteps - c * CH); };
 
   auto issue_loads = [&](int c) {
-    const int lb = c % 3;
+    const int lb = c % NB;
     const int k0 = c * CH;
     const int len = chunk_len(c);
     const float2* xsrc = trb + (size_t)k0 * DP;
@@ -993,7 +1001,7 @@ __global__ void __launch_bounds__(DP* NQ)
   // chunk c: s, inc, dt, alpha_k, beta_k, the direct dL/dA term (from the forward's (E_k, |x_k|^2));
   // x'_k = conj(q_k) x_{k+1} / c_k
   auto prep_elementwise = [&](int c) {
-    const int lb = c % 3, ds = c & 1, len = chunk_len(c);
+    const int lb = c % NB, ds = c & 1, len = chunk_len(c);
     if (t < len) {
       const float inc = sm.wav[lb][t + 1] - sm.wav[lb][t];
       const float s = inc / A;
@@ -1038,25 +1046,38 @@ __global__ void __launch_bounds__(DP* NQ)
     const int cl = nchunks - 1;
     issue_loads(cl);
     cp_async_commit();
-    if (cl >= 1) issue_loads(cl - 1);
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-    prep_elementwise(cl);
+    if (NB == 3) {
+      if (cl >= 1) issue_loads(cl - 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncthreads();
+      prep_elementwise(cl);
+    }
   }
 
   float2* const mu_st = &sm.mus[0][i];
   const bool mu_on = jq == 0;
 
   for (int c = nchunks - 1; c >= 0; --c) {
-    const int lb = c % 3, ds = c & 1;
+    const int lb = c % NB, ds = c & 1;
     const int len = chunk_len(c);
-    if (c >= 2) issue_loads(c - 2);
-    cp_async_commit();
-    cp_async_wait<1>();   // chunk c-1 has landed
-    __syncthreads();      // (T1) prep of chunk c (previous iteration / prologue) visible
-    if (c >= 1) prep_elementwise(c - 1);
+    if (NB == 3) {
+      if (c >= 2) issue_loads(c - 2);
+      cp_async_commit();
+      cp_async_wait<1>();   // chunk c-1 has landed
+      __syncthreads();      // (T1) prep of chunk c (previous iteration / prologue) visible
+      if (c >= 1) prep_elementwise(c - 1);
+    } else {
+      cp_async_wait<0>();   // chunk c has landed (issued one chunk ago)
+      __syncthreads();      // ... for every thread, and everybody is done with chunk c+1's buffer
+      prep_elementwise(c);
+      if (c >= 1) issue_loads(c - 1);   // into the buffer chunk c+1 has just left
+      cp_async_commit();
+      __syncthreads();      // (T1) prep of chunk c visible
+    }
     const float sc = sm.scs[lb][0];
+    // chain-only sweep: mu_k is kept in a two-row ring and written to global memory as it is formed
+    float2* const mu_g = (CHAINM && mu_out) ? mu_out + ((size_t)b * rows + (size_t)c * CH) * DP + i : nullptr;
 
     // adjoint of x' for the chunk's last step (carries the rescale c_k)
     float2 mu;
@@ -1069,7 +1090,10 @@ __global__ void __launch_bounds__(DP* NQ)
       const float2 sp = sm.spl[lb][kk][i];
       mu.x = fmaf(al, sp.x, mu.x * sc);
       mu.y = fmaf(al, sp.y, mu.y * sc);
-      if (mu_on) mu_st[kk * DP] = mu;
+      if (mu_on) {
+        mu_st[(CHAINM ? (kk & 1) : kk) * DP] = mu;
+        if (CHAINM && mu_g) mu_g[(size_t)kk * DP] = mu;
+      }
     }
     __syncthreads();      // (T2)
 
@@ -1078,7 +1102,7 @@ __global__ void __launch_bounds__(DP* NQ)
       float2 mv[CPT];
 #pragma unroll
       for (int m = 0; m < NP; ++m) {
-        const float4 v = *reinterpret_cast<const float4*>(&sm.mus[kk][2 * NQ * m + 2 * jq]);
+        const float4 v = *reinterpret_cast<const float4*>(&sm.mus[CHAINM ? (kk & 1) : kk][2 * NQ * m + 2 * jq]);
         mv[2 * m] = make_float2(v.x, v.y);
         mv[2 * m + 1] = make_float2(v.z, v.w);
       }
@@ -1139,12 +1163,13 @@ __global__ void __launch_bounds__(DP* NQ)
         mu.x = fmaf(al1, sp1.x, mu.x);
         mu.y = fmaf(al1, sp1.y, mu.y);
       }
-      sts_if(mu_on && kk > 0, mu_st + km * DP, mu);
+      sts_if(mu_on && kk > 0, mu_st + (CHAINM ? (km & 1) : km) * DP, mu);
+      if (CHAINM) if (mu_on && kk > 0 && mu_g) mu_g[(size_t)km * DP] = mu;
       __syncthreads();
     };
 
     for (int kk = len - 1; kk >= 0; --kk) step(kk);
-    if (!TILES) if (mu_out) {   // flush the chunk's mu ring (complete after the last step's barrier)
+    if (!TILES && !CHAINM) if (mu_out) {   // flush the chunk's mu ring (complete after the last step's barrier)
       const float4* src = reinterpret_cast<const float4*>(&sm.mus[0][0]);
       float4* dst = reinterpret_cast<float4*>(mu_out + ((size_t)b * rows + (size_t)c * CH) * DP);
       for (int idx = t; idx < len * DP / 2; idx += NT) dst[idx] = src[idx];
