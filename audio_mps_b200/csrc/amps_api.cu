@@ -616,7 +616,7 @@ cudaError_t amps_set_all_func_attrs() {
   if ((e = set_attrs_ws<32, 4>()) != cudaSuccess) return e;
   if ((e = set_smem(psi_fwd_uni_kernel<64, 8>, sizeof(FwdSmemUni<64, 8>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_fwd_uni_kernel<64, 4>, sizeof(FwdSmemUni<64, 4>))) != cudaSuccess) return e;
-  if ((e = set_smem(psi_fwd_uni_kernel<64, 8, true>, sizeof(FwdSmemUni<64, 8>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_fwd_uni_kernel<64, 4, true>, sizeof(FwdSmemUni<64, 4>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_bwd_uni_kernel<64, 8>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_bwd_uni_kernel<64, 8, false, false>, sizeof(BwdSmemUni<64, true>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_tiles_tc_kernel<64, 0>, sizeof(TilesSmem<64, 0>) + 1024)) != cudaSuccess) return e;
@@ -632,8 +632,8 @@ cudaError_t amps_set_all_func_attrs() {
   if ((e = set_smem(psi_sample_c4_kernel<128, C4_CL>, sizeof(SampleC4Smem<128, C4_CL>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_bwd_c4_kernel<128, C4_CL, false, false, C4_CHAIN_THREADS>, sizeof(BwdC4Smem<128, C4_CL, true>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_fwd_c4_kernel<128, C4_CL, false, true, true, C4_CHAIN_THREADS>, sizeof(FwdC4Smem<128, C4_CL>))) != cudaSuccess) return e;
-  if ((e = set_smem(psi_bwd_uni_kernel<64, 8, true, false>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
-  if ((e = set_smem(psi_bwd_uni_kernel<64, 8, true, true>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_bwd_uni_kernel<64, 4, true, false>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_bwd_uni_kernel<64, 4, true, true>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_sample_kernel<64, 8>, sizeof(SampleSmem<64>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_fwd_c4_kernel<128, C4_CL, false>, sizeof(FwdC4Smem<128, C4_CL>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_bwd_c4_kernel<128, C4_CL, false>, sizeof(BwdC4Smem<128, C4_CL>))) != cudaSuccess) return e;
@@ -1334,10 +1334,10 @@ int amps_psi_loss_fwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
   }
   LAUNCH_CHECK(ctx, "psi_scan_boundary_kernel");
   {
-    auto kern = psi_fwd_uni_kernel<64, 8, true>;
-    const size_t smem = sizeof(FwdSmemUni<64, 8>);
+    auto kern = psi_fwd_uni_kernel<64, 4, true>;      // four lanes per row, as the batch kernels (launch_psi_fwd)
+    const size_t smem = sizeof(FwdSmemUni<64, 4>);
     PROF_BEGIN(ctx, 0, st);
-    kern<<<nv, 64 * 8, smem, st>>>((const float2*)(ws + L.base.matN), (const float2*)(ws + L.base.matR),
+    kern<<<nv, 64 * 4, smem, st>>>((const float2*)(ws + L.base.matN), (const float2*)(ws + L.base.matR),
                                    (const float2*)(ws + L.base.matS), (const float2*)(ws + L.base.qtab),
                                    (const float2*)(ws + L.base.psi0p), x_dev, T, aval(p), (float*)nullptr,
                                    (double*)(ws + L.lossv), save ? (float2*)(ws + L.traj) : (float2*)nullptr,
@@ -1378,12 +1378,12 @@ int amps_psi_loss_bwd_scan(amps_ctx* ctx, const amps_params* p, const float* x_d
   const double cprime = -p->delta_t * (double)p->sigma * (double)p->sigma / 2.0;
   psi_scan_expand_w_kernel<<<(nv + 127) / 128, 128, 0, st>>>(w_dev, B, L.nvc, (float*)(ws + L.wv));
   LAUNCH_CHECK(ctx, "psi_scan_expand_w_kernel");
-  auto kern_chain = psi_bwd_uni_kernel<64, 8, true, false>;   // pass 1: adjoint chain only
-  auto kern_full = psi_bwd_uni_kernel<64, 8, true, true>;     // pass 2: chain + gradient tiles
+  auto kern_chain = psi_bwd_uni_kernel<64, 4, true, false>;   // pass 1: adjoint chain only
+  auto kern_full = psi_bwd_uni_kernel<64, 4, true, true>;     // pass 2: chain + gradient tiles
   const size_t smem = sizeof(BwdSmemUni<64>);
   auto adjoint_pass = [&](const float2* lam_end) {
     auto kern = lam_end ? kern_full : kern_chain;
-    kern<<<nv, 64 * 8, smem, st>>>((const float2*)(ws + L.base.matN), (const float2*)(ws + L.base.matRH),
+    kern<<<nv, 64 * 4, smem, st>>>((const float2*)(ws + L.base.matN), (const float2*)(ws + L.base.matRH),
                                    (const float2*)(ws + L.base.matS), (const float2*)(ws + L.base.qtab),
                                    (const float*)(ws + L.base.ttab), x_dev, T, aval(p), w_dev,
                                    (const float2*)(ws + L.traj), (const float*)(ws + L.scales), 0,
