@@ -634,7 +634,7 @@ cudaError_t amps_set_all_func_attrs() {
   if ((e = set_smem(psi_fwd_c4_kernel<128, C4_CL, false, true, true, C4_CHAIN_THREADS>, sizeof(FwdC4Smem<128, C4_CL>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_bwd_uni_kernel<64, 4, true, false>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_bwd_uni_kernel<64, 4, true, true>, sizeof(BwdSmemUni<64>))) != cudaSuccess) return e;
-  if ((e = set_smem(psi_sample_kernel<64, 8>, sizeof(SampleSmem<64>))) != cudaSuccess) return e;
+  if ((e = set_smem(psi_sample_kernel<64, 4>, sizeof(SampleSmem<64>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_fwd_c4_kernel<128, C4_CL, false>, sizeof(FwdC4Smem<128, C4_CL>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_bwd_c4_kernel<128, C4_CL, false>, sizeof(BwdC4Smem<128, C4_CL>))) != cudaSuccess) return e;
   if ((e = set_smem(psi_compose_tc_kernel<true>, sizeof(ScanTcSmem) + 1024)) != cudaSuccess) return e;
@@ -1459,7 +1459,8 @@ int amps_psi_sample(amps_ctx* ctx, const amps_params* p, const float* noise_dev,
     return AMPS_OK;
   }
   return dispatch_dp(DP, [&](auto dp, auto nq) -> int {
-    constexpr int DPc = decltype(dp)::value, NQc = decltype(nq)::value;
+    constexpr int DPc = decltype(dp)::value;
+    constexpr int NQc = DPc == 64 ? 4 : decltype(nq)::value;   // D = 64: four lanes per row, as the training kernels (4.4)
     auto kern = psi_sample_kernel<DPc, NQc>;
     const size_t smem = sizeof(SampleSmem<DPc>);
     PROF_BEGIN(ctx, 2, st);
